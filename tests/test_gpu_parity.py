@@ -1,0 +1,122 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle, the reference fixtures and -- on the
+same GPU -- the op-for-op eager restatement of the reference.  All tests need a B200 (``-m gpu``)."""
+import numpy as np
+import pytest
+import torch
+
+import uda_clr_b200 as clr
+from oracle import clr_oracle as O
+from oracle import clr_torch_port as TP
+from uda_clr_b200 import synth
+from _util import TOL_GRAD, TOL_PROTO, golden, relerr
+
+pytestmark = pytest.mark.gpu
+G = golden()
+DEV = "cuda"
+
+
+def cu(a, grad=False):
+    t = torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32).to(DEV)
+    return t.requires_grad_(grad)
+
+
+def stack(protos):
+    return torch.cat([p.reshape(1, -1) for p in protos], 0).detach().cpu().numpy()
+
+
+@pytest.mark.parametrize("case", ["hard_ragged", "hard_c305", "soft", "hard_big"])
+def test_gen_prototype_vs_reference_fixture(case):
+    c = G[case]
+    soft = "grad_pred" in c
+    pred, feat = cu(c["in_pred"], soft), cu(c["in_feat"], True)
+    out = clr.gen_prototype(pred, feat)
+    assert len(out) == 4 and all(o.shape == (1, feat.shape[1], 1, 1) and o.is_cuda for o in out)
+    assert relerr(stack(out), c["out_protos"]) < TOL_PROTO
+    seeds = cu(c["seed_g"])
+    sum((o.reshape(-1) * s).sum() for o, s in zip(out, seeds)).backward()
+    assert relerr(feat.grad.cpu().numpy(), c["grad_feat"]) < TOL_GRAD
+    if soft:
+        assert relerr(pred.grad.cpu().numpy(), c["grad_pred"]) < TOL_GRAD
+
+
+@pytest.mark.parametrize("shape", [(8, 256, 128, 128, 2), (2, 305, 128, 128, 2), (3, 37, 24, 20, 2),
+                                   (2, 16, 9, 7, 2), (2, 64, 32, 32, 4), (1, 40, 16, 16, 8), (2, 24, 16, 16, 3),
+                                   (1, 12, 8, 8, 1)])
+def test_gen_prototype_hard_vs_oracle(shape):
+    B, C, H, W, K = shape
+    g = torch.Generator().manual_seed(B * 1000 + C)
+    y = synth.nested_ellipse_labels(B, K, H, W, g)
+    x = synth.class_shifted_features(y, C, g)
+    feat = x.to(DEV).requires_grad_(True)
+    out = clr.gen_prototype(y.to(DEV), feat)
+    S, N = O.pool_sums(x.numpy(), O.weights_complement(y.numpy()))
+    assert relerr(stack(out), O.prototypes_from_sums(S, N)) < TOL_PROTO
+    # integer work: the 2K pixel counts are bit-exact
+    sums = clr.ops.pool_sums(feat.detach(), y.to(DEV), 0, K).cpu().numpy()
+    assert np.array_equal(sums[:, C].astype(np.float64), N)
+    seeds = torch.randn(2 * K, C, generator=g)
+    sum((o.reshape(-1) * s).sum() for o, s in zip(out, seeds.to(DEV))).backward()
+    gx, _ = O.gen_prototype_backward(y.numpy(), x.numpy(), seeds.numpy())
+    assert relerr(feat.grad.cpu().numpy(), gx) < TOL_GRAD
+
+
+def test_gen_prototype_soft_vs_eager_reference_on_gpu():
+    """Same GPU, same inputs: our op vs the op-for-op eager restatement of utils/Utils.py:108-131."""
+    b = synth.make_batch(B=4, C=96, H=64, W=64, K=2, image_res=False, seed=77)
+    pred = torch.sigmoid(b.oT_before)
+    p1, f1 = pred.to(DEV).requires_grad_(True), b.xt.to(DEV).requires_grad_(True)
+    p2, f2 = pred.to(DEV).requires_grad_(True), b.xt.to(DEV).requires_grad_(True)
+    ours, ref = clr.gen_prototype(p1, f1), TP.gen_prototype(p2, f2)
+    assert relerr(stack(ours), stack(ref)) < TOL_PROTO
+    seeds = torch.randn(4, 96, generator=torch.Generator().manual_seed(1)).to(DEV)
+    sum((o.reshape(-1) * s).sum() for o, s in zip(ours, seeds)).backward()
+    sum((o.reshape(-1) * s).sum() for o, s in zip(ref, seeds)).backward()
+    assert relerr(f1.grad.cpu().numpy(), f2.grad.cpu().numpy()) < TOL_GRAD
+    assert relerr(p1.grad.cpu().numpy(), p2.grad.cpu().numpy()) < TOL_GRAD
+
+
+def test_src_trg_fixture():
+    c = G["src_trg"]
+    out = clr.gen_prototype_src_trg(cu(c["in_pred_s"]), cu(c["in_feat_s"]), cu(c["in_pred_t"]), cu(c["in_feat_t"]))
+    assert relerr(stack(out), c["out_protos"]) < TOL_PROTO
+
+
+def test_empty_class_gives_nan_like_reference():
+    y = torch.zeros(1, 2, 8, 8)
+    y[:, 1, 2:6, 2:6] = 1.0
+    x = torch.randn(1, 8, 8, 8)
+    out = stack(clr.gen_prototype(y.to(DEV), x.to(DEV)))
+    assert np.isnan(out[0]).all() and not np.isnan(out[1:]).any()
+
+
+def test_noncontiguous_and_misaligned_inputs():
+    """Strided views are made contiguous; a base pointer that is only 4-byte aligned takes the scalar path."""
+    g = torch.Generator().manual_seed(5)
+    y = synth.nested_ellipse_labels(2, 2, 16, 16, g)
+    x = synth.class_shifted_features(y, 10, g)
+    ref = O.gen_prototype(y.numpy(), x.numpy())
+    xp = torch.zeros(2, 10, 16, 20).to(DEV)
+    xp[..., 2:18] = x.to(DEV)
+    assert relerr(stack(clr.gen_prototype(y.to(DEV), xp[..., 2:18])), ref) < TOL_PROTO
+    flat = torch.zeros(x.numel() + 1, device=DEV)
+    flat[1:] = x.to(DEV).reshape(-1)
+    xm = flat[1:].view(2, 10, 16, 16)
+    assert xm.data_ptr() % 16 == 4
+    assert relerr(stack(clr.gen_prototype(y.to(DEV), xm)), ref) < TOL_PROTO
+
+
+def test_linearity_and_shard_sum_property_full_size():
+    """Size-independent properties at the bench size (B=8, C=256, 128x128): pooling is linear in the
+    features, and shard-and-sum of the packed sums equals the whole batch (the all-reduce decomposition)."""
+    b = synth.make_batch(B=8, C=256, H=128, W=128, K=2, image_res=False, seed=1234)
+    y, x = b.ys.to(DEV), b.xs.to(DEV)
+    whole = clr.ops.pool_sums(x, y, 0, 2).double()
+    parts = sum(clr.ops.pool_sums(x[i:i + 2].contiguous(), y[i:i + 2].contiguous(), 0, 2).double() for i in range(0, 8, 2))
+    assert relerr(parts.cpu().numpy(), whole.cpu().numpy()) < 1e-6
+    assert torch.equal(parts[:, 256], whole[:, 256])          # counts: exact
+    assert float(whole[0, 256] + whole[2, 256]) == 8 * 128 * 128  # obj + bck = all pixels
+    a = clr.ops.pool_sums(2.5 * x, y, 0, 2).double()
+    assert relerr(a[:, :256].cpu().numpy(), 2.5 * whole[:, :256].cpu().numpy()) < 1e-6
+    # run-to-run bit stability (fixed-order reduction, no atomics)
+    again = clr.ops.pool_sums(x, y, 0, 2).double()
+    assert torch.equal(again, whole)

@@ -1,0 +1,14 @@
+"""uda_clr_b200 -- B200-native category-level-regularisation (CLR) hot path of fengweie/UDA_CLR.
+
+Public surface = the reference's own function names (``utils/Utils.py``), backed by hand-written
+sm_100a CUDA kernels behind a C ABI (``include/clr_b200.h``, ``libclr_b200.so``):
+
+    from uda_clr_b200 import gen_prototype, gen_prototype_retrify, ...
+    uda_clr_b200.patch_reference()      # rebind the names inside an imported reference tree
+
+Importing the package never touches CUDA; the first op call loads the library and raises if it is
+missing (no CPU fallback).
+"""
+from .ops import (adaptation_factor, gen_prototype, gen_prototype_src_trg, weighted_prototypes)  # noqa: F401
+
+__version__ = "0.1.0"

@@ -1,0 +1,52 @@
+// Library-level entry points of libclr_b200.so: version, status strings, device facts.
+#include "clr_common.cuh"
+
+namespace clr {
+
+const DeviceFacts& device_facts() {
+    static DeviceFacts facts[64];
+    static bool have[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!have[dev]) {
+        DeviceFacts f{148, 0, 48 * 1024};
+        cudaDeviceGetAttribute(&f.sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&f.l2, cudaDevAttrL2CacheSize, dev);
+        cudaDeviceGetAttribute(&f.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        if (f.sms <= 0) f.sms = 148;
+        facts[dev] = f;
+        have[dev] = true;
+    }
+    return facts[dev];
+}
+
+}  // namespace clr
+
+extern "C" {
+
+int clr_version(void) { return CLR_B200_VERSION; }
+
+const char* clr_status_string(int status) {
+    switch (status) {
+        case CLR_OK: return "ok";
+        case CLR_ERR_BAD_ARG: return "bad argument (null pointer, non-positive size or K out of range)";
+        case CLR_ERR_ALIGN: return "pointer not aligned to 4 bytes";
+        case CLR_ERR_WORKSPACE: return "workspace too small";
+        case CLR_ERR_UNSUPPORTED: return "unsupported size or combination";
+        default: break;
+    }
+    if (status <= CLR_ERR_CUDA_BASE) return cudaGetErrorString((cudaError_t)(CLR_ERR_CUDA_BASE - status));
+    return "unknown status";
+}
+
+int clr_device_info(int* sm_count, int* l2_bytes) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { cudaGetLastError(); return CLR_ERR_UNSUPPORTED; }
+    const clr::DeviceFacts& f = clr::device_facts();
+    if (sm_count) *sm_count = f.sms;
+    if (l2_bytes) *l2_bytes = f.l2;
+    return CLR_OK;
+}
+
+}  // extern "C"

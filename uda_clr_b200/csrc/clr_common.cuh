@@ -1,0 +1,115 @@
+// Shared device/host helpers for the CLR kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "clr_b200.h"
+
+namespace clr {
+
+constexpr int kThreads = 256;           // CTA size of every streaming kernel
+constexpr int kWarps = kThreads / 32;
+
+#define CLR_CHECK_ARG(cond) do { if (!(cond)) return CLR_ERR_BAD_ARG; } while (0)
+#define CLR_RETURN_IF_CUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return CLR_ERR_CUDA_BASE - (int)_e; } while (0)
+
+static inline int launch_status() {
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) { cudaGetLastError(); return CLR_ERR_CUDA_BASE - (int)e; }
+    return CLR_OK;
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static inline bool aligned4(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 3u) == 0; }
+
+// Per-device facts, cached per device id (read-mostly; benign race: every writer stores the same values).
+struct DeviceFacts { int sms; int l2; int max_smem_optin; };
+const DeviceFacts& device_facts();
+
+// ---- streaming loads / stores --------------------------------------------------------------------
+// Feature maps are touched exactly once per pass: read through the non-coherent path without
+// allocating in L1; gradients are written with an evict-first hint.
+template <int VEC> struct Pack { float v[VEC]; };
+
+template <int VEC>
+__device__ __forceinline__ Pack<VEC> ld_stream(const float* p);
+template <>
+__device__ __forceinline__ Pack<4> ld_stream<4>(const float* p) {
+    Pack<4> r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]) : "l"(p));
+    return r;
+}
+template <>
+__device__ __forceinline__ Pack<1> ld_stream<1>(const float* p) {
+    Pack<1> r;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r.v[0]) : "l"(p));
+    return r;
+}
+
+// Small, re-read planes (labels / weights): ordinary read-only loads so they stay in L1/L2.
+template <int VEC>
+__device__ __forceinline__ Pack<VEC> ld_keep(const float* p);
+template <>
+__device__ __forceinline__ Pack<4> ld_keep<4>(const float* p) {
+    float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    Pack<4> r; r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w; return r;
+}
+template <>
+__device__ __forceinline__ Pack<1> ld_keep<1>(const float* p) {
+    Pack<1> r; r.v[0] = __ldg(p); return r;
+}
+
+template <int VEC>
+__device__ __forceinline__ void st_stream(float* p, const Pack<VEC>& r);
+template <>
+__device__ __forceinline__ void st_stream<4>(float* p, const Pack<4>& r) {
+    __stcs(reinterpret_cast<float4*>(p), make_float4(r.v[0], r.v[1], r.v[2], r.v[3]));
+}
+template <>
+__device__ __forceinline__ void st_stream<1>(float* p, const Pack<1>& r) { __stcs(p, r.v[0]); }
+
+template <int VEC>
+__device__ __forceinline__ void st_keep(float* p, const Pack<VEC>& r);
+template <>
+__device__ __forceinline__ void st_keep<4>(float* p, const Pack<4>& r) {
+    *reinterpret_cast<float4*>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+}
+template <>
+__device__ __forceinline__ void st_keep<1>(float* p, const Pack<1>& r) { *p = r.v[0]; }
+
+// ---- warp reductions -----------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Transposing butterfly: every lane holds 32 partial values v[0..31]; afterwards lane i holds
+// sum over lanes of v[i] (returned).  31 shuffles instead of 32*5.
+__device__ __forceinline__ float warp_sum_transpose32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int half = 16; half >= 1; half >>= 1) {
+        const bool upper = (lane & half) != 0;
+#pragma unroll
+        for (int j = 0; j < half; ++j) {
+            const float send = upper ? v[j] : v[j + half];
+            const float keep = upper ? v[j + half] : v[j];
+            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+        }
+    }
+    return v[0];
+}
+
+// Static contiguous partition of `total` items over `parts` workers.
+__device__ __forceinline__ void partition(int total, int parts, int idx, int& begin, int& end) {
+    const int per = total / parts, rem = total % parts;
+    begin = idx * per + (idx < rem ? idx : rem);
+    end = begin + per + (idx < rem ? 1 : 0);
+}
+
+}  // namespace clr
