@@ -53,6 +53,9 @@ int clr_version(void);
 const char* clr_status_string(int status);
 /* Number of SMs / L2 bytes of the current device (grid sizing is derived from it; exposed for the bench). */
 int clr_device_info(int* sm_count, int* l2_bytes);
+/* Benchmark knobs (process-wide): "pool_impl" 0 auto / 1 LDG kernel, "pool_stages" TMA ring depth,
+ * "dots_impl", "bwd_impl".  Defaults select the fastest path; results are identical either way. */
+int clr_set_tunable(const char* name, int value);
 
 /* ------------------------------------------------------------------------------------------------
  * Masked / confidence-weighted class-wise pooling  (replaces utils/Utils.py:114-126 -- the four
@@ -62,6 +65,11 @@ int clr_device_info(int* sm_count, int* l2_bytes);
 size_t clr_pool_ws_bytes(int B, int C, int HW, int K);
 int clr_pool_fwd(const float* feat /*[B,C,HW]*/, const float* w, int fmt, int B, int C, int HW, int K,
                  void* ws, size_t ws_bytes, float* sums /*[2K][C+1] out*/, clr_stream_t stream);
+/* Same kernel for R arbitrary explicit weight rows [B,R,HW] (1 <= R <= 16): sums is [R][C+1].
+ * Used for the discriminative term's active-set sums and the per-sample (bmm-style) pooling. */
+size_t clr_pool_rows_ws_bytes(int B, int C, int HW, int R);
+int clr_pool_rows_fwd(const float* feat, const float* rows, int B, int C, int HW, int R,
+                      void* ws, size_t ws_bytes, float* sums /*[R][C+1] out*/, clr_stream_t stream);
 /* Two domains (source, target) in ONE launch: the fused step's forward. sums0/sums1 as above. */
 int clr_pool_fwd2(const float* feat0, const float* w0, int fmt0, int B0,
                   const float* feat1, const float* w1, int fmt1, int B1,
@@ -80,10 +88,20 @@ int clr_pool_bwd(const float* w, int fmt, int B, int C, int HW, int K,
                  const float* g /*[2K][C] dL/dmu*/, const float* sums /*[2K][C+1]*/, float scale,
                  const float* xcoef /*[B,Kx,HW] or NULL*/, const float* xtab /*[Kx][C] or NULL*/, int Kx,
                  float* grad /*[B,C,HW] out*/, clr_stream_t stream);
-int clr_pool_bwd2(const float* w0, int fmt0, int B0, const float* g0, const float* sums0, float scale0,
-                  const float* xcoef0, const float* xtab0, int Kx0, float* grad0,
-                  const float* w1, int fmt1, int B1, const float* g1, const float* sums1, float scale1,
-                  float* grad1, int C, int HW, int K, clr_stream_t stream);
+/* Up to two domains in ONE launch (the fused step's backward).  `scale_dev` (nullable) is a device scalar
+ * multiplied into the result -- the upstream gradient of the step total, so no host sync is needed. */
+typedef struct clr_bwd_dom {
+    const float* w;       /* weight planes of this domain */
+    const float* g;       /* [2K][C] dL/dmu */
+    const float* sums;    /* [2K][C+1] (global) packed sums */
+    const float* xcoef;   /* [B,Kx,HW] or NULL */
+    const float* xtab;    /* [Kx][C] or NULL */
+    float* grad;          /* [B,C,HW] out */
+    const float* scale_dev;
+    float scale;
+    int fmt, B, Kx;
+} clr_bwd_dom;
+int clr_pool_bwd_multi(const clr_bwd_dom* doms, int ndom, int C, int HW, int K, clr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Per-pixel channel contractions: dots[b,q,p] = sum_c V[q][c] * feat[b,c,p]  (+ sumsq[b,p] = sum_c x^2).
@@ -99,6 +117,125 @@ size_t clr_pool_bwd_w_ws_bytes(int C, int K, int fmt);
 int clr_pool_bwd_w(const float* feat, int fmt, int B, int C, int HW, int K,
                    const float* g /*[2K][C]*/, const float* sums /*[2K][C+1]*/, float scale,
                    void* ws, size_t ws_bytes, float* grad_w, clr_stream_t stream);
+
+/* Pixel <-> prototype maps (Trainer_prototype.py:98-116, utils/Utils.py:86-88). */
+int clr_proto_distance(const float* feat, int B, int C, int HW, const float* protos /*[Q][C]*/, int Q,
+                       float* dist /*[B,Q,HW] out: ||proto_q - feat[b,:,p]||_2*/, clr_stream_t stream);
+int clr_proto_cosine(const float* feat, int B, int C, int HW, const float* proto /*[C]*/, float* ws4 /*1 float*/,
+                     float* out /*[B,1,HW]*/, clr_stream_t stream);
+/* (x - min x) / (max x - min x) in place over n floats; ws >= 512 floats. */
+int clr_minmax_normalize(float* x, size_t n, float* ws, clr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Prototype-guided discriminative hinge, forward pass over the source features
+ * (Trainer_prototype_mt.cpython-38.pyc L454-474).  delta_k(p) = d_obj,k - d_bck,k is affine in x, so the
+ * pass is K dot products per pixel with disc_vec[k] = P_obj,k - P_bck,k (from clr_align_finalize):
+ *   coef[b,k,p]  = y_k [delta_k + m > 0] - (1 - y_k) [m - delta_k > 0]       (d(npx*loss)/d delta)
+ *   partials[i]  = per-CTA { sum of hinge terms, sum coef_0, .. }             (row stride 1+K)
+ * The active-set sums A_k[c] = sum coef*x follow from clr_pool_rows_fwd(xs, coef, R=K).
+ * ---------------------------------------------------------------------------------------------- */
+int clr_disc_partials_cap(void);
+int clr_disc_fwd(const float* xs, const float* ys, int B, int C, int HW, int K,
+                 const float* disc_vec /*[K][C]*/, const float* disc_beta /*[K]*/, float margin,
+                 float* coef /*[B,K,HW] out*/, float* delta /*[B,K,HW] out or NULL*/,
+                 float* partials /*[cap][1+K]*/, int partials_cap, int* nparts /*host out*/, clr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * MC-dropout statistics + retrify weights (utils/Utils.py:161-223).
+ * ---------------------------------------------------------------------------------------------- */
+int clr_mc_stats(const float* preds /*[T*B,K,Hi,Wi] logits*/, int T, int B, int K, int Hi, int Wi,
+                 float* std_map /*[B,K,Hi,Wi] out*/, float* pred_mean /*[B,K,Hi,Wi] out*/, clr_stream_t stream);
+int clr_retrify_weights(const float* oT_before /*[B,K,H,W]*/, const float* pred_mean, const float* std_map,
+                        int B, int K, int H, int W, int Hi, int Wi, float pseudo_thr /*0.75*/, float std_thr /*0.04*/,
+                        float* weights /*[B,2K,H,W] out*/, float* masks /*[B,K,H,W] out, {0,2}*/,
+                        float* pseudo_out /*[B,K,H,W] or NULL*/, float* small_out /*[2][B,K,H,W] or NULL*/,
+                        clr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Augmented-consistency masked BCE (Trainer_prototype_mt.cpython-38.pyc L502-561).
+ * stats = { sum(m*l), sum(m), loss, 0 }.
+ * ---------------------------------------------------------------------------------------------- */
+size_t clr_cons_ws_bytes(void);
+int clr_cons_fwd(const float* oT, const float* oT_aug, const float* masks, int B, int K, int Hi, int Wi, int H, int W,
+                 float threshold, float aug_weight, void* ws, size_t ws_bytes, float* stats /*[4] out*/,
+                 clr_stream_t stream);
+int clr_cons_bwd(const float* oT, const float* oT_aug, const float* masks, int B, int K, int Hi, int Wi, int H, int W,
+                 float threshold, float aug_weight, const float* stats, const float* gscale_dev, float gscale,
+                 float* grad_oT_aug /*[B,K,Hi,Wi] out*/, clr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * O(K*C) glue (Trainer_prototype_full.py:335-355, 378-398, 428-449): prototypes, EMA, alignment /
+ * separation losses and their gradients; then the discriminative term's prototype gradients + totals.
+ * losses = { intra, inter, disc, aug, total, 0, 0, 0 }.
+ * ---------------------------------------------------------------------------------------------- */
+int clr_align_finalize(const float* sums_s, const float* sums_t, int K, int C,
+                       float* stored_s /*[2K][C] in/out*/, float* stored_t, int first_s, int first_t, double decay,
+                       float w_intra, float w_inter, float* P_s /*[2K][C] out*/, float* P_t,
+                       float* cur_s /*[2K][C] out or NULL*/, float* cur_t,
+                       float* g_s /*[2K][C] out: dL/d cur_s*/, float* g_t,
+                       float* disc_vec /*[K][C] out or NULL*/, float* disc_beta /*[K] out or NULL*/,
+                       float* losses /*[8]*/, clr_stream_t stream);
+int clr_disc_finalize(const float* packed2 /*[K][C+1] | hinge num | cons num | cons den | 0*/, const float* P_s,
+                      int K, int C, double npx, float w_disc, float ema_factor, float gscale,
+                      float* g_s /*in/out*/, float* xtab /*[K][C] out*/,
+                      float w_intra, float w_inter, float w_aug, float aug_weight, int use_disc, int use_cons,
+                      float* losses, clr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * The fused CLR step: A1 (hard source) + A1/A2 (target) + A4 + A5 [+ A9] [+ A10], forward and backward,
+ * as three forward phases with the two possible cross-GPU exchange points between them, and one
+ * backward.  Single GPU: call a, b, c back to back (clr_step_fwd does).  Everything is enqueued on
+ * `stream`; no host synchronisation anywhere.
+ *
+ *   phase a: [mc_stats + retrify_weights] + pooling of both domains -> packed1 = [sums_s | sums_t]
+ *            --- all-reduce(packed1) when sharded ---
+ *   phase b: align_finalize; [consistency fwd]; [discriminative dots + active-set pooling] -> packed2
+ *            --- all-reduce(packed2) when sharded ---
+ *   phase c: disc_finalize (+ totals)
+ *   bwd    : gradient write for both feature maps in one launch [+ consistency backward]
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct clr_step_args {
+    /* geometry */
+    int B_s, B_t, C, H, W, K;
+    int Hi, Wi, T;                 /* image-resolution geometry of preds / oT (0 when unused) */
+    /* switches */
+    int use_retrify, use_disc, use_cons;
+    int wt_fmt;                    /* format of wt when !use_retrify (CLR_W_COMPLEMENT: sigmoid(oT_before) planes) */
+    int first_s, first_t;          /* 1 on the first step (EMA copies), then 0 */
+    /* hyper-parameters */
+    double decay, npx_global;      /* npx_global = global B_s*H*W (discriminative mean) */
+    float w_intra, w_inter, w_disc, w_aug, margin, aug_weight, cons_threshold, pseudo_thr, std_thr, grad_scale;
+    /* inputs */
+    const float* xs; const float* ys;     /* [B_s,C,H,W], [B_s,K,H,W] hard labels */
+    const float* xt; const float* wt;     /* [B_t,C,H,W]; target weights (ignored when use_retrify) */
+    const float* oT_before;               /* [B_t,K,H,W] (retrify) */
+    const float* preds;                   /* [T*B_t,K,Hi,Wi] (retrify) */
+    const float* oT; const float* oT_aug; /* [B_t,K,Hi,Wi] (consistency) */
+    const float* gup;                     /* device scalar dL/dtotal for the backward, or NULL (= 1) */
+    /* state, in/out */
+    float* stored_s; float* stored_t;     /* [2K][C] */
+    /* outputs */
+    float* packed1;                       /* [2][2K][C+1] */
+    float* packed2;                       /* [K][C+1] + 4 */
+    float* P_s; float* P_t;               /* [2K][C] EMA'd prototypes */
+    float* g_s; float* g_t;               /* [2K][C] dL/d(current prototypes) */
+    float* losses;                        /* [8] */
+    float* std_map; float* pred_mean;     /* [B_t,K,Hi,Wi] (retrify) */
+    float* wt_retrify; float* masks;      /* [B_t,2K,H,W], [B_t,K,H,W] (retrify) */
+    float* disc_coef;                     /* [B_s,K,H,W] (disc) */
+    float* disc_vec; float* disc_beta; float* xtab; /* [K][C], [K], [K][C] (disc) */
+    float* gxs; float* gxt;               /* [B,C,H,W] backward outputs */
+    float* g_oT_aug;                      /* [B_t,K,Hi,Wi] backward output (consistency, when w_aug != 0) */
+    /* workspace */
+    void* ws; size_t ws_bytes;
+} clr_step_args;
+
+size_t clr_step_ws_bytes(const clr_step_args* a);
+int clr_step_fwd_a(const clr_step_args* a, clr_stream_t stream);
+int clr_step_fwd_b(const clr_step_args* a, clr_stream_t stream);
+int clr_step_fwd_c(const clr_step_args* a, clr_stream_t stream);
+int clr_step_fwd(const clr_step_args* a, clr_stream_t stream);
+int clr_step_bwd(const clr_step_args* a, clr_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -8,7 +8,7 @@ from __future__ import annotations
 import ctypes
 import os
 import threading
-from ctypes import POINTER, c_char_p, c_float, c_int, c_size_t, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_size_t, c_void_p
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "lib", "libclr_b200.so")
@@ -27,20 +27,75 @@ class ClrError(RuntimeError):
 
 _P = c_void_p  # device pointers travel as integers
 
+
+class BwdDom(Structure):
+    """``clr_bwd_dom`` (include/clr_b200.h)."""
+    _fields_ = [("w", _P), ("g", _P), ("sums", _P), ("xcoef", _P), ("xtab", _P), ("grad", _P),
+                ("scale_dev", _P), ("scale", c_float), ("fmt", c_int), ("B", c_int), ("Kx", c_int)]
+
+
+class StepArgs(Structure):
+    """``clr_step_args`` (include/clr_b200.h) -- field order must match the header."""
+    _fields_ = [
+        ("B_s", c_int), ("B_t", c_int), ("C", c_int), ("H", c_int), ("W", c_int), ("K", c_int),
+        ("Hi", c_int), ("Wi", c_int), ("T", c_int),
+        ("use_retrify", c_int), ("use_disc", c_int), ("use_cons", c_int),
+        ("wt_fmt", c_int), ("first_s", c_int), ("first_t", c_int),
+        ("decay", c_double), ("npx_global", c_double),
+        ("w_intra", c_float), ("w_inter", c_float), ("w_disc", c_float), ("w_aug", c_float), ("margin", c_float),
+        ("aug_weight", c_float), ("cons_threshold", c_float), ("pseudo_thr", c_float), ("std_thr", c_float),
+        ("grad_scale", c_float),
+        ("xs", _P), ("ys", _P), ("xt", _P), ("wt", _P), ("oT_before", _P), ("preds", _P), ("oT", _P), ("oT_aug", _P),
+        ("gup", _P),
+        ("stored_s", _P), ("stored_t", _P),
+        ("packed1", _P), ("packed2", _P), ("P_s", _P), ("P_t", _P), ("g_s", _P), ("g_t", _P), ("losses", _P),
+        ("std_map", _P), ("pred_mean", _P), ("wt_retrify", _P), ("masks", _P),
+        ("disc_coef", _P), ("disc_vec", _P), ("disc_beta", _P), ("xtab", _P),
+        ("gxs", _P), ("gxt", _P), ("g_oT_aug", _P),
+        ("ws", _P), ("ws_bytes", c_size_t),
+    ]
+
+
 _SIGNATURES = {
     "clr_version": (c_int, []),
     "clr_status_string": (c_char_p, [c_int]),
     "clr_device_info": (c_int, [POINTER(c_int), POINTER(c_int)]),
+    "clr_set_tunable": (c_int, [c_char_p, c_int]),
     "clr_pool_ws_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "clr_pool_rows_ws_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "clr_pool_rows_fwd": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, c_size_t, _P, _P]),
     "clr_pool_fwd": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P, _P]),
     "clr_pool_fwd2": (c_int, [_P, _P, c_int, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P, _P, _P]),
     "clr_proto_finalize": (c_int, [_P, c_int, c_int, _P, _P]),
     "clr_pool_bwd": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_float, _P, _P, c_int, _P, _P]),
-    "clr_pool_bwd2": (c_int, [_P, c_int, c_int, _P, _P, c_float, _P, _P, c_int, _P,
-                              _P, c_int, c_int, _P, _P, c_float, _P, c_int, c_int, c_int, _P]),
+    "clr_pool_bwd_multi": (c_int, [POINTER(BwdDom), c_int, c_int, c_int, c_int, _P]),
     "clr_pixel_dots": (c_int, [_P, c_int, c_int, c_int, _P, c_int, _P, _P, _P]),
     "clr_pool_bwd_w_ws_bytes": (c_size_t, [c_int, c_int, c_int]),
     "clr_pool_bwd_w": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_float, _P, c_size_t, _P, _P]),
+    "clr_proto_distance": (c_int, [_P, c_int, c_int, c_int, _P, c_int, _P, _P]),
+    "clr_proto_cosine": (c_int, [_P, c_int, c_int, c_int, _P, _P, _P, _P]),
+    "clr_minmax_normalize": (c_int, [_P, c_size_t, _P, _P]),
+    "clr_disc_partials_cap": (c_int, []),
+    "clr_disc_fwd": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, c_float, _P, _P, _P, c_int,
+                             POINTER(c_int), _P]),
+    "clr_mc_stats": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P]),
+    "clr_retrify_weights": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float,
+                                    _P, _P, _P, _P, _P]),
+    "clr_cons_ws_bytes": (c_size_t, []),
+    "clr_cons_fwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float, _P, c_size_t,
+                             _P, _P]),
+    "clr_cons_bwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float, _P, _P,
+                             c_float, _P, _P]),
+    "clr_align_finalize": (c_int, [_P, _P, c_int, c_int, _P, _P, c_int, c_int, c_double, c_float, c_float,
+                                   _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "clr_disc_finalize": (c_int, [_P, _P, c_int, c_int, c_double, c_float, c_float, c_float, _P, _P,
+                                  c_float, c_float, c_float, c_float, c_int, c_int, _P, _P]),
+    "clr_step_ws_bytes": (c_size_t, [POINTER(StepArgs)]),
+    "clr_step_fwd_a": (c_int, [POINTER(StepArgs), _P]),
+    "clr_step_fwd_b": (c_int, [POINTER(StepArgs), _P]),
+    "clr_step_fwd_c": (c_int, [POINTER(StepArgs), _P]),
+    "clr_step_fwd": (c_int, [POINTER(StepArgs), _P]),
+    "clr_step_bwd": (c_int, [POINTER(StepArgs), _P]),
 }
 
 

@@ -21,9 +21,27 @@ const DeviceFacts& device_facts() {
     return facts[dev];
 }
 
+Tunables& tunables() {
+    static Tunables t{0, 0, 0, 0};
+    return t;
+}
+
 }  // namespace clr
 
+#include <string.h>
+
 extern "C" {
+
+int clr_set_tunable(const char* name, int value) {
+    if (!name) return CLR_ERR_BAD_ARG;
+    clr::Tunables& t = clr::tunables();
+    if (!strcmp(name, "pool_impl")) t.pool_impl = value;
+    else if (!strcmp(name, "pool_stages")) t.pool_stages = value;
+    else if (!strcmp(name, "dots_impl")) t.dots_impl = value;
+    else if (!strcmp(name, "bwd_impl")) t.bwd_impl = value;
+    else return CLR_ERR_BAD_ARG;
+    return CLR_OK;
+}
 
 int clr_version(void) { return CLR_B200_VERSION; }
 

@@ -25,6 +25,15 @@ static inline bool aligned4(const void* p) { return (reinterpret_cast<uintptr_t>
 struct DeviceFacts { int sms; int l2; int max_smem_optin; };
 const DeviceFacts& device_facts();
 
+// Process-wide kernel-selection knobs for benchmarking (clr_set_tunable); defaults pick the fastest path.
+struct Tunables {
+    int pool_impl;     // 0 = auto (TMA ring when aligned), 1 = force the LDG kernel
+    int pool_stages;   // TMA ring depth (0 = auto)
+    int dots_impl;     // 0 = auto, 1 = force the LDG kernel
+    int bwd_impl;      // reserved
+};
+Tunables& tunables();
+
 // ---- streaming loads / stores --------------------------------------------------------------------
 // Feature maps are touched exactly once per pass: read through the non-coherent path without
 // allocating in L1; gradients are written with an evict-first hint.
@@ -103,6 +112,58 @@ __device__ __forceinline__ float warp_sum_transpose32(float (&v)[32], int lane) 
         }
     }
     return v[0];
+}
+
+// ---- mbarrier + bulk async copy (TMA engine, 1-D form: cp.async.bulk -> SASS UBLKCP) -------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+// make mbarrier initialisation visible to the async proxy before the first bulk copy targets it
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy; completion is signalled on `bar` as `bytes` of transaction count.
+// dst/src 16-byte aligned, bytes a multiple of 16.  Streaming data: L2 evict-first policy.
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+        ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+// named barrier among a subset of the CTA's warps (id 1..15; 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 // Static contiguous partition of `total` items over `parts` workers.

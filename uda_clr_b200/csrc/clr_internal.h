@@ -1,0 +1,23 @@
+// Cross-translation-unit entry points used by the fused step orchestration (step.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+namespace clr {
+
+int pool_fwd_impl(const float* feat0, const float* w0, int fmt0, int B0, float* sums0,
+                  const float* feat1, const float* w1, int fmt1, int B1, float* sums1,
+                  int C, int HW, int R, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t pool_partial_bytes(int B, int C, int HW, int R);
+
+int disc_fwd_impl(const float* xs, const float* ys, int B, int C, int HW, int K,
+                  const float* disc_vec, const float* disc_beta, float margin,
+                  float* coef, float* delta, float* partials, int partials_cap, int* nparts, cudaStream_t st);
+
+int cons_fwd_partials(const float* oT, const float* oT_aug, const float* masks, int B, int K, int Hi, int Wi,
+                      int H, int W, float threshold, double* partial, int* nblocks, cudaStream_t st);
+
+void launch_step_pack(const float* hinge_partials, int n_hinge, int hinge_stride,
+                      const double* cons_partials, int n_cons, float* tail, cudaStream_t st);
+
+}  // namespace clr

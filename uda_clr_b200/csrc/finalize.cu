@@ -1,0 +1,161 @@
+// The O(K*C) glue between the streaming passes -- everything the reference does with ~40 tiny ATen
+// launches and two .item() host syncs (Trainer_prototype_full.py:335-355, 378-398, 428-449):
+//
+// clr_align_finalize : mu = S/N (utils/Utils.py:127-130) -> EMA with the stored prototypes
+//                      (first step: copy; later (1-d)*stored + d*cur; stored <- detached result)
+//                      -> intra / inter losses (:428-444) -> dL/d(cur prototypes) for both domains
+//                      -> the discriminative pass's contraction vectors D_k = P_obj,k - P_bck,k and
+//                         offsets beta_k = (|P_obj,k|^2 - |P_bck,k|^2)/C.
+// clr_disc_finalize  : loss_disc and its prototype gradients from the active-set sums
+//                      (Trainer_prototype_mt bytecode L454-474), the direct-gradient
+//                      table for the backward write, and the step total.
+// One CTA each; reductions in fp64, fixed order.
+#include "clr_common.cuh"
+#include "clr_internal.h"
+
+namespace clr {
+
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    double t = 0.0;
+    const int nw = (blockDim.x + 31) >> 5;
+    for (int i = 0; i < nw; ++i) t += sh[i];
+    return t;
+}
+
+__global__ void __launch_bounds__(256) align_finalize_kernel(
+    const float* __restrict__ sums_s, const float* __restrict__ sums_t, int K, int C,
+    float* __restrict__ stored_s, float* __restrict__ stored_t, int first_s, int first_t, double decay,
+    float w_intra, float w_inter,
+    float* __restrict__ P_s, float* __restrict__ P_t, float* __restrict__ cur_s, float* __restrict__ cur_t,
+    float* __restrict__ g_s, float* __restrict__ g_t,
+    float* __restrict__ disc_vec, float* __restrict__ disc_beta, float* __restrict__ losses) {
+    __shared__ double sh[8];
+    const int R = 2 * K;
+    const float d = (float)decay, omd = (float)(1.0 - decay);   // the reference forms (1 - decay) in double, then casts
+    const float ds = first_s ? 1.f : d, dt = first_t ? 1.f : d;
+    double intra = 0.0, inter = 0.0;
+    // pass 1: prototypes, EMA, intra
+    for (int i = threadIdx.x; i < R * C; i += blockDim.x) {
+        const int r = i / C, c = i - r * C;
+        const float cs = sums_s[(size_t)r * (C + 1) + c] / sums_s[(size_t)r * (C + 1) + C];
+        const float ct = sums_t[(size_t)r * (C + 1) + c] / sums_t[(size_t)r * (C + 1) + C];
+        const float ps = first_s ? cs : __fadd_rn(__fmul_rn(omd, stored_s[i]), __fmul_rn(d, cs));
+        const float pt = first_t ? ct : __fadd_rn(__fmul_rn(omd, stored_t[i]), __fmul_rn(d, ct));
+        if (cur_s) cur_s[i] = cs;
+        if (cur_t) cur_t[i] = ct;
+        P_s[i] = ps; P_t[i] = pt;
+        stored_s[i] = ps; stored_t[i] = pt;       // .detach() copies (Trainer_prototype_full.py:341-344)
+        const double df = (double)ps - (double)pt;
+        intra += df * df;
+        const float gi = w_intra * 2.0f * (ps - pt) / (float)C;
+        g_s[i] = ds * gi;
+        g_t[i] = -dt * gi;
+    }
+    __syncthreads();   // P_s complete (same CTA wrote it)
+    // pass 2: inter loss + its gradient, discriminative vectors
+    for (int k = 0; k < K; ++k) {
+        double nb = 0.0;
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            const float po = P_s[(size_t)k * C + c], pb = P_s[(size_t)(K + k) * C + c];
+            const float df = po - pb;
+            inter += (double)df * df;
+            if (w_inter != 0.f) {
+                const float gi = ds * w_inter * 2.0f * df / (float)C;
+                g_s[(size_t)k * C + c] += gi;
+                g_s[(size_t)(K + k) * C + c] -= gi;
+            }
+            if (disc_vec) disc_vec[(size_t)k * C + c] = df;
+            nb += (double)po * po - (double)pb * pb;
+        }
+        nb = block_sum(nb, sh);
+        if (threadIdx.x == 0 && disc_beta) disc_beta[k] = (float)(nb / C);
+    }
+    intra = block_sum(intra, sh);
+    inter = block_sum(inter, sh);
+    if (threadIdx.x == 0) {
+        losses[0] = (float)(intra / C);
+        losses[1] = (float)(inter / C);
+    }
+}
+
+// packed2 layout: [K][C+1] active-set sums (col C = n_k) | loss numerator | cons num | cons den | pad
+__global__ void __launch_bounds__(256) disc_finalize_kernel(
+    const float* __restrict__ packed2, const float* __restrict__ P_s, int K, int C, double npx, float w_disc,
+    float ema_factor, float gscale, float* __restrict__ g_s, float* __restrict__ xtab,
+    float w_intra, float w_inter, float w_aug, float aug_weight, int use_disc, int use_cons,
+    float* __restrict__ losses) {
+    const float* tail = packed2 + (size_t)K * (C + 1);
+    if (use_disc) {
+        const float coef = (float)(2.0 / ((double)C * npx));
+        for (int i = threadIdx.x; i < K * C; i += blockDim.x) {
+            const int k = i / C, c = i - k * C;
+            const float nk = packed2[(size_t)k * (C + 1) + C];
+            const float A = packed2[(size_t)k * (C + 1) + c];
+            const float po = P_s[(size_t)k * C + c], pb = P_s[(size_t)(K + k) * C + c];
+            g_s[(size_t)k * C + c] += ema_factor * w_disc * coef * (nk * po - A);
+            g_s[(size_t)(K + k) * C + c] -= ema_factor * w_disc * coef * (nk * pb - A);
+            xtab[i] = -gscale * w_disc * coef * (po - pb);
+        }
+    }
+    if (threadIdx.x == 0) {
+        const float disc = use_disc ? (float)((double)tail[0] / npx) : 0.f;
+        const float aug = use_cons ? (float)((double)tail[1] / (double)tail[2] * (double)aug_weight) : 0.f;
+        losses[2] = disc;
+        losses[3] = aug;
+        losses[4] = w_intra * losses[0] + w_inter * losses[1] + w_disc * disc + w_aug * aug;
+    }
+}
+
+// Sum the hinge per-CTA partials and the consistency per-CTA partials into the tail of packed2 (one warp).
+__global__ void step_pack_kernel(const float* __restrict__ hinge_partials, int n_hinge, int hinge_stride,
+                                 const double* __restrict__ cons_partials, int n_cons, float* __restrict__ tail) {
+    double a = 0.0, b = 0.0, c = 0.0;
+    if (hinge_partials)
+        for (int i = threadIdx.x; i < n_hinge; i += 32) a += (double)hinge_partials[(size_t)i * hinge_stride];
+    if (cons_partials)
+        for (int i = threadIdx.x; i < n_cons; i += 32) { b += cons_partials[2 * i]; c += cons_partials[2 * i + 1]; }
+    a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
+    if (threadIdx.x == 0) { tail[0] = (float)a; tail[1] = (float)b; tail[2] = (float)c; tail[3] = 0.f; }
+}
+
+void launch_step_pack(const float* hinge_partials, int n_hinge, int hinge_stride,
+                      const double* cons_partials, int n_cons, float* tail, cudaStream_t st) {
+    step_pack_kernel<<<1, 32, 0, st>>>(hinge_partials, n_hinge, hinge_stride, cons_partials, n_cons, tail);
+}
+
+}  // namespace clr
+
+extern "C" {
+
+int clr_align_finalize(const float* sums_s, const float* sums_t, int K, int C,
+                       float* stored_s, float* stored_t, int first_s, int first_t, double decay,
+                       float w_intra, float w_inter, float* P_s, float* P_t, float* cur_s, float* cur_t,
+                       float* g_s, float* g_t, float* disc_vec, float* disc_beta, float* losses,
+                       clr_stream_t stream) {
+    if (!sums_s || !sums_t || !stored_s || !stored_t || !P_s || !P_t || !g_s || !g_t || !losses ||
+        K < 1 || K > CLR_MAX_K || C < 1)
+        return CLR_ERR_BAD_ARG;
+    clr::align_finalize_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        sums_s, sums_t, K, C, stored_s, stored_t, first_s, first_t, decay, w_intra, w_inter,
+        P_s, P_t, cur_s, cur_t, g_s, g_t, disc_vec, disc_beta, losses);
+    return clr::launch_status();
+}
+
+int clr_disc_finalize(const float* packed2, const float* P_s, int K, int C, double npx, float w_disc,
+                      float ema_factor, float gscale, float* g_s, float* xtab,
+                      float w_intra, float w_inter, float w_aug, float aug_weight, int use_disc, int use_cons,
+                      float* losses, clr_stream_t stream) {
+    if (!packed2 || !losses || K < 1 || K > CLR_MAX_K || C < 1) return CLR_ERR_BAD_ARG;
+    if (use_disc && (!P_s || !g_s || !xtab || npx <= 0)) return CLR_ERR_BAD_ARG;
+    clr::disc_finalize_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        packed2, P_s, K, C, npx, w_disc, ema_factor, gscale, g_s, xtab, w_intra, w_inter, w_aug, aug_weight,
+        use_disc, use_cons, losses);
+    return clr::launch_status();
+}
+
+}  // extern "C"

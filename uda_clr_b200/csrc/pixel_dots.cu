@@ -17,6 +17,7 @@
 //   reduce = lanes l and l+16 by one shuffle, the 8 warps through shared memory; no atomics
 //   grid   = persistent with contiguous item ranges
 #include "clr_common.cuh"
+#include "clr_internal.h"
 
 namespace clr {
 
@@ -35,10 +36,10 @@ struct DotsParams {
     float* coef;           // hinge: d(loss*npx)/d(delta) [B,Q,HW]
     float* partials;       // hinge: [gridDim.x][1+Q] loss numerator and coefficient sums per CTA
     const float* beta_dev; // optional device-side beta[Q] (overrides beta[])
+    const float* vnorm_dev;// cosine: device-side max(|V_0|, eps)
     float alpha[kDotsMaxQ];
     float beta[kDotsMaxQ];
     float margin;
-    float vnorm;           // cosine: max(|V_0|, eps)
     int B, C, HW, Q, epi;
     int tilesPerSample, total;
 };
@@ -145,7 +146,7 @@ __global__ void __launch_bounds__(kThreads, 3) pixel_dots_kernel(const DotsParam
                 float ss = 0.f;
 #pragma unroll
                 for (int wq = 0; wq < kWarps; ++wq) ss += red[(wq * NA + (NA - 1)) * TP + j];
-                p.out[o] = s / (fmaxf(sqrtf(ss), 1e-8f) * p.vnorm);
+                p.out[o] = s / (fmaxf(sqrtf(ss), 1e-8f) * __ldg(p.vnorm_dev));
             } else {  // DOTS_EPI_HINGE
                 const float delta = fmaf(p.alpha[a], s, p.beta_dev ? p.beta_dev[a] : p.beta[a]);
                 const float yv = p.y[o];
@@ -260,9 +261,106 @@ __global__ void bwd_w_tables_kernel(const float* __restrict__ g, const float* __
     }
 }
 
+__global__ void vec_norm_kernel(const float* __restrict__ v, int C, float eps, float* __restrict__ out) {
+    double acc = 0.0;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) acc += (double)v[c] * v[c];
+    acc = warp_sum(acc);
+    __shared__ double sh[8];
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sh[i];
+        out[0] = fmaxf((float)sqrt(t), eps);
+    }
+}
+
+// global min / max of a small map (two stages, fixed order), then (x - min) / (max - min) in place
+__global__ void __launch_bounds__(256) minmax_partial_kernel(const float* __restrict__ x, size_t n, float* __restrict__ part) {
+    float lo = INFINITY, hi = -INFINITY;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float v = x[i];
+        lo = fminf(lo, v); hi = fmaxf(hi, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    __shared__ float sl[8], shh[8];
+    if ((threadIdx.x & 31) == 0) { sl[threadIdx.x >> 5] = lo; shh[threadIdx.x >> 5] = hi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 8; ++i) { lo = fminf(lo, sl[i]); hi = fmaxf(hi, shh[i]); }
+        part[2 * blockIdx.x] = fminf(lo, sl[0]);
+        part[2 * blockIdx.x + 1] = fmaxf(hi, shh[0]);
+    }
+}
+__global__ void __launch_bounds__(256) minmax_apply_kernel(float* __restrict__ x, size_t n, const float* __restrict__ part, int nparts) {
+    float lo = INFINITY, hi = -INFINITY;
+    for (int i = 0; i < nparts; ++i) { lo = fminf(lo, part[2 * i]); hi = fmaxf(hi, part[2 * i + 1]); }
+    const float den = hi - lo;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        x[i] = (x[i] - lo) / den;
+}
+
+int disc_fwd_impl(const float* xs, const float* ys, int B, int C, int HW, int K,
+                  const float* disc_vec, const float* disc_beta, float margin,
+                  float* coef, float* delta, float* partials, int partials_cap, int* nparts, cudaStream_t st) {
+    CLR_CHECK_ARG(xs && ys && disc_vec && disc_beta && coef && partials && nparts && partials_cap > 0);
+    CLR_CHECK_ARG(K >= 1 && K <= CLR_MAX_K);
+    DotsParams p{};
+    p.feat = xs; p.V = disc_vec; p.out = delta; p.y = ys; p.coef = coef; p.partials = partials;
+    p.beta_dev = disc_beta; p.margin = margin;
+    p.B = B; p.C = C; p.HW = HW; p.Q = K; p.epi = DOTS_EPI_HINGE;
+    for (int q = 0; q < kDotsMaxQ; ++q) { p.alpha[q] = -2.0f / (float)C; p.beta[q] = 0.f; }
+    int grid = partials_cap;
+    const int rc = pixel_dots_impl(p, DOTS_OP_DOT, false, &grid, st);
+    *nparts = grid;
+    return rc;
+}
+
 }  // namespace clr
 
 extern "C" {
+
+int clr_disc_partials_cap(void) { return 148 * 16; }
+
+int clr_disc_fwd(const float* xs, const float* ys, int B, int C, int HW, int K,
+                 const float* disc_vec, const float* disc_beta, float margin,
+                 float* coef, float* delta, float* partials, int partials_cap, int* nparts, clr_stream_t stream) {
+    return clr::disc_fwd_impl(xs, ys, B, C, HW, K, disc_vec, disc_beta, margin, coef, delta, partials, partials_cap,
+                              nparts, static_cast<cudaStream_t>(stream));
+}
+
+int clr_proto_distance(const float* feat, int B, int C, int HW, const float* protos, int Q,
+                       float* dist, clr_stream_t stream) {
+    if (!dist) return CLR_ERR_BAD_ARG;
+    clr::DotsParams p{};
+    p.feat = feat; p.V = protos; p.out = dist;
+    p.B = B; p.C = C; p.HW = HW; p.Q = Q; p.epi = clr::DOTS_EPI_SQRT;
+    return clr::pixel_dots_impl(p, clr::DOTS_OP_SQDIFF, false, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int clr_proto_cosine(const float* feat, int B, int C, int HW, const float* proto, float* ws4, float* out,
+                     clr_stream_t stream) {
+    if (!out || !ws4 || !proto || C < 1) return CLR_ERR_BAD_ARG;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    clr::vec_norm_kernel<<<1, 256, 0, st>>>(proto, C, 1e-8f, ws4);
+    clr::DotsParams p{};
+    p.feat = feat; p.V = proto; p.out = out; p.vnorm_dev = ws4;
+    p.B = B; p.C = C; p.HW = HW; p.Q = 1; p.epi = clr::DOTS_EPI_COSINE;
+    return clr::pixel_dots_impl(p, clr::DOTS_OP_DOT, true, nullptr, st);
+}
+
+int clr_minmax_normalize(float* x, size_t n, float* ws /*>= 2*256 floats*/, clr_stream_t stream) {
+    if (!x || !ws || n == 0) return CLR_ERR_BAD_ARG;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int blocks = (int)((n + 255) / 256 < 256 ? (n + 255) / 256 : 256);
+    clr::minmax_partial_kernel<<<blocks, 256, 0, st>>>(x, n, ws);
+    clr::minmax_apply_kernel<<<blocks, 256, 0, st>>>(x, n, ws, blocks);
+    return clr::launch_status();
+}
 
 int clr_pixel_dots(const float* feat, int B, int C, int HW, const float* V, int Q,
                    float* dots, float* sumsq, clr_stream_t stream) {

@@ -5,18 +5,26 @@
 //
 // Bound: HBM.  Algorithmic bytes per domain = 4*B*C*HW (features) + 4*B*WP*HW (weight planes).
 //
-// Layout / decomposition
+// Decomposition (both kernels)
 //   item   = (domain, sample b, pixel chunk of PX pixels, group of CG channels)  -> 4*PX*CG bytes
-//   grid   = persistent: (#SM x resident CTAs), each CTA owns a contiguous range of items, so a
-//            CTA walks the channel groups of one (b, chunk) before moving on and re-stages the
-//            chunk's weight planes in shared memory only when (b, chunk) changes.
-//   thread = owns VEC*REPS fixed pixels of the chunk; per item it streams CG channel rows with
-//            128-bit non-allocating loads (CG*REPS independent loads in flight), keeps CG*2K fp32
-//            accumulators, then the warp does one transposing butterfly (31 shuffles) and the
-//            8 warps combine through shared memory.
+//   grid   = persistent: each CTA owns a contiguous range of items, so it walks the channel groups
+//            of one (b, chunk) before moving on and re-stages that chunk's R weight rows in shared
+//            memory only when (b, chunk) changes.
+//   thread = owns VEC*REPS fixed pixels of the chunk, keeps CG*R fp32 accumulators; per item the warp
+//            does one transposing butterfly (31 shuffles) and the 8 warps combine through shared memory.
 //   output = per-(b,chunk) partials [R][C+1] (column C = weight sums), combined across (b,chunk)
-//            in fp64 and in a fixed order by pool_reduce_kernel -> bit-stable run to run.
+//            in fp64 and in a fixed order by pool_reduce_kernel -> bit-stable run to run, no atomics.
+//
+// Two data paths for the feature rows
+//   pool_fwd_tma_kernel : a producer warp streams each item's CG channel rows (PX*4 contiguous bytes
+//            each) into a shared-memory ring with 1-D bulk async copies (cp.async.bulk + mbarrier
+//            complete_tx, SASS UBLKCP) so that several 32-64 KB stages are in flight per SM regardless
+//            of what the 8 consumer warps are doing (FMA, butterfly, barrier).  Needs HW % 4 == 0 and
+//            16-byte aligned bases.
+//   pool_fwd_ldg_kernel : 128-bit non-allocating loads straight to registers; also the scalar
+//            fallback (VEC = 1) for ragged planes / 4-byte-aligned bases.
 #include "clr_common.cuh"
+#include "clr_internal.h"
 
 namespace clr {
 
@@ -37,80 +45,158 @@ struct PoolParams {
     int C, HW;
     int nChunk, nGroup;
     int total;
+    int stages;       // TMA ring depth
 };
 
-template <int K, int VEC>
-struct PoolCfg {
-    static constexpr int R = 2 * K;
-    static constexpr int CG = 32 / R;                       // channels per item (accumulators <= 32)
-    static constexpr int REPS = (K <= 2) ? 2 : 1;           // pixels per thread = VEC*REPS
-    static constexpr int PX = kThreads * VEC * REPS;        // pixels per chunk
-    static constexpr int SMEM_W = 2 * K * PX;               // explicit planes worst case (floats)
-    static constexpr int SMEM_RED = 2 * kWarps * 32;        // double-buffered cross-warp scratch
-    static constexpr size_t SMEM_BYTES = sizeof(float) * (SMEM_W + SMEM_RED);
-};
+constexpr int pool_cg(int R) { return (32 / R) < 16 ? (32 / R) : 16; }   // channels per item
+constexpr int pool_reps(int R) { return (R >= 3 && R <= 8) ? 2 : 1; }    // VEC-wide pixel groups per thread
 
-template <int K, int VEC>
-__global__ void __launch_bounds__(kThreads, 2) pool_fwd_kernel(const PoolParams p) {
-    using Cfg = PoolCfg<K, VEC>;
-    constexpr int R = Cfg::R, CG = Cfg::CG, REPS = Cfg::REPS, PX = Cfg::PX;
-    extern __shared__ __align__(16) float smem[];
-    float* wsm = smem;                         // [R][PX]  (obj rows then bck rows, already complemented)
-    float* red = smem + Cfg::SMEM_W;           // [2][kWarps][32]
+struct ItemCoord { int d, slot, grp, b, chunk; };
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int begin, end;
-    partition(p.total, gridDim.x, blockIdx.x, begin, end);
+__device__ __forceinline__ ItemCoord decode_item(const PoolParams& p, int it) {
+    ItemCoord c;
+    c.d = (p.ndom > 1 && it >= p.dom[0].items) ? 1 : 0;
+    const int local = it - (c.d ? p.dom[0].items : 0);
+    c.slot = local / p.nGroup;
+    c.grp = local - c.slot * p.nGroup;
+    c.b = c.slot / p.nChunk;
+    c.chunk = c.slot - c.b * p.nChunk;
+    return c;
+}
 
-    int cur_slot_key = -1;
-    int parity = 0;
-    for (int it = begin; it < end; ++it) {
-        const int d = (p.ndom > 1 && it >= p.dom[0].items) ? 1 : 0;
-        const PoolDom& D = p.dom[d];
-        const int local = it - (d ? p.dom[0].items : 0);
-        const int slot = local / p.nGroup, grp = local - slot * p.nGroup;
-        const int b = slot / p.nChunk, chunk = slot - b * p.nChunk;
-        const int px0 = chunk * PX;
-        const int slot_key = d * 0x40000000 + slot;
+// Stage the R weight rows of (b, chunk) in shared memory (complement rows are materialised here:
+// w_bck = 1 - w_obj, utils/Utils.py:111-112).  Pixels past the plane are staged as 0 for every row.
+template <int R, int VEC, int REPS>
+__device__ __forceinline__ void stage_weights(const PoolDom& D, int b, int px0, int HW, float* wsm, int tid) {
+    constexpr int PX = kThreads * VEC * REPS, K = R / 2;
+    const int WP = (D.fmt == CLR_W_COMPLEMENT) ? K : R;
+    const float* wb = D.w + (size_t)b * WP * HW;
+#pragma unroll
+    for (int rep = 0; rep < REPS; ++rep) {
+        const int off = (rep * kThreads + tid) * VEC;
+        const bool ok = px0 + off < HW;   // VEC-granular: HW % VEC == 0 on the VEC = 4 paths
+        if (D.fmt == CLR_W_COMPLEMENT) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                Pack<VEC> wo, wc;
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) { wo.v[v] = 0.f; wc.v[v] = 0.f; }
+                if (ok) {
+                    wo = ld_keep<VEC>(wb + (size_t)k * HW + px0 + off);
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) wc.v[v] = 1.0f - wo.v[v];
+                }
+                st_keep<VEC>(wsm + k * PX + off, wo);
+                st_keep<VEC>(wsm + (K + k) * PX + off, wc);
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                Pack<VEC> wr;
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) wr.v[v] = 0.f;
+                if (ok) wr = ld_keep<VEC>(wb + (size_t)r * HW + px0 + off);
+                st_keep<VEC>(wsm + r * PX + off, wr);
+            }
+        }
+    }
+}
 
-        if (slot_key != cur_slot_key) {
-            // ---- stage this (b, chunk)'s 2K weight rows in shared memory -------------------------
-            __syncthreads();   // previous item's readers of wsm are done
-            cur_slot_key = slot_key;
-            const int WP = (D.fmt == CLR_W_COMPLEMENT) ? K : R;
-            const float* wb = D.w + (size_t)b * WP * p.HW;
+template <int VEC>
+__device__ __forceinline__ Pack<VEC> lds_pack(const float* p) {
+    Pack<VEC> r;
+    if constexpr (VEC == 4) {
+        const float4 t = *reinterpret_cast<const float4*>(p);
+        r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+    } else {
+        r.v[0] = *p;
+    }
+    return r;
+}
+
+// CTA-level combine of the per-thread accumulators of one item and store of the partial row slices.
+// sync() is the barrier over the 256 compute threads.
+template <int R, int CG, int VEC, int REPS, typename Sync>
+__device__ __forceinline__ void reduce_and_store(float (&acc)[32], const float* wsm, float* red, int& parity,
+                                                 float* out, int C, int c0, bool owns_counts,
+                                                 int tid, Sync sync) {
+    constexpr int PX = kThreads * VEC * REPS;
+    const int lane = tid & 31, warp = tid >> 5;
+    float nsum[R];
+    if (owns_counts) {   // the item that owns channel group 0 also sums this chunk's weights
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            float s = 0.f;
 #pragma unroll
             for (int rep = 0; rep < REPS; ++rep) {
                 const int off = (rep * kThreads + tid) * VEC;
-                const bool ok = px0 + off < p.HW;   // VEC-granular: HW % VEC == 0 on the VEC=4 path
 #pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    Pack<VEC> wo, wb_;
-                    if (ok) {
-                        wo = ld_keep<VEC>(wb + (size_t)k * p.HW + px0 + off);
-                        if (D.fmt == CLR_W_COMPLEMENT) {
-#pragma unroll
-                            for (int v = 0; v < VEC; ++v) wb_.v[v] = 1.0f - wo.v[v];   // utils/Utils.py:111-112
-                        } else {
-                            wb_ = ld_keep<VEC>(wb + (size_t)(K + k) * p.HW + px0 + off);
-                        }
-                    } else {
-#pragma unroll
-                        for (int v = 0; v < VEC; ++v) { wo.v[v] = 0.f; wb_.v[v] = 0.f; }
-                    }
-                    st_keep<VEC>(wsm + k * PX + off, wo);
-                    st_keep<VEC>(wsm + (K + k) * PX + off, wb_);
-                }
+                for (int v = 0; v < VEC; ++v) s += wsm[r * PX + off + v];
             }
+            nsum[r] = s;
+        }
+    }
+    const float tot = warp_sum_transpose32(acc, lane);
+    float* redp = red + parity * (kWarps * 32);
+    redp[warp * 32 + lane] = tot;
+    sync();
+    if (warp == 0) {
+        float s = 0.f;
+#pragma unroll
+        for (int wq = 0; wq < kWarps; ++wq) s += redp[wq * 32 + lane];
+        const int j = lane / R, r = lane - j * R;
+        if (j < CG && c0 + j < C) out[(size_t)r * (C + 1) + c0 + j] = s;
+    }
+    parity ^= 1;
+    if (owns_counts) {   // CTA-uniform
+#pragma unroll
+        for (int r = 0; r < R; ++r) nsum[r] = warp_sum(nsum[r]);
+        float* redn = red + parity * (kWarps * 32);
+        if (lane == 0) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) redn[warp * 32 + r] = nsum[r];
+        }
+        sync();
+        if (warp == 0 && lane < R) {
+            float s = 0.f;
+#pragma unroll
+            for (int wq = 0; wq < kWarps; ++wq) s += redn[wq * 32 + lane];
+            out[(size_t)lane * (C + 1) + C] = s;
+        }
+        parity ^= 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LDG path (also the scalar fallback)
+// ------------------------------------------------------------------------------------------------
+template <int R, int VEC>
+__global__ void __launch_bounds__(kThreads, 2) pool_fwd_ldg_kernel(const PoolParams p) {
+    constexpr int CG = pool_cg(R), REPS = pool_reps(R), PX = kThreads * VEC * REPS;
+    extern __shared__ __align__(16) float smem[];
+    float* wsm = smem;                 // [R][PX]
+    float* red = smem + R * PX;        // [2][kWarps][32]
+    const int tid = threadIdx.x;
+    int begin, end;
+    partition(p.total, gridDim.x, blockIdx.x, begin, end);
+    int cur_key = -1, parity = 0;
+    auto sync = [] { __syncthreads(); };
+    for (int it = begin; it < end; ++it) {
+        const ItemCoord ic = decode_item(p, it);
+        const PoolDom& D = p.dom[ic.d];
+        const int px0 = ic.chunk * PX;
+        const int key = ic.d * 0x40000000 + ic.slot;
+        if (key != cur_key) {
+            __syncthreads();
+            cur_key = key;
+            stage_weights<R, VEC, REPS>(D, ic.b, px0, p.HW, wsm, tid);
             __syncthreads();
         }
-
-        // ---- accumulate CG channels x R rows over this thread's pixels ------------------------------
         float acc[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) acc[i] = 0.f;
-        const int c0 = grp * CG;
-        const float* xb = D.feat + ((size_t)b * p.C + c0) * p.HW + px0;
+        const int c0 = ic.grp * CG;
+        const float* xb = D.feat + ((size_t)ic.b * p.C + c0) * p.HW + px0;
 #pragma unroll
         for (int rep = 0; rep < REPS; ++rep) {
             const int off = (rep * kThreads + tid) * VEC;
@@ -118,78 +204,131 @@ __global__ void __launch_bounds__(kThreads, 2) pool_fwd_kernel(const PoolParams 
             Pack<VEC> x[CG];
 #pragma unroll
             for (int j = 0; j < CG; ++j) {
-                if (ok && c0 + j < p.C) x[j] = ld_stream<VEC>(xb + (size_t)j * p.HW + off);
-                else {
 #pragma unroll
-                    for (int v = 0; v < VEC; ++v) x[j].v[v] = 0.f;
-                }
+                for (int v = 0; v < VEC; ++v) x[j].v[v] = 0.f;
+                if (ok && c0 + j < p.C) x[j] = ld_stream<VEC>(xb + (size_t)j * p.HW + off);
             }
             Pack<VEC> w[R];
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                if constexpr (VEC == 4) {
-                    const float4 t = *reinterpret_cast<const float4*>(wsm + r * PX + off);
-                    w[r].v[0] = t.x; w[r].v[1] = t.y; w[r].v[2] = t.z; w[r].v[3] = t.w;
-                } else {
-                    w[r].v[0] = wsm[r * PX + off];
-                }
-            }
+            for (int r = 0; r < R; ++r) w[r] = lds_pack<VEC>(wsm + r * PX + off);
 #pragma unroll
             for (int j = 0; j < CG; ++j)
 #pragma unroll
                 for (int r = 0; r < R; ++r)
 #pragma unroll
-                    for (int v = 0; v < VEC; ++v)
-                        acc[j * R + r] = fmaf(x[j].v[v], w[r].v[v], acc[j * R + r]);
+                    for (int v = 0; v < VEC; ++v) acc[j * R + r] = fmaf(x[j].v[v], w[r].v[v], acc[j * R + r]);
         }
-        // the item that owns channel group 0 also sums this chunk's weights (padding is staged as 0)
-        float nsum[R];
-        if (grp == 0) {
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                float s = 0.f;
-#pragma unroll
-                for (int rep = 0; rep < REPS; ++rep) {
-                    const int off = (rep * kThreads + tid) * VEC;
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v) s += wsm[r * PX + off + v];
-                }
-                nsum[r] = s;
-            }
-        }
+        float* out = D.partial + (size_t)ic.slot * R * (p.C + 1);
+        reduce_and_store<R, CG, VEC, REPS>(acc, wsm, red, parity, out, p.C, c0, ic.grp == 0, tid, sync);
+    }
+}
 
-        // ---- CTA reduction: butterfly inside the warp, shared memory across warps -------------------
-        const float tot = warp_sum_transpose32(acc, lane);
-        float* redp = red + parity * (kWarps * 32);
-        redp[warp * 32 + lane] = tot;
-        __syncthreads();
-        float* out = D.partial + (size_t)slot * R * (p.C + 1);
-        if (warp == 0) {
-            float s = 0.f;
-#pragma unroll
-            for (int wq = 0; wq < kWarps; ++wq) s += redp[wq * 32 + lane];
-            const int j = lane / R, r = lane - j * R;
-            if (j < CG && c0 + j < p.C) out[(size_t)r * (p.C + 1) + c0 + j] = s;
-        }
-        parity ^= 1;
+// ------------------------------------------------------------------------------------------------
+// TMA path: warp 8 = producer (bulk async copies into a ring of `stages` buffers), warps 0-7 = compute
+// ------------------------------------------------------------------------------------------------
+constexpr int kPoolTmaThreads = kThreads + 32;
+constexpr int kMaxStages = 8;
 
-        if (grp == 0) {   // CTA-uniform branch
-#pragma unroll
-            for (int r = 0; r < R; ++r) nsum[r] = warp_sum(nsum[r]);
-            float* redn = red + parity * (kWarps * 32);
-            if (lane == 0) {
-#pragma unroll
-                for (int r = 0; r < R; ++r) redn[warp * 32 + r] = nsum[r];
+template <int R>
+struct PoolTmaSmem {
+    static constexpr int CG = pool_cg(R), REPS = pool_reps(R), PX = kThreads * 4 * REPS;
+    static constexpr size_t stage_bytes = sizeof(float) * CG * PX;
+    static constexpr size_t w_bytes = sizeof(float) * R * PX;
+    static constexpr size_t red_bytes = sizeof(float) * 2 * kWarps * 32;
+    static constexpr size_t bar_bytes = sizeof(uint64_t) * 2 * kMaxStages;
+    static size_t total(int stages) { return stages * stage_bytes + w_bytes + red_bytes + bar_bytes; }
+};
+
+template <int R>
+__global__ void __launch_bounds__(kPoolTmaThreads, 1) pool_fwd_tma_kernel(const PoolParams p) {
+    using SM = PoolTmaSmem<R>;
+    constexpr int CG = SM::CG, REPS = SM::REPS, PX = SM::PX, VEC = 4;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* xs = reinterpret_cast<float*>(smem_raw);                                    // [stages][CG][PX]
+    float* wsm = reinterpret_cast<float*>(smem_raw + p.stages * SM::stage_bytes);      // [R][PX]
+    float* red = wsm + R * PX;                                                         // [2][kWarps][32]
+    uint64_t* full = reinterpret_cast<uint64_t*>(red + 2 * kWarps * 32);               // [kMaxStages]
+    uint64_t* empty = full + kMaxStages;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kWarps); }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    int begin, end;
+    partition(p.total, gridDim.x, blockIdx.x, begin, end);
+
+    if (warp == kWarps) {
+        // ---------------- producer ----------------
+        if (lane == 0) {
+            const uint64_t pol = policy_evict_first();
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int it = begin; it < end; ++it) {
+                const ItemCoord ic = decode_item(p, it);
+                const PoolDom& D = p.dom[ic.d];
+                const int px0 = ic.chunk * PX, c0 = ic.grp * CG;
+                const int rows = (p.C - c0) < CG ? (p.C - c0) : CG;
+                const int npx = (p.HW - px0) < PX ? (p.HW - px0) : PX;
+                mbar_wait(&empty[stage], phase ^ 1u);
+                mbar_arrive_expect_tx(&full[stage], (uint32_t)(rows * npx * sizeof(float)));
+                const float* src = D.feat + ((size_t)ic.b * p.C + c0) * p.HW + px0;
+                float* dst = xs + (size_t)stage * CG * PX;
+                for (int j = 0; j < rows; ++j)
+                    bulk_g2s(dst + j * PX, src + (size_t)j * p.HW, (uint32_t)(npx * sizeof(float)), &full[stage], pol);
+                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
-            __syncthreads();
-            if (warp == 0 && lane < R) {
-                float s = 0.f;
-#pragma unroll
-                for (int wq = 0; wq < kWarps; ++wq) s += redn[wq * 32 + lane];
-                out[(size_t)lane * (p.C + 1) + p.C] = s;
-            }
-            parity ^= 1;
         }
+        return;
+    }
+
+    // ---------------- consumers (256 threads) ----------------
+    auto sync = [] { named_bar_sync(1, kThreads); };
+    int cur_key = -1, parity = 0, stage = 0;
+    uint32_t phase = 0;
+    for (int it = begin; it < end; ++it) {
+        const ItemCoord ic = decode_item(p, it);
+        const PoolDom& D = p.dom[ic.d];
+        const int px0 = ic.chunk * PX;
+        const int key = ic.d * 0x40000000 + ic.slot;
+        if (key != cur_key) {
+            sync();
+            cur_key = key;
+            stage_weights<R, VEC, REPS>(D, ic.b, px0, p.HW, wsm, tid);
+            sync();
+        }
+        float acc[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+        const int c0 = ic.grp * CG;
+        const float* xst = xs + (size_t)stage * CG * PX;
+        mbar_wait(&full[stage], phase);
+#pragma unroll
+        for (int rep = 0; rep < REPS; ++rep) {
+            const int off = (rep * kThreads + tid) * VEC;
+            const bool ok = px0 + off < p.HW;   // bytes past the copied span are stale: never read them
+            Pack<VEC> w[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) w[r] = lds_pack<VEC>(wsm + r * PX + off);
+#pragma unroll
+            for (int j = 0; j < CG; ++j) {
+                Pack<VEC> x;
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) x.v[v] = 0.f;
+                if (ok && c0 + j < p.C) x = lds_pack<VEC>(xst + j * PX + off);
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) acc[j * R + r] = fmaf(x.v[v], w[r].v[v], acc[j * R + r]);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);   // this warp is done with the stage: producer may refill
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        float* out = D.partial + (size_t)ic.slot * R * (p.C + 1);
+        reduce_and_store<R, CG, VEC, REPS>(acc, wsm, red, parity, out, p.C, c0, ic.grp == 0, tid, sync);
     }
 }
 
@@ -221,68 +360,94 @@ __global__ void proto_finalize_kernel(const float* __restrict__ sums, int R, int
     mu[i] = sums[(size_t)r * (C + 1) + c] / sums[(size_t)r * (C + 1) + C];   // 0/0 -> NaN, as the reference
 }
 
-template <int K, int VEC>
-static int launch_pool(const PoolParams& p, cudaStream_t st) {
-    using Cfg = PoolCfg<K, VEC>;
-    static int occ_cache = 0;   // benign race
-    auto kern = pool_fwd_kernel<K, VEC>;
-    if (occ_cache == 0) {
-        CLR_RETURN_IF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
-        int occ = 0;
-        CLR_RETURN_IF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, Cfg::SMEM_BYTES));
-        occ_cache = occ > 0 ? occ : 1;
-    }
-    int grid = device_facts().sms * occ_cache;
+static void launch_reduce(const PoolParams& p, int R, cudaStream_t st) {
+    const int n = R * (p.C + 1);
+    pool_reduce_kernel<<<dim3((n + 31) / 32, p.ndom), dim3(32, 8), 0, st>>>(p, R);
+}
+
+template <int R, int VEC>
+static int launch_ldg(const PoolParams& p, cudaStream_t st) {
+    constexpr int PX = kThreads * VEC * pool_reps(R);
+    constexpr size_t smem = sizeof(float) * (R * PX + 2 * kWarps * 32);
+    auto kern = pool_fwd_ldg_kernel<R, VEC>;
+    CLR_RETURN_IF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CLR_RETURN_IF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem));
+    if (occ < 1) occ = 1;
+    int grid = device_facts().sms * occ;
     if (grid > p.total) grid = p.total;
-    kern<<<grid, kThreads, Cfg::SMEM_BYTES, st>>>(p);
-    const int n = 2 * K * (p.C + 1);
-    pool_reduce_kernel<<<dim3((n + 31) / 32, p.ndom), dim3(32, 8), 0, st>>>(p, 2 * K);
+    kern<<<grid, kThreads, smem, st>>>(p);
+    launch_reduce(p, R, st);
     return launch_status();
 }
 
-template <int VEC>
-static int dispatch_k(int K, const PoolParams& p, cudaStream_t st) {
-    switch (K) {
-        case 1: return launch_pool<1, VEC>(p, st);
-        case 2: return launch_pool<2, VEC>(p, st);
-        case 3: return launch_pool<3, VEC>(p, st);
-        case 4: return launch_pool<4, VEC>(p, st);
-        case 5: return launch_pool<5, VEC>(p, st);
-        case 6: return launch_pool<6, VEC>(p, st);
-        case 7: return launch_pool<7, VEC>(p, st);
-        case 8: return launch_pool<8, VEC>(p, st);
+template <int R>
+static int launch_tma(PoolParams p, cudaStream_t st) {
+    using SM = PoolTmaSmem<R>;
+    const size_t budget = (size_t)device_facts().max_smem_optin;
+    int stages = tunables().pool_stages > 0 ? tunables().pool_stages : 4;
+    if (stages > kMaxStages) stages = kMaxStages;
+    while (stages > 1 && SM::total(stages) > budget) --stages;
+    if (SM::total(stages) > budget) return CLR_ERR_UNSUPPORTED;
+    p.stages = stages;
+    const size_t smem = SM::total(stages);
+    auto kern = pool_fwd_tma_kernel<R>;
+    CLR_RETURN_IF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CLR_RETURN_IF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kPoolTmaThreads, smem));
+    if (occ < 1) occ = 1;
+    int grid = device_facts().sms * occ;
+    if (grid > p.total) grid = p.total;
+    kern<<<grid, kPoolTmaThreads, smem, st>>>(p);
+    launch_reduce(p, R, st);
+    return launch_status();
+}
+
+static int dispatch(int R, bool vec4, bool tma, const PoolParams& p, cudaStream_t st) {
+    switch (R) {
+#define CLR_CASE(r) case r: return tma ? launch_tma<r>(p, st) : (vec4 ? launch_ldg<r, 4>(p, st) : launch_ldg<r, 1>(p, st));
+        CLR_CASE(1) CLR_CASE(2) CLR_CASE(3) CLR_CASE(4) CLR_CASE(5) CLR_CASE(6) CLR_CASE(7) CLR_CASE(8)
+        CLR_CASE(9) CLR_CASE(10) CLR_CASE(11) CLR_CASE(12) CLR_CASE(13) CLR_CASE(14) CLR_CASE(15) CLR_CASE(16)
+#undef CLR_CASE
     }
     return CLR_ERR_UNSUPPORTED;
 }
 
-static int chunk_px(int K, int vec) { return kThreads * vec * (K <= 2 ? 2 : 1); }
+static int chunk_px(int R, int vec) { return kThreads * vec * pool_reps(R); }
 
-// Workspace: partials for up to two domains, sized for the scalar (smallest-chunk) path.
-static size_t partial_floats(int B, int C, int HW, int K) {
-    const int px = chunk_px(K, 1);
+// Workspace: partials for one domain, sized for the scalar (smallest-chunk) path.
+static size_t partial_floats(int B, int C, int HW, int R) {
+    const int px = chunk_px(R, 1);
     const size_t slots = (size_t)B * ((HW + px - 1) / px);
-    return slots * 2 * K * (C + 1);
+    return slots * R * (C + 1);
 }
 
+size_t pool_partial_bytes(int B, int C, int HW, int R) { return sizeof(float) * partial_floats(B, C, HW, R); }
+
+// R = number of output rows (2K for the prototype formats; any 1..16 for explicit rows).
 int pool_fwd_impl(const float* feat0, const float* w0, int fmt0, int B0, float* sums0,
                   const float* feat1, const float* w1, int fmt1, int B1, float* sums1,
-                  int C, int HW, int K, void* ws, size_t ws_bytes, cudaStream_t st) {
+                  int C, int HW, int R, void* ws, size_t ws_bytes, cudaStream_t st) {
     const int ndom = feat1 ? 2 : 1;
-    CLR_CHECK_ARG(feat0 && w0 && sums0 && ws && B0 > 0 && C > 0 && HW > 0 && K >= 1 && K <= CLR_MAX_K);
+    CLR_CHECK_ARG(feat0 && w0 && sums0 && ws && B0 > 0 && C > 0 && HW > 0 && R >= 1 && R <= 2 * CLR_MAX_K);
     CLR_CHECK_ARG(fmt0 == CLR_W_COMPLEMENT || fmt0 == CLR_W_EXPLICIT);
-    if (ndom == 2) CLR_CHECK_ARG(w1 && sums1 && B1 > 0 && (fmt1 == CLR_W_COMPLEMENT || fmt1 == CLR_W_EXPLICIT));
+    CLR_CHECK_ARG(fmt0 != CLR_W_COMPLEMENT || R % 2 == 0);
+    if (ndom == 2) {
+        CLR_CHECK_ARG(w1 && sums1 && B1 > 0 && (fmt1 == CLR_W_COMPLEMENT || fmt1 == CLR_W_EXPLICIT));
+        CLR_CHECK_ARG(fmt1 != CLR_W_COMPLEMENT || R % 2 == 0);
+    }
     if (!aligned4(feat0) || !aligned4(w0) || (feat1 && (!aligned4(feat1) || !aligned4(w1)))) return CLR_ERR_ALIGN;
-    // the partition index is an int; the per-element offsets are size_t
-    bool vec4 = (HW % 4 == 0) && aligned16(feat0) && aligned16(w0) && (!feat1 || (aligned16(feat1) && aligned16(w1)));
+    const bool vec4 = (HW % 4 == 0) && aligned16(feat0) && aligned16(w0) && (!feat1 || (aligned16(feat1) && aligned16(w1)));
+    const bool tma = vec4 && tunables().pool_impl != 1;
     const int vec = vec4 ? 4 : 1;
-    const int px = chunk_px(K, vec);
-    const int CG = 32 / (2 * K);
+    const int px = chunk_px(R, vec);
+    const int CG = pool_cg(R);
 
     PoolParams p{};
     p.ndom = ndom; p.C = C; p.HW = HW;
     p.nChunk = (HW + px - 1) / px;
     p.nGroup = (C + CG - 1) / CG;
-    const size_t need = sizeof(float) * (partial_floats(B0, C, HW, K) + (ndom == 2 ? partial_floats(B1, C, HW, K) : 0));
+    const size_t need = sizeof(float) * (partial_floats(B0, C, HW, R) + (ndom == 2 ? partial_floats(B1, C, HW, R) : 0));
     if (ws_bytes < need) return CLR_ERR_WORKSPACE;
     float* wsf = static_cast<float*>(ws);
     const long long items0 = (long long)B0 * p.nChunk * p.nGroup;
@@ -290,9 +455,9 @@ int pool_fwd_impl(const float* feat0, const float* w0, int fmt0, int B0, float* 
     if (items0 + items1 > 0x3fffffff) return CLR_ERR_UNSUPPORTED;
     p.dom[0] = PoolDom{feat0, w0, wsf, sums0, B0, fmt0, (int)items0, B0 * p.nChunk};
     if (ndom == 2)
-        p.dom[1] = PoolDom{feat1, w1, wsf + partial_floats(B0, C, HW, K), sums1, B1, fmt1, (int)items1, B1 * p.nChunk};
+        p.dom[1] = PoolDom{feat1, w1, wsf + partial_floats(B0, C, HW, R), sums1, B1, fmt1, (int)items1, B1 * p.nChunk};
     p.total = (int)(items0 + items1);
-    return vec4 ? dispatch_k<4>(K, p, st) : dispatch_k<1>(K, p, st);
+    return dispatch(R, vec4, tma, p, st);
 }
 
 }  // namespace clr
@@ -301,12 +466,24 @@ extern "C" {
 
 size_t clr_pool_ws_bytes(int B, int C, int HW, int K) {
     if (B <= 0 || C <= 0 || HW <= 0 || K < 1 || K > CLR_MAX_K) return 0;
-    return sizeof(float) * clr::partial_floats(B, C, HW, K);
+    return sizeof(float) * clr::partial_floats(B, C, HW, 2 * K);
+}
+
+size_t clr_pool_rows_ws_bytes(int B, int C, int HW, int R) {
+    if (B <= 0 || C <= 0 || HW <= 0 || R < 1 || R > 2 * CLR_MAX_K) return 0;
+    return sizeof(float) * clr::partial_floats(B, C, HW, R);
+}
+
+int clr_pool_rows_fwd(const float* feat, const float* rows, int B, int C, int HW, int R,
+                      void* ws, size_t ws_bytes, float* sums, clr_stream_t stream) {
+    return clr::pool_fwd_impl(feat, rows, CLR_W_EXPLICIT, B, sums, nullptr, nullptr, 0, 0, nullptr, C, HW, R, ws, ws_bytes,
+                              static_cast<cudaStream_t>(stream));
 }
 
 int clr_pool_fwd(const float* feat, const float* w, int fmt, int B, int C, int HW, int K,
                  void* ws, size_t ws_bytes, float* sums, clr_stream_t stream) {
-    return clr::pool_fwd_impl(feat, w, fmt, B, sums, nullptr, nullptr, 0, 0, nullptr, C, HW, K, ws, ws_bytes,
+    if (K < 1 || K > CLR_MAX_K) return CLR_ERR_BAD_ARG;
+    return clr::pool_fwd_impl(feat, w, fmt, B, sums, nullptr, nullptr, 0, 0, nullptr, C, HW, 2 * K, ws, ws_bytes,
                               static_cast<cudaStream_t>(stream));
 }
 
@@ -314,8 +491,8 @@ int clr_pool_fwd2(const float* feat0, const float* w0, int fmt0, int B0,
                   const float* feat1, const float* w1, int fmt1, int B1,
                   int C, int HW, int K, void* ws, size_t ws_bytes,
                   float* sums0, float* sums1, clr_stream_t stream) {
-    if (!feat1) return CLR_ERR_BAD_ARG;
-    return clr::pool_fwd_impl(feat0, w0, fmt0, B0, sums0, feat1, w1, fmt1, B1, sums1, C, HW, K, ws, ws_bytes,
+    if (!feat1 || K < 1 || K > CLR_MAX_K) return CLR_ERR_BAD_ARG;
+    return clr::pool_fwd_impl(feat0, w0, fmt0, B0, sums0, feat1, w1, fmt1, B1, sums1, C, HW, 2 * K, ws, ws_bytes,
                               static_cast<cudaStream_t>(stream));
 }
 

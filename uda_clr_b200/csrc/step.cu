@@ -1,0 +1,159 @@
+// The fused CLR step: host-side orchestration of the kernels (no device code of its own).
+//
+// What the reference runs as ~150 eager ATen launches and ~25 passes over each [B,C,H,W] feature map per
+// step (Trainer_prototype_full.py:328-449 plus the two bytecode-only losses) becomes:
+//   forward : 1 read of xs + 1 read of xt (pooling, one launch) + 1 more read of xs (discriminative)
+//   backward: 1 write of gxs + 1 write of gxt (one launch)
+// plus O(K*C) glue kernels, with no host synchronisation (.item()) anywhere.
+#include "clr_common.cuh"
+#include "clr_internal.h"
+
+namespace clr {
+
+struct StepWs {
+    char* pool;        size_t pool_bytes;
+    char* rows;        size_t rows_bytes;
+    float* hinge;      size_t hinge_bytes;
+    double* cons;      size_t cons_bytes;
+    size_t total;
+};
+
+static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static StepWs carve(const clr_step_args* a) {
+    StepWs w{};
+    const int HW = a->H * a->W;
+    w.pool_bytes = align_up(pool_partial_bytes(a->B_s, a->C, HW, 2 * a->K) + pool_partial_bytes(a->B_t, a->C, HW, 2 * a->K));
+    w.rows_bytes = a->use_disc ? align_up(pool_partial_bytes(a->B_s, a->C, HW, a->K)) : 0;
+    w.hinge_bytes = a->use_disc ? align_up(sizeof(float) * (size_t)clr_disc_partials_cap() * (1 + a->K)) : 0;
+    w.cons_bytes = a->use_cons ? align_up(clr_cons_ws_bytes()) : 0;
+    char* base = static_cast<char*>(a->ws);
+    size_t off = 0;
+    w.pool = base + off; off += w.pool_bytes;
+    w.rows = base + off; off += w.rows_bytes;
+    w.hinge = reinterpret_cast<float*>(base + off); off += w.hinge_bytes;
+    w.cons = reinterpret_cast<double*>(base + off); off += w.cons_bytes;
+    w.total = off;
+    return w;
+}
+
+static int check_args(const clr_step_args* a) {
+    CLR_CHECK_ARG(a && a->B_s > 0 && a->B_t > 0 && a->C > 0 && a->H > 0 && a->W > 0 && a->K >= 1 && a->K <= CLR_MAX_K);
+    CLR_CHECK_ARG(a->xs && a->ys && a->xt && a->packed1 && a->packed2 && a->P_s && a->P_t && a->g_s && a->g_t &&
+                  a->losses && a->stored_s && a->stored_t && a->ws);
+    if (a->use_retrify)
+        CLR_CHECK_ARG(a->oT_before && a->preds && a->std_map && a->pred_mean && a->wt_retrify && a->masks &&
+                      a->Hi > 0 && a->Wi > 0 && a->T >= 1);
+    else
+        CLR_CHECK_ARG(a->wt != nullptr);
+    if (a->use_disc) CLR_CHECK_ARG(a->disc_coef && a->disc_vec && a->disc_beta && a->xtab && a->npx_global > 0);
+    if (a->use_cons) CLR_CHECK_ARG(a->oT && a->oT_aug && a->Hi > 0 && a->Wi > 0 && (a->use_retrify || a->masks));
+    if (a->ws_bytes < carve(a).total) return CLR_ERR_WORKSPACE;
+    return CLR_OK;
+}
+
+static const float* target_weights(const clr_step_args* a) { return a->use_retrify ? a->wt_retrify : a->wt; }
+static int target_fmt(const clr_step_args* a) { return a->use_retrify ? CLR_W_EXPLICIT : a->wt_fmt; }
+
+}  // namespace clr
+
+extern "C" {
+
+size_t clr_step_ws_bytes(const clr_step_args* a) {
+    if (!a) return 0;
+    clr_step_args tmp = *a;
+    tmp.ws = nullptr;
+    return clr::carve(&tmp).total;
+}
+
+int clr_step_fwd_a(const clr_step_args* a, clr_stream_t stream) {
+    int rc = clr::check_args(a);
+    if (rc != CLR_OK) return rc;
+    const clr::StepWs w = clr::carve(a);
+    const int HW = a->H * a->W, R = 2 * a->K;
+    if (a->use_retrify) {
+        rc = clr_mc_stats(a->preds, a->T, a->B_t, a->K, a->Hi, a->Wi, a->std_map, a->pred_mean, stream);
+        if (rc != CLR_OK) return rc;
+        rc = clr_retrify_weights(a->oT_before, a->pred_mean, a->std_map, a->B_t, a->K, a->H, a->W, a->Hi, a->Wi,
+                                 a->pseudo_thr, a->std_thr, a->wt_retrify, a->masks, nullptr, nullptr, stream);
+        if (rc != CLR_OK) return rc;
+    }
+    float* sums_s = a->packed1;
+    float* sums_t = a->packed1 + (size_t)R * (a->C + 1);
+    return clr::pool_fwd_impl(a->xs, a->ys, CLR_W_COMPLEMENT, a->B_s, sums_s,
+                              a->xt, clr::target_weights(a), clr::target_fmt(a), a->B_t, sums_t,
+                              a->C, HW, R, w.pool, w.pool_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int clr_step_fwd_b(const clr_step_args* a, clr_stream_t stream) {
+    int rc = clr::check_args(a);
+    if (rc != CLR_OK) return rc;
+    const clr::StepWs w = clr::carve(a);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int HW = a->H * a->W, R = 2 * a->K, C = a->C, K = a->K;
+    const float* sums_s = a->packed1;
+    const float* sums_t = a->packed1 + (size_t)R * (C + 1);
+    rc = clr_align_finalize(sums_s, sums_t, K, C, a->stored_s, a->stored_t, a->first_s, a->first_t, a->decay,
+                            a->w_intra, a->w_inter, a->P_s, a->P_t, nullptr, nullptr, a->g_s, a->g_t,
+                            a->use_disc ? a->disc_vec : nullptr, a->use_disc ? a->disc_beta : nullptr, a->losses, stream);
+    if (rc != CLR_OK) return rc;
+    int n_hinge = 0, n_cons = 0;
+    if (a->use_cons) {
+        rc = clr::cons_fwd_partials(a->oT, a->oT_aug, a->masks, a->B_t, K, a->Hi, a->Wi, a->H, a->W,
+                                    a->cons_threshold, w.cons, &n_cons, st);
+        if (rc != CLR_OK) return rc;
+    }
+    if (a->use_disc) {
+        rc = clr::disc_fwd_impl(a->xs, a->ys, a->B_s, C, HW, K, a->disc_vec, a->disc_beta, a->margin,
+                                a->disc_coef, nullptr, w.hinge, clr_disc_partials_cap(), &n_hinge, st);
+        if (rc != CLR_OK) return rc;
+        rc = clr::pool_fwd_impl(a->xs, a->disc_coef, CLR_W_EXPLICIT, a->B_s, a->packed2, nullptr, nullptr, 0, 0, nullptr,
+                                C, HW, K, w.rows, w.rows_bytes, st);
+        if (rc != CLR_OK) return rc;
+    }
+    clr::launch_step_pack(a->use_disc ? w.hinge : nullptr, n_hinge, 1 + K, a->use_cons ? w.cons : nullptr, n_cons,
+                          a->packed2 + (size_t)K * (C + 1), st);
+    return clr::launch_status();
+}
+
+int clr_step_fwd_c(const clr_step_args* a, clr_stream_t stream) {
+    int rc = clr::check_args(a);
+    if (rc != CLR_OK) return rc;
+    const float ema = a->first_s ? 1.0f : (float)a->decay;
+    return clr_disc_finalize(a->packed2, a->P_s, a->K, a->C, a->npx_global, a->w_disc, ema, a->grad_scale,
+                             a->g_s, a->xtab, a->w_intra, a->w_inter, a->w_aug, a->aug_weight,
+                             a->use_disc, a->use_cons, a->losses, stream);
+}
+
+int clr_step_fwd(const clr_step_args* a, clr_stream_t stream) {
+    int rc = clr_step_fwd_a(a, stream);
+    if (rc != CLR_OK) return rc;
+    rc = clr_step_fwd_b(a, stream);
+    if (rc != CLR_OK) return rc;
+    return clr_step_fwd_c(a, stream);
+}
+
+int clr_step_bwd(const clr_step_args* a, clr_stream_t stream) {
+    int rc = clr::check_args(a);
+    if (rc != CLR_OK) return rc;
+    if (!a->gxs || !a->gxt) return CLR_ERR_BAD_ARG;
+    const int HW = a->H * a->W, R = 2 * a->K, C = a->C, K = a->K;
+    const float* sums_s = a->packed1;
+    const float* sums_t = a->packed1 + (size_t)R * (C + 1);
+    clr_bwd_dom d[2];
+    d[0] = clr_bwd_dom{a->ys, a->g_s, sums_s, a->use_disc ? a->disc_coef : nullptr, a->use_disc ? a->xtab : nullptr,
+                       a->gxs, a->gup, a->grad_scale, CLR_W_COMPLEMENT, a->B_s, a->use_disc ? K : 0};
+    d[1] = clr_bwd_dom{clr::target_weights(a), a->g_t, sums_t, nullptr, nullptr, a->gxt, a->gup, a->grad_scale,
+                       clr::target_fmt(a), a->B_t, 0};
+    rc = clr_pool_bwd_multi(d, 2, C, HW, K, stream);
+    if (rc != CLR_OK) return rc;
+    if (a->use_cons && a->w_aug != 0.f && a->g_oT_aug) {
+        // stats layout expected by clr_cons_bwd: [num, den, ...] = tail[1..2] of packed2
+        const float* stats = a->packed2 + (size_t)K * (C + 1);   // {hinge num, cons num, cons den}: den at [2]
+        rc = clr_cons_bwd(a->oT, a->oT_aug, a->masks, a->B_t, K, a->Hi, a->Wi, a->H, a->W, a->cons_threshold,
+                          a->aug_weight, stats + 1, a->gup, a->grad_scale * a->w_aug, a->g_oT_aug, stream);
+    }
+    return rc;
+}
+
+}  // extern "C"

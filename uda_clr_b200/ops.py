@@ -106,18 +106,18 @@ def _split_protos(mu: torch.Tensor) -> Tuple[torch.Tensor, ...]:
 
 # ----------------------------------------------------------------------------------------------- A1 / A3
 class _WeightedPrototypes(torch.autograd.Function):
-    """``mu_r = sum x w_r / sum w_r`` for one or two concatenated domains.
+    """``mu_r = sum x w_r / sum w_r`` over one or two domains whose sums are added before the divide
+    (utils/Utils.py:132-158, :227-311).
 
-    inputs: (fmt, K, n_dom, w_0, feat_0[, w_1, feat_1]); outputs: 2K tensors ``[1,C,1,1]``.
-    With two domains the sums are added before the divide (utils/Utils.py:132-158, :227-311).
+    inputs: (K, fmts, w_0, feat_0[, w_1, feat_1]); outputs: 2K tensors ``[1,C,1,1]``.
     """
 
     @staticmethod
-    def forward(ctx, fmt: int, K: int, *tensors):
+    def forward(ctx, K: int, fmts, *tensors):
         n_dom = len(tensors) // 2
         ws, feats = tensors[0::2], tensors[1::2]
         sums = None
-        for w, f in zip(ws, feats):
+        for w, f, fmt in zip(ws, feats, fmts):
             s = pool_sums(f, w, fmt, K)
             sums = s if sums is None else sums + s
         scale = 1.0
@@ -125,7 +125,7 @@ class _WeightedPrototypes(torch.autograd.Function):
             _dist.all_reduce_sums(sums)
             scale = _dist.grad_scale()
         mu = protos_from_sums(sums)
-        ctx.fmt, ctx.K, ctx.n_dom, ctx.scale = fmt, K, n_dom, scale
+        ctx.fmts, ctx.K, ctx.n_dom, ctx.scale = tuple(fmts), K, n_dom, scale
         ctx.shapes = [tuple(f.shape) for f in feats]
         need_w = [ctx.needs_input_grad[2 + 2 * i] for i in range(n_dom)]
         ctx.save_for_backward(sums, *ws, *[f if nw else None for f, nw in zip(feats, need_w)])
@@ -135,16 +135,16 @@ class _WeightedPrototypes(torch.autograd.Function):
     def backward(ctx, *grads):
         saved = ctx.saved_tensors
         sums, ws, feats = saved[0], saved[1:1 + ctx.n_dom], saved[1 + ctx.n_dom:]
-        K, fmt = ctx.K, ctx.fmt
+        K = ctx.K
         C = ctx.shapes[0][1]
         g = _stack_grads(grads, 2 * K, C, sums.device)
         out = [None, None]
         for i in range(ctx.n_dom):
             gw = gf = None
             if ctx.needs_input_grad[2 + 2 * i]:
-                gw = pool_backward_weights(feats[i], fmt, K, g, sums, ctx.scale)
+                gw = pool_backward_weights(feats[i], ctx.fmts[i], K, g, sums, ctx.scale)
             if ctx.needs_input_grad[3 + 2 * i]:
-                gf = pool_backward_feat(ws[i], fmt, K, ctx.shapes[i], g, sums, ctx.scale)
+                gf = pool_backward_feat(ws[i], ctx.fmts[i], K, ctx.shapes[i], g, sums, ctx.scale)
             out += [gw, gf]
         return tuple(out)
 
@@ -162,7 +162,7 @@ def gen_prototype(pred_oS: torch.Tensor, xs_feature: torch.Tensor):
     _check_k(K)
     if pred.shape[0] != feat.shape[0] or pred.shape[2:] != feat.shape[2:]:
         raise ValueError("pred_oS %s and xs_feature %s disagree" % (tuple(pred.shape), tuple(feat.shape)))
-    return _WeightedPrototypes.apply(CLR_W_COMPLEMENT, K, pred, feat)
+    return _WeightedPrototypes.apply(K, (CLR_W_COMPLEMENT,), pred, feat)
 
 
 def gen_prototype_src_trg(pred_oS, xs_feature, pred_oT, xt_feature):
@@ -174,7 +174,7 @@ def gen_prototype_src_trg(pred_oS, xs_feature, pred_oT, xt_feature):
     _check_k(K)
     if pt.shape[1] != K or fs.shape[1] != ft.shape[1]:
         raise ValueError("source and target disagree on K or C")
-    return _WeightedPrototypes.apply(CLR_W_COMPLEMENT, K, ps, fs, pt, ft)
+    return _WeightedPrototypes.apply(K, (CLR_W_COMPLEMENT, CLR_W_COMPLEMENT), ps, fs, pt, ft)
 
 
 def weighted_prototypes(weights: torch.Tensor, feat: torch.Tensor):
@@ -185,7 +185,181 @@ def weighted_prototypes(weights: torch.Tensor, feat: torch.Tensor):
         raise ValueError("explicit weights need 2K planes")
     K = w.shape[1] // 2
     _check_k(K)
-    return _WeightedPrototypes.apply(CLR_W_EXPLICIT, K, w, f)
+    return _WeightedPrototypes.apply(K, (CLR_W_EXPLICIT,), w, f)
+
+
+# ----------------------------------------------------------------------------------------------- A2
+PSEUDO_THRESHOLD = 0.75   # utils/Utils.py:176
+STD_THRESHOLD = 0.04      # utils/Utils.py:197
+
+
+def mc_statistics(preds: torch.Tensor, T: int, stride: int):
+    """``std_T(sigmoid(p/2))`` (unbiased) and ``mean_T(sigmoid(p))`` of ``preds [T*stride,K,Hi,Wi]``
+    (utils/Utils.py:161-168) -> two ``[stride,K,Hi,Wi]`` maps.  One read of ``preds``."""
+    lib = _lib.load()
+    p = _require_cuda_f32(preds, "preds")
+    if p.shape[0] != T * stride:
+        raise ValueError("preds has %d maps, expected T*stride = %d" % (p.shape[0], T * stride))
+    _, K, Hi, Wi = p.shape
+    std_map = torch.empty(stride, K, Hi, Wi, dtype=torch.float32, device=p.device)
+    pred_mean = torch.empty_like(std_map)
+    with torch.cuda.device(p.device):
+        check(lib.clr_mc_stats(ptr(p), T, stride, K, Hi, Wi, ptr(std_map), ptr(pred_mean), _stream()), "clr_mc_stats")
+    return std_map, pred_mean
+
+
+def retrify_weights(oT_before: torch.Tensor, pred_mean: torch.Tensor, std_map: torch.Tensor, H: int, W: int,
+                    pseudo_thr: float = PSEUDO_THRESHOLD, std_thr: float = STD_THRESHOLD, debug: bool = False):
+    """Explicit target weights ``[B,2K,H,W]`` and uncertainty masks ``[B,K,H,W]`` in {0,2}
+    (utils/Utils.py:170-223).  ``debug=True`` also returns the pseudo-labels and the two down-sampled maps."""
+    lib = _lib.load()
+    o = _require_cuda_f32(oT_before, "oT_before")
+    B, K = o.shape[:2]
+    Hi, Wi = pred_mean.shape[2:]
+    weights = torch.empty(B, 2 * K, H, W, dtype=torch.float32, device=o.device)
+    masks = torch.empty(B, K, H, W, dtype=torch.float32, device=o.device)
+    pseudo = torch.empty(B, K, H, W, dtype=torch.float32, device=o.device) if debug else None
+    small = torch.empty(2, B, K, H, W, dtype=torch.float32, device=o.device) if debug else None
+    with torch.cuda.device(o.device):
+        check(lib.clr_retrify_weights(ptr(o), ptr(pred_mean), ptr(std_map), B, K, H, W, Hi, Wi,
+                                      float(pseudo_thr), float(std_thr), ptr(weights), ptr(masks),
+                                      ptr(pseudo), ptr(small), _stream()), "clr_retrify_weights")
+    if debug:
+        return weights, masks, pseudo, small
+    return weights, masks
+
+
+class _RetrifyPrototypes(torch.autograd.Function):
+    """A2 end to end; optional joint source domain (A3 retrify variant, utils/Utils.py:227-311).
+
+    inputs: (T, stride, oT_before, xt_feature, preds[, pred_oS, xs_feature])
+    outputs: 2K prototypes, std_map, K masks.
+    Gradients: to xt_feature (and xs_feature / pred_oS in the joint form); oT_before receives exact zeros,
+    as in the reference where the clone + masked fills cut the graph (utils/Utils.py:175-177).
+    """
+
+    @staticmethod
+    def forward(ctx, T, stride, oT_before, xt_feature, preds, pred_oS=None, xs_feature=None):
+        K = oT_before.shape[1]
+        H, W = xt_feature.shape[2:]
+        std_map, pred_mean = mc_statistics(preds, T, stride)
+        weights, masks = retrify_weights(oT_before, pred_mean, std_map, H, W)
+        sums = pool_sums(xt_feature, weights, CLR_W_EXPLICIT, K)
+        joint = xs_feature is not None
+        if joint:
+            sums = sums + pool_sums(xs_feature, pred_oS, CLR_W_COMPLEMENT, K)
+        scale = 1.0
+        if _dist.enabled():
+            _dist.all_reduce_sums(sums)
+            scale = _dist.grad_scale()
+        mu = protos_from_sums(sums)
+        ctx.K, ctx.scale, ctx.joint = K, scale, joint
+        ctx.n_in = 7 if joint else 5
+        ctx.t_shape = tuple(xt_feature.shape)
+        ctx.s_shape = tuple(xs_feature.shape) if joint else None
+        ctx.o_shape = tuple(oT_before.shape)
+        need_ps = joint and ctx.needs_input_grad[5]
+        ctx.save_for_backward(sums, weights, pred_oS if joint else None, xs_feature if need_ps else None)
+        mask_list = tuple(masks[:, k:k + 1] for k in range(K))
+        ctx.mark_non_differentiable(std_map, *mask_list)
+        return _split_protos(mu) + (std_map,) + mask_list
+
+    @staticmethod
+    def backward(ctx, *grads):
+        sums, weights, pred_oS, xs_feature = ctx.saved_tensors
+        K = ctx.K
+        C = ctx.t_shape[1]
+        g = _stack_grads(grads, 2 * K, C, sums.device)
+        g_oT = torch.zeros(ctx.o_shape, dtype=torch.float32, device=sums.device) if ctx.needs_input_grad[2] else None
+        g_xt = None
+        if ctx.needs_input_grad[3]:
+            g_xt = pool_backward_feat(weights, CLR_W_EXPLICIT, K, ctx.t_shape, g, sums, ctx.scale)
+        g_ps = g_xs = None
+        if ctx.joint:
+            if ctx.needs_input_grad[5]:
+                g_ps = pool_backward_weights(xs_feature, CLR_W_COMPLEMENT, K, g, sums, ctx.scale)
+            if ctx.needs_input_grad[6]:
+                g_xs = pool_backward_feat(pred_oS, CLR_W_COMPLEMENT, K, ctx.s_shape, g, sums, ctx.scale)
+        return (None, None, g_oT, g_xt, None, g_ps, g_xs)[:ctx.n_in]
+
+
+def _retrify_inputs(oT_before, xt_feature, preds, T, stride):
+    o = _require_cuda_f32(oT_before, "oT_before")
+    x = _require_cuda_f32(xt_feature, "xt_feature")
+    p = _require_cuda_f32(preds, "preds")
+    K = o.shape[1]
+    _check_k(K)
+    if o.shape[0] != x.shape[0] or o.shape[2:] != x.shape[2:] or p.shape[1] != K or stride != x.shape[0]:
+        raise ValueError("gen_prototype_retrify: inconsistent shapes oT_before %s, xt_feature %s, preds %s, stride %d"
+                         % (tuple(o.shape), tuple(x.shape), tuple(p.shape), stride))
+    return o, x, p
+
+
+def gen_prototype_retrify(oT_before, xt_feature, preds, features, T, stride):
+    """Drop-in for ``utils.Utils.gen_prototype_retrify`` (utils/Utils.py:159-225).
+
+    Returns ``(c0_obj, c1_obj, c0_bck, c1_bck, std_map, mask_0, mask_1)`` for K = 2.  ``features`` is
+    accepted and ignored: the reference averages it (:169) but only reads the result's spatial size,
+    which equals ``xt_feature``'s; the 128x128 / 305-channel hard-codes (:162) are lifted.
+    """
+    del features
+    o, x, p = _retrify_inputs(oT_before, xt_feature, preds, T, stride)
+    return _RetrifyPrototypes.apply(int(T), int(stride), o, x, p)
+
+
+def gen_prototype_src_trg_retrify(pred_oS, xs_feature, oT_before, xt_feature, preds, features, T, stride):
+    """Drop-in for ``utils.Utils.gen_prototype_src_trg_retrify`` (utils/Utils.py:227-311): joint prototypes
+    ``(S_s + S_t)/(N_s + N_t)`` with retrify weights on the target side.  Returns the 2K prototypes only."""
+    del features
+    o, x, p = _retrify_inputs(oT_before, xt_feature, preds, T, stride)
+    ps, fs = _require_cuda_f32(pred_oS, "pred_oS"), _require_cuda_f32(xs_feature, "xs_feature")
+    K = o.shape[1]
+    return _RetrifyPrototypes.apply(int(T), int(stride), o, x, p, ps, fs)[:2 * K]
+
+
+# ----------------------------------------------------------------------------------------------- A8
+def feat_prototype_distance(feat: torch.Tensor, prototype: torch.Tensor, class_numbers: int = 1) -> torch.Tensor:
+    """``Trainer.feat_prototype_distance`` (Trainer_prototype.py:98-104): ``[N, class_numbers, H, W]`` with
+    ``|| prototype - feat[n,:,h,w] ||_2`` in every class slot (the reference broadcasts one prototype).
+    ``prototype`` may also be ``[Q, C]`` with ``Q == class_numbers`` for one distance map per prototype.
+    Forward only (no autograd), as used by the reference (pseudo-label rectification)."""
+    lib = _lib.load()
+    f = _require_cuda_f32(feat.detach(), "feat")
+    N, C, H, W = f.shape
+    P = prototype.detach().to(device=f.device, dtype=torch.float32).reshape(-1, C).contiguous()
+    Q = P.shape[0]
+    out = torch.empty(N, Q, H, W, dtype=torch.float32, device=f.device)
+    with torch.cuda.device(f.device):
+        check(lib.clr_proto_distance(ptr(f), N, C, H * W, ptr(P), Q, ptr(out), _stream()), "clr_proto_distance")
+    if Q == 1 and class_numbers > 1:
+        out = out.expand(N, class_numbers, H, W).contiguous()
+    return out
+
+
+def distance_weight(feat: torch.Tensor, prototype: torch.Tensor, class_num: int = 1) -> torch.Tensor:
+    """``Trainer.get_prototype_weight`` (Trainer_prototype.py:106-116): distance map normalised by its
+    global min / max."""
+    lib = _lib.load()
+    d = feat_prototype_distance(feat, prototype, class_num)
+    ws = torch.empty(512, dtype=torch.float32, device=d.device)
+    with torch.cuda.device(d.device):
+        check(lib.clr_minmax_normalize(ptr(d), d.numel(), ptr(ws), _stream()), "clr_minmax_normalize")
+    return d
+
+
+def get_prototype_weight(feat, class_num, prototype):
+    """Drop-in for ``utils.Utils.get_prototype_weight`` (utils/Utils.py:86-88):
+    ``cosine_similarity(prototype, feat, dim=1).unsqueeze(1)`` -> ``[N,1,H,W]``.  Forward only."""
+    del class_num
+    lib = _lib.load()
+    f = _require_cuda_f32(feat.detach(), "feat")
+    N, C, H, W = f.shape
+    P = prototype.detach().to(device=f.device, dtype=torch.float32).reshape(C).contiguous()
+    out = torch.empty(N, 1, H, W, dtype=torch.float32, device=f.device)
+    ws = torch.empty(4, dtype=torch.float32, device=f.device)
+    with torch.cuda.device(f.device):
+        check(lib.clr_proto_cosine(ptr(f), N, C, H * W, ptr(P), ptr(ws), ptr(out), _stream()), "clr_proto_cosine")
+    return out
 
 
 def adaptation_factor(m):

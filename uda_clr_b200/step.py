@@ -1,0 +1,244 @@
+"""The fused CLR step: everything ``Trainer_prototype_full.train_epoch`` does between the model forward
+and ``loss_all.backward()`` for the CLR terms (Trainer_prototype_full.py:328-449, plus the two losses
+that exist only in ``Trainer_prototype_mt``'s bytecode), as ONE call.
+
+    step = CLRStep(K=2, decay=0.9, pro_weight=0.1, src_reg_weight=1.0, use_disc=True, use_cons=True)
+    out = step(xs_feature, pred_oS, xt_feature, oT_before=oT_before, preds=preds_trg, T=8, oT=oT, oT_aug=oT_aug)
+    (loss_seg + loss_adv + out.total).backward()
+
+The trainer's inline EMA / MSE block cannot be fused without touching the trainer, so this is an
+additional entry point next to the drop-in functions of :mod:`uda_clr_b200.ops`; it owns the EMA state
+(the ``self.sourcecentroid_*`` / ``self.targetcentroid_*`` attributes and the ``First*`` flags of the
+reference trainer, Trainer_prototype_full.py:32-33, 341-344).
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from dataclasses import dataclass
+from typing import List, Optional
+
+import torch
+
+from . import _lib
+from . import dist as _dist
+from ._lib import CLR_W_COMPLEMENT, CLR_W_EXPLICIT, StepArgs, check, ptr
+from .ops import PSEUDO_THRESHOLD, STD_THRESHOLD, _require_cuda_f32, _stream
+
+
+def sigmoid_rampup(current: float, rampup_length: float) -> float:
+    """``sigmoid_rampup`` of the reference (Trainer_prototype_mt bytecode L24-31, utils/Utils.py:312+)."""
+    if rampup_length == 0:
+        return 1.0
+    current = min(max(float(current), 0.0), float(rampup_length))
+    phase = 1.0 - current / rampup_length
+    return math.exp(-5.0 * phase * phase)
+
+
+def consistency_threshold(epoch: float) -> float:
+    """``(0.85 + 0.25*sigmoid_rampup(epoch, 200)) * ln 2`` (Trainer_prototype_mt bytecode L512)."""
+    return (0.85 + 0.25 * sigmoid_rampup(epoch, 200)) * math.log(2.0)
+
+
+@dataclass
+class CLRStepOutput:
+    total: torch.Tensor              # scalar, differentiable: w_intra*intra + w_inter*inter + w_disc*disc + w_aug*aug
+    intra: torch.Tensor              # scalars below are detached views of one device buffer (no host sync)
+    inter: torch.Tensor
+    disc: torch.Tensor
+    aug: torch.Tensor
+    source_prototypes: List[torch.Tensor]   # 2K x [1,C,1,1], EMA'd, detached
+    target_prototypes: List[torch.Tensor]
+    std_map: Optional[torch.Tensor]         # [B,K,Hi,Wi] (retrify)
+    masks: Optional[List[torch.Tensor]]     # K x [B,1,H,W] in {0,2} (retrify)
+
+
+class _Buffers:
+    """All device buffers of one step, carved from a single allocation."""
+
+    def __init__(self, a: "CLRStep", dev, B_s, B_t, C, H, W, K, Hi, Wi):
+        R = 2 * K
+        spec = [("packed1", 2 * R * (C + 1)), ("packed2", K * (C + 1) + 4), ("P_s", R * C), ("P_t", R * C),
+                ("g_s", R * C), ("g_t", R * C), ("losses", 8)]
+        if a.use_disc:
+            spec += [("disc_vec", K * C), ("disc_beta", K), ("xtab", K * C), ("disc_coef", B_s * K * H * W)]
+        if a.retrify:
+            spec += [("std_map", B_t * K * Hi * Wi), ("pred_mean", B_t * K * Hi * Wi),
+                     ("wt_retrify", B_t * R * H * W), ("masks", B_t * K * H * W)]
+        total = sum((n + 63) // 64 * 64 for _, n in spec)
+        self.flat = torch.empty(total, dtype=torch.float32, device=dev)
+        off = 0
+        for name, n in spec:
+            setattr(self, name, self.flat[off:off + n])
+            off += (n + 63) // 64 * 64
+
+
+class _ClrStepFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, step, args_holder, xs, xt, oT_aug):
+        lib = _lib.load()
+        a: StepArgs = args_holder["args"]
+        st = _stream()
+        with torch.cuda.device(xs.device):
+            if _dist.enabled():
+                check(lib.clr_step_fwd_a(ctypes.byref(a), st), "clr_step_fwd_a")
+                _dist.all_reduce_sums(args_holder["buf"].packed1)
+                check(lib.clr_step_fwd_b(ctypes.byref(a), st), "clr_step_fwd_b")
+                _dist.all_reduce_sums(args_holder["buf"].packed2)
+                check(lib.clr_step_fwd_c(ctypes.byref(a), st), "clr_step_fwd_c")
+            else:
+                check(lib.clr_step_fwd(ctypes.byref(a), st), "clr_step_fwd")
+        ctx.holder = args_holder
+        ctx.xs_shape, ctx.xt_shape = tuple(xs.shape), tuple(xt.shape)
+        ctx.aug_shape = None if oT_aug is None else tuple(oT_aug.shape)
+        return args_holder["buf"].losses[4].clone()
+
+    @staticmethod
+    def backward(ctx, gup):
+        lib = _lib.load()
+        h = ctx.holder
+        a: StepArgs = h["args"]
+        dev = h["buf"].flat.device
+        gxs = torch.empty(ctx.xs_shape, dtype=torch.float32, device=dev)
+        gxt = torch.empty(ctx.xt_shape, dtype=torch.float32, device=dev)
+        want_aug = ctx.aug_shape is not None and ctx.needs_input_grad[4] and a.use_cons and a.w_aug != 0.0
+        g_aug = torch.empty(ctx.aug_shape, dtype=torch.float32, device=dev) if want_aug else None
+        gup = gup.to(torch.float32).contiguous()
+        a.gxs, a.gxt, a.g_oT_aug, a.gup = ptr(gxs), ptr(gxt), ptr(g_aug), ptr(gup)
+        with torch.cuda.device(dev):
+            check(lib.clr_step_bwd(ctypes.byref(a), _stream()), "clr_step_bwd")
+        h["keep_bwd"] = (gxs, gxt, g_aug, gup)
+        return None, None, gxs, gxt, g_aug
+
+
+class CLRStep:
+    """Stateful fused CLR step (EMA prototypes live here).
+
+    Parameters mirror the reference trainers: ``decay`` = ``global_pro_weight`` (0.9), ``pro_weight`` (0.1),
+    ``src_reg_weight`` / ``aug_weight`` (Trainer_prototype_mt ctor, bytecode L34), margin 0.01 (L455).
+    ``backprop_aug``: the bytecode computes and logs ``loss_aug`` but never back-propagates it; set True to
+    add it to ``total`` (and obtain ``d total / d oT_aug``).
+    """
+
+    def __init__(self, K: int = 2, decay: float = 0.9, pro_weight: float = 0.1, inter_weight: float = 0.0,
+                 src_reg_weight: float = 1.0, aug_weight: float = 1.0, margin: float = 0.01,
+                 retrify: bool = True, use_disc: bool = True, use_cons: bool = True, backprop_aug: bool = False,
+                 global_batch: Optional[int] = None):
+        self.K, self.decay = K, float(decay)
+        self.pro_weight, self.inter_weight = float(pro_weight), float(inter_weight)
+        self.src_reg_weight, self.aug_weight, self.margin = float(src_reg_weight), float(aug_weight), float(margin)
+        self.retrify, self.use_disc, self.use_cons, self.backprop_aug = retrify, use_disc, use_cons, backprop_aug
+        self.global_batch = global_batch
+        self.stored_s: Optional[torch.Tensor] = None
+        self.stored_t: Optional[torch.Tensor] = None
+        self.first_s = True
+        self.first_t = True
+        self._ws: Optional[torch.Tensor] = None
+
+    # -- state -------------------------------------------------------------------------------------
+    def state_dict(self):
+        return dict(stored_s=self.stored_s, stored_t=self.stored_t, first_s=self.first_s, first_t=self.first_t)
+
+    def load_state_dict(self, sd):
+        self.stored_s, self.stored_t = sd["stored_s"], sd["stored_t"]
+        self.first_s, self.first_t = bool(sd["first_s"]), bool(sd["first_t"])
+
+    # -- the step ------------------------------------------------------------------------------------
+    def __call__(self, xs_feature, pred_oS, xt_feature, oT_before=None, wt=None, preds=None, T: int = 8,
+                 oT=None, oT_aug=None, masks=None, epoch: float = 0.0) -> CLRStepOutput:
+        lib = _lib.load()
+        xs = _require_cuda_f32(xs_feature, "xs_feature")
+        ys = _require_cuda_f32(pred_oS.detach(), "pred_oS")
+        xt = _require_cuda_f32(xt_feature, "xt_feature")
+        dev = xs.device
+        B_s, C, H, W = xs.shape
+        B_t = xt.shape[0]
+        K = self.K
+        if ys.shape != (B_s, K, H, W) or xt.shape[1:] != (C, H, W):
+            raise ValueError("inconsistent shapes: xs %s ys %s xt %s" % (tuple(xs.shape), tuple(ys.shape), tuple(xt.shape)))
+        Hi = Wi = 0
+        use_cons = self.use_cons and oT_aug is not None
+        if self.retrify:
+            if oT_before is None or preds is None:
+                raise ValueError("retrify=True needs oT_before and preds")
+            oTb = _require_cuda_f32(oT_before.detach(), "oT_before")
+            pr = _require_cuda_f32(preds.detach(), "preds")
+            if pr.shape[0] != T * B_t or pr.shape[1] != K:
+                raise ValueError("preds must be [T*B_t, K, Hi, Wi]")
+            Hi, Wi = pr.shape[2:]
+            wt_t, wt_fmt = None, CLR_W_EXPLICIT
+        else:
+            if wt is None:
+                if oT_before is None:
+                    raise ValueError("retrify=False needs wt (target weights) or oT_before")
+                wt = torch.sigmoid(oT_before.detach())
+            wt_t = _require_cuda_f32(wt.detach(), "wt")
+            wt_fmt = CLR_W_COMPLEMENT if wt_t.shape[1] == K else CLR_W_EXPLICIT
+            oTb = pr = None
+        if use_cons:
+            oT_d = _require_cuda_f32(oT.detach(), "oT")
+            oTa = _require_cuda_f32(oT_aug, "oT_aug")
+            Hi, Wi = oT_d.shape[2:]
+            if not self.retrify:
+                if masks is None:
+                    raise ValueError("consistency without retrify needs explicit masks [B,K,H,W]")
+                masks_t = _require_cuda_f32(masks.detach(), "masks")
+        else:
+            oT_d = oTa = None
+
+        buf = _Buffers(self, dev, B_s, B_t, C, H, W, K, Hi, Wi)
+        if self.stored_s is None:
+            self.stored_s = torch.zeros(2 * K, C, dtype=torch.float32, device=dev)
+            self.stored_t = torch.zeros(2 * K, C, dtype=torch.float32, device=dev)
+
+        a = StepArgs()
+        a.B_s, a.B_t, a.C, a.H, a.W, a.K = B_s, B_t, C, H, W, K
+        a.Hi, a.Wi, a.T = Hi, Wi, int(T)
+        a.use_retrify, a.use_disc, a.use_cons = int(self.retrify), int(self.use_disc), int(use_cons)
+        a.wt_fmt, a.first_s, a.first_t = wt_fmt, int(self.first_s), int(self.first_t)
+        world = _dist.world_size()
+        gb = self.global_batch if self.global_batch is not None else world * B_s
+        a.decay, a.npx_global = self.decay, float(gb * H * W)
+        a.w_intra, a.w_inter, a.w_disc = self.pro_weight, self.inter_weight, self.src_reg_weight if self.use_disc else 0.0
+        a.w_aug = 1.0 if (use_cons and self.backprop_aug) else 0.0
+        a.margin, a.aug_weight = self.margin, self.aug_weight
+        a.cons_threshold = consistency_threshold(epoch)
+        a.pseudo_thr, a.std_thr = PSEUDO_THRESHOLD, STD_THRESHOLD
+        a.grad_scale = _dist.grad_scale() if _dist.enabled() else 1.0
+        a.xs, a.ys, a.xt, a.wt = ptr(xs), ptr(ys), ptr(xt), ptr(wt_t)
+        a.oT_before, a.preds, a.oT, a.oT_aug = ptr(oTb), ptr(pr), ptr(oT_d), ptr(oTa)
+        a.gup = None
+        a.stored_s, a.stored_t = ptr(self.stored_s), ptr(self.stored_t)
+        for name in ("packed1", "packed2", "P_s", "P_t", "g_s", "g_t", "losses"):
+            setattr(a, name, ptr(getattr(buf, name)))
+        if self.use_disc:
+            for name in ("disc_vec", "disc_beta", "xtab", "disc_coef"):
+                setattr(a, name, ptr(getattr(buf, name)))
+        if self.retrify:
+            for name in ("std_map", "pred_mean", "wt_retrify", "masks"):
+                setattr(a, name, ptr(getattr(buf, name)))
+        elif use_cons:
+            a.masks = ptr(masks_t)
+        a.ws = None
+        ws_bytes = lib.clr_step_ws_bytes(ctypes.byref(a))
+        if self._ws is None or self._ws.numel() < ws_bytes or self._ws.device != dev:
+            self._ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        a.ws, a.ws_bytes = ptr(self._ws), ws_bytes
+
+        holder = dict(args=a, buf=buf,
+                      keep=(xs, ys, xt, wt_t, oTb, pr, oT_d, oTa, self.stored_s, self.stored_t, self._ws,
+                            masks_t if (use_cons and not self.retrify) else None))
+        total = _ClrStepFn.apply(self, holder, xs, xt, oTa)
+        self.first_s = self.first_t = False
+
+        L = buf.losses
+        R = 2 * K
+        Ps = [buf.P_s[r * C:(r + 1) * C].view(1, C, 1, 1) for r in range(R)]
+        Pt = [buf.P_t[r * C:(r + 1) * C].view(1, C, 1, 1) for r in range(R)]
+        std_map = mask_list = None
+        if self.retrify:
+            std_map = buf.std_map.view(B_t, K, Hi, Wi)
+            m = buf.masks.view(B_t, K, H, W)
+            mask_list = [m[:, k:k + 1] for k in range(K)]
+        return CLRStepOutput(total=total, intra=L[0], inter=L[1], disc=L[2], aug=L[3], source_prototypes=Ps,
+                             target_prototypes=Pt, std_map=std_map, masks=mask_list)
