@@ -1,0 +1,374 @@
+#!/usr/bin/env python3
+"""Benchmark of the CLR hot path: ``CLR loss fwd+bwd Mpixels/s`` (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload clr3|align]
+
+A *step* is one pass of the hot path over one synthetic batch per GPU: source pooling (A1, hard labels) +
+target retrify (A2: MC statistics + confidence-weighted pooling) + EMA (A4) + alignment / separation losses
+(A5) + discriminative hinge (A9) + augmented-consistency BCE (A10), forward AND backward (gradients of both
+feature maps written).  One *pixel* is one (b,h,w) location of one domain's feature map: a step processes
+``2*B*H*W`` pixels per GPU.
+
+Arms
+  ours       the sm_100a kernels through the public API (``CLRStep.plan(...).run()``); inputs resident in HBM.
+             ``e2e`` repeats the measurement with pinned HOST inputs copied to the device inside every step and
+             the losses read back to the host.
+  reference  the reference's own eager-PyTorch CPU implementation of the same step, timed on this box's host
+             cores (the op-for-op port in ``oracle/clr_torch_port.py`` -- the reference tree is Python and does
+             not travel to the GPU box; ``kind: "port"``).
+
+Rank 0 prints ONE JSON line.  Under torchrun each rank runs its own shard of the global batch (weak scaling:
+per-GPU batch fixed) and the only exchange is the all-reduce of the packed class-wise sums.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "clr_fwd_bwd_mpixels_per_s"
+UNIT = "Mpixel/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="clr3", choices=["clr3", "align"])
+    ap.add_argument("--B", type=int, default=8, help="per-GPU batch of each domain")
+    ap.add_argument("--C", type=int, default=256)
+    ap.add_argument("--H", type=int, default=128)
+    ap.add_argument("--K", type=int, default=2)
+    ap.add_argument("--T", type=int, default=8)
+    ap.add_argument("--up", type=int, default=4, help="image resolution / feature resolution")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-budget-s", type=float, default=25.0)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------- byte model
+def algorithmic_bytes(a) -> dict:
+    """SURVEY.md 8(d) / BASELINE.md 3: the minimal traffic of each stage, per step and per GPU."""
+    B, C, HW, K, T, up = a.B, a.C, a.H * a.H, a.K, a.T, a.up
+    F = 4 * B * C * HW
+    Lb = 4 * B * K * HW
+    Li = 4 * B * K * HW * up * up
+    d = {}
+    if a.workload == "clr3":
+        d["mc_stats"] = T * Li + 2 * Li                       # read preds, write std_map + prediction
+        d["retrify_weights"] = Lb + 2 * Li // 4 + 3 * Lb      # logits + sampled taps in, 2K weights + masks out
+        d["pool_fwd"] = 2 * F + Lb + 2 * Lb                   # both feature maps + labels + explicit target weights
+        d["cons_fwd"] = 2 * Li + Lb
+        d["disc_fwd"] = F + Lb + Lb                           # second read of xs, labels in, coefficients out
+        d["pool_bwd"] = 2 * F + Lb + 2 * Lb + Lb              # both gradient maps + weight / coefficient planes
+    else:
+        d["pool_fwd"] = 2 * F + 2 * Lb
+        d["pool_bwd"] = 2 * F + 2 * Lb
+    d["total"] = sum(d.values())
+    return d
+
+
+# ------------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """``nvidia-smi`` clocks + throttle reasons sampled every 200 ms while the timed region runs."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+        self.t_begin = self.t_end = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def mark_begin(self):
+        self.t_begin = time.time()
+
+    def mark_end(self):
+        self.t_end = time.time()
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        inside = [r for (ts, r) in self.rows if self.t_begin is not None and self.t_begin <= ts <= self.t_end + 0.1]
+        rows = inside if inside else [r for (_, r) in self.rows]
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "samples_inside_timed_region": len(inside), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------- reference arm
+def run_reference_cpu(a, steps: int, warmup: int, budget_s: float):
+    """The reference's eager CPU path on the host cores, on a bounded sample of the same workload."""
+    import torch
+    from oracle import clr_torch_port as TP
+    from uda_clr_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    use3 = a.workload == "clr3"
+
+    def make(Bs):
+        b = synth.make_batch(B=Bs, C=a.C, H=a.H, W=a.H, K=a.K, T=a.T, up=a.up, seed=1234, image_res=use3)
+        feats = torch.zeros(a.T * Bs, a.C, a.H, a.H) if use3 else None   # the reference's dead staging buffer
+        return b, feats
+
+    def one(port, b, feats):
+        xs = b.xs.clone().requires_grad_(True)
+        xt = b.xt.clone().requires_grad_(True)
+        t0 = time.perf_counter()
+        if use3:
+            oTa = b.oT_aug.clone().requires_grad_(True)
+            port.step(xs, b.ys, xt, b.oT_before, preds=b.preds, features=feats, T=a.T, oT=b.oT, oT_aug=oTa, epoch=0.0)
+        else:
+            port.step(xs, b.ys, xt, b.oT_before)
+        return time.perf_counter() - t0
+
+    def new_port():
+        return TP.ClrStepPort(retrify=use3, use_disc=use3, use_cons=use3, backprop_aug=False)
+
+    # size the sample: one probe step at B=1, then the largest batch <= B whose run fits the budget
+    b1, f1 = make(1)
+    port = new_port()
+    one(port, b1, f1)
+    t1 = one(port, b1, f1)
+    n_total = steps + warmup
+    Bs = int(max(1, min(a.B, budget_s / max(t1 * n_total, 1e-9))))
+    if Bs * t1 * n_total > 4 * budget_s:      # even B=1 is too slow for K+W steps: cut the step count
+        n_total = max(2, int(4 * budget_s / t1))
+        warmup = min(warmup, n_total - 1)
+        steps = n_total - warmup
+    b, feats = (b1, f1) if Bs == 1 else make(Bs)
+    port = new_port()
+    for _ in range(warmup):
+        one(port, b, feats)
+    ts = [one(port, b, feats) for _ in range(steps)]
+    med = statistics.median(ts)
+    mpix = 2 * Bs * a.H * a.H / med / 1e6
+    sample = "%d steps x (B=%d of %d per domain, C=%d, %dx%d, K=%d%s), median of per-step wall times" % (
+        steps, Bs, a.B, a.C, a.H, a.H, a.K, (", T=%d, %dx%d preds" % (a.T, a.H * a.up, a.H * a.up)) if use3 else "")
+    return dict(value=mpix, unit=UNIT, cores=cores, kind="port", sample=sample, ms_per_step=med * 1e3,
+                torch_threads=torch.get_num_threads(), steps=steps, warmup=warmup)
+
+
+def config_dict(a, n_gpus):
+    return {"workload": ("clr3: A1 hard source + A2 retrify target (MC stats T=%d) + A4 EMA + A5 align + A9 hinge + A10 "
+                         "consistency, fwd+bwd" % a.T) if a.workload == "clr3" else
+                        "align: A1 hard source + A1 soft target + A4 + A5, fwd+bwd (Trainer_prototype_full.py:330-449)",
+            "per_gpu_batch": a.B, "global_batch": a.B * n_gpus, "channels": a.C, "feature_hw": [a.H, a.H],
+            "image_hw": [a.H * a.up, a.H * a.up], "classes": a.K, "mc_passes": a.T,
+            "parallelism": "dp%d (batch-sharded, all-reduce of packed class sums)" % n_gpus,
+            "l2_policy": "inputs larger than L2: 2 rotating input sets, each step streams > 700 MB vs 126 MB L2",
+            "baseline_config": "BASELINE.json configs[0] shape (B=8, 256ch, 128x128, K=2) = the per-GPU CLR workload of configs[1]"}
+
+
+# ------------------------------------------------------------------------------------------------- main
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        r = run_reference_cpu(a, a.steps, a.warmup, budget_s=max(a.cpu_budget_s, 60.0))
+        line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": a.gpus,
+                "steps": r["steps"], "warmup": r["warmup"], "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": config_dict(a, a.gpus),
+                "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+                                 "sample": r["sample"]},
+                "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import uda_clr_b200 as clr
+    from uda_clr_b200 import _lib, synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist_on = world > 1
+    if dist_on:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+        clr.dist.enable()
+    lib = _lib.load()
+
+    use3 = a.workload == "clr3"
+    NSET = 2
+    host = [synth.make_batch(B=a.B, C=a.C, H=a.H, W=a.H, K=a.K, T=a.T, up=a.up, seed=1234 + 17 * rank + s,
+                             image_res=use3) for s in range(NSET)]
+    names = ["xs", "ys", "xt", "oT_before"] + (["preds", "oT", "oT_aug"] if use3 else [])
+    devb = [{k: getattr(h, k).to(dev) for k in names} for h in host]
+
+    step = clr.CLRStep(K=a.K, retrify=use3, use_disc=use3, use_cons=use3, backprop_aug=False,
+                       global_batch=a.B * world)
+    plans = []
+    for d in devb:
+        if use3:
+            plans.append(step.plan(d["xs"], d["ys"], d["xt"], oT_before=d["oT_before"], preds=d["preds"], T=a.T,
+                                   oT=d["oT"], oT_aug=d["oT_aug"], epoch=0.0))
+        else:
+            plans.append(step.plan(d["xs"], d["ys"], d["xt"], wt=torch.sigmoid(d["oT_before"])))
+
+    def barrier():
+        if dist_on:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up -------------------------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    for i in range(max(a.warmup, 3)):
+        plans[i % NSET].run()
+    barrier()
+
+    # ---- timed region: exactly K steps, CUDA events on the launching stream ------------------------
+    K = a.steps
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pool_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    bwd_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    launches0 = lib.clr_launch_count()
+    barrier()
+    sampler.mark_begin()
+    ev0.record()
+    for i in range(K):
+        p = plans[i % NSET]
+        p.set_events(pool_ev[i][0], pool_ev[i][1], bwd_ev[i][0], bwd_ev[i][1])
+        p.run()
+    ev1.record()
+    barrier()
+    sampler.mark_end()
+    launches = lib.clr_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    for p in plans:
+        p.set_events()
+    ms_total = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if dist_on:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / K
+    pool_us = statistics.mean(b.elapsed_time(e) for b, e in pool_ev) * 1e3
+    bwd_us = statistics.mean(b.elapsed_time(e) for b, e in bwd_ev) * 1e3
+    value = 2 * a.B * a.H * a.H * world / (ms_per_step * 1e-3) / 1e6
+    losses = plans[0].losses.detach().cpu().tolist()
+
+    # ---- e2e: pinned host inputs -> device -> step -> losses back to the host, every step ----------
+    e2e = None
+    if not a.no_e2e:
+        pinned = [{k: getattr(h, k).pin_memory() for k in names} for h in host]
+        h2d = sum(v.numel() * 4 for v in pinned[0].values())
+        out_host = torch.empty(8, dtype=torch.float32).pin_memory()
+        n_e2e = max(3, min(K, 10))
+
+        def e2e_step(i):
+            src, dst, p = pinned[i % NSET], devb[i % NSET], plans[i % NSET]
+            for k in names:
+                dst[k].copy_(src[k], non_blocking=True)
+            p.run()
+            out_host.copy_(p.losses, non_blocking=True)
+
+        for i in range(2):
+            e2e_step(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n_e2e):
+            e2e_step(i)
+        e1.record()
+        barrier()
+        te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if dist_on:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        ms_e2e = float(te.item()) / n_e2e
+        e2e = {"value": 2 * a.B * a.H * a.H * world / (ms_e2e * 1e-3) / 1e6, "unit": UNIT,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 32, "ms_per_step": ms_e2e, "steps": n_e2e}
+
+    if rank != 0:
+        if dist_on:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (the two-domain pooling launch), measured live above ------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy)"
+    else:
+        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    ab = algorithmic_bytes(a)
+    achieved = ab["pool_fwd"] / (pool_us * 1e-6) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
+    if os.path.isfile(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("pool_fwd_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "pool_fwd_tma_kernel<4> (source+target pooling, one launch) + pool_reduce",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": ab["pool_fwd"], "kernel_us": pool_us,
+                "bwd_kernel": {"kernel": "pool_bwd_kernel (both gradient maps, one launch)", "kernel_us": bwd_us,
+                               "achieved": ab["pool_bwd"] / (bwd_us * 1e-6) / 1e9,
+                               "frac": ab["pool_bwd"] / (bwd_us * 1e-6) / 1e9 / peak},
+                "step": {"algorithmic_bytes": ab["total"], "achieved": ab["total"] / (ms_per_step * 1e-3) / 1e9,
+                         "frac": ab["total"] / (ms_per_step * 1e-3) / 1e9 / peak,
+                         "frac_of_nominal_8TBs": ab["total"] / (ms_per_step * 1e-3) / 1e9 / 8000.0}}
+
+    cpu_baseline = None
+    if not a.no_cpu_baseline and world == 1:
+        r = run_reference_cpu(a, steps=3, warmup=1, budget_s=a.cpu_budget_s)
+        cpu_baseline = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
+                        "ms_per_step": r["ms_per_step"]}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(a.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config_dict(a, world), "clocks": clocks,
+            "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "losses": {"intra": losses[0], "inter": losses[1], "disc": losses[2], "aug": losses[3], "total": losses[4]}}
+    print(json.dumps(line))
+    if dist_on:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -56,6 +56,8 @@ int clr_device_info(int* sm_count, int* l2_bytes);
 /* Benchmark knobs (process-wide): "pool_impl" 0 auto / 1 LDG kernel, "pool_stages" TMA ring depth,
  * "dots_impl", "bwd_impl".  Defaults select the fastest path; results are identical either way. */
 int clr_set_tunable(const char* name, int value);
+/* Number of CUDA kernels this library has launched in this process so far (bench: "gpu_launches"). */
+unsigned long long clr_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Masked / confidence-weighted class-wise pooling  (replaces utils/Utils.py:114-126 -- the four
@@ -228,6 +230,10 @@ typedef struct clr_step_args {
     float* g_oT_aug;                      /* [B_t,K,Hi,Wi] backward output (consistency, when w_aug != 0) */
     /* workspace */
     void* ws; size_t ws_bytes;
+    /* optional cudaEvent_t handles recorded on `stream` around the dominant kernel (the two-domain
+     * pooling launch) so a harness can time it inside a live step; NULL = not recorded */
+    void* ev_pool_begin; void* ev_pool_end;
+    void* ev_bwd_begin; void* ev_bwd_end;
 } clr_step_args;
 
 size_t clr_step_ws_bytes(const clr_step_args* a);

@@ -12,7 +12,7 @@ missing (no CPU fallback).
 from .ops import (adaptation_factor, distance_weight, feat_prototype_distance, gen_prototype,  # noqa: F401
                   gen_prototype_retrify, gen_prototype_src_trg, gen_prototype_src_trg_retrify,
                   get_prototype_weight, mc_statistics, retrify_weights, weighted_prototypes)
-from .step import CLRStep, CLRStepOutput, consistency_threshold, sigmoid_rampup  # noqa: F401
+from .step import CLRPlan, CLRStep, CLRStepOutput, consistency_threshold, sigmoid_rampup  # noqa: F401
 from . import dist, ops  # noqa: F401
 
 __version__ = "0.1.0"

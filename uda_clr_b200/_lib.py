@@ -53,6 +53,7 @@ class StepArgs(Structure):
         ("disc_coef", _P), ("disc_vec", _P), ("disc_beta", _P), ("xtab", _P),
         ("gxs", _P), ("gxt", _P), ("g_oT_aug", _P),
         ("ws", _P), ("ws_bytes", c_size_t),
+        ("ev_pool_begin", _P), ("ev_pool_end", _P), ("ev_bwd_begin", _P), ("ev_bwd_end", _P),
     ]
 
 
@@ -61,6 +62,7 @@ _SIGNATURES = {
     "clr_status_string": (c_char_p, [c_int]),
     "clr_device_info": (c_int, [POINTER(c_int), POINTER(c_int)]),
     "clr_set_tunable": (c_int, [c_char_p, c_int]),
+    "clr_launch_count": (ctypes.c_ulonglong, []),
     "clr_pool_ws_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "clr_pool_rows_ws_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "clr_pool_rows_fwd": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, c_size_t, _P, _P]),

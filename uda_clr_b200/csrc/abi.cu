@@ -21,6 +21,9 @@ const DeviceFacts& device_facts() {
     return facts[dev];
 }
 
+static unsigned long long g_launches = 0;
+void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
+
 Tunables& tunables() {
     static Tunables t{0, 0, 0, 0};
     return t;
@@ -44,6 +47,8 @@ int clr_set_tunable(const char* name, int value) {
 }
 
 int clr_version(void) { return CLR_B200_VERSION; }
+
+unsigned long long clr_launch_count(void) { return __atomic_load_n(&clr::g_launches, __ATOMIC_RELAXED); }
 
 const char* clr_status_string(int status) {
     switch (status) {

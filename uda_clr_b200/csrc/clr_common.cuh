@@ -34,6 +34,9 @@ struct Tunables {
 };
 Tunables& tunables();
 
+// Process-wide count of kernel launches issued by this library (clr_launch_count); relaxed atomic.
+void count_launch();
+
 // ---- streaming loads / stores --------------------------------------------------------------------
 // Feature maps are touched exactly once per pass: read through the non-coherent path without
 // allocating in L1; gradients are written with an evict-first hint.

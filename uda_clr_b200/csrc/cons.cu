@@ -98,7 +98,7 @@ int cons_fwd_partials(const float* oT, const float* oT_aug, const float* masks, 
                       int H, int W, float threshold, double* partial, int* nblocks, cudaStream_t st) {
     const size_t n = (size_t)B * K * Hi * Wi;
     const int blocks = (int)((n + 255) / 256 < (size_t)kConsMaxBlocks ? (n + 255) / 256 : (size_t)kConsMaxBlocks);
-    cons_fwd_kernel<<<blocks, 256, 0, st>>>(oT, oT_aug, masks, make_geom(B, K, Hi, Wi, H, W), threshold, n, partial);
+    clr::count_launch(); cons_fwd_kernel<<<blocks, 256, 0, st>>>(oT, oT_aug, masks, make_geom(B, K, Hi, Wi, H, W), threshold, n, partial);
     *nblocks = blocks;
     return launch_status();
 }
@@ -117,7 +117,7 @@ int clr_cons_fwd(const float* oT, const float* oT_aug, const float* masks, int B
     int blocks = 0;
     const int rc = clr::cons_fwd_partials(oT, oT_aug, masks, B, K, Hi, Wi, H, W, threshold, static_cast<double*>(ws), &blocks, st);
     if (rc != CLR_OK) return rc;
-    clr::cons_final_kernel<<<1, 32, 0, st>>>(static_cast<const double*>(ws), blocks, aug_weight, stats);
+    clr::count_launch(); clr::cons_final_kernel<<<1, 32, 0, st>>>(static_cast<const double*>(ws), blocks, aug_weight, stats);
     return clr::launch_status();
 }
 
@@ -128,7 +128,7 @@ int clr_cons_bwd(const float* oT, const float* oT_aug, const float* masks, int B
         return CLR_ERR_BAD_ARG;
     const size_t n = (size_t)B * K * Hi * Wi;
     int blocks = (int)((n + 255) / 256 < (size_t)clr::kConsMaxBlocks * 2 ? (n + 255) / 256 : (size_t)clr::kConsMaxBlocks * 2);
-    clr::cons_bwd_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    clr::count_launch(); clr::cons_bwd_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         oT, oT_aug, masks, clr::make_geom(B, K, Hi, Wi, H, W), threshold, stats, gscale_dev, gscale * aug_weight, n, grad_oT_aug);
     return clr::launch_status();
 }

@@ -125,7 +125,7 @@ __global__ void step_pack_kernel(const float* __restrict__ hinge_partials, int n
 
 void launch_step_pack(const float* hinge_partials, int n_hinge, int hinge_stride,
                       const double* cons_partials, int n_cons, float* tail, cudaStream_t st) {
-    step_pack_kernel<<<1, 32, 0, st>>>(hinge_partials, n_hinge, hinge_stride, cons_partials, n_cons, tail);
+    clr::count_launch(); step_pack_kernel<<<1, 32, 0, st>>>(hinge_partials, n_hinge, hinge_stride, cons_partials, n_cons, tail);
 }
 
 }  // namespace clr
@@ -140,7 +140,7 @@ int clr_align_finalize(const float* sums_s, const float* sums_t, int K, int C,
     if (!sums_s || !sums_t || !stored_s || !stored_t || !P_s || !P_t || !g_s || !g_t || !losses ||
         K < 1 || K > CLR_MAX_K || C < 1)
         return CLR_ERR_BAD_ARG;
-    clr::align_finalize_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    clr::count_launch(); clr::align_finalize_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         sums_s, sums_t, K, C, stored_s, stored_t, first_s, first_t, decay, w_intra, w_inter,
         P_s, P_t, cur_s, cur_t, g_s, g_t, disc_vec, disc_beta, losses);
     return clr::launch_status();
@@ -152,7 +152,7 @@ int clr_disc_finalize(const float* packed2, const float* P_s, int K, int C, doub
                       float* losses, clr_stream_t stream) {
     if (!packed2 || !losses || K < 1 || K > CLR_MAX_K || C < 1) return CLR_ERR_BAD_ARG;
     if (use_disc && (!P_s || !g_s || !xtab || npx <= 0)) return CLR_ERR_BAD_ARG;
-    clr::disc_finalize_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    clr::count_launch(); clr::disc_finalize_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         packed2, P_s, K, C, npx, w_disc, ema_factor, gscale, g_s, xtab, w_intra, w_inter, w_aug, aug_weight,
         use_disc, use_cons, losses);
     return clr::launch_status();

@@ -132,9 +132,9 @@ int clr_mc_stats(const float* preds, int T, int B, int K, int Hi, int Wi,
     const bool vec4 = (n % 4 == 0) && clr::aligned16(preds) && clr::aligned16(std_map) && clr::aligned16(pred_mean);
     if (vec4) {
         const size_t threads = n / 4;
-        clr::mc_stats_kernel<4><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(preds, T, n, std_map, pred_mean);
+        clr::count_launch(); clr::mc_stats_kernel<4><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(preds, T, n, std_map, pred_mean);
     } else {
-        clr::mc_stats_kernel<1><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(preds, T, n, std_map, pred_mean);
+        clr::count_launch(); clr::mc_stats_kernel<1><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(preds, T, n, std_map, pred_mean);
     }
     return clr::launch_status();
 }
@@ -146,7 +146,7 @@ int clr_retrify_weights(const float* oT_before, const float* pred_mean, const fl
         H < 1 || W < 1 || Hi < 1 || Wi < 1)
         return CLR_ERR_BAD_ARG;
     const size_t n = (size_t)B * K * H * W;
-    clr::retrify_weights_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    clr::count_launch(); clr::retrify_weights_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         oT_before, pred_mean, std_map, B, K, H, W, Hi, Wi, pseudo_thr, std_thr, weights, masks, pseudo_out, small_out);
     return clr::launch_status();
 }

@@ -201,7 +201,7 @@ static int launch_dots(DotsParams& p, int* grid_out, cudaStream_t st) {
         if (*grid_out > 0 && grid > *grid_out) grid = *grid_out;
         *grid_out = grid;
     }
-    kern<<<grid, kThreads, smem, st>>>(p);
+    clr::count_launch(); kern<<<grid, kThreads, smem, st>>>(p);
     return launch_status();
 }
 
@@ -346,7 +346,7 @@ int clr_proto_cosine(const float* feat, int B, int C, int HW, const float* proto
                      clr_stream_t stream) {
     if (!out || !ws4 || !proto || C < 1) return CLR_ERR_BAD_ARG;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    clr::vec_norm_kernel<<<1, 256, 0, st>>>(proto, C, 1e-8f, ws4);
+    clr::count_launch(); clr::vec_norm_kernel<<<1, 256, 0, st>>>(proto, C, 1e-8f, ws4);
     clr::DotsParams p{};
     p.feat = feat; p.V = proto; p.out = out; p.vnorm_dev = ws4;
     p.B = B; p.C = C; p.HW = HW; p.Q = 1; p.epi = clr::DOTS_EPI_COSINE;
@@ -357,8 +357,8 @@ int clr_minmax_normalize(float* x, size_t n, float* ws /*>= 2*256 floats*/, clr_
     if (!x || !ws || n == 0) return CLR_ERR_BAD_ARG;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int blocks = (int)((n + 255) / 256 < 256 ? (n + 255) / 256 : 256);
-    clr::minmax_partial_kernel<<<blocks, 256, 0, st>>>(x, n, ws);
-    clr::minmax_apply_kernel<<<blocks, 256, 0, st>>>(x, n, ws, blocks);
+    clr::count_launch(); clr::minmax_partial_kernel<<<blocks, 256, 0, st>>>(x, n, ws);
+    clr::count_launch(); clr::minmax_apply_kernel<<<blocks, 256, 0, st>>>(x, n, ws, blocks);
     return clr::launch_status();
 }
 
@@ -388,7 +388,7 @@ int clr_pool_bwd_w(const float* feat, int fmt, int B, int C, int HW, int K,
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     float* V = static_cast<float*>(ws);
     float* beta = V + (size_t)Q * C;
-    clr::bwd_w_tables_kernel<<<Q, 256, 0, st>>>(g, sums, K, C, fmt, scale, V, beta);
+    clr::count_launch(); clr::bwd_w_tables_kernel<<<Q, 256, 0, st>>>(g, sums, K, C, fmt, scale, V, beta);
     clr::DotsParams p{};
     p.feat = feat; p.V = V; p.out = grad_w; p.B = B; p.C = C; p.HW = HW; p.Q = Q; p.epi = clr::DOTS_EPI_AFFINE;
     p.beta_dev = beta;

@@ -114,8 +114,8 @@ __global__ void __launch_bounds__(kThreads) pool_bwd_kernel(const BwdParams p) {
 
 template <int QT>
 static int launch_bwd(const BwdParams& p, bool vec4, int ctas, cudaStream_t st) {
-    if (vec4) pool_bwd_kernel<QT, 4><<<ctas, kThreads, 0, st>>>(p);
-    else pool_bwd_kernel<QT, 1><<<ctas, kThreads, 0, st>>>(p);
+    if (vec4) { count_launch(); pool_bwd_kernel<QT, 4><<<ctas, kThreads, 0, st>>>(p); }
+    else { count_launch(); pool_bwd_kernel<QT, 1><<<ctas, kThreads, 0, st>>>(p); }
     return launch_status();
 }
 

@@ -362,7 +362,7 @@ __global__ void proto_finalize_kernel(const float* __restrict__ sums, int R, int
 
 static void launch_reduce(const PoolParams& p, int R, cudaStream_t st) {
     const int n = R * (p.C + 1);
-    pool_reduce_kernel<<<dim3((n + 31) / 32, p.ndom), dim3(32, 8), 0, st>>>(p, R);
+    clr::count_launch(); pool_reduce_kernel<<<dim3((n + 31) / 32, p.ndom), dim3(32, 8), 0, st>>>(p, R);
 }
 
 template <int R, int VEC>
@@ -376,7 +376,7 @@ static int launch_ldg(const PoolParams& p, cudaStream_t st) {
     if (occ < 1) occ = 1;
     int grid = device_facts().sms * occ;
     if (grid > p.total) grid = p.total;
-    kern<<<grid, kThreads, smem, st>>>(p);
+    clr::count_launch(); kern<<<grid, kThreads, smem, st>>>(p);
     launch_reduce(p, R, st);
     return launch_status();
 }
@@ -398,7 +398,7 @@ static int launch_tma(PoolParams p, cudaStream_t st) {
     if (occ < 1) occ = 1;
     int grid = device_facts().sms * occ;
     if (grid > p.total) grid = p.total;
-    kern<<<grid, kPoolTmaThreads, smem, st>>>(p);
+    clr::count_launch(); kern<<<grid, kPoolTmaThreads, smem, st>>>(p);
     launch_reduce(p, R, st);
     return launch_status();
 }
@@ -499,7 +499,7 @@ int clr_pool_fwd2(const float* feat0, const float* w0, int fmt0, int B0,
 int clr_proto_finalize(const float* sums, int R, int C, float* mu, clr_stream_t stream) {
     if (!sums || !mu || R <= 0 || C <= 0) return CLR_ERR_BAD_ARG;
     const int n = R * C;
-    clr::proto_finalize_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(sums, R, C, mu);
+    clr::count_launch(); clr::proto_finalize_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(sums, R, C, mu);
     return clr::launch_status();
 }
 

@@ -80,9 +80,13 @@ int clr_step_fwd_a(const clr_step_args* a, clr_stream_t stream) {
     }
     float* sums_s = a->packed1;
     float* sums_t = a->packed1 + (size_t)R * (a->C + 1);
-    return clr::pool_fwd_impl(a->xs, a->ys, CLR_W_COMPLEMENT, a->B_s, sums_s,
-                              a->xt, clr::target_weights(a), clr::target_fmt(a), a->B_t, sums_t,
-                              a->C, HW, R, w.pool, w.pool_bytes, static_cast<cudaStream_t>(stream));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (a->ev_pool_begin) cudaEventRecord(static_cast<cudaEvent_t>(a->ev_pool_begin), st);
+    rc = clr::pool_fwd_impl(a->xs, a->ys, CLR_W_COMPLEMENT, a->B_s, sums_s,
+                            a->xt, clr::target_weights(a), clr::target_fmt(a), a->B_t, sums_t,
+                            a->C, HW, R, w.pool, w.pool_bytes, st);
+    if (a->ev_pool_end) cudaEventRecord(static_cast<cudaEvent_t>(a->ev_pool_end), st);
+    return rc;
 }
 
 int clr_step_fwd_b(const clr_step_args* a, clr_stream_t stream) {
@@ -145,7 +149,9 @@ int clr_step_bwd(const clr_step_args* a, clr_stream_t stream) {
                        a->gxs, a->gup, a->grad_scale, CLR_W_COMPLEMENT, a->B_s, a->use_disc ? K : 0};
     d[1] = clr_bwd_dom{clr::target_weights(a), a->g_t, sums_t, nullptr, nullptr, a->gxt, a->gup, a->grad_scale,
                        clr::target_fmt(a), a->B_t, 0};
+    if (a->ev_bwd_begin) cudaEventRecord(static_cast<cudaEvent_t>(a->ev_bwd_begin), static_cast<cudaStream_t>(stream));
     rc = clr_pool_bwd_multi(d, 2, C, HW, K, stream);
+    if (a->ev_bwd_end) cudaEventRecord(static_cast<cudaEvent_t>(a->ev_bwd_end), static_cast<cudaStream_t>(stream));
     if (rc != CLR_OK) return rc;
     if (a->use_cons && a->w_aug != 0.f && a->g_oT_aug) {
         // stats layout expected by clr_cons_bwd: [num, den, ...] = tail[1..2] of packed2

@@ -144,8 +144,9 @@ class CLRStep:
         self.first_s, self.first_t = bool(sd["first_s"]), bool(sd["first_t"])
 
     # -- the step ------------------------------------------------------------------------------------
-    def __call__(self, xs_feature, pred_oS, xt_feature, oT_before=None, wt=None, preds=None, T: int = 8,
-                 oT=None, oT_aug=None, masks=None, epoch: float = 0.0) -> CLRStepOutput:
+    def _prepare(self, xs_feature, pred_oS, xt_feature, oT_before=None, wt=None, preds=None, T: int = 8,
+                 oT=None, oT_aug=None, masks=None, epoch: float = 0.0):
+        """Validate inputs, allocate the step's buffers and fill the C argument block."""
         lib = _lib.load()
         xs = _require_cuda_f32(xs_feature, "xs_feature")
         ys = _require_cuda_f32(pred_oS.detach(), "pred_oS")
@@ -225,12 +226,14 @@ class CLRStep:
             self._ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         a.ws, a.ws_bytes = ptr(self._ws), ws_bytes
 
-        holder = dict(args=a, buf=buf,
+        holder = dict(args=a, buf=buf, xs=xs, xt=xt, oT_aug=oTa, dims=(B_s, B_t, C, H, W, K, Hi, Wi),
                       keep=(xs, ys, xt, wt_t, oTb, pr, oT_d, oTa, self.stored_s, self.stored_t, self._ws,
                             masks_t if (use_cons and not self.retrify) else None))
-        total = _ClrStepFn.apply(self, holder, xs, xt, oTa)
-        self.first_s = self.first_t = False
+        return holder
 
+    def _outputs(self, holder, total) -> CLRStepOutput:
+        buf = holder["buf"]
+        B_s, B_t, C, H, W, K, Hi, Wi = holder["dims"]
         L = buf.losses
         R = 2 * K
         Ps = [buf.P_s[r * C:(r + 1) * C].view(1, C, 1, 1) for r in range(R)]
@@ -242,3 +245,70 @@ class CLRStep:
             mask_list = [m[:, k:k + 1] for k in range(K)]
         return CLRStepOutput(total=total, intra=L[0], inter=L[1], disc=L[2], aug=L[3], source_prototypes=Ps,
                              target_prototypes=Pt, std_map=std_map, masks=mask_list)
+
+    def __call__(self, xs_feature, pred_oS, xt_feature, oT_before=None, wt=None, preds=None, T: int = 8,
+                 oT=None, oT_aug=None, masks=None, epoch: float = 0.0) -> CLRStepOutput:
+        """One differentiable CLR step; ``out.total.backward()`` (or adding it to the trainer's ``loss_all``)
+        writes the gradients of ``xs_feature``, ``xt_feature`` (and ``oT_aug`` with ``backprop_aug``)."""
+        holder = self._prepare(xs_feature, pred_oS, xt_feature, oT_before, wt, preds, T, oT, oT_aug, masks, epoch)
+        total = _ClrStepFn.apply(self, holder, holder["xs"], holder["xt"], holder["oT_aug"])
+        self.first_s = self.first_t = False
+        return self._outputs(holder, total)
+
+    def plan(self, xs_feature, pred_oS, xt_feature, oT_before=None, wt=None, preds=None, T: int = 8,
+             oT=None, oT_aug=None, masks=None, epoch: float = 0.0) -> "CLRPlan":
+        """Bind the step to fixed input buffers (training loops that reuse their activation buffers, CUDA-graph
+        capture, the benchmark): afterwards :meth:`CLRPlan.run` is two C calls -- forward and backward -- with no
+        per-step Python work and no autograd tape."""
+        holder = self._prepare(xs_feature, pred_oS, xt_feature, oT_before, wt, preds, T, oT, oT_aug, masks, epoch)
+        return CLRPlan(self, holder)
+
+
+class CLRPlan:
+    """A prebound fused step: ``run()`` enqueues forward + backward on the current stream.
+
+    Gradients land in ``gxs`` / ``gxt`` (/ ``g_oT_aug``), losses in ``losses`` (device, ``[intra, inter, disc, aug,
+    total, ...]``); nothing is synchronised.  The EMA state advances in the owning :class:`CLRStep`.
+    """
+
+    def __init__(self, step: CLRStep, holder):
+        self.step, self.holder = step, holder
+        a: StepArgs = holder["args"]
+        buf = holder["buf"]
+        dev = buf.flat.device
+        self.gxs = torch.empty_like(holder["xs"])
+        self.gxt = torch.empty_like(holder["xt"])
+        want_aug = holder["oT_aug"] is not None and a.use_cons and a.w_aug != 0.0
+        self.g_oT_aug = torch.empty_like(holder["oT_aug"]) if want_aug else None
+        a.gxs, a.gxt, a.g_oT_aug, a.gup = ptr(self.gxs), ptr(self.gxt), ptr(self.g_oT_aug), None
+        self.losses = buf.losses
+        self.device = dev
+        self._lib = _lib.load()
+        self._ref = ctypes.byref(a)
+        self.launches_per_run: Optional[int] = None
+
+    def set_events(self, pool_begin=None, pool_end=None, bwd_begin=None, bwd_end=None) -> None:
+        """Have the library record these ``torch.cuda.Event`` objects around the pooling / backward launches."""
+        a: StepArgs = self.holder["args"]
+        a.ev_pool_begin = None if pool_begin is None else pool_begin.cuda_event
+        a.ev_pool_end = None if pool_end is None else pool_end.cuda_event
+        a.ev_bwd_begin = None if bwd_begin is None else bwd_begin.cuda_event
+        a.ev_bwd_end = None if bwd_end is None else bwd_end.cuda_event
+
+    def run(self) -> None:
+        a: StepArgs = self.holder["args"]
+        st = _stream()
+        a.first_s, a.first_t = int(self.step.first_s), int(self.step.first_t)
+        if _dist.enabled():
+            check(self._lib.clr_step_fwd_a(self._ref, st), "clr_step_fwd_a")
+            _dist.all_reduce_sums(self.holder["buf"].packed1)
+            check(self._lib.clr_step_fwd_b(self._ref, st), "clr_step_fwd_b")
+            _dist.all_reduce_sums(self.holder["buf"].packed2)
+            check(self._lib.clr_step_fwd_c(self._ref, st), "clr_step_fwd_c")
+        else:
+            check(self._lib.clr_step_fwd(self._ref, st), "clr_step_fwd")
+        check(self._lib.clr_step_bwd(self._ref, st), "clr_step_bwd")
+        self.step.first_s = self.step.first_t = False
+
+    def outputs(self) -> CLRStepOutput:
+        return self.step._outputs(self.holder, self.losses[4])
