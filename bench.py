@@ -265,8 +265,8 @@ def main():
     # ---- timed region: exactly K steps, CUDA events on the launching stream ------------------------
     K = a.steps
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    pool_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    bwd_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    pool_ev = [(_lib.Event(), _lib.Event()) for _ in range(K)]
+    bwd_ev = [(_lib.Event(), _lib.Event()) for _ in range(K)]
     launches0 = lib.clr_launch_count()
     barrier()
     sampler.mark_begin()
@@ -287,8 +287,8 @@ def main():
     if dist_on:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_per_step = float(t.item()) / K
-    pool_us = statistics.mean(b.elapsed_time(e) for b, e in pool_ev) * 1e3
-    bwd_us = statistics.mean(b.elapsed_time(e) for b, e in bwd_ev) * 1e3
+    pool_us = statistics.mean(b.elapsed_us(e) for b, e in pool_ev)
+    bwd_us = statistics.mean(b.elapsed_us(e) for b, e in bwd_ev)
     value = 2 * a.B * a.H * a.H * world / (ms_per_step * 1e-3) / 1e6
     losses = plans[0].losses.detach().cpu().tolist()
 

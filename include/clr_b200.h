@@ -58,6 +58,10 @@ int clr_device_info(int* sm_count, int* l2_bytes);
 int clr_set_tunable(const char* name, int value);
 /* Number of CUDA kernels this library has launched in this process so far (bench: "gpu_launches"). */
 unsigned long long clr_launch_count(void);
+/* cudaEvent_t helpers for clr_step_args.ev_* (the library records them around its own launches). */
+int clr_event_create(void** ev);
+int clr_event_destroy(void* ev);
+int clr_event_elapsed_us(void* begin, void* end, float* us /*valid once both events completed*/);
 
 /* ------------------------------------------------------------------------------------------------
  * Masked / confidence-weighted class-wise pooling  (replaces utils/Utils.py:114-126 -- the four

@@ -1,0 +1,138 @@
+"""Host-side logic that needs no GPU: the reference patch seam and the data-parallel decomposition
+(world_size-2 gloo run: shard -> packed sums -> all-reduce -> finalize == whole batch)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+import uda_clr_b200 as clr
+from oracle import clr_oracle as O
+from oracle import ref_import
+from uda_clr_b200 import synth
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not present")
+def test_patch_reference_rebinds_star_import_copies():
+    import datetime
+    import types
+    U = ref_import.load_utils()
+    pytz = types.ModuleType("pytz")
+    pytz.timezone = lambda n: datetime.timezone.utc
+    saved = sys.modules.get("pytz")
+    sys.modules["pytz"] = pytz
+    try:
+        import train_process.Trainer_prototype_full as TPF   # star-imports utils.Utils (:16)
+    finally:
+        if saved is not None:
+            sys.modules["pytz"] = saved
+    orig = U.gen_prototype
+    assert TPF.gen_prototype is orig
+    report = clr.patch_reference()
+    try:
+        assert U.gen_prototype is clr.gen_prototype
+        assert TPF.gen_prototype is clr.gen_prototype
+        assert TPF.gen_prototype_retrify is clr.gen_prototype_retrify
+        assert "train_process.Trainer_prototype_full" in report["gen_prototype_retrify"]
+        assert U.adaptation_factor(3.0) == clr.adaptation_factor(3.0)
+        with pytest.raises(RuntimeError):
+            clr.patch_reference()
+    finally:
+        clr.unpatch_reference()
+    assert U.gen_prototype is orig and TPF.gen_prototype is orig
+
+
+def test_drop_in_signatures_match_reference_source():
+    """Positional parameter names of the drop-ins equal the reference's (utils/Utils.py:86-311)."""
+    import inspect
+    expect = {
+        "gen_prototype": ["pred_oS", "xs_feature"],
+        "gen_prototype_src_trg": ["pred_oS", "xs_feature", "pred_oT", "xt_feature"],
+        "gen_prototype_retrify": ["oT_before", "xt_feature", "preds", "features", "T", "stride"],
+        "gen_prototype_src_trg_retrify": ["pred_oS", "xs_feature", "oT_before", "xt_feature", "preds", "features",
+                                          "T", "stride"],
+        "get_prototype_weight": ["feat", "class_num", "prototype"],
+        "adaptation_factor": ["m"],
+    }
+    for name, params in expect.items():
+        assert list(inspect.signature(getattr(clr, name)).parameters) == params
+    if ref_import.available():
+        U = ref_import.load_utils()
+        for name, params in expect.items():
+            assert list(inspect.signature(getattr(U, name)).parameters) == params
+
+
+def test_shard_bounds_cover_batch():
+    for n in (1, 7, 8, 64):
+        for world in (1, 2, 3, 8):
+            spans = [clr.dist.shard_bounds(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        clr.dist.shard_bounds(8, 2, 2)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out_q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        clr.dist.enable()
+        assert clr.dist.enabled() and clr.dist.world_size() == world and clr.dist.grad_scale() == float(world)
+        b = synth.make_batch(B=4, C=9, H=8, W=8, K=2, image_res=False, seed=77)
+        ys, xs, xt = clr.dist.shard_batch([b.ys, b.xs, b.xt], rank, world)
+        wt = torch.sigmoid(clr.dist.shard_batch([b.oT_before], rank, world)[0])
+        # per-rank packed sums (what clr_pool_fwd produces on the GPU): [2 domains][2K][C+1]
+        Ss, Ns = O.pool_sums(xs.numpy(), O.weights_complement(ys.numpy()))
+        St, Nt = O.pool_sums(xt.numpy(), O.weights_complement(wt.numpy()))
+        packed = torch.tensor(np.stack([np.concatenate([Ss, Ns[:, None]], 1), np.concatenate([St, Nt[:, None]], 1)]),
+                              dtype=torch.float64)
+        clr.dist.all_reduce_sums(packed)            # THE exchange of the path
+        g = packed.numpy()
+        glob = dict(Ss=g[0, :, :-1], Ns=g[0, :, -1], St=g[1, :, :-1], Nt=g[1, :, -1])
+        o = O.clr_step(xs.numpy(), ys.numpy(), xt.numpy(), wt.numpy(), w_intra=0.1, global_sums=glob,
+                       grad_scale=clr.dist.grad_scale())
+        out_q.put((rank, o["intra"], o["Ps"], o["gxs"], o["gxt"]))
+    finally:
+        clr.dist.disable()
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_shard_and_allreduce_equals_whole_batch():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    b = synth.make_batch(B=4, C=9, H=8, W=8, K=2, image_res=False, seed=77)
+    wt = torch.sigmoid(b.oT_before)
+    whole = O.clr_step(b.xs.numpy(), b.ys.numpy(), b.xt.numpy(), wt.numpy(), w_intra=0.1)
+    for rank, intra, Ps, gxs, gxt in res:
+        assert abs(intra - whole["intra"]) < 1e-12
+        assert np.allclose(Ps, whole["Ps"], rtol=1e-12, atol=0)
+    # DDP averages gradients: (1/G) * sum_ranks (G * local) must equal the single-process gradient
+    gxs = np.concatenate([r[3] for r in res], 0) / world
+    gxt = np.concatenate([r[4] for r in res], 0) / world
+    assert np.allclose(gxs, whole["gxs"], rtol=1e-10, atol=1e-18)
+    assert np.allclose(gxt, whole["gxt"], rtol=1e-10, atol=1e-18)

@@ -1,0 +1,147 @@
+// Stand-alone HBM bandwidth probe for sizing expectations (not part of the library).
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/bin/bwprobe tools/bwprobe.cu
+#include <cstdio>
+#include <cstdlib>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <vector>
+#include <algorithm>
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); exit(1); } } while (0)
+
+__device__ __forceinline__ float4 ldnc(const float4* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+
+template <int U>
+__global__ void __launch_bounds__(256) read_ldg(const float4* __restrict__ src, size_t n4, float* __restrict__ out) {
+    // contiguous chunk per CTA, threads stride inside
+    const size_t per = (n4 + gridDim.x - 1) / gridDim.x;
+    const size_t b = (size_t)blockIdx.x * per, e = min(b + per, n4);
+    float acc = 0.f;
+    size_t i = b + threadIdx.x;
+    for (; i + (size_t)(U - 1) * 256 < e; i += (size_t)U * 256) {
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[u] = ldnc(src + i + (size_t)u * 256);
+#pragma unroll
+        for (int u = 0; u < U; ++u) acc += v[u].x + v[u].y + v[u].z + v[u].w;
+    }
+    for (; i < e; i += 256) { float4 v = ldnc(src + i); acc += v.x + v.y + v.z + v.w; }
+    if (acc == 123.456f) out[blockIdx.x * 256 + threadIdx.x] = acc;
+}
+
+__global__ void __launch_bounds__(256) write_st(float4* __restrict__ dst, size_t n4) {
+    const size_t per = (n4 + gridDim.x - 1) / gridDim.x;
+    const size_t b = (size_t)blockIdx.x * per, e = min(b + per, n4);
+    const float4 v = make_float4(1.f, 2.f, 3.f, 4.f);
+    for (size_t i = b + threadIdx.x; i < e; i += 256) __stcs(dst + i, v);
+}
+
+__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// TMA bulk ring: one producer thread, consumers only wait/arrive (pure fetch ceiling) and read one float4 per stage
+template <int STAGE_BYTES>
+__global__ void __launch_bounds__(288, 1) read_tma(const char* __restrict__ src, size_t bytes, int stages, float* out) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)stages * STAGE_BYTES);
+    uint64_t* empty = full + 8;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < stages; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(&full[s])), "r"(1));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(&empty[s])), "r"(8));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const size_t nchunks = bytes / STAGE_BYTES;
+    const size_t per = nchunks / gridDim.x, rem = nchunks % gridDim.x;
+    const size_t b = blockIdx.x * per + min((size_t)blockIdx.x, rem);
+    const size_t e = b + per + (blockIdx.x < rem ? 1 : 0);
+    if (warp == 8) {
+        if (lane == 0) {
+            int st = 0; uint32_t ph = 0;
+            for (size_t c = b; c < e; ++c) {
+                asm volatile("{\n.reg .pred p;\nW1:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra D1;\nbra W1;\nD1:\n}\n" ::"r"(s32(&empty[st])), "r"(ph ^ 1u) : "memory");
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(&full[st])), "r"((uint32_t)STAGE_BYTES) : "memory");
+                // 8 rows of STAGE_BYTES/8 to mimic the pooling kernel's issue pattern
+                for (int j = 0; j < 8; ++j)
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(s32(smem + (size_t)st * STAGE_BYTES + j * (STAGE_BYTES / 8))), "l"(src + c * STAGE_BYTES + j * (STAGE_BYTES / 8)),
+                                   "r"((uint32_t)(STAGE_BYTES / 8)), "r"(s32(&full[st])) : "memory");
+                if (++st == stages) { st = 0; ph ^= 1u; }
+            }
+        }
+        return;
+    }
+    int st = 0; uint32_t ph = 0;
+    float acc = 0.f;
+    for (size_t c = b; c < e; ++c) {
+        asm volatile("{\n.reg .pred p;\nW2:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra D2;\nbra W2;\nD2:\n}\n" ::"r"(s32(&full[st])), "r"(ph) : "memory");
+        acc += reinterpret_cast<const float*>(smem + (size_t)st * STAGE_BYTES)[tid];
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(&empty[st])) : "memory");
+        if (++st == stages) { st = 0; ph ^= 1u; }
+    }
+    if (acc == 123.456f) out[blockIdx.x * 256 + tid] = acc;
+}
+
+template <typename F>
+float time_us(F f, int iters = 20) {
+    cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+    for (int i = 0; i < 3; ++i) f(i);
+    CK(cudaDeviceSynchronize());
+    std::vector<float> ts;
+    for (int i = 0; i < iters; ++i) {
+        CK(cudaEventRecord(a)); f(i); CK(cudaEventRecord(b)); CK(cudaEventSynchronize(b));
+        float ms; CK(cudaEventElapsedTime(&ms, a, b)); ts.push_back(ms * 1000.f);
+    }
+    std::sort(ts.begin(), ts.end());
+    return ts[ts.size() / 2];
+}
+
+int main() {
+    int sms; CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
+    const size_t sizes[] = {(size_t)128 << 20, (size_t)256 << 20, (size_t)1024 << 20};
+    const int NB = 3;
+    float* out; CK(cudaMalloc(&out, 4 << 20));
+    for (size_t bytes : sizes) {
+        char* buf[NB];
+        for (int i = 0; i < NB; ++i) { CK(cudaMalloc(&buf[i], bytes)); CK(cudaMemset(buf[i], 0, bytes)); }
+        const size_t n4 = bytes / 16;
+        printf("== %zu MiB\n", bytes >> 20);
+        for (int mult : {2, 4, 8, 16}) {
+            float t = time_us([&](int i) { read_ldg<8><<<sms * mult, 256>>>((const float4*)buf[i % NB], n4, out); });
+            printf("read_ldg U=8 grid=%dxSM  %8.2f us  %7.1f GB/s\n", mult, t, bytes / t / 1e3);
+        }
+        {
+            float t = time_us([&](int i) { read_ldg<16><<<sms * 4, 256>>>((const float4*)buf[i % NB], n4, out); });
+            printf("read_ldg U=16 grid=4xSM %8.2f us  %7.1f GB/s\n", t, bytes / t / 1e3);
+        }
+        for (int stages : {2, 3}) {
+            const size_t smem = (size_t)stages * 65536 + 128;
+            CK(cudaFuncSetAttribute(read_tma<65536>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            float t = time_us([&](int i) { read_tma<65536><<<sms, 288, smem>>>(buf[i % NB], bytes, stages, out); });
+            printf("read_tma 64KB x%d        %8.2f us  %7.1f GB/s\n", stages, t, bytes / t / 1e3);
+        }
+        for (int stages : {2, 4, 6}) {
+            const size_t smem = (size_t)stages * 32768 + 128;
+            CK(cudaFuncSetAttribute(read_tma<32768>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            float t = time_us([&](int i) { read_tma<32768><<<sms, 288, smem>>>(buf[i % NB], bytes, stages, out); });
+            printf("read_tma 32KB x%d        %8.2f us  %7.1f GB/s\n", stages, t, bytes / t / 1e3);
+        }
+        for (int mult : {4, 8, 16}) {
+            float t = time_us([&](int i) { write_st<<<sms * mult, 256>>>((float4*)buf[i % NB], n4); });
+            printf("write_st grid=%dxSM      %8.2f us  %7.1f GB/s\n", mult, t, bytes / t / 1e3);
+        }
+        {
+            float t = time_us([&](int i) { CK(cudaMemcpyAsync(buf[(i + 1) % NB], buf[i % NB], bytes, cudaMemcpyDeviceToDevice)); });
+            printf("memcpy d2d               %8.2f us  %7.1f GB/s (R+W)\n", t, 2.0 * bytes / t / 1e3);
+        }
+        for (int i = 0; i < NB; ++i) CK(cudaFree(buf[i]));
+    }
+    return 0;
+}

@@ -14,5 +14,6 @@ from .ops import (adaptation_factor, distance_weight, feat_prototype_distance, g
                   get_prototype_weight, mc_statistics, retrify_weights, weighted_prototypes)
 from .step import CLRPlan, CLRStep, CLRStepOutput, consistency_threshold, sigmoid_rampup  # noqa: F401
 from . import dist, ops  # noqa: F401
+from .patch import patch_reference, unpatch_reference  # noqa: F401
 
 __version__ = "0.1.0"

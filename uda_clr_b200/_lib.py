@@ -63,6 +63,9 @@ _SIGNATURES = {
     "clr_device_info": (c_int, [POINTER(c_int), POINTER(c_int)]),
     "clr_set_tunable": (c_int, [c_char_p, c_int]),
     "clr_launch_count": (ctypes.c_ulonglong, []),
+    "clr_event_create": (c_int, [POINTER(c_void_p)]),
+    "clr_event_destroy": (c_int, [c_void_p]),
+    "clr_event_elapsed_us": (c_int, [c_void_p, c_void_p, POINTER(c_float)]),
     "clr_pool_ws_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "clr_pool_rows_ws_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "clr_pool_rows_fwd": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, c_size_t, _P, _P]),
@@ -130,6 +133,27 @@ def check(status: int, what: str) -> None:
     if status != 0:
         msg = load().clr_status_string(status)
         raise ClrError("%s failed: %s (status %d)" % (what, msg.decode() if msg else "?", status))
+
+
+class Event:
+    """A CUDA timing event owned by the library (recorded by the library around its own launches)."""
+
+    def __init__(self):
+        h = c_void_p()
+        check(load().clr_event_create(ctypes.byref(h)), "clr_event_create")
+        self.handle = h.value
+
+    def elapsed_us(self, end: "Event") -> float:
+        us = c_float()
+        check(load().clr_event_elapsed_us(self.handle, end.handle, ctypes.byref(us)), "clr_event_elapsed_us")
+        return float(us.value)
+
+    def __del__(self):
+        try:
+            if self.handle and _lib is not None:
+                _lib.clr_event_destroy(self.handle)
+        except Exception:
+            pass
 
 
 def ptr(t):

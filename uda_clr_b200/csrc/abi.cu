@@ -25,7 +25,7 @@ static unsigned long long g_launches = 0;
 void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
 
 Tunables& tunables() {
-    static Tunables t{0, 0, 0, 0};
+    static Tunables t{0, 0, 0, 0, 0};
     return t;
 }
 
@@ -42,6 +42,7 @@ int clr_set_tunable(const char* name, int value) {
     else if (!strcmp(name, "pool_stages")) t.pool_stages = value;
     else if (!strcmp(name, "dots_impl")) t.dots_impl = value;
     else if (!strcmp(name, "bwd_impl")) t.bwd_impl = value;
+    else if (!strcmp(name, "mc_precise")) t.mc_precise = value;
     else return CLR_ERR_BAD_ARG;
     return CLR_OK;
 }
@@ -61,6 +62,27 @@ const char* clr_status_string(int status) {
     }
     if (status <= CLR_ERR_CUDA_BASE) return cudaGetErrorString((cudaError_t)(CLR_ERR_CUDA_BASE - status));
     return "unknown status";
+}
+
+/* Timing events for harnesses that want the library to bracket its own launches (clr_step_args.ev_*). */
+int clr_event_create(void** ev) {
+    if (!ev) return CLR_ERR_BAD_ARG;
+    cudaEvent_t e;
+    CLR_RETURN_IF_CUDA(cudaEventCreate(&e));
+    *ev = e;
+    return CLR_OK;
+}
+int clr_event_destroy(void* ev) {
+    if (!ev) return CLR_ERR_BAD_ARG;
+    CLR_RETURN_IF_CUDA(cudaEventDestroy(static_cast<cudaEvent_t>(ev)));
+    return CLR_OK;
+}
+int clr_event_elapsed_us(void* begin, void* end, float* us) {
+    if (!begin || !end || !us) return CLR_ERR_BAD_ARG;
+    float ms = 0.f;
+    CLR_RETURN_IF_CUDA(cudaEventElapsedTime(&ms, static_cast<cudaEvent_t>(begin), static_cast<cudaEvent_t>(end)));
+    *us = ms * 1000.f;
+    return CLR_OK;
 }
 
 int clr_device_info(int* sm_count, int* l2_bytes) {

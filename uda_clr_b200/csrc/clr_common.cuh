@@ -31,6 +31,7 @@ struct Tunables {
     int pool_stages;   // TMA ring depth (0 = auto)
     int dots_impl;     // 0 = auto, 1 = force the LDG kernel
     int bwd_impl;      // reserved
+    int mc_precise;    // 1 = ATen-exact sigmoids in clr_mc_stats (slower), 0 = fast intrinsics
 };
 Tunables& tunables();
 

@@ -14,57 +14,99 @@
 
 namespace clr {
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float sigmoid_aten(float x) { return 1.0f / (1.0f + expf(-x)); }   // label decision: exact
+__device__ __forceinline__ float sigmoid_fast(float x) { return __frcp_rn(1.0f + __expf(-x)); }
 
 struct ConsGeom {
-    int B, K, Hi, Wi, H, W;
+    int BK, Hi, Wi, H, W;
     float sh, sw;   // nearest scales: (float)H/Hi, (float)W/Wi
+    int rows_per_cta;
 };
 
-__device__ __forceinline__ float mask_at(const float* __restrict__ masks, const ConsGeom& g, size_t i) {
-    const int x = (int)(i % g.Wi);
-    const int y = (int)((i / g.Wi) % g.Hi);
-    const size_t bk = i / ((size_t)g.Wi * g.Hi);
-    int sy = (int)floorf((float)y * g.sh); if (sy > g.H - 1) sy = g.H - 1;
-    int sx = (int)floorf((float)x * g.sw); if (sx > g.W - 1) sx = g.W - 1;
-    return __ldg(masks + (bk * g.H + sy) * g.W + sx);
+// F.interpolate(mode='nearest') source index: min(floor(dst * scale), in - 1)
+__device__ __forceinline__ int nearest_src(int dst, float scale, int n_in) {
+    const int s = (int)floorf((float)dst * scale);
+    return s < n_in - 1 ? s : n_in - 1;
 }
 
-__global__ void __launch_bounds__(256) cons_fwd_kernel(const float* __restrict__ oT, const float* __restrict__ oT_aug,
-                                                       const float* __restrict__ masks, ConsGeom g, float thr,
-                                                       size_t n, double* __restrict__ partial) {
-    double num = 0.0, den = 0.0;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const float m = mask_at(masks, g, i);
-        const float y = sigmoidf_(__ldg(oT + i)) > thr ? 1.0f : 0.0f;
-        const float q = sigmoidf_(__ldg(oT_aug + i));
-        const float lq = fmaxf(logf(q), -100.0f);
-        const float l1q = fmaxf(log1pf(-q), -100.0f);
-        const float l = (y - 1.0f) * l1q - y * lq;
-        num += (double)(m * l);
-        den += (double)m;
+// One element of the masked BCE: returns m*l and m; `y` decided exactly, the log terms through fast intrinsics.
+__device__ __forceinline__ void cons_elem(float zt, float za, float m, float thr, float& ml, float& q_out, float& y_out) {
+    const float y = sigmoid_aten(zt) > thr ? 1.0f : 0.0f;
+    const float q = sigmoid_fast(za);
+    const float lq = fmaxf(__logf(q), -100.0f);
+    const float l1q = fmaxf(__logf(1.0f - q), -100.0f);   // ATen: log1p(-q); identical after fp32 rounding of q
+    ml = m * ((y - 1.0f) * l1q - y * lq);
+    q_out = q; y_out = y;
+}
+
+// grid = (row blocks, B*K planes); each CTA covers `rows_per_cta` image rows of one plane.
+template <int VEC, bool BWD>
+__global__ void __launch_bounds__(256) cons_kernel(const float* __restrict__ oT, const float* __restrict__ oT_aug,
+                                                   const float* __restrict__ masks, ConsGeom g, float thr,
+                                                   double* __restrict__ partial,
+                                                   const float* __restrict__ stats, const float* __restrict__ gscale_dev,
+                                                   float gscale, float* __restrict__ grad) {
+    const int bk = blockIdx.y;
+    const int y0 = blockIdx.x * g.rows_per_cta;
+    const int wv = g.Wi / VEC;                       // vectors per row
+    const int nvec = g.rows_per_cta * wv;
+    const size_t plane = (size_t)bk * g.Hi * g.Wi;
+    const float* mplane = masks + (size_t)bk * g.H * g.W;
+    float coef = 0.f;
+    if (BWD) coef = (gscale_dev ? gscale * __ldg(gscale_dev) : gscale) / __ldg(stats + 1);
+    float num = 0.f, den = 0.f;
+    for (int idx = threadIdx.x; idx < nvec; idx += blockDim.x) {
+        const int ry = idx / wv, xv = idx - ry * wv;
+        const int y = y0 + ry;
+        if (y >= g.Hi) break;
+        const int sy = nearest_src(y, g.sh, g.H);
+        const size_t off = plane + (size_t)y * g.Wi + (size_t)xv * VEC;
+        const Pack<VEC> zt = ld_stream<VEC>(oT + off);
+        const Pack<VEC> za = ld_stream<VEC>(oT_aug + off);
+        Pack<VEC> go;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            const int sx = nearest_src(xv * VEC + v, g.sw, g.W);
+            const float m = __ldg(mplane + (size_t)sy * g.W + sx);
+            float ml, q, yv;
+            cons_elem(zt.v[v], za.v[v], m, thr, ml, q, yv);
+            num += ml; den += m;
+            if (BWD) {
+                // ATen binary_cross_entropy_backward: (q - y) / max((1-q) q, 1e-12), chained with sigmoid' = q (1-q)
+                const float qq = (1.0f - q) * q;
+                go.v[v] = coef * m * (q - yv) / fmaxf(qq, 1e-12f) * qq;
+            }
+        }
+        if (BWD) st_stream<VEC>(grad + off, go);
     }
-    num = warp_sum(num);
-    den = warp_sum(den);
-    __shared__ double sh[2][8];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) { sh[0][warp] = num; sh[1][warp] = den; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double a = 0.0, b = 0.0;
-        for (int w = 0; w < 8; ++w) { a += sh[0][w]; b += sh[1][w]; }
-        partial[2 * blockIdx.x] = a;
-        partial[2 * blockIdx.x + 1] = b;
+    if (!BWD) {
+        double dn = warp_sum((double)num), dd = warp_sum((double)den);
+        __shared__ double sh[2][8];
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        if (lane == 0) { sh[0][warp] = dn; sh[1][warp] = dd; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double a = 0.0, b = 0.0;
+            for (int w = 0; w < 8; ++w) { a += sh[0][w]; b += sh[1][w]; }
+            const int cta = blockIdx.y * gridDim.x + blockIdx.x;
+            partial[2 * cta] = a;
+            partial[2 * cta + 1] = b;
+        }
     }
 }
 
-__global__ void cons_final_kernel(const double* __restrict__ partial, int nblk, float aug_weight, float* __restrict__ stats) {
-    // one warp, fixed order
+__global__ void __launch_bounds__(256) cons_final_kernel(const double* __restrict__ partial, int nblk, float aug_weight,
+                                                         float* __restrict__ stats) {
     double a = 0.0, b = 0.0;
-    for (int i = threadIdx.x; i < nblk; i += 32) { a += partial[2 * i]; b += partial[2 * i + 1]; }
+    for (int i = threadIdx.x; i < nblk; i += blockDim.x) { a += partial[2 * i]; b += partial[2 * i + 1]; }
     a = warp_sum(a);
     b = warp_sum(b);
+    __shared__ double sh[2][8];
+    if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = a; sh[1][threadIdx.x >> 5] = b; }
+    __syncthreads();
     if (threadIdx.x == 0) {
+        a = 0.0; b = 0.0;
+        for (int w = 0; w < 8; ++w) { a += sh[0][w]; b += sh[1][w]; }
         stats[0] = (float)a;
         stats[1] = (float)b;
         stats[2] = (float)(a / b * (double)aug_weight);
@@ -72,34 +114,29 @@ __global__ void cons_final_kernel(const double* __restrict__ partial, int nblk, 
     }
 }
 
-__global__ void __launch_bounds__(256) cons_bwd_kernel(const float* __restrict__ oT, const float* __restrict__ oT_aug,
-                                                       const float* __restrict__ masks, ConsGeom g, float thr,
-                                                       const float* __restrict__ stats, const float* __restrict__ gscale_dev,
-                                                       float gscale, size_t n, float* __restrict__ grad) {
-    const float coef = (gscale_dev ? gscale * __ldg(gscale_dev) : gscale) / __ldg(stats + 1);
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const float m = mask_at(masks, g, i);
-        const float y = sigmoidf_(__ldg(oT + i)) > thr ? 1.0f : 0.0f;
-        const float q = sigmoidf_(__ldg(oT_aug + i));
-        const float qq = (1.0f - q) * q;
-        const float gq = coef * m * (q - y) / fmaxf(qq, 1e-12f);
-        grad[i] = gq * qq;
-    }
-}
+constexpr int kConsMaxBlocks = 2048;
 
-static ConsGeom make_geom(int B, int K, int Hi, int Wi, int H, int W) {
-    ConsGeom g{B, K, Hi, Wi, H, W, (float)H / (float)Hi, (float)W / (float)Wi};
+// rows per CTA so that the grid stays <= kConsMaxBlocks CTAs and every CTA has >= 4 vectors per thread
+static ConsGeom make_geom(int B, int K, int Hi, int Wi, int H, int W, dim3& grid) {
+    ConsGeom g{B * K, Hi, Wi, H, W, (float)H / (float)Hi, (float)W / (float)Wi, 1};
+    int rows = (4 * 256 * 4 + Wi - 1) / Wi;
+    if (rows < 1) rows = 1;
+    while ((long long)((Hi + rows - 1) / rows) * B * K > kConsMaxBlocks && rows < Hi) rows *= 2;
+    g.rows_per_cta = rows;
+    grid = dim3((unsigned)((Hi + rows - 1) / rows), (unsigned)(B * K));
     return g;
 }
 
-constexpr int kConsMaxBlocks = 148 * 8;
-
 int cons_fwd_partials(const float* oT, const float* oT_aug, const float* masks, int B, int K, int Hi, int Wi,
                       int H, int W, float threshold, double* partial, int* nblocks, cudaStream_t st) {
-    const size_t n = (size_t)B * K * Hi * Wi;
-    const int blocks = (int)((n + 255) / 256 < (size_t)kConsMaxBlocks ? (n + 255) / 256 : (size_t)kConsMaxBlocks);
-    clr::count_launch(); cons_fwd_kernel<<<blocks, 256, 0, st>>>(oT, oT_aug, masks, make_geom(B, K, Hi, Wi, H, W), threshold, n, partial);
-    *nblocks = blocks;
+    dim3 grid;
+    const ConsGeom g = make_geom(B, K, Hi, Wi, H, W, grid);
+    if ((long long)grid.x * grid.y > kConsMaxBlocks || grid.y > 65535) return CLR_ERR_UNSUPPORTED;
+    const bool vec4 = (Wi % 4 == 0) && aligned16(oT) && aligned16(oT_aug);
+    count_launch();
+    if (vec4) cons_kernel<4, false><<<grid, 256, 0, st>>>(oT, oT_aug, masks, g, threshold, partial, nullptr, nullptr, 0.f, nullptr);
+    else cons_kernel<1, false><<<grid, 256, 0, st>>>(oT, oT_aug, masks, g, threshold, partial, nullptr, nullptr, 0.f, nullptr);
+    *nblocks = (int)(grid.x * grid.y);
     return launch_status();
 }
 
@@ -117,7 +154,7 @@ int clr_cons_fwd(const float* oT, const float* oT_aug, const float* masks, int B
     int blocks = 0;
     const int rc = clr::cons_fwd_partials(oT, oT_aug, masks, B, K, Hi, Wi, H, W, threshold, static_cast<double*>(ws), &blocks, st);
     if (rc != CLR_OK) return rc;
-    clr::count_launch(); clr::cons_final_kernel<<<1, 32, 0, st>>>(static_cast<const double*>(ws), blocks, aug_weight, stats);
+    clr::count_launch(); clr::cons_final_kernel<<<1, 256, 0, st>>>(static_cast<const double*>(ws), blocks, aug_weight, stats);
     return clr::launch_status();
 }
 
@@ -126,10 +163,14 @@ int clr_cons_bwd(const float* oT, const float* oT_aug, const float* masks, int B
                  float* grad_oT_aug, clr_stream_t stream) {
     if (!oT || !oT_aug || !masks || !stats || !grad_oT_aug || B < 1 || K < 1 || Hi < 1 || Wi < 1 || H < 1 || W < 1)
         return CLR_ERR_BAD_ARG;
-    const size_t n = (size_t)B * K * Hi * Wi;
-    int blocks = (int)((n + 255) / 256 < (size_t)clr::kConsMaxBlocks * 2 ? (n + 255) / 256 : (size_t)clr::kConsMaxBlocks * 2);
-    clr::count_launch(); clr::cons_bwd_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        oT, oT_aug, masks, clr::make_geom(B, K, Hi, Wi, H, W), threshold, stats, gscale_dev, gscale * aug_weight, n, grad_oT_aug);
+    dim3 grid;
+    const clr::ConsGeom g = clr::make_geom(B, K, Hi, Wi, H, W, grid);
+    if (grid.y > 65535) return CLR_ERR_UNSUPPORTED;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool vec4 = (Wi % 4 == 0) && clr::aligned16(oT) && clr::aligned16(oT_aug) && clr::aligned16(grad_oT_aug);
+    clr::count_launch();
+    if (vec4) clr::cons_kernel<4, true><<<grid, 256, 0, st>>>(oT, oT_aug, masks, g, threshold, nullptr, stats, gscale_dev, gscale * aug_weight, grad_oT_aug);
+    else clr::cons_kernel<1, true><<<grid, 256, 0, st>>>(oT, oT_aug, masks, g, threshold, nullptr, stats, gscale_dev, gscale * aug_weight, grad_oT_aug);
     return clr::launch_status();
 }
 

@@ -15,71 +15,83 @@
 
 namespace clr {
 
-__device__ __forceinline__ double block_sum(double v, double* sh) {
-    v = warp_sum(v);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// Block-wide sums of NV doubles at once (one pair of barriers): result valid in every thread.
+template <int NV>
+__device__ __forceinline__ void block_sum_n(double (&v)[NV], double* sh /*[NV][32]*/) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) sh[i * 32 + warp] = v[i];
+    }
     __syncthreads();
-    if (lane == 0) sh[warp] = v;
-    __syncthreads();
-    double t = 0.0;
-    const int nw = (blockDim.x + 31) >> 5;
-    for (int i = 0; i < nw; ++i) t += sh[i];
-    return t;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        double t = 0.0;
+        for (int w = 0; w < nw; ++w) t += sh[i * 32 + w];
+        v[i] = t;
+    }
 }
 
-__global__ void __launch_bounds__(256) align_finalize_kernel(
+// One thread per (class k, channel c): it owns BOTH rows k (obj) and K+k (bck) of both domains, so the EMA
+// state can be updated in place with no cross-thread hazard and no second pass.
+__global__ void __launch_bounds__(1024) align_finalize_kernel(
     const float* __restrict__ sums_s, const float* __restrict__ sums_t, int K, int C,
     float* __restrict__ stored_s, float* __restrict__ stored_t, int first_s, int first_t, double decay,
     float w_intra, float w_inter,
     float* __restrict__ P_s, float* __restrict__ P_t, float* __restrict__ cur_s, float* __restrict__ cur_t,
     float* __restrict__ g_s, float* __restrict__ g_t,
     float* __restrict__ disc_vec, float* __restrict__ disc_beta, float* __restrict__ losses) {
-    __shared__ double sh[8];
-    const int R = 2 * K;
+    __shared__ double sh[(2 + CLR_MAX_K) * 32];
     const float d = (float)decay, omd = (float)(1.0 - decay);   // the reference forms (1 - decay) in double, then casts
     const float ds = first_s ? 1.f : d, dt = first_t ? 1.f : d;
-    double intra = 0.0, inter = 0.0;
-    // pass 1: prototypes, EMA, intra
-    for (int i = threadIdx.x; i < R * C; i += blockDim.x) {
-        const int r = i / C, c = i - r * C;
-        const float cs = sums_s[(size_t)r * (C + 1) + c] / sums_s[(size_t)r * (C + 1) + C];
-        const float ct = sums_t[(size_t)r * (C + 1) + c] / sums_t[(size_t)r * (C + 1) + C];
-        const float ps = first_s ? cs : __fadd_rn(__fmul_rn(omd, stored_s[i]), __fmul_rn(d, cs));
-        const float pt = first_t ? ct : __fadd_rn(__fmul_rn(omd, stored_t[i]), __fmul_rn(d, ct));
-        if (cur_s) cur_s[i] = cs;
-        if (cur_t) cur_t[i] = ct;
-        P_s[i] = ps; P_t[i] = pt;
-        stored_s[i] = ps; stored_t[i] = pt;       // .detach() copies (Trainer_prototype_full.py:341-344)
-        const double df = (double)ps - (double)pt;
-        intra += df * df;
-        const float gi = w_intra * 2.0f * (ps - pt) / (float)C;
-        g_s[i] = ds * gi;
-        g_t[i] = -dt * gi;
-    }
-    __syncthreads();   // P_s complete (same CTA wrote it)
-    // pass 2: inter loss + its gradient, discriminative vectors
-    for (int k = 0; k < K; ++k) {
-        double nb = 0.0;
-        for (int c = threadIdx.x; c < C; c += blockDim.x) {
-            const float po = P_s[(size_t)k * C + c], pb = P_s[(size_t)(K + k) * C + c];
-            const float df = po - pb;
-            inter += (double)df * df;
-            if (w_inter != 0.f) {
-                const float gi = ds * w_inter * 2.0f * df / (float)C;
-                g_s[(size_t)k * C + c] += gi;
-                g_s[(size_t)(K + k) * C + c] -= gi;
-            }
-            if (disc_vec) disc_vec[(size_t)k * C + c] = df;
-            nb += (double)po * po - (double)pb * pb;
+    const float invC = 1.0f / (float)C;
+    double acc[2 + CLR_MAX_K];   // intra, inter, nb_0 .. nb_{K-1}
+#pragma unroll
+    for (int i = 0; i < 2 + CLR_MAX_K; ++i) acc[i] = 0.0;
+    for (int i = threadIdx.x; i < K * C; i += blockDim.x) {
+        const int k = i / C, c = i - k * C;
+        float ps[2], pt[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int r = k + h * K;
+            const size_t e = (size_t)r * C + c;
+            const float cs = sums_s[(size_t)r * (C + 1) + c] / sums_s[(size_t)r * (C + 1) + C];   // utils/Utils.py:127-130
+            const float ct = sums_t[(size_t)r * (C + 1) + c] / sums_t[(size_t)r * (C + 1) + C];
+            ps[h] = first_s ? cs : __fadd_rn(__fmul_rn(omd, stored_s[e]), __fmul_rn(d, cs));
+            pt[h] = first_t ? ct : __fadd_rn(__fmul_rn(omd, stored_t[e]), __fmul_rn(d, ct));
+            if (cur_s) cur_s[e] = cs;
+            if (cur_t) cur_t[e] = ct;
+            P_s[e] = ps[h]; P_t[e] = pt[h];
+            stored_s[e] = ps[h]; stored_t[e] = pt[h];     // .detach() copies (Trainer_prototype_full.py:341-344)
+            const double df = (double)ps[h] - (double)pt[h];
+            acc[0] += df * df;
         }
-        nb = block_sum(nb, sh);
-        if (threadIdx.x == 0 && disc_beta) disc_beta[k] = (float)(nb / C);
+        const float dob = ps[0] - ps[1];                    // P_obj,k - P_bck,k
+        acc[1] += (double)dob * dob;
+        const float gsep = ds * w_inter * 2.0f * dob * invC;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const size_t e = (size_t)(k + h * K) * C + c;
+            const float gi = w_intra * 2.0f * (ps[h] - pt[h]) * invC;
+            g_s[e] = ds * gi + (h == 0 ? gsep : -gsep);
+            g_t[e] = -dt * gi;
+        }
+        if (disc_vec) disc_vec[i] = dob;
+#pragma unroll
+        for (int kk = 0; kk < CLR_MAX_K; ++kk)
+            if (kk == k) acc[2 + kk] += (double)ps[0] * ps[0] - (double)ps[1] * ps[1];
     }
-    intra = block_sum(intra, sh);
-    inter = block_sum(inter, sh);
+    block_sum_n<2 + CLR_MAX_K>(acc, sh);
     if (threadIdx.x == 0) {
-        losses[0] = (float)(intra / C);
-        losses[1] = (float)(inter / C);
+        losses[0] = (float)(acc[0] / C);
+        losses[1] = (float)(acc[1] / C);
+    }
+    if (disc_beta && threadIdx.x == 0) {
+#pragma unroll
+        for (int kk = 0; kk < CLR_MAX_K; ++kk)
+            if (kk < K) disc_beta[kk] = (float)(acc[2 + kk] / C);
     }
 }
 
@@ -111,21 +123,23 @@ __global__ void __launch_bounds__(256) disc_finalize_kernel(
     }
 }
 
-// Sum the hinge per-CTA partials and the consistency per-CTA partials into the tail of packed2 (one warp).
-__global__ void step_pack_kernel(const float* __restrict__ hinge_partials, int n_hinge, int hinge_stride,
-                                 const double* __restrict__ cons_partials, int n_cons, float* __restrict__ tail) {
-    double a = 0.0, b = 0.0, c = 0.0;
+// Sum the hinge per-CTA partials and the consistency per-CTA partials into the tail of packed2 (fixed order).
+__global__ void __launch_bounds__(256) step_pack_kernel(const float* __restrict__ hinge_partials, int n_hinge, int hinge_stride,
+                                                        const double* __restrict__ cons_partials, int n_cons,
+                                                        float* __restrict__ tail) {
+    __shared__ double sh[3 * 32];
+    double v[3] = {0.0, 0.0, 0.0};
     if (hinge_partials)
-        for (int i = threadIdx.x; i < n_hinge; i += 32) a += (double)hinge_partials[(size_t)i * hinge_stride];
+        for (int i = threadIdx.x; i < n_hinge; i += blockDim.x) v[0] += (double)hinge_partials[(size_t)i * hinge_stride];
     if (cons_partials)
-        for (int i = threadIdx.x; i < n_cons; i += 32) { b += cons_partials[2 * i]; c += cons_partials[2 * i + 1]; }
-    a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
-    if (threadIdx.x == 0) { tail[0] = (float)a; tail[1] = (float)b; tail[2] = (float)c; tail[3] = 0.f; }
+        for (int i = threadIdx.x; i < n_cons; i += blockDim.x) { v[1] += cons_partials[2 * i]; v[2] += cons_partials[2 * i + 1]; }
+    block_sum_n<3>(v, sh);
+    if (threadIdx.x == 0) { tail[0] = (float)v[0]; tail[1] = (float)v[1]; tail[2] = (float)v[2]; tail[3] = 0.f; }
 }
 
 void launch_step_pack(const float* hinge_partials, int n_hinge, int hinge_stride,
                       const double* cons_partials, int n_cons, float* tail, cudaStream_t st) {
-    clr::count_launch(); step_pack_kernel<<<1, 32, 0, st>>>(hinge_partials, n_hinge, hinge_stride, cons_partials, n_cons, tail);
+    clr::count_launch(); step_pack_kernel<<<1, 256, 0, st>>>(hinge_partials, n_hinge, hinge_stride, cons_partials, n_cons, tail);
 }
 
 }  // namespace clr
@@ -140,7 +154,7 @@ int clr_align_finalize(const float* sums_s, const float* sums_t, int K, int C,
     if (!sums_s || !sums_t || !stored_s || !stored_t || !P_s || !P_t || !g_s || !g_t || !losses ||
         K < 1 || K > CLR_MAX_K || C < 1)
         return CLR_ERR_BAD_ARG;
-    clr::count_launch(); clr::align_finalize_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    clr::count_launch(); clr::align_finalize_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(
         sums_s, sums_t, K, C, stored_s, stored_t, first_s, first_t, decay, w_intra, w_inter,
         P_s, P_t, cur_s, cur_t, g_s, g_t, disc_vec, disc_beta, losses);
     return clr::launch_status();

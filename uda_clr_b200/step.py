@@ -288,12 +288,13 @@ class CLRPlan:
         self.launches_per_run: Optional[int] = None
 
     def set_events(self, pool_begin=None, pool_end=None, bwd_begin=None, bwd_end=None) -> None:
-        """Have the library record these ``torch.cuda.Event`` objects around the pooling / backward launches."""
+        """Have the library record these :class:`uda_clr_b200._lib.Event` objects around the pooling / backward
+        launches of the next :meth:`run` (``None`` = do not record)."""
         a: StepArgs = self.holder["args"]
-        a.ev_pool_begin = None if pool_begin is None else pool_begin.cuda_event
-        a.ev_pool_end = None if pool_end is None else pool_end.cuda_event
-        a.ev_bwd_begin = None if bwd_begin is None else bwd_begin.cuda_event
-        a.ev_bwd_end = None if bwd_end is None else bwd_end.cuda_event
+        a.ev_pool_begin = None if pool_begin is None else pool_begin.handle
+        a.ev_pool_end = None if pool_end is None else pool_end.handle
+        a.ev_bwd_begin = None if bwd_begin is None else bwd_begin.handle
+        a.ev_bwd_end = None if bwd_end is None else bwd_end.handle
 
     def run(self) -> None:
         a: StepArgs = self.holder["args"]
