@@ -53,8 +53,9 @@ int clr_version(void);
 const char* clr_status_string(int status);
 /* Number of SMs / L2 bytes of the current device (grid sizing is derived from it; exposed for the bench). */
 int clr_device_info(int* sm_count, int* l2_bytes);
-/* Benchmark knobs (process-wide): "pool_impl" 0 auto / 1 LDG kernel, "pool_stages" TMA ring depth,
- * "dots_impl", "bwd_impl".  Defaults select the fastest path; results are identical either way. */
+/* Benchmark / debugging knobs (process-wide): "pool_impl" 0 auto / 1 LDG kernel, "pool_stages" TMA ring
+ * depth, "disc_impl" 0 fused / 1 two-pass, "mc_precise" 1 = ATen-exact sigmoids in clr_mc_stats.
+ * Defaults select the fastest path. */
 int clr_set_tunable(const char* name, int value);
 /* Number of CUDA kernels this library has launched in this process so far (bench: "gpu_launches"). */
 unsigned long long clr_launch_count(void);
@@ -145,6 +146,16 @@ int clr_disc_fwd(const float* xs, const float* ys, int B, int C, int HW, int K,
                  const float* disc_vec /*[K][C]*/, const float* disc_beta /*[K]*/, float margin,
                  float* coef /*[B,K,HW] out*/, float* delta /*[B,K,HW] out or NULL*/,
                  float* partials /*[cap][1+K]*/, int partials_cap, int* nparts /*host out*/, clr_stream_t stream);
+
+/* One-read form of the same pass: dot products AND the active-set sums A_k[c] = sum_p coef_k(p) x[c,p] from a
+ * shared-memory tile (TMA bulk ring).  packed2 = [K][C+1] (col C = sum of coefficients) followed by
+ * { hinge numerator, 0, 0, 0 }.  Returns CLR_ERR_UNSUPPORTED for ragged / very wide inputs: use the two-pass
+ * form above then. */
+size_t clr_disc_fused_ws_bytes(int C, int K);
+int clr_disc_fused_fwd(const float* xs, const float* ys, int B, int C, int HW, int K,
+                       const float* disc_vec, const float* disc_beta, float margin,
+                       float* coef /*[B,K,HW] out*/, float* delta /*or NULL*/, void* ws, size_t ws_bytes,
+                       float* packed2 /*[K][C+1] + 4 out*/, clr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * MC-dropout statistics + retrify weights (utils/Utils.py:161-223).

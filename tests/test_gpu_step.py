@@ -216,3 +216,64 @@ def test_fused_step_vs_eager_port_on_gpu():
         g1, g2 = xs1.grad.cpu().numpy(), xs2.grad.cpu().numpy()
         bad = np.abs(g1 - g2) > TOL_GRAD * np.abs(g2).max()
         assert bad.mean() < 1e-4, bad.mean()
+
+
+# ------------------------------------------------------------------------------------------------ A9 kernels
+@pytest.mark.parametrize("B,C,H,W,K", [(2, 24, 32, 32, 2), (1, 305, 32, 48, 2), (2, 40, 16, 16, 3), (1, 600, 16, 16, 2),
+                                       (2, 33, 10, 10, 2)])
+def test_disc_fused_and_two_pass_agree_with_oracle(B, C, H, W, K):
+    """The one-read discriminative kernel and the two-pass form vs the oracle: loss numerator, coefficient
+    planes (integer-valued for hard labels: bit-exact away from the hinge kink) and active-set sums."""
+    import ctypes
+    from uda_clr_b200 import _lib
+    from uda_clr_b200._lib import check, ptr
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(C)
+    y = synth.nested_ellipse_labels(B, K, H, W, g)
+    x = synth.class_shifted_features(y, C, g)
+    P = 0.4 * torch.randn(2 * K, C, generator=g)
+    loss, aux = O.disc_loss(x.numpy(), y.numpy(), P.numpy(), 0.01)
+    edge = np.minimum(np.abs(aux["delta"] + 0.01), np.abs(0.01 - aux["delta"])).min()
+    assert edge > 1e-6
+    coef_ref = aux["coef"]
+    A_ref = np.einsum("bkp,bcp->kc", coef_ref.reshape(B, K, -1), x.numpy().reshape(B, C, -1).astype(np.float64))
+    HW = H * W
+    xs, ys = x.to(DEV), y.to(DEV)
+    D = (P[:K] - P[K:]).contiguous().to(DEV)
+    beta = (((P[:K].double() ** 2).sum(1) - (P[K:].double() ** 2).sum(1)) / C).float().to(DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    results = {}
+    # one-read kernel
+    ws_bytes = lib.clr_disc_fused_ws_bytes(C, K)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=DEV)
+    coef = torch.empty(B, K, H, W, device=DEV)
+    delta = torch.empty(B, K, H, W, device=DEV)
+    packed2 = torch.empty(K * (C + 1) + 4, device=DEV)
+    rc = lib.clr_disc_fused_fwd(ptr(xs), ptr(ys), B, C, HW, K, ptr(D), ptr(beta), 0.01, ptr(coef), ptr(delta), ptr(ws),
+                                ws_bytes, ptr(packed2), st)
+    if HW % 4 == 0:
+        check(rc, "clr_disc_fused_fwd")
+        results["fused"] = (coef.cpu().numpy(), packed2.cpu().numpy(), delta.cpu().numpy())
+    else:
+        assert rc == -4          # CLR_ERR_UNSUPPORTED: ragged planes take the two-pass form
+    # two-pass form
+    cap = lib.clr_disc_partials_cap()
+    parts = torch.zeros(cap, 1 + K, device=DEV)
+    coef2 = torch.empty(B, K, H, W, device=DEV)
+    n = ctypes.c_int(0)
+    check(lib.clr_disc_fwd(ptr(xs), ptr(ys), B, C, HW, K, ptr(D), ptr(beta), 0.01, ptr(coef2), None, ptr(parts), cap,
+                           ctypes.byref(n), st), "clr_disc_fwd")
+    wsr = lib.clr_pool_rows_ws_bytes(B, C, HW, K)
+    ws2 = torch.empty(wsr, dtype=torch.uint8, device=DEV)
+    sums = torch.empty(K, C + 1, device=DEV)
+    check(lib.clr_pool_rows_fwd(ptr(xs), ptr(coef2), B, C, HW, K, ptr(ws2), wsr, ptr(sums), st), "clr_pool_rows_fwd")
+    num = parts[:n.value, 0].double().sum().item()
+    results["two_pass"] = (coef2.cpu().numpy(), np.concatenate([sums.cpu().numpy().reshape(-1), [num, 0, 0, 0]]), None)
+    for name, (cf, pk, dl) in results.items():
+        assert np.array_equal(cf, coef_ref.astype(np.float32)), name       # integer-valued: bit-exact
+        Ak = pk[:K * (C + 1)].reshape(K, C + 1)
+        assert relerr(Ak[:, :C], A_ref) < 1e-5, name
+        assert np.array_equal(Ak[:, C], coef_ref.reshape(B, K, -1).sum(axis=(0, 2)).astype(np.float32)), name
+        assert abs(pk[K * (C + 1)] / (B * HW) - loss) < TOL_LOSS * abs(loss), name
+        if dl is not None:
+            assert np.abs(dl - aux["delta"]).max() < 1e-5 * max(1.0, np.abs(aux["delta"]).max())

@@ -29,7 +29,8 @@ const DeviceFacts& device_facts();
 struct Tunables {
     int pool_impl;     // 0 = auto (TMA ring when aligned), 1 = force the LDG kernel
     int pool_stages;   // TMA ring depth (0 = auto)
-    int dots_impl;     // 0 = auto, 1 = force the LDG kernel
+    int dots_impl;     // reserved
+    int disc_impl;     // 0 = auto (one-read fused discriminative kernel), 1 = force the two-pass form
     int bwd_impl;      // reserved
     int mc_precise;    // 1 = ATen-exact sigmoids in clr_mc_stats (slower), 0 = fast intrinsics
 };

@@ -9,6 +9,13 @@ int pool_fwd_impl(const float* feat0, const float* w0, int fmt0, int B0, float* 
                   const float* feat1, const float* w1, int fmt1, int B1, float* sums1,
                   int C, int HW, int R, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t pool_partial_bytes(int B, int C, int HW, int R);
+// sums[r][c] = sum_slot partial[slot][r][c] (fp64, fixed order) for a [slots][R][C+1] partial buffer
+void launch_partial_reduce(const float* partial, int slots, int R, int C, float* sums, cudaStream_t st);
+
+// One-read discriminative forward (disc_fused.cu); CLR_ERR_UNSUPPORTED -> use the two-pass form.
+int disc_fused_impl(const float* xs, const float* ys, int B, int C, int HW, int K,
+                    const float* disc_vec, const float* disc_beta, float margin,
+                    float* coef, float* delta, float* partial, float* hinge, int* nparts, cudaStream_t st);
 
 int disc_fwd_impl(const float* xs, const float* ys, int B, int C, int HW, int K,
                   const float* disc_vec, const float* disc_beta, float margin,

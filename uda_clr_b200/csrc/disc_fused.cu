@@ -1,0 +1,321 @@
+// Prototype-guided discriminative hinge, forward, in ONE read of the source features
+// (Trainer_prototype_mt.cpython-38.pyc L454-474).
+//
+// Per pixel the hinge argument delta_k = d_obj,k - d_bck,k is affine in x (a dot product with
+// D_k = P_obj,k - P_bck,k over the channel axis); the loss's gradient w.r.t. the prototypes needs the
+// active-set sums A_k[c] = sum_p coef_k(p) x[c,p] (a reduction over the pixel axis with coefficients that
+// are only known once the pixel's dot products are complete).  Both reductions run over the same
+// [C x TP] tile while it sits in shared memory, so the feature map is read once instead of twice
+// (clr_disc_fwd + clr_pool_rows_fwd).
+//
+// Bound: HBM.  Algorithmic bytes = 4*B*C*HW (features) + 2*4*B*K*HW (labels in, coefficients out).
+//
+//   tile     = all C channels x TP (=64 or 32) consecutive pixels of one sample: C rows of 4*TP bytes
+//   producer = one warp; its 32 lanes issue the C row copies (cp.async.bulk, SASS UBLKCP) of the next tile
+//              into a ring of shared-memory stages, completion on an mbarrier (complete_tx)
+//   consumer = 256 threads.  phase 1: thread (pixel quad g, channel slice s) accumulates K dot products
+//              over its slice, slices are combined through shared memory, the epilogue evaluates the
+//              hinge and writes coef (global + shared).  phase 2: thread = channel c walks its row and
+//              accumulates K coefficient-weighted sums in registers ACROSS ALL TILES of the CTA.
+//              Rows are padded by 4 floats so both access patterns are bank-conflict free.
+//   output   = per-CTA partials [K][C+1] (col C = sum of coefficients) + per-CTA hinge sum; combined in
+//              fp64, fixed order, by the pooling reduce kernel -> deterministic.
+#include "clr_common.cuh"
+#include "clr_internal.h"
+
+namespace clr {
+
+struct DiscParams {
+    const float* xs;
+    const float* ys;        // [B,K,HW]
+    const float* V;         // [K][C]  D_k
+    const float* beta;      // [K]
+    float* coef;            // [B,K,HW]
+    float* delta;           // [B,K,HW] or null
+    float* partial;         // [grid][K][C+1]
+    float* hinge;           // [grid]
+    float alpha, margin;
+    int B, C, HW, tilesPerSample, total, stages;
+};
+
+constexpr int kDiscPad = 4;
+constexpr int kDiscMaxParts = 160;   // >= number of SMs: one CTA (and one partial) per SM
+constexpr int kDiscMaxCPT = 3;     // channels per thread in phase 2 (C <= 768)
+
+template <int K, int TP>
+__global__ void __launch_bounds__(kThreads + 32, 1) disc_fused_kernel(const DiscParams p) {
+    constexpr int RS = TP + kDiscPad;            // row stride (floats)
+    constexpr int NG = TP / 4;                   // pixel quads per tile
+    constexpr int NS = kThreads / NG;            // channel slices in phase 1
+    constexpr int NE = (K * TP + kThreads - 1) / kThreads;   // epilogue iterations per thread (<= 2)
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const size_t stage_floats = (size_t)p.C * RS;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);                  // [8]
+    uint64_t* empty = full + 8;                                              // [8]   (128 bytes of barriers)
+    float* tiles = reinterpret_cast<float*>(smem_raw + 128);                 // [stages][C][RS]
+    float* red = tiles + (size_t)p.stages * stage_floats;                    // [NS][K][TP]
+    float* cfs = red + (size_t)NS * K * TP;                                  // [K][TP]
+    float* wred = cfs + (size_t)K * TP;                                      // [1 + NE][kWarps]
+    float* Vs = wred + (1 + NE) * kWarps;                                    // [K][C]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kWarps); }
+        fence_mbar_init();
+    }
+    for (int i = tid; i < K * p.C; i += blockDim.x) Vs[i] = p.V[i];
+    __syncthreads();
+
+    int begin, end;
+    partition(p.total, gridDim.x, blockIdx.x, begin, end);
+
+    if (warp == kWarps) {
+        // ---------------- producer warp ----------------
+        const uint64_t pol = policy_evict_first();
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int it = begin; it < end; ++it) {
+            const int b = it / p.tilesPerSample, tile = it - b * p.tilesPerSample;
+            const int px0 = tile * TP;
+            const int npx = (p.HW - px0) < TP ? (p.HW - px0) : TP;
+            if (lane == 0) {
+                mbar_wait(&empty[stage], phase ^ 1u);
+                mbar_arrive_expect_tx(&full[stage], (uint32_t)((size_t)p.C * npx * sizeof(float)));
+            }
+            __syncwarp();
+            const float* src = p.xs + (size_t)b * p.C * p.HW + px0;
+            float* dst = tiles + (size_t)stage * stage_floats;
+            for (int c = lane; c < p.C; c += 32)
+                bulk_g2s(dst + (size_t)c * RS, src + (size_t)c * p.HW, (uint32_t)(npx * sizeof(float)), &full[stage], pol);
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+        return;
+    }
+
+    // ---------------- consumers ----------------
+    auto sync = [] { named_bar_sync(1, kThreads); };
+    const int g = tid % NG, s = tid / NG;
+    float A[kDiscMaxCPT][K];
+#pragma unroll
+    for (int i = 0; i < kDiscMaxCPT; ++i)
+#pragma unroll
+        for (int k = 0; k < K; ++k) A[i][k] = 0.f;
+    float hinge_sum = 0.f;               // epilogue threads: running sums of their (k, pixel) entries
+    float ncf[NE];
+#pragma unroll
+    for (int i = 0; i < NE; ++i) ncf[i] = 0.f;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int it = begin; it < end; ++it) {
+        const int b = it / p.tilesPerSample, tile = it - b * p.tilesPerSample;
+        const int px0 = tile * TP;
+        const int npx = (p.HW - px0) < TP ? (p.HW - px0) : TP;
+        float* xt = tiles + (size_t)stage * stage_floats;
+        mbar_wait(&full[stage], phase);
+        if (npx < TP) {
+            // ragged last tile: columns >= npx were not copied; zero them so phase 2 never multiplies stale bits
+            for (int i = tid; i < p.C * (TP - npx); i += kThreads) {
+                const int c = i / (TP - npx), j = npx + (i - c * (TP - npx));
+                xt[(size_t)c * RS + j] = 0.f;
+            }
+            sync();
+        }
+        // ---- phase 1: K dot products over the channel axis ----------------------------------------
+        float acc[K][4];
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) acc[k][v] = 0.f;
+#pragma unroll 4
+        for (int c = s; c < p.C; c += NS) {
+            const float4 x = *reinterpret_cast<const float4*>(xt + (size_t)c * RS + 4 * g);
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const float vk = Vs[k * p.C + c];
+                acc[k][0] = fmaf(x.x, vk, acc[k][0]);
+                acc[k][1] = fmaf(x.y, vk, acc[k][1]);
+                acc[k][2] = fmaf(x.z, vk, acc[k][2]);
+                acc[k][3] = fmaf(x.w, vk, acc[k][3]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+            *reinterpret_cast<float4*>(red + ((size_t)s * K + k) * TP + 4 * g) =
+                make_float4(acc[k][0], acc[k][1], acc[k][2], acc[k][3]);
+        sync();
+        // ---- epilogue: thread e -> (k, pixel j) ------------------------------------------------------
+#pragma unroll
+        for (int ei = 0; ei < NE; ++ei) {
+            const int e = tid + ei * kThreads;
+            if (e >= K * TP) break;
+            const int k = e / TP, j = e - k * TP;
+            float dot = 0.f;
+#pragma unroll
+            for (int q = 0; q < NS; ++q) dot += red[((size_t)q * K + k) * TP + j];
+            float cf = 0.f;
+            if (j < npx) {
+                const size_t o = ((size_t)b * K + k) * p.HW + px0 + j;
+                const float delta = fmaf(p.alpha, dot, __ldg(p.beta + k));
+                const float yv = __ldg(p.ys + o);
+                const float ho = delta + p.margin, hb = p.margin - delta;
+                hinge_sum += yv * fmaxf(ho, 0.f) + (1.f - yv) * fmaxf(hb, 0.f);
+                cf = (ho > 0.f ? yv : 0.f) - (hb > 0.f ? (1.f - yv) : 0.f);
+                p.coef[o] = cf;
+                if (p.delta) p.delta[o] = delta;
+            }
+            cfs[e] = cf;
+            ncf[ei] += cf;
+        }
+        sync();
+        // ---- phase 2: coefficient-weighted sums over the pixel axis, one channel row per thread ----------
+#pragma unroll
+        for (int i = 0; i < kDiscMaxCPT; ++i) {
+            const int c = tid + i * kThreads;
+            if (c < p.C) {
+                const float* row = xt + (size_t)c * RS;
+#pragma unroll 4
+                for (int j4 = 0; j4 < NG; ++j4) {
+                    const float4 x = *reinterpret_cast<const float4*>(row + 4 * j4);
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        const float4 cf = *reinterpret_cast<const float4*>(cfs + k * TP + 4 * j4);
+                        A[i][k] = fmaf(x.x, cf.x, A[i][k]);
+                        A[i][k] = fmaf(x.y, cf.y, A[i][k]);
+                        A[i][k] = fmaf(x.z, cf.z, A[i][k]);
+                        A[i][k] = fmaf(x.w, cf.w, A[i][k]);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        // no barrier needed here: `red` is next written after every thread passed this tile's second barrier,
+        // and `cfs` after the next tile's first barrier, which every thread reaches only after its phase 2
+    }
+    // ---- CTA partials --------------------------------------------------------------------------------
+    float* out = p.partial + (size_t)blockIdx.x * K * (p.C + 1);
+#pragma unroll
+    for (int i = 0; i < kDiscMaxCPT; ++i) {
+        const int c = tid + i * kThreads;
+        if (c < p.C) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) out[(size_t)k * (p.C + 1) + c] = A[i][k];
+        }
+    }
+    const float hs = warp_sum(hinge_sum);
+    if (lane == 0) wred[warp] = hs;
+#pragma unroll
+    for (int ei = 0; ei < NE; ++ei) {
+        const float t = warp_sum(ncf[ei]);
+        if (lane == 0) wred[(1 + ei) * kWarps + warp] = t;
+    }
+    sync();
+    if (tid == 0) {
+        float t = 0.f;
+        for (int w = 0; w < kWarps; ++w) t += wred[w];
+        p.hinge[blockIdx.x] = t;
+    }
+    if (tid < K) {
+        // entry e = ei*256 + warp*32 + lane belongs to class e / TP; TP is a multiple of 32, so a warp is one class
+        float t = 0.f;
+        for (int ei = 0; ei < NE; ++ei)
+            for (int w = 0; w < kWarps; ++w)
+                if ((ei * kThreads + w * 32) / TP == tid) t += wred[(1 + ei) * kWarps + w];
+        out[(size_t)tid * (p.C + 1) + p.C] = t;
+    }
+}
+
+template <int K, int TP>
+static size_t disc_smem(int C, int stages) {
+    constexpr int RS = TP + kDiscPad, NS = kThreads / (TP / 4), NE = (K * TP + kThreads - 1) / kThreads;
+    const size_t fl = (size_t)stages * C * RS + (size_t)NS * K * TP + (size_t)K * TP + (1 + NE) * kWarps + (size_t)K * C;
+    return 128 + fl * sizeof(float);
+}
+
+template <int K, int TP>
+static int launch_disc(DiscParams& p, int* nparts, cudaStream_t st) {
+    const size_t budget = (size_t)device_facts().max_smem_optin;
+    int stages = 4;
+    while (stages > 1 && disc_smem<K, TP>(p.C, stages) > budget) --stages;
+    if (stages < 2 || disc_smem<K, TP>(p.C, stages) > budget) return CLR_ERR_UNSUPPORTED;
+    p.stages = stages;
+    p.tilesPerSample = (p.HW + TP - 1) / TP;
+    const long long total = (long long)p.B * p.tilesPerSample;
+    if (total > 0x3fffffff) return CLR_ERR_UNSUPPORTED;
+    p.total = (int)total;
+    int grid = device_facts().sms;
+    if (grid > p.total) grid = p.total;
+    if (grid > *nparts) grid = *nparts;
+    *nparts = grid;
+    const size_t smem = disc_smem<K, TP>(p.C, stages);
+    auto kern = disc_fused_kernel<K, TP>;
+    CLR_RETURN_IF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    count_launch();
+    kern<<<grid, kThreads + 32, smem, st>>>(p);
+    return launch_status();
+}
+
+template <int TP>
+static int dispatch_disc_k(int K, DiscParams& p, int* nparts, cudaStream_t st) {
+    switch (K) {
+        case 1: return launch_disc<1, TP>(p, nparts, st);
+        case 2: return launch_disc<2, TP>(p, nparts, st);
+        case 3: return launch_disc<3, TP>(p, nparts, st);
+        case 4: return launch_disc<4, TP>(p, nparts, st);
+        case 5: return launch_disc<5, TP>(p, nparts, st);
+        case 6: return launch_disc<6, TP>(p, nparts, st);
+        case 7: return launch_disc<7, TP>(p, nparts, st);
+        case 8: return launch_disc<8, TP>(p, nparts, st);
+    }
+    return CLR_ERR_UNSUPPORTED;
+}
+
+// Returns CLR_ERR_UNSUPPORTED when the tile does not fit (very wide C) or the planes are not 16-byte
+// friendly; the caller then falls back to the two-pass form (clr_disc_fwd + clr_pool_rows_fwd).
+int disc_fused_impl(const float* xs, const float* ys, int B, int C, int HW, int K,
+                    const float* disc_vec, const float* disc_beta, float margin,
+                    float* coef, float* delta, float* partial, float* hinge, int* nparts, cudaStream_t st) {
+    CLR_CHECK_ARG(xs && ys && disc_vec && disc_beta && coef && partial && hinge && nparts && *nparts > 0);
+    CLR_CHECK_ARG(B > 0 && C > 0 && HW > 0 && K >= 1 && K <= CLR_MAX_K);
+    if (HW % 4 != 0 || !aligned16(xs) || C > kDiscMaxCPT * kThreads) return CLR_ERR_UNSUPPORTED;
+    DiscParams p{};
+    p.xs = xs; p.ys = ys; p.V = disc_vec; p.beta = disc_beta; p.coef = coef; p.delta = delta;
+    p.partial = partial; p.hinge = hinge; p.alpha = -2.0f / (float)C; p.margin = margin;
+    p.B = B; p.C = C; p.HW = HW;
+    int n64 = *nparts;
+    int rc = dispatch_disc_k<64>(K, p, &n64, st);
+    if (rc == CLR_ERR_UNSUPPORTED) {
+        n64 = *nparts;
+        rc = dispatch_disc_k<32>(K, p, &n64, st);
+    }
+    if (rc == CLR_OK) *nparts = n64;
+    return rc;
+}
+
+}  // namespace clr
+
+extern "C" {
+
+size_t clr_disc_fused_ws_bytes(int C, int K) {
+    if (C < 1 || K < 1 || K > CLR_MAX_K) return 0;
+    return sizeof(float) * ((size_t)clr::kDiscMaxParts * K * (C + 1) + clr::kDiscMaxParts);
+}
+
+int clr_disc_fused_fwd(const float* xs, const float* ys, int B, int C, int HW, int K,
+                       const float* disc_vec, const float* disc_beta, float margin,
+                       float* coef, float* delta, void* ws, size_t ws_bytes, float* packed2, clr_stream_t stream) {
+    if (!ws || !packed2) return CLR_ERR_BAD_ARG;
+    if (ws_bytes < clr_disc_fused_ws_bytes(C, K)) return CLR_ERR_WORKSPACE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float* partial = static_cast<float*>(ws);
+    float* hinge = partial + (size_t)clr::kDiscMaxParts * K * (C + 1);
+    int nparts = clr::kDiscMaxParts;
+    int rc = clr::disc_fused_impl(xs, ys, B, C, HW, K, disc_vec, disc_beta, margin, coef, delta, partial, hinge, &nparts, st);
+    if (rc != CLR_OK) return rc;
+    clr::launch_partial_reduce(partial, nparts, K, C, packed2, st);
+    clr::launch_step_pack(hinge, nparts, 1, nullptr, 0, packed2 + (size_t)K * (C + 1), st);
+    return clr::launch_status();
+}
+
+}  // extern "C"

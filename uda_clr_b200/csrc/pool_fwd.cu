@@ -360,6 +360,17 @@ __global__ void proto_finalize_kernel(const float* __restrict__ sums, int R, int
     mu[i] = sums[(size_t)r * (C + 1) + c] / sums[(size_t)r * (C + 1) + C];   // 0/0 -> NaN, as the reference
 }
 
+void launch_partial_reduce(const float* partial, int slots, int R, int C, float* sums, cudaStream_t st) {
+    PoolParams p{};
+    p.ndom = 1; p.C = C;
+    p.dom[0].partial = const_cast<float*>(partial);
+    p.dom[0].sums = sums;
+    p.dom[0].slots = slots;
+    const int n = R * (C + 1);
+    count_launch();
+    pool_reduce_kernel<<<dim3((n + 31) / 32, 1), dim3(32, 8), 0, st>>>(p, R);
+}
+
 static void launch_reduce(const PoolParams& p, int R, cudaStream_t st) {
     const int n = R * (p.C + 1);
     clr::count_launch(); pool_reduce_kernel<<<dim3((n + 31) / 32, p.ndom), dim3(32, 8), 0, st>>>(p, R);

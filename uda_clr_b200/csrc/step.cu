@@ -24,7 +24,11 @@ static StepWs carve(const clr_step_args* a) {
     StepWs w{};
     const int HW = a->H * a->W;
     w.pool_bytes = align_up(pool_partial_bytes(a->B_s, a->C, HW, 2 * a->K) + pool_partial_bytes(a->B_t, a->C, HW, 2 * a->K));
-    w.rows_bytes = a->use_disc ? align_up(pool_partial_bytes(a->B_s, a->C, HW, a->K)) : 0;
+    // discriminative pass: fused-kernel partials ([parts][K][C+1] + [parts]) or, for the two-pass fallback,
+    // the row-pooling partials; the larger of the two
+    size_t rows = a->use_disc ? pool_partial_bytes(a->B_s, a->C, HW, a->K) : 0;
+    if (a->use_disc && clr_disc_fused_ws_bytes(a->C, a->K) > rows) rows = clr_disc_fused_ws_bytes(a->C, a->K);
+    w.rows_bytes = align_up(rows);
     w.hinge_bytes = a->use_disc ? align_up(sizeof(float) * (size_t)clr_disc_partials_cap() * (1 + a->K)) : 0;
     w.cons_bytes = a->use_cons ? align_up(clr_cons_ws_bytes()) : 0;
     char* base = static_cast<char*>(a->ws);
@@ -107,15 +111,34 @@ int clr_step_fwd_b(const clr_step_args* a, clr_stream_t stream) {
                                     a->cons_threshold, w.cons, &n_cons, st);
         if (rc != CLR_OK) return rc;
     }
+    int hinge_stride = 1 + K;
+    const float* hinge_src = w.hinge;
     if (a->use_disc) {
-        rc = clr::disc_fwd_impl(a->xs, a->ys, a->B_s, C, HW, K, a->disc_vec, a->disc_beta, a->margin,
-                                a->disc_coef, nullptr, w.hinge, clr_disc_partials_cap(), &n_hinge, st);
-        if (rc != CLR_OK) return rc;
-        rc = clr::pool_fwd_impl(a->xs, a->disc_coef, CLR_W_EXPLICIT, a->B_s, a->packed2, nullptr, nullptr, 0, 0, nullptr,
-                                C, HW, K, w.rows, w.rows_bytes, st);
+        // one read of xs: dot products + active-set sums on the same shared-memory tile
+        rc = CLR_ERR_UNSUPPORTED;
+        if (clr::tunables().disc_impl != 1) {
+            float* partial = reinterpret_cast<float*>(w.rows);
+            float* hinge = partial + (size_t)160 * K * (C + 1);   // layout of clr_disc_fused_ws_bytes: [160][K][C+1] | [160]
+            n_hinge = 160;
+            rc = clr::disc_fused_impl(a->xs, a->ys, a->B_s, C, HW, K, a->disc_vec, a->disc_beta, a->margin,
+                                      a->disc_coef, nullptr, partial, hinge, &n_hinge, st);
+            if (rc == CLR_OK) {
+                clr::launch_partial_reduce(partial, n_hinge, K, C, a->packed2, st);
+                hinge_src = hinge;
+                hinge_stride = 1;
+            }
+        }
+        if (rc == CLR_ERR_UNSUPPORTED) {
+            // two-pass form: per-pixel dots (read 1), then pooling of xs with the coefficient planes (read 2)
+            rc = clr::disc_fwd_impl(a->xs, a->ys, a->B_s, C, HW, K, a->disc_vec, a->disc_beta, a->margin,
+                                    a->disc_coef, nullptr, w.hinge, clr_disc_partials_cap(), &n_hinge, st);
+            if (rc != CLR_OK) return rc;
+            rc = clr::pool_fwd_impl(a->xs, a->disc_coef, CLR_W_EXPLICIT, a->B_s, a->packed2, nullptr, nullptr, 0, 0, nullptr,
+                                    C, HW, K, w.rows, w.rows_bytes, st);
+        }
         if (rc != CLR_OK) return rc;
     }
-    clr::launch_step_pack(a->use_disc ? w.hinge : nullptr, n_hinge, 1 + K, a->use_cons ? w.cons : nullptr, n_cons,
+    clr::launch_step_pack(a->use_disc ? hinge_src : nullptr, n_hinge, hinge_stride, a->use_cons ? w.cons : nullptr, n_cons,
                           a->packed2 + (size_t)K * (C + 1), st);
     return clr::launch_status();
 }
