@@ -192,7 +192,7 @@ int clr_align_finalize(const float* sums_s, const float* sums_t, int K, int C,
                        float* g_s /*[2K][C] out: dL/d cur_s*/, float* g_t,
                        float* disc_vec /*[K][C] out or NULL*/, float* disc_beta /*[K] out or NULL*/,
                        float* losses /*[8]*/, clr_stream_t stream);
-int clr_disc_finalize(const float* packed2 /*[K][C+1] | hinge num | cons num | cons den | 0*/, const float* P_s,
+int clr_disc_finalize(float* packed2 /*[K][C+1] | hinge num | cons num | cons den | 0*/, const float* P_s,
                       int K, int C, double npx, float w_disc, float ema_factor, float gscale,
                       float* g_s /*in/out*/, float* xtab /*[K][C] out*/,
                       float w_intra, float w_inter, float w_aug, float aug_weight, int use_disc, int use_cons,

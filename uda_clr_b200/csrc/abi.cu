@@ -25,7 +25,7 @@ static unsigned long long g_launches = 0;
 void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
 
 Tunables& tunables() {
-    static Tunables t{0, 0, 0, 0, 0, 0};
+    static Tunables t{0, 0, 0, 0, 0, 0, 0};
     return t;
 }
 
@@ -44,6 +44,7 @@ int clr_set_tunable(const char* name, int value) {
     else if (!strcmp(name, "bwd_impl")) t.bwd_impl = value;
     else if (!strcmp(name, "mc_precise")) t.mc_precise = value;
     else if (!strcmp(name, "disc_impl")) t.disc_impl = value;
+    else if (!strcmp(name, "disc_tile")) t.disc_tile = value;
     else return CLR_ERR_BAD_ARG;
     return CLR_OK;
 }

@@ -32,6 +32,7 @@ struct Tunables {
     int dots_impl;     // reserved
     int disc_impl;     // 0 = auto (one-read fused discriminative kernel), 1 = force the two-pass form
     int bwd_impl;      // reserved
+    int disc_tile;     // 0 = auto, 64 = force 64-pixel tiles in the fused discriminative kernel
     int mc_precise;    // 1 = ATen-exact sigmoids in clr_mc_stats (slower), 0 = fast intrinsics
 };
 Tunables& tunables();

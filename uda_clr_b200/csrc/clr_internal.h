@@ -27,4 +27,11 @@ int cons_fwd_partials(const float* oT, const float* oT_aug, const float* masks, 
 void launch_step_pack(const float* hinge_partials, int n_hinge, int hinge_stride,
                       const double* cons_partials, int n_cons, float* tail, cudaStream_t st);
 
+// clr_disc_finalize with the per-CTA partial sums folded in (no separate pack launch; single-GPU path).
+int disc_finalize_impl(float* packed2, const float* P_s, int K, int C, double npx, float w_disc,
+                       float ema_factor, float gscale, float* g_s, float* xtab,
+                       float w_intra, float w_inter, float w_aug, float aug_weight, int use_disc, int use_cons,
+                       float* losses, const float* hinge, int n_hinge, int hinge_stride,
+                       const double* cons, int n_cons, cudaStream_t stream);
+
 }  // namespace clr

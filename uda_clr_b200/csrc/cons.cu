@@ -55,29 +55,44 @@ __global__ void __launch_bounds__(256) cons_kernel(const float* __restrict__ oT,
     float coef = 0.f;
     if (BWD) coef = (gscale_dev ? gscale * __ldg(gscale_dev) : gscale) / __ldg(stats + 1);
     float num = 0.f, den = 0.f;
-    for (int idx = threadIdx.x; idx < nvec; idx += blockDim.x) {
-        const int ry = idx / wv, xv = idx - ry * wv;
-        const int y = y0 + ry;
-        if (y >= g.Hi) break;
-        const int sy = nearest_src(y, g.sh, g.H);
-        const size_t off = plane + (size_t)y * g.Wi + (size_t)xv * VEC;
-        const Pack<VEC> zt = ld_stream<VEC>(oT + off);
-        const Pack<VEC> za = ld_stream<VEC>(oT_aug + off);
-        Pack<VEC> go;
+    constexpr int U = 4;   // independent vector loads in flight per thread
+    for (int base = threadIdx.x; base < nvec; base += U * blockDim.x) {
+        Pack<VEC> zt[U], za[U];
+        int yy[U], xv_[U];
+        bool ok[U];
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-            const int sx = nearest_src(xv * VEC + v, g.sw, g.W);
-            const float m = __ldg(mplane + (size_t)sy * g.W + sx);
-            float ml, q, yv;
-            cons_elem(zt.v[v], za.v[v], m, thr, ml, q, yv);
-            num += ml; den += m;
-            if (BWD) {
-                // ATen binary_cross_entropy_backward: (q - y) / max((1-q) q, 1e-12), chained with sigmoid' = q (1-q)
-                const float qq = (1.0f - q) * q;
-                go.v[v] = coef * m * (q - yv) / fmaxf(qq, 1e-12f) * qq;
+        for (int u = 0; u < U; ++u) {
+            const int idx = base + u * blockDim.x;
+            const int ry = idx / wv;
+            xv_[u] = idx - ry * wv;
+            yy[u] = y0 + ry;
+            ok[u] = idx < nvec && yy[u] < g.Hi;
+            if (ok[u]) {
+                const size_t off = plane + (size_t)yy[u] * g.Wi + (size_t)xv_[u] * VEC;
+                zt[u] = ld_stream<VEC>(oT + off);
+                za[u] = ld_stream<VEC>(oT_aug + off);
             }
         }
-        if (BWD) st_stream<VEC>(grad + off, go);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (!ok[u]) continue;
+            const int sy = nearest_src(yy[u], g.sh, g.H);
+            Pack<VEC> go;
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                const int sx = nearest_src(xv_[u] * VEC + v, g.sw, g.W);
+                const float m = __ldg(mplane + (size_t)sy * g.W + sx);
+                float ml, q, yv;
+                cons_elem(zt[u].v[v], za[u].v[v], m, thr, ml, q, yv);
+                num += ml; den += m;
+                if (BWD) {
+                    // ATen binary_cross_entropy_backward: (q - y) / max((1-q) q, 1e-12), chained with sigmoid' = q (1-q)
+                    const float qq = (1.0f - q) * q;
+                    go.v[v] = coef * m * (q - yv) / fmaxf(qq, 1e-12f) * qq;
+                }
+            }
+            if (BWD) st_stream<VEC>(grad + plane + (size_t)yy[u] * g.Wi + (size_t)xv_[u] * VEC, go);
+        }
     }
     if (!BWD) {
         double dn = warp_sum((double)num), dd = warp_sum((double)den);

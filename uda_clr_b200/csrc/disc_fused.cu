@@ -11,9 +11,10 @@
 // Bound: HBM.  Algorithmic bytes = 4*B*C*HW (features) + 2*4*B*K*HW (labels in, coefficients out).
 //
 //   tile     = all C channels x TP (=64 or 32) consecutive pixels of one sample: C rows of 4*TP bytes
-//   producer = one warp; its 32 lanes issue the C row copies (cp.async.bulk, SASS UBLKCP) of the next tile
-//              into a ring of shared-memory stages, completion on an mbarrier (complete_tx)
-//   consumer = 256 threads.  phase 1: thread (pixel quad g, channel slice s) accumulates K dot products
+//   fetch    = all 256 threads issue 16-byte cp.async (LDGSTS) chunks of the tile STAGES-1 ahead into a ring of
+//              shared-memory stages (commit / wait groups).  Bulk-TMA row copies were measured slower here:
+//              a row is only 4*TP = 128-256 bytes, far below the size at which cp.async.bulk is efficient.
+//   compute  = the same 256 threads.  phase 1: thread (pixel quad g, channel slice s) accumulates K dot products
 //              over its slice, slices are combined through shared memory, the epilogue evaluates the
 //              hinge and writes coef (global + shared).  phase 2: thread = channel c walks its row and
 //              accumulates K coefficient-weighted sums in registers ACROSS ALL TILES of the CTA.
@@ -39,61 +40,56 @@ struct DiscParams {
 };
 
 constexpr int kDiscPad = 4;
-constexpr int kDiscMaxParts = 160;   // >= number of SMs: one CTA (and one partial) per SM
+constexpr int kDiscMaxParts = 320;   // >= resident CTAs (2 per SM): one partial per CTA
 constexpr int kDiscMaxCPT = 3;     // channels per thread in phase 2 (C <= 768)
 
-template <int K, int TP>
-__global__ void __launch_bounds__(kThreads + 32, 1) disc_fused_kernel(const DiscParams p) {
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int K, int TP, int STAGES>
+__global__ void __launch_bounds__(kThreads, (TP == 32) ? 2 : 1) disc_fused_kernel(const DiscParams p) {
     constexpr int RS = TP + kDiscPad;            // row stride (floats)
-    constexpr int NG = TP / 4;                   // pixel quads per tile
+    constexpr int NG = TP / 4;                   // pixel quads (16-byte chunks) per row
     constexpr int NS = kThreads / NG;            // channel slices in phase 1
     constexpr int NE = (K * TP + kThreads - 1) / kThreads;   // epilogue iterations per thread (<= 2)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const size_t stage_floats = (size_t)p.C * RS;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);                  // [8]
-    uint64_t* empty = full + 8;                                              // [8]   (128 bytes of barriers)
-    float* tiles = reinterpret_cast<float*>(smem_raw + 128);                 // [stages][C][RS]
-    float* red = tiles + (size_t)p.stages * stage_floats;                    // [NS][K][TP]
-    float* cfs = red + (size_t)NS * K * TP;                                  // [K][TP]
+    float* tiles = reinterpret_cast<float*>(smem_raw);                       // [STAGES][C][RS]
+    float* red = tiles + (size_t)STAGES * stage_floats;                      // [kWarps][K][TP]
+    float* cfs = red + (size_t)kWarps * K * TP;                              // [K][TP]
     float* wred = cfs + (size_t)K * TP;                                      // [1 + NE][kWarps]
     float* Vs = wred + (1 + NE) * kWarps;                                    // [K][C]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid == 0) {
-        for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kWarps); }
-        fence_mbar_init();
-    }
-    for (int i = tid; i < K * p.C; i += blockDim.x) Vs[i] = p.V[i];
-    __syncthreads();
+    for (int i = tid; i < K * p.C; i += kThreads) Vs[i] = p.V[i];
 
     int begin, end;
     partition(p.total, gridDim.x, blockIdx.x, begin, end);
 
-    if (warp == kWarps) {
-        // ---------------- producer warp ----------------
-        const uint64_t pol = policy_evict_first();
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int it = begin; it < end; ++it) {
+    // Asynchronous tile fetch by all 256 threads: 16-byte cp.async (LDGSTS) chunks, a warp covers
+    // 32/NG channel rows per instruction; columns past a ragged plane end are zero-filled.
+    auto issue = [&](int it, int stage) {
+        if (it < end) {
             const int b = it / p.tilesPerSample, tile = it - b * p.tilesPerSample;
             const int px0 = tile * TP;
-            const int npx = (p.HW - px0) < TP ? (p.HW - px0) : TP;
-            if (lane == 0) {
-                mbar_wait(&empty[stage], phase ^ 1u);
-                mbar_arrive_expect_tx(&full[stage], (uint32_t)((size_t)p.C * npx * sizeof(float)));
-            }
-            __syncwarp();
+            const int nchunk = ((p.HW - px0) < TP ? (p.HW - px0) : TP) / 4;
             const float* src = p.xs + (size_t)b * p.C * p.HW + px0;
             float* dst = tiles + (size_t)stage * stage_floats;
-            for (int c = lane; c < p.C; c += 32)
-                bulk_g2s(dst + (size_t)c * RS, src + (size_t)c * p.HW, (uint32_t)(npx * sizeof(float)), &full[stage], pol);
-            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            const int total = p.C * NG;
+            for (int i = tid; i < total; i += kThreads) {
+                const int c = i / NG, q = i - c * NG;
+                float* d = dst + (size_t)c * RS + 4 * q;
+                if (q < nchunk) cp_async16(d, src + (size_t)c * p.HW + 4 * q);
+                else *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
         }
-        return;
-    }
+        cp_async_commit();
+    };
 
-    // ---------------- consumers ----------------
-    auto sync = [] { named_bar_sync(1, kThreads); };
     const int g = tid % NG, s = tid / NG;
     float A[kDiscMaxCPT][K];
 #pragma unroll
@@ -104,22 +100,30 @@ __global__ void __launch_bounds__(kThreads + 32, 1) disc_fused_kernel(const Disc
     float ncf[NE];
 #pragma unroll
     for (int i = 0; i < NE; ++i) ncf[i] = 0.f;
+
+#pragma unroll
+    for (int j = 0; j < STAGES - 1; ++j) issue(begin + j, j);
     int stage = 0;
-    uint32_t phase = 0;
     for (int it = begin; it < end; ++it) {
         const int b = it / p.tilesPerSample, tile = it - b * p.tilesPerSample;
         const int px0 = tile * TP;
         const int npx = (p.HW - px0) < TP ? (p.HW - px0) : TP;
-        float* xt = tiles + (size_t)stage * stage_floats;
-        mbar_wait(&full[stage], phase);
-        if (npx < TP) {
-            // ragged last tile: columns >= npx were not copied; zero them so phase 2 never multiplies stale bits
-            for (int i = tid; i < p.C * (TP - npx); i += kThreads) {
-                const int c = i / (TP - npx), j = npx + (i - c * (TP - npx));
-                xt[(size_t)c * RS + j] = 0.f;
-            }
-            sync();
+        // labels of this thread's epilogue entries: issued now, consumed after phase 1
+        float yv[NE];
+#pragma unroll
+        for (int ei = 0; ei < NE; ++ei) {
+            const int e = tid + ei * kThreads;
+            const int k = e / TP, j = e - k * TP;
+            yv[ei] = (e < K * TP && j < npx) ? __ldg(p.ys + ((size_t)b * K + k) * p.HW + px0 + j) : 0.f;
         }
+        cp_async_wait<STAGES - 2>();     // this thread's copies of tile `it` have landed
+        __syncthreads();                 // ... everyone's have, and everyone is done with the previous tile
+        {
+            int nst = stage + STAGES - 1;
+            if (nst >= STAGES) nst -= STAGES;
+            issue(it + STAGES - 1, nst);  // refill the stage the previous tile occupied
+        }
+        const float* xt = tiles + (size_t)stage * stage_floats;
         // ---- phase 1: K dot products over the channel axis ----------------------------------------
         float acc[K][4];
 #pragma unroll
@@ -138,11 +142,21 @@ __global__ void __launch_bounds__(kThreads + 32, 1) disc_fused_kernel(const Disc
                 acc[k][3] = fmaf(x.w, vk, acc[k][3]);
             }
         }
+        // the 32/NG slices of a warp share their pixel quads: combine them in registers first
 #pragma unroll
         for (int k = 0; k < K; ++k)
-            *reinterpret_cast<float4*>(red + ((size_t)s * K + k) * TP + 4 * g) =
-                make_float4(acc[k][0], acc[k][1], acc[k][2], acc[k][3]);
-        sync();
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+#pragma unroll
+                for (int o = NG; o < 32; o <<= 1) acc[k][v] += __shfl_xor_sync(0xffffffffu, acc[k][v], o);
+            }
+        if (lane < NG) {
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+                *reinterpret_cast<float4*>(red + ((size_t)warp * K + k) * TP + 4 * g) =
+                    make_float4(acc[k][0], acc[k][1], acc[k][2], acc[k][3]);
+        }
+        __syncthreads();
         // ---- epilogue: thread e -> (k, pixel j) ------------------------------------------------------
 #pragma unroll
         for (int ei = 0; ei < NE; ++ei) {
@@ -151,22 +165,21 @@ __global__ void __launch_bounds__(kThreads + 32, 1) disc_fused_kernel(const Disc
             const int k = e / TP, j = e - k * TP;
             float dot = 0.f;
 #pragma unroll
-            for (int q = 0; q < NS; ++q) dot += red[((size_t)q * K + k) * TP + j];
+            for (int q = 0; q < kWarps; ++q) dot += red[((size_t)q * K + k) * TP + j];
             float cf = 0.f;
             if (j < npx) {
                 const size_t o = ((size_t)b * K + k) * p.HW + px0 + j;
                 const float delta = fmaf(p.alpha, dot, __ldg(p.beta + k));
-                const float yv = __ldg(p.ys + o);
                 const float ho = delta + p.margin, hb = p.margin - delta;
-                hinge_sum += yv * fmaxf(ho, 0.f) + (1.f - yv) * fmaxf(hb, 0.f);
-                cf = (ho > 0.f ? yv : 0.f) - (hb > 0.f ? (1.f - yv) : 0.f);
+                hinge_sum += yv[ei] * fmaxf(ho, 0.f) + (1.f - yv[ei]) * fmaxf(hb, 0.f);
+                cf = (ho > 0.f ? yv[ei] : 0.f) - (hb > 0.f ? (1.f - yv[ei]) : 0.f);
                 p.coef[o] = cf;
                 if (p.delta) p.delta[o] = delta;
             }
             cfs[e] = cf;
             ncf[ei] += cf;
         }
-        sync();
+        __syncthreads();
         // ---- phase 2: coefficient-weighted sums over the pixel axis, one channel row per thread ----------
 #pragma unroll
         for (int i = 0; i < kDiscMaxCPT; ++i) {
@@ -187,12 +200,11 @@ __global__ void __launch_bounds__(kThreads + 32, 1) disc_fused_kernel(const Disc
                 }
             }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[stage]);
-        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
-        // no barrier needed here: `red` is next written after every thread passed this tile's second barrier,
-        // and `cfs` after the next tile's first barrier, which every thread reaches only after its phase 2
+        if (++stage == STAGES) stage = 0;
+        // `red` is next written after the next tile's first barrier, `cfs` after its second: both after every
+        // thread finished this tile's phase 2, so no trailing barrier is needed
     }
+    cp_async_wait<0>();
     // ---- CTA partials --------------------------------------------------------------------------------
     float* out = p.partial + (size_t)blockIdx.x * K * (p.C + 1);
 #pragma unroll
@@ -210,7 +222,7 @@ __global__ void __launch_bounds__(kThreads + 32, 1) disc_fused_kernel(const Disc
         const float t = warp_sum(ncf[ei]);
         if (lane == 0) wred[(1 + ei) * kWarps + warp] = t;
     }
-    sync();
+    __syncthreads();
     if (tid == 0) {
         float t = 0.f;
         for (int w = 0; w < kWarps; ++w) t += wred[w];
@@ -228,32 +240,41 @@ __global__ void __launch_bounds__(kThreads + 32, 1) disc_fused_kernel(const Disc
 
 template <int K, int TP>
 static size_t disc_smem(int C, int stages) {
-    constexpr int RS = TP + kDiscPad, NS = kThreads / (TP / 4), NE = (K * TP + kThreads - 1) / kThreads;
-    const size_t fl = (size_t)stages * C * RS + (size_t)NS * K * TP + (size_t)K * TP + (1 + NE) * kWarps + (size_t)K * C;
-    return 128 + fl * sizeof(float);
+    constexpr int RS = TP + kDiscPad, NE = (K * TP + kThreads - 1) / kThreads;
+    const size_t fl = (size_t)stages * C * RS + (size_t)kWarps * K * TP + (size_t)K * TP + (1 + NE) * kWarps + (size_t)K * C;
+    return fl * sizeof(float);
+}
+
+template <int K, int TP, int STAGES>
+static int launch_disc_s(DiscParams& p, int* nparts, cudaStream_t st) {
+    const size_t smem = disc_smem<K, TP>(p.C, STAGES);
+    auto kern = disc_fused_kernel<K, TP, STAGES>;
+    CLR_RETURN_IF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CLR_RETURN_IF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem));
+    if (occ < 1) return CLR_ERR_UNSUPPORTED;
+    p.tilesPerSample = (p.HW + TP - 1) / TP;
+    const long long total = (long long)p.B * p.tilesPerSample;
+    if (total > 0x3fffffff) return CLR_ERR_UNSUPPORTED;
+    p.total = (int)total;
+    int grid = device_facts().sms * occ;
+    if (grid > p.total) grid = p.total;
+    if (grid > *nparts) grid = *nparts;
+    *nparts = grid;
+    count_launch();
+    kern<<<grid, kThreads, smem, st>>>(p);
+    return launch_status();
 }
 
 template <int K, int TP>
 static int launch_disc(DiscParams& p, int* nparts, cudaStream_t st) {
     const size_t budget = (size_t)device_facts().max_smem_optin;
-    int stages = 4;
-    while (stages > 1 && disc_smem<K, TP>(p.C, stages) > budget) --stages;
-    if (stages < 2 || disc_smem<K, TP>(p.C, stages) > budget) return CLR_ERR_UNSUPPORTED;
-    p.stages = stages;
-    p.tilesPerSample = (p.HW + TP - 1) / TP;
-    const long long total = (long long)p.B * p.tilesPerSample;
-    if (total > 0x3fffffff) return CLR_ERR_UNSUPPORTED;
-    p.total = (int)total;
-    int grid = device_facts().sms;
-    if (grid > p.total) grid = p.total;
-    if (grid > *nparts) grid = *nparts;
-    *nparts = grid;
-    const size_t smem = disc_smem<K, TP>(p.C, stages);
-    auto kern = disc_fused_kernel<K, TP>;
-    CLR_RETURN_IF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    count_launch();
-    kern<<<grid, kThreads + 32, smem, st>>>(p);
-    return launch_status();
+    // TP = 32 aims at two resident CTAs per SM (half the budget each)
+    const size_t per_cta = (TP == 32) ? (budget - 2048) / 2 : budget;
+    if (disc_smem<K, TP>(p.C, 4) <= per_cta) return launch_disc_s<K, TP, 4>(p, nparts, st);
+    if (disc_smem<K, TP>(p.C, 3) <= per_cta) return launch_disc_s<K, TP, 3>(p, nparts, st);
+    if (disc_smem<K, TP>(p.C, 2) <= budget) return launch_disc_s<K, TP, 2>(p, nparts, st);
+    return CLR_ERR_UNSUPPORTED;
 }
 
 template <int TP>
@@ -283,13 +304,13 @@ int disc_fused_impl(const float* xs, const float* ys, int B, int C, int HW, int 
     p.xs = xs; p.ys = ys; p.V = disc_vec; p.beta = disc_beta; p.coef = coef; p.delta = delta;
     p.partial = partial; p.hinge = hinge; p.alpha = -2.0f / (float)C; p.margin = margin;
     p.B = B; p.C = C; p.HW = HW;
-    int n64 = *nparts;
-    int rc = dispatch_disc_k<64>(K, p, &n64, st);
-    if (rc == CLR_ERR_UNSUPPORTED) {
-        n64 = *nparts;
-        rc = dispatch_disc_k<32>(K, p, &n64, st);
-    }
-    if (rc == CLR_OK) *nparts = n64;
+    // "disc_tile" tunable: 0 auto (32-pixel tiles, two CTAs per SM), 64 = 64-pixel tiles, one CTA per SM
+    int n = *nparts;
+    int rc = CLR_ERR_UNSUPPORTED;
+    if (tunables().disc_tile == 64) rc = dispatch_disc_k<64>(K, p, &n, st);
+    if (rc == CLR_ERR_UNSUPPORTED) { n = *nparts; rc = dispatch_disc_k<32>(K, p, &n, st); }
+    if (rc == CLR_ERR_UNSUPPORTED && tunables().disc_tile != 64) { n = *nparts; rc = dispatch_disc_k<64>(K, p, &n, st); }
+    if (rc == CLR_OK) *nparts = n;
     return rc;
 }
 

@@ -15,7 +15,7 @@
 
 namespace clr {
 
-// Block-wide sums of NV doubles at once (one pair of barriers): result valid in every thread.
+// Block-wide sums of NV doubles at once (one barrier): result valid in THREAD 0 only.
 template <int NV>
 __device__ __forceinline__ void block_sum_n(double (&v)[NV], double* sh /*[NV][32]*/) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
@@ -26,11 +26,9 @@ __device__ __forceinline__ void block_sum_n(double (&v)[NV], double* sh /*[NV][3
         for (int i = 0; i < NV; ++i) sh[i * 32 + warp] = v[i];
     }
     __syncthreads();
+    if (warp == 0) {
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        double t = 0.0;
-        for (int w = 0; w < nw; ++w) t += sh[i * 32 + w];
-        v[i] = t;
+        for (int i = 0; i < NV; ++i) v[i] = warp_sum(lane < nw ? sh[i * 32 + lane] : 0.0);
     }
 }
 
@@ -96,12 +94,34 @@ __global__ void __launch_bounds__(1024) align_finalize_kernel(
 }
 
 // packed2 layout: [K][C+1] active-set sums (col C = n_k) | loss numerator | cons num | cons den | pad
+struct PackSrc {   // per-CTA partials still to be summed (single-GPU path: no exchange between pack and finalize)
+    const float* hinge; int n_hinge, hinge_stride;
+    const double* cons; int n_cons;
+};
+
 __global__ void __launch_bounds__(256) disc_finalize_kernel(
-    const float* __restrict__ packed2, const float* __restrict__ P_s, int K, int C, double npx, float w_disc,
+    float* __restrict__ packed2, const float* __restrict__ P_s, int K, int C, double npx, float w_disc,
     float ema_factor, float gscale, float* __restrict__ g_s, float* __restrict__ xtab,
     float w_intra, float w_inter, float w_aug, float aug_weight, int use_disc, int use_cons,
-    float* __restrict__ losses) {
-    const float* tail = packed2 + (size_t)K * (C + 1);
+    float* __restrict__ losses, PackSrc ps) {
+    float* tail = packed2 + (size_t)K * (C + 1);
+    __shared__ double shp[3 * 32];
+    __shared__ float tail_s[3];
+    if (ps.hinge || ps.cons) {
+        double v[3] = {0.0, 0.0, 0.0};
+        if (ps.hinge)
+            for (int i = threadIdx.x; i < ps.n_hinge; i += blockDim.x) v[0] += (double)ps.hinge[(size_t)i * ps.hinge_stride];
+        if (ps.cons)
+            for (int i = threadIdx.x; i < ps.n_cons; i += blockDim.x) { v[1] += ps.cons[2 * i]; v[2] += ps.cons[2 * i + 1]; }
+        block_sum_n<3>(v, shp);
+        if (threadIdx.x == 0) {
+            tail[0] = tail_s[0] = (float)v[0]; tail[1] = tail_s[1] = (float)v[1]; tail[2] = tail_s[2] = (float)v[2];
+            tail[3] = 0.f;
+        }
+    } else if (threadIdx.x == 0) {
+        tail_s[0] = tail[0]; tail_s[1] = tail[1]; tail_s[2] = tail[2];
+    }
+    __syncthreads();
     if (use_disc) {
         const float coef = (float)(2.0 / ((double)C * npx));
         for (int i = threadIdx.x; i < K * C; i += blockDim.x) {
@@ -115,8 +135,8 @@ __global__ void __launch_bounds__(256) disc_finalize_kernel(
         }
     }
     if (threadIdx.x == 0) {
-        const float disc = use_disc ? (float)((double)tail[0] / npx) : 0.f;
-        const float aug = use_cons ? (float)((double)tail[1] / (double)tail[2] * (double)aug_weight) : 0.f;
+        const float disc = use_disc ? (float)((double)tail_s[0] / npx) : 0.f;
+        const float aug = use_cons ? (float)((double)tail_s[1] / (double)tail_s[2] * (double)aug_weight) : 0.f;
         losses[2] = disc;
         losses[3] = aug;
         losses[4] = w_intra * losses[0] + w_inter * losses[1] + w_disc * disc + w_aug * aug;
@@ -142,6 +162,20 @@ void launch_step_pack(const float* hinge_partials, int n_hinge, int hinge_stride
     clr::count_launch(); step_pack_kernel<<<1, 256, 0, st>>>(hinge_partials, n_hinge, hinge_stride, cons_partials, n_cons, tail);
 }
 
+int disc_finalize_impl(float* packed2, const float* P_s, int K, int C, double npx, float w_disc,
+                       float ema_factor, float gscale, float* g_s, float* xtab,
+                       float w_intra, float w_inter, float w_aug, float aug_weight, int use_disc, int use_cons,
+                       float* losses, const float* hinge, int n_hinge, int hinge_stride,
+                       const double* cons, int n_cons, cudaStream_t stream) {
+    if (!packed2 || !losses || K < 1 || K > CLR_MAX_K || C < 1) return CLR_ERR_BAD_ARG;
+    if (use_disc && (!P_s || !g_s || !xtab || npx <= 0)) return CLR_ERR_BAD_ARG;
+    PackSrc ps{hinge, n_hinge, hinge_stride, cons, n_cons};
+    count_launch(); disc_finalize_kernel<<<1, 256, 0, stream>>>(
+        packed2, P_s, K, C, npx, w_disc, ema_factor, gscale, g_s, xtab, w_intra, w_inter, w_aug, aug_weight,
+        use_disc, use_cons, losses, ps);
+    return launch_status();
+}
+
 }  // namespace clr
 
 extern "C" {
@@ -160,16 +194,13 @@ int clr_align_finalize(const float* sums_s, const float* sums_t, int K, int C,
     return clr::launch_status();
 }
 
-int clr_disc_finalize(const float* packed2, const float* P_s, int K, int C, double npx, float w_disc,
+int clr_disc_finalize(float* packed2, const float* P_s, int K, int C, double npx, float w_disc,
                       float ema_factor, float gscale, float* g_s, float* xtab,
                       float w_intra, float w_inter, float w_aug, float aug_weight, int use_disc, int use_cons,
                       float* losses, clr_stream_t stream) {
-    if (!packed2 || !losses || K < 1 || K > CLR_MAX_K || C < 1) return CLR_ERR_BAD_ARG;
-    if (use_disc && (!P_s || !g_s || !xtab || npx <= 0)) return CLR_ERR_BAD_ARG;
-    clr::count_launch(); clr::disc_finalize_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        packed2, P_s, K, C, npx, w_disc, ema_factor, gscale, g_s, xtab, w_intra, w_inter, w_aug, aug_weight,
-        use_disc, use_cons, losses);
-    return clr::launch_status();
+    return clr::disc_finalize_impl(packed2, P_s, K, C, npx, w_disc, ema_factor, gscale, g_s, xtab, w_intra, w_inter,
+                                   w_aug, aug_weight, use_disc, use_cons, losses, nullptr, 0, 0, nullptr, 0,
+                                   static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

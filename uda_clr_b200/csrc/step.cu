@@ -93,7 +93,15 @@ int clr_step_fwd_a(const clr_step_args* a, clr_stream_t stream) {
     return rc;
 }
 
-int clr_step_fwd_b(const clr_step_args* a, clr_stream_t stream) {
+namespace clr {
+struct PendingPack { const float* hinge; int n_hinge, hinge_stride; const double* cons; int n_cons; };
+static int step_fwd_b_impl(const clr_step_args* a, clr_stream_t stream, PendingPack* defer);
+}  // namespace clr
+
+int clr_step_fwd_b(const clr_step_args* a, clr_stream_t stream) { return clr::step_fwd_b_impl(a, stream, nullptr); }
+
+// `defer` != NULL: leave the per-CTA partials unsummed and describe them (the caller's finalize kernel sums them)
+static int clr::step_fwd_b_impl(const clr_step_args* a, clr_stream_t stream, clr::PendingPack* defer) {
     int rc = clr::check_args(a);
     if (rc != CLR_OK) return rc;
     const clr::StepWs w = clr::carve(a);
@@ -118,8 +126,8 @@ int clr_step_fwd_b(const clr_step_args* a, clr_stream_t stream) {
         rc = CLR_ERR_UNSUPPORTED;
         if (clr::tunables().disc_impl != 1) {
             float* partial = reinterpret_cast<float*>(w.rows);
-            float* hinge = partial + (size_t)160 * K * (C + 1);   // layout of clr_disc_fused_ws_bytes: [160][K][C+1] | [160]
-            n_hinge = 160;
+            float* hinge = partial + (size_t)320 * K * (C + 1);   // layout of clr_disc_fused_ws_bytes: [320][K][C+1] | [320]
+            n_hinge = 320;
             rc = clr::disc_fused_impl(a->xs, a->ys, a->B_s, C, HW, K, a->disc_vec, a->disc_beta, a->margin,
                                       a->disc_coef, nullptr, partial, hinge, &n_hinge, st);
             if (rc == CLR_OK) {
@@ -138,6 +146,10 @@ int clr_step_fwd_b(const clr_step_args* a, clr_stream_t stream) {
         }
         if (rc != CLR_OK) return rc;
     }
+    if (defer) {
+        *defer = clr::PendingPack{a->use_disc ? hinge_src : nullptr, n_hinge, hinge_stride, a->use_cons ? w.cons : nullptr, n_cons};
+        return CLR_OK;
+    }
     clr::launch_step_pack(a->use_disc ? hinge_src : nullptr, n_hinge, hinge_stride, a->use_cons ? w.cons : nullptr, n_cons,
                           a->packed2 + (size_t)K * (C + 1), st);
     return clr::launch_status();
@@ -155,9 +167,14 @@ int clr_step_fwd_c(const clr_step_args* a, clr_stream_t stream) {
 int clr_step_fwd(const clr_step_args* a, clr_stream_t stream) {
     int rc = clr_step_fwd_a(a, stream);
     if (rc != CLR_OK) return rc;
-    rc = clr_step_fwd_b(a, stream);
+    clr::PendingPack pk{};
+    rc = clr::step_fwd_b_impl(a, stream, &pk);
     if (rc != CLR_OK) return rc;
-    return clr_step_fwd_c(a, stream);
+    const float ema = a->first_s ? 1.0f : (float)a->decay;
+    return clr::disc_finalize_impl(a->packed2, a->P_s, a->K, a->C, a->npx_global, a->w_disc, ema, a->grad_scale,
+                                   a->g_s, a->xtab, a->w_intra, a->w_inter, a->w_aug, a->aug_weight,
+                                   a->use_disc, a->use_cons, a->losses, pk.hinge, pk.n_hinge, pk.hinge_stride,
+                                   pk.cons, pk.n_cons, static_cast<cudaStream_t>(stream));
 }
 
 int clr_step_bwd(const clr_step_args* a, clr_stream_t stream) {
