@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=25.0)
+    ap.add_argument("--tunable", action="append", default=[], help="library knob name=value (clr_set_tunable)")
     return ap.parse_args()
 
 
@@ -231,6 +232,9 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
         clr.dist.enable()
     lib = _lib.load()
+    for kv in a.tunable:
+        name, val = kv.split("=")
+        _lib.check(lib.clr_set_tunable(name.encode(), int(val)), "clr_set_tunable(%s)" % kv)
 
     use3 = a.workload == "clr3"
     NSET = 2

@@ -33,9 +33,18 @@ struct Tunables {
     int disc_impl;     // 0 = auto (one-read fused discriminative kernel), 1 = force the two-pass form
     int bwd_impl;      // reserved
     int disc_tile;     // 0 = auto, 64 = force 64-pixel tiles in the fused discriminative kernel
+    int l2_keep;       // 1 = evict-last policy on xs in the pooling pass (re-read by the discriminative pass); default off
+    int pdl_off;       // 1 = do not use programmatic dependent launch
     int mc_precise;    // 1 = ATen-exact sigmoids in clr_mc_stats (slower), 0 = fast intrinsics
 };
 Tunables& tunables();
+
+// Programmatic dependent launch: every kernel of the library starts with pdl_wait() and is launched through
+// launch_k(), which sets cudaLaunchAttributeProgrammaticStreamSerialization so that the NEXT kernel's launch
+// overlaps this one's tail; griddepcontrol.wait then blocks until the predecessor grid has completed and its
+// writes are visible.  ("pdl" tunable = 0 turns the attribute off; the wait is then a no-op.)
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // Process-wide count of kernel launches issued by this library (clr_launch_count); relaxed atomic.
 void count_launch();
@@ -170,6 +179,23 @@ __device__ __forceinline__ uint64_t policy_evict_last() {
 // named barrier among a subset of the CTA's warps (id 1..15; 0 is __syncthreads)
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+}  // namespace clr
+
+#include <utility>
+namespace clr {
+
+template <typename... KArgs, typename... Args>
+static inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = tunables().pdl_off ? 0 : 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    count_launch();
+    cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
 }
 
 // Static contiguous partition of `total` items over `parts` workers.

@@ -29,9 +29,17 @@ __device__ __forceinline__ int nearest_src(int dst, float scale, int n_in) {
     return s < n_in - 1 ? s : n_in - 1;
 }
 
+// Exact label decision sigmoid(z) > thr at the cost of the fast sigmoid: the fast value (error < 1e-6) decides
+// unless it lies within 1e-5 of the threshold, in which case ATen's exact expression is evaluated.
+__device__ __forceinline__ bool label_above(float z, float thr) {
+    const float qf = sigmoid_fast(z);
+    if (fabsf(qf - thr) > 1e-5f) return qf > thr;
+    return sigmoid_aten(z) > thr;
+}
+
 // One element of the masked BCE: returns m*l and m; `y` decided exactly, the log terms through fast intrinsics.
 __device__ __forceinline__ void cons_elem(float zt, float za, float m, float thr, float& ml, float& q_out, float& y_out) {
-    const float y = sigmoid_aten(zt) > thr ? 1.0f : 0.0f;
+    const float y = label_above(zt, thr) ? 1.0f : 0.0f;
     const float q = sigmoid_fast(za);
     const float lq = fmaxf(__logf(q), -100.0f);
     const float l1q = fmaxf(__logf(1.0f - q), -100.0f);   // ATen: log1p(-q); identical after fp32 rounding of q
@@ -46,6 +54,7 @@ __global__ void __launch_bounds__(256) cons_kernel(const float* __restrict__ oT,
                                                    double* __restrict__ partial,
                                                    const float* __restrict__ stats, const float* __restrict__ gscale_dev,
                                                    float gscale, float* __restrict__ grad) {
+    pdl_wait();
     const int bk = blockIdx.y;
     const int y0 = blockIdx.x * g.rows_per_cta;
     const int wv = g.Wi / VEC;                       // vectors per row
@@ -77,11 +86,14 @@ __global__ void __launch_bounds__(256) cons_kernel(const float* __restrict__ oT,
         for (int u = 0; u < U; ++u) {
             if (!ok[u]) continue;
             const int sy = nearest_src(yy[u], g.sh, g.H);
+            const float* mrow = mplane + (size_t)sy * g.W;
+            // exact VEC:1 upsampling (the reference's 512 -> 128 case): the whole vector shares one mask pixel
+            const bool shared_mask = (g.Wi == VEC * g.W);
+            const float m_shared = shared_mask ? __ldg(mrow + xv_[u]) : 0.f;
             Pack<VEC> go;
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
-                const int sx = nearest_src(xv_[u] * VEC + v, g.sw, g.W);
-                const float m = __ldg(mplane + (size_t)sy * g.W + sx);
+                const float m = shared_mask ? m_shared : __ldg(mrow + nearest_src(xv_[u] * VEC + v, g.sw, g.W));
                 float ml, q, yv;
                 cons_elem(zt[u].v[v], za[u].v[v], m, thr, ml, q, yv);
                 num += ml; den += m;
@@ -112,6 +124,7 @@ __global__ void __launch_bounds__(256) cons_kernel(const float* __restrict__ oT,
 
 __global__ void __launch_bounds__(256) cons_final_kernel(const double* __restrict__ partial, int nblk, float aug_weight,
                                                          float* __restrict__ stats) {
+    pdl_wait();
     double a = 0.0, b = 0.0;
     for (int i = threadIdx.x; i < nblk; i += blockDim.x) { a += partial[2 * i]; b += partial[2 * i + 1]; }
     a = warp_sum(a);
@@ -148,9 +161,8 @@ int cons_fwd_partials(const float* oT, const float* oT_aug, const float* masks, 
     const ConsGeom g = make_geom(B, K, Hi, Wi, H, W, grid);
     if ((long long)grid.x * grid.y > kConsMaxBlocks || grid.y > 65535) return CLR_ERR_UNSUPPORTED;
     const bool vec4 = (Wi % 4 == 0) && aligned16(oT) && aligned16(oT_aug);
-    count_launch();
-    if (vec4) cons_kernel<4, false><<<grid, 256, 0, st>>>(oT, oT_aug, masks, g, threshold, partial, nullptr, nullptr, 0.f, nullptr);
-    else cons_kernel<1, false><<<grid, 256, 0, st>>>(oT, oT_aug, masks, g, threshold, partial, nullptr, nullptr, 0.f, nullptr);
+    if (vec4) launch_k(cons_kernel<4, false>, grid, 256, 0, st, oT, oT_aug, masks, g, threshold, partial, nullptr, nullptr, 0.f, nullptr);
+    else launch_k(cons_kernel<1, false>, grid, 256, 0, st, oT, oT_aug, masks, g, threshold, partial, nullptr, nullptr, 0.f, nullptr);
     *nblocks = (int)(grid.x * grid.y);
     return launch_status();
 }
@@ -169,7 +181,7 @@ int clr_cons_fwd(const float* oT, const float* oT_aug, const float* masks, int B
     int blocks = 0;
     const int rc = clr::cons_fwd_partials(oT, oT_aug, masks, B, K, Hi, Wi, H, W, threshold, static_cast<double*>(ws), &blocks, st);
     if (rc != CLR_OK) return rc;
-    clr::count_launch(); clr::cons_final_kernel<<<1, 256, 0, st>>>(static_cast<const double*>(ws), blocks, aug_weight, stats);
+    clr::launch_k(clr::cons_final_kernel, 1, 256, 0, st, static_cast<const double*>(ws), blocks, aug_weight, stats);
     return clr::launch_status();
 }
 
@@ -183,9 +195,8 @@ int clr_cons_bwd(const float* oT, const float* oT_aug, const float* masks, int B
     if (grid.y > 65535) return CLR_ERR_UNSUPPORTED;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool vec4 = (Wi % 4 == 0) && clr::aligned16(oT) && clr::aligned16(oT_aug) && clr::aligned16(grad_oT_aug);
-    clr::count_launch();
-    if (vec4) clr::cons_kernel<4, true><<<grid, 256, 0, st>>>(oT, oT_aug, masks, g, threshold, nullptr, stats, gscale_dev, gscale * aug_weight, grad_oT_aug);
-    else clr::cons_kernel<1, true><<<grid, 256, 0, st>>>(oT, oT_aug, masks, g, threshold, nullptr, stats, gscale_dev, gscale * aug_weight, grad_oT_aug);
+    if (vec4) clr::launch_k(clr::cons_kernel<4, true>, grid, 256, 0, st, oT, oT_aug, masks, g, threshold, nullptr, stats, gscale_dev, gscale * aug_weight, grad_oT_aug);
+    else clr::launch_k(clr::cons_kernel<1, true>, grid, 256, 0, st, oT, oT_aug, masks, g, threshold, nullptr, stats, gscale_dev, gscale * aug_weight, grad_oT_aug);
     return clr::launch_status();
 }
 

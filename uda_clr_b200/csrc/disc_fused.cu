@@ -52,6 +52,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 template <int K, int TP, int STAGES>
 __global__ void __launch_bounds__(kThreads, (TP == 32) ? 2 : 1) disc_fused_kernel(const DiscParams p) {
+    pdl_wait();
     constexpr int RS = TP + kDiscPad;            // row stride (floats)
     constexpr int NG = TP / 4;                   // pixel quads (16-byte chunks) per row
     constexpr int NS = kThreads / NG;            // channel slices in phase 1
@@ -261,8 +262,7 @@ static int launch_disc_s(DiscParams& p, int* nparts, cudaStream_t st) {
     if (grid > p.total) grid = p.total;
     if (grid > *nparts) grid = *nparts;
     *nparts = grid;
-    count_launch();
-    kern<<<grid, kThreads, smem, st>>>(p);
+    clr::launch_k(kern, grid, kThreads, smem, st, p);
     return launch_status();
 }
 

@@ -41,6 +41,7 @@ __global__ void __launch_bounds__(1024) align_finalize_kernel(
     float* __restrict__ P_s, float* __restrict__ P_t, float* __restrict__ cur_s, float* __restrict__ cur_t,
     float* __restrict__ g_s, float* __restrict__ g_t,
     float* __restrict__ disc_vec, float* __restrict__ disc_beta, float* __restrict__ losses) {
+    pdl_wait();
     __shared__ double sh[(2 + CLR_MAX_K) * 32];
     const float d = (float)decay, omd = (float)(1.0 - decay);   // the reference forms (1 - decay) in double, then casts
     const float ds = first_s ? 1.f : d, dt = first_t ? 1.f : d;
@@ -104,6 +105,7 @@ __global__ void __launch_bounds__(256) disc_finalize_kernel(
     float ema_factor, float gscale, float* __restrict__ g_s, float* __restrict__ xtab,
     float w_intra, float w_inter, float w_aug, float aug_weight, int use_disc, int use_cons,
     float* __restrict__ losses, PackSrc ps) {
+    pdl_wait();
     float* tail = packed2 + (size_t)K * (C + 1);
     __shared__ double shp[3 * 32];
     __shared__ float tail_s[3];
@@ -147,6 +149,7 @@ __global__ void __launch_bounds__(256) disc_finalize_kernel(
 __global__ void __launch_bounds__(256) step_pack_kernel(const float* __restrict__ hinge_partials, int n_hinge, int hinge_stride,
                                                         const double* __restrict__ cons_partials, int n_cons,
                                                         float* __restrict__ tail) {
+    pdl_wait();
     __shared__ double sh[3 * 32];
     double v[3] = {0.0, 0.0, 0.0};
     if (hinge_partials)
@@ -159,7 +162,7 @@ __global__ void __launch_bounds__(256) step_pack_kernel(const float* __restrict_
 
 void launch_step_pack(const float* hinge_partials, int n_hinge, int hinge_stride,
                       const double* cons_partials, int n_cons, float* tail, cudaStream_t st) {
-    clr::count_launch(); step_pack_kernel<<<1, 256, 0, st>>>(hinge_partials, n_hinge, hinge_stride, cons_partials, n_cons, tail);
+    clr::launch_k(step_pack_kernel, 1, 256, 0, st, hinge_partials, n_hinge, hinge_stride, cons_partials, n_cons, tail);
 }
 
 int disc_finalize_impl(float* packed2, const float* P_s, int K, int C, double npx, float w_disc,
@@ -170,8 +173,7 @@ int disc_finalize_impl(float* packed2, const float* P_s, int K, int C, double np
     if (!packed2 || !losses || K < 1 || K > CLR_MAX_K || C < 1) return CLR_ERR_BAD_ARG;
     if (use_disc && (!P_s || !g_s || !xtab || npx <= 0)) return CLR_ERR_BAD_ARG;
     PackSrc ps{hinge, n_hinge, hinge_stride, cons, n_cons};
-    count_launch(); disc_finalize_kernel<<<1, 256, 0, stream>>>(
-        packed2, P_s, K, C, npx, w_disc, ema_factor, gscale, g_s, xtab, w_intra, w_inter, w_aug, aug_weight,
+    clr::launch_k(disc_finalize_kernel, 1, 256, 0, stream, packed2, P_s, K, C, npx, w_disc, ema_factor, gscale, g_s, xtab, w_intra, w_inter, w_aug, aug_weight,
         use_disc, use_cons, losses, ps);
     return launch_status();
 }
@@ -188,8 +190,7 @@ int clr_align_finalize(const float* sums_s, const float* sums_t, int K, int C,
     if (!sums_s || !sums_t || !stored_s || !stored_t || !P_s || !P_t || !g_s || !g_t || !losses ||
         K < 1 || K > CLR_MAX_K || C < 1)
         return CLR_ERR_BAD_ARG;
-    clr::count_launch(); clr::align_finalize_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(
-        sums_s, sums_t, K, C, stored_s, stored_t, first_s, first_t, decay, w_intra, w_inter,
+    clr::launch_k(clr::align_finalize_kernel, 1, 1024, 0, static_cast<cudaStream_t>(stream), sums_s, sums_t, K, C, stored_s, stored_t, first_s, first_t, decay, w_intra, w_inter,
         P_s, P_t, cur_s, cur_t, g_s, g_t, disc_vec, disc_beta, losses);
     return clr::launch_status();
 }

@@ -42,6 +42,7 @@ __device__ __forceinline__ void mc_sigmoids(float p, float& s_half, float& s_ful
 template <int VEC, int TT, bool PRECISE>
 __global__ void __launch_bounds__(256) mc_stats_kernel(const float* __restrict__ preds, int T, size_t n,
                                                        float* __restrict__ std_map, float* __restrict__ pred_mean) {
+    pdl_wait();
     // n = B*K*Hi*Wi positions; preds is [T][n].  TT > 0: T <= TT, values kept in registers (two-pass
     // variance); TT == 0: any T, Welford.
     const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
@@ -105,10 +106,9 @@ template <int VEC, bool PRECISE>
 static void launch_mc(const float* preds, int T, size_t n, float* std_map, float* pred_mean, cudaStream_t st) {
     const size_t threads = (n + VEC - 1) / VEC;
     const unsigned blocks = (unsigned)((threads + 255) / 256);
-    count_launch();
-    if (T <= 8) mc_stats_kernel<VEC, 8, PRECISE><<<blocks, 256, 0, st>>>(preds, T, n, std_map, pred_mean);
-    else if (T <= 16) mc_stats_kernel<VEC, 16, PRECISE><<<blocks, 256, 0, st>>>(preds, T, n, std_map, pred_mean);
-    else mc_stats_kernel<VEC, 0, PRECISE><<<blocks, 256, 0, st>>>(preds, T, n, std_map, pred_mean);
+    if (T <= 8) launch_k(mc_stats_kernel<VEC, 8, PRECISE>, blocks, 256, 0, st, preds, T, n, std_map, pred_mean);
+    else if (T <= 16) launch_k(mc_stats_kernel<VEC, 16, PRECISE>, blocks, 256, 0, st, preds, T, n, std_map, pred_mean);
+    else launch_k(mc_stats_kernel<VEC, 0, PRECISE>, blocks, 256, 0, st, preds, T, n, std_map, pred_mean);
 }
 
 // upsample_bilinear2d (align_corners=True) source coordinates, as ATen computes them in fp32
@@ -134,6 +134,7 @@ __global__ void __launch_bounds__(256) retrify_weights_kernel(
     int B, int K, int H, int W, int Hi, int Wi, float pseudo_thr, float std_thr,
     float* __restrict__ weights /*[B,2K,H,W]*/, float* __restrict__ masks /*[B,K,H,W]*/,
     float* __restrict__ pseudo_out /*[B,K,H,W] or null*/, float* __restrict__ small_out /*[2][B,K,H,W] or null*/) {
+    pdl_wait();
     // grid.y = b*K + k (one plane), grid.x covers the plane: no 64-bit divisions
     const size_t n = (size_t)B * K * H * W;
     const int pixi = blockIdx.x * blockDim.x + threadIdx.x;
@@ -186,8 +187,7 @@ int clr_retrify_weights(const float* oT_before, const float* pred_mean, const fl
         H < 1 || W < 1 || Hi < 1 || Wi < 1)
         return CLR_ERR_BAD_ARG;
     if ((long long)H * W > 0x7fffff00LL || (long long)B * K > 65535) return CLR_ERR_UNSUPPORTED;
-    clr::count_launch(); clr::retrify_weights_kernel<<<dim3((unsigned)((H * W + 255) / 256), (unsigned)(B * K)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        oT_before, pred_mean, std_map, B, K, H, W, Hi, Wi, pseudo_thr, std_thr, weights, masks, pseudo_out, small_out);
+    clr::launch_k(clr::retrify_weights_kernel, dim3((unsigned)((H * W + 255) / 256), (unsigned)(B * K)), 256, 0, static_cast<cudaStream_t>(stream), oT_before, pred_mean, std_map, B, K, H, W, Hi, Wi, pseudo_thr, std_thr, weights, masks, pseudo_out, small_out);
     return clr::launch_status();
 }
 

@@ -46,6 +46,7 @@ struct DotsParams {
 
 template <int QT, int VEC, int OP, bool SUMSQ>
 __global__ void __launch_bounds__(kThreads, 3) pixel_dots_kernel(const DotsParams p) {
+    pdl_wait();
     constexpr int TP = 16 * VEC;                 // pixels per tile
     constexpr int NA = QT + (SUMSQ ? 1 : 0);     // accumulator rows
     extern __shared__ __align__(16) float smem[];
@@ -201,7 +202,7 @@ static int launch_dots(DotsParams& p, int* grid_out, cudaStream_t st) {
         if (*grid_out > 0 && grid > *grid_out) grid = *grid_out;
         *grid_out = grid;
     }
-    clr::count_launch(); kern<<<grid, kThreads, smem, st>>>(p);
+    clr::launch_k(kern, grid, kThreads, smem, st, p);
     return launch_status();
 }
 
@@ -229,6 +230,7 @@ int pixel_dots_impl(DotsParams& p, int op, bool want_sumsq, int* grid_out, cudaS
 // built on the device so the call stays asynchronous.
 __global__ void bwd_w_tables_kernel(const float* __restrict__ g, const float* __restrict__ sums, int K, int C,
                                     int fmt, float scale, float* __restrict__ V, float* __restrict__ beta) {
+    pdl_wait();
     // one CTA per output row q
     const int q = blockIdx.x;
     const int R = 2 * K;
@@ -262,6 +264,7 @@ __global__ void bwd_w_tables_kernel(const float* __restrict__ g, const float* __
 }
 
 __global__ void vec_norm_kernel(const float* __restrict__ v, int C, float eps, float* __restrict__ out) {
+    pdl_wait();
     double acc = 0.0;
     for (int c = threadIdx.x; c < C; c += blockDim.x) acc += (double)v[c] * v[c];
     acc = warp_sum(acc);
@@ -277,6 +280,7 @@ __global__ void vec_norm_kernel(const float* __restrict__ v, int C, float eps, f
 
 // global min / max of a small map (two stages, fixed order), then (x - min) / (max - min) in place
 __global__ void __launch_bounds__(256) minmax_partial_kernel(const float* __restrict__ x, size_t n, float* __restrict__ part) {
+    pdl_wait();
     float lo = INFINITY, hi = -INFINITY;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const float v = x[i];
@@ -297,6 +301,7 @@ __global__ void __launch_bounds__(256) minmax_partial_kernel(const float* __rest
     }
 }
 __global__ void __launch_bounds__(256) minmax_apply_kernel(float* __restrict__ x, size_t n, const float* __restrict__ part, int nparts) {
+    pdl_wait();
     float lo = INFINITY, hi = -INFINITY;
     for (int i = 0; i < nparts; ++i) { lo = fminf(lo, part[2 * i]); hi = fmaxf(hi, part[2 * i + 1]); }
     const float den = hi - lo;
@@ -346,7 +351,7 @@ int clr_proto_cosine(const float* feat, int B, int C, int HW, const float* proto
                      clr_stream_t stream) {
     if (!out || !ws4 || !proto || C < 1) return CLR_ERR_BAD_ARG;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    clr::count_launch(); clr::vec_norm_kernel<<<1, 256, 0, st>>>(proto, C, 1e-8f, ws4);
+    clr::launch_k(clr::vec_norm_kernel, 1, 256, 0, st, proto, C, 1e-8f, ws4);
     clr::DotsParams p{};
     p.feat = feat; p.V = proto; p.out = out; p.vnorm_dev = ws4;
     p.B = B; p.C = C; p.HW = HW; p.Q = 1; p.epi = clr::DOTS_EPI_COSINE;
@@ -357,8 +362,8 @@ int clr_minmax_normalize(float* x, size_t n, float* ws /*>= 2*256 floats*/, clr_
     if (!x || !ws || n == 0) return CLR_ERR_BAD_ARG;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int blocks = (int)((n + 255) / 256 < 256 ? (n + 255) / 256 : 256);
-    clr::count_launch(); clr::minmax_partial_kernel<<<blocks, 256, 0, st>>>(x, n, ws);
-    clr::count_launch(); clr::minmax_apply_kernel<<<blocks, 256, 0, st>>>(x, n, ws, blocks);
+    clr::launch_k(clr::minmax_partial_kernel, blocks, 256, 0, st, x, n, ws);
+    clr::launch_k(clr::minmax_apply_kernel, blocks, 256, 0, st, x, n, ws, blocks);
     return clr::launch_status();
 }
 
@@ -388,7 +393,7 @@ int clr_pool_bwd_w(const float* feat, int fmt, int B, int C, int HW, int K,
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     float* V = static_cast<float*>(ws);
     float* beta = V + (size_t)Q * C;
-    clr::count_launch(); clr::bwd_w_tables_kernel<<<Q, 256, 0, st>>>(g, sums, K, C, fmt, scale, V, beta);
+    clr::launch_k(clr::bwd_w_tables_kernel, Q, 256, 0, st, g, sums, K, C, fmt, scale, V, beta);
     clr::DotsParams p{};
     p.feat = feat; p.V = V; p.out = grad_w; p.B = B; p.C = C; p.HW = HW; p.Q = Q; p.epi = clr::DOTS_EPI_AFFINE;
     p.beta_dev = beta;

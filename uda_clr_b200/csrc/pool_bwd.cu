@@ -39,6 +39,7 @@ constexpr int kBwdSpan = 32;   // channels per CTA
 
 template <int QT, int VEC>
 __global__ void __launch_bounds__(kThreads) pool_bwd_kernel(const BwdParams p) {
+    pdl_wait();
     __shared__ __align__(16) float T[(1 + QT) * kBwdSpan];
     const int tid = threadIdx.x;
     int bid = blockIdx.x;
@@ -114,8 +115,8 @@ __global__ void __launch_bounds__(kThreads) pool_bwd_kernel(const BwdParams p) {
 
 template <int QT>
 static int launch_bwd(const BwdParams& p, bool vec4, int ctas, cudaStream_t st) {
-    if (vec4) { count_launch(); pool_bwd_kernel<QT, 4><<<ctas, kThreads, 0, st>>>(p); }
-    else { count_launch(); pool_bwd_kernel<QT, 1><<<ctas, kThreads, 0, st>>>(p); }
+    if (vec4) { clr::launch_k(pool_bwd_kernel<QT, 4>, ctas, kThreads, 0, st, p); }
+    else { clr::launch_k(pool_bwd_kernel<QT, 1>, ctas, kThreads, 0, st, p); }
     return launch_status();
 }
 

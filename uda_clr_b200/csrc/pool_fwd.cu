@@ -37,6 +37,7 @@ struct PoolDom {
     int fmt;
     int items;        // B*nChunk*nGroup
     int slots;        // B*nChunk
+    int keep_l2;      // 1: this feature map is read again soon (evict-last L2 policy), 0: streaming (evict-first)
 };
 
 struct PoolParams {
@@ -172,6 +173,7 @@ __device__ __forceinline__ void reduce_and_store(float (&acc)[32], const float* 
 // ------------------------------------------------------------------------------------------------
 template <int R, int VEC>
 __global__ void __launch_bounds__(kThreads, 2) pool_fwd_ldg_kernel(const PoolParams p) {
+    pdl_wait();
     constexpr int CG = pool_cg(R), REPS = pool_reps(R), PX = kThreads * VEC * REPS;
     extern __shared__ __align__(16) float smem[];
     float* wsm = smem;                 // [R][PX]
@@ -241,6 +243,7 @@ struct PoolTmaSmem {
 
 template <int R>
 __global__ void __launch_bounds__(kPoolTmaThreads, 1) pool_fwd_tma_kernel(const PoolParams p) {
+    pdl_wait();
     using SM = PoolTmaSmem<R>;
     constexpr int CG = SM::CG, REPS = SM::REPS, PX = SM::PX, VEC = 4;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -263,7 +266,7 @@ __global__ void __launch_bounds__(kPoolTmaThreads, 1) pool_fwd_tma_kernel(const 
     if (warp == kWarps) {
         // ---------------- producer ----------------
         if (lane == 0) {
-            const uint64_t pol = policy_evict_first();
+            const uint64_t pol_stream = policy_evict_first(), pol_keep = policy_evict_last();
             int stage = 0;
             uint32_t phase = 0;
             for (int it = begin; it < end; ++it) {
@@ -276,6 +279,7 @@ __global__ void __launch_bounds__(kPoolTmaThreads, 1) pool_fwd_tma_kernel(const 
                 mbar_arrive_expect_tx(&full[stage], (uint32_t)(rows * npx * sizeof(float)));
                 const float* src = D.feat + ((size_t)ic.b * p.C + c0) * p.HW + px0;
                 float* dst = xs + (size_t)stage * CG * PX;
+                const uint64_t pol = D.keep_l2 ? pol_keep : pol_stream;
                 for (int j = 0; j < rows; ++j)
                     bulk_g2s(dst + j * PX, src + (size_t)j * p.HW, (uint32_t)(npx * sizeof(float)), &full[stage], pol);
                 if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -334,6 +338,7 @@ __global__ void __launch_bounds__(kPoolTmaThreads, 1) pool_fwd_tma_kernel(const 
 
 // sums[r][c] = sum over (b,chunk) slots of partial[slot][r][c], fp64, fixed order.
 __global__ void __launch_bounds__(256) pool_reduce_kernel(const PoolParams p, int R) {
+    pdl_wait();
     const int d = blockIdx.y;
     const PoolDom& D = p.dom[d];
     const int n = R * (p.C + 1);
@@ -354,6 +359,7 @@ __global__ void __launch_bounds__(256) pool_reduce_kernel(const PoolParams p, in
 }
 
 __global__ void proto_finalize_kernel(const float* __restrict__ sums, int R, int C, float* __restrict__ mu) {
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= R * C) return;
     const int r = i / C, c = i - r * C;
@@ -367,13 +373,12 @@ void launch_partial_reduce(const float* partial, int slots, int R, int C, float*
     p.dom[0].sums = sums;
     p.dom[0].slots = slots;
     const int n = R * (C + 1);
-    count_launch();
-    pool_reduce_kernel<<<dim3((n + 31) / 32, 1), dim3(32, 8), 0, st>>>(p, R);
+    clr::launch_k(pool_reduce_kernel, dim3((n + 31) / 32, 1), dim3(32, 8), 0, st, p, R);
 }
 
 static void launch_reduce(const PoolParams& p, int R, cudaStream_t st) {
     const int n = R * (p.C + 1);
-    clr::count_launch(); pool_reduce_kernel<<<dim3((n + 31) / 32, p.ndom), dim3(32, 8), 0, st>>>(p, R);
+    clr::launch_k(pool_reduce_kernel, dim3((n + 31) / 32, p.ndom), dim3(32, 8), 0, st, p, R);
 }
 
 template <int R, int VEC>
@@ -387,7 +392,7 @@ static int launch_ldg(const PoolParams& p, cudaStream_t st) {
     if (occ < 1) occ = 1;
     int grid = device_facts().sms * occ;
     if (grid > p.total) grid = p.total;
-    clr::count_launch(); kern<<<grid, kThreads, smem, st>>>(p);
+    clr::launch_k(kern, grid, kThreads, smem, st, p);
     launch_reduce(p, R, st);
     return launch_status();
 }
@@ -409,7 +414,7 @@ static int launch_tma(PoolParams p, cudaStream_t st) {
     if (occ < 1) occ = 1;
     int grid = device_facts().sms * occ;
     if (grid > p.total) grid = p.total;
-    clr::count_launch(); kern<<<grid, kPoolTmaThreads, smem, st>>>(p);
+    clr::launch_k(kern, grid, kPoolTmaThreads, smem, st, p);
     launch_reduce(p, R, st);
     return launch_status();
 }
@@ -438,7 +443,7 @@ size_t pool_partial_bytes(int B, int C, int HW, int R) { return sizeof(float) * 
 // R = number of output rows (2K for the prototype formats; any 1..16 for explicit rows).
 int pool_fwd_impl(const float* feat0, const float* w0, int fmt0, int B0, float* sums0,
                   const float* feat1, const float* w1, int fmt1, int B1, float* sums1,
-                  int C, int HW, int R, void* ws, size_t ws_bytes, cudaStream_t st) {
+                  int C, int HW, int R, void* ws, size_t ws_bytes, cudaStream_t st, int keep0, int keep1) {
     const int ndom = feat1 ? 2 : 1;
     CLR_CHECK_ARG(feat0 && w0 && sums0 && ws && B0 > 0 && C > 0 && HW > 0 && R >= 1 && R <= 2 * CLR_MAX_K);
     CLR_CHECK_ARG(fmt0 == CLR_W_COMPLEMENT || fmt0 == CLR_W_EXPLICIT);
@@ -464,9 +469,9 @@ int pool_fwd_impl(const float* feat0, const float* w0, int fmt0, int B0, float* 
     const long long items0 = (long long)B0 * p.nChunk * p.nGroup;
     const long long items1 = ndom == 2 ? (long long)B1 * p.nChunk * p.nGroup : 0;
     if (items0 + items1 > 0x3fffffff) return CLR_ERR_UNSUPPORTED;
-    p.dom[0] = PoolDom{feat0, w0, wsf, sums0, B0, fmt0, (int)items0, B0 * p.nChunk};
+    p.dom[0] = PoolDom{feat0, w0, wsf, sums0, B0, fmt0, (int)items0, B0 * p.nChunk, keep0};
     if (ndom == 2)
-        p.dom[1] = PoolDom{feat1, w1, wsf + partial_floats(B0, C, HW, R), sums1, B1, fmt1, (int)items1, B1 * p.nChunk};
+        p.dom[1] = PoolDom{feat1, w1, wsf + partial_floats(B0, C, HW, R), sums1, B1, fmt1, (int)items1, B1 * p.nChunk, keep1};
     p.total = (int)(items0 + items1);
     return dispatch(R, vec4, tma, p, st);
 }
@@ -510,7 +515,7 @@ int clr_pool_fwd2(const float* feat0, const float* w0, int fmt0, int B0,
 int clr_proto_finalize(const float* sums, int R, int C, float* mu, clr_stream_t stream) {
     if (!sums || !mu || R <= 0 || C <= 0) return CLR_ERR_BAD_ARG;
     const int n = R * C;
-    clr::count_launch(); clr::proto_finalize_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(sums, R, C, mu);
+    clr::launch_k(clr::proto_finalize_kernel, (n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream), sums, R, C, mu);
     return clr::launch_status();
 }
 

@@ -86,9 +86,12 @@ int clr_step_fwd_a(const clr_step_args* a, clr_stream_t stream) {
     float* sums_t = a->packed1 + (size_t)R * (a->C + 1);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (a->ev_pool_begin) cudaEventRecord(static_cast<cudaEvent_t>(a->ev_pool_begin), st);
-    rc = clr::pool_fwd_impl(a->xs, a->ys, CLR_W_COMPLEMENT, a->B_s, sums_s,
-                            a->xt, clr::target_weights(a), clr::target_fmt(a), a->B_t, sums_t,
-                            a->C, HW, R, w.pool, w.pool_bytes, st);
+    // target first, source last; optionally ("l2_keep" = 1) the source rows get an evict-last L2 policy because
+    // the discriminative pass re-reads xs right afterwards
+    const int keep_xs = (a->use_disc && clr::tunables().l2_keep == 1) ? 1 : 0;   // measured slower on B200 (profiles/): off by default
+    rc = clr::pool_fwd_impl(a->xt, clr::target_weights(a), clr::target_fmt(a), a->B_t, sums_t,
+                            a->xs, a->ys, CLR_W_COMPLEMENT, a->B_s, sums_s,
+                            a->C, HW, R, w.pool, w.pool_bytes, st, 0, keep_xs);
     if (a->ev_pool_end) cudaEventRecord(static_cast<cudaEvent_t>(a->ev_pool_end), st);
     return rc;
 }
