@@ -15,7 +15,10 @@
 namespace clr {
 
 __device__ __forceinline__ float sigmoid_aten(float x) { return 1.0f / (1.0f + expf(-x)); }   // label decision: exact
-__device__ __forceinline__ float sigmoid_fast(float x) { return __frcp_rn(1.0f + __expf(-x)); }
+__device__ __forceinline__ float ex2_approx(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float lg2_approx(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float sigmoid_fast(float x) { return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x)); }
 
 struct ConsGeom {
     int BK, Hi, Wi, H, W;
@@ -37,82 +40,85 @@ __device__ __forceinline__ bool label_above(float z, float thr) {
     return sigmoid_aten(z) > thr;
 }
 
-// One element of the masked BCE: returns m*l and m; `y` decided exactly, the log terms through fast intrinsics.
+// One element of the masked BCE: returns m*l; `y` decided exactly, the log terms through fast intrinsics
+// (ATen: (y-1)*max(log1p(-q),-100) - y*max(log(q),-100) with q = sigmoid(z) rounded to fp32).
 __device__ __forceinline__ void cons_elem(float zt, float za, float m, float thr, float& ml, float& q_out, float& y_out) {
     const float y = label_above(zt, thr) ? 1.0f : 0.0f;
     const float q = sigmoid_fast(za);
-    const float lq = fmaxf(__logf(q), -100.0f);
-    const float l1q = fmaxf(__logf(1.0f - q), -100.0f);   // ATen: log1p(-q); identical after fp32 rounding of q
+    const float lq = fmaxf(0.6931471805599453f * lg2_approx(q), -100.0f);
+    const float l1q = fmaxf(0.6931471805599453f * lg2_approx(1.0f - q), -100.0f);
     ml = m * ((y - 1.0f) * l1q - y * lq);
     q_out = q; y_out = y;
 }
 
-// grid = (row blocks, B*K planes); each CTA covers `rows_per_cta` image rows of one plane.
+constexpr int kConsTX = 64, kConsTY = 4;   // block = 64 vector columns x 4 rows
+
+// grid = (row blocks, B*K planes); each CTA covers `rows_per_cta` image rows of one plane; thread (tx, ty) walks
+// vector columns tx, tx+64, .. of rows ty, ty+4, .. -- no divisions, up to 4 independent 128-bit load pairs in flight.
 template <int VEC, bool BWD>
-__global__ void __launch_bounds__(256) cons_kernel(const float* __restrict__ oT, const float* __restrict__ oT_aug,
-                                                   const float* __restrict__ masks, ConsGeom g, float thr,
-                                                   double* __restrict__ partial,
-                                                   const float* __restrict__ stats, const float* __restrict__ gscale_dev,
-                                                   float gscale, float* __restrict__ grad) {
+__global__ void __launch_bounds__(kConsTX * kConsTY) cons_kernel(const float* __restrict__ oT, const float* __restrict__ oT_aug,
+                                                                 const float* __restrict__ masks, ConsGeom g, float thr,
+                                                                 double* __restrict__ partial,
+                                                                 const float* __restrict__ stats, const float* __restrict__ gscale_dev,
+                                                                 float gscale, float* __restrict__ grad) {
     pdl_wait();
     const int bk = blockIdx.y;
     const int y0 = blockIdx.x * g.rows_per_cta;
     const int wv = g.Wi / VEC;                       // vectors per row
-    const int nvec = g.rows_per_cta * wv;
     const size_t plane = (size_t)bk * g.Hi * g.Wi;
     const float* mplane = masks + (size_t)bk * g.H * g.W;
+    const bool shared_mask = (g.Wi == VEC * g.W);    // exact VEC:1 upsampling: a vector shares one mask pixel
     float coef = 0.f;
     if (BWD) coef = (gscale_dev ? gscale * __ldg(gscale_dev) : gscale) / __ldg(stats + 1);
     float num = 0.f, den = 0.f;
-    constexpr int U = 4;   // independent vector loads in flight per thread
-    for (int base = threadIdx.x; base < nvec; base += U * blockDim.x) {
-        Pack<VEC> zt[U], za[U];
-        int yy[U], xv_[U];
-        bool ok[U];
+    constexpr int U = 4;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    for (int ry = ty; ry < g.rows_per_cta; ry += kConsTY) {
+        const int y = y0 + ry;
+        if (y >= g.Hi) break;
+        const int sy = nearest_src(y, g.sh, g.H);
+        const float* mrow = mplane + (size_t)sy * g.W;
+        const size_t rowoff = plane + (size_t)y * g.Wi;
+        for (int xb = tx; xb < wv; xb += U * kConsTX) {
+            Pack<VEC> zt[U], za[U];
+            float msh[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int idx = base + u * blockDim.x;
-            const int ry = idx / wv;
-            xv_[u] = idx - ry * wv;
-            yy[u] = y0 + ry;
-            ok[u] = idx < nvec && yy[u] < g.Hi;
-            if (ok[u]) {
-                const size_t off = plane + (size_t)yy[u] * g.Wi + (size_t)xv_[u] * VEC;
-                zt[u] = ld_stream<VEC>(oT + off);
-                za[u] = ld_stream<VEC>(oT_aug + off);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (!ok[u]) continue;
-            const int sy = nearest_src(yy[u], g.sh, g.H);
-            const float* mrow = mplane + (size_t)sy * g.W;
-            // exact VEC:1 upsampling (the reference's 512 -> 128 case): the whole vector shares one mask pixel
-            const bool shared_mask = (g.Wi == VEC * g.W);
-            const float m_shared = shared_mask ? __ldg(mrow + xv_[u]) : 0.f;
-            Pack<VEC> go;
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) {
-                const float m = shared_mask ? m_shared : __ldg(mrow + nearest_src(xv_[u] * VEC + v, g.sw, g.W));
-                float ml, q, yv;
-                cons_elem(zt[u].v[v], za[u].v[v], m, thr, ml, q, yv);
-                num += ml; den += m;
-                if (BWD) {
-                    // ATen binary_cross_entropy_backward: (q - y) / max((1-q) q, 1e-12), chained with sigmoid' = q (1-q)
-                    const float qq = (1.0f - q) * q;
-                    go.v[v] = coef * m * (q - yv) / fmaxf(qq, 1e-12f) * qq;
+            for (int u = 0; u < U; ++u) {
+                const int xv = xb + u * kConsTX;
+                if (xv < wv) {
+                    zt[u] = ld_stream<VEC>(oT + rowoff + (size_t)xv * VEC);
+                    za[u] = ld_stream<VEC>(oT_aug + rowoff + (size_t)xv * VEC);
+                    msh[u] = shared_mask ? __ldg(mrow + xv) : 0.f;
                 }
             }
-            if (BWD) st_stream<VEC>(grad + plane + (size_t)yy[u] * g.Wi + (size_t)xv_[u] * VEC, go);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int xv = xb + u * kConsTX;
+                if (xv >= wv) continue;
+                Pack<VEC> go;
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) {
+                    const float m = shared_mask ? msh[u] : __ldg(mrow + nearest_src(xv * VEC + v, g.sw, g.W));
+                    float ml, q, yv;
+                    cons_elem(zt[u].v[v], za[u].v[v], m, thr, ml, q, yv);
+                    num += ml; den += m;
+                    if (BWD) {
+                        // ATen binary_cross_entropy_backward: (q - y) / max((1-q) q, 1e-12), chained with sigmoid' = q (1-q)
+                        const float qq = (1.0f - q) * q;
+                        go.v[v] = coef * m * (q - yv) / fmaxf(qq, 1e-12f) * qq;
+                    }
+                }
+                if (BWD) st_stream<VEC>(grad + rowoff + (size_t)xv * VEC, go);
+            }
         }
     }
     if (!BWD) {
         double dn = warp_sum((double)num), dd = warp_sum((double)den);
         __shared__ double sh[2][8];
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const int t = ty * kConsTX + tx, lane = t & 31, warp = t >> 5;
         if (lane == 0) { sh[0][warp] = dn; sh[1][warp] = dd; }
         __syncthreads();
-        if (threadIdx.x == 0) {
+        if (t == 0) {
             double a = 0.0, b = 0.0;
             for (int w = 0; w < 8; ++w) { a += sh[0][w]; b += sh[1][w]; }
             const int cta = blockIdx.y * gridDim.x + blockIdx.x;
@@ -161,8 +167,8 @@ int cons_fwd_partials(const float* oT, const float* oT_aug, const float* masks, 
     const ConsGeom g = make_geom(B, K, Hi, Wi, H, W, grid);
     if ((long long)grid.x * grid.y > kConsMaxBlocks || grid.y > 65535) return CLR_ERR_UNSUPPORTED;
     const bool vec4 = (Wi % 4 == 0) && aligned16(oT) && aligned16(oT_aug);
-    if (vec4) launch_k(cons_kernel<4, false>, grid, 256, 0, st, oT, oT_aug, masks, g, threshold, partial, nullptr, nullptr, 0.f, nullptr);
-    else launch_k(cons_kernel<1, false>, grid, 256, 0, st, oT, oT_aug, masks, g, threshold, partial, nullptr, nullptr, 0.f, nullptr);
+    if (vec4) launch_k(cons_kernel<4, false>, grid, dim3(kConsTX, kConsTY), 0, st, oT, oT_aug, masks, g, threshold, partial, nullptr, nullptr, 0.f, nullptr);
+    else launch_k(cons_kernel<1, false>, grid, dim3(kConsTX, kConsTY), 0, st, oT, oT_aug, masks, g, threshold, partial, nullptr, nullptr, 0.f, nullptr);
     *nblocks = (int)(grid.x * grid.y);
     return launch_status();
 }
@@ -195,8 +201,8 @@ int clr_cons_bwd(const float* oT, const float* oT_aug, const float* masks, int B
     if (grid.y > 65535) return CLR_ERR_UNSUPPORTED;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool vec4 = (Wi % 4 == 0) && clr::aligned16(oT) && clr::aligned16(oT_aug) && clr::aligned16(grad_oT_aug);
-    if (vec4) clr::launch_k(clr::cons_kernel<4, true>, grid, 256, 0, st, oT, oT_aug, masks, g, threshold, nullptr, stats, gscale_dev, gscale * aug_weight, grad_oT_aug);
-    else clr::launch_k(clr::cons_kernel<1, true>, grid, 256, 0, st, oT, oT_aug, masks, g, threshold, nullptr, stats, gscale_dev, gscale * aug_weight, grad_oT_aug);
+    if (vec4) clr::launch_k(clr::cons_kernel<4, true>, grid, dim3(clr::kConsTX, clr::kConsTY), 0, st, oT, oT_aug, masks, g, threshold, nullptr, stats, gscale_dev, gscale * aug_weight, grad_oT_aug);
+    else clr::launch_k(clr::cons_kernel<1, true>, grid, dim3(clr::kConsTX, clr::kConsTY), 0, st, oT, oT_aug, masks, g, threshold, nullptr, stats, gscale_dev, gscale * aug_weight, grad_oT_aug);
     return clr::launch_status();
 }
 

@@ -41,7 +41,9 @@ struct DiscParams {
 
 constexpr int kDiscPad = 4;
 constexpr int kDiscMaxParts = 320;   // >= resident CTAs (2 per SM): one partial per CTA
-constexpr int kDiscMaxCPT = 3;     // channels per thread in phase 2 (C <= 768)
+constexpr int kDiscCols = 64;      // phase 2: 64 channel columns x 4 pixel quarters = 256 threads
+constexpr int kDiscMaxCPT = 12;    // channels per thread in phase 2 (C <= 768)
+constexpr int kDiscMaxAcc = 48;    // (C/64)*K register accumulators at most
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
@@ -66,7 +68,7 @@ __global__ void __launch_bounds__(kThreads, (TP == 32) ? 2 : 1) disc_fused_kerne
     float* Vs = wred + (1 + NE) * kWarps;                                    // [K][C]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    for (int i = tid; i < K * p.C; i += kThreads) Vs[i] = p.V[i];
+    for (int i = tid; i < K * p.C; i += kThreads) { const int k = i / p.C, c = i - k * p.C; Vs[c * K + k] = p.V[i]; }   // [C][K]
 
     int begin, end;
     partition(p.total, gridDim.x, blockIdx.x, begin, end);
@@ -134,9 +136,20 @@ __global__ void __launch_bounds__(kThreads, (TP == 32) ? 2 : 1) disc_fused_kerne
 #pragma unroll 4
         for (int c = s; c < p.C; c += NS) {
             const float4 x = *reinterpret_cast<const float4*>(xt + (size_t)c * RS + 4 * g);
+            float vv[K];
+            if constexpr (K == 2) {
+                const float2 t2 = *reinterpret_cast<const float2*>(Vs + 2 * c);
+                vv[0] = t2.x; vv[1] = t2.y;
+            } else if constexpr (K == 4) {
+                const float4 t4 = *reinterpret_cast<const float4*>(Vs + 4 * c);
+                vv[0] = t4.x; vv[1] = t4.y; vv[2] = t4.z; vv[3] = t4.w;
+            } else {
+#pragma unroll
+                for (int k = 0; k < K; ++k) vv[k] = Vs[c * K + k];
+            }
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                const float vk = Vs[k * p.C + c];
+                const float vk = vv[k];
                 acc[k][0] = fmaf(x.x, vk, acc[k][0]);
                 acc[k][1] = fmaf(x.y, vk, acc[k][1]);
                 acc[k][2] = fmaf(x.z, vk, acc[k][2]);
@@ -181,22 +194,32 @@ __global__ void __launch_bounds__(kThreads, (TP == 32) ? 2 : 1) disc_fused_kerne
             ncf[ei] += cf;
         }
         __syncthreads();
-        // ---- phase 2: coefficient-weighted sums over the pixel axis, one channel row per thread ----------
+        // ---- phase 2: coefficient-weighted sums over the pixel axis.  Thread = (channel column cp, pixel quarter h):
+        //      it walks channels cp, cp+64, .. over its quarter of the tile's pixels, so the coefficient loads
+        //      are shared by all of the thread's channels (12 LDS.128 per 64 FMA at C = 256, K = 2)
+        {
+            const int cp = tid % kDiscCols, h = tid / kDiscCols;
+            constexpr int JQ = NG / 4;             // pixel quads per quarter
+            float4 cf[JQ][K];
 #pragma unroll
-        for (int i = 0; i < kDiscMaxCPT; ++i) {
-            const int c = tid + i * kThreads;
-            if (c < p.C) {
-                const float* row = xt + (size_t)c * RS;
-#pragma unroll 4
-                for (int j4 = 0; j4 < NG; ++j4) {
-                    const float4 x = *reinterpret_cast<const float4*>(row + 4 * j4);
+            for (int jq = 0; jq < JQ; ++jq)
 #pragma unroll
-                    for (int k = 0; k < K; ++k) {
-                        const float4 cf = *reinterpret_cast<const float4*>(cfs + k * TP + 4 * j4);
-                        A[i][k] = fmaf(x.x, cf.x, A[i][k]);
-                        A[i][k] = fmaf(x.y, cf.y, A[i][k]);
-                        A[i][k] = fmaf(x.z, cf.z, A[i][k]);
-                        A[i][k] = fmaf(x.w, cf.w, A[i][k]);
+                for (int k = 0; k < K; ++k) cf[jq][k] = *reinterpret_cast<const float4*>(cfs + k * TP + 4 * (h * JQ + jq));
+#pragma unroll
+            for (int i = 0; i < kDiscMaxCPT; ++i) {
+                const int c = cp + i * kDiscCols;
+                if (c < p.C) {
+                    const float* row = xt + (size_t)c * RS + 4 * h * JQ;
+#pragma unroll
+                    for (int jq = 0; jq < JQ; ++jq) {
+                        const float4 x = *reinterpret_cast<const float4*>(row + 4 * jq);
+#pragma unroll
+                        for (int k = 0; k < K; ++k) {
+                            A[i][k] = fmaf(x.x, cf[jq][k].x, A[i][k]);
+                            A[i][k] = fmaf(x.y, cf[jq][k].y, A[i][k]);
+                            A[i][k] = fmaf(x.z, cf[jq][k].z, A[i][k]);
+                            A[i][k] = fmaf(x.w, cf[jq][k].w, A[i][k]);
+                        }
                     }
                 }
             }
@@ -206,15 +229,26 @@ __global__ void __launch_bounds__(kThreads, (TP == 32) ? 2 : 1) disc_fused_kerne
         // thread finished this tile's phase 2, so no trailing barrier is needed
     }
     cp_async_wait<0>();
-    // ---- CTA partials --------------------------------------------------------------------------------
-    float* out = p.partial + (size_t)blockIdx.x * K * (p.C + 1);
+    // ---- CTA partials: the 4 pixel quarters of every (k, c) are combined through shared memory (tiles are free now)
+    __syncthreads();
+    {
+        float* comb = tiles;                     // [4][K][C]
+        const int cp = tid % kDiscCols, h = tid / kDiscCols;
 #pragma unroll
-    for (int i = 0; i < kDiscMaxCPT; ++i) {
-        const int c = tid + i * kThreads;
-        if (c < p.C) {
+        for (int i = 0; i < kDiscMaxCPT; ++i) {
+            const int c = cp + i * kDiscCols;
+            if (c < p.C) {
 #pragma unroll
-            for (int k = 0; k < K; ++k) out[(size_t)k * (p.C + 1) + c] = A[i][k];
+                for (int k = 0; k < K; ++k) comb[((size_t)h * K + k) * p.C + c] = A[i][k];
+            }
         }
+    }
+    __syncthreads();
+    float* out = p.partial + (size_t)blockIdx.x * K * (p.C + 1);
+    for (int i = tid; i < K * p.C; i += kThreads) {
+        const int k = i / p.C, c = i - k * p.C;
+        const float* comb = tiles;
+        out[(size_t)k * (p.C + 1) + c] = (comb[i] + comb[(size_t)K * p.C + i]) + (comb[(size_t)2 * K * p.C + i] + comb[(size_t)3 * K * p.C + i]);
     }
     const float hs = warp_sum(hinge_sum);
     if (lane == 0) wred[warp] = hs;
@@ -299,7 +333,8 @@ int disc_fused_impl(const float* xs, const float* ys, int B, int C, int HW, int 
                     float* coef, float* delta, float* partial, float* hinge, int* nparts, cudaStream_t st) {
     CLR_CHECK_ARG(xs && ys && disc_vec && disc_beta && coef && partial && hinge && nparts && *nparts > 0);
     CLR_CHECK_ARG(B > 0 && C > 0 && HW > 0 && K >= 1 && K <= CLR_MAX_K);
-    if (HW % 4 != 0 || !aligned16(xs) || C > kDiscMaxCPT * kThreads) return CLR_ERR_UNSUPPORTED;
+    if (HW % 4 != 0 || !aligned16(xs) || C > kDiscMaxCPT * kDiscCols) return CLR_ERR_UNSUPPORTED;
+    if (((C + kDiscCols - 1) / kDiscCols) * K > kDiscMaxAcc) return CLR_ERR_UNSUPPORTED;
     DiscParams p{};
     p.xs = xs; p.ys = ys; p.V = disc_vec; p.beta = disc_beta; p.coef = coef; p.delta = delta;
     p.partial = partial; p.hinge = hinge; p.alpha = -2.0f / (float)C; p.margin = margin;

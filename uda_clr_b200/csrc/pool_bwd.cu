@@ -38,7 +38,7 @@ struct BwdParams {
 constexpr int kBwdSpan = 32;   // channels per CTA
 
 template <int QT, int VEC>
-__global__ void __launch_bounds__(kThreads) pool_bwd_kernel(const BwdParams p) {
+__global__ void __launch_bounds__(kThreads, 4) pool_bwd_kernel(const BwdParams p) {
     pdl_wait();
     __shared__ __align__(16) float T[(1 + QT) * kBwdSpan];
     const int tid = threadIdx.x;
@@ -68,29 +68,34 @@ __global__ void __launch_bounds__(kThreads) pool_bwd_kernel(const BwdParams p) {
             cf[q] = ld_keep<VEC>(src + px);
         }
     }
-    // ---- per-CTA table for channels c0 .. c0+31: T[0] constant term, T[1+q] coefficient of plane q -
-    if (tid < kBwdSpan) {
-        const int c = c0 + tid;
+    // ---- per-CTA table for channels c0 .. c0+31: T[0] constant term, T[1+q] coefficient of plane q.
+    //      One thread per (row q, channel j) entry so the g / N loads and divides are a single parallel round.
+    {
+        const int j = tid & (kBwdSpan - 1), q = tid / kBwdSpan;     // q in [0, 8): rows 0..QT handled in rounds
+        const int c = c0 + j;
         const float scale = D.scale_dev ? D.scale * __ldg(D.scale_dev) : D.scale;
-        float t0 = 0.f;
-#pragma unroll
-        for (int q = 0; q < QT; ++q) T[(1 + q) * kBwdSpan + tid] = 0.f;
-        if (c < p.C) {
-            if (D.fmt == CLR_W_COMPLEMENT) {
-                for (int k = 0; k < K; ++k) {
-                    const float go = scale * D.g[(size_t)k * p.C + c] / D.sums[(size_t)k * (p.C + 1) + p.C];
-                    const float gb = scale * D.g[(size_t)(K + k) * p.C + c] / D.sums[(size_t)(K + k) * (p.C + 1) + p.C];
-                    t0 += gb;
-                    T[(1 + k) * kBwdSpan + tid] = go - gb;
+        for (int row = q; row <= QT; row += kThreads / kBwdSpan) {
+            float t = 0.f;
+            if (c < p.C) {
+                if (row == 0) {
+                    if (D.fmt == CLR_W_COMPLEMENT)
+                        for (int k = 0; k < K; ++k)
+                            t += scale * __ldg(D.g + (size_t)(K + k) * p.C + c) / __ldg(D.sums + (size_t)(K + k) * (p.C + 1) + p.C);
+                } else if (row - 1 < QW) {
+                    const int r = row - 1;
+                    const float gr = scale * __ldg(D.g + (size_t)r * p.C + c) / __ldg(D.sums + (size_t)r * (p.C + 1) + p.C);
+                    if (D.fmt == CLR_W_COMPLEMENT) {
+                        const float gb = scale * __ldg(D.g + (size_t)(K + r) * p.C + c) / __ldg(D.sums + (size_t)(K + r) * (p.C + 1) + p.C);
+                        t = gr - gb;
+                    } else {
+                        t = gr;
+                    }
+                } else if (row - 1 < Q) {
+                    t = (D.scale_dev ? __ldg(D.scale_dev) : 1.f) * __ldg(D.xtab + (size_t)(row - 1 - QW) * p.C + c);
                 }
-            } else {
-                for (int r = 0; r < R; ++r)
-                    T[(1 + r) * kBwdSpan + tid] = scale * D.g[(size_t)r * p.C + c] / D.sums[(size_t)r * (p.C + 1) + p.C];
             }
-            for (int k = 0; k < D.Kx; ++k)
-                T[(1 + QW + k) * kBwdSpan + tid] = (D.scale_dev ? __ldg(D.scale_dev) : 1.f) * D.xtab[(size_t)k * p.C + c];
+            T[row * kBwdSpan + j] = t;
         }
-        T[tid] = t0;
     }
     __syncthreads();
     if (!ok) return;
