@@ -249,6 +249,9 @@ typedef struct clr_step_args {
      * pooling launch) so a harness can time it inside a live step; NULL = not recorded */
     void* ev_pool_begin; void* ev_pool_end;
     void* ev_bwd_begin; void* ev_bwd_end;
+    /* optional second stream + two events (clr_event_create) for clr_step_run: the consistency pass and the
+     * backward of the target features run on `aux_stream` concurrently with the discriminative pass */
+    void* aux_stream; void* ev_fork; void* ev_join;
 } clr_step_args;
 
 size_t clr_step_ws_bytes(const clr_step_args* a);
@@ -257,6 +260,12 @@ int clr_step_fwd_b(const clr_step_args* a, clr_stream_t stream);
 int clr_step_fwd_c(const clr_step_args* a, clr_stream_t stream);
 int clr_step_fwd(const clr_step_args* a, clr_stream_t stream);
 int clr_step_bwd(const clr_step_args* a, clr_stream_t stream);
+/* Forward AND backward in one call, for the common case that the step total enters the training loss with a known
+ * (device-side, `gup`, default 1) coefficient.  With `aux_stream` set, independent kernels overlap: after the
+ * alignment finalize, { consistency forward, gradient of the target features } run on the auxiliary stream while
+ * the main stream does the discriminative pass; both join before the last finalize and the source-gradient write.
+ * Results are identical to clr_step_fwd + clr_step_bwd. */
+int clr_step_run(const clr_step_args* a, clr_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -277,3 +277,33 @@ def test_disc_fused_and_two_pass_agree_with_oracle(B, C, H, W, K):
         assert abs(pk[K * (C + 1)] / (B * HW) - loss) < TOL_LOSS * abs(loss), name
         if dl is not None:
             assert np.abs(dl - aux["delta"]).max() < 1e-5 * max(1.0, np.abs(aux["delta"]).max())
+
+
+def test_plan_run_overlapped_equals_serial_and_autograd():
+    """CLRPlan.run() (clr_step_run: fork/join on an auxiliary stream) must give bit-identical results to the serial
+    order, and the same numbers as the autograd path (forward, then .backward())."""
+    from uda_clr_b200 import _lib
+    lib = _lib.load()
+    K, C, H, up, T, B = 2, 48, 64, 4, 8, 4
+    b = synth.make_batch(B=B, C=C, H=H, W=H, K=K, T=T, up=up, seed=77)
+    t = {k: getattr(b, k).to(DEV) for k in ("xs", "ys", "xt", "oT_before", "preds", "oT", "oT_aug")}
+    outs = []
+    for overlap_off in (0, 1):
+        lib.clr_set_tunable(b"overlap_off", overlap_off)
+        step = clr.CLRStep(K=K, retrify=True, use_disc=True, use_cons=True, backprop_aug=True)
+        plan = step.plan(t["xs"], t["ys"], t["xt"], oT_before=t["oT_before"], preds=t["preds"], T=T, oT=t["oT"],
+                         oT_aug=t["oT_aug"], epoch=2.0)
+        for _ in range(3):   # EMA state advances; the third step is compared
+            plan.run()
+        torch.cuda.synchronize()
+        outs.append((plan.losses.clone(), plan.gxs.clone(), plan.gxt.clone(), plan.g_oT_aug.clone()))
+    lib.clr_set_tunable(b"overlap_off", 0)
+    for a_, b_ in zip(outs[0], outs[1]):
+        assert torch.equal(a_, b_)
+    step = clr.CLRStep(K=K, retrify=True, use_disc=True, use_cons=True, backprop_aug=True)
+    for _ in range(3):
+        xs, xt, oTa = (t[k].clone().requires_grad_(True) for k in ("xs", "xt", "oT_aug"))
+        out = step(xs, t["ys"], xt, oT_before=t["oT_before"], preds=t["preds"], T=T, oT=t["oT"], oT_aug=oTa, epoch=2.0)
+        out.total.backward()
+    assert torch.equal(outs[0][0][:5], torch.stack([out.intra, out.inter, out.disc, out.aug, out.total.detach()]))
+    assert torch.equal(outs[0][1], xs.grad) and torch.equal(outs[0][2], xt.grad) and torch.equal(outs[0][3], oTa.grad)

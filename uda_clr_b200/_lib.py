@@ -54,6 +54,7 @@ class StepArgs(Structure):
         ("gxs", _P), ("gxt", _P), ("g_oT_aug", _P),
         ("ws", _P), ("ws_bytes", c_size_t),
         ("ev_pool_begin", _P), ("ev_pool_end", _P), ("ev_bwd_begin", _P), ("ev_bwd_end", _P),
+        ("aux_stream", _P), ("ev_fork", _P), ("ev_join", _P),
     ]
 
 
@@ -103,6 +104,7 @@ _SIGNATURES = {
     "clr_step_fwd_c": (c_int, [POINTER(StepArgs), _P]),
     "clr_step_fwd": (c_int, [POINTER(StepArgs), _P]),
     "clr_step_bwd": (c_int, [POINTER(StepArgs), _P]),
+    "clr_step_run": (c_int, [POINTER(StepArgs), _P]),
 }
 
 

@@ -25,7 +25,7 @@ static unsigned long long g_launches = 0;
 void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
 
 Tunables& tunables() {
-    static Tunables t{0, 0, 0, 0, 0, 0, 0, 0, 0};
+    static Tunables t{0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     return t;
 }
 
@@ -47,6 +47,7 @@ int clr_set_tunable(const char* name, int value) {
     else if (!strcmp(name, "disc_tile")) t.disc_tile = value;
     else if (!strcmp(name, "l2_keep")) t.l2_keep = value;
     else if (!strcmp(name, "pdl_off")) t.pdl_off = value;
+    else if (!strcmp(name, "overlap_off")) t.overlap_off = value;
     else return CLR_ERR_BAD_ARG;
     return CLR_OK;
 }

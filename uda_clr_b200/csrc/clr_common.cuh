@@ -35,6 +35,7 @@ struct Tunables {
     int disc_tile;     // 0 = auto, 64 = force 64-pixel tiles in the fused discriminative kernel
     int l2_keep;       // 1 = evict-last policy on xs in the pooling pass (re-read by the discriminative pass); default off
     int pdl_off;       // 1 = do not use programmatic dependent launch
+    int overlap_off;   // 1 = clr_step_run ignores aux_stream (serial order)
     int mc_precise;    // 1 = ATen-exact sigmoids in clr_mc_stats (slower), 0 = fast intrinsics
 };
 Tunables& tunables();

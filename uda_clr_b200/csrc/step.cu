@@ -98,13 +98,14 @@ int clr_step_fwd_a(const clr_step_args* a, clr_stream_t stream) {
 
 namespace clr {
 struct PendingPack { const float* hinge; int n_hinge, hinge_stride; const double* cons; int n_cons; };
-static int step_fwd_b_impl(const clr_step_args* a, clr_stream_t stream, PendingPack* defer);
+static int step_fwd_b_impl(const clr_step_args* a, clr_stream_t stream, PendingPack* defer, cudaStream_t side);
 }  // namespace clr
 
-int clr_step_fwd_b(const clr_step_args* a, clr_stream_t stream) { return clr::step_fwd_b_impl(a, stream, nullptr); }
+int clr_step_fwd_b(const clr_step_args* a, clr_stream_t stream) { return clr::step_fwd_b_impl(a, stream, nullptr, nullptr); }
 
-// `defer` != NULL: leave the per-CTA partials unsummed and describe them (the caller's finalize kernel sums them)
-static int clr::step_fwd_b_impl(const clr_step_args* a, clr_stream_t stream, clr::PendingPack* defer) {
+// `defer` != NULL: leave the per-CTA partials unsummed and describe them (the caller's finalize kernel sums them).
+// `side` != NULL: fork after the alignment finalize (a->ev_fork) and run the consistency pass on that stream.
+static int clr::step_fwd_b_impl(const clr_step_args* a, clr_stream_t stream, clr::PendingPack* defer, cudaStream_t side) {
     int rc = clr::check_args(a);
     if (rc != CLR_OK) return rc;
     const clr::StepWs w = clr::carve(a);
@@ -117,9 +118,13 @@ static int clr::step_fwd_b_impl(const clr_step_args* a, clr_stream_t stream, clr
                             a->use_disc ? a->disc_vec : nullptr, a->use_disc ? a->disc_beta : nullptr, a->losses, stream);
     if (rc != CLR_OK) return rc;
     int n_hinge = 0, n_cons = 0;
+    if (side) {
+        CLR_RETURN_IF_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(a->ev_fork), st));
+        CLR_RETURN_IF_CUDA(cudaStreamWaitEvent(side, static_cast<cudaEvent_t>(a->ev_fork), 0));
+    }
     if (a->use_cons) {
         rc = clr::cons_fwd_partials(a->oT, a->oT_aug, a->masks, a->B_t, K, a->Hi, a->Wi, a->H, a->W,
-                                    a->cons_threshold, w.cons, &n_cons, st);
+                                    a->cons_threshold, w.cons, &n_cons, side ? side : st);
         if (rc != CLR_OK) return rc;
     }
     int hinge_stride = 1 + K;
@@ -171,7 +176,7 @@ int clr_step_fwd(const clr_step_args* a, clr_stream_t stream) {
     int rc = clr_step_fwd_a(a, stream);
     if (rc != CLR_OK) return rc;
     clr::PendingPack pk{};
-    rc = clr::step_fwd_b_impl(a, stream, &pk);
+    rc = clr::step_fwd_b_impl(a, stream, &pk, nullptr);
     if (rc != CLR_OK) return rc;
     const float ema = a->first_s ? 1.0f : (float)a->decay;
     return clr::disc_finalize_impl(a->packed2, a->P_s, a->K, a->C, a->npx_global, a->w_disc, ema, a->grad_scale,
@@ -180,18 +185,64 @@ int clr_step_fwd(const clr_step_args* a, clr_stream_t stream) {
                                    pk.cons, pk.n_cons, static_cast<cudaStream_t>(stream));
 }
 
+namespace clr {
+static void bwd_doms(const clr_step_args* a, clr_bwd_dom (&d)[2]) {
+    const int R = 2 * a->K, C = a->C, K = a->K;
+    const float* sums_s = a->packed1;
+    const float* sums_t = a->packed1 + (size_t)R * (C + 1);
+    d[0] = clr_bwd_dom{a->ys, a->g_s, sums_s, a->use_disc ? a->disc_coef : nullptr, a->use_disc ? a->xtab : nullptr,
+                       a->gxs, a->gup, a->grad_scale, CLR_W_COMPLEMENT, a->B_s, a->use_disc ? K : 0};
+    d[1] = clr_bwd_dom{target_weights(a), a->g_t, sums_t, nullptr, nullptr, a->gxt, a->gup, a->grad_scale,
+                       target_fmt(a), a->B_t, 0};
+}
+}  // namespace clr
+
+int clr_step_run(const clr_step_args* a, clr_stream_t stream) {
+    int rc = clr::check_args(a);
+    if (rc != CLR_OK) return rc;
+    if (!a->gxs || !a->gxt) return CLR_ERR_BAD_ARG;
+    if (!a->aux_stream || !a->ev_fork || !a->ev_join || clr::tunables().overlap_off) {
+        rc = clr_step_fwd(a, stream);
+        return rc != CLR_OK ? rc : clr_step_bwd(a, stream);
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream), aux = static_cast<cudaStream_t>(a->aux_stream);
+    const int HW = a->H * a->W, C = a->C, K = a->K;
+    rc = clr_step_fwd_a(a, stream);
+    if (rc != CLR_OK) return rc;
+    clr::PendingPack pk{};
+    rc = clr::step_fwd_b_impl(a, stream, &pk, aux);      // align (main) | fork | cons (aux) | disc (main)
+    if (rc != CLR_OK) return rc;
+    clr_bwd_dom d[2];
+    clr::bwd_doms(a, d);
+    rc = clr_pool_bwd_multi(&d[1], 1, C, HW, K, aux);    // d total / d xt needs only g_t: overlaps the discriminative pass
+    if (rc != CLR_OK) return rc;
+    CLR_RETURN_IF_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(a->ev_join), aux));
+    CLR_RETURN_IF_CUDA(cudaStreamWaitEvent(st, static_cast<cudaEvent_t>(a->ev_join), 0));
+    const float ema = a->first_s ? 1.0f : (float)a->decay;
+    rc = clr::disc_finalize_impl(a->packed2, a->P_s, K, C, a->npx_global, a->w_disc, ema, a->grad_scale,
+                                 a->g_s, a->xtab, a->w_intra, a->w_inter, a->w_aug, a->aug_weight,
+                                 a->use_disc, a->use_cons, a->losses, pk.hinge, pk.n_hinge, pk.hinge_stride,
+                                 pk.cons, pk.n_cons, st);
+    if (rc != CLR_OK) return rc;
+    if (a->ev_bwd_begin) cudaEventRecord(static_cast<cudaEvent_t>(a->ev_bwd_begin), st);
+    rc = clr_pool_bwd_multi(&d[0], 1, C, HW, K, stream);
+    if (a->ev_bwd_end) cudaEventRecord(static_cast<cudaEvent_t>(a->ev_bwd_end), st);
+    if (rc != CLR_OK) return rc;
+    if (a->use_cons && a->w_aug != 0.f && a->g_oT_aug) {
+        const float* stats = a->packed2 + (size_t)K * (C + 1);
+        rc = clr_cons_bwd(a->oT, a->oT_aug, a->masks, a->B_t, K, a->Hi, a->Wi, a->H, a->W, a->cons_threshold,
+                          a->aug_weight, stats + 1, a->gup, a->grad_scale * a->w_aug, a->g_oT_aug, stream);
+    }
+    return rc;
+}
+
 int clr_step_bwd(const clr_step_args* a, clr_stream_t stream) {
     int rc = clr::check_args(a);
     if (rc != CLR_OK) return rc;
     if (!a->gxs || !a->gxt) return CLR_ERR_BAD_ARG;
-    const int HW = a->H * a->W, R = 2 * a->K, C = a->C, K = a->K;
-    const float* sums_s = a->packed1;
-    const float* sums_t = a->packed1 + (size_t)R * (C + 1);
+    const int HW = a->H * a->W, C = a->C, K = a->K;
     clr_bwd_dom d[2];
-    d[0] = clr_bwd_dom{a->ys, a->g_s, sums_s, a->use_disc ? a->disc_coef : nullptr, a->use_disc ? a->xtab : nullptr,
-                       a->gxs, a->gup, a->grad_scale, CLR_W_COMPLEMENT, a->B_s, a->use_disc ? K : 0};
-    d[1] = clr_bwd_dom{clr::target_weights(a), a->g_t, sums_t, nullptr, nullptr, a->gxt, a->gup, a->grad_scale,
-                       clr::target_fmt(a), a->B_t, 0};
+    clr::bwd_doms(a, d);
     if (a->ev_bwd_begin) cudaEventRecord(static_cast<cudaEvent_t>(a->ev_bwd_begin), static_cast<cudaStream_t>(stream));
     rc = clr_pool_bwd_multi(d, 2, C, HW, K, stream);
     if (a->ev_bwd_end) cudaEventRecord(static_cast<cudaEvent_t>(a->ev_bwd_end), static_cast<cudaStream_t>(stream));

@@ -285,7 +285,11 @@ class CLRPlan:
         self.device = dev
         self._lib = _lib.load()
         self._ref = ctypes.byref(a)
-        self.launches_per_run: Optional[int] = None
+        # auxiliary stream + fork/join events: the consistency pass and the target-gradient write overlap the
+        # discriminative pass (clr_step_run); harmless when there is nothing to overlap
+        self._aux = torch.cuda.Stream(device=dev)
+        self._ev = (_lib.Event(), _lib.Event())
+        a.aux_stream, a.ev_fork, a.ev_join = self._aux.cuda_stream, self._ev[0].handle, self._ev[1].handle
 
     def set_events(self, pool_begin=None, pool_end=None, bwd_begin=None, bwd_end=None) -> None:
         """Have the library record these :class:`uda_clr_b200._lib.Event` objects around the pooling / backward
@@ -306,9 +310,9 @@ class CLRPlan:
             check(self._lib.clr_step_fwd_b(self._ref, st), "clr_step_fwd_b")
             _dist.all_reduce_sums(self.holder["buf"].packed2)
             check(self._lib.clr_step_fwd_c(self._ref, st), "clr_step_fwd_c")
+            check(self._lib.clr_step_bwd(self._ref, st), "clr_step_bwd")
         else:
-            check(self._lib.clr_step_fwd(self._ref, st), "clr_step_fwd")
-        check(self._lib.clr_step_bwd(self._ref, st), "clr_step_bwd")
+            check(self._lib.clr_step_run(self._ref, st), "clr_step_run")
         self.step.first_s = self.step.first_t = False
 
     def outputs(self) -> CLRStepOutput:
