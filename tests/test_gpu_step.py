@@ -288,16 +288,15 @@ def test_plan_run_overlapped_equals_serial_and_autograd():
     b = synth.make_batch(B=B, C=C, H=H, W=H, K=K, T=T, up=up, seed=77)
     t = {k: getattr(b, k).to(DEV) for k in ("xs", "ys", "xt", "oT_before", "preds", "oT", "oT_aug")}
     outs = []
-    for overlap_off in (0, 1):
-        lib.clr_set_tunable(b"overlap_off", overlap_off)
+    for overlap in (True, False):
         step = clr.CLRStep(K=K, retrify=True, use_disc=True, use_cons=True, backprop_aug=True)
         plan = step.plan(t["xs"], t["ys"], t["xt"], oT_before=t["oT_before"], preds=t["preds"], T=T, oT=t["oT"],
                          oT_aug=t["oT_aug"], epoch=2.0)
+        plan.enable_overlap(overlap)
         for _ in range(3):   # EMA state advances; the third step is compared
             plan.run()
         torch.cuda.synchronize()
         outs.append((plan.losses.clone(), plan.gxs.clone(), plan.gxt.clone(), plan.g_oT_aug.clone()))
-    lib.clr_set_tunable(b"overlap_off", 0)
     for a_, b_ in zip(outs[0], outs[1]):
         assert torch.equal(a_, b_)
     step = clr.CLRStep(K=K, retrify=True, use_disc=True, use_cons=True, backprop_aug=True)

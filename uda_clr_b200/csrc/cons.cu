@@ -32,23 +32,39 @@ __device__ __forceinline__ int nearest_src(int dst, float scale, int n_in) {
     return s < n_in - 1 ? s : n_in - 1;
 }
 
-// Exact label decision sigmoid(z) > thr at the cost of the fast sigmoid: the fast value (error < 1e-6) decides
-// unless it lies within 1e-5 of the threshold, in which case ATen's exact expression is evaluated.
-__device__ __forceinline__ bool label_above(float z, float thr) {
-    const float qf = sigmoid_fast(z);
-    if (fabsf(qf - thr) > 1e-5f) return qf > thr;
-    return sigmoid_aten(z) > thr;
+// Exact label decision sigmoid(z) > thr for the price of one compare: sigmoid is monotone with slope thr(1-thr) at
+// the threshold, so |z - logit(thr)| > guard implies |sigmoid(z) - thr| >> the fp32 evaluation error and the sign
+// of (z - logit(thr)) IS the decision; inside the guard band ATen's exact expression is evaluated.
+struct LabelRule { float thr, zthr, guard; };
+__device__ __forceinline__ bool label_above(float z, const LabelRule& r) {
+    const float d = z - r.zthr;
+    if (fabsf(d) > r.guard) return d > 0.f;
+    return sigmoid_aten(z) > r.thr;
 }
 
-// One element of the masked BCE: returns m*l; `y` decided exactly, the log terms through fast intrinsics
-// (ATen: (y-1)*max(log1p(-q),-100) - y*max(log(q),-100) with q = sigmoid(z) rounded to fp32).
-__device__ __forceinline__ void cons_elem(float zt, float za, float m, float thr, float& ml, float& q_out, float& y_out) {
-    const float y = label_above(zt, thr) ? 1.0f : 0.0f;
+// One element of the masked BCE: returns m*l.  y is 0/1, so only one of ATen's two log terms is non-zero:
+// l = -max(log(y ? q : 1-q), -100) with q = sigmoid(z) (fast intrinsics; ATen: log(q) / log1p(-q)).
+__device__ __forceinline__ void cons_elem(float zt, float za, float m, const LabelRule& r, float& ml, float& q_out, float& y_out) {
+    const bool yb = label_above(zt, r);
     const float q = sigmoid_fast(za);
-    const float lq = fmaxf(0.6931471805599453f * lg2_approx(q), -100.0f);
-    const float l1q = fmaxf(0.6931471805599453f * lg2_approx(1.0f - q), -100.0f);
-    ml = m * ((y - 1.0f) * l1q - y * lq);
-    q_out = q; y_out = y;
+    const float t = yb ? q : 1.0f - q;
+    ml = -m * fmaxf(0.6931471805599453f * lg2_approx(t), -100.0f);
+    q_out = q; y_out = yb ? 1.0f : 0.0f;
+}
+
+static LabelRule make_rule(float thr) {
+    LabelRule r;
+    r.thr = thr;
+    const double t = (double)thr;
+    if (t > 0.0 && t < 1.0) {
+        r.zthr = (float)log(t / (1.0 - t));
+        const double g = 4e-6 / (t * (1.0 - t));
+        r.guard = (float)(g > 1e-4 ? g : 1e-4);
+    } else {
+        r.zthr = 0.f;
+        r.guard = 3.0e38f;   // degenerate threshold: always take the exact path
+    }
+    return r;
 }
 
 constexpr int kConsTX = 64, kConsTY = 4;   // block = 64 vector columns x 4 rows
@@ -57,7 +73,7 @@ constexpr int kConsTX = 64, kConsTY = 4;   // block = 64 vector columns x 4 rows
 // vector columns tx, tx+64, .. of rows ty, ty+4, .. -- no divisions, up to 4 independent 128-bit load pairs in flight.
 template <int VEC, bool BWD>
 __global__ void __launch_bounds__(kConsTX * kConsTY) cons_kernel(const float* __restrict__ oT, const float* __restrict__ oT_aug,
-                                                                 const float* __restrict__ masks, ConsGeom g, float thr,
+                                                                 const float* __restrict__ masks, ConsGeom g, LabelRule thr,
                                                                  double* __restrict__ partial,
                                                                  const float* __restrict__ stats, const float* __restrict__ gscale_dev,
                                                                  float gscale, float* __restrict__ grad) {
@@ -167,8 +183,8 @@ int cons_fwd_partials(const float* oT, const float* oT_aug, const float* masks, 
     const ConsGeom g = make_geom(B, K, Hi, Wi, H, W, grid);
     if ((long long)grid.x * grid.y > kConsMaxBlocks || grid.y > 65535) return CLR_ERR_UNSUPPORTED;
     const bool vec4 = (Wi % 4 == 0) && aligned16(oT) && aligned16(oT_aug);
-    if (vec4) launch_k(cons_kernel<4, false>, grid, dim3(kConsTX, kConsTY), 0, st, oT, oT_aug, masks, g, threshold, partial, nullptr, nullptr, 0.f, nullptr);
-    else launch_k(cons_kernel<1, false>, grid, dim3(kConsTX, kConsTY), 0, st, oT, oT_aug, masks, g, threshold, partial, nullptr, nullptr, 0.f, nullptr);
+    if (vec4) launch_k(cons_kernel<4, false>, grid, dim3(kConsTX, kConsTY), 0, st, oT, oT_aug, masks, g, make_rule(threshold), partial, nullptr, nullptr, 0.f, nullptr);
+    else launch_k(cons_kernel<1, false>, grid, dim3(kConsTX, kConsTY), 0, st, oT, oT_aug, masks, g, make_rule(threshold), partial, nullptr, nullptr, 0.f, nullptr);
     *nblocks = (int)(grid.x * grid.y);
     return launch_status();
 }
@@ -201,8 +217,8 @@ int clr_cons_bwd(const float* oT, const float* oT_aug, const float* masks, int B
     if (grid.y > 65535) return CLR_ERR_UNSUPPORTED;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool vec4 = (Wi % 4 == 0) && clr::aligned16(oT) && clr::aligned16(oT_aug) && clr::aligned16(grad_oT_aug);
-    if (vec4) clr::launch_k(clr::cons_kernel<4, true>, grid, dim3(clr::kConsTX, clr::kConsTY), 0, st, oT, oT_aug, masks, g, threshold, nullptr, stats, gscale_dev, gscale * aug_weight, grad_oT_aug);
-    else clr::launch_k(clr::cons_kernel<1, true>, grid, dim3(clr::kConsTX, clr::kConsTY), 0, st, oT, oT_aug, masks, g, threshold, nullptr, stats, gscale_dev, gscale * aug_weight, grad_oT_aug);
+    if (vec4) clr::launch_k(clr::cons_kernel<4, true>, grid, dim3(clr::kConsTX, clr::kConsTY), 0, st, oT, oT_aug, masks, g, clr::make_rule(threshold), nullptr, stats, gscale_dev, gscale * aug_weight, grad_oT_aug);
+    else clr::launch_k(clr::cons_kernel<1, true>, grid, dim3(clr::kConsTX, clr::kConsTY), 0, st, oT, oT_aug, masks, g, clr::make_rule(threshold), nullptr, stats, gscale_dev, gscale * aug_weight, grad_oT_aug);
     return clr::launch_status();
 }
 

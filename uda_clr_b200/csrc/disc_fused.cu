@@ -73,25 +73,27 @@ __global__ void __launch_bounds__(kThreads, (TP == 32) ? 2 : 1) disc_fused_kerne
     int begin, end;
     partition(p.total, gridDim.x, blockIdx.x, begin, end);
 
-    // Asynchronous tile fetch by all 256 threads: 16-byte cp.async (LDGSTS) chunks, a warp covers
-    // 32/NG channel rows per instruction; columns past a ragged plane end are zero-filled.
-    auto issue = [&](int it, int stage) {
-        if (it < end) {
-            const int b = it / p.tilesPerSample, tile = it - b * p.tilesPerSample;
+    // Asynchronous tile fetch by all 256 threads: 16-byte cp.async (LDGSTS) chunks; thread (q = tid % NG chunk
+    // column, r0 = tid / NG row) copies rows r0, r0 + NS, ..: pointer increments only.  Columns past a ragged plane
+    // end are zero-filled.
+    const int fq = tid % NG, fr0 = tid / NG;
+    auto issue = [&](int b, int tile, int stage) {
+        if (b < p.B) {
             const int px0 = tile * TP;
             const int nchunk = ((p.HW - px0) < TP ? (p.HW - px0) : TP) / 4;
-            const float* src = p.xs + (size_t)b * p.C * p.HW + px0;
-            float* dst = tiles + (size_t)stage * stage_floats;
-            const int total = p.C * NG;
-            for (int i = tid; i < total; i += kThreads) {
-                const int c = i / NG, q = i - c * NG;
-                float* d = dst + (size_t)c * RS + 4 * q;
-                if (q < nchunk) cp_async16(d, src + (size_t)c * p.HW + 4 * q);
-                else *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float* src = p.xs + ((size_t)b * p.C + fr0) * p.HW + px0 + 4 * fq;
+            float* dst = tiles + (size_t)stage * stage_floats + (size_t)fr0 * RS + 4 * fq;
+            const size_t sstep = (size_t)NS * p.HW;
+            if (fq < nchunk) {
+                for (int c = fr0; c < p.C; c += NS, src += sstep, dst += NS * RS) cp_async16(dst, src);
+            } else {
+                for (int c = fr0; c < p.C; c += NS, dst += NS * RS) *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
         cp_async_commit();
     };
+    // (b, tile) of an item index, advanced incrementally afterwards
+    auto advance = [&](int& b, int& tile) { if (++tile == p.tilesPerSample) { tile = 0; ++b; } };
 
     const int g = tid % NG, s = tid / NG;
     float A[kDiscMaxCPT][K];
@@ -104,11 +106,16 @@ __global__ void __launch_bounds__(kThreads, (TP == 32) ? 2 : 1) disc_fused_kerne
 #pragma unroll
     for (int i = 0; i < NE; ++i) ncf[i] = 0.f;
 
+    int b = begin / p.tilesPerSample, tile = begin - b * p.tilesPerSample;   // current item
+    int fb = b, ftile = tile;                                               // next item to fetch
+    int fetched = begin;
 #pragma unroll
-    for (int j = 0; j < STAGES - 1; ++j) issue(begin + j, j);
+    for (int j = 0; j < STAGES - 1; ++j) {
+        issue(fetched < end ? fb : p.B, ftile, j);
+        advance(fb, ftile); ++fetched;
+    }
     int stage = 0;
-    for (int it = begin; it < end; ++it) {
-        const int b = it / p.tilesPerSample, tile = it - b * p.tilesPerSample;
+    for (int it = begin; it < end; ++it, advance(b, tile)) {
         const int px0 = tile * TP;
         const int npx = (p.HW - px0) < TP ? (p.HW - px0) : TP;
         // labels of this thread's epilogue entries: issued now, consumed after phase 1
@@ -124,7 +131,8 @@ __global__ void __launch_bounds__(kThreads, (TP == 32) ? 2 : 1) disc_fused_kerne
         {
             int nst = stage + STAGES - 1;
             if (nst >= STAGES) nst -= STAGES;
-            issue(it + STAGES - 1, nst);  // refill the stage the previous tile occupied
+            issue(fetched < end ? fb : p.B, ftile, nst);  // refill the stage the previous tile occupied
+            advance(fb, ftile); ++fetched;
         }
         const float* xt = tiles + (size_t)stage * stage_floats;
         // ---- phase 1: K dot products over the channel axis ----------------------------------------

@@ -113,8 +113,18 @@ __global__ void __launch_bounds__(256) disc_finalize_kernel(
         double v[3] = {0.0, 0.0, 0.0};
         if (ps.hinge)
             for (int i = threadIdx.x; i < ps.n_hinge; i += blockDim.x) v[0] += (double)ps.hinge[(size_t)i * ps.hinge_stride];
-        if (ps.cons)
-            for (int i = threadIdx.x; i < ps.n_cons; i += blockDim.x) { v[1] += ps.cons[2 * i]; v[2] += ps.cons[2 * i + 1]; }
+        if (ps.cons) {
+            const double2* c2 = reinterpret_cast<const double2*>(ps.cons);
+            int i = threadIdx.x;
+            for (; i + 3 * (int)blockDim.x < ps.n_cons; i += 4 * blockDim.x) {
+                double2 t[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) t[u] = c2[i + u * blockDim.x];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { v[1] += t[u].x; v[2] += t[u].y; }
+            }
+            for (; i < ps.n_cons; i += blockDim.x) { const double2 t = c2[i]; v[1] += t.x; v[2] += t.y; }
+        }
         block_sum_n<3>(v, shp);
         if (threadIdx.x == 0) {
             tail[0] = tail_s[0] = (float)v[0]; tail[1] = tail_s[1] = (float)v[1]; tail[2] = tail_s[2] = (float)v[2];
@@ -142,6 +152,7 @@ __global__ void __launch_bounds__(256) disc_finalize_kernel(
         losses[2] = disc;
         losses[3] = aug;
         losses[4] = w_intra * losses[0] + w_inter * losses[1] + w_disc * disc + w_aug * aug;
+        losses[5] = 0.f; losses[6] = 0.f; losses[7] = 0.f;
     }
 }
 

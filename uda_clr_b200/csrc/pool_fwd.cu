@@ -346,8 +346,18 @@ __global__ void __launch_bounds__(256) pool_reduce_kernel(const PoolParams p, in
     const int col = blockIdx.x * 32 + threadIdx.x;
     __shared__ double sh[8][33];
     double s = 0.0;
-    if (col < n)
-        for (int sl = threadIdx.y; sl < D.slots; sl += 8) s += (double)D.partial[(size_t)sl * n + col];
+    if (col < n) {
+        // 8 independent loads per round (the slots of one column are n floats apart)
+        int sl = threadIdx.y;
+        for (; sl + 56 < D.slots; sl += 64) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = D.partial[(size_t)(sl + 8 * u) * n + col];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += (double)v[u];
+        }
+        for (; sl < D.slots; sl += 8) s += (double)D.partial[(size_t)sl * n + col];
+    }
     sh[threadIdx.y][threadIdx.x] = s;
     __syncthreads();
     if (threadIdx.y == 0 && col < n) {
