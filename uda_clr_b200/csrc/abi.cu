@@ -25,7 +25,7 @@ static unsigned long long g_launches = 0;
 void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
 
 Tunables& tunables() {
-    static Tunables t{0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    static Tunables t{};
     return t;
 }
 
@@ -45,6 +45,7 @@ int clr_set_tunable(const char* name, int value) {
     else if (!strcmp(name, "mc_precise")) t.mc_precise = value;
     else if (!strcmp(name, "disc_impl")) t.disc_impl = value;
     else if (!strcmp(name, "disc_tile")) t.disc_tile = value;
+    else if (!strcmp(name, "disc_threads")) t.disc_threads = value;
     else if (!strcmp(name, "l2_keep")) t.l2_keep = value;
     else if (!strcmp(name, "pdl_off")) t.pdl_off = value;
     else if (!strcmp(name, "overlap_off")) t.overlap_off = value;

@@ -32,6 +32,7 @@ struct Tunables {
     int dots_impl;     // reserved
     int disc_impl;     // 0 = auto (one-read fused discriminative kernel), 1 = force the two-pass form
     int bwd_impl;      // reserved
+    int disc_threads;  // 0 = auto (512-thread CTAs when K <= 2), 256 = force 256
     int disc_tile;     // 0 = auto, 64 = force 64-pixel tiles in the fused discriminative kernel
     int l2_keep;       // 1 = evict-last policy on xs in the pooling pass (re-read by the discriminative pass); default off
     int pdl_off;       // 1 = do not use programmatic dependent launch

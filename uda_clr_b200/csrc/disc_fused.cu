@@ -52,26 +52,28 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int K, int TP, int STAGES>
-__global__ void __launch_bounds__(kThreads, (TP == 32) ? 2 : 1) disc_fused_kernel(const DiscParams p) {
+template <int K, int TP, int STAGES, int NT>
+__global__ void __launch_bounds__(NT, (TP == 32) ? 2 : 1) disc_fused_kernel(const DiscParams p) {
     pdl_wait();
     constexpr int RS = TP + kDiscPad;            // row stride (floats)
     constexpr int NG = TP / 4;                   // pixel quads (16-byte chunks) per row
-    constexpr int NS = kThreads / NG;            // channel slices in phase 1
-    constexpr int NE = (K * TP + kThreads - 1) / kThreads;   // epilogue iterations per thread (<= 2)
+    constexpr int NS = NT / NG;                  // channel slices in phase 1
+    constexpr int NW = NT / 32;                  // warps
+    constexpr int PS = NT / kDiscCols;           // pixel splits in phase 2
+    constexpr int NE = (K * TP + NT - 1) / NT;   // epilogue iterations per thread
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const size_t stage_floats = (size_t)p.C * RS;
     float* tiles = reinterpret_cast<float*>(smem_raw);                       // [STAGES][C][RS]
-    float* red = tiles + (size_t)STAGES * stage_floats;                      // [kWarps][K][TP]
-    float* cfs = red + (size_t)kWarps * K * TP;                              // [K][TP]
-    float* wred = cfs + (size_t)K * TP;                                      // [1 + NE][kWarps]
-    float* Vs = wred + (1 + NE) * kWarps;                                    // [K][C]
+    float* red = tiles + (size_t)STAGES * stage_floats;                      // [NW][K][TP]
+    float* cfs = red + (size_t)NW * K * TP;                              // [K][TP]
+    float* wred = cfs + (size_t)K * TP;                                      // [1 + NE][NW]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    for (int i = tid; i < K * p.C; i += kThreads) { const int k = i / p.C, c = i - k * p.C; Vs[c * K + k] = p.V[i]; }   // [C][K]
 
-    int begin, end;
-    partition(p.total, gridDim.x, blockIdx.x, begin, end);
+    // Tiles are dealt round-robin (CTA k: tiles k, k+grid, ..): at any moment the resident CTAs fetch ADJACENT
+    // 128-byte segments of the same channel rows, which keeps DRAM pages open across CTAs -- a contiguous range
+    // per CTA would have every CTA touching its own page of every row.
+    const int begin = blockIdx.x, end = p.total, step = gridDim.x;
 
     // Asynchronous tile fetch by all 256 threads: 16-byte cp.async (LDGSTS) chunks; thread (q = tid % NG chunk
     // column, r0 = tid / NG row) copies rows r0, r0 + NS, ..: pointer increments only.  Columns past a ragged plane
@@ -92,8 +94,11 @@ __global__ void __launch_bounds__(kThreads, (TP == 32) ? 2 : 1) disc_fused_kerne
         }
         cp_async_commit();
     };
-    // (b, tile) of an item index, advanced incrementally afterwards
-    auto advance = [&](int& b, int& tile) { if (++tile == p.tilesPerSample) { tile = 0; ++b; } };
+    // (b, tile) of the item `step` further on
+    auto advance = [&](int& b, int& tile) {
+        tile += step;
+        while (tile >= p.tilesPerSample) { tile -= p.tilesPerSample; ++b; }
+    };
 
     const int g = tid % NG, s = tid / NG;
     float A[kDiscMaxCPT][K];
@@ -112,17 +117,17 @@ __global__ void __launch_bounds__(kThreads, (TP == 32) ? 2 : 1) disc_fused_kerne
 #pragma unroll
     for (int j = 0; j < STAGES - 1; ++j) {
         issue(fetched < end ? fb : p.B, ftile, j);
-        advance(fb, ftile); ++fetched;
+        advance(fb, ftile); fetched += step;
     }
     int stage = 0;
-    for (int it = begin; it < end; ++it, advance(b, tile)) {
+    for (int it = begin; it < end; it += step, advance(b, tile)) {
         const int px0 = tile * TP;
         const int npx = (p.HW - px0) < TP ? (p.HW - px0) : TP;
         // labels of this thread's epilogue entries: issued now, consumed after phase 1
         float yv[NE];
 #pragma unroll
         for (int ei = 0; ei < NE; ++ei) {
-            const int e = tid + ei * kThreads;
+            const int e = tid + ei * NT;
             const int k = e / TP, j = e - k * TP;
             yv[ei] = (e < K * TP && j < npx) ? __ldg(p.ys + ((size_t)b * K + k) * p.HW + px0 + j) : 0.f;
         }
@@ -132,7 +137,7 @@ __global__ void __launch_bounds__(kThreads, (TP == 32) ? 2 : 1) disc_fused_kerne
             int nst = stage + STAGES - 1;
             if (nst >= STAGES) nst -= STAGES;
             issue(fetched < end ? fb : p.B, ftile, nst);  // refill the stage the previous tile occupied
-            advance(fb, ftile); ++fetched;
+            advance(fb, ftile); fetched += step;
         }
         const float* xt = tiles + (size_t)stage * stage_floats;
         // ---- phase 1: K dot products over the channel axis ----------------------------------------
@@ -144,17 +149,9 @@ __global__ void __launch_bounds__(kThreads, (TP == 32) ? 2 : 1) disc_fused_kerne
 #pragma unroll 4
         for (int c = s; c < p.C; c += NS) {
             const float4 x = *reinterpret_cast<const float4*>(xt + (size_t)c * RS + 4 * g);
-            float vv[K];
-            if constexpr (K == 2) {
-                const float2 t2 = *reinterpret_cast<const float2*>(Vs + 2 * c);
-                vv[0] = t2.x; vv[1] = t2.y;
-            } else if constexpr (K == 4) {
-                const float4 t4 = *reinterpret_cast<const float4*>(Vs + 4 * c);
-                vv[0] = t4.x; vv[1] = t4.y; vv[2] = t4.z; vv[3] = t4.w;
-            } else {
+            float vv[K];   // D_k[c]: 4 KB table, read through L1 (saves the shared-memory copy: a third stage fits)
 #pragma unroll
-                for (int k = 0; k < K; ++k) vv[k] = Vs[c * K + k];
-            }
+            for (int k = 0; k < K; ++k) vv[k] = __ldg(p.V + (size_t)k * p.C + c);
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 const float vk = vv[k];
@@ -182,12 +179,12 @@ __global__ void __launch_bounds__(kThreads, (TP == 32) ? 2 : 1) disc_fused_kerne
         // ---- epilogue: thread e -> (k, pixel j) ------------------------------------------------------
 #pragma unroll
         for (int ei = 0; ei < NE; ++ei) {
-            const int e = tid + ei * kThreads;
+            const int e = tid + ei * NT;
             if (e >= K * TP) break;
             const int k = e / TP, j = e - k * TP;
             float dot = 0.f;
 #pragma unroll
-            for (int q = 0; q < kWarps; ++q) dot += red[((size_t)q * K + k) * TP + j];
+            for (int q = 0; q < NW; ++q) dot += red[((size_t)q * K + k) * TP + j];
             float cf = 0.f;
             if (j < npx) {
                 const size_t o = ((size_t)b * K + k) * p.HW + px0 + j;
@@ -207,7 +204,8 @@ __global__ void __launch_bounds__(kThreads, (TP == 32) ? 2 : 1) disc_fused_kerne
         //      are shared by all of the thread's channels (12 LDS.128 per 64 FMA at C = 256, K = 2)
         {
             const int cp = tid % kDiscCols, h = tid / kDiscCols;
-            constexpr int JQ = NG / 4;             // pixel quads per quarter
+            constexpr int JQ = NG / PS;            // pixel quads per split
+            static_assert(JQ >= 1, "tile too narrow for this CTA size");
             float4 cf[JQ][K];
 #pragma unroll
             for (int jq = 0; jq < JQ; ++jq)
@@ -240,7 +238,7 @@ __global__ void __launch_bounds__(kThreads, (TP == 32) ? 2 : 1) disc_fused_kerne
     // ---- CTA partials: the 4 pixel quarters of every (k, c) are combined through shared memory (tiles are free now)
     __syncthreads();
     {
-        float* comb = tiles;                     // [4][K][C]
+        float* comb = tiles;                     // [PS][K][C]
         const int cp = tid % kDiscCols, h = tid / kDiscCols;
 #pragma unroll
         for (int i = 0; i < kDiscMaxCPT; ++i) {
@@ -253,48 +251,53 @@ __global__ void __launch_bounds__(kThreads, (TP == 32) ? 2 : 1) disc_fused_kerne
     }
     __syncthreads();
     float* out = p.partial + (size_t)blockIdx.x * K * (p.C + 1);
-    for (int i = tid; i < K * p.C; i += kThreads) {
+    for (int i = tid; i < K * p.C; i += NT) {
         const int k = i / p.C, c = i - k * p.C;
         const float* comb = tiles;
-        out[(size_t)k * (p.C + 1) + c] = (comb[i] + comb[(size_t)K * p.C + i]) + (comb[(size_t)2 * K * p.C + i] + comb[(size_t)3 * K * p.C + i]);
+        float t = 0.f;
+#pragma unroll
+        for (int h = 0; h < PS; ++h) t += comb[(size_t)h * K * p.C + i];
+        out[(size_t)k * (p.C + 1) + c] = t;
     }
     const float hs = warp_sum(hinge_sum);
     if (lane == 0) wred[warp] = hs;
 #pragma unroll
     for (int ei = 0; ei < NE; ++ei) {
         const float t = warp_sum(ncf[ei]);
-        if (lane == 0) wred[(1 + ei) * kWarps + warp] = t;
+        if (lane == 0) wred[(1 + ei) * NW + warp] = t;
     }
     __syncthreads();
     if (tid == 0) {
         float t = 0.f;
-        for (int w = 0; w < kWarps; ++w) t += wred[w];
+        for (int w = 0; w < NW; ++w) t += wred[w];
         p.hinge[blockIdx.x] = t;
     }
     if (tid < K) {
         // entry e = ei*256 + warp*32 + lane belongs to class e / TP; TP is a multiple of 32, so a warp is one class
         float t = 0.f;
         for (int ei = 0; ei < NE; ++ei)
-            for (int w = 0; w < kWarps; ++w)
-                if ((ei * kThreads + w * 32) / TP == tid) t += wred[(1 + ei) * kWarps + w];
+            for (int w = 0; w < NW; ++w)
+                if ((ei * NT + w * 32) / TP == tid) t += wred[(1 + ei) * NW + w];
         out[(size_t)tid * (p.C + 1) + p.C] = t;
     }
 }
 
-template <int K, int TP>
+template <int K, int TP, int NT>
 static size_t disc_smem(int C, int stages) {
-    constexpr int RS = TP + kDiscPad, NE = (K * TP + kThreads - 1) / kThreads;
-    const size_t fl = (size_t)stages * C * RS + (size_t)kWarps * K * TP + (size_t)K * TP + (1 + NE) * kWarps + (size_t)K * C;
+    constexpr int RS = TP + kDiscPad, NW = NT / 32, NE = (K * TP + NT - 1) / NT;
+    size_t fl = (size_t)stages * C * RS + (size_t)NW * K * TP + (size_t)K * TP + (1 + NE) * NW;
+    const size_t comb = (size_t)(NT / kDiscCols) * K * C;     // end-of-kernel combine buffer aliases the tile ring
+    if (comb > (size_t)stages * C * RS) fl += comb - (size_t)stages * C * RS;
     return fl * sizeof(float);
 }
 
-template <int K, int TP, int STAGES>
+template <int K, int TP, int STAGES, int NT>
 static int launch_disc_s(DiscParams& p, int* nparts, cudaStream_t st) {
-    const size_t smem = disc_smem<K, TP>(p.C, STAGES);
-    auto kern = disc_fused_kernel<K, TP, STAGES>;
+    const size_t smem = disc_smem<K, TP, NT>(p.C, STAGES);
+    auto kern = disc_fused_kernel<K, TP, STAGES, NT>;
     CLR_RETURN_IF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    CLR_RETURN_IF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem));
+    CLR_RETURN_IF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem));
     if (occ < 1) return CLR_ERR_UNSUPPORTED;
     p.tilesPerSample = (p.HW + TP - 1) / TP;
     const long long total = (long long)p.B * p.tilesPerSample;
@@ -304,7 +307,7 @@ static int launch_disc_s(DiscParams& p, int* nparts, cudaStream_t st) {
     if (grid > p.total) grid = p.total;
     if (grid > *nparts) grid = *nparts;
     *nparts = grid;
-    clr::launch_k(kern, grid, kThreads, smem, st, p);
+    clr::launch_k(kern, grid, NT, smem, st, p);
     return launch_status();
 }
 
@@ -313,9 +316,15 @@ static int launch_disc(DiscParams& p, int* nparts, cudaStream_t st) {
     const size_t budget = (size_t)device_facts().max_smem_optin;
     // TP = 32 aims at two resident CTAs per SM (half the budget each)
     const size_t per_cta = (TP == 32) ? (budget - 2048) / 2 : budget;
-    if (disc_smem<K, TP>(p.C, 4) <= per_cta) return launch_disc_s<K, TP, 4>(p, nparts, st);
-    if (disc_smem<K, TP>(p.C, 3) <= per_cta) return launch_disc_s<K, TP, 3>(p, nparts, st);
-    if (disc_smem<K, TP>(p.C, 2) <= budget) return launch_disc_s<K, TP, 2>(p, nparts, st);
+    // 512-thread CTAs (32 warps per SM at two CTAs) when the accumulators fit the 64-register budget
+    constexpr bool wide = (K <= 2);
+    if (tunables().disc_threads != 256 && wide) {
+        if (disc_smem<K, TP, 512>(p.C, 3) <= per_cta) return launch_disc_s<K, TP, 3, 512>(p, nparts, st);
+        if (disc_smem<K, TP, 512>(p.C, 2) <= budget) return launch_disc_s<K, TP, 2, 512>(p, nparts, st);
+    }
+    if (disc_smem<K, TP, 256>(p.C, 4) <= per_cta) return launch_disc_s<K, TP, 4, 256>(p, nparts, st);
+    if (disc_smem<K, TP, 256>(p.C, 3) <= per_cta) return launch_disc_s<K, TP, 3, 256>(p, nparts, st);
+    if (disc_smem<K, TP, 256>(p.C, 2) <= budget) return launch_disc_s<K, TP, 2, 256>(p, nparts, st);
     return CLR_ERR_UNSUPPORTED;
 }
 
