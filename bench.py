@@ -229,6 +229,7 @@ def main():
     dist_on = world > 1
     if dist_on:
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
         clr.dist.enable()
     lib = _lib.load()

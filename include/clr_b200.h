@@ -77,6 +77,15 @@ int clr_pool_fwd(const float* feat /*[B,C,HW]*/, const float* w, int fmt, int B,
 size_t clr_pool_rows_ws_bytes(int B, int C, int HW, int R);
 int clr_pool_rows_fwd(const float* feat, const float* rows, int B, int C, int HW, int R,
                       void* ws, size_t ws_bytes, float* sums /*[R][C+1] out*/, clr_stream_t stream);
+/* bmm-style per-sample pooling (Trainer_prototype.py:364-383, cal_prototype.py:156-175):
+ *   proto[r][c] = mean_b( sum_p rows[b,r,p] x[b,c,p] / (sum_p rows[b,r,p] + 1) )
+ * = clr_pool_rows_fwd_ps (per-sample packed sums [B][R][C+1]; ws >= R*(C+1)*4 + clr_pool_rows_ws_bytes)
+ *   + clr_bmm_finalize (n_add = 1).  clr_pool_bwd_ps is the adjoint w.r.t. the features. */
+int clr_pool_rows_fwd_ps(const float* feat, const float* rows, int B, int C, int HW, int R,
+                         void* ws, size_t ws_bytes, float* sums_b /*[B][R][C+1] out*/, clr_stream_t stream);
+int clr_bmm_finalize(const float* sums_b, int B, int R, int C, float n_add, float* out /*[R][C]*/, clr_stream_t stream);
+int clr_pool_bwd_ps(const float* rows, int B, int C, int HW, int R, const float* g /*[R][C]*/, const float* sums_b,
+                    float n_add, float scale, float* grad /*[B,C,HW] out*/, clr_stream_t stream);
 /* Two domains (source, target) in ONE launch: the fused step's forward. sums0/sums1 as above. */
 int clr_pool_fwd2(const float* feat0, const float* w0, int fmt0, int B0,
                   const float* feat1, const float* w1, int fmt1, int B1,

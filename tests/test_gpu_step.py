@@ -123,6 +123,45 @@ def test_distance_cosine_fixture_and_oracle():
     assert relerr(cw.cpu().numpy(), O.cosine_weight(x.numpy(), p.numpy())) < 1e-5
 
 
+# ------------------------------------------------------------------------------------------------ A6 / A7
+@pytest.mark.parametrize("B,C,H,W,R,hard", [(4, 305, 32, 32, 2, True), (3, 304, 24, 40, 1, False), (2, 37, 6, 7, 3, False),
+                                             (8, 256, 128, 128, 2, True)])
+def test_bmm_prototypes_vs_oracle_and_port(B, C, H, W, R, hard):
+    """A6: per-sample normalised pooling ``mean_b(m.X / (sum m + 1))`` (Trainer_prototype.py:364-383), forward and
+    the adjoint w.r.t. the features, against the fp64 oracle and the bmm port under autograd on the same GPU."""
+    g = torch.Generator().manual_seed(11 + C)
+    x = torch.randn(B, C, H, W, generator=g)
+    m = torch.rand(B, R, H, W, generator=g)
+    if hard:
+        m = (m > 0.6).float()
+        m[0, 0] = 0.0                      # an empty mask: the +1 keeps the prototype finite (0, not NaN)
+    seeds = torch.randn(R, C, generator=g)
+    xg = x.to(DEV).requires_grad_(True)
+    out = clr.bmm_prototypes(m.to(DEV), xg)
+    assert out.shape == (R, C)
+    (out * seeds.to(DEV)).sum().backward()
+    ref = np.stack([O.bmm_pool(m[:, r].numpy(), x.numpy()) for r in range(R)])
+    assert relerr(out.detach().cpu().numpy(), ref) < TOL_PROTO
+    # eager port (the reference's bmm sequence) under autograd
+    xp = x.to(DEV).requires_grad_(True)
+    outp = torch.cat([TP.bmm_pool(m[:, r:r + 1].to(DEV), xp) for r in range(R)], 0)
+    (outp * seeds.to(DEV)).sum().backward()
+    assert relerr(out.detach().cpu().numpy(), outp.detach().cpu().numpy()) < TOL_PROTO
+    assert relerr(xg.grad.cpu().numpy(), xp.grad.cpu().numpy()) < TOL_GRAD
+    # closed form of the adjoint in fp64
+    N = m.double().sum(dim=(2, 3)) + 1.0
+    gx = torch.einsum("rc,br,brp->bcp", seeds.double(), 1.0 / N, m.double().reshape(B, R, -1)) / B
+    assert relerr(xg.grad.cpu().numpy().reshape(B, C, -1), gx.numpy()) < TOL_GRAD
+
+
+def test_update_objective_single_vector():
+    obj = torch.randn(305, device=DEV)
+    v = torch.randn(1, 305, device=DEV)
+    new = clr.update_objective_single_vector(obj, v)
+    assert relerr(new.cpu().numpy(), O.ema_single_vector(obj.cpu().numpy(), v.cpu().numpy())) < 1e-6
+    assert torch.equal(clr.update_objective_single_vector(obj, torch.zeros_like(v)), obj)
+
+
 # ------------------------------------------------------------------------------------------------ fused step
 @pytest.mark.parametrize("variant", ["align_soft", "align_retrify", "clr3", "clr3_aug_bwd"])
 def test_fused_step_vs_oracle(variant):

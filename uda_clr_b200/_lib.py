@@ -70,6 +70,9 @@ _SIGNATURES = {
     "clr_pool_ws_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "clr_pool_rows_ws_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "clr_pool_rows_fwd": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, c_size_t, _P, _P]),
+    "clr_pool_rows_fwd_ps": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, c_size_t, _P, _P]),
+    "clr_bmm_finalize": (c_int, [_P, c_int, c_int, c_int, c_float, _P, _P]),
+    "clr_pool_bwd_ps": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, c_float, c_float, _P, _P]),
     "clr_pool_fwd": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P, _P]),
     "clr_pool_fwd2": (c_int, [_P, _P, c_int, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P, _P, _P]),
     "clr_proto_finalize": (c_int, [_P, c_int, c_int, _P, _P]),

@@ -28,6 +28,9 @@ struct BwdDom {
     const float* scale_dev;   // optional device scalar multiplied into `scale` (upstream dL/dtotal)
     float scale;
     int fmt, B, Kx, ctas;
+    int nrows;            // explicit format: number of weight planes (2K for prototypes, any 1..16 for row pooling)
+    int per_sample;       // 1: sums is [B][nrows][C+1] and the divisor is N_b[r] + n_add (bmm-style pooling)
+    float n_add;
 };
 
 struct BwdParams {
@@ -49,8 +52,8 @@ __global__ void __launch_bounds__(kThreads, 4) pool_bwd_kernel(const BwdParams p
     const int span = bid % p.nSpan;
     const int rest = bid / p.nSpan;
     const int pb = rest % p.nPx, b = rest / p.nPx;
-    const int K = p.K, R = 2 * K;
-    const int QW = (D.fmt == CLR_W_COMPLEMENT) ? K : R;
+    const int K = p.K;
+    const int QW = (D.fmt == CLR_W_COMPLEMENT) ? K : D.nrows;
     const int Q = QW + D.Kx;
     const int c0 = span * kBwdSpan;
 
@@ -74,18 +77,20 @@ __global__ void __launch_bounds__(kThreads, 4) pool_bwd_kernel(const BwdParams p
         const int j = tid & (kBwdSpan - 1), q = tid / kBwdSpan;     // q in [0, 8): rows 0..QT handled in rounds
         const int c = c0 + j;
         const float scale = D.scale_dev ? D.scale * __ldg(D.scale_dev) : D.scale;
+        const float* sums = D.per_sample ? D.sums + (size_t)b * D.nrows * (p.C + 1) : D.sums;
+        const float nadd = D.n_add;
         for (int row = q; row <= QT; row += kThreads / kBwdSpan) {
             float t = 0.f;
             if (c < p.C) {
                 if (row == 0) {
                     if (D.fmt == CLR_W_COMPLEMENT)
                         for (int k = 0; k < K; ++k)
-                            t += scale * __ldg(D.g + (size_t)(K + k) * p.C + c) / __ldg(D.sums + (size_t)(K + k) * (p.C + 1) + p.C);
+                            t += scale * __ldg(D.g + (size_t)(K + k) * p.C + c) / (__ldg(sums + (size_t)(K + k) * (p.C + 1) + p.C) + nadd);
                 } else if (row - 1 < QW) {
                     const int r = row - 1;
-                    const float gr = scale * __ldg(D.g + (size_t)r * p.C + c) / __ldg(D.sums + (size_t)r * (p.C + 1) + p.C);
+                    const float gr = scale * __ldg(D.g + (size_t)r * p.C + c) / (__ldg(sums + (size_t)r * (p.C + 1) + p.C) + nadd);
                     if (D.fmt == CLR_W_COMPLEMENT) {
-                        const float gb = scale * __ldg(D.g + (size_t)(K + r) * p.C + c) / __ldg(D.sums + (size_t)(K + r) * (p.C + 1) + p.C);
+                        const float gb = scale * __ldg(D.g + (size_t)(K + r) * p.C + c) / (__ldg(sums + (size_t)(K + r) * (p.C + 1) + p.C) + nadd);
                         t = gr - gb;
                     } else {
                         t = gr;
@@ -136,7 +141,8 @@ int pool_bwd_impl(const BwdDom* doms, int ndom, int C, int HW, int K, cudaStream
         CLR_CHECK_ARG(D.Kx >= 0 && D.Kx <= K && (D.Kx == 0 || (D.xcoef && D.xtab)));
         if (!aligned4(D.w) || !aligned4(D.grad)) return CLR_ERR_ALIGN;
         vec4 = vec4 && aligned16(D.w) && aligned16(D.grad) && (D.Kx == 0 || aligned16(D.xcoef));
-        const int Q = (D.fmt == CLR_W_COMPLEMENT ? K : 2 * K) + D.Kx;
+        const int Q = (D.fmt == CLR_W_COMPLEMENT ? K : D.nrows) + D.Kx;
+        CLR_CHECK_ARG(D.fmt == CLR_W_COMPLEMENT || (D.nrows >= 1 && D.nrows <= 2 * CLR_MAX_K));
         if (Q > Qmax) Qmax = Q;
     }
     BwdParams p{};
@@ -172,7 +178,7 @@ int clr_pool_bwd(const float* w, int fmt, int B, int C, int HW, int K,
                  const float* g, const float* sums, float scale,
                  const float* xcoef, const float* xtab, int Kx,
                  float* grad, clr_stream_t stream) {
-    clr::BwdDom d{w, g, sums, xcoef, xtab, grad, nullptr, scale, fmt, B, Kx, 0};
+    clr::BwdDom d{w, g, sums, xcoef, xtab, grad, nullptr, scale, fmt, B, Kx, 0, 2 * K, 0, 0.f};
     return clr::pool_bwd_impl(&d, 1, C, HW, K, static_cast<cudaStream_t>(stream));
 }
 
@@ -181,8 +187,17 @@ int clr_pool_bwd_multi(const clr_bwd_dom* doms, int ndom, int C, int HW, int K, 
     clr::BwdDom d[2];
     for (int i = 0; i < ndom; ++i)
         d[i] = clr::BwdDom{doms[i].w, doms[i].g, doms[i].sums, doms[i].xcoef, doms[i].xtab, doms[i].grad,
-                           doms[i].scale_dev, doms[i].scale, doms[i].fmt, doms[i].B, doms[i].Kx, 0};
+                           doms[i].scale_dev, doms[i].scale, doms[i].fmt, doms[i].B, doms[i].Kx, 0, 2 * K, 0, 0.f};
     return clr::pool_bwd_impl(d, ndom, C, HW, K, static_cast<cudaStream_t>(stream));
+}
+
+/* bmm-style (per-sample normalised) pooling, adjoint w.r.t. the features (Trainer_prototype.py:364-383 under autograd):
+ * grad[b,c,p] = scale * sum_r g[r][c] / (N_b[r] + n_add) * rows[b,r,p]   (scale carries the 1/B of the batch mean) */
+int clr_pool_bwd_ps(const float* rows, int B, int C, int HW, int R, const float* g, const float* sums_b, float n_add,
+                    float scale, float* grad, clr_stream_t stream) {
+    if (R < 1 || R > 2 * CLR_MAX_K) return CLR_ERR_BAD_ARG;
+    clr::BwdDom d{rows, g, sums_b, nullptr, nullptr, grad, nullptr, scale, CLR_W_EXPLICIT, B, 0, 0, R, 1, n_add};
+    return clr::pool_bwd_impl(&d, 1, C, HW, /*K (unused for explicit rows)*/ 1, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -368,6 +368,32 @@ __global__ void __launch_bounds__(256) pool_reduce_kernel(const PoolParams p, in
     }
 }
 
+// Per-sample variant: sums_b[b][r][c] = sum over the chunks of sample b only (bmm-style pooling keeps samples apart).
+__global__ void __launch_bounds__(256) pool_reduce_ps_kernel(const float* __restrict__ partial, int nChunk, int R, int C,
+                                                             float* __restrict__ sums_b) {
+    pdl_wait();
+    const int b = blockIdx.y, n = R * (C + 1);
+    const int col = blockIdx.x * 256 + threadIdx.x;
+    if (col >= n) return;
+    double s = 0.0;
+    for (int ch = 0; ch < nChunk; ++ch) s += (double)partial[((size_t)b * nChunk + ch) * n + col];
+    sums_b[(size_t)b * n + col] = (float)s;
+}
+
+// out[r][c] = mean_b S_b[r][c] / (N_b[r] + n_add)      (Trainer_prototype.py:366-368: bmm / (sum + 1), mean over batch)
+__global__ void bmm_finalize_kernel(const float* __restrict__ sums_b, int B, int R, int C, float n_add, float* __restrict__ out) {
+    pdl_wait();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R * C) return;
+    const int r = i / C, c = i - r * C;
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b) {
+        const float* sb = sums_b + ((size_t)b * R + r) * (C + 1);
+        acc += sb[c] / (sb[C] + n_add);
+    }
+    out[i] = acc / (float)B;
+}
+
 __global__ void proto_finalize_kernel(const float* __restrict__ sums, int R, int C, float* __restrict__ mu) {
     pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -504,6 +530,33 @@ int clr_pool_rows_fwd(const float* feat, const float* rows, int B, int C, int HW
                       void* ws, size_t ws_bytes, float* sums, clr_stream_t stream) {
     return clr::pool_fwd_impl(feat, rows, CLR_W_EXPLICIT, B, sums, nullptr, nullptr, 0, 0, nullptr, C, HW, R, ws, ws_bytes,
                               static_cast<cudaStream_t>(stream));
+}
+
+int clr_pool_rows_fwd_ps(const float* feat, const float* rows, int B, int C, int HW, int R,
+                         void* ws, size_t ws_bytes, float* sums_b, clr_stream_t stream) {
+    if (!sums_b || !ws || ws_bytes < sizeof(float) * ((size_t)R * (C + 1)) + clr_pool_rows_ws_bytes(B, C, HW, R)) return CLR_ERR_WORKSPACE;
+    // run the ordinary pooling (its batch-wide sums land in the head of the workspace and are ignored), then
+    // re-reduce the per-(b,chunk) partials sample by sample
+    float* scratch = static_cast<float*>(ws);
+    char* partial = static_cast<char*>(ws) + sizeof(float) * (size_t)R * (C + 1);
+    const size_t pbytes = ws_bytes - sizeof(float) * (size_t)R * (C + 1);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc = clr::pool_fwd_impl(feat, rows, CLR_W_EXPLICIT, B, scratch, nullptr, nullptr, 0, 0, nullptr, C, HW, R, partial, pbytes, st);
+    if (rc != CLR_OK) return rc;
+    const bool vec4 = (HW % 4 == 0) && clr::aligned16(feat) && clr::aligned16(rows);
+    const int px = clr::chunk_px(R, vec4 ? 4 : 1);
+    const int nChunk = (HW + px - 1) / px;
+    const int n = R * (C + 1);
+    clr::launch_k(clr::pool_reduce_ps_kernel, dim3((n + 255) / 256, B), 256, 0, st,
+                  reinterpret_cast<const float*>(partial), nChunk, R, C, sums_b);
+    return clr::launch_status();
+}
+
+int clr_bmm_finalize(const float* sums_b, int B, int R, int C, float n_add, float* out, clr_stream_t stream) {
+    if (!sums_b || !out || B < 1 || R < 1 || C < 1) return CLR_ERR_BAD_ARG;
+    const int n = R * C;
+    clr::launch_k(clr::bmm_finalize_kernel, (n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream), sums_b, B, R, C, n_add, out);
+    return clr::launch_status();
 }
 
 int clr_pool_fwd(const float* feat, const float* w, int fmt, int B, int C, int HW, int K,

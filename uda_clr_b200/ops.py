@@ -317,6 +317,67 @@ def gen_prototype_src_trg_retrify(pred_oS, xs_feature, oT_before, xt_feature, pr
     return _RetrifyPrototypes.apply(int(T), int(stride), o, x, p, ps, fs)[:2 * K]
 
 
+# ----------------------------------------------------------------------------------------------- A6
+class _BmmPrototypes(torch.autograd.Function):
+    """``proto[r] = mean_b( sum_p m[b,r,p] x[b,:,p] / (sum_p m[b,r,p] + n_add) )`` -- the bmm-style per-sample
+    pooling of Trainer_prototype.py:364-383 / cal_prototype.py:156-175.  One read of ``feat`` forward, one write
+    backward (the adjoint never re-reads the features)."""
+
+    @staticmethod
+    def forward(ctx, masks, feat, n_add):
+        lib = _lib.load()
+        B, C, H, W = feat.shape
+        R, HW = masks.shape[1], H * W
+        ws_bytes = 4 * R * (C + 1) + lib.clr_pool_rows_ws_bytes(B, C, HW, R)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=feat.device)
+        sums_b = torch.empty(B, R, C + 1, dtype=torch.float32, device=feat.device)
+        out = torch.empty(R, C, dtype=torch.float32, device=feat.device)
+        with torch.cuda.device(feat.device):
+            check(lib.clr_pool_rows_fwd_ps(ptr(feat), ptr(masks), B, C, HW, R, ptr(ws), ws_bytes, ptr(sums_b), _stream()),
+                  "clr_pool_rows_fwd_ps")
+            check(lib.clr_bmm_finalize(ptr(sums_b), B, R, C, float(n_add), ptr(out), _stream()), "clr_bmm_finalize")
+        ctx.shape, ctx.n_add = (B, C, H, W), float(n_add)
+        ctx.save_for_backward(masks, sums_b)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        masks, sums_b = ctx.saved_tensors
+        B, C, H, W = ctx.shape
+        R = masks.shape[1]
+        gf = None
+        if ctx.needs_input_grad[1]:
+            g = g.contiguous()
+            gf = torch.empty(ctx.shape, dtype=torch.float32, device=masks.device)
+            with torch.cuda.device(masks.device):
+                check(lib.clr_pool_bwd_ps(ptr(masks), B, C, H * W, R, ptr(g), ptr(sums_b), ctx.n_add, 1.0 / B,
+                                          ptr(gf), _stream()), "clr_pool_bwd_ps")
+        return None, gf, None
+
+
+def bmm_prototypes(masks: torch.Tensor, feat: torch.Tensor, n_add: float = 1.0) -> torch.Tensor:
+    """Per-sample-normalised (bmm-style) prototypes of ``Trainer_prototype.py:364-383, 404-451`` and
+    ``cal_prototype.py:156-175``: ``masks [B,R,H,W]`` (R mask planes pooled in ONE read of ``feat``: e.g. cup and
+    disc together, where the reference runs one cuBLAS bmm per mask) -> ``[R, C]``; row r equals the reference's
+    ``torch.mean(bmm(m_r, X) / (sum m_r + 1), dim=0)``.  Gradient flows to ``feat`` (masks are labels or
+    thresholded predictions in every reference call site)."""
+    m = _require_cuda_f32(masks, "masks")
+    f = _require_cuda_f32(feat, "feat")
+    if m.shape[0] != f.shape[0] or m.shape[2:] != f.shape[2:]:
+        raise ValueError("masks %s and feat %s disagree" % (tuple(m.shape), tuple(f.shape)))
+    if not 1 <= m.shape[1] <= 2 * _lib.CLR_MAX_K:
+        raise ValueError("number of mask planes R=%d outside [1, %d]" % (m.shape[1], 2 * _lib.CLR_MAX_K))
+    return _BmmPrototypes.apply(m, f, float(n_add))
+
+
+def update_objective_single_vector(obj: torch.Tensor, vector: torch.Tensor, rate: float = 0.001) -> torch.Tensor:
+    """``Trainer.update_objective_SingleVector`` (Trainer_prototype.py:117-123): ``obj = (1-rate) obj + rate v``
+    unless ``v`` sums to zero -- decided on the device (``torch.where``), without the reference's host sync."""
+    v = vector.detach().reshape(obj.shape)
+    return torch.where(v.sum() == 0, obj, obj * (1.0 - rate) + rate * v)
+
+
 # ----------------------------------------------------------------------------------------------- A8
 def feat_prototype_distance(feat: torch.Tensor, prototype: torch.Tensor, class_numbers: int = 1) -> torch.Tensor:
     """``Trainer.feat_prototype_distance`` (Trainer_prototype.py:98-104): ``[N, class_numbers, H, W]`` with
