@@ -53,12 +53,19 @@ int clr_version(void);
 const char* clr_status_string(int status);
 /* Number of SMs / L2 bytes of the current device (grid sizing is derived from it; exposed for the bench). */
 int clr_device_info(int* sm_count, int* l2_bytes);
-/* Benchmark / debugging knobs (process-wide): "pool_impl" 0 auto / 1 LDG kernel, "pool_stages" TMA ring
+/* Benchmark / debugging knobs (process-wide): "pool_impl" 0 auto / 1 LDG kernel / 2 TMA ring, "pool_stages" TMA ring
  * depth, "disc_impl" 0 fused / 1 two-pass, "mc_precise" 1 = ATen-exact sigmoids in clr_mc_stats.
  * Defaults select the fastest path. */
 int clr_set_tunable(const char* name, int value);
 /* Number of CUDA kernels this library has launched in this process so far (bench: "gpu_launches"). */
 unsigned long long clr_launch_count(void);
+/* Device-side kernel timeline (profiling aid; tools/timeline.py).  While enabled every kernel of the library stamps
+ * %globaltimer into its slot: { earliest CTA start, earliest return from griddepcontrol.wait, latest CTA exit, CTAs }.
+ * clr_trace_read synchronises the device, copies [clr_trace_slots()][4] uint64 to the host and resets the slots. */
+int clr_trace_enable(int on);
+int clr_trace_slots(void);
+const char* clr_trace_name(int slot);
+int clr_trace_read(unsigned long long* out_host);
 /* cudaEvent_t helpers for clr_step_args.ev_* (the library records them around its own launches). */
 int clr_event_create(void** ev);
 int clr_event_destroy(void* ev);

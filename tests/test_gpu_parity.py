@@ -120,3 +120,24 @@ def test_linearity_and_shard_sum_property_full_size():
     # run-to-run bit stability (fixed-order reduction, no atomics)
     again = clr.ops.pool_sums(x, y, 0, 2).double()
     assert torch.equal(again, whole)
+
+
+@pytest.mark.parametrize("impl", [1, 2])
+@pytest.mark.parametrize("shape", [(8, 256, 128, 128, 2), (2, 305, 64, 64, 2), (2, 64, 32, 32, 4), (1, 40, 16, 16, 8)])
+def test_both_pooling_kernels_agree_with_oracle(impl, shape):
+    """The 128-bit LDG kernel (pool_impl=1, the default) and the bulk-TMA ring kernel (pool_impl=2) are the same
+    decomposition with different data paths: both must meet the prototype tolerance and give bit-exact counts."""
+    from uda_clr_b200 import _lib
+    lib = _lib.load()
+    B, C, H, W, K = shape
+    g = torch.Generator().manual_seed(77 + C)
+    y = synth.nested_ellipse_labels(B, K, H, W, g)
+    x = synth.class_shifted_features(y, C, g)
+    S, N = O.pool_sums(x.numpy(), O.weights_complement(y.numpy()))
+    try:
+        _lib.check(lib.clr_set_tunable(b"pool_impl", impl), "pool_impl")
+        sums = clr.ops.pool_sums(x.to(DEV), y.to(DEV), 0, K).cpu().numpy()
+    finally:
+        lib.clr_set_tunable(b"pool_impl", 0)
+    assert np.array_equal(sums[:, C].astype(np.float64), N)
+    assert relerr(sums[:, :C], S) < TOL_PROTO

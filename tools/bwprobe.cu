@@ -89,6 +89,64 @@ __global__ void __launch_bounds__(288, 1) read_tma(const char* __restrict__ src,
     if (acc == 123.456f) out[blockIdx.x * 256 + tid] = acc;
 }
 
+
+// ---- access-pattern probes for the one-read discriminative kernel: tile = [C rows x TP pixels], row stride HW floats ----
+__device__ __forceinline__ void cpa16(void* d, const void* g) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s32(d)), "l"(g) : "memory");
+}
+// cp.async ring of STAGES tiles, NT threads, round-robin tiles; "compute" = one shared-memory read per thread per tile
+template <int TP, int STAGES, int NT>
+__global__ void __launch_bounds__(NT) read_tile_cpasync(const float* __restrict__ src, int B, int C, int HW, float* out) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    float* tiles = reinterpret_cast<float*>(smem);
+    constexpr int RS = TP + 4, NG = TP / 4, NS = NT / NG;
+    const int tps = HW / TP, total = B * tps;
+    const int tid = threadIdx.x, fq = tid % NG, fr0 = tid / NG;
+    const size_t stage_floats = (size_t)C * RS;
+    auto issue = [&](int t, int stage) {
+        if (t < total) {
+            const int b = t / tps, tile = t - b * tps;
+            const float* g = src + ((size_t)b * C + fr0) * HW + tile * TP + 4 * fq;
+            float* d = tiles + stage * stage_floats + (size_t)fr0 * RS + 4 * fq;
+            for (int c = fr0; c < C; c += NS, g += (size_t)NS * HW, d += NS * RS) cpa16(d, g);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    int fetched = blockIdx.x;
+    for (int j = 0; j < STAGES - 1; ++j) { issue(fetched, j); fetched += gridDim.x; }
+    int stage = 0;
+    float acc = 0.f;
+    for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 2) : "memory");
+        __syncthreads();
+        int nst = stage + STAGES - 1; if (nst >= STAGES) nst -= STAGES;
+        issue(fetched, nst); fetched += gridDim.x;
+        acc += tiles[stage * stage_floats + (tid % C) * RS + (tid / C) % TP];
+        if (++stage == STAGES) stage = 0;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (acc == 123.456f) out[blockIdx.x * NT + tid] = acc;
+}
+// tile straight to registers: warp w holds channels w, w+NW, ..; lane = pixel quad (TP = 128 -> 512-byte warp rows);
+// next tile's loads are issued before the current one is consumed (register double buffer of depth CPT)
+template <int CPT, int NT>
+__global__ void __launch_bounds__(NT) read_tile_regs(const float* __restrict__ src, int B, int C, int HW, float* out) {
+    constexpr int TP = 128, NW = NT / 32;
+    const int tps = HW / TP, total = B * tps;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float acc = 0.f;
+    for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        const int b = t / tps, tile = t - b * tps;
+        const float4* g = reinterpret_cast<const float4*>(src + ((size_t)b * C + warp) * HW + tile * TP) + lane;
+        float4 v[CPT];
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) v[i] = ldnc(g + (size_t)i * NW * (HW / 4));
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) acc += v[i].x + v[i].y + v[i].z + v[i].w;
+    }
+    if (acc == 123.456f) out[blockIdx.x * NT + threadIdx.x] = acc;
+}
+
 template <typename F>
 float time_us(F f, int iters = 20) {
     cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
@@ -103,12 +161,14 @@ float time_us(F f, int iters = 20) {
     return ts[ts.size() / 2];
 }
 
-int main() {
+int main(int argc, char** argv) {
+    const bool tiles_only = argc > 1 && argv[1][0] == 't';
     int sms; CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
     const size_t sizes[] = {(size_t)128 << 20, (size_t)256 << 20, (size_t)1024 << 20};
     const int NB = 3;
     float* out; CK(cudaMalloc(&out, 4 << 20));
     for (size_t bytes : sizes) {
+        if (tiles_only) break;
         char* buf[NB];
         for (int i = 0; i < NB; ++i) { CK(cudaMalloc(&buf[i], bytes)); CK(cudaMemset(buf[i], 0, bytes)); }
         const size_t n4 = bytes / 16;
@@ -141,6 +201,38 @@ int main() {
             float t = time_us([&](int i) { CK(cudaMemcpyAsync(buf[(i + 1) % NB], buf[i % NB], bytes, cudaMemcpyDeviceToDevice)); });
             printf("memcpy d2d               %8.2f us  %7.1f GB/s (R+W)\n", t, 2.0 * bytes / t / 1e3);
         }
+        for (int i = 0; i < NB; ++i) CK(cudaFree(buf[i]));
+    }
+
+    {   // tile-pattern probes on the config-1 feature map [8,256,128*128]
+        const int B = 8, C = 256, HW = 16384;
+        const size_t bytes = (size_t)B * C * HW * 4;
+        float* buf[NB];
+        for (int i = 0; i < NB; ++i) { CK(cudaMalloc(&buf[i], bytes)); CK(cudaMemset(buf[i], 0, bytes)); }
+        printf("== tile patterns, %zu MiB\n", bytes >> 20);
+#define TILE_PROBE(TP, ST, NT, MULT) { \
+            const size_t smem = (size_t)ST * C * (TP + 4) * 4; \
+            CK(cudaFuncSetAttribute(read_tile_cpasync<TP, ST, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            float t = time_us([&](int i) { read_tile_cpasync<TP, ST, NT><<<sms * MULT, NT, smem>>>(buf[i % NB], B, C, HW, out); }); \
+            CK(cudaGetLastError()); \
+            printf("tile cp.async TP=%d stages=%d NT=%d ctas/SM=%d  %8.2f us  %7.1f GB/s\n", TP, ST, NT, MULT, t, bytes / t / 1e3); }
+        TILE_PROBE(32, 3, 512, 2)
+        TILE_PROBE(32, 3, 256, 2)
+        TILE_PROBE(32, 2, 512, 2)
+        TILE_PROBE(64, 3, 512, 1)
+        TILE_PROBE(64, 2, 512, 1)
+        TILE_PROBE(64, 2, 1024, 1)
+        TILE_PROBE(16, 3, 256, 4)
+#define REG_PROBE(CPT, NT, MULT) { \
+            float t = time_us([&](int i) { read_tile_regs<CPT, NT><<<sms * MULT, NT>>>(buf[i % NB], B, C, HW, out); }); \
+            CK(cudaGetLastError()); \
+            printf("tile regs TP=128 CPT=%d NT=%d ctas/SM=%d  %8.2f us  %7.1f GB/s\n", CPT, NT, MULT, t, bytes / t / 1e3); }
+        REG_PROBE(16, 512, 1)
+        REG_PROBE(16, 512, 2)
+        REG_PROBE(32, 256, 2)
+        REG_PROBE(32, 256, 4)
+        REG_PROBE(8, 1024, 1)
+        REG_PROBE(8, 1024, 2)
         for (int i = 0; i < NB; ++i) CK(cudaFree(buf[i]));
     }
     return 0;

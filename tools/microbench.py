@@ -90,12 +90,13 @@ def main():
     lib.clr_set_tunable(b"pool_impl", 1)
     rec("pool_fwd_ldg", fwd, F + Lb)
     rec("pool_fwd2_ldg", fwd2, 2 * (F + Lb))
-    lib.clr_set_tunable(b"pool_impl", 0)
+    lib.clr_set_tunable(b"pool_impl", 2)
     for stages in (2, 3, 4):
         lib.clr_set_tunable(b"pool_stages", stages)
         rec("pool_fwd_tma_s%d" % stages, fwd, F + Lb)
         rec("pool_fwd2_tma_s%d" % stages, fwd2, 2 * (F + Lb))
     lib.clr_set_tunable(b"pool_stages", 0)
+    lib.clr_set_tunable(b"pool_impl", 0)
 
     def bwd(i):
         check(lib.clr_pool_bwd(ptr(y), 0, B, C, HW, K, ptr(gmat), ptr(sums), 1.0, None, None, 0,

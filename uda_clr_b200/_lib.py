@@ -67,6 +67,10 @@ _SIGNATURES = {
     "clr_event_create": (c_int, [POINTER(c_void_p)]),
     "clr_event_destroy": (c_int, [c_void_p]),
     "clr_event_elapsed_us": (c_int, [c_void_p, c_void_p, POINTER(c_float)]),
+    "clr_trace_enable": (c_int, [c_int]),
+    "clr_trace_slots": (c_int, []),
+    "clr_trace_name": (c_char_p, [c_int]),
+    "clr_trace_read": (c_int, [c_void_p]),
     "clr_pool_ws_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "clr_pool_rows_ws_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "clr_pool_rows_fwd": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, c_size_t, _P, _P]),

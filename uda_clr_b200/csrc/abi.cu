@@ -49,8 +49,40 @@ int clr_set_tunable(const char* name, int value) {
     else if (!strcmp(name, "l2_keep")) t.l2_keep = value;
     else if (!strcmp(name, "pdl_off")) t.pdl_off = value;
     else if (!strcmp(name, "overlap_off")) t.overlap_off = value;
+    else if (!strcmp(name, "finish_off")) t.finish_off = value;
     else return CLR_ERR_BAD_ARG;
     return CLR_OK;
+}
+
+/* Device-side kernel timeline (clr_common.cuh TraceRec).  The buffer is allocated once per process and never freed,
+ * so a stale pointer in a translation unit that has not launched since tracing was switched off stays harmless. */
+static clr::TraceRec* g_trace_alloc = nullptr;
+static int trace_reset() {
+    clr::TraceRec init[clr::kTraceSlots];
+    for (int i = 0; i < clr::kTraceSlots; ++i) init[i] = clr::TraceRec{~0ull, ~0ull, 0ull, 0ull};
+    CLR_RETURN_IF_CUDA(cudaMemcpy(g_trace_alloc, init, sizeof(init), cudaMemcpyHostToDevice));
+    return CLR_OK;
+}
+int clr_trace_enable(int on) {
+    if (!on) { clr::tunables().trace_buf = nullptr; return CLR_OK; }
+    if (!g_trace_alloc) CLR_RETURN_IF_CUDA(cudaMalloc(&g_trace_alloc, sizeof(clr::TraceRec) * clr::kTraceSlots));
+    const int rc = trace_reset();
+    if (rc != CLR_OK) return rc;
+    clr::tunables().trace_buf = g_trace_alloc;
+    return CLR_OK;
+}
+int clr_trace_slots(void) { return clr::kTraceSlots; }
+const char* clr_trace_name(int slot) {
+    static const char* names[clr::kTraceSlots] = {"mc_stats", "retrify_weights", "pool_fwd", "pool_reduce", "align_finalize",
+        "cons_fwd", "disc_fused", "disc_reduce", "disc_finalize", "pool_bwd_target", "pool_bwd_source", "pool_bwd_both",
+        "cons_bwd", "step_pack", "other", ""};
+    return (slot >= 0 && slot < clr::kTraceSlots) ? names[slot] : "";
+}
+int clr_trace_read(unsigned long long* out_host) {
+    if (!out_host || !g_trace_alloc) return CLR_ERR_BAD_ARG;
+    CLR_RETURN_IF_CUDA(cudaDeviceSynchronize());
+    CLR_RETURN_IF_CUDA(cudaMemcpy(out_host, g_trace_alloc, sizeof(clr::TraceRec) * clr::kTraceSlots, cudaMemcpyDeviceToHost));
+    return trace_reset();
 }
 
 int clr_version(void) { return CLR_B200_VERSION; }

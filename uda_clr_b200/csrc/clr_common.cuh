@@ -27,17 +27,20 @@ const DeviceFacts& device_facts();
 
 // Process-wide kernel-selection knobs for benchmarking (clr_set_tunable); defaults pick the fastest path.
 struct Tunables {
-    int pool_impl;     // 0 = auto (TMA ring when aligned), 1 = force the LDG kernel
+    int pool_impl;     // 0 = auto (128-bit LDG kernel, 2 CTAs/SM: fastest in the live step), 1 = force LDG, 2 = force the TMA ring
     int pool_stages;   // TMA ring depth (0 = auto)
     int dots_impl;     // reserved
     int disc_impl;     // 0 = auto (one-read fused discriminative kernel), 1 = force the two-pass form
     int bwd_impl;      // reserved
-    int disc_threads;  // 0 = auto (512-thread CTAs when K <= 2), 256 = force 256
+    int disc_threads;  // 0 = auto (256-thread CTAs: fastest in the live step), 512 = 512-thread CTAs when K <= 2
     int disc_tile;     // 0 = auto, 64 = force 64-pixel tiles in the fused discriminative kernel
     int l2_keep;       // 1 = evict-last policy on xs in the pooling pass (re-read by the discriminative pass); default off
     int pdl_off;       // 1 = do not use programmatic dependent launch
     int overlap_off;   // 1 = clr_step_run ignores aux_stream (serial order)
     int mc_precise;    // 1 = ATen-exact sigmoids in clr_mc_stats (slower), 0 = fast intrinsics
+    int finish_off;    // 1 = single-GPU step uses the separate reduce / finalize kernels instead of the merged finish kernels
+    void* trace_buf;   // device TraceRec[kTraceSlots] or NULL (clr_trace_set): device-side timeline of the kernels
+    int bwd_trace_id;  // trace slot of the next pool_bwd launch (set by the step orchestration)
 };
 Tunables& tunables();
 
@@ -50,6 +53,39 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 
 // Process-wide count of kernel launches issued by this library (clr_launch_count); relaxed atomic.
 void count_launch();
+
+// ---- device-side timeline (profiling aid; inert unless clr_trace_set installed a buffer) ---------------------
+// Every kernel stamps %globaltimer into its slot: t_first = earliest CTA start (before griddepcontrol.wait),
+// t_ready = earliest return from griddepcontrol.wait (predecessor complete), t_last = latest CTA exit.  This is the
+// only way to see the live step's overlap / gaps without a timeline profiler (no nsys in the image); ncu
+// serialises kernels and event records break programmatic dependent launch.
+struct TraceRec { unsigned long long t_first, t_ready, t_last, n_cta; };
+enum TraceId { TR_MC_STATS = 0, TR_RETRIFY, TR_POOL, TR_POOL_REDUCE, TR_ALIGN, TR_CONS, TR_DISC, TR_DISC_REDUCE,
+               TR_DISC_FIN, TR_BWD_T, TR_BWD_S, TR_BWD_BOTH, TR_CONS_BWD, TR_PACK, TR_OTHER, kTraceSlots = 16 };
+static __device__ TraceRec* g_trace_dev = nullptr;     // one copy per translation unit, installed by launch_k
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ bool trace_leader() { return threadIdx.x == 0 && threadIdx.y == 0 && threadIdx.z == 0; }
+__device__ __forceinline__ void trace_enter(int id) {
+    TraceRec* t = g_trace_dev;
+    if (t && trace_leader()) { atomicMin(&t[id].t_first, global_ns()); atomicAdd(&t[id].n_cta, 1ull); }
+}
+__device__ __forceinline__ void trace_ready(int id) {
+    TraceRec* t = g_trace_dev;
+    if (t && trace_leader()) atomicMin(&t[id].t_ready, global_ns());
+}
+__device__ __forceinline__ void trace_exit(int id) {
+    TraceRec* t = g_trace_dev;
+    if (t && trace_leader()) atomicMax(&t[id].t_last, global_ns());
+}
+// kernel prologue: stamp; let the NEXT kernel of the stream start launching right away (its CTAs become resident as
+// ours retire and park in their own griddepcontrol.wait, so launch latency and CTA ramp-up leave the critical path --
+// the wait still blocks until this whole grid has completed and flushed, so ordering is unchanged); wait for the
+// predecessor grid; stamp
+__device__ __forceinline__ void kernel_begin(int id) { trace_enter(id); pdl_trigger(); pdl_wait(); trace_ready(id); }
 
 // ---- streaming loads / stores --------------------------------------------------------------------
 // Feature maps are touched exactly once per pass: read through the non-coherent path without
@@ -196,6 +232,11 @@ static inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = tunables().pdl_off ? 0 : 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
+    {   // install / remove the trace buffer pointer in THIS translation unit's copy of g_trace_dev (stream-ordered)
+        static void* installed = nullptr;
+        void* want = tunables().trace_buf;
+        if (want != installed) { cudaMemcpyToSymbolAsync(g_trace_dev, &want, sizeof(want), 0, cudaMemcpyHostToDevice, st); installed = want; }
+    }
     count_launch();
     cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
 }

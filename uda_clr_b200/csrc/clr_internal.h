@@ -5,9 +5,11 @@
 
 namespace clr {
 
+struct PoolLayout;
 int pool_fwd_impl(const float* feat0, const float* w0, int fmt0, int B0, float* sums0,
                   const float* feat1, const float* w1, int fmt1, int B1, float* sums1,
-                  int C, int HW, int R, void* ws, size_t ws_bytes, cudaStream_t st, int keep0 = 0, int keep1 = 0);
+                  int C, int HW, int R, void* ws, size_t ws_bytes, cudaStream_t st, int keep0 = 0, int keep1 = 0,
+                  struct PoolLayout* skip_reduce_layout = nullptr, unsigned int* counter_reset = nullptr);
 size_t pool_partial_bytes(int B, int C, int HW, int R);
 // sums[r][c] = sum_slot partial[slot][r][c] (fp64, fixed order) for a [slots][R][C+1] partial buffer
 void launch_partial_reduce(const float* partial, int slots, int R, int C, float* sums, cudaStream_t st);
@@ -33,5 +35,20 @@ int disc_finalize_impl(float* packed2, const float* P_s, int K, int C, double np
                        float w_intra, float w_inter, float w_aug, float aug_weight, int use_disc, int use_cons,
                        float* losses, const float* hinge, int n_hinge, int hinge_stride,
                        const double* cons, int n_cons, cudaStream_t stream);
+
+// Single-GPU fused step: partial reduce + finalize in one launch each (finalize.cu).
+int pool_finish_impl(const float* partial_s, int slots_s, const float* partial_t, int slots_t, float* sums_s, float* sums_t,
+                     int K, int C, float* stored_s, float* stored_t, int first_s, int first_t, double decay,
+                     float w_intra, float w_inter, float* P_s, float* P_t, float* g_s, float* g_t,
+                     float* disc_vec, float* disc_beta, float* losses, double* loss_partial, unsigned int* counter,
+                     cudaStream_t st);
+int pool_finish_max_ctas(int C);
+int disc_finish_impl(const float* partial, int slots, float* packed2, const float* P_s, int K, int C, double npx,
+                     float w_disc, float ema_factor, float gscale, float* g_s, float* xtab,
+                     float w_intra, float w_inter, float w_aug, float aug_weight, int use_cons, float* losses,
+                     const float* hinge, int n_hinge, int hinge_stride, const double* cons, int n_cons, cudaStream_t st);
+
+// Where pool_fwd_impl left its per-(b,chunk) partials (for callers that reduce them themselves).
+struct PoolLayout { const float* partial[2]; int slots[2]; };
 
 }  // namespace clr

@@ -23,7 +23,8 @@ __device__ __forceinline__ float sigmoid_fast(float x) { return rcp_approx(1.0f 
 struct ConsGeom {
     int BK, Hi, Wi, H, W;
     float sh, sw;   // nearest scales: (float)H/Hi, (float)W/Wi
-    int rows_per_cta;
+    unsigned total_vec, wv;      // vectors in all planes / per image row
+    int wv_shift, hi_shift;      // log2 when a power of two (shifts instead of integer divisions), else -1
 };
 
 // F.interpolate(mode='nearest') source index: min(floor(dst * scale), in - 1)
@@ -42,14 +43,24 @@ __device__ __forceinline__ bool label_above(float z, const LabelRule& r) {
     return sigmoid_aten(z) > r.thr;
 }
 
-// One element of the masked BCE: returns m*l.  y is 0/1, so only one of ATen's two log terms is non-zero:
-// l = -max(log(y ? q : 1-q), -100) with q = sigmoid(z) (fast intrinsics; ATen: log(q) / log1p(-q)).
-__device__ __forceinline__ void cons_elem(float zt, float za, float m, const LabelRule& r, float& ml, float& q_out, float& y_out) {
+// Forward element: l = BCE(sigmoid(za), y) = -log(y ? q : 1-q) = softplus(-/+ za) = ln2 * lg2(1 + 2^(-/+ za*log2 e)):
+// two MUFU ops per element instead of three (exp, reciprocal, log).  ATen evaluates log(q) / log(1-q) on the ROUNDED
+// fp32 q and clamps the log at -100: q rounds to exactly 1 (0) once |za| >= 24 ln 2, where the wrong-side term becomes
+// 100 -- reproduced by the explicit saturation test; in the narrow band below it ATen's own value carries the
+// quantisation error of 1-q, the softplus form is the mathematically exact one.
+__device__ __forceinline__ float cons_loss_elem(float zt, float za, const LabelRule& r) {
     const bool yb = label_above(zt, r);
+    const float x = (yb ? -1.4426950408889634f : 1.4426950408889634f) * za;    // wrong-side exponent, base 2
+    const float l = 0.6931471805599453f * lg2_approx(1.0f + ex2_approx(x));
+    return x >= 24.0f ? 100.0f : l;
+}
+
+// Backward element: (q - y) / max(q (1-q), 1e-12) * q (1-q)   (ATen binary_cross_entropy_backward x sigmoid')
+__device__ __forceinline__ float cons_grad_elem(float zt, float za, const LabelRule& r) {
+    const float y = label_above(zt, r) ? 1.0f : 0.0f;
     const float q = sigmoid_fast(za);
-    const float t = yb ? q : 1.0f - q;
-    ml = -m * fmaxf(0.6931471805599453f * lg2_approx(t), -100.0f);
-    q_out = q; y_out = yb ? 1.0f : 0.0f;
+    const float qq = (1.0f - q) * q;
+    return (q - y) / fmaxf(qq, 1e-12f) * qq;
 }
 
 static LabelRule make_rule(float thr) {
@@ -67,86 +78,81 @@ static LabelRule make_rule(float thr) {
     return r;
 }
 
-constexpr int kConsTX = 64, kConsTY = 4;   // block = 64 vector columns x 4 rows
+constexpr int kConsThreads = 256;
 
-// grid = (row blocks, B*K planes); each CTA covers `rows_per_cta` image rows of one plane; thread (tx, ty) walks
-// vector columns tx, tx+64, .. of rows ty, ty+4, .. -- no divisions, up to 4 independent 128-bit load pairs in flight.
+// Persistent flat grid-stride kernel over the VEC-wide vectors of [B*K, Hi, Wi]: the grid is exactly the resident CTA
+// capacity (no partial last wave -- the 2-D grid this replaces ran 2.3 waves), every thread keeps U = 4 independent
+// 128-bit load pairs in flight, and the (plane, row, column) of a vector costs two shifts (two 32-bit divisions when
+// the image size is not a power of two).
 template <int VEC, bool BWD>
-__global__ void __launch_bounds__(kConsTX * kConsTY) cons_kernel(const float* __restrict__ oT, const float* __restrict__ oT_aug,
-                                                                 const float* __restrict__ masks, ConsGeom g, LabelRule thr,
-                                                                 double* __restrict__ partial,
-                                                                 const float* __restrict__ stats, const float* __restrict__ gscale_dev,
-                                                                 float gscale, float* __restrict__ grad) {
-    pdl_wait();
-    const int bk = blockIdx.y;
-    const int y0 = blockIdx.x * g.rows_per_cta;
-    const int wv = g.Wi / VEC;                       // vectors per row
-    const size_t plane = (size_t)bk * g.Hi * g.Wi;
-    const float* mplane = masks + (size_t)bk * g.H * g.W;
+__global__ void __launch_bounds__(kConsThreads, 4) cons_kernel(const float* __restrict__ oT, const float* __restrict__ oT_aug,
+                                                            const float* __restrict__ masks, ConsGeom g, LabelRule thr,
+                                                            double* __restrict__ partial,
+                                                            const float* __restrict__ stats, const float* __restrict__ gscale_dev,
+                                                            float gscale, float* __restrict__ grad) {
+    kernel_begin(BWD ? TR_CONS_BWD : TR_CONS);
     const bool shared_mask = (g.Wi == VEC * g.W);    // exact VEC:1 upsampling: a vector shares one mask pixel
     float coef = 0.f;
     if (BWD) coef = (gscale_dev ? gscale * __ldg(gscale_dev) : gscale) / __ldg(stats + 1);
     float num = 0.f, den = 0.f;
     constexpr int U = 4;
-    const int tx = threadIdx.x, ty = threadIdx.y;
-    for (int ry = ty; ry < g.rows_per_cta; ry += kConsTY) {
-        const int y = y0 + ry;
-        if (y >= g.Hi) break;
-        const int sy = nearest_src(y, g.sh, g.H);
-        const float* mrow = mplane + (size_t)sy * g.W;
-        const size_t rowoff = plane + (size_t)y * g.Wi;
-        for (int xb = tx; xb < wv; xb += U * kConsTX) {
-            Pack<VEC> zt[U], za[U];
-            float msh[U];
+    const unsigned nthreads = gridDim.x * kConsThreads;
+    for (unsigned v0 = blockIdx.x * kConsThreads + threadIdx.x; v0 < g.total_vec; v0 += U * nthreads) {
+        Pack<VEC> zt[U], za[U];
+        const float* mrow[U];
+        unsigned xv[U];
+        float msh[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int xv = xb + u * kConsTX;
-                if (xv < wv) {
-                    zt[u] = ld_stream<VEC>(oT + rowoff + (size_t)xv * VEC);
-                    za[u] = ld_stream<VEC>(oT_aug + rowoff + (size_t)xv * VEC);
-                    msh[u] = shared_mask ? __ldg(mrow + xv) : 0.f;
+        for (int u = 0; u < U; ++u) {
+            const unsigned v = v0 + u * nthreads;
+            if (v < g.total_vec) {
+                zt[u] = ld_stream<VEC>(oT + (size_t)v * VEC);
+                za[u] = ld_stream<VEC>(oT_aug + (size_t)v * VEC);
+                const unsigned row = g.wv_shift >= 0 ? (v >> g.wv_shift) : (v / g.wv);
+                xv[u] = v - row * g.wv;
+                const unsigned plane = g.hi_shift >= 0 ? (row >> g.hi_shift) : (row / (unsigned)g.Hi);
+                const int y = (int)(row - plane * (unsigned)g.Hi);
+                mrow[u] = masks + ((size_t)plane * g.H + nearest_src(y, g.sh, g.H)) * g.W;
+                msh[u] = shared_mask ? __ldg(mrow[u] + xv[u]) : 0.f;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const unsigned v = v0 + u * nthreads;
+            if (v >= g.total_vec) continue;
+            Pack<VEC> go;
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                const float m = shared_mask ? msh[u] : __ldg(mrow[u] + nearest_src((int)(xv[u] * VEC + e), g.sw, g.W));
+                if (BWD) {
+                    go.v[e] = coef * m * cons_grad_elem(zt[u].v[e], za[u].v[e], thr);
+                } else {
+                    num = fmaf(m, cons_loss_elem(zt[u].v[e], za[u].v[e], thr), num);
+                    den += m;
                 }
             }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int xv = xb + u * kConsTX;
-                if (xv >= wv) continue;
-                Pack<VEC> go;
-#pragma unroll
-                for (int v = 0; v < VEC; ++v) {
-                    const float m = shared_mask ? msh[u] : __ldg(mrow + nearest_src(xv * VEC + v, g.sw, g.W));
-                    float ml, q, yv;
-                    cons_elem(zt[u].v[v], za[u].v[v], m, thr, ml, q, yv);
-                    num += ml; den += m;
-                    if (BWD) {
-                        // ATen binary_cross_entropy_backward: (q - y) / max((1-q) q, 1e-12), chained with sigmoid' = q (1-q)
-                        const float qq = (1.0f - q) * q;
-                        go.v[v] = coef * m * (q - yv) / fmaxf(qq, 1e-12f) * qq;
-                    }
-                }
-                if (BWD) st_stream<VEC>(grad + rowoff + (size_t)xv * VEC, go);
-            }
+            if (BWD) st_stream<VEC>(grad + (size_t)v * VEC, go);
         }
     }
     if (!BWD) {
         double dn = warp_sum((double)num), dd = warp_sum((double)den);
-        __shared__ double sh[2][8];
-        const int t = ty * kConsTX + tx, lane = t & 31, warp = t >> 5;
+        __shared__ double sh[2][kConsThreads / 32];
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         if (lane == 0) { sh[0][warp] = dn; sh[1][warp] = dd; }
         __syncthreads();
-        if (t == 0) {
+        if (threadIdx.x == 0) {
             double a = 0.0, b = 0.0;
-            for (int w = 0; w < 8; ++w) { a += sh[0][w]; b += sh[1][w]; }
-            const int cta = blockIdx.y * gridDim.x + blockIdx.x;
-            partial[2 * cta] = a;
-            partial[2 * cta + 1] = b;
+            for (int w = 0; w < kConsThreads / 32; ++w) { a += sh[0][w]; b += sh[1][w]; }
+            partial[2 * blockIdx.x] = a;
+            partial[2 * blockIdx.x + 1] = b;
         }
     }
+    trace_exit(BWD ? TR_CONS_BWD : TR_CONS);
 }
 
 __global__ void __launch_bounds__(256) cons_final_kernel(const double* __restrict__ partial, int nblk, float aug_weight,
                                                          float* __restrict__ stats) {
-    pdl_wait();
+    kernel_begin(TR_OTHER);
     double a = 0.0, b = 0.0;
     for (int i = threadIdx.x; i < nblk; i += blockDim.x) { a += partial[2 * i]; b += partial[2 * i + 1]; }
     a = warp_sum(a);
@@ -166,26 +172,46 @@ __global__ void __launch_bounds__(256) cons_final_kernel(const double* __restric
 
 constexpr int kConsMaxBlocks = 2048;
 
-// rows per CTA so that the grid stays <= kConsMaxBlocks CTAs and every CTA has >= 4 vectors per thread
-static ConsGeom make_geom(int B, int K, int Hi, int Wi, int H, int W, dim3& grid) {
-    ConsGeom g{B * K, Hi, Wi, H, W, (float)H / (float)Hi, (float)W / (float)Wi, 1};
-    int rows = (4 * 256 * 4 + Wi - 1) / Wi;
-    if (rows < 1) rows = 1;
-    while ((long long)((Hi + rows - 1) / rows) * B * K > kConsMaxBlocks && rows < Hi) rows *= 2;
-    g.rows_per_cta = rows;
-    grid = dim3((unsigned)((Hi + rows - 1) / rows), (unsigned)(B * K));
-    return g;
+static int log2_exact(unsigned x) {
+    if (x == 0 || (x & (x - 1))) return -1;
+    int s = 0;
+    while ((1u << s) != x) ++s;
+    return s;
+}
+
+static int make_geom(int B, int K, int Hi, int Wi, int H, int W, int vec, ConsGeom& g) {
+    const unsigned long long total = (unsigned long long)B * K * Hi * (unsigned long long)(Wi / vec);
+    if (total > 0x7fffffffull) return CLR_ERR_UNSUPPORTED;
+    g = ConsGeom{B * K, Hi, Wi, H, W, (float)H / (float)Hi, (float)W / (float)Wi, (unsigned)total, (unsigned)(Wi / vec),
+                 log2_exact((unsigned)(Wi / vec)), log2_exact((unsigned)Hi)};
+    return CLR_OK;
+}
+
+template <int VEC, bool BWD>
+static int cons_grid(const ConsGeom& g, int& grid) {
+    int occ = 0;
+    CLR_RETURN_IF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cons_kernel<VEC, BWD>, kConsThreads, 0));
+    if (occ < 1) occ = 1;
+    long long want = (long long)device_facts().sms * occ;
+    const long long need = ((long long)g.total_vec + kConsThreads - 1) / kConsThreads;
+    if (want > need) want = need;
+    if (want > kConsMaxBlocks) want = kConsMaxBlocks;
+    grid = (int)(want < 1 ? 1 : want);
+    return CLR_OK;
 }
 
 int cons_fwd_partials(const float* oT, const float* oT_aug, const float* masks, int B, int K, int Hi, int Wi,
                       int H, int W, float threshold, double* partial, int* nblocks, cudaStream_t st) {
-    dim3 grid;
-    const ConsGeom g = make_geom(B, K, Hi, Wi, H, W, grid);
-    if ((long long)grid.x * grid.y > kConsMaxBlocks || grid.y > 65535) return CLR_ERR_UNSUPPORTED;
     const bool vec4 = (Wi % 4 == 0) && aligned16(oT) && aligned16(oT_aug);
-    if (vec4) launch_k(cons_kernel<4, false>, grid, dim3(kConsTX, kConsTY), 0, st, oT, oT_aug, masks, g, make_rule(threshold), partial, nullptr, nullptr, 0.f, nullptr);
-    else launch_k(cons_kernel<1, false>, grid, dim3(kConsTX, kConsTY), 0, st, oT, oT_aug, masks, g, make_rule(threshold), partial, nullptr, nullptr, 0.f, nullptr);
-    *nblocks = (int)(grid.x * grid.y);
+    ConsGeom g;
+    int rc = make_geom(B, K, Hi, Wi, H, W, vec4 ? 4 : 1, g);
+    if (rc != CLR_OK) return rc;
+    int grid = 1;
+    rc = vec4 ? cons_grid<4, false>(g, grid) : cons_grid<1, false>(g, grid);
+    if (rc != CLR_OK) return rc;
+    if (vec4) launch_k(cons_kernel<4, false>, grid, kConsThreads, 0, st, oT, oT_aug, masks, g, make_rule(threshold), partial, nullptr, nullptr, 0.f, nullptr);
+    else launch_k(cons_kernel<1, false>, grid, kConsThreads, 0, st, oT, oT_aug, masks, g, make_rule(threshold), partial, nullptr, nullptr, 0.f, nullptr);
+    *nblocks = grid;
     return launch_status();
 }
 
@@ -212,13 +238,16 @@ int clr_cons_bwd(const float* oT, const float* oT_aug, const float* masks, int B
                  float* grad_oT_aug, clr_stream_t stream) {
     if (!oT || !oT_aug || !masks || !stats || !grad_oT_aug || B < 1 || K < 1 || Hi < 1 || Wi < 1 || H < 1 || W < 1)
         return CLR_ERR_BAD_ARG;
-    dim3 grid;
-    const clr::ConsGeom g = clr::make_geom(B, K, Hi, Wi, H, W, grid);
-    if (grid.y > 65535) return CLR_ERR_UNSUPPORTED;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool vec4 = (Wi % 4 == 0) && clr::aligned16(oT) && clr::aligned16(oT_aug) && clr::aligned16(grad_oT_aug);
-    if (vec4) clr::launch_k(clr::cons_kernel<4, true>, grid, dim3(clr::kConsTX, clr::kConsTY), 0, st, oT, oT_aug, masks, g, clr::make_rule(threshold), nullptr, stats, gscale_dev, gscale * aug_weight, grad_oT_aug);
-    else clr::launch_k(clr::cons_kernel<1, true>, grid, dim3(clr::kConsTX, clr::kConsTY), 0, st, oT, oT_aug, masks, g, clr::make_rule(threshold), nullptr, stats, gscale_dev, gscale * aug_weight, grad_oT_aug);
+    clr::ConsGeom g;
+    int rc = clr::make_geom(B, K, Hi, Wi, H, W, vec4 ? 4 : 1, g);
+    if (rc != CLR_OK) return rc;
+    int grid = 1;
+    rc = vec4 ? clr::cons_grid<4, true>(g, grid) : clr::cons_grid<1, true>(g, grid);
+    if (rc != CLR_OK) return rc;
+    if (vec4) clr::launch_k(clr::cons_kernel<4, true>, grid, clr::kConsThreads, 0, st, oT, oT_aug, masks, g, clr::make_rule(threshold), nullptr, stats, gscale_dev, gscale * aug_weight, grad_oT_aug);
+    else clr::launch_k(clr::cons_kernel<1, true>, grid, clr::kConsThreads, 0, st, oT, oT_aug, masks, g, clr::make_rule(threshold), nullptr, stats, gscale_dev, gscale * aug_weight, grad_oT_aug);
     return clr::launch_status();
 }
 

@@ -54,7 +54,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 template <int K, int TP, int STAGES, int NT>
 __global__ void __launch_bounds__(NT, (TP == 32) ? 2 : 1) disc_fused_kernel(const DiscParams p) {
-    pdl_wait();
+    kernel_begin(TR_DISC);
     constexpr int RS = TP + kDiscPad;            // row stride (floats)
     constexpr int NG = TP / 4;                   // pixel quads (16-byte chunks) per row
     constexpr int NS = NT / NG;                  // channel slices in phase 1
@@ -280,6 +280,7 @@ __global__ void __launch_bounds__(NT, (TP == 32) ? 2 : 1) disc_fused_kernel(cons
                 if ((ei * NT + w * 32) / TP == tid) t += wred[(1 + ei) * NW + w];
         out[(size_t)tid * (p.C + 1) + p.C] = t;
     }
+    trace_exit(TR_DISC);
 }
 
 template <int K, int TP, int NT>
@@ -318,7 +319,7 @@ static int launch_disc(DiscParams& p, int* nparts, cudaStream_t st) {
     const size_t per_cta = (TP == 32) ? (budget - 2048) / 2 : budget;
     // 512-thread CTAs (32 warps per SM at two CTAs) when the accumulators fit the 64-register budget
     constexpr bool wide = (K <= 2);
-    if (tunables().disc_threads != 256 && wide) {
+    if (tunables().disc_threads == 512 && wide) {
         if (disc_smem<K, TP, 512>(p.C, 3) <= per_cta) return launch_disc_s<K, TP, 3, 512>(p, nparts, st);
         if (disc_smem<K, TP, 512>(p.C, 2) <= budget) return launch_disc_s<K, TP, 2, 512>(p, nparts, st);
     }

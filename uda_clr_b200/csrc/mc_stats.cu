@@ -42,11 +42,11 @@ __device__ __forceinline__ void mc_sigmoids(float p, float& s_half, float& s_ful
 template <int VEC, int TT, bool PRECISE>
 __global__ void __launch_bounds__(256) mc_stats_kernel(const float* __restrict__ preds, int T, size_t n,
                                                        float* __restrict__ std_map, float* __restrict__ pred_mean) {
-    pdl_wait();
+    kernel_begin(TR_MC_STATS);
     // n = B*K*Hi*Wi positions; preds is [T][n].  TT > 0: T <= TT, values kept in registers (two-pass
     // variance); TT == 0: any T, Welford.
     const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
-    if (i >= n) return;
+    if (i >= n) { trace_exit(TR_MC_STATS); return; }
     float mean_h[VEC], m2[VEC], mean_f[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) { mean_h[v] = 0.f; m2[v] = 0.f; mean_f[v] = 0.f; }
@@ -100,6 +100,7 @@ __global__ void __launch_bounds__(256) mc_stats_kernel(const float* __restrict__
     }
     st_keep<VEC>(std_map + i, s);
     st_keep<VEC>(pred_mean + i, m);
+    trace_exit(TR_MC_STATS);
 }
 
 template <int VEC, bool PRECISE>
@@ -134,11 +135,11 @@ __global__ void __launch_bounds__(256) retrify_weights_kernel(
     int B, int K, int H, int W, int Hi, int Wi, float pseudo_thr, float std_thr,
     float* __restrict__ weights /*[B,2K,H,W]*/, float* __restrict__ masks /*[B,K,H,W]*/,
     float* __restrict__ pseudo_out /*[B,K,H,W] or null*/, float* __restrict__ small_out /*[2][B,K,H,W] or null*/) {
-    pdl_wait();
+    kernel_begin(TR_RETRIFY);
     // grid.y = b*K + k (one plane), grid.x covers the plane: no 64-bit divisions
     const size_t n = (size_t)B * K * H * W;
     const int pixi = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pixi >= H * W) return;
+    if (pixi >= H * W) { trace_exit(TR_RETRIFY); return; }
     const int bk = blockIdx.y;
     const int b = bk / K, k = bk - b * K;
     const int y = pixi / W, x = pixi - y * W;
@@ -157,6 +158,7 @@ __global__ void __launch_bounds__(256) retrify_weights_kernel(
     masks[i] = m ? 2.0f : 0.f;
     if (pseudo_out) pseudo_out[i] = pseudo ? 1.0f : 0.f;
     if (small_out) { small_out[i] = ps; small_out[n + i] = ss; }
+    trace_exit(TR_RETRIFY);
 }
 
 }  // namespace clr

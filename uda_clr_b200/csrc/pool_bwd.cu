@@ -36,13 +36,14 @@ struct BwdDom {
 struct BwdParams {
     BwdDom dom[2];
     int ndom, C, HW, K, nPx, nSpan;
+    int trace_id;
 };
 
 constexpr int kBwdSpan = 32;   // channels per CTA
 
 template <int QT, int VEC>
 __global__ void __launch_bounds__(kThreads, 4) pool_bwd_kernel(const BwdParams p) {
-    pdl_wait();
+    kernel_begin(p.trace_id);
     __shared__ __align__(16) float T[(1 + QT) * kBwdSpan];
     const int tid = threadIdx.x;
     int bid = blockIdx.x;
@@ -103,7 +104,7 @@ __global__ void __launch_bounds__(kThreads, 4) pool_bwd_kernel(const BwdParams p
         }
     }
     __syncthreads();
-    if (!ok) return;
+    if (!ok) { trace_exit(p.trace_id); return; }
 
     float* gp = D.grad + ((size_t)b * p.C + c0) * p.HW + px;
     const int nc = (p.C - c0) < kBwdSpan ? (p.C - c0) : kBwdSpan;
@@ -121,6 +122,7 @@ __global__ void __launch_bounds__(kThreads, 4) pool_bwd_kernel(const BwdParams p
         }
         st_stream<VEC>(gp + (size_t)j * p.HW, o);
     }
+    trace_exit(p.trace_id);
 }
 
 template <int QT>
@@ -146,6 +148,7 @@ int pool_bwd_impl(const BwdDom* doms, int ndom, int C, int HW, int K, cudaStream
         if (Q > Qmax) Qmax = Q;
     }
     BwdParams p{};
+    p.trace_id = tunables().bwd_trace_id ? tunables().bwd_trace_id : TR_BWD_BOTH;
     p.ndom = ndom; p.C = C; p.HW = HW; p.K = K;
     const int pxb = kThreads * (vec4 ? 4 : 1);
     p.nPx = (HW + pxb - 1) / pxb;

@@ -47,6 +47,9 @@ struct PoolParams {
     int nChunk, nGroup;
     int total;
     int stages;       // TMA ring depth
+    int reduce_trace_id;
+    int skip_reduce;               // 1: the caller reduces the partials itself (pool_finish_kernel)
+    unsigned int* counter_reset;   // optional: zeroed by CTA 0 (arms the finish kernel's last-CTA counter)
 };
 
 constexpr int pool_cg(int R) { return (32 / R) < 16 ? (32 / R) : 16; }   // channels per item
@@ -173,7 +176,8 @@ __device__ __forceinline__ void reduce_and_store(float (&acc)[32], const float* 
 // ------------------------------------------------------------------------------------------------
 template <int R, int VEC>
 __global__ void __launch_bounds__(kThreads, 2) pool_fwd_ldg_kernel(const PoolParams p) {
-    pdl_wait();
+    kernel_begin(TR_POOL);
+    if (p.counter_reset && blockIdx.x == 0 && threadIdx.x == 0) *p.counter_reset = 0u;
     constexpr int CG = pool_cg(R), REPS = pool_reps(R), PX = kThreads * VEC * REPS;
     extern __shared__ __align__(16) float smem[];
     float* wsm = smem;                 // [R][PX]
@@ -223,6 +227,7 @@ __global__ void __launch_bounds__(kThreads, 2) pool_fwd_ldg_kernel(const PoolPar
         float* out = D.partial + (size_t)ic.slot * R * (p.C + 1);
         reduce_and_store<R, CG, VEC, REPS>(acc, wsm, red, parity, out, p.C, c0, ic.grp == 0, tid, sync);
     }
+    trace_exit(TR_POOL);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -243,7 +248,8 @@ struct PoolTmaSmem {
 
 template <int R>
 __global__ void __launch_bounds__(kPoolTmaThreads, 1) pool_fwd_tma_kernel(const PoolParams p) {
-    pdl_wait();
+    kernel_begin(TR_POOL);
+    if (p.counter_reset && blockIdx.x == 0 && threadIdx.x == 0) *p.counter_reset = 0u;
     using SM = PoolTmaSmem<R>;
     constexpr int CG = SM::CG, REPS = SM::REPS, PX = SM::PX, VEC = 4;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -334,11 +340,12 @@ __global__ void __launch_bounds__(kPoolTmaThreads, 1) pool_fwd_tma_kernel(const 
         float* out = D.partial + (size_t)ic.slot * R * (p.C + 1);
         reduce_and_store<R, CG, VEC, REPS>(acc, wsm, red, parity, out, p.C, c0, ic.grp == 0, tid, sync);
     }
+    trace_exit(TR_POOL);
 }
 
 // sums[r][c] = sum over (b,chunk) slots of partial[slot][r][c], fp64, fixed order.
 __global__ void __launch_bounds__(256) pool_reduce_kernel(const PoolParams p, int R) {
-    pdl_wait();
+    kernel_begin(p.reduce_trace_id);
     const int d = blockIdx.y;
     const PoolDom& D = p.dom[d];
     const int n = R * (p.C + 1);
@@ -366,12 +373,13 @@ __global__ void __launch_bounds__(256) pool_reduce_kernel(const PoolParams p, in
         for (int i = 0; i < 8; ++i) t += sh[i][threadIdx.x];
         D.sums[col] = (float)t;
     }
+    trace_exit(p.reduce_trace_id);
 }
 
 // Per-sample variant: sums_b[b][r][c] = sum over the chunks of sample b only (bmm-style pooling keeps samples apart).
 __global__ void __launch_bounds__(256) pool_reduce_ps_kernel(const float* __restrict__ partial, int nChunk, int R, int C,
                                                              float* __restrict__ sums_b) {
-    pdl_wait();
+    kernel_begin(TR_OTHER);
     const int b = blockIdx.y, n = R * (C + 1);
     const int col = blockIdx.x * 256 + threadIdx.x;
     if (col >= n) return;
@@ -382,7 +390,7 @@ __global__ void __launch_bounds__(256) pool_reduce_ps_kernel(const float* __rest
 
 // out[r][c] = mean_b S_b[r][c] / (N_b[r] + n_add)      (Trainer_prototype.py:366-368: bmm / (sum + 1), mean over batch)
 __global__ void bmm_finalize_kernel(const float* __restrict__ sums_b, int B, int R, int C, float n_add, float* __restrict__ out) {
-    pdl_wait();
+    kernel_begin(TR_OTHER);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= R * C) return;
     const int r = i / C, c = i - r * C;
@@ -395,7 +403,7 @@ __global__ void bmm_finalize_kernel(const float* __restrict__ sums_b, int B, int
 }
 
 __global__ void proto_finalize_kernel(const float* __restrict__ sums, int R, int C, float* __restrict__ mu) {
-    pdl_wait();
+    kernel_begin(TR_OTHER);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= R * C) return;
     const int r = i / C, c = i - r * C;
@@ -408,6 +416,7 @@ void launch_partial_reduce(const float* partial, int slots, int R, int C, float*
     p.dom[0].partial = const_cast<float*>(partial);
     p.dom[0].sums = sums;
     p.dom[0].slots = slots;
+    p.reduce_trace_id = TR_DISC_REDUCE;
     const int n = R * (C + 1);
     clr::launch_k(pool_reduce_kernel, dim3((n + 31) / 32, 1), dim3(32, 8), 0, st, p, R);
 }
@@ -429,7 +438,7 @@ static int launch_ldg(const PoolParams& p, cudaStream_t st) {
     int grid = device_facts().sms * occ;
     if (grid > p.total) grid = p.total;
     clr::launch_k(kern, grid, kThreads, smem, st, p);
-    launch_reduce(p, R, st);
+    if (!p.skip_reduce) launch_reduce(p, R, st);
     return launch_status();
 }
 
@@ -451,7 +460,7 @@ static int launch_tma(PoolParams p, cudaStream_t st) {
     int grid = device_facts().sms * occ;
     if (grid > p.total) grid = p.total;
     clr::launch_k(kern, grid, kPoolTmaThreads, smem, st, p);
-    launch_reduce(p, R, st);
+    if (!p.skip_reduce) launch_reduce(p, R, st);
     return launch_status();
 }
 
@@ -479,7 +488,8 @@ size_t pool_partial_bytes(int B, int C, int HW, int R) { return sizeof(float) * 
 // R = number of output rows (2K for the prototype formats; any 1..16 for explicit rows).
 int pool_fwd_impl(const float* feat0, const float* w0, int fmt0, int B0, float* sums0,
                   const float* feat1, const float* w1, int fmt1, int B1, float* sums1,
-                  int C, int HW, int R, void* ws, size_t ws_bytes, cudaStream_t st, int keep0, int keep1) {
+                  int C, int HW, int R, void* ws, size_t ws_bytes, cudaStream_t st, int keep0, int keep1,
+                  PoolLayout* skip_reduce_layout, unsigned int* counter_reset) {
     const int ndom = feat1 ? 2 : 1;
     CLR_CHECK_ARG(feat0 && w0 && sums0 && ws && B0 > 0 && C > 0 && HW > 0 && R >= 1 && R <= 2 * CLR_MAX_K);
     CLR_CHECK_ARG(fmt0 == CLR_W_COMPLEMENT || fmt0 == CLR_W_EXPLICIT);
@@ -490,7 +500,7 @@ int pool_fwd_impl(const float* feat0, const float* w0, int fmt0, int B0, float* 
     }
     if (!aligned4(feat0) || !aligned4(w0) || (feat1 && (!aligned4(feat1) || !aligned4(w1)))) return CLR_ERR_ALIGN;
     const bool vec4 = (HW % 4 == 0) && aligned16(feat0) && aligned16(w0) && (!feat1 || (aligned16(feat1) && aligned16(w1)));
-    const bool tma = vec4 && tunables().pool_impl != 1;
+    const bool tma = vec4 && tunables().pool_impl == 2;
     const int vec = vec4 ? 4 : 1;
     const int px = chunk_px(R, vec);
     const int CG = pool_cg(R);
@@ -509,6 +519,14 @@ int pool_fwd_impl(const float* feat0, const float* w0, int fmt0, int B0, float* 
     if (ndom == 2)
         p.dom[1] = PoolDom{feat1, w1, wsf + partial_floats(B0, C, HW, R), sums1, B1, fmt1, (int)items1, B1 * p.nChunk, keep1};
     p.total = (int)(items0 + items1);
+    p.reduce_trace_id = TR_POOL_REDUCE;
+    p.counter_reset = counter_reset;
+    if (skip_reduce_layout) {
+        p.skip_reduce = 1;
+        skip_reduce_layout->partial[0] = p.dom[0].partial; skip_reduce_layout->slots[0] = p.dom[0].slots;
+        skip_reduce_layout->partial[1] = ndom == 2 ? p.dom[1].partial : nullptr;
+        skip_reduce_layout->slots[1] = ndom == 2 ? p.dom[1].slots : 0;
+    }
     return dispatch(R, vec4, tma, p, st);
 }
 

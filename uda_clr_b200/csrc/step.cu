@@ -15,6 +15,7 @@ struct StepWs {
     char* rows;        size_t rows_bytes;
     float* hinge;      size_t hinge_bytes;
     double* cons;      size_t cons_bytes;
+    double* fin;       size_t fin_bytes;     // pool_finish: per-CTA loss partials + the last-CTA counter
     size_t total;
 };
 
@@ -31,12 +32,14 @@ static StepWs carve(const clr_step_args* a) {
     w.rows_bytes = align_up(rows);
     w.hinge_bytes = a->use_disc ? align_up(sizeof(float) * (size_t)clr_disc_partials_cap() * (1 + a->K)) : 0;
     w.cons_bytes = a->use_cons ? align_up(clr_cons_ws_bytes()) : 0;
+    w.fin_bytes = align_up(sizeof(double) * (size_t)pool_finish_max_ctas(a->C) * (2 + CLR_MAX_K) + 64);
     char* base = static_cast<char*>(a->ws);
     size_t off = 0;
     w.pool = base + off; off += w.pool_bytes;
     w.rows = base + off; off += w.rows_bytes;
     w.hinge = reinterpret_cast<float*>(base + off); off += w.hinge_bytes;
     w.cons = reinterpret_cast<double*>(base + off); off += w.cons_bytes;
+    w.fin = reinterpret_cast<double*>(base + off); off += w.fin_bytes;
     w.total = off;
     return w;
 }
@@ -172,17 +175,82 @@ int clr_step_fwd_c(const clr_step_args* a, clr_stream_t stream) {
                              a->use_disc, a->use_cons, a->losses, stream);
 }
 
+// Single-GPU forward: no exchange points, so each partial reduce is folded into the finalize that consumes it
+// (pool_finish_kernel, disc_finish_kernel): 8 launches instead of 10 and two fewer single-CTA latency chains.
 int clr_step_fwd(const clr_step_args* a, clr_stream_t stream) {
-    int rc = clr_step_fwd_a(a, stream);
+    int rc = clr::check_args(a);
     if (rc != CLR_OK) return rc;
-    clr::PendingPack pk{};
-    rc = clr::step_fwd_b_impl(a, stream, &pk, nullptr);
+    if (clr::tunables().finish_off) {     // separate reduce / finalize kernels (the sharded path's kernels), for A/B runs
+        rc = clr_step_fwd_a(a, stream);
+        if (rc != CLR_OK) return rc;
+        clr::PendingPack pk{};
+        rc = clr::step_fwd_b_impl(a, stream, &pk, nullptr);
+        if (rc != CLR_OK) return rc;
+        const float ema0 = a->first_s ? 1.0f : (float)a->decay;
+        return clr::disc_finalize_impl(a->packed2, a->P_s, a->K, a->C, a->npx_global, a->w_disc, ema0, a->grad_scale,
+                                       a->g_s, a->xtab, a->w_intra, a->w_inter, a->w_aug, a->aug_weight,
+                                       a->use_disc, a->use_cons, a->losses, pk.hinge, pk.n_hinge, pk.hinge_stride,
+                                       pk.cons, pk.n_cons, static_cast<cudaStream_t>(stream));
+    }
+    const clr::StepWs w = clr::carve(a);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int HW = a->H * a->W, R = 2 * a->K, C = a->C, K = a->K;
+    if (a->use_retrify) {
+        rc = clr_mc_stats(a->preds, a->T, a->B_t, K, a->Hi, a->Wi, a->std_map, a->pred_mean, stream);
+        if (rc != CLR_OK) return rc;
+        rc = clr_retrify_weights(a->oT_before, a->pred_mean, a->std_map, a->B_t, K, a->H, a->W, a->Hi, a->Wi,
+                                 a->pseudo_thr, a->std_thr, a->wt_retrify, a->masks, nullptr, nullptr, stream);
+        if (rc != CLR_OK) return rc;
+    }
+    float* sums_s = a->packed1;
+    float* sums_t = a->packed1 + (size_t)R * (C + 1);
+    unsigned int* counter = reinterpret_cast<unsigned int*>(w.fin + (size_t)clr::pool_finish_max_ctas(C) * (2 + CLR_MAX_K));
+    clr::PoolLayout lay{};
+    if (a->ev_pool_begin) cudaEventRecord(static_cast<cudaEvent_t>(a->ev_pool_begin), st);
+    rc = clr::pool_fwd_impl(a->xt, clr::target_weights(a), clr::target_fmt(a), a->B_t, sums_t,
+                            a->xs, a->ys, CLR_W_COMPLEMENT, a->B_s, sums_s,
+                            C, HW, R, w.pool, w.pool_bytes, st, 0, 0, &lay, counter);
+    if (a->ev_pool_end) cudaEventRecord(static_cast<cudaEvent_t>(a->ev_pool_end), st);
     if (rc != CLR_OK) return rc;
+    rc = clr::pool_finish_impl(lay.partial[1], lay.slots[1], lay.partial[0], lay.slots[0], sums_s, sums_t, K, C,
+                               a->stored_s, a->stored_t, a->first_s, a->first_t, a->decay, a->w_intra, a->w_inter,
+                               a->P_s, a->P_t, a->g_s, a->g_t, a->use_disc ? a->disc_vec : nullptr,
+                               a->use_disc ? a->disc_beta : nullptr, a->losses, w.fin, counter, st);
+    if (rc != CLR_OK) return rc;
+    int n_cons = 0;
+    if (a->use_cons) {
+        rc = clr::cons_fwd_partials(a->oT, a->oT_aug, a->masks, a->B_t, K, a->Hi, a->Wi, a->H, a->W,
+                                    a->cons_threshold, w.cons, &n_cons, st);
+        if (rc != CLR_OK) return rc;
+    }
     const float ema = a->first_s ? 1.0f : (float)a->decay;
-    return clr::disc_finalize_impl(a->packed2, a->P_s, a->K, a->C, a->npx_global, a->w_disc, ema, a->grad_scale,
+    const double* cons = a->use_cons ? w.cons : nullptr;
+    if (a->use_disc && clr::tunables().disc_impl != 1) {
+        float* partial = reinterpret_cast<float*>(w.rows);
+        float* hinge = partial + (size_t)320 * K * (C + 1);   // layout of clr_disc_fused_ws_bytes: [320][K][C+1] | [320]
+        int n_hinge = 320;
+        rc = clr::disc_fused_impl(a->xs, a->ys, a->B_s, C, HW, K, a->disc_vec, a->disc_beta, a->margin,
+                                  a->disc_coef, nullptr, partial, hinge, &n_hinge, st);
+        if (rc == CLR_OK)
+            return clr::disc_finish_impl(partial, n_hinge, a->packed2, a->P_s, K, C, a->npx_global, a->w_disc, ema,
+                                         a->grad_scale, a->g_s, a->xtab, a->w_intra, a->w_inter, a->w_aug, a->aug_weight,
+                                         a->use_cons, a->losses, hinge, n_hinge, 1, cons, n_cons, st);
+        if (rc != CLR_ERR_UNSUPPORTED) return rc;
+    }
+    int n_hinge = 0;
+    if (a->use_disc) {
+        // two-pass form: per-pixel dots (read 1), then pooling of xs with the coefficient planes (read 2)
+        rc = clr::disc_fwd_impl(a->xs, a->ys, a->B_s, C, HW, K, a->disc_vec, a->disc_beta, a->margin,
+                                a->disc_coef, nullptr, w.hinge, clr_disc_partials_cap(), &n_hinge, st);
+        if (rc != CLR_OK) return rc;
+        rc = clr::pool_fwd_impl(a->xs, a->disc_coef, CLR_W_EXPLICIT, a->B_s, a->packed2, nullptr, nullptr, 0, 0, nullptr,
+                                C, HW, K, w.rows, w.rows_bytes, st);
+        if (rc != CLR_OK) return rc;
+    }
+    return clr::disc_finalize_impl(a->packed2, a->P_s, K, C, a->npx_global, a->w_disc, ema, a->grad_scale,
                                    a->g_s, a->xtab, a->w_intra, a->w_inter, a->w_aug, a->aug_weight,
-                                   a->use_disc, a->use_cons, a->losses, pk.hinge, pk.n_hinge, pk.hinge_stride,
-                                   pk.cons, pk.n_cons, static_cast<cudaStream_t>(stream));
+                                   a->use_disc, a->use_cons, a->losses, a->use_disc ? w.hinge : nullptr, n_hinge, 1 + K,
+                                   cons, n_cons, st);
 }
 
 namespace clr {
@@ -214,7 +282,9 @@ int clr_step_run(const clr_step_args* a, clr_stream_t stream) {
     if (rc != CLR_OK) return rc;
     clr_bwd_dom d[2];
     clr::bwd_doms(a, d);
+    clr::tunables().bwd_trace_id = clr::TR_BWD_T;
     rc = clr_pool_bwd_multi(&d[1], 1, C, HW, K, aux);    // d total / d xt needs only g_t: overlaps the discriminative pass
+    clr::tunables().bwd_trace_id = 0;
     if (rc != CLR_OK) return rc;
     CLR_RETURN_IF_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(a->ev_join), aux));
     CLR_RETURN_IF_CUDA(cudaStreamWaitEvent(st, static_cast<cudaEvent_t>(a->ev_join), 0));
@@ -225,7 +295,9 @@ int clr_step_run(const clr_step_args* a, clr_stream_t stream) {
                                  pk.cons, pk.n_cons, st);
     if (rc != CLR_OK) return rc;
     if (a->ev_bwd_begin) cudaEventRecord(static_cast<cudaEvent_t>(a->ev_bwd_begin), st);
+    clr::tunables().bwd_trace_id = clr::TR_BWD_S;
     rc = clr_pool_bwd_multi(&d[0], 1, C, HW, K, stream);
+    clr::tunables().bwd_trace_id = 0;
     if (a->ev_bwd_end) cudaEventRecord(static_cast<cudaEvent_t>(a->ev_bwd_end), st);
     if (rc != CLR_OK) return rc;
     if (a->use_cons && a->w_aug != 0.f && a->g_oT_aug) {
