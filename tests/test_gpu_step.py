@@ -377,3 +377,20 @@ def test_merged_finish_kernels_equal_separate_kernels(K, C, H):
         assert relerr(x.cpu().numpy(), y.cpu().numpy()) < 2e-6
     for x, y in zip(res[0], res[2]):
         assert torch.equal(x, y)
+    # the finish bodies riding with the consistency pass / the target-gradient write (default) vs launched on their own
+    try:
+        _lib.check(lib.clr_set_tunable(b"hfuse_off", 1), "hfuse_off")
+        step = clr.CLRStep(K=K, retrify=True, use_disc=True, use_cons=True, backprop_aug=True)
+        plan = step.plan(t["xs"], t["ys"], t["xt"], oT_before=t["oT_before"], preds=t["preds"], T=4, oT=t["oT"],
+                         oT_aug=t["oT_aug"], epoch=1.0)
+        for _ in range(2):
+            plan.run()
+        torch.cuda.synchronize()
+        o = plan.outputs()
+        alone = [plan.losses.clone(), plan.gxs.clone(), plan.gxt.clone(), plan.g_oT_aug.clone(),
+                 torch.cat([p.reshape(-1) for p in o.source_prototypes]),
+                 torch.cat([p.reshape(-1) for p in o.target_prototypes])]
+    finally:
+        lib.clr_set_tunable(b"hfuse_off", 0)
+    for x, y in zip(res[0], alone):
+        assert torch.equal(x, y)

@@ -50,6 +50,7 @@ int clr_set_tunable(const char* name, int value) {
     else if (!strcmp(name, "pdl_off")) t.pdl_off = value;
     else if (!strcmp(name, "overlap_off")) t.overlap_off = value;
     else if (!strcmp(name, "finish_off")) t.finish_off = value;
+    else if (!strcmp(name, "hfuse_off")) t.hfuse_off = value;
     else return CLR_ERR_BAD_ARG;
     return CLR_OK;
 }
@@ -75,7 +76,7 @@ int clr_trace_slots(void) { return clr::kTraceSlots; }
 const char* clr_trace_name(int slot) {
     static const char* names[clr::kTraceSlots] = {"mc_stats", "retrify_weights", "pool_fwd", "pool_reduce", "align_finalize",
         "cons_fwd", "disc_fused", "disc_reduce", "disc_finalize", "pool_bwd_target", "pool_bwd_source", "pool_bwd_both",
-        "cons_bwd", "step_pack", "other", ""};
+        "cons_bwd", "step_pack", "other", "", "dbg0", "dbg1", "dbg2", "dbg3", "dbg4", "dbg5", "dbg6", "dbg7"};
     return (slot >= 0 && slot < clr::kTraceSlots) ? names[slot] : "";
 }
 int clr_trace_read(unsigned long long* out_host) {

@@ -39,6 +39,7 @@ struct Tunables {
     int overlap_off;   // 1 = clr_step_run ignores aux_stream (serial order)
     int mc_precise;    // 1 = ATen-exact sigmoids in clr_mc_stats (slower), 0 = fast intrinsics
     int finish_off;    // 1 = single-GPU step uses the separate reduce / finalize kernels instead of the merged finish kernels
+    int hfuse_off;     // 1 = finish bodies get launches of their own instead of riding with cons / the target-gradient write
     void* trace_buf;   // device TraceRec[kTraceSlots] or NULL (clr_trace_set): device-side timeline of the kernels
     int bwd_trace_id;  // trace slot of the next pool_bwd launch (set by the step orchestration)
 };
@@ -61,7 +62,8 @@ void count_launch();
 // serialises kernels and event records break programmatic dependent launch.
 struct TraceRec { unsigned long long t_first, t_ready, t_last, n_cta; };
 enum TraceId { TR_MC_STATS = 0, TR_RETRIFY, TR_POOL, TR_POOL_REDUCE, TR_ALIGN, TR_CONS, TR_DISC, TR_DISC_REDUCE,
-               TR_DISC_FIN, TR_BWD_T, TR_BWD_S, TR_BWD_BOTH, TR_CONS_BWD, TR_PACK, TR_OTHER, kTraceSlots = 16 };
+               TR_DISC_FIN, TR_BWD_T, TR_BWD_S, TR_BWD_BOTH, TR_CONS_BWD, TR_PACK, TR_OTHER, TR_DBG0 = 16, TR_DBG1, TR_DBG2, TR_DBG3, TR_DBG4, TR_DBG5,
+               TR_DBG6, TR_DBG7, kTraceSlots = 24 };
 static __device__ TraceRec* g_trace_dev = nullptr;     // one copy per translation unit, installed by launch_k
 __device__ __forceinline__ unsigned long long global_ns() {
     unsigned long long t;
@@ -80,6 +82,12 @@ __device__ __forceinline__ void trace_ready(int id) {
 __device__ __forceinline__ void trace_exit(int id) {
     TraceRec* t = g_trace_dev;
     if (t && trace_leader()) atomicMax(&t[id].t_last, global_ns());
+}
+// phase marks for ad-hoc instrumentation of one kernel (slots TR_DBG*): first / last time any CTA passed the mark
+__device__ __forceinline__ void trace_mark(int id) {
+    TraceRec* t = g_trace_dev;
+    if (t && trace_leader()) { const unsigned long long now = global_ns(); atomicMin(&t[id].t_first, now); atomicMin(&t[id].t_ready, now);
+                               atomicMax(&t[id].t_last, now); atomicAdd(&t[id].n_cta, 1ull); }
 }
 // kernel prologue: stamp; let the NEXT kernel of the stream start launching right away (its CTAs become resident as
 // ours retire and park in their own griddepcontrol.wait, so launch latency and CTA ramp-up leave the critical path --

@@ -1,0 +1,257 @@
+// "Finish" stages of the single-GPU fused step: per-CTA partial reduce + the O(K*C) finalize arithmetic in ONE body
+// each (no exchange point sits between reduce and finalize when nothing is sharded).  They are latency chains, not
+// bandwidth, so the fused step never gives them a launch of their own: the bodies are co-scheduled as the first few
+// CTAs of the streaming kernel that follows them in the step and does not depend on them --
+//   pool_finish_body  rides with the consistency pass      (cons.cu:     pool_finish_cons_kernel)
+//   disc_finish_body  rides with the target-gradient write (pool_bwd.cu: bwd_finish_kernel)
+// -- which takes both chains (and two kernel boundaries) off the step's critical path.  finalize.cu also launches them
+// stand-alone.  Both bodies are written for exactly kThreads (256) threads and any K <= CLR_MAX_K.
+//
+// Arithmetic = align_finalize_kernel / disc_finalize_kernel (finalize.cu), i.e. Trainer_prototype_full.py:335-355,
+// 378-398, 428-449 and the Trainer_prototype_mt bytecode L454-474.
+#pragma once
+#include "clr_common.cuh"
+
+namespace clr {
+
+// Block-wide sums of NV doubles at once (one barrier): result valid in THREAD 0 only.
+template <int NV>
+__device__ __forceinline__ void block_sum_n(double (&v)[NV], double* sh /*[NV][32]*/) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) sh[i * 32 + warp] = v[i];
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) v[i] = warp_sum(lane < nw ? sh[i * 32 + lane] : 0.0);
+    }
+}
+
+// packed2 layout: [K][C+1] active-set sums (col C = n_k) | loss numerator | cons num | cons den | pad
+struct PackSrc {   // per-CTA partials still to be summed (single-GPU path: no exchange between pack and finalize)
+    const float* hinge; int n_hinge, hinge_stride;
+    const double* cons; int n_cons;
+};
+
+// Sum of col[(sl + i*step) * stride] over the slots in [.., s_end): rounds of U predicated loads, all in flight at once
+// (a plain remainder loop would serialise one L2 round trip per slot); fp64 accumulation in slot order.
+template <int U>
+__device__ __forceinline__ double strided_slot_sum(const float* __restrict__ col, int sl, int s_end, size_t stride, int step) {
+    double s = 0.0;
+    for (; sl < s_end; sl += U * step) {
+        float v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[u] = (sl + u * step < s_end) ? __ldcg(col + (size_t)(sl + u * step) * stride) : 0.f;
+#pragma unroll
+        for (int u = 0; u < U; ++u) s += (double)v[u];
+    }
+    return s;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// pool finish: CTA = 8 channels.  Warp w takes the (domain d, row r) pairs w, w+8, ..: it reduces the column block
+// [c0, c0+8) of partial[d][slot][r][.] over the slots with 4 slot-lanes per channel (fp64, fixed order) plus the pair's
+// weight-sum column; then K*8 threads do the align_finalize arithmetic for the CTA's channels; the loss terms are
+// combined across CTAs by the last CTA to finish (per-CTA fp64 partials summed in a fixed order -> deterministic).
+// `counter` is zeroed by the pooling kernel of the same step (stream order), so no initialisation contract leaks out.
+// ---------------------------------------------------------------------------------------------------------------
+struct PoolFinishParams {
+    const float* partial[2];   // [slots][R][C+1]   (0 = source, 1 = target)
+    float* sums[2];            // packed sums out
+    float* stored[2];
+    float* P[2];
+    float* g[2];
+    int slots[2];
+    int first[2];
+    int K, C;
+    float d, omd, w_intra, w_inter;
+    float* disc_vec;
+    float* disc_beta;
+    float* losses;
+    double* loss_partial;      // [ctas][2 + CLR_MAX_K]
+    unsigned int* counter;
+};
+static inline int pool_finish_ctas(int C) { return (C + 7) / 8; }
+
+__device__ __forceinline__ void pool_finish_body(const PoolFinishParams& p, const int cta, const int ncta) {
+    constexpr int NL = 2 + CLR_MAX_K;
+    const int K = p.K, R = 2 * K, C = p.C, n = R * (C + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ch = lane >> 2, sl0 = lane & 3;
+    const int c = cta * 8 + ch;
+    __shared__ float S[2][2 * CLR_MAX_K][8];
+    __shared__ float Nn[2][2 * CLR_MAX_K];
+    __shared__ double lp[8 * CLR_MAX_K][NL];
+    __shared__ bool is_last;
+    for (int pair = warp; pair < 2 * R; pair += kWarps) {
+        const int d = pair / R, r = pair - d * R;
+        const float* part = p.partial[d];
+        const int slots = p.slots[d];
+        double s = 0.0;
+        if (c < C) s = strided_slot_sum<8>(part + (size_t)r * (C + 1) + c, sl0, slots, (size_t)n, 4);
+        double nn = strided_slot_sum<4>(part + (size_t)r * (C + 1) + C, lane, slots, (size_t)n, 32);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        nn = warp_sum(nn);
+        if (sl0 == 0 && c < C) { S[d][r][ch] = (float)s; p.sums[d][(size_t)r * (C + 1) + c] = (float)s; }
+        if (lane == 0) { Nn[d][r] = (float)nn; if (cta == 0) p.sums[d][(size_t)r * (C + 1) + C] = (float)nn; }
+    }
+    __syncthreads();
+    if (tid < K * 8) {
+        const int k = tid >> 3, j = tid & 7, cc = cta * 8 + j;
+        double acc[NL];
+#pragma unroll
+        for (int i = 0; i < NL; ++i) acc[i] = 0.0;
+        if (cc < C) {
+            const float dd = p.d, omd = p.omd, invC = 1.0f / (float)C;
+            const float ds = p.first[0] ? 1.f : dd, dt = p.first[1] ? 1.f : dd;
+            float ps[2], pt[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int rr = k + h * K;
+                const size_t e = (size_t)rr * C + cc;
+                const float cs = S[0][rr][j] / Nn[0][rr];                         // utils/Utils.py:127-130
+                const float ct = S[1][rr][j] / Nn[1][rr];
+                ps[h] = p.first[0] ? cs : __fadd_rn(__fmul_rn(omd, p.stored[0][e]), __fmul_rn(dd, cs));
+                pt[h] = p.first[1] ? ct : __fadd_rn(__fmul_rn(omd, p.stored[1][e]), __fmul_rn(dd, ct));
+                p.P[0][e] = ps[h]; p.P[1][e] = pt[h];
+                p.stored[0][e] = ps[h]; p.stored[1][e] = pt[h];                  // .detach() copies (Trainer_prototype_full.py:341-344)
+                const double df = (double)ps[h] - (double)pt[h];
+                acc[0] += df * df;
+            }
+            const float dob = ps[0] - ps[1];
+            acc[1] += (double)dob * dob;
+            const float gsep = ds * p.w_inter * 2.0f * dob * invC;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const size_t e = (size_t)(k + h * K) * C + cc;
+                const float gi = p.w_intra * 2.0f * (ps[h] - pt[h]) * invC;
+                p.g[0][e] = ds * gi + (h == 0 ? gsep : -gsep);
+                p.g[1][e] = -dt * gi;
+            }
+            if (p.disc_vec) p.disc_vec[(size_t)k * C + cc] = dob;
+#pragma unroll
+            for (int kk = 0; kk < CLR_MAX_K; ++kk)
+                if (kk == k) acc[2 + kk] = (double)ps[0] * ps[0] - (double)ps[1] * ps[1];
+        }
+#pragma unroll
+        for (int i = 0; i < NL; ++i) lp[tid][i] = acc[i];
+    }
+    __syncthreads();
+    if (tid < NL) {
+        double t = 0.0;
+        for (int e = 0; e < K * 8; ++e) t += lp[e][tid];
+        __stcg(p.loss_partial + (size_t)cta * NL + tid, t);
+        __threadfence();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned prev = atomicAdd(p.counter, 1u);
+        is_last = (prev == (unsigned)ncta - 1u);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        // warp i sums value i over the CTAs: lanes take CTAs lane, lane+32, .. (loads in flight together), fixed order
+        for (int i = warp; i < 2 + K; i += kWarps) {
+            double t = 0.0;
+            for (int b = lane; b < ncta; b += 32) t += __ldcg(p.loss_partial + (size_t)b * NL + i);
+            t = warp_sum(t);
+            if (lane == 0) {
+                const float val = (float)(t * (1.0 / (double)C));
+                if (i < 2) p.losses[i] = val;
+                else if (p.disc_beta) p.disc_beta[i - 2] = val;
+            }
+        }
+        if (tid == 0) *p.counter = 0u;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// disc finish: CTA = 8 channels.  Warp w takes the (class k, slot quarter q) pairs w, w+8, ..: it reduces the per-CTA
+// partials of the fused discriminative kernel ([slots][K][C+1]) for the CTA's channels; then K*8 threads apply the
+// disc_finalize arithmetic.  One extra (last) CTA owns no channels: it folds the hinge / consistency per-CTA partials
+// into the loss tail and writes the step totals.  No cross-CTA step.
+// ---------------------------------------------------------------------------------------------------------------
+struct DiscFinishParams {
+    const float* partial; int slots;
+    float* packed2; const float* P_s; float* g_s; float* xtab; float* losses;
+    int K, C;
+    double npx;
+    float coef;       // 2 / (C * npx)
+    float w_disc, ema_factor, gscale, w_intra, w_inter, w_aug, aug_weight;
+    int use_cons;
+    PackSrc ps;
+};
+static inline int disc_finish_ctas(int C) { return (C + 7) / 8 + 1; }
+
+__device__ __forceinline__ void disc_finish_body(const DiscFinishParams& p, const int cta, const int ncta) {
+    const int K = p.K, C = p.C, n = K * (C + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ch = lane >> 2, sl0 = lane & 3;
+    const int c = cta * 8 + ch;
+    __shared__ double Sq[CLR_MAX_K][4][8];
+    __shared__ double Nq[CLR_MAX_K][4];
+    __shared__ double shp[3 * 32];
+    const bool loss_cta = cta == ncta - 1;
+    const int per = (p.slots + 3) / 4;
+    if (!loss_cta) {
+        for (int pair = warp; pair < 4 * K; pair += kWarps) {
+            const int k = pair >> 2, q = pair & 3;
+            const int s_begin = q * per, s_end = (s_begin + per) < p.slots ? (s_begin + per) : p.slots;
+            double s = 0.0;
+            if (c < C) s = strided_slot_sum<10>(p.partial + (size_t)k * (C + 1) + c, s_begin + sl0, s_end, (size_t)n, 4);
+            double nn = strided_slot_sum<4>(p.partial + (size_t)k * (C + 1) + C, s_begin + lane, s_end, (size_t)n, 32);
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            nn = warp_sum(nn);
+            if (sl0 == 0) Sq[k][q][ch] = s;
+            if (lane == 0) Nq[k][q] = nn;
+        }
+        __syncthreads();
+        if (tid < K * 8) {
+            const int kk = tid >> 3, j = tid & 7, cc = cta * 8 + j;
+            const float nk = (float)(((Nq[kk][0] + Nq[kk][1]) + Nq[kk][2]) + Nq[kk][3]);
+            if (cc < C) {
+                const float A = (float)(((Sq[kk][0][j] + Sq[kk][1][j]) + Sq[kk][2][j]) + Sq[kk][3][j]);
+                p.packed2[(size_t)kk * (C + 1) + cc] = A;
+                const float po = p.P_s[(size_t)kk * C + cc], pb = p.P_s[(size_t)(K + kk) * C + cc];
+                p.g_s[(size_t)kk * C + cc] += p.ema_factor * p.w_disc * p.coef * (nk * po - A);
+                p.g_s[(size_t)(K + kk) * C + cc] -= p.ema_factor * p.w_disc * p.coef * (nk * pb - A);
+                p.xtab[(size_t)kk * C + cc] = -p.gscale * p.w_disc * p.coef * (po - pb);
+            }
+            if (cta == 0 && j == 0) p.packed2[(size_t)kk * (C + 1) + C] = nk;
+        }
+        return;
+    }
+    // ---- the loss CTA ----
+    double v[3] = {0.0, 0.0, 0.0};
+    if (p.ps.hinge) v[0] = strided_slot_sum<4>(p.ps.hinge, tid, p.ps.n_hinge, (size_t)p.ps.hinge_stride, kThreads);
+    if (p.ps.cons) {
+        const double2* c2 = reinterpret_cast<const double2*>(p.ps.cons);
+        for (int i = tid; i < p.ps.n_cons; i += 4 * kThreads) {
+            double2 t[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) t[u] = (i + u * kThreads < p.ps.n_cons) ? __ldcg(c2 + i + u * kThreads) : make_double2(0.0, 0.0);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { v[1] += t[u].x; v[2] += t[u].y; }
+        }
+    }
+    block_sum_n<3>(v, shp);
+    if (tid == 0) {
+        float* tail = p.packed2 + (size_t)K * (C + 1);
+        tail[0] = (float)v[0]; tail[1] = (float)v[1]; tail[2] = (float)v[2]; tail[3] = 0.f;
+        const float disc = (float)((double)(float)v[0] / p.npx);
+        const float aug = p.use_cons ? (float)((double)(float)v[1] / (double)(float)v[2] * (double)p.aug_weight) : 0.f;
+        p.losses[2] = disc;
+        p.losses[3] = aug;
+        p.losses[4] = p.w_intra * p.losses[0] + p.w_inter * p.losses[1] + p.w_disc * disc + p.w_aug * aug;
+        p.losses[5] = 0.f; p.losses[6] = 0.f; p.losses[7] = 0.f;
+    }
+}
+
+}  // namespace clr

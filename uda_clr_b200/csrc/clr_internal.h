@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stddef.h>
+#include "clr_b200.h"
 
 namespace clr {
 
@@ -23,8 +24,10 @@ int disc_fwd_impl(const float* xs, const float* ys, int B, int C, int HW, int K,
                   const float* disc_vec, const float* disc_beta, float margin,
                   float* coef, float* delta, float* partials, int partials_cap, int* nparts, cudaStream_t st);
 
+struct PoolFinishParams;
 int cons_fwd_partials(const float* oT, const float* oT_aug, const float* masks, int B, int K, int Hi, int Wi,
-                      int H, int W, float threshold, double* partial, int* nblocks, cudaStream_t st);
+                      int H, int W, float threshold, double* partial, int* nblocks, cudaStream_t st,
+                      const PoolFinishParams* fused_finish = nullptr);
 
 void launch_step_pack(const float* hinge_partials, int n_hinge, int hinge_stride,
                       const double* cons_partials, int n_cons, float* tail, cudaStream_t st);
@@ -36,17 +39,13 @@ int disc_finalize_impl(float* packed2, const float* P_s, int K, int C, double np
                        float* losses, const float* hinge, int n_hinge, int hinge_stride,
                        const double* cons, int n_cons, cudaStream_t stream);
 
-// Single-GPU fused step: partial reduce + finalize in one launch each (finalize.cu).
-int pool_finish_impl(const float* partial_s, int slots_s, const float* partial_t, int slots_t, float* sums_s, float* sums_t,
-                     int K, int C, float* stored_s, float* stored_t, int first_s, int first_t, double decay,
-                     float w_intra, float w_inter, float* P_s, float* P_t, float* g_s, float* g_t,
-                     float* disc_vec, float* disc_beta, float* losses, double* loss_partial, unsigned int* counter,
-                     cudaStream_t st);
-int pool_finish_max_ctas(int C);
-int disc_finish_impl(const float* partial, int slots, float* packed2, const float* P_s, int K, int C, double npx,
-                     float w_disc, float ema_factor, float gscale, float* g_s, float* xtab,
-                     float w_intra, float w_inter, float w_aug, float aug_weight, int use_cons, float* losses,
-                     const float* hinge, int n_hinge, int hinge_stride, const double* cons, int n_cons, cudaStream_t st);
+// Single-GPU fused step: merged reduce + finalize bodies (clr_finish.cuh), launched stand-alone (finalize.cu) or riding
+// with the consistency pass (cons.cu) / the target-gradient write (pool_bwd.cu).
+struct PoolFinishParams;
+struct DiscFinishParams;
+int pool_finish_launch(const PoolFinishParams& p, cudaStream_t st);
+int disc_finish_launch(const DiscFinishParams& p, cudaStream_t st);
+int pool_bwd_with_finish(const clr_bwd_dom* dom, int C, int HW, int K, const DiscFinishParams& f, cudaStream_t st);
 
 // Where pool_fwd_impl left its per-(b,chunk) partials (for callers that reduce them themselves).
 struct PoolLayout { const float* partial[2]; int slots[2]; };

@@ -11,6 +11,7 @@
 // Bound: HBM; algorithmic bytes fwd = 2*4*B*K*Hi*Wi (+masks), bwd = 2 reads + 1 write of the same size.
 #include "clr_common.cuh"
 #include "clr_internal.h"
+#include "clr_finish.cuh"
 
 namespace clr {
 
@@ -84,20 +85,27 @@ constexpr int kConsThreads = 256;
 // capacity (no partial last wave -- the 2-D grid this replaces ran 2.3 waves), every thread keeps U = 4 independent
 // 128-bit load pairs in flight, and the (plane, row, column) of a vector costs two shifts (two 32-bit divisions when
 // the image size is not a power of two).
+struct ConsArgs {
+    const float* oT; const float* oT_aug; const float* masks;
+    ConsGeom g; LabelRule thr;
+    double* partial;                                   // forward: [ctas][2] per-CTA { sum m*l, sum m }
+    const float* stats; const float* gscale_dev; float gscale; float* grad;    // backward
+};
+
+// `cta` of `ncta` CTAs (the body may share a launch with other work, see pool_finish_cons_kernel)
 template <int VEC, bool BWD>
-__global__ void __launch_bounds__(kConsThreads, 4) cons_kernel(const float* __restrict__ oT, const float* __restrict__ oT_aug,
-                                                            const float* __restrict__ masks, ConsGeom g, LabelRule thr,
-                                                            double* __restrict__ partial,
-                                                            const float* __restrict__ stats, const float* __restrict__ gscale_dev,
-                                                            float gscale, float* __restrict__ grad) {
-    kernel_begin(BWD ? TR_CONS_BWD : TR_CONS);
+__device__ __forceinline__ void cons_body(const ConsArgs& a, const unsigned cta, const unsigned ncta) {
+    const float* __restrict__ oT = a.oT; const float* __restrict__ oT_aug = a.oT_aug; const float* __restrict__ masks = a.masks;
+    const ConsGeom& g = a.g; const LabelRule& thr = a.thr;
+    double* __restrict__ partial = a.partial; const float* __restrict__ stats = a.stats;
+    const float* __restrict__ gscale_dev = a.gscale_dev; const float gscale = a.gscale; float* __restrict__ grad = a.grad;
     const bool shared_mask = (g.Wi == VEC * g.W);    // exact VEC:1 upsampling: a vector shares one mask pixel
     float coef = 0.f;
     if (BWD) coef = (gscale_dev ? gscale * __ldg(gscale_dev) : gscale) / __ldg(stats + 1);
     float num = 0.f, den = 0.f;
     constexpr int U = 4;
-    const unsigned nthreads = gridDim.x * kConsThreads;
-    for (unsigned v0 = blockIdx.x * kConsThreads + threadIdx.x; v0 < g.total_vec; v0 += U * nthreads) {
+    const unsigned nthreads = ncta * kConsThreads;
+    for (unsigned v0 = cta * kConsThreads + threadIdx.x; v0 < g.total_vec; v0 += U * nthreads) {
         Pack<VEC> zt[U], za[U];
         const float* mrow[U];
         unsigned xv[U];
@@ -141,13 +149,34 @@ __global__ void __launch_bounds__(kConsThreads, 4) cons_kernel(const float* __re
         if (lane == 0) { sh[0][warp] = dn; sh[1][warp] = dd; }
         __syncthreads();
         if (threadIdx.x == 0) {
-            double a = 0.0, b = 0.0;
-            for (int w = 0; w < kConsThreads / 32; ++w) { a += sh[0][w]; b += sh[1][w]; }
-            partial[2 * blockIdx.x] = a;
-            partial[2 * blockIdx.x + 1] = b;
+            double sa = 0.0, sb = 0.0;
+            for (int w = 0; w < kConsThreads / 32; ++w) { sa += sh[0][w]; sb += sh[1][w]; }
+            partial[2 * cta] = sa;
+            partial[2 * cta + 1] = sb;
         }
     }
+}
+
+template <int VEC, bool BWD>
+__global__ void __launch_bounds__(kConsThreads, 4) cons_kernel(const ConsArgs a) {
+    kernel_begin(BWD ? TR_CONS_BWD : TR_CONS);
+    cons_body<VEC, BWD>(a, blockIdx.x, gridDim.x);
     trace_exit(BWD ? TR_CONS_BWD : TR_CONS);
+}
+
+// Horizontal fusion for the fused step: CTAs [0, n_fin) run the pooling finish (partial reduce + EMA + alignment losses:
+// a latency chain of a few KB) while the remaining CTAs stream the consistency pass, which does not depend on it.
+template <int VEC>
+__global__ void __launch_bounds__(kConsThreads, 4) pool_finish_cons_kernel(const PoolFinishParams f, const int n_fin, const ConsArgs a) {
+    if ((int)blockIdx.x < n_fin) {
+        kernel_begin(TR_ALIGN);
+        pool_finish_body(f, blockIdx.x, n_fin);
+        trace_exit(TR_ALIGN);
+    } else {
+        kernel_begin(TR_CONS);
+        cons_body<VEC, false>(a, blockIdx.x - n_fin, gridDim.x - n_fin);
+        trace_exit(TR_CONS);
+    }
 }
 
 __global__ void __launch_bounds__(256) cons_final_kernel(const double* __restrict__ partial, int nblk, float aug_weight,
@@ -201,16 +230,25 @@ static int cons_grid(const ConsGeom& g, int& grid) {
 }
 
 int cons_fwd_partials(const float* oT, const float* oT_aug, const float* masks, int B, int K, int Hi, int Wi,
-                      int H, int W, float threshold, double* partial, int* nblocks, cudaStream_t st) {
+                      int H, int W, float threshold, double* partial, int* nblocks, cudaStream_t st,
+                      const PoolFinishParams* fused_finish) {
     const bool vec4 = (Wi % 4 == 0) && aligned16(oT) && aligned16(oT_aug);
-    ConsGeom g;
-    int rc = make_geom(B, K, Hi, Wi, H, W, vec4 ? 4 : 1, g);
+    ConsArgs a{};
+    int rc = make_geom(B, K, Hi, Wi, H, W, vec4 ? 4 : 1, a.g);
     if (rc != CLR_OK) return rc;
     int grid = 1;
-    rc = vec4 ? cons_grid<4, false>(g, grid) : cons_grid<1, false>(g, grid);
+    rc = vec4 ? cons_grid<4, false>(a.g, grid) : cons_grid<1, false>(a.g, grid);
     if (rc != CLR_OK) return rc;
-    if (vec4) launch_k(cons_kernel<4, false>, grid, kConsThreads, 0, st, oT, oT_aug, masks, g, make_rule(threshold), partial, nullptr, nullptr, 0.f, nullptr);
-    else launch_k(cons_kernel<1, false>, grid, kConsThreads, 0, st, oT, oT_aug, masks, g, make_rule(threshold), partial, nullptr, nullptr, 0.f, nullptr);
+    a.oT = oT; a.oT_aug = oT_aug; a.masks = masks; a.thr = make_rule(threshold); a.partial = partial;
+    if (fused_finish) {
+        const int n_fin = pool_finish_ctas(fused_finish->C);
+        if (grid > n_fin + 1) grid -= n_fin;          // keep the launch at one resident wave
+        if (vec4) launch_k(pool_finish_cons_kernel<4>, n_fin + grid, kConsThreads, 0, st, *fused_finish, n_fin, a);
+        else launch_k(pool_finish_cons_kernel<1>, n_fin + grid, kConsThreads, 0, st, *fused_finish, n_fin, a);
+    } else {
+        if (vec4) launch_k(cons_kernel<4, false>, grid, kConsThreads, 0, st, a);
+        else launch_k(cons_kernel<1, false>, grid, kConsThreads, 0, st, a);
+    }
     *nblocks = grid;
     return launch_status();
 }
@@ -227,7 +265,7 @@ int clr_cons_fwd(const float* oT, const float* oT_aug, const float* masks, int B
     if (ws_bytes < clr_cons_ws_bytes()) return CLR_ERR_WORKSPACE;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int blocks = 0;
-    const int rc = clr::cons_fwd_partials(oT, oT_aug, masks, B, K, Hi, Wi, H, W, threshold, static_cast<double*>(ws), &blocks, st);
+    const int rc = clr::cons_fwd_partials(oT, oT_aug, masks, B, K, Hi, Wi, H, W, threshold, static_cast<double*>(ws), &blocks, st, nullptr);
     if (rc != CLR_OK) return rc;
     clr::launch_k(clr::cons_final_kernel, 1, 256, 0, st, static_cast<const double*>(ws), blocks, aug_weight, stats);
     return clr::launch_status();
@@ -246,8 +284,9 @@ int clr_cons_bwd(const float* oT, const float* oT_aug, const float* masks, int B
     int grid = 1;
     rc = vec4 ? clr::cons_grid<4, true>(g, grid) : clr::cons_grid<1, true>(g, grid);
     if (rc != CLR_OK) return rc;
-    if (vec4) clr::launch_k(clr::cons_kernel<4, true>, grid, clr::kConsThreads, 0, st, oT, oT_aug, masks, g, clr::make_rule(threshold), nullptr, stats, gscale_dev, gscale * aug_weight, grad_oT_aug);
-    else clr::launch_k(clr::cons_kernel<1, true>, grid, clr::kConsThreads, 0, st, oT, oT_aug, masks, g, clr::make_rule(threshold), nullptr, stats, gscale_dev, gscale * aug_weight, grad_oT_aug);
+    clr::ConsArgs a{oT, oT_aug, masks, g, clr::make_rule(threshold), nullptr, stats, gscale_dev, gscale * aug_weight, grad_oT_aug};
+    if (vec4) clr::launch_k(clr::cons_kernel<4, true>, grid, clr::kConsThreads, 0, st, a);
+    else clr::launch_k(clr::cons_kernel<1, true>, grid, clr::kConsThreads, 0, st, a);
     return clr::launch_status();
 }
 

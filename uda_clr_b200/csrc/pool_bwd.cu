@@ -15,6 +15,8 @@
 //            is read as a warp-wide broadcast; one 128-bit evict-first store per channel.
 //   grid   = every CTA writes the same 128 KB, all are short; no persistent scheduling needed.
 #include "clr_common.cuh"
+#include "clr_internal.h"
+#include "clr_finish.cuh"
 
 namespace clr {
 
@@ -42,11 +44,9 @@ struct BwdParams {
 constexpr int kBwdSpan = 32;   // channels per CTA
 
 template <int QT, int VEC>
-__global__ void __launch_bounds__(kThreads, 4) pool_bwd_kernel(const BwdParams p) {
-    kernel_begin(p.trace_id);
+__device__ __forceinline__ void pool_bwd_body(const BwdParams& p, int bid) {
     __shared__ __align__(16) float T[(1 + QT) * kBwdSpan];
     const int tid = threadIdx.x;
-    int bid = blockIdx.x;
     const int d = (p.ndom > 1 && bid >= p.dom[0].ctas) ? 1 : 0;
     if (d) bid -= p.dom[0].ctas;
     const BwdDom& D = p.dom[d];
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(kThreads, 4) pool_bwd_kernel(const BwdParams p
         }
     }
     __syncthreads();
-    if (!ok) { trace_exit(p.trace_id); return; }
+    if (!ok) return;
 
     float* gp = D.grad + ((size_t)b * p.C + c0) * p.HW + px;
     const int nc = (p.C - c0) < kBwdSpan ? (p.C - c0) : kBwdSpan;
@@ -122,17 +122,45 @@ __global__ void __launch_bounds__(kThreads, 4) pool_bwd_kernel(const BwdParams p
         }
         st_stream<VEC>(gp + (size_t)j * p.HW, o);
     }
+}
+
+template <int QT, int VEC>
+__global__ void __launch_bounds__(kThreads, 4) pool_bwd_kernel(const BwdParams p) {
+    kernel_begin(p.trace_id);
+    pool_bwd_body<QT, VEC>(p, blockIdx.x);
     trace_exit(p.trace_id);
 }
 
+// Horizontal fusion for the fused step: CTAs [0, n_fin) run the discriminative finish (partial reduce + prototype
+// gradients + direct-gradient table + step totals: a latency chain) while the remaining CTAs write the gradient of the
+// TARGET features, which depends on the alignment term only.  The source-gradient write follows as the next launch.
+template <int QT, int VEC>
+__global__ void __launch_bounds__(kThreads, 4) bwd_finish_kernel(const BwdParams p, const DiscFinishParams f, const int n_fin) {
+    if ((int)blockIdx.x < n_fin) {
+        kernel_begin(TR_DISC_FIN);
+        disc_finish_body(f, blockIdx.x, n_fin);
+        trace_exit(TR_DISC_FIN);
+    } else {
+        kernel_begin(p.trace_id);
+        pool_bwd_body<QT, VEC>(p, blockIdx.x - n_fin);
+        trace_exit(p.trace_id);
+    }
+}
+
 template <int QT>
-static int launch_bwd(const BwdParams& p, bool vec4, int ctas, cudaStream_t st) {
+static int launch_bwd(const BwdParams& p, bool vec4, int ctas, cudaStream_t st, const DiscFinishParams* fin) {
+    if (fin) {
+        const int n_fin = disc_finish_ctas(fin->C);
+        if (vec4) { clr::launch_k(bwd_finish_kernel<QT, 4>, ctas + n_fin, kThreads, 0, st, p, *fin, n_fin); }
+        else { clr::launch_k(bwd_finish_kernel<QT, 1>, ctas + n_fin, kThreads, 0, st, p, *fin, n_fin); }
+        return launch_status();
+    }
     if (vec4) { clr::launch_k(pool_bwd_kernel<QT, 4>, ctas, kThreads, 0, st, p); }
     else { clr::launch_k(pool_bwd_kernel<QT, 1>, ctas, kThreads, 0, st, p); }
     return launch_status();
 }
 
-int pool_bwd_impl(const BwdDom* doms, int ndom, int C, int HW, int K, cudaStream_t st) {
+int pool_bwd_impl(const BwdDom* doms, int ndom, int C, int HW, int K, cudaStream_t st, const DiscFinishParams* fin = nullptr) {
     CLR_CHECK_ARG(ndom >= 1 && ndom <= 2 && C > 0 && HW > 0 && K >= 1 && K <= CLR_MAX_K);
     bool vec4 = (HW % 4 == 0);
     int Qmax = 0;
@@ -163,14 +191,21 @@ int pool_bwd_impl(const BwdDom* doms, int ndom, int C, int HW, int K, cudaStream
     }
     if (total > 0x7fffffff) return CLR_ERR_UNSUPPORTED;
     const int ctas = (int)total;
-    if (Qmax <= 2) return launch_bwd<2>(p, vec4, ctas, st);
-    if (Qmax <= 3) return launch_bwd<3>(p, vec4, ctas, st);
-    if (Qmax <= 4) return launch_bwd<4>(p, vec4, ctas, st);
-    if (Qmax <= 6) return launch_bwd<6>(p, vec4, ctas, st);
-    if (Qmax <= 8) return launch_bwd<8>(p, vec4, ctas, st);
-    if (Qmax <= 12) return launch_bwd<12>(p, vec4, ctas, st);
-    if (Qmax <= 16) return launch_bwd<16>(p, vec4, ctas, st);
-    return launch_bwd<24>(p, vec4, ctas, st);
+    if (Qmax <= 2) return launch_bwd<2>(p, vec4, ctas, st, fin);
+    if (Qmax <= 3) return launch_bwd<3>(p, vec4, ctas, st, fin);
+    if (Qmax <= 4) return launch_bwd<4>(p, vec4, ctas, st, fin);
+    if (Qmax <= 6) return launch_bwd<6>(p, vec4, ctas, st, fin);
+    if (Qmax <= 8) return launch_bwd<8>(p, vec4, ctas, st, fin);
+    if (Qmax <= 12) return launch_bwd<12>(p, vec4, ctas, st, fin);
+    if (Qmax <= 16) return launch_bwd<16>(p, vec4, ctas, st, fin);
+    return launch_bwd<24>(p, vec4, ctas, st, fin);
+}
+
+int pool_bwd_with_finish(const clr_bwd_dom* dom, int C, int HW, int K, const DiscFinishParams& f, cudaStream_t st) {
+    if (!dom) return CLR_ERR_BAD_ARG;
+    BwdDom d{dom->w, dom->g, dom->sums, dom->xcoef, dom->xtab, dom->grad, dom->scale_dev, dom->scale, dom->fmt, dom->B, dom->Kx,
+             0, 2 * K, 0, 0.f};
+    return pool_bwd_impl(&d, 1, C, HW, K, st, &f);
 }
 
 }  // namespace clr

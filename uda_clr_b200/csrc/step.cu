@@ -7,6 +7,7 @@
 // plus O(K*C) glue kernels, with no host synchronisation (.item()) anywhere.
 #include "clr_common.cuh"
 #include "clr_internal.h"
+#include "clr_finish.cuh"
 
 namespace clr {
 
@@ -32,7 +33,7 @@ static StepWs carve(const clr_step_args* a) {
     w.rows_bytes = align_up(rows);
     w.hinge_bytes = a->use_disc ? align_up(sizeof(float) * (size_t)clr_disc_partials_cap() * (1 + a->K)) : 0;
     w.cons_bytes = a->use_cons ? align_up(clr_cons_ws_bytes()) : 0;
-    w.fin_bytes = align_up(sizeof(double) * (size_t)pool_finish_max_ctas(a->C) * (2 + CLR_MAX_K) + 64);
+    w.fin_bytes = align_up(sizeof(double) * (size_t)pool_finish_ctas(a->C) * (2 + CLR_MAX_K) + 64);
     char* base = static_cast<char*>(a->ws);
     size_t off = 0;
     w.pool = base + off; off += w.pool_bytes;
@@ -176,25 +177,17 @@ int clr_step_fwd_c(const clr_step_args* a, clr_stream_t stream) {
 }
 
 // Single-GPU forward: no exchange points, so each partial reduce is folded into the finalize that consumes it
-// (pool_finish_kernel, disc_finish_kernel): 8 launches instead of 10 and two fewer single-CTA latency chains.
-int clr_step_fwd(const clr_step_args* a, clr_stream_t stream) {
-    int rc = clr::check_args(a);
-    if (rc != CLR_OK) return rc;
-    if (clr::tunables().finish_off) {     // separate reduce / finalize kernels (the sharded path's kernels), for A/B runs
-        rc = clr_step_fwd_a(a, stream);
-        if (rc != CLR_OK) return rc;
-        clr::PendingPack pk{};
-        rc = clr::step_fwd_b_impl(a, stream, &pk, nullptr);
-        if (rc != CLR_OK) return rc;
-        const float ema0 = a->first_s ? 1.0f : (float)a->decay;
-        return clr::disc_finalize_impl(a->packed2, a->P_s, a->K, a->C, a->npx_global, a->w_disc, ema0, a->grad_scale,
-                                       a->g_s, a->xtab, a->w_intra, a->w_inter, a->w_aug, a->aug_weight,
-                                       a->use_disc, a->use_cons, a->losses, pk.hinge, pk.n_hinge, pk.hinge_stride,
-                                       pk.cons, pk.n_cons, static_cast<cudaStream_t>(stream));
-    }
-    const clr::StepWs w = clr::carve(a);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
+// (clr_finish.cuh), and the two finish bodies ride as the first CTAs of the streaming launch that follows them:
+//   mc_stats -> retrify_weights -> pooling (xt + xs) -> [pool finish | consistency] -> discriminative
+//            -> [disc finish | gradient of xt] -> gradient of xs                       (7 launches; was 10)
+// `defer` != NULL: do not launch the disc finish; describe it instead (clr_step_run co-schedules it with the backward).
+namespace clr {
+static void bwd_doms(const clr_step_args* a, clr_bwd_dom (&d)[2]);
+static int step_fwd_core(const clr_step_args* a, cudaStream_t st, DiscFinishParams* defer, int* deferred) {
+    const StepWs w = carve(a);
+    clr_stream_t stream = st;
     const int HW = a->H * a->W, R = 2 * a->K, C = a->C, K = a->K;
+    int rc;
     if (a->use_retrify) {
         rc = clr_mc_stats(a->preds, a->T, a->B_t, K, a->Hi, a->Wi, a->std_map, a->pred_mean, stream);
         if (rc != CLR_OK) return rc;
@@ -204,53 +197,91 @@ int clr_step_fwd(const clr_step_args* a, clr_stream_t stream) {
     }
     float* sums_s = a->packed1;
     float* sums_t = a->packed1 + (size_t)R * (C + 1);
-    unsigned int* counter = reinterpret_cast<unsigned int*>(w.fin + (size_t)clr::pool_finish_max_ctas(C) * (2 + CLR_MAX_K));
-    clr::PoolLayout lay{};
+    unsigned int* counter = reinterpret_cast<unsigned int*>(w.fin + (size_t)pool_finish_ctas(C) * (2 + CLR_MAX_K));
+    PoolLayout lay{};
     if (a->ev_pool_begin) cudaEventRecord(static_cast<cudaEvent_t>(a->ev_pool_begin), st);
-    rc = clr::pool_fwd_impl(a->xt, clr::target_weights(a), clr::target_fmt(a), a->B_t, sums_t,
-                            a->xs, a->ys, CLR_W_COMPLEMENT, a->B_s, sums_s,
-                            C, HW, R, w.pool, w.pool_bytes, st, 0, 0, &lay, counter);
+    rc = pool_fwd_impl(a->xt, target_weights(a), target_fmt(a), a->B_t, sums_t,
+                       a->xs, a->ys, CLR_W_COMPLEMENT, a->B_s, sums_s,
+                       C, HW, R, w.pool, w.pool_bytes, st, 0, 0, &lay, counter);
     if (a->ev_pool_end) cudaEventRecord(static_cast<cudaEvent_t>(a->ev_pool_end), st);
     if (rc != CLR_OK) return rc;
-    rc = clr::pool_finish_impl(lay.partial[1], lay.slots[1], lay.partial[0], lay.slots[0], sums_s, sums_t, K, C,
-                               a->stored_s, a->stored_t, a->first_s, a->first_t, a->decay, a->w_intra, a->w_inter,
-                               a->P_s, a->P_t, a->g_s, a->g_t, a->use_disc ? a->disc_vec : nullptr,
-                               a->use_disc ? a->disc_beta : nullptr, a->losses, w.fin, counter, st);
-    if (rc != CLR_OK) return rc;
+    PoolFinishParams pf{};
+    pf.partial[0] = lay.partial[1]; pf.partial[1] = lay.partial[0];       // pooling ran (target, source)
+    pf.slots[0] = lay.slots[1]; pf.slots[1] = lay.slots[0];
+    pf.sums[0] = sums_s; pf.sums[1] = sums_t;
+    pf.stored[0] = a->stored_s; pf.stored[1] = a->stored_t; pf.P[0] = a->P_s; pf.P[1] = a->P_t;
+    pf.g[0] = a->g_s; pf.g[1] = a->g_t; pf.first[0] = a->first_s; pf.first[1] = a->first_t;
+    pf.K = K; pf.C = C; pf.d = (float)a->decay; pf.omd = (float)(1.0 - a->decay);
+    pf.w_intra = a->w_intra; pf.w_inter = a->w_inter;
+    pf.disc_vec = a->use_disc ? a->disc_vec : nullptr; pf.disc_beta = a->use_disc ? a->disc_beta : nullptr;
+    pf.losses = a->losses; pf.loss_partial = w.fin; pf.counter = counter;
     int n_cons = 0;
     if (a->use_cons) {
-        rc = clr::cons_fwd_partials(a->oT, a->oT_aug, a->masks, a->B_t, K, a->Hi, a->Wi, a->H, a->W,
-                                    a->cons_threshold, w.cons, &n_cons, st);
+        rc = cons_fwd_partials(a->oT, a->oT_aug, a->masks, a->B_t, K, a->Hi, a->Wi, a->H, a->W,
+                               a->cons_threshold, w.cons, &n_cons, st, tunables().hfuse_off ? nullptr : &pf);
+        if (rc != CLR_OK) return rc;
+    }
+    if (!a->use_cons || tunables().hfuse_off) {
+        rc = pool_finish_launch(pf, st);     // (stream order: after the consistency launch is fine, they are independent)
         if (rc != CLR_OK) return rc;
     }
     const float ema = a->first_s ? 1.0f : (float)a->decay;
     const double* cons = a->use_cons ? w.cons : nullptr;
-    if (a->use_disc && clr::tunables().disc_impl != 1) {
+    if (a->use_disc && tunables().disc_impl != 1) {
         float* partial = reinterpret_cast<float*>(w.rows);
         float* hinge = partial + (size_t)320 * K * (C + 1);   // layout of clr_disc_fused_ws_bytes: [320][K][C+1] | [320]
         int n_hinge = 320;
-        rc = clr::disc_fused_impl(a->xs, a->ys, a->B_s, C, HW, K, a->disc_vec, a->disc_beta, a->margin,
-                                  a->disc_coef, nullptr, partial, hinge, &n_hinge, st);
-        if (rc == CLR_OK)
-            return clr::disc_finish_impl(partial, n_hinge, a->packed2, a->P_s, K, C, a->npx_global, a->w_disc, ema,
-                                         a->grad_scale, a->g_s, a->xtab, a->w_intra, a->w_inter, a->w_aug, a->aug_weight,
-                                         a->use_cons, a->losses, hinge, n_hinge, 1, cons, n_cons, st);
+        rc = disc_fused_impl(a->xs, a->ys, a->B_s, C, HW, K, a->disc_vec, a->disc_beta, a->margin,
+                             a->disc_coef, nullptr, partial, hinge, &n_hinge, st);
+        if (rc == CLR_OK) {
+            DiscFinishParams df{};
+            df.partial = partial; df.slots = n_hinge; df.packed2 = a->packed2; df.P_s = a->P_s; df.g_s = a->g_s;
+            df.xtab = a->xtab; df.losses = a->losses; df.K = K; df.C = C; df.npx = a->npx_global;
+            df.coef = (float)(2.0 / ((double)C * a->npx_global));
+            df.w_disc = a->w_disc; df.ema_factor = ema; df.gscale = a->grad_scale; df.w_intra = a->w_intra;
+            df.w_inter = a->w_inter; df.w_aug = a->w_aug; df.aug_weight = a->aug_weight; df.use_cons = a->use_cons;
+            df.ps = PackSrc{hinge, n_hinge, 1, cons, n_cons};
+            if (defer && !tunables().hfuse_off) { *defer = df; *deferred = 1; return CLR_OK; }
+            return disc_finish_launch(df, st);
+        }
         if (rc != CLR_ERR_UNSUPPORTED) return rc;
     }
     int n_hinge = 0;
     if (a->use_disc) {
         // two-pass form: per-pixel dots (read 1), then pooling of xs with the coefficient planes (read 2)
-        rc = clr::disc_fwd_impl(a->xs, a->ys, a->B_s, C, HW, K, a->disc_vec, a->disc_beta, a->margin,
-                                a->disc_coef, nullptr, w.hinge, clr_disc_partials_cap(), &n_hinge, st);
+        rc = disc_fwd_impl(a->xs, a->ys, a->B_s, C, HW, K, a->disc_vec, a->disc_beta, a->margin,
+                           a->disc_coef, nullptr, w.hinge, clr_disc_partials_cap(), &n_hinge, st);
         if (rc != CLR_OK) return rc;
-        rc = clr::pool_fwd_impl(a->xs, a->disc_coef, CLR_W_EXPLICIT, a->B_s, a->packed2, nullptr, nullptr, 0, 0, nullptr,
-                                C, HW, K, w.rows, w.rows_bytes, st);
+        rc = pool_fwd_impl(a->xs, a->disc_coef, CLR_W_EXPLICIT, a->B_s, a->packed2, nullptr, nullptr, 0, 0, nullptr,
+                           C, HW, K, w.rows, w.rows_bytes, st);
         if (rc != CLR_OK) return rc;
     }
-    return clr::disc_finalize_impl(a->packed2, a->P_s, K, C, a->npx_global, a->w_disc, ema, a->grad_scale,
-                                   a->g_s, a->xtab, a->w_intra, a->w_inter, a->w_aug, a->aug_weight,
-                                   a->use_disc, a->use_cons, a->losses, a->use_disc ? w.hinge : nullptr, n_hinge, 1 + K,
-                                   cons, n_cons, st);
+    return disc_finalize_impl(a->packed2, a->P_s, K, C, a->npx_global, a->w_disc, ema, a->grad_scale,
+                              a->g_s, a->xtab, a->w_intra, a->w_inter, a->w_aug, a->aug_weight,
+                              a->use_disc, a->use_cons, a->losses, a->use_disc ? w.hinge : nullptr, n_hinge, 1 + K,
+                              cons, n_cons, st);
+}
+
+// the separate reduce / finalize kernels (the sharded path's kernels) on one GPU, for A/B runs ("finish_off" = 1)
+static int step_fwd_unmerged(const clr_step_args* a, clr_stream_t stream) {
+    int rc = clr_step_fwd_a(a, stream);
+    if (rc != CLR_OK) return rc;
+    PendingPack pk{};
+    rc = step_fwd_b_impl(a, stream, &pk, nullptr);
+    if (rc != CLR_OK) return rc;
+    const float ema0 = a->first_s ? 1.0f : (float)a->decay;
+    return disc_finalize_impl(a->packed2, a->P_s, a->K, a->C, a->npx_global, a->w_disc, ema0, a->grad_scale,
+                              a->g_s, a->xtab, a->w_intra, a->w_inter, a->w_aug, a->aug_weight,
+                              a->use_disc, a->use_cons, a->losses, pk.hinge, pk.n_hinge, pk.hinge_stride,
+                              pk.cons, pk.n_cons, static_cast<cudaStream_t>(stream));
+}
+}  // namespace clr
+
+int clr_step_fwd(const clr_step_args* a, clr_stream_t stream) {
+    int rc = clr::check_args(a);
+    if (rc != CLR_OK) return rc;
+    if (clr::tunables().finish_off) return clr::step_fwd_unmerged(a, stream);
+    return clr::step_fwd_core(a, static_cast<cudaStream_t>(stream), nullptr, nullptr);
 }
 
 namespace clr {
@@ -270,8 +301,33 @@ int clr_step_run(const clr_step_args* a, clr_stream_t stream) {
     if (rc != CLR_OK) return rc;
     if (!a->gxs || !a->gxt) return CLR_ERR_BAD_ARG;
     if (!a->aux_stream || !a->ev_fork || !a->ev_join || clr::tunables().overlap_off) {
-        rc = clr_step_fwd(a, stream);
-        return rc != CLR_OK ? rc : clr_step_bwd(a, stream);
+        if (clr::tunables().finish_off) {
+            rc = clr::step_fwd_unmerged(a, stream);
+            return rc != CLR_OK ? rc : clr_step_bwd(a, stream);
+        }
+        clr::DiscFinishParams df{};
+        int deferred = 0;
+        rc = clr::step_fwd_core(a, static_cast<cudaStream_t>(stream), &df, &deferred);
+        if (rc != CLR_OK) return rc;
+        if (!deferred) return clr_step_bwd(a, stream);
+        // [disc finish | gradient of xt] in one launch, then the gradient of xs (needs the finish's table)
+        clr_bwd_dom dd[2];
+        clr::bwd_doms(a, dd);
+        cudaStream_t s0 = static_cast<cudaStream_t>(stream);
+        if (a->ev_bwd_begin) cudaEventRecord(static_cast<cudaEvent_t>(a->ev_bwd_begin), s0);
+        clr::tunables().bwd_trace_id = clr::TR_BWD_T;
+        rc = clr::pool_bwd_with_finish(&dd[1], a->C, a->H * a->W, a->K, df, s0);
+        clr::tunables().bwd_trace_id = clr::TR_BWD_S;
+        if (rc == CLR_OK) rc = clr_pool_bwd_multi(&dd[0], 1, a->C, a->H * a->W, a->K, stream);
+        clr::tunables().bwd_trace_id = 0;
+        if (a->ev_bwd_end) cudaEventRecord(static_cast<cudaEvent_t>(a->ev_bwd_end), s0);
+        if (rc != CLR_OK) return rc;
+        if (a->use_cons && a->w_aug != 0.f && a->g_oT_aug) {
+            const float* stats = a->packed2 + (size_t)a->K * (a->C + 1);
+            rc = clr_cons_bwd(a->oT, a->oT_aug, a->masks, a->B_t, a->K, a->Hi, a->Wi, a->H, a->W, a->cons_threshold,
+                              a->aug_weight, stats + 1, a->gup, a->grad_scale * a->w_aug, a->g_oT_aug, stream);
+        }
+        return rc;
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream), aux = static_cast<cudaStream_t>(a->aux_stream);
     const int HW = a->H * a->W, C = a->C, K = a->K;
