@@ -184,6 +184,14 @@ int clr_retrify_weights(const float* oT_before /*[B,K,H,W]*/, const float* pred_
                         float* pseudo_out /*[B,K,H,W] or NULL*/, float* small_out /*[2][B,K,H,W] or NULL*/,
                         clr_stream_t stream);
 
+/* Both of the above in ONE pass over preds (utils/Utils.py:161-223 end to end): each CTA owns the image rows between
+ * two consecutive bilinear source rows, so the taps of its feature row never leave shared memory.  pred_mean may be
+ * NULL (the full-resolution mean is only ever down-sampled, :170).  Returns CLR_ERR_UNSUPPORTED when the geometry does
+ * not allow it ((Hi-1) < 2 (H-1), Wi % 4 != 0, misaligned maps): call the two functions above then. */
+int clr_mc_retrify(const float* preds, const float* oT_before, int T, int B, int K, int H, int W, int Hi, int Wi,
+                   float pseudo_thr, float std_thr, float* std_map, float* pred_mean /*nullable*/,
+                   float* weights /*[B,2K,H,W] out*/, float* masks /*[B,K,H,W] out*/, clr_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Augmented-consistency masked BCE (Trainer_prototype_mt.cpython-38.pyc L502-561).
  * stats = { sum(m*l), sum(m), loss, 0 }.

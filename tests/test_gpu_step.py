@@ -123,6 +123,29 @@ def test_distance_cosine_fixture_and_oracle():
     assert relerr(cw.cpu().numpy(), O.cosine_weight(x.numpy(), p.numpy())) < 1e-5
 
 
+@pytest.mark.parametrize("B,K,H,W,up,T", [(2, 2, 64, 64, 4, 8), (1, 3, 16, 24, 2, 4), (2, 2, 32, 32, 8, 12), (1, 2, 8, 8, 4, 20)])
+def test_one_pass_mc_retrify_equals_two_kernels(B, K, H, W, up, T):
+    """clr_mc_retrify (MC statistics + bilinear taps + pseudo-labels + masks + weights in one pass, the fused step's
+    form) against clr_mc_stats + clr_retrify_weights: same arithmetic on the same values -> identical outputs."""
+    g = torch.Generator().manual_seed(3 + H)
+    oT = (2.0 * torch.randn(B, K, H, W, generator=g)).to(DEV)
+    preds = (torch.nn.functional.interpolate(oT.cpu(), scale_factor=up, mode="nearest")
+             + 0.3 * torch.randn(T * B, K, H * up, W * up, generator=g).reshape(T, B, K, H * up, W * up)).reshape(T * B, K, H * up, W * up).to(DEV)
+    std2, mean2 = clr.mc_statistics(preds, T, B)
+    w2, m2 = clr.retrify_weights(oT, mean2, std2, H, W)
+    from uda_clr_b200 import _lib
+    lib = _lib.load()
+    for split in (0, 1):
+        try:
+            lib.clr_set_tunable(b"mc_split", split)
+            std1, w1, m1 = clr.ops.mc_retrify(oT, preds, T, B, H, W)
+        finally:
+            lib.clr_set_tunable(b"mc_split", 0)
+        assert torch.equal(std1, std2)
+        assert torch.equal(m1, m2)
+        assert torch.equal(w1, w2)
+
+
 # ------------------------------------------------------------------------------------------------ A6 / A7
 @pytest.mark.parametrize("B,C,H,W,R,hard", [(4, 305, 32, 32, 2, True), (3, 304, 24, 40, 1, False), (2, 37, 6, 7, 3, False),
                                              (8, 256, 128, 128, 2, True)])

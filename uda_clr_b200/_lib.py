@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_PKG, "lib", "libclr_b200.so")
 CLR_W_COMPLEMENT = 0
 CLR_W_EXPLICIT = 1
 CLR_MAX_K = 8
+CLR_ERR_UNSUPPORTED = -4
 
 _lock = threading.Lock()
 _lib = None
@@ -96,6 +97,7 @@ _SIGNATURES = {
     "clr_mc_stats": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P]),
     "clr_retrify_weights": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float,
                                     _P, _P, _P, _P, _P]),
+    "clr_mc_retrify": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float, _P, _P, _P, _P, _P]),
     "clr_cons_ws_bytes": (c_size_t, []),
     "clr_cons_fwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float, _P, c_size_t,
                              _P, _P]),

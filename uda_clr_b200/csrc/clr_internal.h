@@ -47,6 +47,11 @@ int pool_finish_launch(const PoolFinishParams& p, cudaStream_t st);
 int disc_finish_launch(const DiscFinishParams& p, cudaStream_t st);
 int pool_bwd_with_finish(const clr_bwd_dom* dom, int C, int HW, int K, const DiscFinishParams& f, cudaStream_t st);
 
+// MC statistics + retrify weights in one pass (mc_stats.cu); CLR_ERR_UNSUPPORTED -> run the two kernels.
+int mc_retrify_fused(const float* preds, const float* oT_before, int T, int B, int K, int H, int W, int Hi, int Wi,
+                     float pseudo_thr, float std_thr, float* std_map, float* pred_mean /*nullable*/, float* weights,
+                     float* masks, cudaStream_t st);
+
 // Where pool_fwd_impl left its per-(b,chunk) partials (for callers that reduce them themselves).
 struct PoolLayout { const float* partial[2]; int slots[2]; };
 

@@ -11,6 +11,7 @@
 // Integer-valued decisions follow ATen's CUDA arithmetic: sigmoid = 1/(1+expf(-x)) in fp32 with IEEE
 // division (no fast-math), thresholds compared in fp32.
 #include "clr_common.cuh"
+#include "clr_internal.h"
 
 namespace clr {
 
@@ -39,14 +40,10 @@ __device__ __forceinline__ void mc_sigmoids(float p, float& s_half, float& s_ful
     }
 }
 
+// std (unbiased, of sigmoid(p/2)) and mean (of sigmoid(p)) over the T MC passes for the VEC positions starting at i.
+// preds is [T][n].  TT > 0: T <= TT, values kept in registers (two-pass variance); TT == 0: any T, Welford.
 template <int VEC, int TT, bool PRECISE>
-__global__ void __launch_bounds__(256) mc_stats_kernel(const float* __restrict__ preds, int T, size_t n,
-                                                       float* __restrict__ std_map, float* __restrict__ pred_mean) {
-    kernel_begin(TR_MC_STATS);
-    // n = B*K*Hi*Wi positions; preds is [T][n].  TT > 0: T <= TT, values kept in registers (two-pass
-    // variance); TT == 0: any T, Welford.
-    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
-    if (i >= n) { trace_exit(TR_MC_STATS); return; }
+__device__ __forceinline__ void mc_vec_stats(const float* __restrict__ preds, int T, size_t n, size_t i, Pack<VEC>& s, Pack<VEC>& m) {
     float mean_h[VEC], m2[VEC], mean_f[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) { mean_h[v] = 0.f; m2[v] = 0.f; mean_f[v] = 0.f; }
@@ -92,12 +89,22 @@ __global__ void __launch_bounds__(256) mc_stats_kernel(const float* __restrict__
             }
         }
     }
-    Pack<VEC> s, m;
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
         s.v[v] = sqrtf(m2[v] / (float)(T - 1));   // unbiased (torch.std default, :166); T = 1 -> NaN like torch
         m.v[v] = mean_f[v] / (float)T;            // :168
     }
+}
+
+template <int VEC, int TT, bool PRECISE>
+__global__ void __launch_bounds__(256) mc_stats_kernel(const float* __restrict__ preds, int T, size_t n,
+                                                       float* __restrict__ std_map, float* __restrict__ pred_mean) {
+    kernel_begin(TR_MC_STATS);
+    // n = B*K*Hi*Wi positions
+    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+    if (i >= n) { trace_exit(TR_MC_STATS); return; }
+    Pack<VEC> s, m;
+    mc_vec_stats<VEC, TT, PRECISE>(preds, T, n, i, s, m);
     st_keep<VEC>(std_map + i, s);
     st_keep<VEC>(pred_mean + i, m);
     trace_exit(TR_MC_STATS);
@@ -123,11 +130,17 @@ __device__ __forceinline__ Tap bilinear_tap(int dst, int n_in, float scale) {
     t.l0 = 1.0f - t.l1;
     return t;
 }
+// h0 * (w0 * a + w1 * b) + h1 * (w0 * c + w1 * d) with the contraction nvcc applies to that expression in ATen's
+// upsample_bilinear2d kernel pinned explicitly, so every caller rounds identically
+__device__ __forceinline__ float bilinear_mix(float a, float b, float c, float d, const Tap& h, const Tap& w) {
+    const float top = __fmaf_rn(w.l0, a, __fmul_rn(w.l1, b));
+    const float bot = __fmaf_rn(w.l0, c, __fmul_rn(w.l1, d));
+    return __fmaf_rn(h.l0, top, __fmul_rn(h.l1, bot));
+}
 __device__ __forceinline__ float bilinear_at(const float* __restrict__ plane, int Wi, const Tap& h, const Tap& w) {
     const float* r0 = plane + (size_t)h.i0 * Wi;
     const float* r1 = plane + (size_t)h.i1 * Wi;
-    return h.l0 * (w.l0 * __ldg(r0 + w.i0) + w.l1 * __ldg(r0 + w.i1)) +
-           h.l1 * (w.l0 * __ldg(r1 + w.i0) + w.l1 * __ldg(r1 + w.i1));
+    return bilinear_mix(__ldg(r0 + w.i0), __ldg(r0 + w.i1), __ldg(r1 + w.i0), __ldg(r1 + w.i1), h, w);
 }
 
 __global__ void __launch_bounds__(256) retrify_weights_kernel(
@@ -161,6 +174,130 @@ __global__ void __launch_bounds__(256) retrify_weights_kernel(
     trace_exit(TR_RETRIFY);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// MC statistics + retrify weights in ONE pass (the fused step): CTA = (plane b*K+k, feature row y).  It owns the image
+// rows [r0(y), r0(y+1)) with r0(y) = (int)(sh*y) -- exactly ATen's align_corners source row of feature row y -- so the
+// two bilinear tap rows r0(y), r0(y)+1 of its feature row are rows it computes itself (needs sh >= 2): their std / mean
+// values are kept in shared memory, and after one barrier W threads evaluate the bilinear taps, the pseudo-label and
+// the uncertainty mask and write the 2K weight planes.  The rows in between are computed and stored to std_map only.
+// Saves the retrify launch, its re-read of the two maps and the write of pred_mean (never needed at full resolution:
+// utils/Utils.py:170 only down-samples it).
+// ---------------------------------------------------------------------------------------------------------------
+struct McRetrifyParams {
+    const float* preds; const float* oT_before;
+    float* std_map; float* pred_mean /*nullable*/; float* weights; float* masks;
+    int T, B, K, H, W, Hi, Wi;
+    int parts, cw;            // the image rows are split into `parts` column blocks of cw floats, one CTA each
+    float sh, sw, pseudo_thr, std_thr;
+    size_t n;
+};
+
+template <int TT, bool PRECISE>
+__global__ void __launch_bounds__(256, 4) mc_retrify_kernel(const McRetrifyParams p) {
+    kernel_begin(TR_MC_STATS);
+    extern __shared__ __align__(16) float taps[];      // [2 maps: std, mean][2 rows][cw]
+    const int y = blockIdx.x / p.parts, part = blockIdx.x - y * p.parts, bk = blockIdx.y;
+    const int c0 = part * p.cw;                        // first image column of this CTA
+    const int r0 = (int)(p.sh * (float)y);
+    const int r1 = (y == p.H - 1) ? p.Hi : (int)(p.sh * (float)(y + 1));
+    const int i1 = r0 + ((r0 < p.Hi - 1) ? 1 : 0);
+    const int wv = p.cw >> 2;
+    const int total = (r1 - r0) * wv;
+    const size_t plane = (size_t)bk * p.Hi * p.Wi;
+    const size_t hw = (size_t)p.H * p.W;
+    // the feature pixels whose taps fall into this column block: x in [x_lo, x_hi) (host checked: no tap pair straddles)
+    const Tap th = bilinear_tap(y, p.Hi, p.sh);          // th.i0 == r0, th.i1 == i1
+    // this thread's feature-row logit for the epilogue: issued now so its latency hides behind the streaming phase
+    const int xg = (int)threadIdx.x;                     // candidate feature column handled in the epilogue (round 0)
+    float o_pre = 0.f;
+    if (xg < p.W) o_pre = __ldg(p.oT_before + (size_t)bk * hw + (size_t)y * p.W + xg);
+    for (int v = threadIdx.x; v < total; v += 256) {
+        const int rr = v / wv, xv = v - rr * wv;
+        const int row = r0 + rr;
+        const size_t i = plane + (size_t)row * p.Wi + c0 + 4 * xv;
+        Pack<4> s, m;
+        mc_vec_stats<4, TT, PRECISE>(p.preds, p.T, p.n, i, s, m);
+        st_keep<4>(p.std_map + i, s);
+        if (p.pred_mean) st_keep<4>(p.pred_mean + i, m);
+        if (row == r0) { st_keep<4>(taps + 4 * xv, s); st_keep<4>(taps + 2 * p.cw + 4 * xv, m); }
+        if (row == i1) { st_keep<4>(taps + p.cw + 4 * xv, s); st_keep<4>(taps + 3 * p.cw + 4 * xv, m); }
+    }
+    __syncthreads();
+    const int b = bk / p.K, k = bk - b * p.K;
+    const float* s0 = taps;                 // std, row i0
+    const float* s1 = taps + p.cw;          // std, row i1
+    const float* m0 = taps + 2 * p.cw;      // mean, row i0
+    const float* m1 = taps + 3 * p.cw;      // mean, row i1
+    for (int x = threadIdx.x; x < p.W; x += 256) {
+        const Tap tw = bilinear_tap(x, p.Wi, p.sw);
+        if (tw.i0 < c0 || tw.i0 >= c0 + p.cw) continue;    // another column block's pixel
+        const int a0 = tw.i0 - c0, a1 = tw.i1 - c0;
+        const float ps = bilinear_mix(m0[a0], m0[a1], m1[a0], m1[a1], th, tw);
+        const float ss = bilinear_mix(s0[a0], s0[a1], s1[a0], s1[a1], th, tw);
+        const size_t pix = (size_t)y * p.W + x;
+        const size_t i = (size_t)bk * hw + pix;
+        const float o = (x == xg) ? o_pre : __ldg(p.oT_before + i);
+        const bool pseudo = sigmoid_aten(o) > p.pseudo_thr;
+        const bool m = ss < p.std_thr;
+        p.weights[((size_t)b * 2 * p.K + k) * hw + pix] = (pseudo && m) ? ps : 0.f;
+        p.weights[((size_t)b * 2 * p.K + p.K + k) * hw + pix] = (!pseudo && m) ? (1.0f - ps) : 0.f;
+        p.masks[i] = m ? 2.0f : 0.f;
+    }
+    trace_exit(TR_MC_STATS);
+}
+
+// host mirror of bilinear_tap's source index (same fp32 expression)
+static inline int tap_i0(int dst, float scale) { return (int)(scale * (float)dst); }
+
+// Largest split of the image rows into column blocks such that (a) blocks are whole float4 vectors, (b) no feature
+// pixel's tap pair (i0, i0+1) straddles a block boundary, (c) a typical CTA still has a full 256 vectors of work.
+static int choose_parts(int W, int Wi, float sw, int rows_per_cta) {
+    for (int parts = 8; parts > 1; parts >>= 1) {
+        if (Wi % (4 * parts)) continue;
+        const int cw = Wi / parts;
+        if ((long long)rows_per_cta * (cw / 4) < 256) continue;
+        bool ok = true;
+        for (int x = 0; x < W && ok; ++x) {
+            const int i0 = tap_i0(x, sw), i1 = i0 + ((i0 < Wi - 1) ? 1 : 0);
+            ok = (i0 / cw) == (i1 / cw);
+        }
+        if (ok) return parts;
+    }
+    return 1;
+}
+
+// CLR_ERR_UNSUPPORTED when the geometry does not allow the fusion (the caller then runs the two kernels).
+int mc_retrify_fused(const float* preds, const float* oT_before, int T, int B, int K, int H, int W, int Hi, int Wi,
+                     float pseudo_thr, float std_thr, float* std_map, float* pred_mean, float* weights, float* masks,
+                     cudaStream_t st) {
+    if (!preds || !oT_before || !std_map || !weights || !masks || T < 1 || B < 1 || K < 1 || K > CLR_MAX_K) return CLR_ERR_BAD_ARG;
+    if (H < 2 || W < 1 || Hi - 1 < 2 * (H - 1) || Wi % 4 != 0 || (long long)B * K > 65535) return CLR_ERR_UNSUPPORTED;
+    if (!aligned16(preds) || !aligned16(std_map) || (pred_mean && !aligned16(pred_mean))) return CLR_ERR_UNSUPPORTED;
+    const float sh_f = (float)(Hi - 1) / (float)(H - 1), sw_f = W > 1 ? (float)(Wi - 1) / (float)(W - 1) : 0.f;
+    const int parts = tunables().mc_split ? choose_parts(W, Wi, sw_f, (int)sh_f) : 1;   // column split measured slower (shorter DRAM runs): opt-in
+    const size_t smem = sizeof(float) * 4 * (size_t)(Wi / parts);
+    if (smem > 48 * 1024 || (long long)H * parts > 0x7fffffffLL) return CLR_ERR_UNSUPPORTED;
+    McRetrifyParams p{};
+    p.preds = preds; p.oT_before = oT_before; p.std_map = std_map; p.pred_mean = pred_mean; p.weights = weights; p.masks = masks;
+    p.T = T; p.B = B; p.K = K; p.H = H; p.W = W; p.Hi = Hi; p.Wi = Wi;
+    p.sh = sh_f; p.sw = sw_f; p.parts = parts; p.cw = Wi / parts;
+    p.pseudo_thr = pseudo_thr; p.std_thr = std_thr;
+    p.n = (size_t)B * K * Hi * Wi;
+    const dim3 grid((unsigned)(H * parts), (unsigned)(B * K));
+    const bool precise = tunables().mc_precise != 0;
+    if (T <= 8) {
+        if (precise) launch_k(mc_retrify_kernel<8, true>, grid, 256, smem, st, p);
+        else launch_k(mc_retrify_kernel<8, false>, grid, 256, smem, st, p);
+    } else if (T <= 16) {
+        if (precise) launch_k(mc_retrify_kernel<16, true>, grid, 256, smem, st, p);
+        else launch_k(mc_retrify_kernel<16, false>, grid, 256, smem, st, p);
+    } else {
+        if (precise) launch_k(mc_retrify_kernel<0, true>, grid, 256, smem, st, p);
+        else launch_k(mc_retrify_kernel<0, false>, grid, 256, smem, st, p);
+    }
+    return launch_status();
+}
+
 }  // namespace clr
 
 extern "C" {
@@ -191,6 +328,13 @@ int clr_retrify_weights(const float* oT_before, const float* pred_mean, const fl
     if ((long long)H * W > 0x7fffff00LL || (long long)B * K > 65535) return CLR_ERR_UNSUPPORTED;
     clr::launch_k(clr::retrify_weights_kernel, dim3((unsigned)((H * W + 255) / 256), (unsigned)(B * K)), 256, 0, static_cast<cudaStream_t>(stream), oT_before, pred_mean, std_map, B, K, H, W, Hi, Wi, pseudo_thr, std_thr, weights, masks, pseudo_out, small_out);
     return clr::launch_status();
+}
+
+int clr_mc_retrify(const float* preds, const float* oT_before, int T, int B, int K, int H, int W, int Hi, int Wi,
+                   float pseudo_thr, float std_thr, float* std_map, float* pred_mean, float* weights, float* masks,
+                   clr_stream_t stream) {
+    return clr::mc_retrify_fused(preds, oT_before, T, B, K, H, W, Hi, Wi, pseudo_thr, std_thr, std_map, pred_mean, weights,
+                                 masks, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

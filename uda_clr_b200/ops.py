@@ -229,6 +229,32 @@ def retrify_weights(oT_before: torch.Tensor, pred_mean: torch.Tensor, std_map: t
     return weights, masks
 
 
+def mc_retrify(oT_before: torch.Tensor, preds: torch.Tensor, T: int, stride: int, H: int, W: int,
+               pseudo_thr: float = PSEUDO_THRESHOLD, std_thr: float = STD_THRESHOLD):
+    """``mc_statistics`` + ``retrify_weights`` in one pass over ``preds`` (``clr_mc_retrify``): returns
+    ``(std_map [stride,K,Hi,Wi], weights [B,2K,H,W], masks [B,K,H,W])``.  Falls back to the two separate kernels when
+    the geometry does not allow the fusion (up-sampling factor below 2, ragged or misaligned maps)."""
+    lib = _lib.load()
+    o = _require_cuda_f32(oT_before, "oT_before")
+    p = _require_cuda_f32(preds, "preds")
+    if p.shape[0] != T * stride:
+        raise ValueError("preds has %d maps, expected T*stride = %d" % (p.shape[0], T * stride))
+    B, K = o.shape[:2]
+    Hi, Wi = p.shape[2:]
+    std_map = torch.empty(stride, K, Hi, Wi, dtype=torch.float32, device=p.device)
+    weights = torch.empty(B, 2 * K, H, W, dtype=torch.float32, device=o.device)
+    masks = torch.empty(B, K, H, W, dtype=torch.float32, device=o.device)
+    with torch.cuda.device(p.device):
+        rc = lib.clr_mc_retrify(ptr(p), ptr(o), int(T), int(stride), K, H, W, Hi, Wi, float(pseudo_thr), float(std_thr),
+                                ptr(std_map), None, ptr(weights), ptr(masks), _stream())
+    if rc == _lib.CLR_ERR_UNSUPPORTED:
+        std_map, pred_mean = mc_statistics(p, T, stride)
+        weights, masks = retrify_weights(o, pred_mean, std_map, H, W, pseudo_thr, std_thr)
+        return std_map, weights, masks
+    check(rc, "clr_mc_retrify")
+    return std_map, weights, masks
+
+
 class _RetrifyPrototypes(torch.autograd.Function):
     """A2 end to end; optional joint source domain (A3 retrify variant, utils/Utils.py:227-311).
 
@@ -242,8 +268,7 @@ class _RetrifyPrototypes(torch.autograd.Function):
     def forward(ctx, T, stride, oT_before, xt_feature, preds, pred_oS=None, xs_feature=None):
         K = oT_before.shape[1]
         H, W = xt_feature.shape[2:]
-        std_map, pred_mean = mc_statistics(preds, T, stride)
-        weights, masks = retrify_weights(oT_before, pred_mean, std_map, H, W)
+        std_map, weights, masks = mc_retrify(oT_before, preds, T, stride, H, W)
         sums = pool_sums(xt_feature, weights, CLR_W_EXPLICIT, K)
         joint = xs_feature is not None
         if joint:
