@@ -282,7 +282,7 @@ def test_fused_step_vs_eager_port_on_gpu():
 
 # ------------------------------------------------------------------------------------------------ A9 kernels
 @pytest.mark.parametrize("B,C,H,W,K", [(2, 24, 32, 32, 2), (1, 305, 32, 48, 2), (2, 40, 16, 16, 3), (1, 600, 16, 16, 2),
-                                       (2, 33, 10, 10, 2)])
+                                       (2, 33, 10, 10, 2), (2, 256, 64, 64, 2), (3, 37, 6, 10, 4), (1, 64, 4, 4, 8)])
 def test_disc_fused_and_two_pass_agree_with_oracle(B, C, H, W, K):
     """The one-read discriminative kernel and the two-pass form vs the oracle: loss numerator, coefficient
     planes (integer-valued for hard labels: bit-exact away from the hinge kink) and active-set sums."""
@@ -311,13 +311,20 @@ def test_disc_fused_and_two_pass_agree_with_oracle(B, C, H, W, K):
     coef = torch.empty(B, K, H, W, device=DEV)
     delta = torch.empty(B, K, H, W, device=DEV)
     packed2 = torch.empty(K * (C + 1) + 4, device=DEV)
-    rc = lib.clr_disc_fused_fwd(ptr(xs), ptr(ys), B, C, HW, K, ptr(D), ptr(beta), 0.01, ptr(coef), ptr(delta), ptr(ws),
-                                ws_bytes, ptr(packed2), st)
-    if HW % 4 == 0:
-        check(rc, "clr_disc_fused_fwd")
-        results["fused"] = (coef.cpu().numpy(), packed2.cpu().numpy(), delta.cpu().numpy())
-    else:
-        assert rc == -4          # CLR_ERR_UNSUPPORTED: ragged planes take the two-pass form
+    # both data paths of the one-read kernel: tensor-map TMA tiles (disc_impl = 0, default) and cp.async tiles (= 2)
+    for impl, tag in ((0, "fused_tma"), (2, "fused_cp_async")):
+        try:
+            lib.clr_set_tunable(b"disc_impl", impl)
+            coef.zero_(); delta.zero_(); packed2.zero_()
+            rc = lib.clr_disc_fused_fwd(ptr(xs), ptr(ys), B, C, HW, K, ptr(D), ptr(beta), 0.01, ptr(coef), ptr(delta), ptr(ws),
+                                        ws_bytes, ptr(packed2), st)
+        finally:
+            lib.clr_set_tunable(b"disc_impl", 0)
+        if HW % 4 == 0:
+            check(rc, "clr_disc_fused_fwd")
+            results[tag] = (coef.cpu().numpy(), packed2.cpu().numpy(), delta.cpu().numpy())
+        else:
+            assert rc == -4          # CLR_ERR_UNSUPPORTED: ragged planes take the two-pass form
     # two-pass form
     cap = lib.clr_disc_partials_cap()
     parts = torch.zeros(cap, 1 + K, device=DEV)

@@ -3,6 +3,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cuda_runtime.h>
+#include <cuda.h>
 #include <stdint.h>
 #include <vector>
 #include <algorithm>
@@ -147,6 +148,56 @@ __global__ void __launch_bounds__(NT) read_tile_regs(const float* __restrict__ s
     if (acc == 123.456f) out[blockIdx.x * NT + threadIdx.x] = acc;
 }
 
+
+// ---- TMA tensor-map tile fetch: one cp.async.bulk.tensor.3d per [rows x 32 px] box, 128B swizzle, mbarrier ring ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled() {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (!fn || q != cudaDriverEntryPointSuccess) { printf("cuTensorMapEncodeTiled unavailable\n"); exit(1); }
+    return (EncodeTiledFn)fn;
+}
+template <int STAGES, int NT>
+__global__ void __launch_bounds__(NT) read_tile_tma(const __grid_constant__ CUtensorMap tmap, int B, int C, int HW, int rows_box, int nbox, float* out) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int rt = rows_box * nbox;
+    const size_t stage_bytes = (size_t)rt * 128;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes);
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(&full[s])), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int tps = (HW + 31) / 32, total = B * tps;
+    auto issue = [&](int t, int stage) {
+        if (t < total && tid == 0) {
+            const int b = t / tps, tile = t - b * tps;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(&full[stage])), "r"((uint32_t)stage_bytes) : "memory");
+            for (int j = 0; j < nbox; ++j)
+                asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                             ::"r"(s32(smem + stage * stage_bytes + (size_t)j * rows_box * 128)), "l"(&tmap), "r"(tile * 32), "r"(j * rows_box), "r"(b),
+                               "r"(s32(&full[stage])) : "memory");
+        }
+    };
+    int fetched = blockIdx.x;
+    for (int j = 0; j < STAGES - 1; ++j) { issue(fetched, j); fetched += gridDim.x; }
+    int stage = 0; uint32_t phase = 0;
+    float acc = 0.f;
+    for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        asm volatile("{\n.reg .pred p;\nW3:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra D3;\nbra W3;\nD3:\n}\n" ::"r"(s32(&full[stage])), "r"(phase) : "memory");
+        __syncthreads();
+        int nst = stage + STAGES - 1; if (nst >= STAGES) nst -= STAGES;
+        issue(fetched, nst); fetched += gridDim.x;
+        acc += reinterpret_cast<const float*>(smem + stage * stage_bytes)[(tid % C) * 32 + (tid / C) % 32];
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+    }
+    if (acc == 123.456f) out[blockIdx.x * NT + tid] = acc;
+}
+
 template <typename F>
 float time_us(F f, int iters = 20) {
     cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
@@ -233,6 +284,32 @@ int main(int argc, char** argv) {
         REG_PROBE(32, 256, 4)
         REG_PROBE(8, 1024, 1)
         REG_PROBE(8, 1024, 2)
+
+        {
+            EncodeTiledFn enc = encode_tiled();
+            const int rows_box = 256, nbox = 1;
+#define TMA_PROBE(ST, NT, MULT) { \
+            CUtensorMap maps[NB]; \
+            for (int i = 0; i < NB; ++i) { \
+                cuuint64_t gdim[3] = {(cuuint64_t)HW, (cuuint64_t)C, (cuuint64_t)B}; \
+                cuuint64_t gstr[2] = {(cuuint64_t)HW * 4, (cuuint64_t)C * HW * 4}; \
+                cuuint32_t box[3] = {32, (cuuint32_t)rows_box, 1}; \
+                cuuint32_t estr[3] = {1, 1, 1}; \
+                CUresult r = enc(&maps[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, buf[i], gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, \
+                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE); \
+                if (r != CUDA_SUCCESS) { printf("encode failed %d\n", (int)r); exit(1); } \
+            } \
+            const size_t smem = (size_t)ST * rows_box * nbox * 128 + 64 + 1024; \
+            CK(cudaFuncSetAttribute(read_tile_tma<ST, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            float t = time_us([&](int i) { read_tile_tma<ST, NT><<<sms * MULT, NT, smem>>>(maps[i % NB], B, C, HW, rows_box, nbox, out); }); \
+            CK(cudaGetLastError()); \
+            printf("tile TMA tensor TP=32 stages=%d NT=%d ctas/SM=%d  %8.2f us  %7.1f GB/s\n", ST, NT, MULT, t, bytes / t / 1e3); }
+            TMA_PROBE(3, 256, 2)
+            TMA_PROBE(2, 256, 2)
+            TMA_PROBE(2, 256, 3)
+            TMA_PROBE(6, 256, 1)
+            TMA_PROBE(3, 512, 2)
+        }
         for (int i = 0; i < NB; ++i) CK(cudaFree(buf[i]));
     }
     return 0;

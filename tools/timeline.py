@@ -78,6 +78,9 @@ def main():
             t_first, t_ready, t_last, ncta = buf[4 * i], buf[4 * i + 1], buf[4 * i + 2], buf[4 * i + 3]
             if ncta == 0:
                 continue
+            if t_first == 0:      # per-phase cycle counters (builds with CLR_NVCC_EXTRA=-DCLR_PHASE_PROFILE)
+                print("  %-18s %d cycles" % (slot_names[i], t_last))
+                continue
             rows.append((slot_names[i], t_first, t_ready, t_last, ncta))
         t0 = min(r[1] for r in rows)
         rows.sort(key=lambda r: r[2])

@@ -25,7 +25,7 @@ LIB = os.path.join(LIBDIR, "libclr_b200.so")
 STAMP = os.path.join(LIBDIR, "libclr_b200.stamp")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
-              "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+              "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"] + os.environ.get("CLR_NVCC_EXTRA", "").split()
 
 
 def nvcc_path() -> str:

@@ -21,10 +21,22 @@
 //              Rows are padded by 4 floats so both access patterns are bank-conflict free.
 //   output   = per-CTA partials [K][C+1] (col C = sum of coefficients) + per-CTA hinge sum; combined in
 //              fp64, fixed order, by the pooling reduce kernel -> deterministic.
+#include <cuda.h>   // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, no libcuda link)
 #include "clr_common.cuh"
 #include "clr_internal.h"
 
 namespace clr {
+
+// Per-phase cycle accounting of CTA 0 (build with -DCLR_PHASE_PROFILE; read through the trace slots dbg0..dbg4)
+#ifdef CLR_PHASE_PROFILE
+#define PH_DECL long long ph_t = clock64(), ph_acc[5] = {0, 0, 0, 0, 0};
+#define PH_MARK(i) { const long long now_ = clock64(); ph_acc[i] += now_ - ph_t; ph_t = now_; }
+#define PH_FLUSH if (g_trace_dev && blockIdx.x == 0 && threadIdx.x == 0) { for (int i_ = 0; i_ < 5; ++i_) { g_trace_dev[TR_DBG0 + i_].t_first = 0; g_trace_dev[TR_DBG0 + i_].t_ready = 0; g_trace_dev[TR_DBG0 + i_].t_last = (unsigned long long)ph_acc[i_]; g_trace_dev[TR_DBG0 + i_].n_cta = 1; } }
+#else
+#define PH_DECL
+#define PH_MARK(i)
+#define PH_FLUSH
+#endif
 
 struct DiscParams {
     const float* xs;
@@ -37,6 +49,7 @@ struct DiscParams {
     float* hinge;           // [grid]
     float alpha, margin;
     int B, C, HW, tilesPerSample, total, stages;
+    int rows_box, nbox;     // TMA path: the [C x 32] tile is fetched as nbox boxes of rows_box channel rows (rows_box % 8 == 0)
 };
 
 constexpr int kDiscPad = 4;
@@ -52,23 +65,48 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int K, int TP, int STAGES, int NT>
-__global__ void __launch_bounds__(NT, (TP == 32) ? 2 : 1) disc_fused_kernel(const DiscParams p) {
+// One box of a rank-3 tensor map (pixels, channels, samples) -> shared memory; completion on `bar` (complete_tx bytes).
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tmap, int x, int y, int z, uint64_t* bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;"
+        ::"r"(smem_u32(dst)), "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+
+// TMA = false: tile rows fetched with 16-byte cp.async (LDGSTS) by all threads into padded rows.
+// TMA = true : the whole [C x 32] tile is ONE cp.async.bulk.tensor box per <= 256 channel rows (rank-3 tensor map
+//              (pixel, channel, sample), 128-byte swizzle instead of padding, zero fill past ragged edges), issued by one
+//              thread; completion through an mbarrier per stage.  The LDGSTS form is bound by the SM's load/store
+//              pipe (measured: ~2300 cycles per tile spent behind the next tile's 2048 LDGSTS, none waiting for
+//              data), the tensor form leaves that pipe to the two compute phases.
+template <int K, int TP, int STAGES, int NT, bool TMA>
+__global__ void __launch_bounds__(NT, (TP == 32 && STAGES <= 4) ? 2 : 1) disc_fused_kernel(const DiscParams p, const __grid_constant__ CUtensorMap tmap) {
     kernel_begin(TR_DISC);
-    constexpr int RS = TP + kDiscPad;            // row stride (floats)
+    static_assert(!TMA || TP == 32, "the tensor-map path uses 128-byte rows");
+    constexpr int RS = TMA ? TP : TP + kDiscPad; // row stride (floats): dense + swizzled (TMA) or padded (cp.async)
     constexpr int NG = TP / 4;                   // pixel quads (16-byte chunks) per row
     constexpr int NS = NT / NG;                  // channel slices in phase 1
     constexpr int NW = NT / 32;                  // warps
     constexpr int PS = NT / kDiscCols;           // pixel splits in phase 2
     constexpr int NE = (K * TP + NT - 1) / NT;   // epilogue iterations per thread
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const size_t stage_floats = (size_t)p.C * RS;
-    float* tiles = reinterpret_cast<float*>(smem_raw);                       // [STAGES][C][RS]
+    extern __shared__ __align__(1024) unsigned char smem_raw[];              // 128B swizzle: stages 1024-byte aligned
+    const int rows_total = TMA ? p.rows_box * p.nbox : p.C;
+    const size_t stage_floats = (size_t)rows_total * RS;
+    float* tiles = reinterpret_cast<float*>(smem_raw);                       // [STAGES][rows][RS]
     float* red = tiles + (size_t)STAGES * stage_floats;                      // [NW][K][TP]
     float* cfs = red + (size_t)NW * K * TP;                              // [K][TP]
     float* wred = cfs + (size_t)K * TP;                                      // [1 + NE][NW]
+    uint64_t* full = reinterpret_cast<uint64_t*>(wred + (1 + NE) * NW + ((1 + NE) * NW & 1));   // [STAGES] (TMA), 8-byte aligned
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (TMA) {
+        if (tid == 0) {
+            for (int st = 0; st < STAGES; ++st) mbar_init(&full[st], 1);
+            fence_mbar_init();
+        }
+        __syncthreads();
+    }
+    // physical float offset of 16-byte chunk `q` in row `c`: XOR swizzle (TMA) or identity (padded rows)
+    auto chunk_off = [&](int c, int q) -> int { return TMA ? 4 * (q ^ (c & 7)) : 4 * q; };
 
     // Tiles are dealt round-robin (CTA k: tiles k, k+grid, ..): at any moment the resident CTAs fetch ADJACENT
     // 128-byte segments of the same channel rows, which keeps DRAM pages open across CTAs -- a contiguous range
@@ -79,7 +117,18 @@ __global__ void __launch_bounds__(NT, (TP == 32) ? 2 : 1) disc_fused_kernel(cons
     // column, r0 = tid / NG row) copies rows r0, r0 + NS, ..: pointer increments only.  Columns past a ragged plane
     // end are zero-filled.
     const int fq = tid % NG, fr0 = tid / NG;
+    uint64_t pol_stream = 0;
+    if (TMA && tid == 0) pol_stream = policy_evict_first();
     auto issue = [&](int b, int tile, int stage) {
+        if (TMA) {
+            if (tid == 0 && b < p.B) {
+                mbar_arrive_expect_tx(&full[stage], (uint32_t)(stage_floats * sizeof(float)));
+                for (int j = 0; j < p.nbox; ++j)
+                    tma_load_3d(tiles + (size_t)stage * stage_floats + (size_t)j * p.rows_box * RS, &tmap, tile * TP, j * p.rows_box, b,
+                                &full[stage], pol_stream);
+            }
+            return;
+        }
         if (b < p.B) {
             const int px0 = tile * TP;
             const int nchunk = ((p.HW - px0) < TP ? (p.HW - px0) : TP) / 4;
@@ -120,6 +169,8 @@ __global__ void __launch_bounds__(NT, (TP == 32) ? 2 : 1) disc_fused_kernel(cons
         advance(fb, ftile); fetched += step;
     }
     int stage = 0;
+    uint32_t phase = 0;
+    PH_DECL
     for (int it = begin; it < end; it += step, advance(b, tile)) {
         const int px0 = tile * TP;
         const int npx = (p.HW - px0) < TP ? (p.HW - px0) : TP;
@@ -131,8 +182,11 @@ __global__ void __launch_bounds__(NT, (TP == 32) ? 2 : 1) disc_fused_kernel(cons
             const int k = e / TP, j = e - k * TP;
             yv[ei] = (e < K * TP && j < npx) ? __ldg(p.ys + ((size_t)b * K + k) * p.HW + px0 + j) : 0.f;
         }
-        cp_async_wait<STAGES - 2>();     // this thread's copies of tile `it` have landed
+        PH_MARK(4)
+        if (TMA) mbar_wait(&full[stage], phase);     // the tile's boxes have landed
+        else cp_async_wait<STAGES - 2>();            // this thread's copies of tile `it` have landed
         __syncthreads();                 // ... everyone's have, and everyone is done with the previous tile
+        PH_MARK(0)
         {
             int nst = stage + STAGES - 1;
             if (nst >= STAGES) nst -= STAGES;
@@ -148,7 +202,7 @@ __global__ void __launch_bounds__(NT, (TP == 32) ? 2 : 1) disc_fused_kernel(cons
             for (int v = 0; v < 4; ++v) acc[k][v] = 0.f;
 #pragma unroll 4
         for (int c = s; c < p.C; c += NS) {
-            const float4 x = *reinterpret_cast<const float4*>(xt + (size_t)c * RS + 4 * g);
+            const float4 x = *reinterpret_cast<const float4*>(xt + (size_t)c * RS + chunk_off(c, g));
             float vv[K];   // D_k[c]: 4 KB table, read through L1 (saves the shared-memory copy: a third stage fits)
 #pragma unroll
             for (int k = 0; k < K; ++k) vv[k] = __ldg(p.V + (size_t)k * p.C + c);
@@ -176,6 +230,7 @@ __global__ void __launch_bounds__(NT, (TP == 32) ? 2 : 1) disc_fused_kernel(cons
                     make_float4(acc[k][0], acc[k][1], acc[k][2], acc[k][3]);
         }
         __syncthreads();
+        PH_MARK(1)
         // ---- epilogue: thread e -> (k, pixel j) ------------------------------------------------------
 #pragma unroll
         for (int ei = 0; ei < NE; ++ei) {
@@ -199,6 +254,7 @@ __global__ void __launch_bounds__(NT, (TP == 32) ? 2 : 1) disc_fused_kernel(cons
             ncf[ei] += cf;
         }
         __syncthreads();
+        PH_MARK(2)
         // ---- phase 2: coefficient-weighted sums over the pixel axis.  Thread = (channel column cp, pixel quarter h):
         //      it walks channels cp, cp+64, .. over its quarter of the tile's pixels, so the coefficient loads
         //      are shared by all of the thread's channels (12 LDS.128 per 64 FMA at C = 256, K = 2)
@@ -215,10 +271,10 @@ __global__ void __launch_bounds__(NT, (TP == 32) ? 2 : 1) disc_fused_kernel(cons
             for (int i = 0; i < kDiscMaxCPT; ++i) {
                 const int c = cp + i * kDiscCols;
                 if (c < p.C) {
-                    const float* row = xt + (size_t)c * RS + 4 * h * JQ;
+                    const float* row = xt + (size_t)c * RS;
 #pragma unroll
                     for (int jq = 0; jq < JQ; ++jq) {
-                        const float4 x = *reinterpret_cast<const float4*>(row + 4 * jq);
+                        const float4 x = *reinterpret_cast<const float4*>(row + chunk_off(c, h * JQ + jq));
 #pragma unroll
                         for (int k = 0; k < K; ++k) {
                             A[i][k] = fmaf(x.x, cf[jq][k].x, A[i][k]);
@@ -230,11 +286,13 @@ __global__ void __launch_bounds__(NT, (TP == 32) ? 2 : 1) disc_fused_kernel(cons
                 }
             }
         }
-        if (++stage == STAGES) stage = 0;
+        PH_MARK(3)
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         // `red` is next written after the next tile's first barrier, `cfs` after its second: both after every
         // thread finished this tile's phase 2, so no trailing barrier is needed
     }
-    cp_async_wait<0>();
+    PH_FLUSH
+    if (!TMA) cp_async_wait<0>();
     // ---- CTA partials: the 4 pixel quarters of every (k, c) are combined through shared memory (tiles are free now)
     __syncthreads();
     {
@@ -289,27 +347,108 @@ static size_t disc_smem(int C, int stages) {
     size_t fl = (size_t)stages * C * RS + (size_t)NW * K * TP + (size_t)K * TP + (1 + NE) * NW;
     const size_t comb = (size_t)(NT / kDiscCols) * K * C;     // end-of-kernel combine buffer aliases the tile ring
     if (comb > (size_t)stages * C * RS) fl += comb - (size_t)stages * C * RS;
-    return fl * sizeof(float);
+    return fl * sizeof(float) + 16;
 }
 
-template <int K, int TP, int STAGES, int NT>
-static int launch_disc_s(DiscParams& p, int* nparts, cudaStream_t st) {
-    const size_t smem = disc_smem<K, TP, NT>(p.C, STAGES);
-    auto kern = disc_fused_kernel<K, TP, STAGES, NT>;
-    CLR_RETURN_IF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 0;
-    CLR_RETURN_IF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem));
-    if (occ < 1) return CLR_ERR_UNSUPPORTED;
+// tensor-map path: dense 128-byte rows (rows_total >= C, a multiple of 8), one mbarrier per stage
+template <int K, int NT>
+static size_t disc_smem_tma(int C, int rows_total, int stages) {
+    constexpr int TP = 32, NW = NT / 32, NE = (K * TP + NT - 1) / NT;
+    size_t fl = (size_t)stages * rows_total * TP + (size_t)NW * K * TP + (size_t)K * TP + (1 + NE) * NW + 2;
+    const size_t comb = (size_t)(NT / kDiscCols) * K * C;
+    if (comb > (size_t)stages * rows_total * TP) fl += comb - (size_t)stages * rows_total * TP;
+    return fl * sizeof(float) + sizeof(uint64_t) * stages;
+}
+
+static int finish_launch_geometry(DiscParams& p, int TP, int occ, int* nparts) {
     p.tilesPerSample = (p.HW + TP - 1) / TP;
     const long long total = (long long)p.B * p.tilesPerSample;
-    if (total > 0x3fffffff) return CLR_ERR_UNSUPPORTED;
+    if (total > 0x3fffffff) return -1;
     p.total = (int)total;
     int grid = device_facts().sms * occ;
     if (grid > p.total) grid = p.total;
     if (grid > *nparts) grid = *nparts;
     *nparts = grid;
-    clr::launch_k(kern, grid, NT, smem, st, p);
+    return grid;
+}
+
+template <int K, int TP, int STAGES, int NT>
+static int launch_disc_s(DiscParams& p, int* nparts, cudaStream_t st) {
+    const size_t smem = disc_smem<K, TP, NT>(p.C, STAGES);
+    auto kern = disc_fused_kernel<K, TP, STAGES, NT, false>;
+    CLR_RETURN_IF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CLR_RETURN_IF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem));
+    if (occ < 1) return CLR_ERR_UNSUPPORTED;
+    const int grid = finish_launch_geometry(p, TP, occ, nparts);
+    if (grid < 1) return CLR_ERR_UNSUPPORTED;
+    CUtensorMap unused{};
+    clr::launch_k(kern, grid, NT, smem, st, p, unused);
     return launch_status();
+}
+
+// ---- tensor map for xs viewed as (pixel HW, channel C, sample B), box = (32 pixels, rows_box channels, 1 sample) -----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            f = nullptr;
+        }
+        return reinterpret_cast<EncodeTiledFn>(f);
+    }();
+    return fn;
+}
+
+static bool make_feature_tmap(const float* xs, int B, int C, int HW, int rows_box, CUtensorMap* out) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return false;
+    const cuuint64_t gdim[3] = {(cuuint64_t)HW, (cuuint64_t)C, (cuuint64_t)B};
+    const cuuint64_t gstr[2] = {(cuuint64_t)HW * sizeof(float), (cuuint64_t)C * HW * sizeof(float)};
+    const cuuint32_t box[3] = {32u, (cuuint32_t)rows_box, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    return enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(xs), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int K, int STAGES, int NT>
+static int launch_disc_tma_s(DiscParams& p, const CUtensorMap& tmap, int* nparts, cudaStream_t st) {
+    const size_t smem = disc_smem_tma<K, NT>(p.C, p.rows_box * p.nbox, STAGES);
+    auto kern = disc_fused_kernel<K, 32, STAGES, NT, true>;
+    CLR_RETURN_IF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CLR_RETURN_IF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem));
+    if (occ < 1) return CLR_ERR_UNSUPPORTED;
+    const int grid = finish_launch_geometry(p, 32, occ, nparts);
+    if (grid < 1) return CLR_ERR_UNSUPPORTED;
+    clr::launch_k(kern, grid, NT, smem, st, p, tmap);
+    return launch_status();
+}
+
+// Tensor-map path: two CTAs per SM with a 3-stage (else 2-stage) ring; 512-thread CTAs on request when K <= 2.
+template <int K>
+static int launch_disc_tma(DiscParams& p, int* nparts, cudaStream_t st) {
+    if (p.HW < 32 || p.HW % 4 != 0 || !aligned16(p.xs)) return CLR_ERR_UNSUPPORTED;
+    p.nbox = (p.C + 255) / 256;
+    p.rows_box = (((p.C + p.nbox - 1) / p.nbox) + 7) & ~7;
+    CUtensorMap tmap;
+    if (!make_feature_tmap(p.xs, p.B, p.C, p.HW, p.rows_box, &tmap)) return CLR_ERR_UNSUPPORTED;
+    const size_t budget = (size_t)device_facts().max_smem_optin;
+    const size_t per_cta = (budget - 2048) / 2;
+    const int rt = p.rows_box * p.nbox;
+    constexpr bool wide = (K <= 2);
+    if (wide && tunables().disc_threads == 512) {
+        if (disc_smem_tma<K, 512>(p.C, rt, 3) <= per_cta) return launch_disc_tma_s<K, 3, 512>(p, tmap, nparts, st);
+        if (disc_smem_tma<K, 512>(p.C, rt, 2) <= per_cta) return launch_disc_tma_s<K, 2, 512>(p, tmap, nparts, st);
+    }
+    if (disc_smem_tma<K, 256>(p.C, rt, 3) <= per_cta) return launch_disc_tma_s<K, 3, 256>(p, tmap, nparts, st);
+    if (disc_smem_tma<K, 256>(p.C, rt, 2) <= per_cta) return launch_disc_tma_s<K, 2, 256>(p, tmap, nparts, st);
+    if (disc_smem_tma<K, 256>(p.C, rt, 2) <= budget) return launch_disc_tma_s<K, 2, 256>(p, tmap, nparts, st);
+    return CLR_ERR_UNSUPPORTED;
 }
 
 template <int K, int TP>
@@ -326,6 +465,20 @@ static int launch_disc(DiscParams& p, int* nparts, cudaStream_t st) {
     if (disc_smem<K, TP, 256>(p.C, 4) <= per_cta) return launch_disc_s<K, TP, 4, 256>(p, nparts, st);
     if (disc_smem<K, TP, 256>(p.C, 3) <= per_cta) return launch_disc_s<K, TP, 3, 256>(p, nparts, st);
     if (disc_smem<K, TP, 256>(p.C, 2) <= budget) return launch_disc_s<K, TP, 2, 256>(p, nparts, st);
+    return CLR_ERR_UNSUPPORTED;
+}
+
+static int dispatch_disc_tma(int K, DiscParams& p, int* nparts, cudaStream_t st) {
+    switch (K) {
+        case 1: return launch_disc_tma<1>(p, nparts, st);
+        case 2: return launch_disc_tma<2>(p, nparts, st);
+        case 3: return launch_disc_tma<3>(p, nparts, st);
+        case 4: return launch_disc_tma<4>(p, nparts, st);
+        case 5: return launch_disc_tma<5>(p, nparts, st);
+        case 6: return launch_disc_tma<6>(p, nparts, st);
+        case 7: return launch_disc_tma<7>(p, nparts, st);
+        case 8: return launch_disc_tma<8>(p, nparts, st);
+    }
     return CLR_ERR_UNSUPPORTED;
 }
 
@@ -360,6 +513,11 @@ int disc_fused_impl(const float* xs, const float* ys, int B, int C, int HW, int 
     // "disc_tile" tunable: 0 auto (32-pixel tiles, two CTAs per SM), 64 = 64-pixel tiles, one CTA per SM
     int n = *nparts;
     int rc = CLR_ERR_UNSUPPORTED;
+    // "disc_impl": 0 auto = tensor-map TMA tiles, 2 = cp.async (LDGSTS) tiles, (1 = two-pass form, handled by the caller)
+    if (tunables().disc_impl != 2 && tunables().disc_tile != 64) rc = dispatch_disc_tma(K, p, &n, st);
+    if (rc == CLR_OK) { *nparts = n; return rc; }
+    if (rc != CLR_ERR_UNSUPPORTED) return rc;
+    n = *nparts;
     if (tunables().disc_tile == 64) rc = dispatch_disc_k<64>(K, p, &n, st);
     if (rc == CLR_ERR_UNSUPPORTED) { n = *nparts; rc = dispatch_disc_k<32>(K, p, &n, st); }
     if (rc == CLR_ERR_UNSUPPORTED && tunables().disc_tile != 64) { n = *nparts; rc = dispatch_disc_k<64>(K, p, &n, st); }
