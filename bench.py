@@ -56,6 +56,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=25.0)
     ap.add_argument("--tunable", action="append", default=[], help="library knob name=value (clr_set_tunable)")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: in-kernel exchange over peer-mapped memory (default) or NCCL all-reduce between phases")
     return ap.parse_args()
 
 
@@ -191,7 +193,9 @@ def config_dict(a, n_gpus):
                         "align: A1 hard source + A1 soft target + A4 + A5, fwd+bwd (Trainer_prototype_full.py:330-449)",
             "per_gpu_batch": a.B, "global_batch": a.B * n_gpus, "channels": a.C, "feature_hw": [a.H, a.H],
             "image_hw": [a.H * a.up, a.H * a.up], "classes": a.K, "mc_passes": a.T,
-            "parallelism": "dp%d (batch-sharded, all-reduce of packed class sums)" % n_gpus,
+            "parallelism": "dp%d (batch-sharded; packed class sums exchanged %s)" % (
+                n_gpus, "inside the step's kernels over NVLink peer memory" if (a.exchange == "peer" and n_gpus > 1) else
+                ("by NCCL all-reduce" if n_gpus > 1 else "-")),
             "l2_policy": "inputs larger than L2: 2 rotating input sets, each step streams > 700 MB vs 126 MB L2",
             "baseline_config": "BASELINE.json configs[0] shape (B=8, 256ch, 128x128, K=2) = the per-GPU CLR workload of configs[1]"}
 
@@ -231,7 +235,10 @@ def main():
         import torch.distributed as dist
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
-        clr.dist.enable()
+        if a.exchange == "peer":
+            clr.dist.enable_peer()
+        else:
+            clr.dist.enable()
     lib = _lib.load()
     for kv in a.tunable:
         name, val = kv.split("=")

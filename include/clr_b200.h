@@ -30,6 +30,7 @@ extern "C" {
 
 #define CLR_B200_VERSION 100 /* major*100 + minor */
 #define CLR_MAX_K 8          /* classes per call */
+#define CLR_MAX_WORLD 8      /* ranks of one NVLink domain that can share the fused step's in-kernel exchange */
 
 typedef void* clr_stream_t;
 
@@ -276,7 +277,25 @@ typedef struct clr_step_args {
     /* optional second stream + two events (clr_event_create) for clr_step_run: the consistency pass and the
      * backward of the target features run on `aux_stream` concurrently with the discriminative pass */
     void* aux_stream; void* ev_fork; void* ev_join;
+    /* Sharded step with the exchange INSIDE the kernels (clr_step_run only; world <= 1: unused).  peer_rx[q] is rank q's
+     * receive buffer (clr_step_xchg_bytes bytes, zeroed once, see clr_peer_*) mapped into THIS process; peer_rx[rank] is
+     * the local one.  `seq` must be the same on every rank and change by +1 per clr_step_run call (start at 1).  The
+     * finish stages push their packed sums to every peer as (value, seq) 64-bit words over NVLink and sum the G
+     * contributions in rank order from their own buffer -- one NVLink traversal, no fences, no extra launches, every rank
+     * obtains bit-identical sums.  losses[7] is set to 1 if a peer did not answer within ~2 s. */
+    int world, rank;
+    unsigned int seq; int reserved0;
+    void* peer_rx[CLR_MAX_WORLD];
 } clr_step_args;
+
+/* Peer-visible device memory for the in-kernel exchange: plain cudaMalloc (zero-filled) + CUDA IPC handles, so that a
+ * host in any language can wire the ranks of one node together (exchange the 64-byte handles over its own channel). */
+int clr_peer_alloc(size_t bytes, void** ptr);
+int clr_peer_free(void* ptr);
+int clr_peer_export(void* ptr, unsigned char handle[64]);
+int clr_peer_open(const unsigned char handle[64], void** ptr);
+int clr_peer_close(void* ptr);
+size_t clr_step_xchg_bytes(int world, int K, int C);
 
 size_t clr_step_ws_bytes(const clr_step_args* a);
 int clr_step_fwd_a(const clr_step_args* a, clr_stream_t stream);

@@ -38,7 +38,7 @@ def main():
     mine = {k: v[lo:hi].contiguous() for k, v in full.items()}
     preds_mine = preds[:, lo:hi].reshape(T * (hi - lo), K, H * up, H * up).contiguous()
     ok = True
-    for variant in ("align", "clr3"):
+    for variant, mode in (("align", "nccl"), ("clr3", "nccl"), ("align", "peer"), ("clr3", "peer"), ("clr3", "peer_plan")):
         use3 = variant == "clr3"
         # single-GPU reference on the whole batch (every rank computes it redundantly)
         ref = clr.CLRStep(K=K, retrify=use3, use_disc=use3, use_cons=use3, backprop_aug=use3)
@@ -49,13 +49,29 @@ def main():
                         oT=full["oT"], oT_aug=a_f) if use3 else dict(wt=torch.sigmoid(full["oT_before"]))
             out_f = ref(xs_f, full["ys"], xt_f, **kw_f)
             out_f.total.backward()
-            clr.dist.enable()
+            # nccl: all-reduce of the packed sums between the step's phases; peer: the exchange runs inside the step's
+            # own kernels over peer-mapped memory (autograd call path / prebound plan)
+            if mode == "nccl":
+                clr.dist.enable()
+            else:
+                clr.dist.enable_peer()
             xs_s, xt_s, a_s = (mine[k].clone().requires_grad_(True) for k in ("xs", "xt", "oT_aug"))
             kw_s = dict(oT_before=mine["oT_before"], preds=preds_mine, T=T, oT=mine["oT"], oT_aug=a_s) if use3 \
                 else dict(wt=torch.sigmoid(mine["oT_before"]))
-            out_s = sh(xs_s, mine["ys"], xt_s, **kw_s)
-            out_s.total.backward()
+            if mode == "peer_plan":
+                plan = sh.plan(xs_s.detach(), mine["ys"], xt_s.detach(), **{k: (v.detach() if torch.is_tensor(v) else v) for k, v in kw_s.items()})
+                plan.run()
+                out_s = plan.outputs()
+                xs_s.grad, xt_s.grad, a_s.grad = plan.gxs, plan.gxt, plan.g_oT_aug
+                timeout_flag = float(plan.losses[7])
+            else:
+                out_s = sh(xs_s, mine["ys"], xt_s, **kw_s)
+                out_s.total.backward()
+                timeout_flag = 0.0
             clr.dist.disable()
+            if timeout_flag != 0.0:
+                print("rank %d: exchange timeout flag set" % rank, flush=True)
+                ok = False
             errs = dict(
                 total=abs(float(out_s.total) - float(out_f.total)) / abs(float(out_f.total)),
                 Ps=relerr(torch.cat(out_s.source_prototypes), torch.cat(out_f.source_prototypes)),
@@ -67,7 +83,7 @@ def main():
                 errs["disc"] = abs(float(out_s.disc) - float(out_f.disc)) / abs(float(out_f.disc))
                 errs["aug"] = abs(float(out_s.aug) - float(out_f.aug)) / abs(float(out_f.aug))
             bad = {k: v for k, v in errs.items() if not (v < (1e-5 if k in ("Ps", "Pt") else 1e-4))}
-            print("rank %d %s step %d: %s %s" % (rank, variant, it, {k: "%.1e" % v for k, v in errs.items()},
+            print("rank %d %s/%s step %d: %s %s" % (rank, variant, mode, it, {k: "%.1e" % v for k, v in errs.items()},
                                                    "FAIL " + str(bad) if bad else "ok"), flush=True)
             ok = ok and not bad
     flag = torch.tensor([0 if ok else 1], device=dev)

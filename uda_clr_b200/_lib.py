@@ -17,6 +17,7 @@ CLR_W_COMPLEMENT = 0
 CLR_W_EXPLICIT = 1
 CLR_MAX_K = 8
 CLR_ERR_UNSUPPORTED = -4
+CLR_MAX_WORLD = 8
 
 _lock = threading.Lock()
 _lib = None
@@ -56,6 +57,7 @@ class StepArgs(Structure):
         ("ws", _P), ("ws_bytes", c_size_t),
         ("ev_pool_begin", _P), ("ev_pool_end", _P), ("ev_bwd_begin", _P), ("ev_bwd_end", _P),
         ("aux_stream", _P), ("ev_fork", _P), ("ev_join", _P),
+        ("world", c_int), ("rank", c_int), ("seq", ctypes.c_uint), ("reserved0", c_int), ("peer_rx", _P * 8),
     ]
 
 
@@ -68,6 +70,12 @@ _SIGNATURES = {
     "clr_event_create": (c_int, [POINTER(c_void_p)]),
     "clr_event_destroy": (c_int, [c_void_p]),
     "clr_event_elapsed_us": (c_int, [c_void_p, c_void_p, POINTER(c_float)]),
+    "clr_peer_alloc": (c_int, [c_size_t, POINTER(c_void_p)]),
+    "clr_peer_free": (c_int, [c_void_p]),
+    "clr_peer_export": (c_int, [c_void_p, c_char_p]),
+    "clr_peer_open": (c_int, [c_char_p, POINTER(c_void_p)]),
+    "clr_peer_close": (c_int, [c_void_p]),
+    "clr_step_xchg_bytes": (c_size_t, [c_int, c_int, c_int]),
     "clr_trace_enable": (c_int, [c_int]),
     "clr_trace_slots": (c_int, []),
     "clr_trace_name": (c_char_p, [c_int]),

@@ -53,6 +53,43 @@ __device__ __forceinline__ double strided_slot_sum(const float* __restrict__ col
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// In-kernel exchange of the packed sums between the ranks of one NVLink domain ("LL" style: value and sequence number
+// travel in ONE 64-bit store, so a reader that sees the expected sequence number has the value -- no fences, no
+// flags, one NVLink traversal).  Every rank owns a receive buffer [2 parities][world sources][n words]; a sender
+// writes its word into slot [parity][its rank][idx] of EVERY rank's buffer (its own included), a receiver sums the
+// `world` words of one index in rank order, so all ranks compute bit-identical totals.  Two parities: a rank can run
+// at most one exchange ahead of the slowest peer (it needs that peer's next contribution to go further).
+// ---------------------------------------------------------------------------------------------------------------
+struct PeerXchg {
+    unsigned long long* rx[CLR_MAX_WORLD];   // rank q's receive area for THIS exchange (peer-mapped); rx[rank] is local
+    int world, rank;
+    unsigned int seq;
+    int n;                                   // words per source
+    float* err;                              // set to 1 on timeout (losses[7])
+};
+__device__ __forceinline__ void xchg_push(const PeerXchg& x, int idx, float v) {
+    const unsigned long long w = ((unsigned long long)x.seq << 32) | (unsigned long long)__float_as_uint(v);
+    const size_t off = ((size_t)(x.seq & 1u) * x.world + x.rank) * x.n + idx;
+    for (int q = 0; q < x.world; ++q) *reinterpret_cast<volatile unsigned long long*>(x.rx[q] + off) = w;
+}
+__device__ __forceinline__ float xchg_pull_sum(const PeerXchg& x, int idx) {
+    const volatile unsigned long long* base = x.rx[x.rank] + (size_t)(x.seq & 1u) * x.world * x.n + idx;
+    double s = 0.0;
+    for (int q = 0; q < x.world; ++q) {
+        unsigned long long w = base[(size_t)q * x.n];
+        if ((unsigned int)(w >> 32) != x.seq) {
+            const long long t0 = clock64();
+            do {
+                w = base[(size_t)q * x.n];
+                if (clock64() - t0 > 4000000000LL) { if (x.err) *x.err = 1.f; break; }     // ~2 s: a peer is gone
+            } while ((unsigned int)(w >> 32) != x.seq);
+        }
+        s += (double)__uint_as_float((unsigned int)(w & 0xffffffffull));
+    }
+    return (float)s;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // pool finish: CTA = 8 channels.  Warp w takes the (domain d, row r) pairs w, w+8, ..: it reduces the column block
 // [c0, c0+8) of partial[d][slot][r][.] over the slots with 4 slot-lanes per channel (fp64, fixed order) plus the pair's
 // weight-sum column; then K*8 threads do the align_finalize arithmetic for the CTA's channels; the loss terms are
@@ -74,6 +111,7 @@ struct PoolFinishParams {
     float* losses;
     double* loss_partial;      // [ctas][2 + CLR_MAX_K]
     unsigned int* counter;
+    PeerXchg x;                // world > 1: sum the packed sums over the ranks before the finalize arithmetic
 };
 static inline int pool_finish_ctas(int C) { return (C + 7) / 8; }
 
@@ -97,8 +135,29 @@ __device__ __forceinline__ void pool_finish_body(const PoolFinishParams& p, cons
         s += __shfl_xor_sync(0xffffffffu, s, 1);
         s += __shfl_xor_sync(0xffffffffu, s, 2);
         nn = warp_sum(nn);
-        if (sl0 == 0 && c < C) { S[d][r][ch] = (float)s; p.sums[d][(size_t)r * (C + 1) + c] = (float)s; }
-        if (lane == 0) { Nn[d][r] = (float)nn; if (cta == 0) p.sums[d][(size_t)r * (C + 1) + C] = (float)nn; }
+        if (p.x.world > 1) {          // this rank's contribution goes to every rank (word index = position in packed1)
+            if (sl0 == 0 && c < C) xchg_push(p.x, (d * R + r) * (C + 1) + c, (float)s);
+            if (lane == 0 && cta == 0) xchg_push(p.x, (d * R + r) * (C + 1) + C, (float)nn);
+        } else {
+            if (sl0 == 0 && c < C) { S[d][r][ch] = (float)s; p.sums[d][(size_t)r * (C + 1) + c] = (float)s; }
+            if (lane == 0) { Nn[d][r] = (float)nn; if (cta == 0) p.sums[d][(size_t)r * (C + 1) + C] = (float)nn; }
+        }
+    }
+    if (p.x.world > 1) {
+        // global sums: thread t < 2R*8 owns (pair, channel), the next 2R threads the weight-sum columns
+        if (tid < 2 * R * 8) {
+            const int pair = tid >> 3, j = tid & 7, d = pair / R, r = pair - d * R, cc = cta * 8 + j;
+            if (cc < C) {
+                const float v = xchg_pull_sum(p.x, (d * R + r) * (C + 1) + cc);
+                S[d][r][j] = v;
+                p.sums[d][(size_t)r * (C + 1) + cc] = v;
+            }
+        } else if (tid < 2 * R * 8 + 2 * R) {
+            const int pair = tid - 2 * R * 8, d = pair / R, r = pair - d * R;
+            const float v = xchg_pull_sum(p.x, (d * R + r) * (C + 1) + C);
+            Nn[d][r] = v;
+            if (cta == 0) p.sums[d][(size_t)r * (C + 1) + C] = v;
+        }
     }
     __syncthreads();
     if (tid < K * 8) {
@@ -186,6 +245,7 @@ struct DiscFinishParams {
     float w_disc, ema_factor, gscale, w_intra, w_inter, w_aug, aug_weight;
     int use_cons;
     PackSrc ps;
+    PeerXchg x;       // world > 1: sum the active-set sums and the loss numerators over the ranks
 };
 static inline int disc_finish_ctas(int C) { return (C + 7) / 8 + 1; }
 
@@ -215,9 +275,15 @@ __device__ __forceinline__ void disc_finish_body(const DiscFinishParams& p, cons
         __syncthreads();
         if (tid < K * 8) {
             const int kk = tid >> 3, j = tid & 7, cc = cta * 8 + j;
-            const float nk = (float)(((Nq[kk][0] + Nq[kk][1]) + Nq[kk][2]) + Nq[kk][3]);
+            float nk = (float)(((Nq[kk][0] + Nq[kk][1]) + Nq[kk][2]) + Nq[kk][3]);
+            float A = (float)(((Sq[kk][0][j] + Sq[kk][1][j]) + Sq[kk][2][j]) + Sq[kk][3][j]);
+            if (p.x.world > 1) {
+                if (cc < C) xchg_push(p.x, kk * (C + 1) + cc, A);
+                if (cta == 0 && j == 0) xchg_push(p.x, kk * (C + 1) + C, nk);
+                if (cc < C) A = xchg_pull_sum(p.x, kk * (C + 1) + cc);
+                nk = xchg_pull_sum(p.x, kk * (C + 1) + C);
+            }
             if (cc < C) {
-                const float A = (float)(((Sq[kk][0][j] + Sq[kk][1][j]) + Sq[kk][2][j]) + Sq[kk][3][j]);
                 p.packed2[(size_t)kk * (C + 1) + cc] = A;
                 const float po = p.P_s[(size_t)kk * C + cc], pb = p.P_s[(size_t)(K + kk) * C + cc];
                 p.g_s[(size_t)kk * C + cc] += p.ema_factor * p.w_disc * p.coef * (nk * po - A);
@@ -244,13 +310,19 @@ __device__ __forceinline__ void disc_finish_body(const DiscFinishParams& p, cons
     block_sum_n<3>(v, shp);
     if (tid == 0) {
         float* tail = p.packed2 + (size_t)K * (C + 1);
-        tail[0] = (float)v[0]; tail[1] = (float)v[1]; tail[2] = (float)v[2]; tail[3] = 0.f;
-        const float disc = (float)((double)(float)v[0] / p.npx);
-        const float aug = p.use_cons ? (float)((double)(float)v[1] / (double)(float)v[2] * (double)p.aug_weight) : 0.f;
+        float t[3] = {(float)v[0], (float)v[1], (float)v[2]};
+        if (p.x.world > 1) {
+            for (int i = 0; i < 3; ++i) xchg_push(p.x, K * (C + 1) + i, t[i]);
+            for (int i = 0; i < 3; ++i) t[i] = xchg_pull_sum(p.x, K * (C + 1) + i);
+        }
+        tail[0] = t[0]; tail[1] = t[1]; tail[2] = t[2]; tail[3] = 0.f;
+        const float disc = (float)((double)t[0] / p.npx);
+        const float aug = p.use_cons ? (float)((double)t[1] / (double)t[2] * (double)p.aug_weight) : 0.f;
         p.losses[2] = disc;
         p.losses[3] = aug;
         p.losses[4] = p.w_intra * p.losses[0] + p.w_inter * p.losses[1] + p.w_disc * disc + p.w_aug * aug;
-        p.losses[5] = 0.f; p.losses[6] = 0.f; p.losses[7] = 0.f;
+        p.losses[5] = 0.f; p.losses[6] = 0.f;
+        if (p.x.world <= 1) p.losses[7] = 0.f;     // sharded: [7] is the exchange-timeout flag (host zeroes it once)
     }
 }
 

@@ -8,6 +8,7 @@
 #include "clr_common.cuh"
 #include "clr_internal.h"
 #include "clr_finish.cuh"
+#include <string.h>
 
 namespace clr {
 
@@ -56,6 +57,10 @@ static int check_args(const clr_step_args* a) {
         CLR_CHECK_ARG(a->wt != nullptr);
     if (a->use_disc) CLR_CHECK_ARG(a->disc_coef && a->disc_vec && a->disc_beta && a->xtab && a->npx_global > 0);
     if (a->use_cons) CLR_CHECK_ARG(a->oT && a->oT_aug && a->Hi > 0 && a->Wi > 0 && (a->use_retrify || a->masks));
+    if (a->world > 1) {
+        CLR_CHECK_ARG(a->world <= CLR_MAX_WORLD && a->rank >= 0 && a->rank < a->world && a->seq != 0);
+        for (int q = 0; q < a->world; ++q) CLR_CHECK_ARG(a->peer_rx[q] != nullptr);
+    }
     if (a->ws_bytes < carve(a).total) return CLR_ERR_WORKSPACE;
     return CLR_OK;
 }
@@ -183,6 +188,24 @@ int clr_step_fwd_c(const clr_step_args* a, clr_stream_t stream) {
 // `defer` != NULL: do not launch the disc finish; describe it instead (clr_step_run co-schedules it with the backward).
 namespace clr {
 static void bwd_doms(const clr_step_args* a, clr_bwd_dom (&d)[2]);
+
+// receive-buffer layout (64-bit words): exchange 1 (packed1) [2][world][n1] | exchange 2 (packed2 + tail) [2][world][n2]
+static size_t xchg_words1(int K, int C) { return (size_t)2 * 2 * K * (C + 1); }
+static size_t xchg_words2(int K, int C) { return (size_t)K * (C + 1) + 4; }
+static PeerXchg make_xchg(const clr_step_args* a, int which) {
+    PeerXchg x{};
+    x.world = a->world > 1 ? a->world : 1;
+    x.rank = a->rank;
+    x.seq = a->seq;
+    x.err = a->losses + 7;
+    const size_t n1 = xchg_words1(a->K, a->C), n2 = xchg_words2(a->K, a->C);
+    x.n = (int)(which == 1 ? n1 : n2);
+    const size_t off = which == 1 ? 0 : 2 * (size_t)x.world * n1;
+    for (int q = 0; q < x.world && q < CLR_MAX_WORLD; ++q)
+        x.rx[q] = a->world > 1 ? static_cast<unsigned long long*>(a->peer_rx[q]) + off : nullptr;
+    return x;
+}
+
 static int step_fwd_core(const clr_step_args* a, cudaStream_t st, DiscFinishParams* defer, int* deferred) {
     const StepWs w = carve(a);
     clr_stream_t stream = st;
@@ -223,6 +246,7 @@ static int step_fwd_core(const clr_step_args* a, cudaStream_t st, DiscFinishPara
     pf.w_intra = a->w_intra; pf.w_inter = a->w_inter;
     pf.disc_vec = a->use_disc ? a->disc_vec : nullptr; pf.disc_beta = a->use_disc ? a->disc_beta : nullptr;
     pf.losses = a->losses; pf.loss_partial = w.fin; pf.counter = counter;
+    pf.x = make_xchg(a, 1);
     int n_cons = 0;
     if (a->use_cons) {
         rc = cons_fwd_partials(a->oT, a->oT_aug, a->masks, a->B_t, K, a->Hi, a->Wi, a->H, a->W,
@@ -249,11 +273,14 @@ static int step_fwd_core(const clr_step_args* a, cudaStream_t st, DiscFinishPara
             df.w_disc = a->w_disc; df.ema_factor = ema; df.gscale = a->grad_scale; df.w_intra = a->w_intra;
             df.w_inter = a->w_inter; df.w_aug = a->w_aug; df.aug_weight = a->aug_weight; df.use_cons = a->use_cons;
             df.ps = PackSrc{hinge, n_hinge, 1, cons, n_cons};
+            df.x = make_xchg(a, 2);
             if (defer && !tunables().hfuse_off) { *defer = df; *deferred = 1; return CLR_OK; }
             return disc_finish_launch(df, st);
         }
         if (rc != CLR_ERR_UNSUPPORTED) return rc;
     }
+    // the in-kernel exchange of the discriminative / consistency numerators lives in disc_finish_body (one-read path)
+    if (a->world > 1 && (a->use_disc || a->use_cons)) return CLR_ERR_UNSUPPORTED;
     int n_hinge = 0;
     if (a->use_disc) {
         // two-pass form: per-pixel dots (read 1), then pooling of xs with the coefficient planes (read 2)
@@ -288,6 +315,7 @@ static int step_fwd_unmerged(const clr_step_args* a, clr_stream_t stream) {
 int clr_step_fwd(const clr_step_args* a, clr_stream_t stream) {
     int rc = clr::check_args(a);
     if (rc != CLR_OK) return rc;
+    if (a->world > 1 && clr::tunables().finish_off) return CLR_ERR_UNSUPPORTED;
     if (clr::tunables().finish_off) return clr::step_fwd_unmerged(a, stream);
     return clr::step_fwd_core(a, static_cast<cudaStream_t>(stream), nullptr, nullptr);
 }
@@ -308,7 +336,8 @@ int clr_step_run(const clr_step_args* a, clr_stream_t stream) {
     int rc = clr::check_args(a);
     if (rc != CLR_OK) return rc;
     if (!a->gxs || !a->gxt) return CLR_ERR_BAD_ARG;
-    if (!a->aux_stream || !a->ev_fork || !a->ev_join || clr::tunables().overlap_off) {
+    if (a->world > 1 && clr::tunables().finish_off) return CLR_ERR_UNSUPPORTED;
+    if (!a->aux_stream || !a->ev_fork || !a->ev_join || clr::tunables().overlap_off || a->world > 1) {
         if (clr::tunables().finish_off) {
             rc = clr::step_fwd_unmerged(a, stream);
             return rc != CLR_OK ? rc : clr_step_bwd(a, stream);
@@ -390,6 +419,48 @@ int clr_step_bwd(const clr_step_args* a, clr_stream_t stream) {
                           a->aug_weight, stats + 1, a->gup, a->grad_scale * a->w_aug, a->g_oT_aug, stream);
     }
     return rc;
+}
+
+size_t clr_step_xchg_bytes(int world, int K, int C) {
+    if (world < 1 || world > CLR_MAX_WORLD || K < 1 || K > CLR_MAX_K || C < 1) return 0;
+    return sizeof(unsigned long long) * 2 * (size_t)world * (clr::xchg_words1(K, C) + clr::xchg_words2(K, C));
+}
+
+int clr_peer_alloc(size_t bytes, void** ptr) {
+    if (!ptr || bytes == 0) return CLR_ERR_BAD_ARG;
+    void* p = nullptr;
+    CLR_RETURN_IF_CUDA(cudaMalloc(&p, bytes));
+    CLR_RETURN_IF_CUDA(cudaMemset(p, 0, bytes));
+    CLR_RETURN_IF_CUDA(cudaDeviceSynchronize());
+    *ptr = p;
+    return CLR_OK;
+}
+int clr_peer_free(void* ptr) {
+    if (!ptr) return CLR_ERR_BAD_ARG;
+    CLR_RETURN_IF_CUDA(cudaFree(ptr));
+    return CLR_OK;
+}
+int clr_peer_export(void* ptr, unsigned char handle[64]) {
+    if (!ptr || !handle) return CLR_ERR_BAD_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    CLR_RETURN_IF_CUDA(cudaIpcGetMemHandle(&h, ptr));
+    memcpy(handle, &h, 64);
+    return CLR_OK;
+}
+int clr_peer_open(const unsigned char handle[64], void** ptr) {
+    if (!ptr || !handle) return CLR_ERR_BAD_ARG;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    void* p = nullptr;
+    CLR_RETURN_IF_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    *ptr = p;
+    return CLR_OK;
+}
+int clr_peer_close(void* ptr) {
+    if (!ptr) return CLR_ERR_BAD_ARG;
+    CLR_RETURN_IF_CUDA(cudaIpcCloseMemHandle(ptr));
+    return CLR_OK;
 }
 
 }  // extern "C"

@@ -16,7 +16,7 @@ from typing import Optional, Sequence, Tuple
 
 import torch
 
-_STATE = {"enabled": False, "group": None, "grad_scale": None}
+_STATE = {"enabled": False, "group": None, "grad_scale": None, "peer": False}
 
 
 def enable(group=None, grad_scale: Optional[float] = None) -> None:
@@ -27,11 +27,78 @@ def enable(group=None, grad_scale: Optional[float] = None) -> None:
     import torch.distributed as dist
     if not dist.is_initialized():
         raise RuntimeError("torch.distributed is not initialised")
-    _STATE.update(enabled=True, group=group, grad_scale=grad_scale)
+    _STATE.update(enabled=True, group=group, grad_scale=grad_scale, peer=False)
 
 
 def disable() -> None:
-    _STATE.update(enabled=False, group=None, grad_scale=None)
+    _STATE.update(enabled=False, group=None, grad_scale=None, peer=False)
+
+
+# ------------------------------------------------------------------------------------------------- in-kernel exchange
+# Instead of two NCCL all-reduces per step (launch + ~10 us each, and a kernel boundary on either side), the ranks of
+# one NVLink domain can let the step's finish stages exchange the packed sums themselves: every rank owns a small
+# receive buffer that all peers map through CUDA IPC; senders store (value, sequence) words straight into it over
+# NVLink and each rank sums the contributions in rank order (include/clr_b200.h, clr_step_args.world ...).
+_PEER = {}      # (K, C, world) -> dict(local=ptr, ptrs=[...], seq=int)
+
+
+def enable_peer(group=None, grad_scale: Optional[float] = None) -> None:
+    """Like :func:`enable`, but the fused step (``CLRStep`` / ``CLRPlan``) exchanges its sums inside its own kernels
+    over peer-mapped memory (single node, world size <= 8).  The drop-in ops keep using the NCCL all-reduce."""
+    enable(group, grad_scale)
+    _STATE["peer"] = True
+
+
+def peer_enabled() -> bool:
+    return bool(_STATE.get("peer")) and enabled() and world_size() > 1
+
+
+def rank() -> int:
+    import torch.distributed as dist
+    return dist.get_rank(_STATE["group"]) if enabled() else 0
+
+
+def peer_buffers(K: int, C: int, device) -> dict:
+    """Collective (every rank must call it with the same K, C): allocate this rank's receive buffer, exchange the IPC
+    handles through the process group and map every peer's buffer.  Cached per (K, C, world)."""
+    import ctypes
+    import torch.distributed as dist
+    from . import _lib
+    world = world_size()
+    key = (K, C, world)
+    if key in _PEER:
+        return _PEER[key]
+    lib = _lib.load()
+    if world > _lib.CLR_MAX_WORLD:
+        raise RuntimeError("in-kernel exchange supports at most %d ranks (got %d): use dist.enable()" % (_lib.CLR_MAX_WORLD, world))
+    nbytes = lib.clr_step_xchg_bytes(world, K, C)
+    with torch.cuda.device(device):
+        local = ctypes.c_void_p()
+        _lib.check(lib.clr_peer_alloc(nbytes, ctypes.byref(local)), "clr_peer_alloc")
+        handle = ctypes.create_string_buffer(64)
+        _lib.check(lib.clr_peer_export(local, handle), "clr_peer_export")
+        mine = torch.tensor(list(handle.raw), dtype=torch.uint8, device=device)
+        gathered = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine, group=_STATE["group"])
+        me = rank()
+        ptrs = []
+        for q in range(world):
+            if q == me:
+                ptrs.append(local.value)
+            else:
+                pq = ctypes.c_void_p()
+                _lib.check(lib.clr_peer_open(bytes(gathered[q].cpu().tolist()), ctypes.byref(pq)), "clr_peer_open")
+                ptrs.append(pq.value)
+        torch.cuda.synchronize(device)
+        dist.barrier(group=_STATE["group"])      # nobody sends before every buffer is mapped and zeroed
+    _PEER[key] = dict(local=local.value, ptrs=ptrs, seq=0, world=world, rank=me, bytes=nbytes)
+    return _PEER[key]
+
+
+def next_seq(peer: dict) -> int:
+    """Sequence number of the next exchange on these buffers (identical on every rank: one per fused step)."""
+    peer["seq"] = (peer["seq"] % 0xFFFFFFFE) + 1
+    return peer["seq"]
 
 
 def enabled() -> bool:

@@ -66,7 +66,7 @@ class _Buffers:
             spec += [("std_map", B_t * K * Hi * Wi), ("pred_mean", B_t * K * Hi * Wi),
                      ("wt_retrify", B_t * R * H * W), ("masks", B_t * K * H * W)]
         total = sum((n + 63) // 64 * 64 for _, n in spec)
-        self.flat = torch.empty(total, dtype=torch.float32, device=dev)
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)     # (losses[7]: exchange-timeout flag, starts 0)
         off = 0
         for name, n in spec:
             setattr(self, name, self.flat[off:off + n])
@@ -80,7 +80,10 @@ class _ClrStepFn(torch.autograd.Function):
         a: StepArgs = args_holder["args"]
         st = _stream()
         with torch.cuda.device(xs.device):
-            if _dist.enabled():
+            if args_holder["peer"] is not None:
+                a.seq = _dist.next_seq(args_holder["peer"])
+                check(lib.clr_step_fwd(ctypes.byref(a), st), "clr_step_fwd (in-kernel exchange)")
+            elif _dist.enabled():
                 check(lib.clr_step_fwd_a(ctypes.byref(a), st), "clr_step_fwd_a")
                 _dist.all_reduce_sums(args_holder["buf"].packed1)
                 check(lib.clr_step_fwd_b(ctypes.byref(a), st), "clr_step_fwd_b")
@@ -220,13 +223,19 @@ class CLRStep:
                 setattr(a, name, ptr(getattr(buf, name)))
         elif use_cons:
             a.masks = ptr(masks_t)
+        peer = None
+        if _dist.peer_enabled():
+            peer = _dist.peer_buffers(K, C, dev)
+            a.world, a.rank, a.seq = peer["world"], peer["rank"], 1
+            for q, pq in enumerate(peer["ptrs"]):
+                a.peer_rx[q] = pq
         a.ws = None
         ws_bytes = lib.clr_step_ws_bytes(ctypes.byref(a))
         if self._ws is None or self._ws.numel() < ws_bytes or self._ws.device != dev:
             self._ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         a.ws, a.ws_bytes = ptr(self._ws), ws_bytes
 
-        holder = dict(args=a, buf=buf, xs=xs, xt=xt, oT_aug=oTa, dims=(B_s, B_t, C, H, W, K, Hi, Wi),
+        holder = dict(args=a, buf=buf, xs=xs, xt=xt, oT_aug=oTa, dims=(B_s, B_t, C, H, W, K, Hi, Wi), peer=peer,
                       keep=(xs, ys, xt, wt_t, oTb, pr, oT_d, oTa, self.stored_s, self.stored_t, self._ws,
                             masks_t if (use_cons and not self.retrify) else None))
         return holder
@@ -314,7 +323,10 @@ class CLRPlan:
         a: StepArgs = self.holder["args"]
         st = _stream()
         a.first_s, a.first_t = int(self.step.first_s), int(self.step.first_t)
-        if _dist.enabled():
+        if self.holder["peer"] is not None:
+            a.seq = _dist.next_seq(self.holder["peer"])
+            check(self._lib.clr_step_run(self._ref, st), "clr_step_run (in-kernel exchange)")
+        elif _dist.enabled():
             check(self._lib.clr_step_fwd_a(self._ref, st), "clr_step_fwd_a")
             _dist.all_reduce_sums(self.holder["buf"].packed1)
             check(self._lib.clr_step_fwd_b(self._ref, st), "clr_step_fwd_b")
