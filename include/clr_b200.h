@@ -206,6 +206,23 @@ int clr_cons_bwd(const float* oT, const float* oT_aug, const float* masks, int B
                  float* grad_oT_aug /*[B,K,Hi,Wi] out*/, clr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Image-resolution elementwise glue around the CLR block.
+ *   seg loss : BCELoss(sigmoid(oS), target_map) + MSELoss(sigmoid(boundaryS), target_boundary), both means
+ *              (Trainer_prototype_full.py:292-294).  out = { bce, mse, bce + mse, 0 }.  n2 may be 0 (BCE only).
+ *              bwd writes d/d oS and d/d boundaryS of (gscale * *gup_dev) * (bce + mse); gup_dev may be NULL (= 1).
+ *   entropy  : uncertainty_map = -sigmoid(o) * log(sigmoid(o) + smooth)  (:452, :481, :500) and its adjoint.
+ * ---------------------------------------------------------------------------------------------- */
+size_t clr_seg_loss_ws_bytes(void);
+int clr_seg_loss_fwd(const float* oS, const float* target_map, size_t n1, const float* boundaryS,
+                     const float* target_boundary, size_t n2, void* ws, size_t ws_bytes, float* out /*[4]*/,
+                     clr_stream_t stream);
+int clr_seg_loss_bwd(const float* oS, const float* target_map, size_t n1, const float* boundaryS,
+                     const float* target_boundary, size_t n2, const float* gup_dev, float gscale,
+                     float* g_oS, float* g_boundaryS, clr_stream_t stream);
+int clr_entropy_fwd(const float* o, size_t n, float smooth, float* out, clr_stream_t stream);
+int clr_entropy_bwd(const float* o, const float* gout, size_t n, float smooth, float* gin, clr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * O(K*C) glue (Trainer_prototype_full.py:335-355, 378-398, 428-449): prototypes, EMA, alignment /
  * separation losses and their gradients; then the discriminative term's prototype gradients + totals.
  * losses = { intra, inter, disc, aug, total, 0, 0, 0 }.

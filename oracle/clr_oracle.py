@@ -357,6 +357,38 @@ def cosine_weight(feat: np.ndarray, proto: np.ndarray, eps: float = 1e-8) -> np.
     return (num / den)[:, None]
 
 
+# --------------------------------------------------------------------------- 8(f) rank 2: step glue at image resolution
+def seg_loss(oS: np.ndarray, boundaryS: Optional[np.ndarray], target_map: np.ndarray,
+             target_boundary: Optional[np.ndarray]):
+    """Trainer_prototype_full.py:292-294: ``BCELoss(sigmoid(oS), map) + MSELoss(sigmoid(bS), boundary)`` (means) and
+    the gradients w.r.t. the two logit maps.  fp64, log terms clamped at -100 like ATen's BCELoss."""
+    o = np.asarray(oS, F64)
+    y = np.asarray(target_map, F64)
+    q = 1.0 / (1.0 + np.exp(-o))
+    with np.errstate(divide="ignore"):
+        lq = np.maximum(np.log(q), -100.0)
+        l1q = np.maximum(np.log1p(-q), -100.0)
+    bce = float(np.mean(-(y * lq + (1.0 - y) * l1q)))
+    g_o = (q - y) / o.size
+    mse, g_b = 0.0, None
+    if boundaryS is not None:
+        b = np.asarray(boundaryS, F64)
+        t = np.asarray(target_boundary, F64)
+        qb = 1.0 / (1.0 + np.exp(-b))
+        mse = float(np.mean((qb - t) ** 2))
+        g_b = 2.0 * (qb - t) * qb * (1.0 - qb) / b.size
+    return bce + mse, dict(bce=bce, mse=mse, g_oS=g_o, g_boundaryS=g_b)
+
+
+def uncertainty_map(o: np.ndarray, smooth: float = 1e-7):
+    """Trainer_prototype_full.py:452: ``-sigmoid(o) * log(sigmoid(o) + smooth)`` and d/do (per unit upstream gradient)."""
+    x = np.asarray(o, F64)
+    q = 1.0 / (1.0 + np.exp(-x))
+    u = -q * np.log(q + smooth)
+    du = -q * (1.0 - q) * (np.log(q + smooth) + q / (q + smooth))
+    return u, du
+
+
 # --------------------------------------------------------------------------- the fused step (A1/A2 + A4 + A5 + A9 + A10)
 def clr_step(xs, ys, xt, wt, *, stored_s=None, stored_t=None, decay: float = 0.9,
              w_intra: float = 0.1, w_inter: float = 0.0, w_disc: float = 0.0, margin: float = 0.01,

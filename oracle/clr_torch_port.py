@@ -203,6 +203,20 @@ def adaptation_factor(m):
     return 1.0 / (1.0 + math.exp(-0.8 * (m + 1))) - 0.3
 
 
+# ----------------------------------------------------------------------------- step glue (Trainer_prototype_full.py:292-294, 452)
+def seg_loss(oS, boundaryS, target_map, target_boundary):
+    """``loss_seg1 + loss_seg2`` exactly as the trainer forms them (:18-19, :292-294)."""
+    loss = torch.nn.BCELoss()(torch.sigmoid(oS), target_map)
+    if boundaryS is not None:
+        loss = loss + torch.nn.MSELoss()(torch.sigmoid(boundaryS), target_boundary)
+    return loss
+
+
+def uncertainty_map(o, smooth: float = 1e-7):
+    """``-1.0 * torch.sigmoid(oT) * torch.log(torch.sigmoid(oT) + smooth)`` (:452)."""
+    return -1.0 * torch.sigmoid(o) * torch.log(torch.sigmoid(o) + smooth)
+
+
 # ----------------------------------------------------------------------------- one whole CLR step, the way the trainer runs it
 class ClrStepPort:
     """The CLR block of one training step (Trainer_prototype_full.py:328-449 + the two bytecode-only

@@ -185,6 +185,83 @@ def test_update_objective_single_vector():
     assert torch.equal(clr.update_objective_single_vector(obj, torch.zeros_like(v)), obj)
 
 
+def test_cons_loss_confidently_wrong_pixels_follow_aten():
+    """A10 on pixels where the augmented prediction is confidently WRONG: ATen evaluates log(q) / log(1-q) on the
+    fp32-rounded q (quantised, then clamped at -100); the kernel must follow it, not the exact softplus."""
+    from uda_clr_b200 import _lib
+    from uda_clr_b200._lib import check, ptr
+    lib = _lib.load()
+    B, K, H, W, up = 1, 2, 4, 4, 4
+    vals = torch.tensor([-30.0, -17.0, -16.0, -12.0, -9.5, -3.0, 0.5, 3.0, 9.5, 12.0, 15.0, 16.0, 16.5, 17.0, 40.0, 100.0])
+    oT_aug = vals.repeat(B * K * H * up * W * up // vals.numel()).reshape(B, K, H * up, W * up).to(DEV)
+    thr = clr.consistency_threshold(0.0)
+    for sign in (1.0, -1.0):      # pseudo-label all ones / all zeros
+        oT = torch.full_like(oT_aug, 5.0 * sign)
+        masks = 2.0 * torch.ones(B, K, H, W, device=DEV)
+        ws = torch.empty(lib.clr_cons_ws_bytes(), dtype=torch.uint8, device=DEV)
+        stats = torch.empty(4, device=DEV)
+        check(lib.clr_cons_fwd(ptr(oT), ptr(oT_aug), ptr(masks), B, K, H * up, W * up, H, W, thr, 1.0, ptr(ws), ws.numel(),
+                               ptr(stats), torch.cuda.current_stream().cuda_stream), "clr_cons_fwd")
+        ref = TP.cons_loss(oT, oT_aug, [masks[:, k:k + 1] for k in range(K)], 0.0, 1.0)
+        assert abs(float(stats[2]) - float(ref)) < TOL_LOSS * abs(float(ref)), (sign, float(stats[2]), float(ref))
+
+
+# ------------------------------------------------------------------------------------------------ 8(f) glue
+@pytest.mark.parametrize("shape,with_boundary", [((8, 2, 512, 512), True), ((2, 2, 33, 47), True), ((3, 2, 64, 64), False)])
+def test_seg_loss_vs_oracle_and_eager(shape, with_boundary):
+    """loss_seg = BCELoss(sigmoid(oS), map) + MSELoss(sigmoid(bS), boundary) (Trainer_prototype_full.py:292-294):
+    value and both gradients against the fp64 oracle and against the eager ATen sequence on the same GPU."""
+    g = torch.Generator().manual_seed(13)
+    B, K, H, W = shape
+    oS = 3.0 * torch.randn(B, K, H, W, generator=g)
+    tmap = (torch.rand(B, K, H, W, generator=g) > 0.6).float()
+    bS = 2.0 * torch.randn(B, 1, H, W, generator=g) if with_boundary else None
+    tbd = torch.rand(B, 1, H, W, generator=g) if with_boundary else None
+    o1 = oS.to(DEV).requires_grad_(True)
+    b1 = bS.to(DEV).requires_grad_(True) if with_boundary else None
+    loss = clr.seg_loss(o1, b1, tmap.to(DEV), tbd.to(DEV) if with_boundary else None)
+    (2.5 * loss).backward()
+    ref, aux = O.seg_loss(oS.numpy(), bS.numpy() if with_boundary else None, tmap.numpy(), tbd.numpy() if with_boundary else None)
+    assert abs(float(loss) - ref) < TOL_LOSS * abs(ref)
+    assert relerr(o1.grad.cpu().numpy(), 2.5 * aux["g_oS"]) < TOL_GRAD
+    o2 = oS.to(DEV).requires_grad_(True)
+    b2 = bS.to(DEV).requires_grad_(True) if with_boundary else None
+    l2 = TP.seg_loss(o2, b2, tmap.to(DEV), tbd.to(DEV) if with_boundary else None)
+    (2.5 * l2).backward()
+    assert abs(float(loss) - float(l2)) < TOL_LOSS * abs(float(l2))
+    assert relerr(o1.grad.cpu().numpy(), o2.grad.cpu().numpy()) < TOL_GRAD
+    if with_boundary:
+        assert relerr(b1.grad.cpu().numpy(), 2.5 * aux["g_boundaryS"]) < TOL_GRAD
+        assert relerr(b1.grad.cpu().numpy(), b2.grad.cpu().numpy()) < TOL_GRAD
+
+
+def test_seg_loss_saturation_matches_aten():
+    """Confidently wrong logits: ATen's BCELoss clamps the log at -100 once sigmoid rounds to 0 / 1 in fp32."""
+    o = torch.tensor([[-120.0, -95.0, -50.0, 16.0, 17.0, 30.0, 90.0, 0.0]], device=DEV).reshape(1, 1, 2, 4)
+    for y in (0.0, 1.0):
+        t = torch.full_like(o, y)
+        ours = float(clr.seg_loss(o.clone(), None, t, None))
+        ref = float(TP.seg_loss(o.clone(), None, t, None))
+        assert abs(ours - ref) < 1e-4 * abs(ref), (y, ours, ref)
+
+
+def test_uncertainty_map_vs_oracle_and_eager():
+    g = torch.Generator().manual_seed(21)
+    o = 4.0 * torch.randn(4, 2, 96, 80, generator=g)
+    w = torch.randn(4, 2, 96, 80, generator=g)
+    x1 = o.to(DEV).requires_grad_(True)
+    u1 = clr.uncertainty_map(x1)
+    (u1 * w.to(DEV)).sum().backward()
+    un, du = O.uncertainty_map(o.numpy())
+    assert relerr(u1.detach().cpu().numpy(), un) < 1e-5
+    assert relerr(x1.grad.cpu().numpy(), du * w.numpy()) < TOL_GRAD
+    x2 = o.to(DEV).requires_grad_(True)
+    u2 = TP.uncertainty_map(x2)
+    (u2 * w.to(DEV)).sum().backward()
+    assert relerr(u1.detach().cpu().numpy(), u2.detach().cpu().numpy()) < 1e-5
+    assert relerr(x1.grad.cpu().numpy(), x2.grad.cpu().numpy()) < TOL_GRAD
+
+
 # ------------------------------------------------------------------------------------------------ fused step
 @pytest.mark.parametrize("variant", ["align_soft", "align_retrify", "clr3", "clr3_aug_bwd"])
 def test_fused_step_vs_oracle(variant):

@@ -108,3 +108,26 @@ def test_full_step_matches_port_autograd():
         # soft target: grad reaches the logits through sigmoid'
         gw = o["gwt"][:, :K] - o["gwt"][:, K:]
         assert relerr(gw * pt * (1 - pt), oTb.grad.numpy()) < 1e-9
+
+
+def test_seg_loss_and_entropy_closed_forms_vs_aten():
+    """8(f) glue: the fp64 closed forms of loss_seg (Trainer_prototype_full.py:292-294) and of the uncertainty map
+    (:452) with their gradients vs the ATen op sequence the trainer runs, under autograd in fp64."""
+    g = torch.Generator().manual_seed(5)
+    oS = (3.0 * torch.randn(2, 2, 12, 10, generator=g)).double().requires_grad_(True)
+    bS = (2.0 * torch.randn(2, 1, 12, 10, generator=g)).double().requires_grad_(True)
+    tmap = (torch.rand(2, 2, 12, 10, generator=g) > 0.5).double()
+    tbd = torch.rand(2, 1, 12, 10, generator=g).double()
+    loss = TP.seg_loss(oS, bS, tmap, tbd)
+    loss.backward()
+    l, aux = O.seg_loss(oS.detach().numpy(), bS.detach().numpy(), tmap.numpy(), tbd.numpy())
+    assert abs(l - float(loss.detach())) < 1e-12
+    assert relerr(aux["g_oS"], oS.grad.numpy()) < 1e-10
+    assert relerr(aux["g_boundaryS"], bS.grad.numpy()) < 1e-10
+    o = (4.0 * torch.randn(3, 2, 9, 7, generator=g)).double().requires_grad_(True)
+    w = torch.randn(3, 2, 9, 7, generator=g).double()
+    u = TP.uncertainty_map(o)
+    (u * w).sum().backward()
+    un, du = O.uncertainty_map(o.detach().numpy())
+    assert relerr(un, u.detach().numpy()) < 1e-12
+    assert relerr(du * w.numpy(), o.grad.numpy()) < 1e-10

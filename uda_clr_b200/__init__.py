@@ -11,8 +11,8 @@ missing (no CPU fallback).
 """
 from .ops import (adaptation_factor, bmm_prototypes, distance_weight, feat_prototype_distance, gen_prototype,  # noqa: F401
                   gen_prototype_retrify, gen_prototype_src_trg, gen_prototype_src_trg_retrify,
-                  get_prototype_weight, mc_statistics, retrify_weights, update_objective_single_vector,
-                  weighted_prototypes)
+                  get_prototype_weight, mc_statistics, retrify_weights, seg_loss, uncertainty_map,
+                  update_objective_single_vector, weighted_prototypes)
 from .step import CLRPlan, CLRStep, CLRStepOutput, consistency_threshold, sigmoid_rampup  # noqa: F401
 from . import dist, ops  # noqa: F401
 from .patch import patch_reference, unpatch_reference  # noqa: F401

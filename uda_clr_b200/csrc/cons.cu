@@ -49,11 +49,18 @@ __device__ __forceinline__ bool label_above(float z, const LabelRule& r) {
 // fp32 q and clamps the log at -100: q rounds to exactly 1 (0) once |za| >= 24 ln 2, where the wrong-side term becomes
 // 100 -- reproduced by the explicit saturation test; in the narrow band below it ATen's own value carries the
 // quantisation error of 1-q, the softplus form is the mathematically exact one.
+__device__ __noinline__ float cons_loss_elem_aten(float za, bool yb) {
+    const float q = sigmoid_aten(za);
+    return -fmaxf(yb ? logf(q) : log1pf(-q), -100.0f);
+}
 __device__ __forceinline__ float cons_loss_elem(float zt, float za, const LabelRule& r) {
     const bool yb = label_above(zt, r);
     const float x = (yb ? -1.4426950408889634f : 1.4426950408889634f) * za;    // wrong-side exponent, base 2
     const float l = 0.6931471805599453f * lg2_approx(1.0f + ex2_approx(x));
-    return x >= 24.0f ? 100.0f : l;
+    // confidently wrong (|za| > 9): ATen's 1 - q (or q) keeps only a few significant bits before it saturates, and its
+    // log drifts by up to 2 % from the softplus -- evaluate the reference's own expression (rare, out of line)
+    if (x > 13.0f) return cons_loss_elem_aten(za, yb);
+    return l;
 }
 
 // Backward element: (q - y) / max(q (1-q), 1e-12) * q (1-q)   (ATen binary_cross_entropy_backward x sigmoid')
@@ -158,7 +165,7 @@ __device__ __forceinline__ void cons_body(const ConsArgs& a, const unsigned cta,
 }
 
 template <int VEC, bool BWD>
-__global__ void __launch_bounds__(kConsThreads, 4) cons_kernel(const ConsArgs a) {
+__global__ void __launch_bounds__(kConsThreads, 3) cons_kernel(const ConsArgs a) {
     kernel_begin(BWD ? TR_CONS_BWD : TR_CONS);
     cons_body<VEC, BWD>(a, blockIdx.x, gridDim.x);
     trace_exit(BWD ? TR_CONS_BWD : TR_CONS);
@@ -167,7 +174,7 @@ __global__ void __launch_bounds__(kConsThreads, 4) cons_kernel(const ConsArgs a)
 // Horizontal fusion for the fused step: CTAs [0, n_fin) run the pooling finish (partial reduce + EMA + alignment losses:
 // a latency chain of a few KB) while the remaining CTAs stream the consistency pass, which does not depend on it.
 template <int VEC>
-__global__ void __launch_bounds__(kConsThreads, 4) pool_finish_cons_kernel(const PoolFinishParams f, const int n_fin, const ConsArgs a) {
+__global__ void __launch_bounds__(kConsThreads, 3) pool_finish_cons_kernel(const PoolFinishParams f, const int n_fin, const ConsArgs a) {
     if ((int)blockIdx.x < n_fin) {
         kernel_begin(TR_ALIGN);
         pool_finish_body(f, blockIdx.x, n_fin);

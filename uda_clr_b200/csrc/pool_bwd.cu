@@ -124,8 +124,11 @@ __device__ __forceinline__ void pool_bwd_body(const BwdParams& p, int bid) {
     }
 }
 
+// resident CTAs per SM by register need: QT coefficient planes x VEC pixels live in registers (QT = 16 -> 64 of them)
+constexpr int bwd_min_blocks(int QT) { return QT <= 4 ? 4 : (QT <= 8 ? 3 : 2); }
+
 template <int QT, int VEC>
-__global__ void __launch_bounds__(kThreads, 4) pool_bwd_kernel(const BwdParams p) {
+__global__ void __launch_bounds__(kThreads, bwd_min_blocks(QT)) pool_bwd_kernel(const BwdParams p) {
     kernel_begin(p.trace_id);
     pool_bwd_body<QT, VEC>(p, blockIdx.x);
     trace_exit(p.trace_id);
@@ -135,7 +138,7 @@ __global__ void __launch_bounds__(kThreads, 4) pool_bwd_kernel(const BwdParams p
 // gradients + direct-gradient table + step totals: a latency chain) while the remaining CTAs write the gradient of the
 // TARGET features, which depends on the alignment term only.  The source-gradient write follows as the next launch.
 template <int QT, int VEC>
-__global__ void __launch_bounds__(kThreads, 4) bwd_finish_kernel(const BwdParams p, const DiscFinishParams f, const int n_fin) {
+__global__ void __launch_bounds__(kThreads, bwd_min_blocks(QT)) bwd_finish_kernel(const BwdParams p, const DiscFinishParams f, const int n_fin) {
     if ((int)blockIdx.x < n_fin) {
         kernel_begin(TR_DISC_FIN);
         disc_finish_body(f, blockIdx.x, n_fin);

@@ -452,3 +452,81 @@ def adaptation_factor(m):
     """Drop-in for ``utils.Utils.adaptation_factor`` (utils/Utils.py:104-107); host scalar math."""
     den = 1.0 + math.exp(-0.8 * (m + 1))
     return 1.0 / den - 0.3
+
+
+# ----------------------------------------------------------------------------------------------- 8(f): step glue
+class _SegLoss(torch.autograd.Function):
+    """``BCELoss(sigmoid(oS), map) + MSELoss(sigmoid(boundaryS), boundary)`` (Trainer_prototype_full.py:292-294):
+    one streaming launch forward, one backward; the upstream gradient stays on the device."""
+
+    @staticmethod
+    def forward(ctx, oS, boundaryS, target_map, target_boundary):
+        lib = _lib.load()
+        ws_bytes = lib.clr_seg_loss_ws_bytes()
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=oS.device)
+        out = torch.empty(4, dtype=torch.float32, device=oS.device)
+        n2 = 0 if boundaryS is None else boundaryS.numel()
+        with torch.cuda.device(oS.device):
+            check(lib.clr_seg_loss_fwd(ptr(oS), ptr(target_map), oS.numel(), ptr(boundaryS), ptr(target_boundary), n2,
+                                       ptr(ws), ws_bytes, ptr(out), _stream()), "clr_seg_loss_fwd")
+        ctx.save_for_backward(oS, boundaryS, target_map, target_boundary)
+        ctx.parts = out
+        return out[2].clone()
+
+    @staticmethod
+    def backward(ctx, gup):
+        lib = _lib.load()
+        oS, boundaryS, target_map, target_boundary = ctx.saved_tensors
+        g1 = torch.empty_like(oS)
+        g2 = None if boundaryS is None else torch.empty_like(boundaryS)
+        gup = gup.to(torch.float32).contiguous()
+        n2 = 0 if boundaryS is None else boundaryS.numel()
+        with torch.cuda.device(oS.device):
+            check(lib.clr_seg_loss_bwd(ptr(oS), ptr(target_map), oS.numel(), ptr(boundaryS), ptr(target_boundary), n2,
+                                       ptr(gup), 1.0, ptr(g1), ptr(g2), _stream()), "clr_seg_loss_bwd")
+        return g1, g2, None, None
+
+
+def seg_loss(oS: torch.Tensor, boundaryS: Optional[torch.Tensor], target_map: torch.Tensor,
+             target_boundary: Optional[torch.Tensor]) -> torch.Tensor:
+    """``bceloss(sigmoid(oS), target_map) + mseloss(sigmoid(boundaryS), target_boundary)`` of the reference's step
+    (Trainer_prototype_full.py:292-294) as one differentiable scalar.  ``boundaryS=None`` -> the BCE term alone."""
+    o = _require_cuda_f32(oS, "oS")
+    y = _require_cuda_f32(target_map.detach(), "target_map")
+    if o.shape != y.shape:
+        raise ValueError("oS %s and target_map %s disagree" % (tuple(o.shape), tuple(y.shape)))
+    b = t = None
+    if boundaryS is not None:
+        b = _require_cuda_f32(boundaryS, "boundaryS")
+        t = _require_cuda_f32(target_boundary.detach(), "target_boundary")
+        if b.shape != t.shape:
+            raise ValueError("boundaryS %s and target_boundary %s disagree" % (tuple(b.shape), tuple(t.shape)))
+    return _SegLoss.apply(o, b, y, t)
+
+
+class _EntropyMap(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, o, smooth):
+        lib = _lib.load()
+        out = torch.empty_like(o)
+        with torch.cuda.device(o.device):
+            check(lib.clr_entropy_fwd(ptr(o), o.numel(), float(smooth), ptr(out), _stream()), "clr_entropy_fwd")
+        ctx.save_for_backward(o)
+        ctx.smooth = float(smooth)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        lib = _lib.load()
+        (o,) = ctx.saved_tensors
+        gout = gout.contiguous()
+        gin = torch.empty_like(o)
+        with torch.cuda.device(o.device):
+            check(lib.clr_entropy_bwd(ptr(o), ptr(gout), o.numel(), ctx.smooth, ptr(gin), _stream()), "clr_entropy_bwd")
+        return gin, None
+
+
+def uncertainty_map(o: torch.Tensor, smooth: float = 1e-7) -> torch.Tensor:
+    """``-1.0 * torch.sigmoid(o) * torch.log(torch.sigmoid(o) + smooth)`` (Trainer_prototype_full.py:452, 481, 500):
+    the entropy map fed to the uncertainty discriminator, one launch each way instead of five."""
+    return _EntropyMap.apply(_require_cuda_f32(o, "o", o.dim()), smooth)
