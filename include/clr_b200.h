@@ -221,6 +221,10 @@ int clr_seg_loss_bwd(const float* oS, const float* target_map, size_t n1, const 
                      float* g_oS, float* g_boundaryS, clr_stream_t stream);
 int clr_entropy_fwd(const float* o, size_t n, float smooth, float* out, clr_stream_t stream);
 int clr_entropy_bwd(const float* o, const float* gout, size_t n, float smooth, float* gin, clr_stream_t stream);
+/* Validation counts (utils/metrics.py:118-168): counts[k][2*gt + pred] with pred = sigmoid(logit) > thr (exact fp32
+ * decision), gt = target != 0; [K][4] unsigned 64-bit, zeroed by the call.  Dice / pixel accuracy / IoU follow. */
+int clr_seg_counts(const float* logits /*[B,K,HW]*/, const float* target /*[B,K,HW]*/, int B, int K, size_t HW, float thr,
+                   unsigned long long* counts /*[K][4] out*/, clr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * O(K*C) glue (Trainer_prototype_full.py:335-355, 378-398, 428-449): prototypes, EMA, alignment /

@@ -262,6 +262,33 @@ def test_uncertainty_map_vs_oracle_and_eager():
     assert relerr(x1.grad.cpu().numpy(), x2.grad.cpu().numpy()) < TOL_GRAD
 
 
+def test_validation_counts_bit_exact_and_metrics():
+    """8(f) rank 3: confusion counts of sigmoid(pred) > 0.75 vs the ground truth are bit-exact integers (compared with
+    eager torch on the same GPU), and Dice / PA / mIoU equal the reference formulas (utils/metrics.py:81-100, 10-33)."""
+    g = torch.Generator().manual_seed(8)
+    B, K, H, W = 3, 2, 200, 173
+    z = (2.5 * torch.randn(B, K, H, W, generator=g)).to(DEV)
+    z[0, 0, 0, :4] = torch.tensor([1.0986123, 1.0986122, 1.0986124, 1.09861])     # around logit(0.75) = ln 3
+    t = (torch.rand(B, K, H, W, generator=g) > 0.7).float().to(DEV)
+    c = clr.validation_counts(z, t, 0.75)
+    pred = torch.sigmoid(z) > 0.75
+    gt = t != 0
+    ref = torch.stack([torch.stack([((gt[:, k] == bool(gi)) & (pred[:, k] == bool(pi))).sum() for gi in (0, 1) for pi in (0, 1)])
+                       for k in range(K)])
+    assert torch.equal(c.cpu(), ref.cpu())
+    assert int(c.sum()) == B * K * H * W
+    dice = clr.dice_from_counts(c).cpu().numpy()
+    pa, miou = (v.cpu().numpy() for v in clr.pixel_acc_from_counts(c))
+    for k in range(K):
+        p_, g_ = pred[:, k].cpu().numpy(), gt[:, k].cpu().numpy()
+        inter = float(np.logical_and(p_, g_).sum())
+        assert abs(dice[k] - (2 * inter + 1.0) / (1.0 + float(p_.sum()) + float(g_.sum()))) < 1e-15
+        cm = np.array([[np.sum(~g_ & ~p_), np.sum(~g_ & p_)], [np.sum(g_ & ~p_), np.sum(g_ & p_)]], dtype=np.float64)
+        assert abs(pa[k] - np.diag(cm).sum() / cm.sum()) < 1e-15
+        iou = np.diag(cm) / (cm.sum(1) + cm.sum(0) - np.diag(cm))
+        assert abs(miou[k] - np.nanmean(iou)) < 1e-15
+
+
 # ------------------------------------------------------------------------------------------------ fused step
 @pytest.mark.parametrize("variant", ["align_soft", "align_retrify", "clr3", "clr3_aug_bwd"])
 def test_fused_step_vs_oracle(variant):

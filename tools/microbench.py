@@ -152,8 +152,39 @@ def main():
         bat = time_batch(run, a.iters)
         res[name] = dict(us=round(med, 2), best_us=round(best, 2), batch_us=round(bat, 2))
 
-    # 8(f) glue at image resolution: ours vs the eager ATen sequence of the trainer on the same GPU (fwd + bwd)
+    # the tougher baseline: the reference's eager op sequence ON THIS GPU, whole CLR step fwd + bwd,
+    # and the drop-in ops (gen_prototype / gen_prototype_retrify under autograd) against the same eager functions
     from oracle import clr_torch_port as TP
+    port = TP.ClrStepPort(retrify=True, use_disc=True, use_cons=True, backprop_aug=False)
+
+    def eager_step(i):
+        xs, xt = xs_l[i % a.nbuf], xs_l[(i + 1) % a.nbuf]
+        xs.grad = None
+        xt.grad = None
+        port.step(xs, t["ys"], xt, t["oT_before"], preds=t["preds"], features=None, T=8, oT=t["oT"], oT_aug=t["oT_aug"], epoch=0.0)
+    med, best = time_it(eager_step, max(5, a.iters // 2))
+    res["step_clr3_eager_port_on_gpu"] = dict(us=round(med, 2), best_us=round(best, 2))
+    step_p = clr.CLRStep(K=K, retrify=True, use_disc=True, use_cons=True)
+    plan_p = step_p.plan(xs_l[0].detach(), t["ys"], xs_l[1].detach(), oT_before=t["oT_before"], preds=t["preds"], T=8, oT=t["oT"],
+                         oT_aug=t["oT_aug"])
+    res["step_clr3_plan_run"] = dict(batch_us=round(time_batch(lambda i: plan_p.run(), 50), 2))
+    seeds4 = [torch.randn(1, C, 1, 1, device=dev) for _ in range(2 * K)]
+
+    def dropin(fn_proto, fn_retr):
+        def run(i):
+            xs, xt = xs_l[i % a.nbuf], xs_l[(i + 1) % a.nbuf]
+            xs.grad = None
+            xt.grad = None
+            ps = fn_proto(t["ys"], xs)
+            pt = fn_retr(t["oT_before"], xt, t["preds"], None, 8, B)[:2 * K]
+            sum((p * s).sum() for p, s in zip(list(ps) + list(pt), seeds4 + seeds4)).backward()
+        return run
+    med, best = time_it(dropin(clr.gen_prototype, clr.gen_prototype_retrify), a.iters)
+    res["dropin_gen_prototype+retrify_ours"] = dict(us=round(med, 2), best_us=round(best, 2))
+    med, best = time_it(dropin(TP.gen_prototype, TP.gen_prototype_retrify), max(5, a.iters // 2))
+    res["dropin_gen_prototype+retrify_eager_gpu"] = dict(us=round(med, 2), best_us=round(best, 2))
+
+    # 8(f) glue at image resolution: ours vs the eager ATen sequence of the trainer on the same GPU (fwd + bwd)
     Hi = 4 * H
     oS = [torch.randn(B, K, Hi, Hi, device=dev).requires_grad_(True) for _ in range(a.nbuf)]
     bS = [torch.randn(B, 1, Hi, Hi, device=dev).requires_grad_(True) for _ in range(a.nbuf)]

@@ -9,9 +9,10 @@ sm_100a CUDA kernels behind a C ABI (``include/clr_b200.h``, ``libclr_b200.so``)
 Importing the package never touches CUDA; the first op call loads the library and raises if it is
 missing (no CPU fallback).
 """
-from .ops import (adaptation_factor, bmm_prototypes, distance_weight, feat_prototype_distance, gen_prototype,  # noqa: F401
+from .ops import (adaptation_factor, bmm_prototypes, dice_from_counts, distance_weight, feat_prototype_distance, gen_prototype,  # noqa: F401
                   gen_prototype_retrify, gen_prototype_src_trg, gen_prototype_src_trg_retrify,
-                  get_prototype_weight, mc_statistics, retrify_weights, seg_loss, uncertainty_map,
+                  get_prototype_weight, mc_statistics, pixel_acc_from_counts, retrify_weights, seg_loss,
+                  uncertainty_map, validation_counts,
                   update_objective_single_vector, weighted_prototypes)
 from .step import CLRPlan, CLRStep, CLRStepOutput, consistency_threshold, sigmoid_rampup  # noqa: F401
 from . import dist, ops  # noqa: F401

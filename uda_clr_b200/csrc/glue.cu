@@ -16,6 +16,7 @@
 // Backward = ATen's binary_cross_entropy_backward chained with sigmoid'.
 #include "clr_common.cuh"
 #include "clr_internal.h"
+#include <math.h>
 
 namespace clr {
 
@@ -199,6 +200,49 @@ static int launch_entropy(const float* o, const float* gout, size_t n, float smo
     return launch_status();
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Validation counts: per class the 2x2 confusion matrix of (sigmoid(logit) > thr) against the
+// binary ground truth -- everything utils/metrics.py:118-168 derives Dice@0.75, pixel accuracy and IoU from, as exact
+// integers, without the full-resolution device->host copy and the NumPy passes of the reference.
+// counts[k][2*gt + pred]  (the reference's genConfusionMatrix index, utils/metrics.py:38-43).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool above_thr(float z, float thr, float zthr, float guard) {
+    const float d = z - zthr;
+    if (fabsf(d) > guard) return d > 0.f;
+    return 1.0f / (1.0f + expf(-z)) > thr;           // ATen's sigmoid, exact decision inside the guard band
+}
+
+__global__ void __launch_bounds__(256) seg_counts_kernel(const float* __restrict__ logits, const float* __restrict__ target,
+                                                         int K, size_t HW, float thr, float zthr, float guard,
+                                                         unsigned long long* __restrict__ counts) {
+    kernel_begin(TR_OTHER);
+    const int plane = blockIdx.y;                     // b*K + k
+    const int k = plane % K;
+    const float* z = logits + (size_t)plane * HW;
+    const float* t = target + (size_t)plane * HW;
+    unsigned int c[4] = {0u, 0u, 0u, 0u};
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (size_t)gridDim.x * blockDim.x) {
+        const int p = above_thr(__ldg(z + i), thr, zthr, guard) ? 1 : 0;
+        const int g = (__ldg(t + i) != 0.f) ? 1 : 0;
+        ++c[2 * g + p];
+    }
+    __shared__ unsigned int sh[4][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        unsigned int v = c[j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) sh[j][warp] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        unsigned long long s = 0;
+        for (int w = 0; w < 8; ++w) s += sh[threadIdx.x][w];
+        if (s) atomicAdd(counts + (size_t)k * 4 + threadIdx.x, s);      // integer atomics: order-independent, exact
+    }
+}
+
 }  // namespace clr
 
 extern "C" {
@@ -245,6 +289,25 @@ int clr_entropy_fwd(const float* o, size_t n, float smooth, float* out, clr_stre
 
 int clr_entropy_bwd(const float* o, const float* gout, size_t n, float smooth, float* gin, clr_stream_t stream) {
     return clr::launch_entropy<true>(o, gout, n, smooth, gin, static_cast<cudaStream_t>(stream));
+}
+
+int clr_seg_counts(const float* logits, const float* target, int B, int K, size_t HW, float thr,
+                   unsigned long long* counts, clr_stream_t stream) {
+    if (!logits || !target || !counts || B < 1 || K < 1 || HW == 0 || (long long)B * K > 65535) return CLR_ERR_BAD_ARG;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CLR_RETURN_IF_CUDA(cudaMemsetAsync(counts, 0, sizeof(unsigned long long) * 4 * (size_t)K, st));
+    float zthr = 0.f, guard = 3.0e38f;
+    const double t = (double)thr;
+    if (t > 0.0 && t < 1.0) {
+        zthr = (float)log(t / (1.0 - t));
+        const double g = 4e-6 / (t * (1.0 - t));
+        guard = (float)(g > 1e-4 ? g : 1e-4);
+    }
+    unsigned gx = (unsigned)((HW + 256 * 8 - 1) / (256 * 8));
+    if (gx < 1) gx = 1;
+    if (gx > 64) gx = 64;
+    clr::launch_k(clr::seg_counts_kernel, dim3(gx, (unsigned)(B * K)), 256, 0, st, logits, target, K, HW, thr, zthr, guard, counts);
+    return clr::launch_status();
 }
 
 }  // extern "C"

@@ -52,7 +52,10 @@ struct PoolParams {
     unsigned int* counter_reset;   // optional: zeroed by CTA 0 (arms the finish kernel's last-CTA counter)
 };
 
-constexpr int pool_cg(int R) { return (32 / R) < 16 ? (32 / R) : 16; }   // channels per item
+// Register blocking: a thread keeps CG x R accumulators -- 32 of them up to R = 8, 64 beyond (R = 16 would otherwise
+// leave 2 channels = 8 KB per item, and the per-item butterfly + barriers, not HBM, would bound the kernel).
+constexpr int pool_nacc(int R) { return R > 8 ? 64 : 32; }
+constexpr int pool_cg(int R) { return (pool_nacc(R) / R) < 16 ? (pool_nacc(R) / R) : 16; }   // channels per item
 constexpr int pool_reps(int R) { return (R >= 3 && R <= 8) ? 2 : 1; }    // VEC-wide pixel groups per thread
 
 struct ItemCoord { int d, slot, grp, b, chunk; };
@@ -121,10 +124,10 @@ __device__ __forceinline__ Pack<VEC> lds_pack(const float* p) {
 // CTA-level combine of the per-thread accumulators of one item and store of the partial row slices.
 // sync() is the barrier over the 256 compute threads.
 template <int R, int CG, int VEC, int REPS, typename Sync>
-__device__ __forceinline__ void reduce_and_store(float (&acc)[32], const float* wsm, float* red, int& parity,
+__device__ __forceinline__ void reduce_and_store(float (&acc)[pool_nacc(R)], const float* wsm, float* red, int& parity,
                                                  float* out, int C, int c0, bool owns_counts,
                                                  int tid, Sync sync) {
-    constexpr int PX = kThreads * VEC * REPS;
+    constexpr int PX = kThreads * VEC * REPS, NB = pool_nacc(R) / 32;
     const int lane = tid & 31, warp = tid >> 5;
     float nsum[R];
     if (owns_counts) {   // the item that owns channel group 0 also sums this chunk's weights
@@ -140,22 +143,28 @@ __device__ __forceinline__ void reduce_and_store(float (&acc)[32], const float* 
             nsum[r] = s;
         }
     }
-    const float tot = warp_sum_transpose32(acc, lane);
-    float* redp = red + parity * (kWarps * 32);
-    redp[warp * 32 + lane] = tot;
+    // accumulator i = j*R + r; block b of 32 goes through one transposing butterfly: lane l ends up with entry 32b + l
+    float* redp = red + parity * (NB * kWarps * 32);
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        float blk[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) blk[i] = acc[32 * b + i];
+        redp[(b * kWarps + warp) * 32 + lane] = warp_sum_transpose32(blk, lane);
+    }
     sync();
-    if (warp == 0) {
+    if (warp < NB) {
         float s = 0.f;
 #pragma unroll
-        for (int wq = 0; wq < kWarps; ++wq) s += redp[wq * 32 + lane];
-        const int j = lane / R, r = lane - j * R;
+        for (int wq = 0; wq < kWarps; ++wq) s += redp[(warp * kWarps + wq) * 32 + lane];
+        const int i = 32 * warp + lane, j = i / R, r = i - j * R;
         if (j < CG && c0 + j < C) out[(size_t)r * (C + 1) + c0 + j] = s;
     }
     parity ^= 1;
     if (owns_counts) {   // CTA-uniform
 #pragma unroll
         for (int r = 0; r < R; ++r) nsum[r] = warp_sum(nsum[r]);
-        float* redn = red + parity * (kWarps * 32);
+        float* redn = red + parity * (NB * kWarps * 32);
         if (lane == 0) {
 #pragma unroll
             for (int r = 0; r < R; ++r) redn[warp * 32 + r] = nsum[r];
@@ -181,7 +190,7 @@ __global__ void __launch_bounds__(kThreads, 2) pool_fwd_ldg_kernel(const PoolPar
     constexpr int CG = pool_cg(R), REPS = pool_reps(R), PX = kThreads * VEC * REPS;
     extern __shared__ __align__(16) float smem[];
     float* wsm = smem;                 // [R][PX]
-    float* red = smem + R * PX;        // [2][kWarps][32]
+    float* red = smem + R * PX;        // [2][NB][kWarps][32]
     const int tid = threadIdx.x;
     int begin, end;
     partition(p.total, gridDim.x, blockIdx.x, begin, end);
@@ -198,9 +207,9 @@ __global__ void __launch_bounds__(kThreads, 2) pool_fwd_ldg_kernel(const PoolPar
             stage_weights<R, VEC, REPS>(D, ic.b, px0, p.HW, wsm, tid);
             __syncthreads();
         }
-        float acc[32];
+        float acc[pool_nacc(R)];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+        for (int i = 0; i < pool_nacc(R); ++i) acc[i] = 0.f;
         const int c0 = ic.grp * CG;
         const float* xb = D.feat + ((size_t)ic.b * p.C + c0) * p.HW + px0;
 #pragma unroll
@@ -214,15 +223,15 @@ __global__ void __launch_bounds__(kThreads, 2) pool_fwd_ldg_kernel(const PoolPar
                 for (int v = 0; v < VEC; ++v) x[j].v[v] = 0.f;
                 if (ok && c0 + j < p.C) x[j] = ld_stream<VEC>(xb + (size_t)j * p.HW + off);
             }
-            Pack<VEC> w[R];
+            // weight row outermost: one row vector live at a time (R = 16 rows would not fit in registers otherwise)
 #pragma unroll
-            for (int r = 0; r < R; ++r) w[r] = lds_pack<VEC>(wsm + r * PX + off);
+            for (int r = 0; r < R; ++r) {
+                const Pack<VEC> w = lds_pack<VEC>(wsm + r * PX + off);
 #pragma unroll
-            for (int j = 0; j < CG; ++j)
+                for (int j = 0; j < CG; ++j)
 #pragma unroll
-                for (int r = 0; r < R; ++r)
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v) acc[j * R + r] = fmaf(x[j].v[v], w[r].v[v], acc[j * R + r]);
+                    for (int v = 0; v < VEC; ++v) acc[j * R + r] = fmaf(x[j].v[v], w.v[v], acc[j * R + r]);
+            }
         }
         float* out = D.partial + (size_t)ic.slot * R * (p.C + 1);
         reduce_and_store<R, CG, VEC, REPS>(acc, wsm, red, parity, out, p.C, c0, ic.grp == 0, tid, sync);
@@ -241,7 +250,7 @@ struct PoolTmaSmem {
     static constexpr int CG = pool_cg(R), REPS = pool_reps(R), PX = kThreads * 4 * REPS;
     static constexpr size_t stage_bytes = sizeof(float) * CG * PX;
     static constexpr size_t w_bytes = sizeof(float) * R * PX;
-    static constexpr size_t red_bytes = sizeof(float) * 2 * kWarps * 32;
+    static constexpr size_t red_bytes = sizeof(float) * 2 * (pool_nacc(R) / 32) * kWarps * 32;
     static constexpr size_t bar_bytes = sizeof(uint64_t) * 2 * kMaxStages;
     static size_t total(int stages) { return stages * stage_bytes + w_bytes + red_bytes + bar_bytes; }
 };
@@ -255,8 +264,8 @@ __global__ void __launch_bounds__(kPoolTmaThreads, 1) pool_fwd_tma_kernel(const 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* xs = reinterpret_cast<float*>(smem_raw);                                    // [stages][CG][PX]
     float* wsm = reinterpret_cast<float*>(smem_raw + p.stages * SM::stage_bytes);      // [R][PX]
-    float* red = wsm + R * PX;                                                         // [2][kWarps][32]
-    uint64_t* full = reinterpret_cast<uint64_t*>(red + 2 * kWarps * 32);               // [kMaxStages]
+    float* red = wsm + R * PX;                                                         // [2][NB][kWarps][32]
+    uint64_t* full = reinterpret_cast<uint64_t*>(red + 2 * (pool_nacc(R) / 32) * kWarps * 32);   // [kMaxStages]
     uint64_t* empty = full + kMaxStages;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -309,9 +318,9 @@ __global__ void __launch_bounds__(kPoolTmaThreads, 1) pool_fwd_tma_kernel(const 
             stage_weights<R, VEC, REPS>(D, ic.b, px0, p.HW, wsm, tid);
             sync();
         }
-        float acc[32];
+        float acc[pool_nacc(R)];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+        for (int i = 0; i < pool_nacc(R); ++i) acc[i] = 0.f;
         const int c0 = ic.grp * CG;
         const float* xst = xs + (size_t)stage * CG * PX;
         mbar_wait(&full[stage], phase);
@@ -319,19 +328,20 @@ __global__ void __launch_bounds__(kPoolTmaThreads, 1) pool_fwd_tma_kernel(const 
         for (int rep = 0; rep < REPS; ++rep) {
             const int off = (rep * kThreads + tid) * VEC;
             const bool ok = px0 + off < p.HW;   // bytes past the copied span are stale: never read them
-            Pack<VEC> w[R];
-#pragma unroll
-            for (int r = 0; r < R; ++r) w[r] = lds_pack<VEC>(wsm + r * PX + off);
+            Pack<VEC> x[CG];
 #pragma unroll
             for (int j = 0; j < CG; ++j) {
-                Pack<VEC> x;
 #pragma unroll
-                for (int v = 0; v < VEC; ++v) x.v[v] = 0.f;
-                if (ok && c0 + j < p.C) x = lds_pack<VEC>(xst + j * PX + off);
+                for (int v = 0; v < VEC; ++v) x[j].v[v] = 0.f;
+                if (ok && c0 + j < p.C) x[j] = lds_pack<VEC>(xst + j * PX + off);
+            }
 #pragma unroll
-                for (int r = 0; r < R; ++r)
+            for (int r = 0; r < R; ++r) {
+                const Pack<VEC> w = lds_pack<VEC>(wsm + r * PX + off);
 #pragma unroll
-                    for (int v = 0; v < VEC; ++v) acc[j * R + r] = fmaf(x.v[v], w[r].v[v], acc[j * R + r]);
+                for (int j = 0; j < CG; ++j)
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) acc[j * R + r] = fmaf(x[j].v[v], w.v[v], acc[j * R + r]);
             }
         }
         __syncwarp();
@@ -429,7 +439,7 @@ static void launch_reduce(const PoolParams& p, int R, cudaStream_t st) {
 template <int R, int VEC>
 static int launch_ldg(const PoolParams& p, cudaStream_t st) {
     constexpr int PX = kThreads * VEC * pool_reps(R);
-    constexpr size_t smem = sizeof(float) * (R * PX + 2 * kWarps * 32);
+    constexpr size_t smem = sizeof(float) * (R * PX + 2 * (pool_nacc(R) / 32) * kWarps * 32);
     auto kern = pool_fwd_ldg_kernel<R, VEC>;
     CLR_RETURN_IF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;

@@ -530,3 +530,37 @@ def uncertainty_map(o: torch.Tensor, smooth: float = 1e-7) -> torch.Tensor:
     """``-1.0 * torch.sigmoid(o) * torch.log(torch.sigmoid(o) + smooth)`` (Trainer_prototype_full.py:452, 481, 500):
     the entropy map fed to the uncertainty discriminator, one launch each way instead of five."""
     return _EntropyMap.apply(_require_cuda_f32(o, "o", o.dim()), smooth)
+
+
+# ----------------------------------------------------------------------------------------------- 8(f): validation
+def validation_counts(pred_logits: torch.Tensor, target: torch.Tensor, thr: float = 0.75) -> torch.Tensor:
+    """Per-class 2x2 confusion counts ``[K, 4]`` (int64, index ``2*gt + pred``) of ``sigmoid(pred) > thr`` against the
+    binary ``target`` -- the integers behind ``dice_coeff_2label`` and ``pixel_acc`` (utils/metrics.py:118-168),
+    computed on the device in one pass instead of a full-resolution ``.cpu()`` copy plus NumPy."""
+    lib = _lib.load()
+    z = _require_cuda_f32(pred_logits.detach(), "pred_logits")
+    t = _require_cuda_f32(target.detach(), "target")
+    if z.shape != t.shape:
+        raise ValueError("pred_logits %s and target %s disagree" % (tuple(z.shape), tuple(t.shape)))
+    B, K, H, W = z.shape
+    counts = torch.empty(K, 4, dtype=torch.int64, device=z.device)
+    with torch.cuda.device(z.device):
+        check(lib.clr_seg_counts(ptr(z), ptr(t), B, K, H * W, float(thr), ptr(counts), _stream()), "clr_seg_counts")
+    return counts
+
+
+def dice_from_counts(counts: torch.Tensor) -> torch.Tensor:
+    """``dice_coefficient_numpy`` (utils/metrics.py:81-100) per class: ``(2 |P&G| + 1) / (1 + |P| + |G|)`` -> ``[K]`` float64."""
+    c = counts.to(torch.float64)
+    inter, seg, gt = c[:, 3], c[:, 1] + c[:, 3], c[:, 2] + c[:, 3]
+    return (2.0 * inter + 1.0) / (1.0 + seg + gt)
+
+
+def pixel_acc_from_counts(counts: torch.Tensor):
+    """``pixelAccuracy`` and ``meanIntersectionOverUnion`` of ``SegmentationMetric(2)`` (utils/metrics.py:10-33) per
+    class -> ``(PA [K], mIoU [K])`` float64 (``nanmean`` over the two labels, as the reference)."""
+    c = counts.to(torch.float64)
+    n00, n01, n10, n11 = c[:, 0], c[:, 1], c[:, 2], c[:, 3]
+    pa = (n00 + n11) / c.sum(dim=1)
+    iou = torch.stack([n00 / (n00 + n01 + n10), n11 / (n11 + n10 + n01)], dim=1)
+    return pa, torch.nanmean(iou, dim=1)
