@@ -364,7 +364,7 @@ def main():
             traffic = json.load(open(tpath)).get("pool_fwd_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "pool_fwd_ldg_kernel<4,4> (source+target pooling, one launch) + pool_reduce",
+    roofline = {"bound": "hbm", "kernel": "pool_fwd_ldg_kernel<%d,4> (source + target pooling in one launch)" % (2 * a.K),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": ab["pool_fwd"], "kernel_us": pool_us,
                 "kernel_samples": len(pool_ev), "kernel_sample_stride": ev_stride,
