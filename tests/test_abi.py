@@ -67,3 +67,47 @@ def test_library_is_plain_c_abi():
     import subprocess
     out = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "torch" not in out and "python" not in out
+
+
+def test_new_entry_points_validate_arguments_without_gpu(lib):
+    """Argument checks of the one-pass / glue / exchange entry points run before any CUDA call."""
+    import ctypes
+    assert lib.clr_mc_retrify(None, None, 8, 1, 2, 8, 8, 32, 32, 0.75, 0.04, None, None, None, None, None) == -1
+    assert lib.clr_seg_loss_ws_bytes() > 0
+    assert lib.clr_seg_loss_fwd(None, None, 0, None, None, 0, None, 0, None, None) == -1
+    assert lib.clr_seg_loss_bwd(None, None, 0, None, None, 0, None, 1.0, None, None, None) == -1
+    assert lib.clr_entropy_fwd(None, 0, 1e-7, None, None) == -1
+    assert lib.clr_seg_counts(None, None, 1, 2, 16, 0.75, None, None) == -1
+    assert lib.clr_pool_rows_fwd_ps(None, None, 1, 1, 1, 1, None, 0, None, None) == -3      # workspace check comes first
+    assert lib.clr_bmm_finalize(None, 1, 1, 1, 1.0, None, None) == -1
+    assert lib.clr_peer_alloc(0, None) == -1 and lib.clr_peer_export(None, None) == -1
+    assert lib.clr_peer_open(None, None) == -1 and lib.clr_peer_close(None) == -1 and lib.clr_peer_free(None) == -1
+    assert lib.clr_trace_slots() >= 16 and lib.clr_trace_name(0) == b"mc_stats"
+
+
+def test_exchange_buffer_size_formula(lib):
+    """Receive buffer of the in-kernel exchange: 64-bit words, 2 parities x world sources x (packed1 + packed2 + tail)."""
+    K, C = 2, 256
+    n1, n2 = 2 * 2 * K * (C + 1), K * (C + 1) + 4
+    for world in (1, 2, 8):
+        assert lib.clr_step_xchg_bytes(world, K, C) == 8 * 2 * world * (n1 + n2)
+    assert lib.clr_step_xchg_bytes(9, K, C) == 0 and lib.clr_step_xchg_bytes(2, 9, C) == 0
+
+
+def test_step_args_layout_matches_header():
+    """The ctypes mirror of clr_step_args must keep the header's field order (the exchange fields were appended)."""
+    from uda_clr_b200 import _lib
+    src = open(HEADER).read()
+    start = src.index("typedef struct clr_step_args {") + len("typedef struct clr_step_args {")
+    body = src[start:src.index("} clr_step_args;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        for part in decl.split(","):
+            m = re.search(r"(\w+)\s*(\[\w+\])?\s*$", part.strip())
+            if m:
+                names.append(m.group(1))
+    assert names == [f[0] for f in _lib.StepArgs._fields_]
