@@ -295,9 +295,7 @@ typedef struct clr_step_args {
      * pooling launch) so a harness can time it inside a live step; NULL = not recorded */
     void* ev_pool_begin; void* ev_pool_end;
     void* ev_bwd_begin; void* ev_bwd_end;
-    /* optional second stream + two events (clr_event_create) for clr_step_run: the consistency pass and the
-     * backward of the target features run on `aux_stream` concurrently with the discriminative pass */
-    void* aux_stream; void* ev_fork; void* ev_join;
+    void* reserved_ptr[3];                /* (a second-stream schedule lived here; measured slower, removed) */
     /* Sharded step with the exchange INSIDE the kernels (clr_step_run only; world <= 1: unused).  peer_rx[q] is rank q's
      * receive buffer (clr_step_xchg_bytes bytes, zeroed once, see clr_peer_*) mapped into THIS process; peer_rx[rank] is
      * the local one.  `seq` must be the same on every rank and change by +1 per clr_step_run call (start at 1).  The
@@ -325,10 +323,8 @@ int clr_step_fwd_c(const clr_step_args* a, clr_stream_t stream);
 int clr_step_fwd(const clr_step_args* a, clr_stream_t stream);
 int clr_step_bwd(const clr_step_args* a, clr_stream_t stream);
 /* Forward AND backward in one call, for the common case that the step total enters the training loss with a known
- * (device-side, `gup`, default 1) coefficient.  With `aux_stream` set, independent kernels overlap: after the
- * alignment finalize, { consistency forward, gradient of the target features } run on the auxiliary stream while
- * the main stream does the discriminative pass; both join before the last finalize and the source-gradient write.
- * Results are identical to clr_step_fwd + clr_step_bwd. */
+ * (device-side, `gup`, default 1) coefficient: 7 launches; the two finish stages ride as the first CTAs of the
+ * consistency pass / the target-gradient write.  Results are identical to clr_step_fwd + clr_step_bwd. */
 int clr_step_run(const clr_step_args* a, clr_stream_t stream);
 
 #ifdef __cplusplus

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Device-side timeline of ONE live CLR step (GPU box only): which kernel ran when, where the gaps are.
 
-    python tools/timeline.py [--overlap] [--steps 3] [--B 8 --C 256 --H 128 --K 2] [--tunable name=value ...]
+    python tools/timeline.py [--steps 3] [--B 8 --C 256 --H 128 --K 2] [--tunable name=value ...]
 
 Every kernel of the library stamps ``%globaltimer`` into its trace slot (``clr_trace_enable``): earliest CTA start
 (before ``griddepcontrol.wait``), earliest return from the wait (= predecessor grid complete), latest CTA exit.
@@ -30,7 +30,6 @@ def main():
     ap.add_argument("--T", type=int, default=8)
     ap.add_argument("--up", type=int, default=4)
     ap.add_argument("--steps", type=int, default=3)
-    ap.add_argument("--overlap", action="store_true")
     ap.add_argument("--workload", default="clr3", choices=["clr3", "align"])
     ap.add_argument("--tunable", action="append", default=[])
     ap.add_argument("--json", default=None)
@@ -54,8 +53,6 @@ def main():
                           oT=d["oT"], oT_aug=d["oT_aug"], epoch=0.0)
         else:
             p = step.plan(d["xs"], d["ys"], d["xt"], wt=torch.sigmoid(d["oT_before"]))
-        if a.overlap:
-            p.enable_overlap(True)
         plans.append(p)
     for i in range(10):
         plans[i % NSET].run()
@@ -84,8 +81,7 @@ def main():
             rows.append((slot_names[i], t_first, t_ready, t_last, ncta))
         t0 = min(r[1] for r in rows)
         rows.sort(key=lambda r: r[2])
-        print("step %d (%s, overlap %s): kernel, first CTA start, predecessor done, last CTA exit, busy, CTAs [us]"
-              % (s, a.workload, "on" if a.overlap else "off"))
+        print("step %d (%s): kernel, first CTA start, predecessor done, last CTA exit, busy, CTAs [us]" % (s, a.workload))
         prev_end = None
         for name, tf, tr, tl, ncta in rows:
             gap = "" if prev_end is None else "  gap_after_prev %+6.2f" % ((tr - prev_end) / 1e3)

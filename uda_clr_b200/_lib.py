@@ -56,7 +56,7 @@ class StepArgs(Structure):
         ("gxs", _P), ("gxt", _P), ("g_oT_aug", _P),
         ("ws", _P), ("ws_bytes", c_size_t),
         ("ev_pool_begin", _P), ("ev_pool_end", _P), ("ev_bwd_begin", _P), ("ev_bwd_end", _P),
-        ("aux_stream", _P), ("ev_fork", _P), ("ev_join", _P),
+        ("reserved_ptr", _P * 3),
         ("world", c_int), ("rank", c_int), ("seq", ctypes.c_uint), ("reserved0", c_int), ("peer_rx", _P * 8),
     ]
 

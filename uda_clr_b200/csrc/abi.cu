@@ -40,15 +40,11 @@ int clr_set_tunable(const char* name, int value) {
     clr::Tunables& t = clr::tunables();
     if (!strcmp(name, "pool_impl")) t.pool_impl = value;
     else if (!strcmp(name, "pool_stages")) t.pool_stages = value;
-    else if (!strcmp(name, "dots_impl")) t.dots_impl = value;
-    else if (!strcmp(name, "bwd_impl")) t.bwd_impl = value;
     else if (!strcmp(name, "mc_precise")) t.mc_precise = value;
     else if (!strcmp(name, "disc_impl")) t.disc_impl = value;
     else if (!strcmp(name, "disc_tile")) t.disc_tile = value;
     else if (!strcmp(name, "disc_threads")) t.disc_threads = value;
-    else if (!strcmp(name, "l2_keep")) t.l2_keep = value;
     else if (!strcmp(name, "pdl_off")) t.pdl_off = value;
-    else if (!strcmp(name, "overlap_off")) t.overlap_off = value;
     else if (!strcmp(name, "finish_off")) t.finish_off = value;
     else if (!strcmp(name, "hfuse_off")) t.hfuse_off = value;
     else if (!strcmp(name, "mc_fuse")) t.mc_fuse = value;

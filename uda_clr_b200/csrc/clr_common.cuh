@@ -29,14 +29,10 @@ const DeviceFacts& device_facts();
 struct Tunables {
     int pool_impl;     // 0 = auto (128-bit LDG kernel, 2 CTAs/SM: fastest in the live step), 1 = force LDG, 2 = force the TMA ring
     int pool_stages;   // TMA ring depth (0 = auto)
-    int dots_impl;     // reserved
     int disc_impl;     // 0 = auto (one-read fused kernel, tensor-map TMA tiles), 1 = two-pass form, 2 = one-read kernel with cp.async tiles
-    int bwd_impl;      // reserved
     int disc_threads;  // 0 = auto (256-thread CTAs: fastest in the live step), 512 = 512-thread CTAs when K <= 2
     int disc_tile;     // 0 = auto, 64 = force 64-pixel tiles in the fused discriminative kernel
-    int l2_keep;       // 1 = evict-last policy on xs in the pooling pass (re-read by the discriminative pass); default off
     int pdl_off;       // 1 = do not use programmatic dependent launch
-    int overlap_off;   // 1 = clr_step_run ignores aux_stream (serial order)
     int mc_precise;    // 1 = ATen-exact sigmoids in clr_mc_stats (slower), 0 = fast intrinsics
     int finish_off;    // 1 = single-GPU step uses the separate reduce / finalize kernels instead of the merged finish kernels
     int hfuse_off;     // 1 = finish bodies get launches of their own instead of riding with cons / the target-gradient write

@@ -95,26 +95,24 @@ int clr_step_fwd_a(const clr_step_args* a, clr_stream_t stream) {
     float* sums_t = a->packed1 + (size_t)R * (a->C + 1);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (a->ev_pool_begin) cudaEventRecord(static_cast<cudaEvent_t>(a->ev_pool_begin), st);
-    // target first, source last; optionally ("l2_keep" = 1) the source rows get an evict-last L2 policy because
-    // the discriminative pass re-reads xs right afterwards
-    const int keep_xs = (a->use_disc && clr::tunables().l2_keep == 1) ? 1 : 0;   // measured slower on B200 (profiles/): off by default
+    // target first, source last (an evict-last L2 policy on xs for the discriminative re-read was measured slower:
+    // 134 MB > the 126 MB L2)
     rc = clr::pool_fwd_impl(a->xt, clr::target_weights(a), clr::target_fmt(a), a->B_t, sums_t,
                             a->xs, a->ys, CLR_W_COMPLEMENT, a->B_s, sums_s,
-                            a->C, HW, R, w.pool, w.pool_bytes, st, 0, keep_xs);
+                            a->C, HW, R, w.pool, w.pool_bytes, st, 0, 0);
     if (a->ev_pool_end) cudaEventRecord(static_cast<cudaEvent_t>(a->ev_pool_end), st);
     return rc;
 }
 
 namespace clr {
 struct PendingPack { const float* hinge; int n_hinge, hinge_stride; const double* cons; int n_cons; };
-static int step_fwd_b_impl(const clr_step_args* a, clr_stream_t stream, PendingPack* defer, cudaStream_t side);
+static int step_fwd_b_impl(const clr_step_args* a, clr_stream_t stream, PendingPack* defer);
 }  // namespace clr
 
-int clr_step_fwd_b(const clr_step_args* a, clr_stream_t stream) { return clr::step_fwd_b_impl(a, stream, nullptr, nullptr); }
+int clr_step_fwd_b(const clr_step_args* a, clr_stream_t stream) { return clr::step_fwd_b_impl(a, stream, nullptr); }
 
 // `defer` != NULL: leave the per-CTA partials unsummed and describe them (the caller's finalize kernel sums them).
-// `side` != NULL: fork after the alignment finalize (a->ev_fork) and run the consistency pass on that stream.
-static int clr::step_fwd_b_impl(const clr_step_args* a, clr_stream_t stream, clr::PendingPack* defer, cudaStream_t side) {
+static int clr::step_fwd_b_impl(const clr_step_args* a, clr_stream_t stream, clr::PendingPack* defer) {
     int rc = clr::check_args(a);
     if (rc != CLR_OK) return rc;
     const clr::StepWs w = clr::carve(a);
@@ -127,13 +125,9 @@ static int clr::step_fwd_b_impl(const clr_step_args* a, clr_stream_t stream, clr
                             a->use_disc ? a->disc_vec : nullptr, a->use_disc ? a->disc_beta : nullptr, a->losses, stream);
     if (rc != CLR_OK) return rc;
     int n_hinge = 0, n_cons = 0;
-    if (side) {
-        CLR_RETURN_IF_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(a->ev_fork), st));
-        CLR_RETURN_IF_CUDA(cudaStreamWaitEvent(side, static_cast<cudaEvent_t>(a->ev_fork), 0));
-    }
     if (a->use_cons) {
         rc = clr::cons_fwd_partials(a->oT, a->oT_aug, a->masks, a->B_t, K, a->Hi, a->Wi, a->H, a->W,
-                                    a->cons_threshold, w.cons, &n_cons, side ? side : st);
+                                    a->cons_threshold, w.cons, &n_cons, st);
         if (rc != CLR_OK) return rc;
     }
     int hinge_stride = 1 + K;
@@ -302,7 +296,7 @@ static int step_fwd_unmerged(const clr_step_args* a, clr_stream_t stream) {
     int rc = clr_step_fwd_a(a, stream);
     if (rc != CLR_OK) return rc;
     PendingPack pk{};
-    rc = step_fwd_b_impl(a, stream, &pk, nullptr);
+    rc = step_fwd_b_impl(a, stream, &pk);
     if (rc != CLR_OK) return rc;
     const float ema0 = a->first_s ? 1.0f : (float)a->decay;
     return disc_finalize_impl(a->packed2, a->P_s, a->K, a->C, a->npx_global, a->w_disc, ema0, a->grad_scale,
@@ -336,66 +330,31 @@ int clr_step_run(const clr_step_args* a, clr_stream_t stream) {
     int rc = clr::check_args(a);
     if (rc != CLR_OK) return rc;
     if (!a->gxs || !a->gxt) return CLR_ERR_BAD_ARG;
-    if (a->world > 1 && clr::tunables().finish_off) return CLR_ERR_UNSUPPORTED;
-    if (!a->aux_stream || !a->ev_fork || !a->ev_join || clr::tunables().overlap_off || a->world > 1) {
-        if (clr::tunables().finish_off) {
-            rc = clr::step_fwd_unmerged(a, stream);
-            return rc != CLR_OK ? rc : clr_step_bwd(a, stream);
-        }
-        clr::DiscFinishParams df{};
-        int deferred = 0;
-        rc = clr::step_fwd_core(a, static_cast<cudaStream_t>(stream), &df, &deferred);
-        if (rc != CLR_OK) return rc;
-        if (!deferred) return clr_step_bwd(a, stream);
-        // [disc finish | gradient of xt] in one launch, then the gradient of xs (needs the finish's table)
-        clr_bwd_dom dd[2];
-        clr::bwd_doms(a, dd);
-        cudaStream_t s0 = static_cast<cudaStream_t>(stream);
-        if (a->ev_bwd_begin) cudaEventRecord(static_cast<cudaEvent_t>(a->ev_bwd_begin), s0);
-        clr::tunables().bwd_trace_id = clr::TR_BWD_T;
-        rc = clr::pool_bwd_with_finish(&dd[1], a->C, a->H * a->W, a->K, df, s0);
-        clr::tunables().bwd_trace_id = clr::TR_BWD_S;
-        if (rc == CLR_OK) rc = clr_pool_bwd_multi(&dd[0], 1, a->C, a->H * a->W, a->K, stream);
-        clr::tunables().bwd_trace_id = 0;
-        if (a->ev_bwd_end) cudaEventRecord(static_cast<cudaEvent_t>(a->ev_bwd_end), s0);
-        if (rc != CLR_OK) return rc;
-        if (a->use_cons && a->w_aug != 0.f && a->g_oT_aug) {
-            const float* stats = a->packed2 + (size_t)a->K * (a->C + 1);
-            rc = clr_cons_bwd(a->oT, a->oT_aug, a->masks, a->B_t, a->K, a->Hi, a->Wi, a->H, a->W, a->cons_threshold,
-                              a->aug_weight, stats + 1, a->gup, a->grad_scale * a->w_aug, a->g_oT_aug, stream);
-        }
-        return rc;
+    if (clr::tunables().finish_off) {
+        if (a->world > 1) return CLR_ERR_UNSUPPORTED;
+        rc = clr::step_fwd_unmerged(a, stream);
+        return rc != CLR_OK ? rc : clr_step_bwd(a, stream);
     }
-    cudaStream_t st = static_cast<cudaStream_t>(stream), aux = static_cast<cudaStream_t>(a->aux_stream);
-    const int HW = a->H * a->W, C = a->C, K = a->K;
-    rc = clr_step_fwd_a(a, stream);
+    clr::DiscFinishParams df{};
+    int deferred = 0;
+    rc = clr::step_fwd_core(a, static_cast<cudaStream_t>(stream), &df, &deferred);
     if (rc != CLR_OK) return rc;
-    clr::PendingPack pk{};
-    rc = clr::step_fwd_b_impl(a, stream, &pk, aux);      // align (main) | fork | cons (aux) | disc (main)
-    if (rc != CLR_OK) return rc;
-    clr_bwd_dom d[2];
-    clr::bwd_doms(a, d);
+    if (!deferred) return clr_step_bwd(a, stream);
+    // [disc finish | gradient of xt] in one launch, then the gradient of xs (needs the finish's table)
+    clr_bwd_dom dd[2];
+    clr::bwd_doms(a, dd);
+    cudaStream_t s0 = static_cast<cudaStream_t>(stream);
+    if (a->ev_bwd_begin) cudaEventRecord(static_cast<cudaEvent_t>(a->ev_bwd_begin), s0);
     clr::tunables().bwd_trace_id = clr::TR_BWD_T;
-    rc = clr_pool_bwd_multi(&d[1], 1, C, HW, K, aux);    // d total / d xt needs only g_t: overlaps the discriminative pass
-    clr::tunables().bwd_trace_id = 0;
-    if (rc != CLR_OK) return rc;
-    CLR_RETURN_IF_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(a->ev_join), aux));
-    CLR_RETURN_IF_CUDA(cudaStreamWaitEvent(st, static_cast<cudaEvent_t>(a->ev_join), 0));
-    const float ema = a->first_s ? 1.0f : (float)a->decay;
-    rc = clr::disc_finalize_impl(a->packed2, a->P_s, K, C, a->npx_global, a->w_disc, ema, a->grad_scale,
-                                 a->g_s, a->xtab, a->w_intra, a->w_inter, a->w_aug, a->aug_weight,
-                                 a->use_disc, a->use_cons, a->losses, pk.hinge, pk.n_hinge, pk.hinge_stride,
-                                 pk.cons, pk.n_cons, st);
-    if (rc != CLR_OK) return rc;
-    if (a->ev_bwd_begin) cudaEventRecord(static_cast<cudaEvent_t>(a->ev_bwd_begin), st);
+    rc = clr::pool_bwd_with_finish(&dd[1], a->C, a->H * a->W, a->K, df, s0);
     clr::tunables().bwd_trace_id = clr::TR_BWD_S;
-    rc = clr_pool_bwd_multi(&d[0], 1, C, HW, K, stream);
+    if (rc == CLR_OK) rc = clr_pool_bwd_multi(&dd[0], 1, a->C, a->H * a->W, a->K, stream);
     clr::tunables().bwd_trace_id = 0;
-    if (a->ev_bwd_end) cudaEventRecord(static_cast<cudaEvent_t>(a->ev_bwd_end), st);
+    if (a->ev_bwd_end) cudaEventRecord(static_cast<cudaEvent_t>(a->ev_bwd_end), s0);
     if (rc != CLR_OK) return rc;
     if (a->use_cons && a->w_aug != 0.f && a->g_oT_aug) {
-        const float* stats = a->packed2 + (size_t)K * (C + 1);
-        rc = clr_cons_bwd(a->oT, a->oT_aug, a->masks, a->B_t, K, a->Hi, a->Wi, a->H, a->W, a->cons_threshold,
+        const float* stats = a->packed2 + (size_t)a->K * (a->C + 1);
+        rc = clr_cons_bwd(a->oT, a->oT_aug, a->masks, a->B_t, a->K, a->Hi, a->Wi, a->H, a->W, a->cons_threshold,
                           a->aug_weight, stats + 1, a->gup, a->grad_scale * a->w_aug, a->g_oT_aug, stream);
     }
     return rc;

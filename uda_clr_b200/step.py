@@ -294,21 +294,6 @@ class CLRPlan:
         self.device = dev
         self._lib = _lib.load()
         self._ref = ctypes.byref(a)
-        self._aux = None
-        self._ev = None
-
-    def enable_overlap(self, on: bool = True) -> None:
-        """Run the consistency pass and the target-gradient write on an auxiliary stream, concurrently with the
-        discriminative pass (``clr_step_run`` fork/join).  Results are bit-identical; on a B200 the step is
-        HBM-bound end to end, so the measured gain is nil (profiles/r01_summary.md) and the default is off."""
-        a: StepArgs = self.holder["args"]
-        if on:
-            if self._aux is None:
-                self._aux = torch.cuda.Stream(device=self.device)
-                self._ev = (_lib.Event(), _lib.Event())
-            a.aux_stream, a.ev_fork, a.ev_join = self._aux.cuda_stream, self._ev[0].handle, self._ev[1].handle
-        else:
-            a.aux_stream = a.ev_fork = a.ev_join = None
 
     def set_events(self, pool_begin=None, pool_end=None, bwd_begin=None, bwd_end=None) -> None:
         """Have the library record these :class:`uda_clr_b200._lib.Event` objects around the pooling / backward
