@@ -313,6 +313,38 @@ def main():
     value = 2 * a.B * a.H * a.H * world / (ms_per_step * 1e-3) / 1e6
     losses = plans[0].losses.detach().cpu().tolist()
 
+    # ---- supplementary (outside the timed region): per-kernel busy time of a live step from the library's own
+    #      device-side %globaltimer stamps -- no event records, programmatic dependent launch intact ----------------
+    device_trace = None
+    N_TRACE = 6                      # every rank runs the same number of steps (the in-kernel exchange is collective)
+    if rank == 0:
+        try:
+            import ctypes
+            n_slots = lib.clr_trace_slots()
+            tbuf = (ctypes.c_ulonglong * (4 * n_slots))()
+            _lib.check(lib.clr_trace_enable(1), "clr_trace_enable")
+            acc = {}
+            for i in range(N_TRACE):
+                plans[i % NSET].run()
+                _lib.check(lib.clr_trace_read(tbuf), "clr_trace_read")
+                if i == 0:
+                    continue         # the first traced step installs the trace pointers (one memcpy per kernel type)
+                rows = [(lib.clr_trace_name(j).decode(), tbuf[4 * j], tbuf[4 * j + 1], tbuf[4 * j + 2]) for j in range(n_slots)
+                        if tbuf[4 * j + 3] and tbuf[4 * j]]
+                t0 = min(r[1] for r in rows)
+                acc.setdefault("step_span", []).append((max(r[3] for r in rows) - t0) / 1e3)
+                for name, tf, tr, tl in rows:
+                    acc.setdefault(name, []).append((tl - tr) / 1e3)
+            _lib.check(lib.clr_trace_enable(0), "clr_trace_enable")
+            device_trace = {k: round(statistics.median(v), 2) for k, v in acc.items()}
+        except Exception as e:       # profiling aid only
+            device_trace = {"error": str(e)[:120]}
+    else:
+        for i in range(N_TRACE):
+            plans[i % NSET].run()
+            torch.cuda.synchronize()
+    barrier()
+
     # ---- e2e: pinned host inputs -> device -> step -> losses back to the host, every step ----------
     e2e = None
     if not a.no_e2e:
@@ -367,6 +399,7 @@ def main():
     roofline = {"bound": "hbm", "kernel": "pool_fwd_ldg_kernel<%d,4> (source + target pooling in one launch)" % (2 * a.K),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": ab["pool_fwd"], "kernel_us": pool_us,
+                "kernel_us_device_trace": (device_trace or {}).get("pool_fwd"), "device_trace_us": device_trace,
                 "kernel_samples": len(pool_ev), "kernel_sample_stride": ev_stride,
                 "bwd_kernel": {"kernel": "pool_bwd_kernel (both gradient maps, one launch)", "kernel_us": bwd_us,
                                "achieved": ab["pool_bwd"] / (bwd_us * 1e-6) / 1e9,
