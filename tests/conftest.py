@@ -23,3 +23,13 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords and not has_gpu:
             item.add_marker(skip_gpu)
+
+
+def pytest_sessionstart(session):
+    """Make sure the in-tree C-ABI library matches the sources (no-op when the stamp is fresh; nvcc cross-compiles
+    without a GPU).  A failed build is not hidden: the ops raise when the library is missing."""
+    try:
+        from uda_clr_b200 import build
+        build.build()
+    except Exception as e:  # pragma: no cover
+        sys.stderr.write("conftest: could not (re)build libclr_b200.so: %s\n" % str(e)[:300])
