@@ -452,6 +452,44 @@ def test_disc_fused_and_two_pass_agree_with_oracle(B, C, H, W, K):
             assert np.abs(dl - aux["delta"]).max() < 1e-5 * max(1.0, np.abs(aux["delta"]).max())
 
 
+def test_fused_step_soft_target_gradient_reaches_the_logits():
+    """Without retrify the shipped trainer pools the target with SOFT predictions sigmoid(oT_before) that carry a
+    graph (Trainer_prototype_full.py:375-377): the fused step must return dL/dwt too (one more read of xt), and
+    autograd chains it into oT_before.  Checked against the fp64 oracle and against the eager port on the same GPU."""
+    K, C, H, B = 2, 40, 32, 3
+    b = synth.make_batch(B=B, C=C, H=H, W=H, K=K, image_res=False, seed=91)
+    step = clr.CLRStep(K=K, retrify=False, use_disc=False, use_cons=False)
+    port = TP.ClrStepPort(retrify=False, use_disc=False, use_cons=False)
+    for it in range(2):
+        xs = b.xs.to(DEV).requires_grad_(True)
+        xt = b.xt.to(DEV).requires_grad_(True)
+        o1 = b.oT_before.to(DEV).requires_grad_(True)
+        out = step(xs, b.ys.to(DEV), xt, oT_before=o1)
+        (1.5 * out.total).backward()
+        xs2 = b.xs.to(DEV).requires_grad_(True)
+        xt2 = b.xt.to(DEV).requires_grad_(True)
+        o2 = b.oT_before.to(DEV).requires_grad_(True)
+        # the port's step() calls backward() on its own total: scale through a hook-free second pass
+        cur_s = TP.gen_prototype(b.ys.to(DEV), xs2)
+        Ps = port.ema_s.update(cur_s)
+        cur_t = TP.gen_prototype(torch.sigmoid(o2), xt2)
+        Pt = port.ema_t.update(cur_t)
+        intra, _ = TP.align_losses(Ps, Pt)
+        (1.5 * 0.1 * intra).backward()
+        assert o1.grad is not None and float(o1.grad.abs().max()) > 0
+        assert relerr(o1.grad.cpu().numpy(), o2.grad.cpu().numpy()) < TOL_GRAD
+        assert relerr(xt.grad.cpu().numpy(), xt2.grad.cpu().numpy()) < TOL_GRAD
+        assert relerr(xs.grad.cpu().numpy(), xs2.grad.cpu().numpy()) < TOL_GRAD
+    # oracle (first step of a fresh state): d total / d wt chained through sigmoid' by hand
+    step = clr.CLRStep(K=K, retrify=False, use_disc=False, use_cons=False)
+    o1 = b.oT_before.to(DEV).requires_grad_(True)
+    out = step(b.xs.to(DEV).requires_grad_(True), b.ys.to(DEV), b.xt.to(DEV).requires_grad_(True), oT_before=o1)
+    out.total.backward()
+    wt = 1.0 / (1.0 + np.exp(-b.oT_before.numpy().astype(np.float64)))
+    o = O.clr_step(b.xs.numpy(), b.ys.numpy(), b.xt.numpy(), wt, w_intra=0.1)
+    assert relerr(o1.grad.cpu().numpy(), o["gwt"] * wt * (1.0 - wt)) < TOL_GRAD
+
+
 def test_plan_run_equals_autograd_path():
     """CLRPlan.run() (clr_step_run: forward + backward in one call, finish stages riding with the streaming launches)
     must give the same numbers as the autograd path (clr_step_fwd, then .backward() -> clr_step_bwd), bit for bit."""

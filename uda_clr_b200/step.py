@@ -75,7 +75,7 @@ class _Buffers:
 
 class _ClrStepFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, step, args_holder, xs, xt, oT_aug):
+    def forward(ctx, step, args_holder, xs, xt, oT_aug, wt_soft=None):
         lib = _lib.load()
         a: StepArgs = args_holder["args"]
         st = _stream()
@@ -94,6 +94,7 @@ class _ClrStepFn(torch.autograd.Function):
         ctx.holder = args_holder
         ctx.xs_shape, ctx.xt_shape = tuple(xs.shape), tuple(xt.shape)
         ctx.aug_shape = None if oT_aug is None else tuple(oT_aug.shape)
+        ctx.xt_saved = xt if (wt_soft is not None and ctx.needs_input_grad[5]) else None    # dL/dw needs the features again
         return args_holder["buf"].losses[4].clone()
 
     @staticmethod
@@ -111,7 +112,18 @@ class _ClrStepFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             check(lib.clr_step_bwd(ctypes.byref(a), _stream()), "clr_step_bwd")
         h["keep_bwd"] = (gxs, gxt, g_aug, gup)
-        return None, None, gxs, gxt, g_aug
+        g_wt = None
+        if ctx.xt_saved is not None:
+            # soft target predictions (gen_prototype(sigmoid(oT_before), xt), Trainer_prototype_full.py:375-377):
+            # dL/dw_r[b,p] = sum_c g_r[c]/N_r (x[b,c,p] - mu_r[c]); one more read of xt, chained into sigmoid by autograd
+            from .ops import pool_backward_weights
+            K, C = a.K, a.C
+            R = 2 * K
+            buf = h["buf"]
+            g_t = buf.g_t.view(R, C)
+            sums_t = buf.packed1[R * (C + 1):].view(R, C + 1)
+            g_wt = pool_backward_weights(ctx.xt_saved, a.wt_fmt, K, g_t, sums_t, float(a.grad_scale)) * gup
+        return None, None, gxs, gxt, g_aug, g_wt
 
 
 class CLRStep:
@@ -175,7 +187,7 @@ class CLRStep:
             if wt is None:
                 if oT_before is None:
                     raise ValueError("retrify=False needs wt (target weights) or oT_before")
-                wt = torch.sigmoid(oT_before.detach())
+                wt = torch.sigmoid(oT_before)     # graph kept: the step returns dL/dwt, autograd chains it into oT_before
             wt_t = _require_cuda_f32(wt.detach(), "wt")
             wt_fmt = CLR_W_COMPLEMENT if wt_t.shape[1] == K else CLR_W_EXPLICIT
             oTb = pr = None
@@ -235,7 +247,8 @@ class CLRStep:
             self._ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         a.ws, a.ws_bytes = ptr(self._ws), ws_bytes
 
-        holder = dict(args=a, buf=buf, xs=xs, xt=xt, oT_aug=oTa, dims=(B_s, B_t, C, H, W, K, Hi, Wi), peer=peer,
+        wt_soft = wt if (not self.retrify and isinstance(wt, torch.Tensor) and wt.requires_grad) else None
+        holder = dict(args=a, buf=buf, xs=xs, xt=xt, oT_aug=oTa, dims=(B_s, B_t, C, H, W, K, Hi, Wi), peer=peer, wt_soft=wt_soft,
                       keep=(xs, ys, xt, wt_t, oTb, pr, oT_d, oTa, self.stored_s, self.stored_t, self._ws,
                             masks_t if (use_cons and not self.retrify) else None))
         return holder
@@ -258,9 +271,11 @@ class CLRStep:
     def __call__(self, xs_feature, pred_oS, xt_feature, oT_before=None, wt=None, preds=None, T: int = 8,
                  oT=None, oT_aug=None, masks=None, epoch: float = 0.0) -> CLRStepOutput:
         """One differentiable CLR step; ``out.total.backward()`` (or adding it to the trainer's ``loss_all``)
-        writes the gradients of ``xs_feature``, ``xt_feature`` (and ``oT_aug`` with ``backprop_aug``)."""
+        writes the gradients of ``xs_feature``, ``xt_feature`` (and ``oT_aug`` with ``backprop_aug``).  Without retrify,
+        soft target weights that require grad (``wt``, or ``sigmoid(oT_before)`` built here) receive theirs too, as
+        in ``gen_prototype(torch.sigmoid(oT_before), xt_feature)`` (Trainer_prototype_full.py:375-377)."""
         holder = self._prepare(xs_feature, pred_oS, xt_feature, oT_before, wt, preds, T, oT, oT_aug, masks, epoch)
-        total = _ClrStepFn.apply(self, holder, holder["xs"], holder["xt"], holder["oT_aug"])
+        total = _ClrStepFn.apply(self, holder, holder["xs"], holder["xt"], holder["oT_aug"], holder["wt_soft"])
         self.first_s = self.first_t = False
         return self._outputs(holder, total)
 
