@@ -136,17 +136,34 @@ __device__ __forceinline__ void cons_body(const ConsArgs& a, const unsigned cta,
             const unsigned v = v0 + u * nthreads;
             if (v >= g.total_vec) continue;
             Pack<VEC> go;
+            float lv[VEC], mv[VEC];
+            bool rare = false;
 #pragma unroll
             for (int e = 0; e < VEC; ++e) {
                 const float m = shared_mask ? msh[u] : __ldg(mrow[u] + nearest_src((int)(xv[u] * VEC + e), g.sw, g.W));
                 if (BWD) {
                     go.v[e] = coef * m * cons_grad_elem(zt[u].v[e], za[u].v[e], thr);
                 } else {
-                    num = fmaf(m, cons_loss_elem(zt[u].v[e], za[u].v[e], thr), num);
+                    // branch-free common case; `rare` collects the elements that need the exact expressions (label
+                    // inside the guard band, or confidently wrong |za| > 9): ONE branch per vector re-does them
+                    const float d = zt[u].v[e] - thr.zthr;
+                    const float x = (d > 0.f ? -1.4426950408889634f : 1.4426950408889634f) * za[u].v[e];
+                    lv[e] = 0.6931471805599453f * lg2_approx(1.0f + ex2_approx(x));
+                    mv[e] = m;
+                    rare |= (fabsf(d) <= thr.guard) | (x > 13.0f);
                     den += m;
                 }
             }
-            if (BWD) st_stream<VEC>(grad + (size_t)v * VEC, go);
+            if (BWD) {
+                st_stream<VEC>(grad + (size_t)v * VEC, go);
+            } else {
+                if (rare) {
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) lv[e] = cons_loss_elem(zt[u].v[e], za[u].v[e], thr);
+                }
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) num = fmaf(mv[e], lv[e], num);
+            }
         }
     }
     if (!BWD) {
