@@ -1,7 +1,10 @@
 #!/usr/bin/env python3
 """CLR op sweep (BASELINE.json configs[4]): C = 256/305/512, H = W = 64..256, K = 2..8, B = 8..64 on one GPU.
 
-    python tools/sweep.py [--quick] [--json out.json]
+    python tests/perf/sweep.py [--quick] [--json out.json]
+
+(Lives under tests/ because it uses the oracle's eager port as the checker; nothing outside tests/, smoke() and
+bench.py's CPU legs may import oracle/.)
 
 Per point: the fused step (clr3 workload) is timed with CUDA events over back-to-back steps (two rotating input sets),
 checked for finite outputs and -- where the eager-PyTorch port of the reference fits in memory -- compared with that
@@ -14,7 +17,7 @@ import sys
 
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import uda_clr_b200 as clr  # noqa: E402
 from oracle import clr_torch_port as TP  # noqa: E402  (checker only)
 from uda_clr_b200 import synth  # noqa: E402

@@ -152,91 +152,8 @@ def main():
         bat = time_batch(run, a.iters)
         res[name] = dict(us=round(med, 2), best_us=round(best, 2), batch_us=round(bat, 2))
 
-    # the tougher baseline: the reference's eager op sequence ON THIS GPU, whole CLR step fwd + bwd,
-    # and the drop-in ops (gen_prototype / gen_prototype_retrify under autograd) against the same eager functions
-    from oracle import clr_torch_port as TP
-    port = TP.ClrStepPort(retrify=True, use_disc=True, use_cons=True, backprop_aug=False)
-
-    def eager_step(i):
-        xs, xt = xs_l[i % a.nbuf], xs_l[(i + 1) % a.nbuf]
-        xs.grad = None
-        xt.grad = None
-        port.step(xs, t["ys"], xt, t["oT_before"], preds=t["preds"], features=None, T=8, oT=t["oT"], oT_aug=t["oT_aug"], epoch=0.0)
-    med, best = time_it(eager_step, max(5, a.iters // 2))
-    res["step_clr3_eager_port_on_gpu"] = dict(us=round(med, 2), best_us=round(best, 2))
-    step_p = clr.CLRStep(K=K, retrify=True, use_disc=True, use_cons=True)
-    plan_p = step_p.plan(xs_l[0].detach(), t["ys"], xs_l[1].detach(), oT_before=t["oT_before"], preds=t["preds"], T=8, oT=t["oT"],
-                         oT_aug=t["oT_aug"])
-    res["step_clr3_plan_run"] = dict(batch_us=round(time_batch(lambda i: plan_p.run(), 50), 2))
-    seeds4 = [torch.randn(1, C, 1, 1, device=dev) for _ in range(2 * K)]
-
-    def dropin(fn_proto, fn_retr):
-        def run(i):
-            xs, xt = xs_l[i % a.nbuf], xs_l[(i + 1) % a.nbuf]
-            xs.grad = None
-            xt.grad = None
-            ps = fn_proto(t["ys"], xs)
-            pt = fn_retr(t["oT_before"], xt, t["preds"], None, 8, B)[:2 * K]
-            sum((p * s).sum() for p, s in zip(list(ps) + list(pt), seeds4 + seeds4)).backward()
-        return run
-    med, best = time_it(dropin(clr.gen_prototype, clr.gen_prototype_retrify), a.iters)
-    res["dropin_gen_prototype+retrify_ours"] = dict(us=round(med, 2), best_us=round(best, 2))
-    med, best = time_it(dropin(TP.gen_prototype, TP.gen_prototype_retrify), max(5, a.iters // 2))
-    res["dropin_gen_prototype+retrify_eager_gpu"] = dict(us=round(med, 2), best_us=round(best, 2))
-
-    # 8(f) glue at image resolution: ours vs the eager ATen sequence of the trainer on the same GPU (fwd + bwd)
-    Hi = 4 * H
-    oS = [torch.randn(B, K, Hi, Hi, device=dev).requires_grad_(True) for _ in range(a.nbuf)]
-    bS = [torch.randn(B, 1, Hi, Hi, device=dev).requires_grad_(True) for _ in range(a.nbuf)]
-    tmap = (torch.rand(B, K, Hi, Hi, device=dev) > 0.5).float()
-    tbd = torch.rand(B, 1, Hi, Hi, device=dev)
-    seg_bytes = 4 * B * Hi * Hi * (K + 1) * (2 + 3)       # fwd: 2 reads; bwd: 2 reads + 1 write, per term
-
-    def seg_ours(i):
-        o, b_ = oS[i % a.nbuf], bS[i % a.nbuf]
-        o.grad = None; b_.grad = None
-        clr.seg_loss(o, b_, tmap, tbd).backward()
-
-    def seg_eager(i):
-        o, b_ = oS[i % a.nbuf], bS[i % a.nbuf]
-        o.grad = None; b_.grad = None
-        TP.seg_loss(o, b_, tmap, tbd).backward()
-    rec("seg_loss_fwd_bwd_ours", seg_ours, seg_bytes)
-    rec("seg_loss_fwd_bwd_eager_aten", seg_eager, seg_bytes)
-    # the same through the raw C ABI (no autograd / allocator overhead): kernel-level time
-    segws = torch.empty(lib.clr_seg_loss_ws_bytes(), dtype=torch.uint8, device=dev)
-    segout = torch.empty(4, device=dev)
-    g1 = torch.empty(B, K, Hi, Hi, device=dev)
-    g2 = torch.empty(B, 1, Hi, Hi, device=dev)
-
-    def seg_raw(i):
-        o, b_ = oS[i % a.nbuf], bS[i % a.nbuf]
-        check(lib.clr_seg_loss_fwd(ptr(o), ptr(tmap), o.numel(), ptr(b_), ptr(tbd), b_.numel(), ptr(segws), segws.numel(),
-                                   ptr(segout), stream), "seg fwd")
-        check(lib.clr_seg_loss_bwd(ptr(o), ptr(tmap), o.numel(), ptr(b_), ptr(tbd), b_.numel(), None, 1.0, ptr(g1), ptr(g2),
-                                   stream), "seg bwd")
-    rec("seg_loss_fwd_bwd_c_abi", seg_raw, seg_bytes)
-    gw = torch.randn(B, K, Hi, Hi, device=dev)
-
-    def ent_raw(i):
-        o = oS[i % a.nbuf]
-        check(lib.clr_entropy_fwd(ptr(o), o.numel(), 1e-7, ptr(g1), stream), "ent fwd")
-        check(lib.clr_entropy_bwd(ptr(o), ptr(gw), o.numel(), 1e-7, ptr(g1), stream), "ent bwd")
-    rec("uncertainty_map_fwd_bwd_c_abi", ent_raw, 4 * B * K * Hi * Hi * (2 + 3))
-    ent_bytes = 4 * B * K * Hi * Hi * (2 + 3)
-
-    def ent_ours(i):
-        o = oS[i % a.nbuf]
-        o.grad = None
-        clr.uncertainty_map(o).backward(gw)
-
-    def ent_eager(i):
-        o = oS[i % a.nbuf]
-        o.grad = None
-        TP.uncertainty_map(o).backward(gw)
-    rec("uncertainty_map_fwd_bwd_ours", ent_ours, ent_bytes)
-    rec("uncertainty_map_fwd_bwd_eager_aten", ent_eager, ent_bytes)
-
+    # (the eager-ATen baselines of the same workloads on this GPU live in tests/perf/eager_gpu_baseline.py: they use the
+    #  oracle's port, which only tests/ may import)
     print(json.dumps(dict(shape=[B, C, H, H, K], F_MB=F / 1e6, results=res), indent=1))
 
 
