@@ -78,7 +78,7 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tmap, 
 //              thread; completion through an mbarrier per stage.  The LDGSTS form is bound by the SM's load/store
 //              pipe (measured: ~2300 cycles per tile spent behind the next tile's 2048 LDGSTS, none waiting for
 //              data), the tensor form leaves that pipe to the two compute phases.
-template <int K, int TP, int STAGES, int NT, bool TMA>
+template <int K, int TP, int STAGES, int NT, bool TMA, int CPT>
 __global__ void __launch_bounds__(NT, (TP == 32 && STAGES <= 4) ? 2 : 1) disc_fused_kernel(const DiscParams p, const __grid_constant__ CUtensorMap tmap) {
     kernel_begin(TR_DISC);
     static_assert(!TMA || TP == 32, "the tensor-map path uses 128-byte rows");
@@ -150,9 +150,9 @@ __global__ void __launch_bounds__(NT, (TP == 32 && STAGES <= 4) ? 2 : 1) disc_fu
     };
 
     const int g = tid % NG, s = tid / NG;
-    float A[kDiscMaxCPT][K];
+    float A[CPT][K];             // CPT = channels per thread in phase 2 (5: C <= 320, 12: C <= 768)
 #pragma unroll
-    for (int i = 0; i < kDiscMaxCPT; ++i)
+    for (int i = 0; i < CPT; ++i)
 #pragma unroll
         for (int k = 0; k < K; ++k) A[i][k] = 0.f;
     float hinge_sum = 0.f;               // epilogue threads: running sums of their (k, pixel) entries
@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(NT, (TP == 32 && STAGES <= 4) ? 2 : 1) disc_fu
 #pragma unroll
                 for (int k = 0; k < K; ++k) cf[jq][k] = *reinterpret_cast<const float4*>(cfs + k * TP + 4 * (h * JQ + jq));
 #pragma unroll
-            for (int i = 0; i < kDiscMaxCPT; ++i) {
+            for (int i = 0; i < CPT; ++i) {
                 const int c = cp + i * kDiscCols;
                 if (c < p.C) {
                     const float* row = xt + (size_t)c * RS;
@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(NT, (TP == 32 && STAGES <= 4) ? 2 : 1) disc_fu
         float* comb = tiles;                     // [PS][K][C]
         const int cp = tid % kDiscCols, h = tid / kDiscCols;
 #pragma unroll
-        for (int i = 0; i < kDiscMaxCPT; ++i) {
+        for (int i = 0; i < CPT; ++i) {
             const int c = cp + i * kDiscCols;
             if (c < p.C) {
 #pragma unroll
@@ -372,10 +372,12 @@ static int finish_launch_geometry(DiscParams& p, int TP, int occ, int* nparts) {
     return grid;
 }
 
-template <int K, int TP, int STAGES, int NT>
-static int launch_disc_s(DiscParams& p, int* nparts, cudaStream_t st) {
+constexpr int kDiscSmallCPT = 5;   // C <= 320 (the reference's 256 / 305 channels): 5*K accumulators instead of 12*K
+
+template <int K, int TP, int STAGES, int NT, int CPT>
+static int launch_disc_c(DiscParams& p, int* nparts, cudaStream_t st) {
     const size_t smem = disc_smem<K, TP, NT>(p.C, STAGES);
-    auto kern = disc_fused_kernel<K, TP, STAGES, NT, false>;
+    auto kern = disc_fused_kernel<K, TP, STAGES, NT, false, CPT>;
     CLR_RETURN_IF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     CLR_RETURN_IF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem));
@@ -385,6 +387,11 @@ static int launch_disc_s(DiscParams& p, int* nparts, cudaStream_t st) {
     CUtensorMap unused{};
     clr::launch_k(kern, grid, NT, smem, st, p, unused);
     return launch_status();
+}
+template <int K, int TP, int STAGES, int NT>
+static int launch_disc_s(DiscParams& p, int* nparts, cudaStream_t st) {
+    return p.C <= kDiscSmallCPT * kDiscCols ? launch_disc_c<K, TP, STAGES, NT, kDiscSmallCPT>(p, nparts, st)
+                                            : launch_disc_c<K, TP, STAGES, NT, kDiscMaxCPT>(p, nparts, st);
 }
 
 // ---- tensor map for xs viewed as (pixel HW, channel C, sample B), box = (32 pixels, rows_box channels, 1 sample) -----
@@ -415,10 +422,10 @@ static bool make_feature_tmap(const float* xs, int B, int C, int HW, int rows_bo
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int K, int STAGES, int NT>
-static int launch_disc_tma_s(DiscParams& p, const CUtensorMap& tmap, int* nparts, cudaStream_t st) {
+template <int K, int STAGES, int NT, int CPT>
+static int launch_disc_tma_c(DiscParams& p, const CUtensorMap& tmap, int* nparts, cudaStream_t st) {
     const size_t smem = disc_smem_tma<K, NT>(p.C, p.rows_box * p.nbox, STAGES);
-    auto kern = disc_fused_kernel<K, 32, STAGES, NT, true>;
+    auto kern = disc_fused_kernel<K, 32, STAGES, NT, true, CPT>;
     CLR_RETURN_IF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     CLR_RETURN_IF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem));
@@ -427,6 +434,11 @@ static int launch_disc_tma_s(DiscParams& p, const CUtensorMap& tmap, int* nparts
     if (grid < 1) return CLR_ERR_UNSUPPORTED;
     clr::launch_k(kern, grid, NT, smem, st, p, tmap);
     return launch_status();
+}
+template <int K, int STAGES, int NT>
+static int launch_disc_tma_s(DiscParams& p, const CUtensorMap& tmap, int* nparts, cudaStream_t st) {
+    return p.C <= kDiscSmallCPT * kDiscCols ? launch_disc_tma_c<K, STAGES, NT, kDiscSmallCPT>(p, tmap, nparts, st)
+                                            : launch_disc_tma_c<K, STAGES, NT, kDiscMaxCPT>(p, tmap, nparts, st);
 }
 
 // Tensor-map path: two CTAs per SM with a 3-stage (else 2-stage) ring; 512-thread CTAs on request when K <= 2.
@@ -441,9 +453,11 @@ static int launch_disc_tma(DiscParams& p, int* nparts, cudaStream_t st) {
     const size_t per_cta = (budget - 2048) / 2;
     const int rt = p.rows_box * p.nbox;
     constexpr bool wide = (K <= 2);
-    if (wide && tunables().disc_threads == 512) {
-        if (disc_smem_tma<K, 512>(p.C, rt, 3) <= per_cta) return launch_disc_tma_s<K, 3, 512>(p, tmap, nparts, st);
-        if (disc_smem_tma<K, 512>(p.C, rt, 2) <= per_cta) return launch_disc_tma_s<K, 2, 512>(p, tmap, nparts, st);
+    if constexpr (wide) {
+        if (tunables().disc_threads == 512) {
+            if (disc_smem_tma<K, 512>(p.C, rt, 3) <= per_cta) return launch_disc_tma_s<K, 3, 512>(p, tmap, nparts, st);
+            if (disc_smem_tma<K, 512>(p.C, rt, 2) <= per_cta) return launch_disc_tma_s<K, 2, 512>(p, tmap, nparts, st);
+        }
     }
     if (disc_smem_tma<K, 256>(p.C, rt, 3) <= per_cta) return launch_disc_tma_s<K, 3, 256>(p, tmap, nparts, st);
     if (disc_smem_tma<K, 256>(p.C, rt, 2) <= per_cta) return launch_disc_tma_s<K, 2, 256>(p, tmap, nparts, st);
@@ -458,9 +472,11 @@ static int launch_disc(DiscParams& p, int* nparts, cudaStream_t st) {
     const size_t per_cta = (TP == 32) ? (budget - 2048) / 2 : budget;
     // 512-thread CTAs (32 warps per SM at two CTAs) when the accumulators fit the 64-register budget
     constexpr bool wide = (K <= 2);
-    if (tunables().disc_threads == 512 && wide) {
-        if (disc_smem<K, TP, 512>(p.C, 3) <= per_cta) return launch_disc_s<K, TP, 3, 512>(p, nparts, st);
-        if (disc_smem<K, TP, 512>(p.C, 2) <= budget) return launch_disc_s<K, TP, 2, 512>(p, nparts, st);
+    if constexpr (wide) {
+        if (tunables().disc_threads == 512) {
+            if (disc_smem<K, TP, 512>(p.C, 3) <= per_cta) return launch_disc_s<K, TP, 3, 512>(p, nparts, st);
+            if (disc_smem<K, TP, 512>(p.C, 2) <= budget) return launch_disc_s<K, TP, 2, 512>(p, nparts, st);
+        }
     }
     if (disc_smem<K, TP, 256>(p.C, 4) <= per_cta) return launch_disc_s<K, TP, 4, 256>(p, nparts, st);
     if (disc_smem<K, TP, 256>(p.C, 3) <= per_cta) return launch_disc_s<K, TP, 3, 256>(p, nparts, st);
