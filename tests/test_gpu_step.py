@@ -384,6 +384,46 @@ def test_fused_step_vs_eager_port_on_gpu():
         assert bad.mean() < 1e-4, bad.mean()
 
 
+@pytest.mark.parametrize("Bs,Bt,C,H,W,K,up,T", [(3, 2, 37, 24, 40, 3, 2, 5),      # unequal batches, odd C, H != W, up 2, odd T
+                                                (2, 2, 19, 7, 9, 2, 4, 3),         # ragged planes (HW % 4 != 0): scalar paths
+                                                (1, 3, 305, 16, 16, 1, 4, 8),      # one class, the real decoder's 305 channels
+                                                (2, 2, 320, 32, 32, 4, 3, 8),      # up 3, K = 4
+                                                (2, 1, 321, 16, 32, 2, 4, 2)])     # C just past the small-CPT kernels, T = 2
+def test_fused_step_odd_shapes_vs_eager_port(Bs, Bt, C, H, W, K, up, T):
+    """Generality of the fused step (every kernel's fallback paths) against the eager port on the same GPU."""
+    g = torch.Generator().manual_seed(7 * C + H)
+    ys = synth.nested_ellipse_labels(Bs, K, H, W, g)
+    yt = synth.nested_ellipse_labels(Bt, K, H, W, g)
+    xs = synth.class_shifted_features(ys, C, g)
+    xt = synth.class_shifted_features(yt, C, g)
+    oTb = synth.confident_logits(yt, g)
+    base = torch.nn.functional.interpolate(oTb, scale_factor=up, mode="nearest")
+    preds = base.repeat(T, 1, 1, 1) + 0.3 * torch.randn(T * Bt, K, H * up, W * up, generator=g)
+    oT = base + 0.1 * torch.randn(Bt, K, H * up, W * up, generator=g)
+    oTa = base + 0.5 * torch.randn(Bt, K, H * up, W * up, generator=g)
+    t = {k: v.to(DEV) for k, v in dict(xs=xs, ys=ys, xt=xt, oT_before=oTb, preds=preds, oT=oT, oT_aug=oTa).items()}
+    ours = clr.CLRStep(K=K, retrify=True, use_disc=True, use_cons=True, backprop_aug=True)
+    port = TP.ClrStepPort(retrify=True, use_disc=True, use_cons=True, backprop_aug=True)
+    for it in range(2):
+        xs1, xt1, a1 = (t[k].clone().requires_grad_(True) for k in ("xs", "xt", "oT_aug"))
+        xs2, xt2, a2 = (t[k].clone().requires_grad_(True) for k in ("xs", "xt", "oT_aug"))
+        out = ours(xs1, t["ys"], xt1, oT_before=t["oT_before"], preds=t["preds"], T=T, oT=t["oT"], oT_aug=a1, epoch=1.0)
+        out.total.backward()
+        res = port.step(xs2, t["ys"], xt2, t["oT_before"], preds=t["preds"], features=None, T=T, oT=t["oT"], oT_aug=a2, epoch=1.0)
+        masks_ref = torch.cat([m for m in res.get("masks", [])], 1) if "masks" in res else None
+        if not all(np.isfinite(float(res[k])) for k in ("intra", "disc", "aug", "total")):
+            pytest.skip("degenerate synthetic case (empty class) in the eager reference")
+        for k in ("intra", "disc", "aug", "total"):
+            assert abs(float(getattr(out, k)) - float(res[k])) < TOL_LOSS * max(abs(float(res[k])), 1e-12), k
+        assert relerr(stack(out.source_prototypes), stack(res["Ps"])) < TOL_PROTO
+        assert relerr(stack(out.target_prototypes), stack(res["Pt"])) < TOL_PROTO
+        assert relerr(xt1.grad.cpu().numpy(), xt2.grad.cpu().numpy()) < TOL_GRAD
+        assert relerr(a1.grad.cpu().numpy(), a2.grad.cpu().numpy()) < TOL_GRAD
+        g1, g2 = xs1.grad.cpu().numpy(), xs2.grad.cpu().numpy()
+        bad = np.abs(g1 - g2) > TOL_GRAD * np.abs(g2).max()
+        assert bad.mean() < 1e-3, bad.mean()
+
+
 # ------------------------------------------------------------------------------------------------ A9 kernels
 @pytest.mark.parametrize("B,C,H,W,K", [(2, 24, 32, 32, 2), (1, 305, 32, 48, 2), (2, 40, 16, 16, 3), (1, 600, 16, 16, 2),
                                        (2, 33, 10, 10, 2), (2, 256, 64, 64, 2), (3, 37, 6, 10, 4), (1, 64, 4, 4, 8)])
