@@ -141,3 +141,34 @@ def test_both_pooling_kernels_agree_with_oracle(impl, shape):
         lib.clr_set_tunable(b"pool_impl", 0)
     assert np.array_equal(sums[:, C].astype(np.float64), N)
     assert relerr(sums[:, :C], S) < TOL_PROTO
+
+
+def test_two_to_the_31_elements_feature_map():
+    """The sweep corner B=64, C=512, 256x256 is exactly 2^31 floats (8.6 GB): int32 element offsets overflow there.
+    Size-independent checks: exact counts, shard-and-sum == whole, and the adjoint at the far end of the address space."""
+    free, _ = torch.cuda.mem_get_info()
+    if free < 30 * 2 ** 30:
+        pytest.skip("needs ~26 GB of free device memory")
+    B, C, H, W, K = 64, 512, 256, 256, 2
+    g = torch.Generator().manual_seed(5)
+    y = synth.nested_ellipse_labels(B, K, H, W, g).to(DEV)
+    x = torch.randn(B, C, H, W, device=DEV)
+    assert x.numel() == 2 ** 31
+    whole = clr.ops.pool_sums(x, y, 0, K).double()
+    halves = sum(clr.ops.pool_sums(x[i:i + 32], y[i:i + 32].contiguous(), 0, K).double() for i in (0, 32))
+    assert torch.equal(halves[:, C], whole[:, C])                        # counts exact
+    assert float(whole[0, C] + whole[K, C]) == B * H * W                 # obj + bck = all pixels (< 2^24: exact in fp32)
+    assert float(whole[0, C]) == float(y[:, 0].sum())
+    assert relerr(halves.cpu().numpy(), whole.cpu().numpy()) < 1e-6
+    # last sample, last channels: direct fp64 evaluation of S_r[c] for a probe
+    probe = torch.stack([(x[:, C - 1].double() * y[:, k].double()).sum() for k in range(K)])
+    assert relerr(whole[:K, C - 1].cpu().numpy(), probe.cpu().numpy()) < 1e-5
+    # adjoint: grad[b, c, p] = sum_r g[r][c] / N_r * w_r[b, p]; check the very last plane
+    gmat = torch.randn(2 * K, C, device=DEV)
+    grad = clr.ops.pool_backward_feat(y, 0, K, (B, C, H, W), gmat, whole.float(), 1.0)
+    N = whole[:, C]
+    wlast = torch.cat([y[B - 1], 1.0 - y[B - 1]], 0).double()            # [2K, H, W] complement rows
+    ref = torch.einsum("r,rhw->hw", (gmat[:, C - 1].double() / N), wlast)
+    assert relerr(grad[B - 1, C - 1].cpu().numpy(), ref.cpu().numpy()) < TOL_GRAD
+    del x, grad
+    torch.cuda.empty_cache()
