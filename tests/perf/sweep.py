@@ -84,7 +84,7 @@ def main():
     a = ap.parse_args()
     pts = [(8, 256, 128, 2), (8, 305, 128, 2), (8, 512, 128, 2), (8, 256, 64, 2), (16, 256, 128, 2), (32, 256, 128, 2),
            (8, 256, 128, 4), (8, 256, 128, 8), (8, 256, 256, 2), (4, 305, 256, 2), (16, 512, 64, 4), (64, 256, 64, 2),
-           (64, 256, 128, 2), (16, 512, 256, 2)]
+           (64, 256, 128, 2), (16, 512, 256, 2), (64, 512, 256, 2)]
     if a.quick:
         pts = pts[:5]
     out = []
@@ -92,7 +92,7 @@ def main():
         T, up = 8, 4
         feat_gb = 4 * B * C * H * H / 1e9
         check = feat_gb <= 0.6          # the eager port materialises ~8 feature-map-sized temporaries
-        steps = 200 if feat_gb < 0.3 else (60 if feat_gb < 1.5 else 20)
+        steps = 200 if feat_gb < 0.3 else (60 if feat_gb < 1.5 else (20 if feat_gb < 4 else 4))
         try:
             r = run_point(B, C, H, K, T, up, steps, check)
         except Exception as e:          # keep sweeping; report the failure
