@@ -111,3 +111,23 @@ def test_step_args_layout_matches_header():
             if m:
                 names.append(m.group(1))
     assert names == [f[0] for f in _lib.StepArgs._fields_]
+
+
+def test_header_is_plain_c99_and_c_host_links(lib, tmp_path):
+    """The boundary is a C ABI: the header must compile as C (not only C++), and a C host must link against the
+    library with nothing but cudart (examples/clr_host.c; it is RUN in tests/test_gpu_parity.py)."""
+    import shutil
+    import subprocess
+    from uda_clr_b200 import _lib
+    if not shutil.which("gcc"):
+        pytest.skip("gcc not available")
+    r = subprocess.run(["gcc", "-std=c99", "-fsyntax-only", "-x", "c", "-Wall", "-Wpedantic", HEADER], capture_output=True, text=True)
+    assert r.returncode == 0 and not r.stderr.strip(), r.stderr
+    cuda_inc, cuda_lib = "/usr/local/cuda/include", "/usr/local/cuda/lib64"
+    if not os.path.isdir(cuda_inc):
+        pytest.skip("CUDA toolkit headers not found")
+    exe = str(tmp_path / "clr_host")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-I", os.path.join(ROOT, "include"), "-I", cuda_inc,
+                        os.path.join(ROOT, "examples", "clr_host.c"), "-o", exe, "-L", os.path.dirname(_lib.LIB_PATH),
+                        "-lclr_b200", "-L", cuda_lib, "-lcudart", "-lm"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr

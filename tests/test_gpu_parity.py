@@ -172,3 +172,23 @@ def test_two_to_the_31_elements_feature_map():
     assert relerr(grad[B - 1, C - 1].cpu().numpy(), ref.cpu().numpy()) < TOL_GRAD
     del x, grad
     torch.cuda.empty_cache()
+
+
+def test_plain_c_host_runs_against_the_library(tmp_path):
+    """examples/clr_host.c: a C99 program that links libclr_b200.so + cudart only, runs pooling / prototypes / the
+    adjoint through the C ABI and checks them against a closed form in double on the host."""
+    import os
+    import shutil
+    import subprocess
+    from uda_clr_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not shutil.which("gcc") or not os.path.isdir("/usr/local/cuda/include"):
+        pytest.skip("gcc / CUDA toolkit not available")
+    exe = str(tmp_path / "clr_host")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    r = subprocess.run(["gcc", "-std=c99", "-I", os.path.join(root, "include"), "-I", "/usr/local/cuda/include",
+                        os.path.join(root, "examples", "clr_host.c"), "-o", exe, "-L", libdir, "-lclr_b200",
+                        "-L", "/usr/local/cuda/lib64", "-lcudart", "-lm", "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "clr_host ok" in r.stdout, r.stdout + r.stderr
