@@ -34,18 +34,25 @@ def main():
     ap.add_argument("--tunable", action="append", default=[])
     ap.add_argument("--json", default=None)
     a = ap.parse_args()
-    dev = torch.device("cuda", 0)
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:       # under torchrun: sharded step with the in-kernel exchange; rank 0 prints its own timeline
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+        clr.dist.enable_peer()
     lib = _lib.load()
     for kv in a.tunable:
         name, val = kv.split("=")
         _lib.check(lib.clr_set_tunable(name.encode(), int(val)), "clr_set_tunable(%s)" % kv)
     use3 = a.workload == "clr3"
     NSET = 2
-    host = [synth.make_batch(B=a.B, C=a.C, H=a.H, W=a.H, K=a.K, T=a.T, up=a.up, seed=1234 + s, image_res=use3)
+    host = [synth.make_batch(B=a.B, C=a.C, H=a.H, W=a.H, K=a.K, T=a.T, up=a.up, seed=1234 + s + 17 * rank, image_res=use3)
             for s in range(NSET)]
     names = ["xs", "ys", "xt", "oT_before"] + (["preds", "oT", "oT_aug"] if use3 else [])
     devb = [{k: getattr(h, k).to(dev) for k in names} for h in host]
-    step = clr.CLRStep(K=a.K, retrify=use3, use_disc=use3, use_cons=use3, backprop_aug=False, global_batch=a.B)
+    step = clr.CLRStep(K=a.K, retrify=use3, use_disc=use3, use_cons=use3, backprop_aug=False, global_batch=a.B * world)
     plans = []
     for d in devb:
         if use3:
@@ -76,12 +83,16 @@ def main():
             if ncta == 0:
                 continue
             if t_first == 0:      # per-phase cycle counters (builds with CLR_NVCC_EXTRA=-DCLR_PHASE_PROFILE)
-                print("  %-18s %d cycles" % (slot_names[i], t_last))
+                if rank == 0:
+                    print("  %-18s %d cycles" % (slot_names[i], t_last))
                 continue
             rows.append((slot_names[i], t_first, t_ready, t_last, ncta))
         t0 = min(r[1] for r in rows)
         rows.sort(key=lambda r: r[2])
-        print("step %d (%s): kernel, first CTA start, predecessor done, last CTA exit, busy, CTAs [us]" % (s, a.workload))
+        if rank != 0:
+            continue
+        print("step %d (%s, %d GPU%s): kernel, first CTA start, predecessor done, last CTA exit, busy, CTAs [us]"
+              % (s, a.workload, world, "s" if world > 1 else ""))
         prev_end = None
         for name, tf, tr, tl, ncta in rows:
             gap = "" if prev_end is None else "  gap_after_prev %+6.2f" % ((tr - prev_end) / 1e3)
@@ -94,7 +105,10 @@ def main():
                     "kernels": [{"name": r[0], "start_us": (r[1] - t0) / 1e3, "ready_us": (r[2] - t0) / 1e3,
                                  "exit_us": (r[3] - t0) / 1e3, "ctas": int(r[4])} for r in rows]})
     _lib.check(lib.clr_trace_enable(0), "clr_trace_enable")
-    if a.json:
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+    if a.json and rank == 0:
         with open(a.json, "w") as fh:
             json.dump({"config": vars(a), "steps": out}, fh, indent=1)
 

@@ -38,6 +38,9 @@ struct Tunables {
     int hfuse_off;     // 1 = finish bodies get launches of their own instead of riding with cons / the target-gradient write
     int mc_fuse;       // 1 = the fused step uses the one-pass mc_retrify kernel instead of mc_stats + retrify_weights
     int mc_split;      // 1 = one-pass mc_retrify kernel splits image rows into column blocks (more, smaller CTAs)
+    int flag_dep_off;  // 1 = the discriminative kernel waits for the whole [finish | consistency] grid (griddepcontrol.wait)
+                       //     instead of the finish CTAs' completion counter
+    int xchg_pull;     // in-kernel exchange: 1 = readers poll the peers' buffers (no remote stores), 0 = senders push
     void* trace_buf;   // device TraceRec[kTraceSlots] or NULL (clr_trace_set): device-side timeline of the kernels
     int bwd_trace_id;  // trace slot of the next pool_bwd launch (set by the step orchestration)
 };
@@ -87,6 +90,32 @@ __device__ __forceinline__ void trace_mark(int id) {
     if (t && trace_leader()) { const unsigned long long now = global_ns(); atomicMin(&t[id].t_first, now); atomicMin(&t[id].t_ready, now);
                                atomicMax(&t[id].t_last, now); atomicAdd(&t[id].n_cta, 1ull); }
 }
+// ---- flag dependencies (finer than grid completion) ---------------------------------------------------------------
+// A kernel whose consumer needs only what a FEW of its CTAs produce (the finish CTAs riding in front of a streaming
+// launch) publishes a counter: every thread fences, the CTA synchronises, one thread increments.  The consumer skips
+// griddepcontrol.wait, spins on the counter with one thread, and from then on reads the produced data through
+// coherent loads only.  This removes the grid-completion latency -- notably the system-scope flush a grid pays at
+// its end once it has touched peer memory (the in-kernel exchange) -- from the step's critical path.
+__device__ __forceinline__ void cta_signal(unsigned int* counter_a, unsigned int* counter_b) {
+    __threadfence();
+    __syncthreads();
+    if (trace_leader()) {
+        if (counter_a) atomicAdd(counter_a, 1u);
+        if (counter_b) atomicAdd(counter_b, 1u);
+    }
+}
+// one thread: returns false on timeout (~2 s)
+__device__ __forceinline__ bool spin_until_at_least(const unsigned int* counter, unsigned int expected) {
+    const volatile unsigned int* c = counter;
+    if (*c < expected) {
+        const long long t0 = clock64();
+        while (*c < expected)
+            if (clock64() - t0 > 4000000000LL) return false;
+    }
+    __threadfence();
+    return true;
+}
+
 // kernel prologue: stamp; let the NEXT kernel of the stream start launching right away (its CTAs become resident as
 // ours retire and park in their own griddepcontrol.wait, so launch latency and CTA ramp-up leave the critical path --
 // the wait still blocks until this whole grid has completed and flushed, so ordering is unchanged); wait for the

@@ -65,22 +65,26 @@ struct PeerXchg {
     int world, rank;
     unsigned int seq;
     int n;                                   // words per source
+    int pull;                                // 0: senders store into every peer's buffer, readers poll locally (push)
+                                             // 1: senders store locally, readers poll the peers' buffers over NVLink (pull)
     float* err;                              // set to 1 on timeout (losses[7])
 };
 __device__ __forceinline__ void xchg_push(const PeerXchg& x, int idx, float v) {
     const unsigned long long w = ((unsigned long long)x.seq << 32) | (unsigned long long)__float_as_uint(v);
     const size_t off = ((size_t)(x.seq & 1u) * x.world + x.rank) * x.n + idx;
+    if (x.pull) { *reinterpret_cast<volatile unsigned long long*>(x.rx[x.rank] + off) = w; return; }
     for (int q = 0; q < x.world; ++q) *reinterpret_cast<volatile unsigned long long*>(x.rx[q] + off) = w;
 }
 __device__ __forceinline__ float xchg_pull_sum(const PeerXchg& x, int idx) {
-    const volatile unsigned long long* base = x.rx[x.rank] + (size_t)(x.seq & 1u) * x.world * x.n + idx;
     double s = 0.0;
     for (int q = 0; q < x.world; ++q) {
-        unsigned long long w = base[(size_t)q * x.n];
+        // slot [parity][source q] of rank q's own buffer (pull) or of the local buffer (push)
+        const volatile unsigned long long* src = x.rx[x.pull ? q : x.rank] + ((size_t)(x.seq & 1u) * x.world + q) * x.n + idx;
+        unsigned long long w = *src;
         if ((unsigned int)(w >> 32) != x.seq) {
             const long long t0 = clock64();
             do {
-                w = base[(size_t)q * x.n];
+                w = *src;
                 if (clock64() - t0 > 4000000000LL) { if (x.err) *x.err = 1.f; break; }     // ~2 s: a peer is gone
             } while ((unsigned int)(w >> 32) != x.seq);
         }
@@ -112,6 +116,8 @@ struct PoolFinishParams {
     double* loss_partial;      // [ctas][2 + CLR_MAX_K]
     unsigned int* counter;
     PeerXchg x;                // world > 1: sum the packed sums over the ranks before the finalize arithmetic
+    unsigned int* done_fin;    // optional completion counters (cta_signal): finish CTAs only / every CTA of the launch
+    unsigned int* done_all;
 };
 static inline int pool_finish_ctas(int C) { return (C + 7) / 8; }
 

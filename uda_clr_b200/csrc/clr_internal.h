@@ -16,9 +16,15 @@ size_t pool_partial_bytes(int B, int C, int HW, int R);
 void launch_partial_reduce(const float* partial, int slots, int R, int C, float* sums, cudaStream_t st);
 
 // One-read discriminative forward (disc_fused.cu); CLR_ERR_UNSUPPORTED -> use the two-pass form.
+struct DiscFlagDep {   // flag dependency on the preceding [finish | consistency] launch (clr_common.cuh), or NULL
+    const unsigned int* wait_fin; const unsigned int* wait_all;
+    unsigned int wait_fin_n, wait_all_n;
+    float* err;
+};
 int disc_fused_impl(const float* xs, const float* ys, int B, int C, int HW, int K,
                     const float* disc_vec, const float* disc_beta, float margin,
-                    float* coef, float* delta, float* partial, float* hinge, int* nparts, cudaStream_t st);
+                    float* coef, float* delta, float* partial, float* hinge, int* nparts, cudaStream_t st,
+                    const DiscFlagDep* dep = nullptr);
 
 int disc_fwd_impl(const float* xs, const float* ys, int B, int C, int HW, int K,
                   const float* disc_vec, const float* disc_beta, float margin,

@@ -195,10 +195,12 @@ __global__ void __launch_bounds__(kConsThreads, 3) pool_finish_cons_kernel(const
     if ((int)blockIdx.x < n_fin) {
         kernel_begin(TR_ALIGN);
         pool_finish_body(f, blockIdx.x, n_fin);
+        if (f.done_fin) cta_signal(f.done_fin, f.done_all);
         trace_exit(TR_ALIGN);
     } else {
         kernel_begin(TR_CONS);
         cons_body<VEC, false>(a, blockIdx.x - n_fin, gridDim.x - n_fin);
+        if (f.done_all) cta_signal(nullptr, f.done_all);
         trace_exit(TR_CONS);
     }
 }

@@ -50,6 +50,11 @@ struct DiscParams {
     float alpha, margin;
     int B, C, HW, tilesPerSample, total, stages;
     int rows_box, nbox;     // TMA path: the [C x 32] tile is fetched as nbox boxes of rows_box channel rows (rows_box % 8 == 0)
+    // flag dependency (clr_common.cuh): instead of griddepcontrol.wait on the whole producer grid, wait until `wait_fin`
+    // reaches wait_fin_n before the first read of V / beta, and until `wait_all` reaches wait_all_n before exiting
+    const unsigned int* wait_fin; const unsigned int* wait_all;
+    unsigned int wait_fin_n, wait_all_n;
+    float* err;             // set to 1 if a wait times out
 };
 
 constexpr int kDiscPad = 4;
@@ -80,7 +85,10 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tmap, 
 //              data), the tensor form leaves that pipe to the two compute phases.
 template <int K, int TP, int STAGES, int NT, bool TMA, int CPT>
 __global__ void __launch_bounds__(NT, (TP == 32 && STAGES <= 4) ? 2 : 1) disc_fused_kernel(const DiscParams p, const __grid_constant__ CUtensorMap tmap) {
-    kernel_begin(TR_DISC);
+    trace_enter(TR_DISC);
+    pdl_trigger();
+    if (!p.wait_fin) pdl_wait();      // else: the feature tiles are inputs -- start fetching, wait for the flag below
+    trace_ready(TR_DISC);
     static_assert(!TMA || TP == 32, "the tensor-map path uses 128-byte rows");
     constexpr int RS = TMA ? TP : TP + kDiscPad; // row stride (floats): dense + swizzled (TMA) or padded (cp.async)
     constexpr int NG = TP / 4;                   // pixel quads (16-byte chunks) per row
@@ -96,6 +104,8 @@ __global__ void __launch_bounds__(NT, (TP == 32 && STAGES <= 4) ? 2 : 1) disc_fu
     float* cfs = red + (size_t)NW * K * TP;                              // [K][TP]
     float* wred = cfs + (size_t)K * TP;                                      // [1 + NE][NW]
     uint64_t* full = reinterpret_cast<uint64_t*>(wred + (1 + NE) * NW + ((1 + NE) * NW & 1));   // [STAGES] (TMA), 8-byte aligned
+    float* Vs = reinterpret_cast<float*>(full + STAGES);                     // [K][C] contraction vectors + [K] offsets
+    float* betas = Vs + (size_t)K * p.C;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (TMA) {
@@ -168,6 +178,16 @@ __global__ void __launch_bounds__(NT, (TP == 32 && STAGES <= 4) ? 2 : 1) disc_fu
         issue(fetched < end ? fb : p.B, ftile, j);
         advance(fb, ftile); fetched += step;
     }
+    // the contraction vectors come from the finish CTAs of the preceding launch: wait for THEM (not for the whole grid),
+    // then stage V / beta in shared memory through coherent loads (they were written while this kernel was resident,
+    // so the non-coherent __ldg path must not be used for them)
+    if (p.wait_fin) {
+        if (tid == 0 && !spin_until_at_least(p.wait_fin, p.wait_fin_n) && p.err) *p.err = 1.f;
+        __syncthreads();
+    }
+    for (int i = tid; i < K * p.C; i += NT) Vs[i] = __ldcg(p.V + i);
+    if (tid < K) betas[tid] = __ldcg(p.beta + tid);
+    __syncthreads();
     int stage = 0;
     uint32_t phase = 0;
     PH_DECL
@@ -203,9 +223,9 @@ __global__ void __launch_bounds__(NT, (TP == 32 && STAGES <= 4) ? 2 : 1) disc_fu
 #pragma unroll 4
         for (int c = s; c < p.C; c += NS) {
             const float4 x = *reinterpret_cast<const float4*>(xt + (size_t)c * RS + chunk_off(c, g));
-            float vv[K];   // D_k[c]: 4 KB table, read through L1 (saves the shared-memory copy: a third stage fits)
+            float vv[K];   // D_k[c] from the shared-memory copy
 #pragma unroll
-            for (int k = 0; k < K; ++k) vv[k] = __ldg(p.V + (size_t)k * p.C + c);
+            for (int k = 0; k < K; ++k) vv[k] = Vs[(size_t)k * p.C + c];
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 const float vk = vv[k];
@@ -243,7 +263,7 @@ __global__ void __launch_bounds__(NT, (TP == 32 && STAGES <= 4) ? 2 : 1) disc_fu
             float cf = 0.f;
             if (j < npx) {
                 const size_t o = ((size_t)b * K + k) * p.HW + px0 + j;
-                const float delta = fmaf(p.alpha, dot, __ldg(p.beta + k));
+                const float delta = fmaf(p.alpha, dot, betas[k]);
                 const float ho = delta + p.margin, hb = p.margin - delta;
                 hinge_sum += yv[ei] * fmaxf(ho, 0.f) + (1.f - yv[ei]) * fmaxf(hb, 0.f);
                 cf = (ho > 0.f ? yv[ei] : 0.f) - (hb > 0.f ? (1.f - yv[ei]) : 0.f);
@@ -338,6 +358,9 @@ __global__ void __launch_bounds__(NT, (TP == 32 && STAGES <= 4) ? 2 : 1) disc_fu
                 if ((ei * NT + w * 32) / TP == tid) t += wred[(1 + ei) * NW + w];
         out[(size_t)tid * (p.C + 1) + p.C] = t;
     }
+    // completing this grid must imply that the WHOLE producer launch is complete (its streaming CTAs too): the next
+    // kernel's griddepcontrol.wait only covers this grid
+    if (p.wait_all && tid == 0 && !spin_until_at_least(p.wait_all, p.wait_all_n) && p.err) *p.err = 1.f;
     trace_exit(TR_DISC);
 }
 
@@ -347,7 +370,7 @@ static size_t disc_smem(int C, int stages) {
     size_t fl = (size_t)stages * C * RS + (size_t)NW * K * TP + (size_t)K * TP + (1 + NE) * NW;
     const size_t comb = (size_t)(NT / kDiscCols) * K * C;     // end-of-kernel combine buffer aliases the tile ring
     if (comb > (size_t)stages * C * RS) fl += comb - (size_t)stages * C * RS;
-    return fl * sizeof(float) + 16;
+    return (fl + (size_t)K * C + K + 2) * sizeof(float) + 16 + sizeof(uint64_t) * 8;
 }
 
 // tensor-map path: dense 128-byte rows (rows_total >= C, a multiple of 8), one mbarrier per stage
@@ -357,7 +380,7 @@ static size_t disc_smem_tma(int C, int rows_total, int stages) {
     size_t fl = (size_t)stages * rows_total * TP + (size_t)NW * K * TP + (size_t)K * TP + (1 + NE) * NW + 2;
     const size_t comb = (size_t)(NT / kDiscCols) * K * C;
     if (comb > (size_t)stages * rows_total * TP) fl += comb - (size_t)stages * rows_total * TP;
-    return fl * sizeof(float) + sizeof(uint64_t) * stages;
+    return (fl + (size_t)K * C + K + 2) * sizeof(float) + sizeof(uint64_t) * stages;
 }
 
 static int finish_launch_geometry(DiscParams& p, int TP, int occ, int* nparts) {
@@ -517,7 +540,8 @@ static int dispatch_disc_k(int K, DiscParams& p, int* nparts, cudaStream_t st) {
 // friendly; the caller then falls back to the two-pass form (clr_disc_fwd + clr_pool_rows_fwd).
 int disc_fused_impl(const float* xs, const float* ys, int B, int C, int HW, int K,
                     const float* disc_vec, const float* disc_beta, float margin,
-                    float* coef, float* delta, float* partial, float* hinge, int* nparts, cudaStream_t st) {
+                    float* coef, float* delta, float* partial, float* hinge, int* nparts, cudaStream_t st,
+                    const DiscFlagDep* dep) {
     CLR_CHECK_ARG(xs && ys && disc_vec && disc_beta && coef && partial && hinge && nparts && *nparts > 0);
     CLR_CHECK_ARG(B > 0 && C > 0 && HW > 0 && K >= 1 && K <= CLR_MAX_K);
     if (HW % 4 != 0 || !aligned16(xs) || C > kDiscMaxCPT * kDiscCols) return CLR_ERR_UNSUPPORTED;
@@ -526,6 +550,7 @@ int disc_fused_impl(const float* xs, const float* ys, int B, int C, int HW, int 
     p.xs = xs; p.ys = ys; p.V = disc_vec; p.beta = disc_beta; p.coef = coef; p.delta = delta;
     p.partial = partial; p.hinge = hinge; p.alpha = -2.0f / (float)C; p.margin = margin;
     p.B = B; p.C = C; p.HW = HW;
+    if (dep) { p.wait_fin = dep->wait_fin; p.wait_all = dep->wait_all; p.wait_fin_n = dep->wait_fin_n; p.wait_all_n = dep->wait_all_n; p.err = dep->err; }
     // "disc_tile" tunable: 0 auto (32-pixel tiles, two CTAs per SM), 64 = 64-pixel tiles, one CTA per SM
     int n = *nparts;
     int rc = CLR_ERR_UNSUPPORTED;

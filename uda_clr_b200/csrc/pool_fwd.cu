@@ -49,7 +49,7 @@ struct PoolParams {
     int stages;       // TMA ring depth
     int reduce_trace_id;
     int skip_reduce;               // 1: the caller reduces the partials itself (pool_finish_kernel)
-    unsigned int* counter_reset;   // optional: zeroed by CTA 0 (arms the finish kernel's last-CTA counter)
+    unsigned int* counter_reset;   // optional: 4 words zeroed by CTA 0 (the finish stage's last-CTA and completion counters)
 };
 
 // Register blocking: a thread keeps CG x R accumulators -- 32 of them up to R = 8, 64 beyond (R = 16 would otherwise
@@ -186,7 +186,7 @@ __device__ __forceinline__ void reduce_and_store(float (&acc)[pool_nacc(R)], con
 template <int R, int VEC>
 __global__ void __launch_bounds__(kThreads, 2) pool_fwd_ldg_kernel(const PoolParams p) {
     kernel_begin(TR_POOL);
-    if (p.counter_reset && blockIdx.x == 0 && threadIdx.x == 0) *p.counter_reset = 0u;
+    if (p.counter_reset && blockIdx.x == 0 && threadIdx.x < 4) p.counter_reset[threadIdx.x] = 0u;   // last-CTA counter + completion counters
     constexpr int CG = pool_cg(R), REPS = pool_reps(R), PX = kThreads * VEC * REPS;
     extern __shared__ __align__(16) float smem[];
     float* wsm = smem;                 // [R][PX]
@@ -258,7 +258,7 @@ struct PoolTmaSmem {
 template <int R>
 __global__ void __launch_bounds__(kPoolTmaThreads, 1) pool_fwd_tma_kernel(const PoolParams p) {
     kernel_begin(TR_POOL);
-    if (p.counter_reset && blockIdx.x == 0 && threadIdx.x == 0) *p.counter_reset = 0u;
+    if (p.counter_reset && blockIdx.x == 0 && threadIdx.x < 4) p.counter_reset[threadIdx.x] = 0u;   // last-CTA counter + completion counters
     using SM = PoolTmaSmem<R>;
     constexpr int CG = SM::CG, REPS = SM::REPS, PX = SM::PX, VEC = 4;
     extern __shared__ __align__(128) unsigned char smem_raw[];

@@ -192,6 +192,7 @@ static PeerXchg make_xchg(const clr_step_args* a, int which) {
     x.rank = a->rank;
     x.seq = a->seq;
     x.err = a->losses + 7;
+    x.pull = tunables().xchg_pull;
     const size_t n1 = xchg_words1(a->K, a->C), n2 = xchg_words2(a->K, a->C);
     x.n = (int)(which == 1 ? n1 : n2);
     const size_t off = which == 1 ? 0 : 2 * (size_t)x.world * n1;
@@ -241,15 +242,22 @@ static int step_fwd_core(const clr_step_args* a, cudaStream_t st, DiscFinishPara
     pf.disc_vec = a->use_disc ? a->disc_vec : nullptr; pf.disc_beta = a->use_disc ? a->disc_beta : nullptr;
     pf.losses = a->losses; pf.loss_partial = w.fin; pf.counter = counter;
     pf.x = make_xchg(a, 1);
+    // completion counters right behind the last-CTA counter (all three zeroed by the pooling kernel): the discriminative
+    // kernel waits for the finish CTAs only, not for the grid (and its end-of-grid flush) they ride in
+    const bool flag_dep = a->use_disc && tunables().disc_impl != 1 && !tunables().flag_dep_off;
+    if (flag_dep) { pf.done_fin = counter + 1; pf.done_all = counter + 2; }
     int n_cons = 0;
     if (a->use_cons) {
         rc = cons_fwd_partials(a->oT, a->oT_aug, a->masks, a->B_t, K, a->Hi, a->Wi, a->H, a->W,
                                a->cons_threshold, w.cons, &n_cons, st, tunables().hfuse_off ? nullptr : &pf);
         if (rc != CLR_OK) return rc;
     }
+    unsigned int producers = (unsigned int)pool_finish_ctas(C);      // CTAs that signal done_all
     if (!a->use_cons || tunables().hfuse_off) {
         rc = pool_finish_launch(pf, st);     // (stream order: after the consistency launch is fine, they are independent)
         if (rc != CLR_OK) return rc;
+    } else {
+        producers += (unsigned int)n_cons;
     }
     const float ema = a->first_s ? 1.0f : (float)a->decay;
     const double* cons = a->use_cons ? w.cons : nullptr;
@@ -257,8 +265,11 @@ static int step_fwd_core(const clr_step_args* a, cudaStream_t st, DiscFinishPara
         float* partial = reinterpret_cast<float*>(w.rows);
         float* hinge = partial + (size_t)320 * K * (C + 1);   // layout of clr_disc_fused_ws_bytes: [320][K][C+1] | [320]
         int n_hinge = 320;
+        // (a separate consistency launch sits between the finish launch and this kernel when hfuse_off: plain wait then)
+        DiscFlagDep dep{counter + 1, counter + 2, (unsigned int)pool_finish_ctas(C), producers, a->losses + 7};
+        const bool use_dep = flag_dep && !(a->use_cons && tunables().hfuse_off);
         rc = disc_fused_impl(a->xs, a->ys, a->B_s, C, HW, K, a->disc_vec, a->disc_beta, a->margin,
-                             a->disc_coef, nullptr, partial, hinge, &n_hinge, st);
+                             a->disc_coef, nullptr, partial, hinge, &n_hinge, st, use_dep ? &dep : nullptr);
         if (rc == CLR_OK) {
             DiscFinishParams df{};
             df.partial = partial; df.slots = n_hinge; df.packed2 = a->packed2; df.P_s = a->P_s; df.g_s = a->g_s;
