@@ -118,6 +118,7 @@ struct PoolFinishParams {
     PeerXchg x;                // world > 1: sum the packed sums over the ranks before the finalize arithmetic
     unsigned int* done_fin;    // optional completion counters (cta_signal): finish CTAs only / every CTA of the launch
     unsigned int* done_all;
+    int write_total;           // alignment-only step (no discriminative / consistency term): the last CTA also writes the totals
 };
 static inline int pool_finish_ctas(int C) { return (C + 7) / 8; }
 
@@ -230,6 +231,15 @@ __device__ __forceinline__ void pool_finish_body(const PoolFinishParams& p, cons
                 const float val = (float)(t * (1.0 / (double)C));
                 if (i < 2) p.losses[i] = val;
                 else if (p.disc_beta) p.disc_beta[i - 2] = val;
+            }
+        }
+        if (p.write_total) {
+            __syncthreads();       // (is_last is CTA-uniform) losses[0..1] written above by lanes 0 of warps 0 / 1
+            if (tid == 0) {
+                p.losses[2] = 0.f; p.losses[3] = 0.f;
+                p.losses[4] = p.w_intra * p.losses[0] + p.w_inter * p.losses[1];
+                p.losses[5] = 0.f; p.losses[6] = 0.f;
+                if (p.x.world <= 1) p.losses[7] = 0.f;
             }
         }
         if (tid == 0) *p.counter = 0u;

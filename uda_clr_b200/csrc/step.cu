@@ -246,6 +246,8 @@ static int step_fwd_core(const clr_step_args* a, cudaStream_t st, DiscFinishPara
     // kernel waits for the finish CTAs only, not for the grid (and its end-of-grid flush) they ride in
     const bool flag_dep = a->use_disc && tunables().disc_impl != 1 && !tunables().flag_dep_off;
     if (flag_dep) { pf.done_fin = counter + 1; pf.done_all = counter + 2; }
+    const bool align_only = !a->use_disc && !a->use_cons;      // the shipped trainer's step: totals come from the finish itself
+    pf.write_total = align_only ? 1 : 0;
     int n_cons = 0;
     if (a->use_cons) {
         rc = cons_fwd_partials(a->oT, a->oT_aug, a->masks, a->B_t, K, a->Hi, a->Wi, a->H, a->W,
@@ -286,6 +288,7 @@ static int step_fwd_core(const clr_step_args* a, cudaStream_t st, DiscFinishPara
     }
     // the in-kernel exchange of the discriminative / consistency numerators lives in disc_finish_body (one-read path)
     if (a->world > 1 && (a->use_disc || a->use_cons)) return CLR_ERR_UNSUPPORTED;
+    if (align_only) return CLR_OK;
     int n_hinge = 0;
     if (a->use_disc) {
         // two-pass form: per-pixel dots (read 1), then pooling of xs with the coefficient planes (read 2)
