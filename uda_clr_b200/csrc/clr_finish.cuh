@@ -52,6 +52,30 @@ __device__ __forceinline__ double strided_slot_sum(const float* __restrict__ col
     return s;
 }
 
+// Two strided sums whose loads are issued TOGETHER (one L2 round trip instead of two dependent ones): a over
+// col_a[(sa + i*step_a) * stride], b over col_b[(sb + i*step_b) * stride], slots below s_end; fp64, slot order.
+template <int UA, int UB>
+__device__ __forceinline__ void strided_slot_sum2(const float* __restrict__ col_a, int sa, int step_a, bool use_a,
+                                                  const float* __restrict__ col_b, int sb, int step_b,
+                                                  int s_end, size_t stride, double& out_a, double& out_b) {
+    double a = 0.0, b = 0.0;
+    while ((use_a && sa < s_end) || sb < s_end) {
+        float va[UA], vb[UB];
+#pragma unroll
+        for (int u = 0; u < UA; ++u) va[u] = (use_a && sa + u * step_a < s_end) ? __ldcg(col_a + (size_t)(sa + u * step_a) * stride) : 0.f;
+#pragma unroll
+        for (int u = 0; u < UB; ++u) vb[u] = (sb + u * step_b < s_end) ? __ldcg(col_b + (size_t)(sb + u * step_b) * stride) : 0.f;
+#pragma unroll
+        for (int u = 0; u < UA; ++u) a += (double)va[u];
+#pragma unroll
+        for (int u = 0; u < UB; ++u) b += (double)vb[u];
+        sa += UA * step_a;
+        sb += UB * step_b;
+    }
+    out_a = a;
+    out_b = b;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // In-kernel exchange of the packed sums between the ranks of one NVLink domain ("LL" style: value and sequence number
 // travel in ONE 64-bit store, so a reader that sees the expected sequence number has the value -- no fences, no
@@ -136,9 +160,9 @@ __device__ __forceinline__ void pool_finish_body(const PoolFinishParams& p, cons
         const int d = pair / R, r = pair - d * R;
         const float* part = p.partial[d];
         const int slots = p.slots[d];
-        double s = 0.0;
-        if (c < C) s = strided_slot_sum<8>(part + (size_t)r * (C + 1) + c, sl0, slots, (size_t)n, 4);
-        double nn = strided_slot_sum<4>(part + (size_t)r * (C + 1) + C, lane, slots, (size_t)n, 32);
+        double s, nn;              // 64 slots: ONE round of loads for the channel column and the weight-sum column
+        strided_slot_sum2<16, 2>(part + (size_t)r * (C + 1) + (c < C ? c : 0), sl0, 4, c < C,
+                                 part + (size_t)r * (C + 1) + C, lane, 32, slots, (size_t)n, s, nn);
         s += __shfl_xor_sync(0xffffffffu, s, 1);
         s += __shfl_xor_sync(0xffffffffu, s, 2);
         nn = warp_sum(nn);
@@ -279,9 +303,9 @@ __device__ __forceinline__ void disc_finish_body(const DiscFinishParams& p, cons
         for (int pair = warp; pair < 4 * K; pair += kWarps) {
             const int k = pair >> 2, q = pair & 3;
             const int s_begin = q * per, s_end = (s_begin + per) < p.slots ? (s_begin + per) : p.slots;
-            double s = 0.0;
-            if (c < C) s = strided_slot_sum<10>(p.partial + (size_t)k * (C + 1) + c, s_begin + sl0, s_end, (size_t)n, 4);
-            double nn = strided_slot_sum<4>(p.partial + (size_t)k * (C + 1) + C, s_begin + lane, s_end, (size_t)n, 32);
+            double s, nn;          // 296 slots / 4 quarters: one round for both columns
+            strided_slot_sum2<20, 3>(p.partial + (size_t)k * (C + 1) + (c < C ? c : 0), s_begin + sl0, 4, c < C,
+                                     p.partial + (size_t)k * (C + 1) + C, s_begin + lane, 32, s_end, (size_t)n, s, nn);
             s += __shfl_xor_sync(0xffffffffu, s, 1);
             s += __shfl_xor_sync(0xffffffffu, s, 2);
             nn = warp_sum(nn);
