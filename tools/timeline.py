@@ -33,6 +33,8 @@ def main():
     ap.add_argument("--workload", default="clr3", choices=["clr3", "align"])
     ap.add_argument("--tunable", action="append", default=[])
     ap.add_argument("--json", default=None)
+    ap.add_argument("--pipelined", type=int, default=0,
+                    help="also enqueue N steps back to back under ONE trace window: (last exit - first start) / N is the steady-state step time on the device")
     a = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -104,6 +106,16 @@ def main():
         out.append({"step": s, "span_us": total,
                     "kernels": [{"name": r[0], "start_us": (r[1] - t0) / 1e3, "ready_us": (r[2] - t0) / 1e3,
                                  "exit_us": (r[3] - t0) / 1e3, "ctas": int(r[4])} for r in rows]})
+    if a.pipelined > 0:
+        for i in range(a.pipelined):
+            plans[i % NSET].run()
+        _lib.check(lib.clr_trace_read(buf), "clr_trace_read")
+        firsts = [buf[4 * i] for i in range(n) if buf[4 * i + 3] and buf[4 * i]]
+        lasts = [buf[4 * i + 2] for i in range(n) if buf[4 * i + 3] and buf[4 * i]]
+        if rank == 0:
+            per_kernel = {slot_names[i]: (buf[4 * i + 2] - buf[4 * i]) / 1e3 for i in range(n) if buf[4 * i + 3] and buf[4 * i]}
+            print("pipelined: %d steps back to back: %.2f us per step (device stamps, first start -> last exit)"
+                  % (a.pipelined, (max(lasts) - min(firsts)) / 1e3 / a.pipelined))
     _lib.check(lib.clr_trace_enable(0), "clr_trace_enable")
     if world > 1:
         torch.distributed.barrier()
