@@ -520,6 +520,15 @@ def test_fused_step_soft_target_gradient_reaches_the_logits():
         assert relerr(o1.grad.cpu().numpy(), o2.grad.cpu().numpy()) < TOL_GRAD
         assert relerr(xt.grad.cpu().numpy(), xt2.grad.cpu().numpy()) < TOL_GRAD
         assert relerr(xs.grad.cpu().numpy(), xs2.grad.cpu().numpy()) < TOL_GRAD
+    # the prebound plan leaves the same quantity in plan.g_wt (here: first step of a fresh state on both sides)
+    wt_t = torch.sigmoid(b.oT_before.to(DEV)).requires_grad_(True)
+    stp = clr.CLRStep(K=K, retrify=False, use_disc=False, use_cons=False)
+    plan = stp.plan(b.xs.to(DEV), b.ys.to(DEV), b.xt.to(DEV), wt=wt_t)
+    plan.run()
+    stq = clr.CLRStep(K=K, retrify=False, use_disc=False, use_cons=False)
+    wt_q = torch.sigmoid(b.oT_before.to(DEV)).requires_grad_(True)
+    stq(b.xs.to(DEV).requires_grad_(True), b.ys.to(DEV), b.xt.to(DEV).requires_grad_(True), wt=wt_q).total.backward()
+    assert plan.g_wt is not None and torch.equal(plan.g_wt, wt_q.grad)
     # oracle (first step of a fresh state): d total / d wt chained through sigmoid' by hand
     step = clr.CLRStep(K=K, retrify=False, use_disc=False, use_cons=False)
     o1 = b.oT_before.to(DEV).requires_grad_(True)

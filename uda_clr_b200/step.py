@@ -309,6 +309,14 @@ class CLRPlan:
         self.device = dev
         self._lib = _lib.load()
         self._ref = ctypes.byref(a)
+        # soft target weights (no retrify) that carry a graph: run() also leaves d total / d wt in ``g_wt`` ([B,K,H,W] for
+        # complement weights), the quantity autograd chains into oT_before in the __call__ path
+        self.g_wt = None
+        if holder["wt_soft"] is not None:
+            Q = a.K if a.wt_fmt == CLR_W_COMPLEMENT else 2 * a.K
+            self.g_wt = torch.empty(a.B_t, Q, a.H, a.W, dtype=torch.float32, device=dev)
+            self._gw_ws_bytes = self._lib.clr_pool_bwd_w_ws_bytes(a.C, a.K, a.wt_fmt)
+            self._gw_ws = torch.empty(self._gw_ws_bytes, dtype=torch.uint8, device=dev)
 
     def set_events(self, pool_begin=None, pool_end=None, bwd_begin=None, bwd_end=None) -> None:
         """Have the library record these :class:`uda_clr_b200._lib.Event` objects around the pooling / backward
@@ -335,6 +343,12 @@ class CLRPlan:
             check(self._lib.clr_step_bwd(self._ref, st), "clr_step_bwd")
         else:
             check(self._lib.clr_step_run(self._ref, st), "clr_step_run")
+        if self.g_wt is not None:
+            buf = self.holder["buf"]
+            R, C = 2 * a.K, a.C
+            check(self._lib.clr_pool_bwd_w(ptr(self.holder["xt"]), a.wt_fmt, a.B_t, C, a.H * a.W, a.K, ptr(buf.g_t),
+                                           ptr(buf.packed1[R * (C + 1):]), float(a.grad_scale), ptr(self._gw_ws),
+                                           self._gw_ws_bytes, ptr(self.g_wt), st), "clr_pool_bwd_w")
         self.step.first_s = self.step.first_t = False
 
     def outputs(self) -> CLRStepOutput:
