@@ -42,7 +42,6 @@ struct Tunables {
                        //     instead of the finish CTAs' completion counter
     int xchg_pull;     // in-kernel exchange: 1 = readers poll the peers' buffers (no remote stores), 0 = senders push
     void* trace_buf;   // device TraceRec[kTraceSlots] or NULL (clr_trace_set): device-side timeline of the kernels
-    int bwd_trace_id;  // trace slot of the next pool_bwd launch (set by the step orchestration)
 };
 Tunables& tunables();
 

@@ -163,7 +163,8 @@ static int launch_bwd(const BwdParams& p, bool vec4, int ctas, cudaStream_t st, 
     return launch_status();
 }
 
-int pool_bwd_impl(const BwdDom* doms, int ndom, int C, int HW, int K, cudaStream_t st, const DiscFinishParams* fin = nullptr) {
+int pool_bwd_impl(const BwdDom* doms, int ndom, int C, int HW, int K, cudaStream_t st, const DiscFinishParams* fin = nullptr,
+                  int trace_id = TR_BWD_BOTH) {
     CLR_CHECK_ARG(ndom >= 1 && ndom <= 2 && C > 0 && HW > 0 && K >= 1 && K <= CLR_MAX_K);
     bool vec4 = (HW % 4 == 0);
     int Qmax = 0;
@@ -179,7 +180,7 @@ int pool_bwd_impl(const BwdDom* doms, int ndom, int C, int HW, int K, cudaStream
         if (Q > Qmax) Qmax = Q;
     }
     BwdParams p{};
-    p.trace_id = tunables().bwd_trace_id ? tunables().bwd_trace_id : TR_BWD_BOTH;
+    p.trace_id = trace_id;
     p.ndom = ndom; p.C = C; p.HW = HW; p.K = K;
     const int pxb = kThreads * (vec4 ? 4 : 1);
     p.nPx = (HW + pxb - 1) / pxb;
@@ -204,11 +205,12 @@ int pool_bwd_impl(const BwdDom* doms, int ndom, int C, int HW, int K, cudaStream
     return launch_bwd<24>(p, vec4, ctas, st, fin);
 }
 
-int pool_bwd_with_finish(const clr_bwd_dom* dom, int C, int HW, int K, const DiscFinishParams& f, cudaStream_t st) {
+// one domain; `f` != NULL: the disc finish body rides as the first CTAs of the launch.  `source` picks the trace slot.
+int pool_bwd_one(const clr_bwd_dom* dom, int C, int HW, int K, const DiscFinishParams* f, bool source, cudaStream_t st) {
     if (!dom) return CLR_ERR_BAD_ARG;
     BwdDom d{dom->w, dom->g, dom->sums, dom->xcoef, dom->xtab, dom->grad, dom->scale_dev, dom->scale, dom->fmt, dom->B, dom->Kx,
              0, 2 * K, 0, 0.f};
-    return pool_bwd_impl(&d, 1, C, HW, K, st, &f);
+    return pool_bwd_impl(&d, 1, C, HW, K, st, f, source ? TR_BWD_S : TR_BWD_T);
 }
 
 }  // namespace clr

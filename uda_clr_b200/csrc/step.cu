@@ -359,11 +359,8 @@ int clr_step_run(const clr_step_args* a, clr_stream_t stream) {
     clr::bwd_doms(a, dd);
     cudaStream_t s0 = static_cast<cudaStream_t>(stream);
     if (a->ev_bwd_begin) cudaEventRecord(static_cast<cudaEvent_t>(a->ev_bwd_begin), s0);
-    clr::tunables().bwd_trace_id = clr::TR_BWD_T;
-    rc = clr::pool_bwd_with_finish(&dd[1], a->C, a->H * a->W, a->K, df, s0);
-    clr::tunables().bwd_trace_id = clr::TR_BWD_S;
-    if (rc == CLR_OK) rc = clr_pool_bwd_multi(&dd[0], 1, a->C, a->H * a->W, a->K, stream);
-    clr::tunables().bwd_trace_id = 0;
+    rc = clr::pool_bwd_one(&dd[1], a->C, a->H * a->W, a->K, &df, false, s0);
+    if (rc == CLR_OK) rc = clr::pool_bwd_one(&dd[0], a->C, a->H * a->W, a->K, nullptr, true, s0);
     if (a->ev_bwd_end) cudaEventRecord(static_cast<cudaEvent_t>(a->ev_bwd_end), s0);
     if (rc != CLR_OK) return rc;
     if (a->use_cons && a->w_aug != 0.f && a->g_oT_aug) {
