@@ -307,6 +307,32 @@ typedef struct clr_step_args {
     void* peer_rx[CLR_MAX_WORLD];
 } clr_step_args;
 
+/* ------------------------------------------------------------------------------------------------
+ * TransNorm: the domain-split batch normalisation with the adaptive channel weight that the
+ * reference's DeepLab uses with --use_TN.  Replaces `_BatchNorm.forward` of networks/sync_batchnorm/batchnorm.py
+ * (:439-493 training, :494-521 eval; class BatchNorm2d :523, selected at networks/deeplabv3.py:17-23).
+ * x, y, gy, gx: [B, C, HW] fp32 contiguous (HW = 1 for 2-D inputs); source = samples [0, B/2), target = the rest.
+ * weight / bias [C] may be NULL (affine = False).  save [5][C] = { mean_s, mean_t, rstd_s, rstd_t, alpha } is
+ * written by the forward and read by the backward.  ws: clr_tn_ws_bytes(C) bytes.
+ *   clr_tn_fwd : y = ((x - mean_d) * rstd_d * weight + bias) * (1 + alpha); running estimates (may be NULL) are
+ *                updated in place: r = (1 - momentum) r + momentum stat (unbiased variance), like F.batch_norm.
+ *                3 launches: one read of x (statistics), O(C), one read + one write.
+ *   clr_tn_bwd : gx, gweight [C], gbias [C] (either may be NULL); alpha is a constant (detached, :493).  eval_mode = 1:
+ *                adjoint of clr_tn_eval (the statistics are constants too).
+ *   clr_tn_eval: statistics = the running estimates; every sample is normalised with the TARGET ones (:497-509),
+ *                alpha from both (:510-514).  B >= 1.
+ * Returns CLR_ERR_UNSUPPORTED for C > 8192 or B > 65535. */
+size_t clr_tn_ws_bytes(int C);
+int clr_tn_fwd(const float* x, int B, int C, int HW, const float* weight, const float* bias,
+               float* running_mean_s, float* running_var_s, float* running_mean_t, float* running_var_t,
+               float momentum, float eps, void* ws, size_t ws_bytes, float* y, float* save, clr_stream_t stream);
+int clr_tn_eval(const float* x, int B, int C, int HW, const float* weight, const float* bias,
+                const float* running_mean_s, const float* running_var_s, const float* running_mean_t,
+                const float* running_var_t, float eps, void* ws, size_t ws_bytes, float* y, float* save,
+                clr_stream_t stream);
+int clr_tn_bwd(const float* x, const float* gy, int B, int C, int HW, const float* weight, const float* save,
+               int eval_mode, void* ws, size_t ws_bytes, float* gx, float* gweight, float* gbias, clr_stream_t stream);
+
 /* Peer-visible device memory for the in-kernel exchange: plain cudaMalloc (zero-filled) + CUDA IPC handles, so that a
  * host in any language can wire the ranks of one node together (exchange the 64-byte handles over its own channel). */
 int clr_peer_alloc(size_t bytes, void** ptr);

@@ -390,6 +390,87 @@ def uncertainty_map(o: np.ndarray, smooth: float = 1e-7):
 
 
 # --------------------------------------------------------------------------- the fused step (A1/A2 + A4 + A5 + A9 + A10)
+# --------------------------------------------------------------------------- 8(f) rank 4: TransNorm
+def _tn_flat(x: np.ndarray) -> np.ndarray:
+    """[B, C, ...] -> [B, C, HW] float64."""
+    x = np.asarray(x, F64)
+    return x.reshape(x.shape[0], x.shape[1], -1)
+
+
+def transnorm_alpha(mean: np.ndarray, var: np.ndarray, eps: float) -> np.ndarray:
+    """``alpha = C * prob / sum(prob)``, ``prob = 1 / (1 + |mu_s/sqrt(var_s+eps) - mu_t/sqrt(var_t+eps)|)``
+    (networks/sync_batchnorm/batchnorm.py:481-487); ``mean``/``var`` are ``[2, C]`` (source, target)."""
+    dis = np.abs(mean[0] / np.sqrt(var[0] + eps) - mean[1] / np.sqrt(var[1] + eps))
+    prob = 1.0 / (1.0 + dis)
+    return mean.shape[1] * prob / prob.sum()
+
+
+def transnorm_train(x: np.ndarray, weight: Optional[np.ndarray], bias: Optional[np.ndarray], eps: float = 1e-5
+                    ) -> Dict[str, np.ndarray]:
+    """Training forward of the reference's TransNorm (batchnorm.py:451-493): each half of the batch normalised with its
+    own statistics (biased variance, F.batch_norm), shared affine, times ``1 + alpha`` (unbiased variances, :474-476).
+    Returns ``y`` (shape of ``x``), ``alpha [C]``, ``mean``, ``var_b``, ``var_u`` (``[2, C]``)."""
+    xf = _tn_flat(x)
+    B, C, _ = xf.shape
+    h = B // 2
+    gamma = np.ones(C) if weight is None else np.asarray(weight, F64)
+    beta = np.zeros(C) if bias is None else np.asarray(bias, F64)
+    mean, var_b, var_u = np.zeros((2, C)), np.zeros((2, C)), np.zeros((2, C))
+    z = np.empty_like(xf)
+    for d, sl in enumerate((slice(0, h), slice(h, B))):
+        part = xf[sl]
+        n = part.shape[0] * part.shape[2]
+        mean[d] = part.mean(axis=(0, 2))
+        ss = ((part - mean[d][None, :, None]) ** 2).sum(axis=(0, 2))
+        var_b[d], var_u[d] = ss / n, ss / (n - 1)
+        z[sl] = (part - mean[d][None, :, None]) / np.sqrt(var_b[d] + eps)[None, :, None] * gamma[None, :, None] \
+            + beta[None, :, None]
+    alpha = transnorm_alpha(mean, var_u, eps)
+    y = z * (1.0 + alpha)[None, :, None]
+    return {"y": y.reshape(np.shape(x)), "alpha": alpha, "mean": mean, "var_b": var_b, "var_u": var_u}
+
+
+def transnorm_running(running: np.ndarray, stat: np.ndarray, factor: float) -> np.ndarray:
+    """``running = (1 - factor) running + factor stat`` (F.batch_norm's update; the variance fed in is the unbiased one)."""
+    return (1.0 - factor) * np.asarray(running, F64) + factor * np.asarray(stat, F64)
+
+
+def transnorm_train_backward(x: np.ndarray, weight: Optional[np.ndarray], gy: np.ndarray, eps: float = 1e-5):
+    """Adjoint of :func:`transnorm_train` with ``alpha`` held constant (``alpha.detach()``, batchnorm.py:493):
+    ``(gx, gweight, gbias)``."""
+    xf, gf = _tn_flat(x), _tn_flat(gy)
+    B, C, _ = xf.shape
+    h = B // 2
+    gamma = np.ones(C) if weight is None else np.asarray(weight, F64)
+    fw = transnorm_train(x, weight, None, eps)
+    q = 1.0 + fw["alpha"]
+    gx = np.empty_like(xf)
+    gw, gb = np.zeros(C), np.zeros(C)
+    for d, sl in enumerate((slice(0, h), slice(h, B))):
+        part, dz = xf[sl], gf[sl] * q[None, :, None]
+        n = part.shape[0] * part.shape[2]
+        rstd = 1.0 / np.sqrt(fw["var_b"][d] + eps)
+        xhat = (part - fw["mean"][d][None, :, None]) * rstd[None, :, None]
+        s1, s2 = dz.sum(axis=(0, 2)), (dz * xhat).sum(axis=(0, 2))
+        gx[sl] = (gamma * rstd)[None, :, None] * (dz - (s1 / n)[None, :, None] - xhat * (s2 / n)[None, :, None])
+        gw += s2
+        gb += s1
+    return gx.reshape(np.shape(x)), gw, gb
+
+
+def transnorm_eval(x: np.ndarray, weight, bias, rm_s, rv_s, rm_t, rv_t, eps: float = 1e-5) -> np.ndarray:
+    """Eval forward (batchnorm.py:494-521): target running estimates for every sample, ``alpha`` from both sets."""
+    xf = _tn_flat(x)
+    C = xf.shape[1]
+    gamma = np.ones(C) if weight is None else np.asarray(weight, F64)
+    beta = np.zeros(C) if bias is None else np.asarray(bias, F64)
+    mean = np.stack([np.asarray(rm_s, F64), np.asarray(rm_t, F64)])
+    var = np.stack([np.asarray(rv_s, F64), np.asarray(rv_t, F64)])
+    alpha = transnorm_alpha(mean, var, eps)
+    z = (xf - mean[1][None, :, None]) / np.sqrt(var[1] + eps)[None, :, None] * gamma[None, :, None] + beta[None, :, None]
+    return (z * (1.0 + alpha)[None, :, None]).reshape(np.shape(x))
+
+
 def clr_step(xs, ys, xt, wt, *, stored_s=None, stored_t=None, decay: float = 0.9,
              w_intra: float = 0.1, w_inter: float = 0.0, w_disc: float = 0.0, margin: float = 0.01,
              cons: Optional[dict] = None, w_aug: float = 0.0,

@@ -218,6 +218,32 @@ def uncertainty_map(o, smooth: float = 1e-7):
 
 
 # ----------------------------------------------------------------------------- one whole CLR step, the way the trainer runs it
+# ----------------------------------------------------------------------------- 8(f) rank 4: TransNorm
+def trans_norm(x, weight, bias, rm_s, rv_s, rm_t, rv_t, training: bool, factor: float = 0.1, eps: float = 1e-5):
+    """The ATen sequence of the reference's TransNorm forward (networks/sync_batchnorm/batchnorm.py:451-521): two
+    ``F.batch_norm`` calls + ``cat`` + two transposed copies + four reductions (training), or one ``F.batch_norm`` with
+    the target estimates (eval); ``alpha`` detached.  The running estimates are updated in place by ``F.batch_norm``."""
+    C = x.shape[1]
+    if training:
+        h = x.size()[0] // 2
+        src, tgt = x[:h], x[h:]
+        z = torch.cat((F.batch_norm(src, rm_s, rv_s, weight, bias, True, factor, eps),
+                       F.batch_norm(tgt, rm_t, rv_t, weight, bias, True, factor, eps)), dim=0)
+        if x.dim() == 4:
+            src = src.permute(0, 2, 3, 1).contiguous().view(-1, C)
+            tgt = tgt.permute(0, 2, 3, 1).contiguous().view(-1, C)
+        m_s, v_s = torch.mean(src, dim=0), torch.var(src, dim=0)
+        m_t, v_t = torch.mean(tgt, dim=0), torch.var(tgt, dim=0)
+    else:
+        z = F.batch_norm(x, rm_t, rv_t, weight, bias, False, factor, eps)
+        m_s, v_s, m_t, v_t = rm_s, rv_s, rm_t, rv_t
+    dis = torch.abs(m_s / torch.sqrt(v_s + eps) - m_t / torch.sqrt(v_t + eps))
+    prob = 1.0 / (1.0 + dis)
+    alpha = C * prob / sum(prob)
+    alpha = alpha.view(1, C, 1, 1) if x.dim() == 4 else alpha.view(1, C)
+    return z * (1 + alpha.detach())
+
+
 class ClrStepPort:
     """The CLR block of one training step (Trainer_prototype_full.py:328-449 + the two bytecode-only
     losses), fwd + ``backward()``, on whatever device the tensors live on."""

@@ -86,3 +86,13 @@ def ref_get_prototype_weight(feat, class_num, prototype):
 
 def ref_adaptation_factor(m):
     return load_utils().adaptation_factor(m)
+
+
+def ref_transnorm_class():
+    """The reference's TransNorm module class: ``networks.sync_batchnorm.batchnorm.BatchNorm2d`` (imports cleanly)."""
+    if not available():
+        raise RuntimeError("reference tree not present at %s" % REFERENCE_ROOT)
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    import networks.sync_batchnorm.batchnorm as ref_bn  # noqa: E402
+    return ref_bn.BatchNorm2d

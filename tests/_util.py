@@ -24,3 +24,16 @@ def golden():
         case, name = key.split("/", 1)
         cases.setdefault(case, {})[name] = z[key]
     return cases
+
+
+TN_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "transnorm_golden.npz")
+TOL_TN = 1e-5      # TransNorm outputs, running estimates and gradients: max|ours-ref| / max|ref| per tensor
+
+
+def transnorm_golden():
+    z = np.load(TN_GOLDEN)
+    cases = {}
+    for key in z.files:
+        case, name = key.split("/", 1)
+        cases.setdefault(case, {})[name] = z[key]
+    return cases

@@ -4,7 +4,8 @@ torch port, run on CUDA tensors) against this library, fwd + bwd, for
 
   * the whole CLR step (clr3 workload),
   * the drop-in pair gen_prototype + gen_prototype_retrify under autograd,
-  * the 8(f) glue ops (seg loss, uncertainty map) -- through autograd and through the raw C ABI.
+  * the 8(f) glue ops (seg loss, uncertainty map) -- through autograd and through the raw C ABI,
+  * TransNorm (8(f) rank 4) on decoder / ASPP / backbone-like activation shapes (``--only tn`` runs just this part).
 
     python tests/perf/eager_gpu_baseline.py [--B 8 --C 256 --H 128 --K 2 --iters 20]
 
@@ -27,6 +28,55 @@ from uda_clr_b200 import _lib, synth  # noqa: E402
 from uda_clr_b200._lib import check, ptr  # noqa: E402
 
 
+def transnorm_section(a):
+    """TransNorm forward + backward (module under autograd, and the raw C ABI) vs the reference's eager ATen sequence;
+    algorithmic bytes = 2 reads + 1 write forward, 4 reads + 1 write backward = 8 x 4BCHW."""
+    from uda_clr_b200 import transnorm as TN
+    dev = torch.device("cuda:0")
+    lib = _lib.load()
+    stream = torch.cuda.current_stream().cuda_stream
+    res = {}
+    for (B, C, H) in [(16, 305, 128), (16, 256, 128), (16, 1280, 32), (16, 24, 128), (16, 32, 256)]:
+        xs = [torch.randn(B, C, H, H, device=dev).requires_grad_(True) for _ in range(a.nbuf)]
+        gy = torch.randn(B, C, H, H, device=dev)
+        m = TN.TransNorm2d(C).to(dev)
+        bufs = [torch.zeros(C, device=dev), torch.ones(C, device=dev), torch.zeros(C, device=dev), torch.ones(C, device=dev)]
+        w = torch.ones(C, device=dev, requires_grad=True)
+        b_ = torch.zeros(C, device=dev, requires_grad=True)
+
+        def ours(i):
+            x = xs[i % a.nbuf]
+            x.grad = None
+            m(x).backward(gy)
+
+        def eager(i):
+            x = xs[i % a.nbuf]
+            x.grad = None
+            TP.trans_norm(x, w, b_, *bufs, True, 0.1, 1e-5).backward(gy)
+        y = torch.empty(B, C, H, H, device=dev)
+        gx = torch.empty(B, C, H, H, device=dev)
+        save = torch.empty(5, C, device=dev)
+        gw_, gb_ = torch.empty(C, device=dev), torch.empty(C, device=dev)
+        wsb = lib.clr_tn_ws_bytes(C)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+
+        def raw(i):
+            x = xs[i % a.nbuf]
+            check(lib.clr_tn_fwd(ptr(x), B, C, H * H, ptr(w), ptr(b_), ptr(bufs[0]), ptr(bufs[1]), ptr(bufs[2]), ptr(bufs[3]),
+                                 0.1, 1e-5, ptr(ws), wsb, ptr(y), ptr(save), stream), "tn fwd")
+            check(lib.clr_tn_bwd(ptr(x), ptr(gy), B, C, H * H, ptr(w), ptr(save), 0, ptr(ws), wsb, ptr(gx), ptr(gw_), ptr(gb_),
+                                 stream), "tn bwd")
+        tag = "transnorm_B%d_C%d_%dx%d" % (B, C, H, H)
+        alg = 8 * 4.0 * B * C * H * H
+        us_raw = time_batch(raw, a.iters)
+        res[tag] = dict(ours_autograd_us=round(time_batch(ours, a.iters), 2), c_abi_us=round(us_raw, 2),
+                        eager_aten_us=round(time_batch(eager, max(5, a.iters // 2)), 2),
+                        algorithmic_mb=round(alg / 1e6, 1), c_abi_gbs=round(alg / us_raw / 1e3, 1))
+        del xs, gy, y, gx
+        torch.cuda.empty_cache()
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--B", type=int, default=8)
@@ -35,7 +85,11 @@ def main():
     ap.add_argument("--K", type=int, default=2)
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--nbuf", type=int, default=3)
+    ap.add_argument("--only", default="", choices=["", "tn"])
     a = ap.parse_args()
+    if a.only == "tn":
+        print(json.dumps(dict(results=transnorm_section(a)), indent=1))
+        return
     B, C, H, K = a.B, a.C, a.H, a.K
     dev = torch.device("cuda:0")
     lib = _lib.load()
@@ -125,6 +179,7 @@ def main():
         check(lib.clr_entropy_fwd(ptr(o), o.numel(), 1e-7, ptr(g1), stream), "ent fwd")
         check(lib.clr_entropy_bwd(ptr(o), ptr(gw), o.numel(), 1e-7, ptr(g1), stream), "ent bwd")
     rec("uncertainty_map_fwd_bwd_c_abi", ent_raw)
+    res.update(transnorm_section(a))
     print(json.dumps(dict(shape=[B, C, H, H, K], results=res), indent=1))
 
 

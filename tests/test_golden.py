@@ -49,3 +49,33 @@ def test_cosine_and_schedule_golden():
     assert relerr(O.cosine_weight(c["in_feat"], c["in_proto"]), c["out_weight"]) < 1e-6
     ours = np.array([O.adaptation_factor(float(m)) for m in c["in_m"]])
     assert np.array_equal(ours, c["out_adaptation_factor"])
+
+
+# ---- 8(f) rank 4: TransNorm fixtures recorded from the reference module (tests/golden/make_transnorm_golden.py)
+from _util import TOL_TN, transnorm_golden  # noqa: E402
+
+TN = transnorm_golden()
+
+
+@pytest.mark.parametrize("case", sorted(TN))
+def test_transnorm_golden(case):
+    c = TN[case]
+    w, b, gy = c["in_weight"], c["in_bias"], c["seed_gy"]
+    run = {k: (np.zeros_like(w) if "mean" in k else np.ones_like(w)).astype(np.float64)
+           for k in ("running_mean_source", "running_var_source", "running_mean_target", "running_var_target")}
+    for step, key in enumerate(("in_x", "in_x2")):
+        x = c[key]
+        fw = O.transnorm_train(x, w, b)
+        assert relerr(fw["y"], c["out_y%d" % step]) < TOL_TN
+        gx, gw, gb = O.transnorm_train_backward(x, w, gy)
+        assert relerr(gx, c["grad_x%d" % step]) < TOL_TN * 10     # the reference's own fp32 backward carries ~1e-5
+        assert relerr(gw, c["grad_weight%d" % step]) < TOL_TN
+        assert relerr(gb, c["grad_bias%d" % step]) < TOL_TN
+        for d, dom in enumerate(("source", "target")):
+            run["running_mean_" + dom] = O.transnorm_running(run["running_mean_" + dom], fw["mean"][d], 0.1)
+            run["running_var_" + dom] = O.transnorm_running(run["running_var_" + dom], fw["var_u"][d], 0.1)
+        for k, v in run.items():
+            assert relerr(v, c["out_%s%d" % (k, step)]) < TOL_TN
+    y = O.transnorm_eval(c["in_x"], w, b, run["running_mean_source"], run["running_var_source"],
+                         run["running_mean_target"], run["running_var_target"])
+    assert relerr(y, c["out_eval"]) < TOL_TN

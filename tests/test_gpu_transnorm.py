@@ -1,0 +1,166 @@
+"""Parity of the TransNorm CUDA path (``clr_tn_fwd`` / ``clr_tn_bwd`` / ``clr_tn_eval`` through
+``uda_clr_b200.transnorm``) against the fixtures recorded from the reference module, the fp64 oracle and -- on the same
+GPU -- the eager ATen sequence of the reference (``oracle.clr_torch_port.trans_norm``).  SURVEY.md 8(f) rank 4;
+reference: networks/sync_batchnorm/batchnorm.py:439-521.  Floating point: 1e-5 relative (``TOL_TN``) for outputs, running
+estimates and parameter gradients, 1e-4 (``TOL_GRAD``) for input gradients."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import clr_oracle as O
+from oracle import clr_torch_port as TP
+from uda_clr_b200 import transnorm as TN
+from _util import TOL_GRAD, TOL_TN, relerr, transnorm_golden
+
+pytestmark = pytest.mark.gpu
+G = transnorm_golden()
+DEV = "cuda"
+BUFS = ("running_mean_source", "running_var_source", "running_mean_target", "running_var_target")
+
+
+def cu(a, grad=False):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32).to(DEV).requires_grad_(grad)
+
+
+def module(C, w, b):
+    m = TN.TransNorm2d(C).to(DEV)
+    with torch.no_grad():
+        m.weight.copy_(cu(w))
+        m.bias.copy_(cu(b))
+    return m
+
+
+@pytest.mark.parametrize("case", sorted(G))
+def test_module_vs_reference_fixture(case):
+    """Two training steps and one eval forward of the module against what the reference module produced."""
+    c = G[case]
+    C = c["in_weight"].shape[0]
+    m = module(C, c["in_weight"], c["in_bias"])
+    m.train()
+    gy = cu(c["seed_gy"])
+    for step, key in enumerate(("in_x", "in_x2")):
+        x = cu(c[key], True)
+        m.zero_grad()
+        y = m(x)
+        (y * gy).sum().backward()
+        assert relerr(y.detach().cpu().numpy(), c["out_y%d" % step]) < TOL_TN
+        assert relerr(x.grad.cpu().numpy(), c["grad_x%d" % step]) < TOL_GRAD
+        assert relerr(m.weight.grad.cpu().numpy(), c["grad_weight%d" % step]) < TOL_TN
+        assert relerr(m.bias.grad.cpu().numpy(), c["grad_bias%d" % step]) < TOL_TN
+        for buf in BUFS:
+            assert relerr(getattr(m, buf).cpu().numpy(), c["out_%s%d" % (buf, step)]) < TOL_TN
+        assert int(m.num_batches_tracked) == step + 1
+    m.eval()
+    with torch.no_grad():
+        assert relerr(m(cu(c["in_x"])).cpu().numpy(), c["out_eval"]) < TOL_TN
+
+
+@pytest.mark.parametrize("shape", [(8, 24, 128, 128), (8, 305, 32, 32), (4, 1280, 16, 16), (2, 3, 6, 7), (6, 16, 256, 256)])
+def test_train_vs_oracle_and_eager_port(shape):
+    """Decoder / ASPP / backbone-like shapes: fp64 oracle and the reference's eager ATen sequence on the same GPU."""
+    B, C, H, W = shape
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(B, C, H, W, generator=g) * (0.5 + 2.0 * torch.rand(1, C, 1, 1, generator=g)) + 3.0 * torch.randn(1, C, 1, 1, generator=g)
+    x[B // 2:] += 0.5
+    w, b = 0.5 + torch.rand(C, generator=g), 0.2 * torch.randn(C, generator=g)
+    gy = torch.randn(B, C, H, W, generator=g)
+    m = module(C, w.numpy(), b.numpy())
+    xo = cu(x.numpy(), True)
+    y = m(xo)
+    (y * gy.to(DEV)).sum().backward()
+
+    bufs = [torch.zeros(C, device=DEV), torch.ones(C, device=DEV), torch.zeros(C, device=DEV), torch.ones(C, device=DEV)]
+    xp, wp, bp = cu(x.numpy(), True), cu(w.numpy(), True), cu(b.numpy(), True)
+    yp = TP.trans_norm(xp, wp, bp, *bufs, True, 0.1, 1e-5)
+    (yp * gy.to(DEV)).sum().backward()
+    assert relerr(y.detach().cpu().numpy(), yp.detach().cpu().numpy()) < TOL_TN
+    assert relerr(xo.grad.cpu().numpy(), xp.grad.cpu().numpy()) < TOL_GRAD
+    assert relerr(m.weight.grad.cpu().numpy(), wp.grad.cpu().numpy()) < TOL_GRAD
+    assert relerr(m.bias.grad.cpu().numpy(), bp.grad.cpu().numpy()) < TOL_GRAD
+    for buf, ref in zip(BUFS, bufs):
+        assert relerr(getattr(m, buf).cpu().numpy(), ref.cpu().numpy()) < TOL_TN
+
+    if B * C * H * W <= 8 * 305 * 32 * 32:      # the fp64 oracle is a checker for small cases
+        fw = O.transnorm_train(x.numpy(), w.numpy(), b.numpy())
+        assert relerr(y.detach().cpu().numpy(), fw["y"]) < TOL_TN
+        gx, gw, gb = O.transnorm_train_backward(x.numpy(), w.numpy(), gy.numpy())
+        assert relerr(xo.grad.cpu().numpy(), gx) < TOL_TN * 2
+        assert relerr(m.weight.grad.cpu().numpy(), gw) < TOL_TN
+        assert relerr(m.bias.grad.cpu().numpy(), gb) < TOL_TN
+
+
+def test_large_mean_small_spread_is_stable():
+    """|mean| = 300 sigma: the shifted sums keep the variance accurate where sum x^2 - n mean^2 in fp32 would not."""
+    g = torch.Generator().manual_seed(5)
+    B, C, H, W = 4, 8, 64, 64
+    x = 300.0 + torch.randn(B, C, H, W, generator=g)
+    m = TN.TransNorm2d(C, affine=False).to(DEV)
+    y = m(x.to(DEV))
+    fw = O.transnorm_train(x.numpy(), None, None)
+    assert relerr(y.cpu().numpy(), fw["y"]) < 1e-4          # fp32 (x - mean) itself carries 300 * 6e-8 / 1
+    assert relerr(m.running_var_source.cpu().numpy(), O.transnorm_running(np.ones(C), fw["var_u"][0], 0.1)) < TOL_TN
+
+
+def test_eval_forward_backward_and_state_dict():
+    g = torch.Generator().manual_seed(9)
+    B, C, H, W = 3, 10, 12, 12
+    x = torch.randn(B, C, H, W, generator=g)
+    m = TN.TransNorm2d(C).to(DEV)
+    sd = m.state_dict()
+    assert list(sd) == ["weight", "bias"] + list(BUFS) + ["num_batches_tracked"]     # batchnorm.py:296-333 order
+    with torch.no_grad():
+        m.running_mean_source.copy_(torch.randn(C, generator=g))
+        m.running_var_source.copy_(0.5 + torch.rand(C, generator=g))
+        m.running_mean_target.copy_(torch.randn(C, generator=g))
+        m.running_var_target.copy_(0.5 + torch.rand(C, generator=g))
+        m.weight.copy_(0.5 + torch.rand(C, generator=g))
+    m.eval()
+    xo, xp = cu(x.numpy(), True), cu(x.numpy(), True)
+    y = m(xo)
+    wp, bp = m.weight.detach().clone().requires_grad_(True), m.bias.detach().clone().requires_grad_(True)
+    yp = TP.trans_norm(xp, wp, bp, m.running_mean_source, m.running_var_source, m.running_mean_target,
+                       m.running_var_target, False, 0.1, 1e-5)
+    gy = torch.randn(B, C, H, W, generator=g).to(DEV)
+    (y * gy).sum().backward()
+    (yp * gy).sum().backward()
+    assert relerr(y.detach().cpu().numpy(), yp.detach().cpu().numpy()) < TOL_TN
+    assert relerr(xo.grad.cpu().numpy(), xp.grad.cpu().numpy()) < TOL_TN
+    assert relerr(m.weight.grad.cpu().numpy(), wp.grad.cpu().numpy()) < TOL_GRAD
+    assert relerr(m.bias.grad.cpu().numpy(), bp.grad.cpu().numpy()) < TOL_GRAD
+    assert int(m.num_batches_tracked) == 0           # eval does not count batches
+    # a single-sample eval batch is allowed (validation runs with whatever the loader yields)
+    with torch.no_grad():
+        y1 = m(cu(x.numpy()[:1]))
+    assert relerr(y1.cpu().numpy(), y.detach().cpu().numpy()[:1]) < 1e-6
+
+
+def test_two_d_input_no_running_stats_and_errors():
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(64, 12, generator=g) * 2 + 1
+    m = TN.TransNorm1d(12, track_running_stats=False).to(DEV)
+    y = m(x.to(DEV))
+    fw = O.transnorm_train(x.numpy(), np.ones(12), np.zeros(12))
+    assert relerr(y.detach().cpu().numpy(), fw["y"]) < TOL_TN
+    assert m.running_mean_source is None and m.num_batches_tracked is None
+    with pytest.raises(ValueError):
+        TN.TransNorm2d(12).to(DEV)(x.to(DEV))                       # 2-D input into the 2d module
+    with pytest.raises(ValueError):
+        TN.TransNorm2d(4).to(DEV)(torch.randn(1, 4, 8, 8, device=DEV))   # training needs two halves
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        TN.TransNorm2d(4)(torch.randn(2, 4, 8, 8))
+    m.eval()
+    with pytest.raises(AssertionError):
+        m(x.to(DEV))                                                # eval without tracked estimates (batchnorm.py:495)
+
+
+def test_momentum_none_is_cumulative_average():
+    g = torch.Generator().manual_seed(4)
+    C = 5
+    m = TN.TransNorm2d(C, momentum=None).to(DEV)
+    means = []
+    for _ in range(3):
+        x = torch.randn(4, C, 8, 8, generator=g) + 2.0
+        m(x.to(DEV))
+        means.append(x[:2].mean(dim=(0, 2, 3)).numpy())
+    # factor = 1 / num_batches_tracked (batchnorm.py:424-425): the running mean is the plain average of the batch means
+    assert relerr(m.running_mean_source.cpu().numpy(), np.mean(means, axis=0)) < 1e-5

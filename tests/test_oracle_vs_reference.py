@@ -185,3 +185,56 @@ def test_trainer_ema_and_alignment_block():
         assert relerr(o["gxs"], xs.grad.numpy()) < 1e-10
         assert relerr(o["gxt"], xt.grad.numpy()) < 1e-10
     del b
+
+
+# ---- 8(f) rank 4: TransNorm (networks/sync_batchnorm/batchnorm.py:439-521)
+@pytest.mark.parametrize("shape", [(4, 6, 5, 7), (6, 10, 8, 8), (5, 3, 4, 4)])
+def test_transnorm_oracle_and_port_vs_reference(shape):
+    """fp64 reference module vs the oracle (forward, adjoint, running estimates, eval) and fp32 reference vs the torch
+    port (bit-for-bit: same ATen sequence)."""
+    B, C, H, W = shape
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(B, C, H, W, generator=g) * 1.7 + torch.randn(1, C, 1, 1, generator=g)
+    w, b = 0.5 + torch.rand(C, generator=g), torch.randn(C, generator=g) * 0.2
+    gy = torch.randn(B, C, H, W, generator=g)
+    cls = ref_import.ref_transnorm_class()
+
+    m = cls(C).double()
+    with torch.no_grad():
+        m.weight.copy_(w)
+        m.bias.copy_(b)
+    x64 = x.double().requires_grad_(True)
+    y = m(x64)
+    (y * gy.double()).sum().backward()
+    fw = O.transnorm_train(x.numpy(), w.numpy(), b.numpy())
+    assert relerr(fw["y"], y.detach().numpy()) < 1e-12
+    gx, gw, gb = O.transnorm_train_backward(x.numpy(), w.numpy(), gy.numpy())
+    assert relerr(gx, x64.grad.numpy()) < 1e-10
+    assert relerr(gw, m.weight.grad.numpy()) < 1e-11
+    assert relerr(gb, m.bias.grad.numpy()) < 1e-11
+    assert relerr(O.transnorm_running(np.zeros(C), fw["mean"][0], 0.1), m.running_mean_source.numpy()) < 1e-12
+    assert relerr(O.transnorm_running(np.ones(C), fw["var_u"][1], 0.1), m.running_var_target.numpy()) < 1e-12
+    m.eval()
+    with torch.no_grad():
+        ye = m(x.double())
+    yo = O.transnorm_eval(x.numpy(), w.numpy(), b.numpy(), m.running_mean_source.numpy(), m.running_var_source.numpy(),
+                          m.running_mean_target.numpy(), m.running_var_target.numpy())
+    assert relerr(yo, ye.numpy()) < 1e-12
+
+    m32 = cls(C)
+    with torch.no_grad():
+        m32.weight.copy_(w)
+        m32.bias.copy_(b)
+    bufs = [torch.zeros(C), torch.ones(C), torch.zeros(C), torch.ones(C)]
+    xr, xp = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    wp, bp = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    yr = m32(xr)
+    yp = TP.trans_norm(xp, wp, bp, *bufs, True, 0.1, 1e-5)
+    assert torch.equal(yr, yp)
+    (yr * gy).sum().backward()
+    (yp * gy).sum().backward()
+    assert torch.equal(xr.grad, xp.grad) and torch.equal(m32.weight.grad, wp.grad) and torch.equal(m32.bias.grad, bp.grad)
+    assert torch.equal(m32.running_var_source, bufs[1]) and torch.equal(m32.running_mean_target, bufs[2])
+    m32.eval()
+    with torch.no_grad():
+        assert torch.equal(m32(x), TP.trans_norm(x, w, b, *bufs, False, 0.1, 1e-5))

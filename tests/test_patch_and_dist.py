@@ -46,6 +46,37 @@ def test_patch_reference_rebinds_star_import_copies():
     assert U.gen_prototype is orig and TPF.gen_prototype is orig
 
 
+@pytest.mark.reference
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not present")
+def test_patch_transnorm_rebuilds_deeplab_with_our_module():
+    """``DeepLab(sync_bn=False)`` (--use_TN, networks/deeplabv3.py:17-27) built after ``patch_transnorm()`` carries
+    ``TransNorm2d`` everywhere the reference puts its TransNorm, with an identical state-dict layout."""
+    ref_import.ref_transnorm_class()
+    import networks.deeplabv3 as dl
+    from networks.backbone import mobilenet
+    from uda_clr_b200.transnorm import TransNorm2d
+    saved = mobilenet.MobileNetV2._load_pretrained_model
+    mobilenet.MobileNetV2._load_pretrained_model = lambda self: None        # no network: random init
+    try:
+        ref_model = dl.DeepLab(num_classes=2, backbone="mobilenet", output_stride=16, sync_bn=False, freeze_bn=False)
+        patched = clr.patch_transnorm()
+        try:
+            assert "networks.deeplabv3" in patched
+            ours = dl.DeepLab(num_classes=2, backbone="mobilenet", output_stride=16, sync_bn=False, freeze_bn=False)
+        finally:
+            clr.unpatch_reference()
+        assert dl.BatchNorm2d is not TransNorm2d
+    finally:
+        mobilenet.MobileNetV2._load_pretrained_model = saved
+    n_ref = sum(1 for m in ref_model.modules() if type(m).__name__ == "BatchNorm2d" and hasattr(m, "running_mean_source"))
+    n_ours = sum(1 for m in ours.modules() if isinstance(m, TransNorm2d))
+    assert n_ref == n_ours and n_ours > 30
+    sd_ref, sd_ours = ref_model.state_dict(), ours.state_dict()
+    assert list(sd_ref) == list(sd_ours)
+    assert all(sd_ref[k].shape == sd_ours[k].shape and sd_ref[k].dtype == sd_ours[k].dtype for k in sd_ref)
+    ours.load_state_dict(sd_ref)        # checkpoints of the reference load into the patched model
+
+
 def test_drop_in_signatures_match_reference_source():
     """Positional parameter names of the drop-ins equal the reference's (utils/Utils.py:86-311)."""
     import inspect

@@ -16,6 +16,7 @@ from .ops import (adaptation_factor, bmm_prototypes, dice_from_counts, distance_
                   update_objective_single_vector, weighted_prototypes)
 from .step import CLRPlan, CLRStep, CLRStepOutput, consistency_threshold, sigmoid_rampup  # noqa: F401
 from . import dist, ops  # noqa: F401
-from .patch import patch_reference, unpatch_reference  # noqa: F401
+from .patch import patch_reference, patch_transnorm, unpatch_reference  # noqa: F401
+from .transnorm import TransNorm1d, TransNorm2d, trans_norm  # noqa: F401
 
 __version__ = "0.1.0"

@@ -112,6 +112,10 @@ _SIGNATURES = {
     "clr_entropy_fwd": (c_int, [_P, c_size_t, c_float, _P, _P]),
     "clr_entropy_bwd": (c_int, [_P, _P, c_size_t, c_float, _P, _P]),
     "clr_seg_counts": (c_int, [_P, _P, c_int, c_int, c_size_t, c_float, _P, _P]),
+    "clr_tn_ws_bytes": (c_size_t, [c_int]),
+    "clr_tn_fwd": (c_int, [_P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, c_float, c_float, _P, c_size_t, _P, _P, _P]),
+    "clr_tn_eval": (c_int, [_P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, c_float, _P, c_size_t, _P, _P, _P]),
+    "clr_tn_bwd": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, c_int, _P, c_size_t, _P, _P, _P, _P]),
     "clr_cons_ws_bytes": (c_size_t, []),
     "clr_cons_fwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float, _P, c_size_t,
                              _P, _P]),

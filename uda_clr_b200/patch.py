@@ -52,7 +52,7 @@ def _reference_modules():
 
 def patch_reference() -> Dict[str, List[str]]:
     """Rebind the six CLR names everywhere they were copied.  Returns ``{name: [module names patched]}``."""
-    if _saved:
+    if any(n in REPLACEMENTS for _, n, _o in _saved):
         raise RuntimeError("reference already patched; call unpatch_reference() first")
     utils_mod = sys.modules.get("utils.Utils")
     report: Dict[str, List[str]] = {n: [] for n in REPLACEMENTS}
@@ -65,6 +65,30 @@ def patch_reference() -> Dict[str, List[str]]:
                 setattr(mod, n, REPLACEMENTS[n])
                 report[n].append(mod.__name__)
     return report
+
+
+def patch_transnorm() -> List[str]:
+    """Rebind the reference's TransNorm class (``networks.sync_batchnorm.batchnorm.BatchNorm2d``, the ``BatchNorm`` that
+    ``DeepLab`` picks with ``sync_bn=False`` / ``--use_TN``, networks/deeplabv3.py:4, 17-23) to :class:`TransNorm2d` in
+    every loaded module that imported it by name.  Call before the model is constructed; undone by
+    :func:`unpatch_reference`.  Returns the names of the modules patched."""
+    from .transnorm import TransNorm2d
+    ref_bn = sys.modules.get("networks.sync_batchnorm.batchnorm")
+    if ref_bn is None or not hasattr(ref_bn, "BatchNorm2d"):
+        raise RuntimeError("the reference's networks.sync_batchnorm.batchnorm is not imported")
+    orig = ref_bn.BatchNorm2d
+    if orig is TransNorm2d:
+        return []
+    patched = []
+    for name, mod in list(sys.modules.items()):
+        if mod is None or name.startswith("uda_clr_b200"):
+            continue
+        d = getattr(mod, "__dict__", None)
+        if d and d.get("BatchNorm2d") is orig:
+            _saved.append((mod, "BatchNorm2d", orig))
+            setattr(mod, "BatchNorm2d", TransNorm2d)
+            patched.append(name)
+    return patched
 
 
 def unpatch_reference() -> None:
