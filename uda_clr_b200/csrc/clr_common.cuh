@@ -120,6 +120,13 @@ __device__ __forceinline__ bool spin_until_at_least(const unsigned int* counter,
 // the wait still blocks until this whole grid has completed and flushed, so ordering is unchanged); wait for the
 // predecessor grid; stamp
 __device__ __forceinline__ void kernel_begin(int id) { trace_enter(id); pdl_trigger(); pdl_wait(); trace_ready(id); }
+// The same with the trigger AFTER the wait, for the producers of a flag dependency: their consumer skips
+// griddepcontrol.wait and trusts completion counters that the kernel BEFORE the producer zeroes, so it must not be
+// launched before that kernel has completed.  (With the early trigger a chain of small grids can become resident all at
+// once -- e.g. a CUDA-graph replay of a small step -- and the consumer would read the previous step's counters, still at
+// their final values, before the reset.)  Triggering after the wait makes "reset -> producer started -> consumer
+// launched" a happens-before chain; the consumer still overlaps the producer's whole body.
+__device__ __forceinline__ void kernel_begin_late_trigger(int id) { trace_enter(id); pdl_wait(); pdl_trigger(); trace_ready(id); }
 
 // ---- streaming loads / stores --------------------------------------------------------------------
 // Feature maps are touched exactly once per pass: read through the non-coherent path without

@@ -192,13 +192,14 @@ __global__ void __launch_bounds__(kConsThreads, 3) cons_kernel(const ConsArgs a)
 // a latency chain of a few KB) while the remaining CTAs stream the consistency pass, which does not depend on it.
 template <int VEC>
 __global__ void __launch_bounds__(kConsThreads, 3) pool_finish_cons_kernel(const PoolFinishParams f, const int n_fin, const ConsArgs a) {
+    const bool flag_producer = f.done_all != nullptr;      // grid-uniform
     if ((int)blockIdx.x < n_fin) {
-        kernel_begin(TR_ALIGN);
+        if (flag_producer) kernel_begin_late_trigger(TR_ALIGN); else kernel_begin(TR_ALIGN);
         pool_finish_body(f, blockIdx.x, n_fin);
         if (f.done_fin) cta_signal(f.done_fin, f.done_all);
         trace_exit(TR_ALIGN);
     } else {
-        kernel_begin(TR_CONS);
+        if (flag_producer) kernel_begin_late_trigger(TR_CONS); else kernel_begin(TR_CONS);
         cons_body<VEC, false>(a, blockIdx.x - n_fin, gridDim.x - n_fin);
         if (f.done_all) cta_signal(nullptr, f.done_all);
         trace_exit(TR_CONS);

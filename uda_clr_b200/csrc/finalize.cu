@@ -174,7 +174,7 @@ int disc_finalize_impl(float* packed2, const float* P_s, int K, int C, double np
 // Stand-alone launches of the merged reduce + finalize bodies (clr_finish.cuh); the fused step co-schedules them with
 // the consistency pass / the target-gradient write instead (cons.cu, pool_bwd.cu).
 __global__ void __launch_bounds__(kThreads) pool_finish_kernel(const PoolFinishParams p) {
-    kernel_begin(TR_ALIGN);
+    if (p.done_fin) kernel_begin_late_trigger(TR_ALIGN); else kernel_begin(TR_ALIGN);
     pool_finish_body(p, blockIdx.x, gridDim.x);
     if (p.done_fin) cta_signal(p.done_fin, p.done_all);
     trace_exit(TR_ALIGN);
