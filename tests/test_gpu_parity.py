@@ -192,3 +192,28 @@ def test_plain_c_host_runs_against_the_library(tmp_path):
     assert r.returncode == 0, r.stderr
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "clr_host ok" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("K", [1, 2, 4, 5, 8])
+def test_pool_cta_sizes_agree_with_oracle(K):
+    """The 128-bit pooling kernel is built for 256- and 128-thread CTAs (same chunk, same partial layout; 128 is the
+    default for more than 8 weight rows): both must reproduce the oracle's sums, and exact integer counts."""
+    from uda_clr_b200 import _lib, ops
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(40 + K)
+    B, C, H, W = 3, 37, 48, 64
+    y = synth.nested_ellipse_labels(B, K, H, W, g)
+    x = synth.class_shifted_features(y, C, g)
+    S, N = O.pool_sums(x.numpy(), O.weights_complement(y.numpy()))
+    want = np.concatenate([S, N[:, None]], axis=1)
+    got = {}
+    try:
+        for nt in (256, 128):
+            _lib.check(lib.clr_set_tunable(b"pool_threads", nt), "pool_threads")
+            got[nt] = ops.pool_sums(x.to(DEV), y.to(DEV), _lib.CLR_W_COMPLEMENT, K).cpu().numpy()
+    finally:
+        lib.clr_set_tunable(b"pool_threads", 0)
+    for nt, s in got.items():
+        assert relerr(s[:, :-1], want[:, :-1]) < TOL_PROTO
+        assert np.array_equal(s[:, -1], want[:, -1])          # hard labels: pixel counts are exact integers
+    assert relerr(got[128], got[256]) < 2e-6

@@ -73,14 +73,14 @@ __device__ __forceinline__ ItemCoord decode_item(const PoolParams& p, int it) {
 
 // Stage the R weight rows of (b, chunk) in shared memory (complement rows are materialised here:
 // w_bck = 1 - w_obj, utils/Utils.py:111-112).  Pixels past the plane are staged as 0 for every row.
-template <int R, int VEC, int REPS>
+template <int R, int VEC, int REPS, int NT = kThreads>
 __device__ __forceinline__ void stage_weights(const PoolDom& D, int b, int px0, int HW, float* wsm, int tid) {
-    constexpr int PX = kThreads * VEC * REPS, K = R / 2;
+    constexpr int PX = NT * VEC * REPS, K = R / 2;
     const int WP = (D.fmt == CLR_W_COMPLEMENT) ? K : R;
     const float* wb = D.w + (size_t)b * WP * HW;
 #pragma unroll
     for (int rep = 0; rep < REPS; ++rep) {
-        const int off = (rep * kThreads + tid) * VEC;
+        const int off = (rep * NT + tid) * VEC;
         const bool ok = px0 + off < HW;   // VEC-granular: HW % VEC == 0 on the VEC = 4 paths
         if (D.fmt == CLR_W_COMPLEMENT) {
 #pragma unroll
@@ -123,11 +123,12 @@ __device__ __forceinline__ Pack<VEC> lds_pack(const float* p) {
 
 // CTA-level combine of the per-thread accumulators of one item and store of the partial row slices.
 // sync() is the barrier over the 256 compute threads.
-template <int R, int CG, int VEC, int REPS, typename Sync>
+template <int R, int CG, int VEC, int REPS, int NT = kThreads, typename Sync>
 __device__ __forceinline__ void reduce_and_store(float (&acc)[pool_nacc(R)], const float* wsm, float* red, int& parity,
                                                  float* out, int C, int c0, bool owns_counts,
                                                  int tid, Sync sync) {
-    constexpr int PX = kThreads * VEC * REPS, NB = pool_nacc(R) / 32;
+    constexpr int PX = NT * VEC * REPS, NB = pool_nacc(R) / 32, kWarps = NT / 32;   // (shadows the 256-thread constant)
+    static_assert(NT / 32 >= NB, "one warp per 32-accumulator block in the cross-warp combine");
     const int lane = tid & 31, warp = tid >> 5;
     float nsum[R];
     if (owns_counts) {   // the item that owns channel group 0 also sums this chunk's weights
@@ -136,7 +137,7 @@ __device__ __forceinline__ void reduce_and_store(float (&acc)[pool_nacc(R)], con
             float s = 0.f;
 #pragma unroll
             for (int rep = 0; rep < REPS; ++rep) {
-                const int off = (rep * kThreads + tid) * VEC;
+                const int off = (rep * NT + tid) * VEC;
 #pragma unroll
                 for (int v = 0; v < VEC; ++v) s += wsm[r * PX + off + v];
             }
@@ -183,11 +184,16 @@ __device__ __forceinline__ void reduce_and_store(float (&acc)[pool_nacc(R)], con
 // ------------------------------------------------------------------------------------------------
 // LDG path (also the scalar fallback)
 // ------------------------------------------------------------------------------------------------
-template <int R, int VEC>
-__global__ void __launch_bounds__(kThreads, 2) pool_fwd_ldg_kernel(const PoolParams p) {
+// NT = threads per CTA.  The chunk (PX pixels, fixed per R so that the partial layout does not depend on NT) is spread
+// over NT threads: NT = 128 gives every thread twice the pixels per item, i.e. twice the FMAs per accumulator between two
+// transposing butterflies -- for R > 8 (64 accumulators, 4 channels x 1024 pixels per item) the butterfly's FSEL / SHFL /
+// FADD were as many instructions as the FMAs themselves (ncu source page, K = 8: 33.5 M FFMA vs 33.3 M).
+template <int R, int VEC, int NT>
+__global__ void __launch_bounds__(NT, 2) pool_fwd_ldg_kernel(const PoolParams p) {
     kernel_begin(TR_POOL);
     if (p.counter_reset && blockIdx.x == 0 && threadIdx.x < 4) p.counter_reset[threadIdx.x] = 0u;   // last-CTA counter + completion counters
-    constexpr int CG = pool_cg(R), REPS = pool_reps(R), PX = kThreads * VEC * REPS;
+    constexpr int CG = pool_cg(R), REPS = pool_reps(R) * (kThreads / NT), PX = NT * VEC * REPS;
+    static_assert(PX == kThreads * VEC * pool_reps(R), "chunk size is independent of the CTA size");
     extern __shared__ __align__(16) float smem[];
     float* wsm = smem;                 // [R][PX]
     float* red = smem + R * PX;        // [2][NB][kWarps][32]
@@ -204,7 +210,7 @@ __global__ void __launch_bounds__(kThreads, 2) pool_fwd_ldg_kernel(const PoolPar
         if (key != cur_key) {
             __syncthreads();
             cur_key = key;
-            stage_weights<R, VEC, REPS>(D, ic.b, px0, p.HW, wsm, tid);
+            stage_weights<R, VEC, REPS, NT>(D, ic.b, px0, p.HW, wsm, tid);
             __syncthreads();
         }
         float acc[pool_nacc(R)];
@@ -214,7 +220,7 @@ __global__ void __launch_bounds__(kThreads, 2) pool_fwd_ldg_kernel(const PoolPar
         const float* xb = D.feat + ((size_t)ic.b * p.C + c0) * p.HW + px0;
 #pragma unroll
         for (int rep = 0; rep < REPS; ++rep) {
-            const int off = (rep * kThreads + tid) * VEC;
+            const int off = (rep * NT + tid) * VEC;
             const bool ok = px0 + off < p.HW;
             Pack<VEC> x[CG];
 #pragma unroll
@@ -234,7 +240,7 @@ __global__ void __launch_bounds__(kThreads, 2) pool_fwd_ldg_kernel(const PoolPar
             }
         }
         float* out = D.partial + (size_t)ic.slot * R * (p.C + 1);
-        reduce_and_store<R, CG, VEC, REPS>(acc, wsm, red, parity, out, p.C, c0, ic.grp == 0, tid, sync);
+        reduce_and_store<R, CG, VEC, REPS, NT>(acc, wsm, red, parity, out, p.C, c0, ic.grp == 0, tid, sync);
     }
     trace_exit(TR_POOL);
 }
@@ -436,20 +442,35 @@ static void launch_reduce(const PoolParams& p, int R, cudaStream_t st) {
     clr::launch_k(pool_reduce_kernel, dim3((n + 31) / 32, p.ndom), dim3(32, 8), 0, st, p, R);
 }
 
-template <int R, int VEC>
-static int launch_ldg(const PoolParams& p, cudaStream_t st) {
+template <int R, int VEC, int NT>
+static int launch_ldg_nt(const PoolParams& p, cudaStream_t st) {
     constexpr int PX = kThreads * VEC * pool_reps(R);
-    constexpr size_t smem = sizeof(float) * (R * PX + 2 * (pool_nacc(R) / 32) * kWarps * 32);
-    auto kern = pool_fwd_ldg_kernel<R, VEC>;
+    constexpr size_t smem = sizeof(float) * (R * PX + 2 * (pool_nacc(R) / 32) * (NT / 32) * 32);
+    auto kern = pool_fwd_ldg_kernel<R, VEC, NT>;
     CLR_RETURN_IF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    CLR_RETURN_IF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem));
+    CLR_RETURN_IF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem));
     if (occ < 1) occ = 1;
     int grid = device_facts().sms * occ;
     if (grid > p.total) grid = p.total;
-    clr::launch_k(kern, grid, kThreads, smem, st, p);
+    clr::launch_k(kern, grid, NT, smem, st, p);
     if (!p.skip_reduce) launch_reduce(p, R, st);
     return launch_status();
+}
+
+// CTA size: 128 threads (2 CTAs / SM, ~254 registers: every load of an item in flight at once) where the per-item
+// butterfly would otherwise rival the FMAs (R > 8: K >= 5), 256 otherwise.  Measured in the live step (bench.py --K):
+// K = 8 pooling 129 -> 114 us; K = 4 unchanged (69.7 / 68.5 us); K = 2 (HBM-bound) 45.4 -> 49.7 us, hence the switch
+// point.  Compiling the 128-thread form for 3 CTAs / SM (168 registers, spills) lost everywhere.  "pool_threads" tunable:
+// 128 / 256 force one of them for A/B runs.
+template <int R, int VEC>
+static int launch_ldg(const PoolParams& p, cudaStream_t st) {
+    const int want = tunables().pool_threads;
+    const bool small = want == 128 || (want != 256 && R > 8);
+    if constexpr (VEC == 4) {
+        if (small) return launch_ldg_nt<R, VEC, 128>(p, st);
+    }
+    return launch_ldg_nt<R, VEC, kThreads>(p, st);
 }
 
 template <int R>
