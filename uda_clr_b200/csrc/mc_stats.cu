@@ -35,15 +35,18 @@ __device__ __forceinline__ void mc_sigmoids(float p, float& s_half, float& s_ful
         asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(u) : "f"(pc * -0.72134752044448170368f));
         const float a = 1.0f + u, b = fmaf(u, u, 1.0f);
         asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a * b));
-        s_half = r * b;
-        s_full = r * a;
+        s_half = __fmul_rn(r, b);      // pinned (never contracted into a later add / subtract): the value is also stored
+        s_full = r * a;                // and re-used by the variance pass, and every instantiation must round alike
     }
 }
 
 // std (unbiased, of sigmoid(p/2)) and mean (of sigmoid(p)) over the T MC passes for the VEC positions starting at i.
 // preds is [T][n].  TT > 0: T <= TT, values kept in registers (two-pass variance); TT == 0: any T, Welford.
-template <int VEC, int TT, bool PRECISE>
-__device__ __forceinline__ void mc_vec_stats(const float* __restrict__ preds, int T, size_t n, size_t i, Pack<VEC>& s, Pack<VEC>& m) {
+// EXACT: T == TT is known at compile time (the reference's T = 8): no per-pass predicates -- they were ~10 % of the
+// kernel's instructions (32 BRA + 26 ISETP per thread in the ncu source page) in a pass that is issue / MUFU co-limited.
+template <int VEC, int TT, bool PRECISE, bool EXACT = false>
+__device__ __forceinline__ void mc_vec_stats(const float* __restrict__ preds, int T_rt, size_t n, size_t i, Pack<VEC>& s, Pack<VEC>& m) {
+    const int T = EXACT ? TT : T_rt;
     float mean_h[VEC], m2[VEC], mean_f[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) { mean_h[v] = 0.f; m2[v] = 0.f; mean_f[v] = 0.f; }
@@ -67,7 +70,8 @@ __device__ __forceinline__ void mc_vec_stats(const float* __restrict__ preds, in
         }
         const float invT = 1.0f / (float)T;
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) mean_h[v] *= invT;
+        for (int v = 0; v < VEC; ++v) mean_h[v] = __fmul_rn(mean_h[v], invT);   // pinned: never contracted into the subtraction
+                                                                                 // below, so every instantiation rounds alike
 #pragma unroll
         for (int t = 0; t < TT; ++t) {
             if (t < T) {
@@ -96,7 +100,7 @@ __device__ __forceinline__ void mc_vec_stats(const float* __restrict__ preds, in
     }
 }
 
-template <int VEC, int TT, bool PRECISE>
+template <int VEC, int TT, bool PRECISE, bool EXACT = false>
 __global__ void __launch_bounds__(256) mc_stats_kernel(const float* __restrict__ preds, int T, size_t n,
                                                        float* __restrict__ std_map, float* __restrict__ pred_mean) {
     kernel_begin(TR_MC_STATS);
@@ -104,7 +108,7 @@ __global__ void __launch_bounds__(256) mc_stats_kernel(const float* __restrict__
     const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
     if (i >= n) { trace_exit(TR_MC_STATS); return; }
     Pack<VEC> s, m;
-    mc_vec_stats<VEC, TT, PRECISE>(preds, T, n, i, s, m);
+    mc_vec_stats<VEC, TT, PRECISE, EXACT>(preds, T, n, i, s, m);
     st_keep<VEC>(std_map + i, s);
     st_keep<VEC>(pred_mean + i, m);
     trace_exit(TR_MC_STATS);
@@ -114,7 +118,8 @@ template <int VEC, bool PRECISE>
 static void launch_mc(const float* preds, int T, size_t n, float* std_map, float* pred_mean, cudaStream_t st) {
     const size_t threads = (n + VEC - 1) / VEC;
     const unsigned blocks = (unsigned)((threads + 255) / 256);
-    if (T <= 8) launch_k(mc_stats_kernel<VEC, 8, PRECISE>, blocks, 256, 0, st, preds, T, n, std_map, pred_mean);
+    if (T == 8 && !tunables().mc_generic) launch_k(mc_stats_kernel<VEC, 8, PRECISE, true>, blocks, 256, 0, st, preds, T, n, std_map, pred_mean);
+    else if (T <= 8) launch_k(mc_stats_kernel<VEC, 8, PRECISE>, blocks, 256, 0, st, preds, T, n, std_map, pred_mean);
     else if (T <= 16) launch_k(mc_stats_kernel<VEC, 16, PRECISE>, blocks, 256, 0, st, preds, T, n, std_map, pred_mean);
     else launch_k(mc_stats_kernel<VEC, 0, PRECISE>, blocks, 256, 0, st, preds, T, n, std_map, pred_mean);
 }
