@@ -164,3 +164,43 @@ def test_momentum_none_is_cumulative_average():
         means.append(x[:2].mean(dim=(0, 2, 3)).numpy())
     # factor = 1 / num_batches_tracked (batchnorm.py:424-425): the running mean is the plain average of the batch means
     assert relerr(m.running_mean_source.cpu().numpy(), np.mean(means, axis=0)) < 1e-5
+
+
+def test_full_size_properties_decoder_shape():
+    """B = 16, C = 305, 128 x 128 (two 8-sample domains of the real decoder feature map: 320 MB) -- too big for the fp64
+    oracle to be a quick checker, so the size-independent laws pinned in tests/test_oracle_properties.py are asserted on
+    the device: every half comes out centred on beta with scale gamma, alpha sums to C, and the adjoint satisfies
+    sum(gx) == 0 and sum(gx * xhat) == 0 per (domain, channel) when beta / gamma carry no upstream-dependent shift."""
+    g = torch.Generator(device=DEV).manual_seed(17)
+    B, C, H, W = 16, 305, 128, 128
+    x = torch.randn(B, C, H, W, device=DEV, generator=g) * 2.0 + torch.randn(1, C, 1, 1, device=DEV, generator=g)
+    x[B // 2:] += 0.3
+    x.requires_grad_(True)
+    m = TN.TransNorm2d(C).to(DEV)
+    with torch.no_grad():
+        m.weight.uniform_(0.5, 1.5)
+        m.bias.normal_()
+    y = m(x)
+    gy = torch.randn(B, C, H, W, device=DEV, generator=g)
+    y.backward(gy)
+    h = B // 2
+    with torch.no_grad():
+        xs, xt = x[:h].double(), x[h:].double()
+        var = torch.stack([xs.var(dim=(0, 2, 3), unbiased=True), xt.var(dim=(0, 2, 3), unbiased=True)])
+        mean = torch.stack([xs.mean(dim=(0, 2, 3)), xt.mean(dim=(0, 2, 3))])
+        dis = (mean[0] / (var[0] + 1e-5).sqrt() - mean[1] / (var[1] + 1e-5).sqrt()).abs()
+        prob = 1.0 / (1.0 + dis)
+        alpha = C * prob / prob.sum()
+        q = (1.0 + alpha).view(1, C, 1, 1)
+        for d, sl in enumerate((slice(0, h), slice(h, B))):
+            z = y[sl].double() / q
+            assert float((z.mean(dim=(0, 2, 3)) - m.bias.double()).abs().max()) < 2e-6
+            vb = (xs if d == 0 else xt).var(dim=(0, 2, 3), unbiased=False)
+            want = m.weight.double() ** 2 * vb / (vb + 1e-5)
+            assert float(((z.var(dim=(0, 2, 3), unbiased=False) - want).abs() / want).max()) < 1e-5
+            gxd = x.grad[sl].double()
+            xhat = ((xs if d == 0 else xt) - mean[d].view(1, C, 1, 1))
+            scale = float(gxd.abs().sum(dim=(0, 2, 3)).max())
+            assert float(gxd.sum(dim=(0, 2, 3)).abs().max()) < 1e-5 * scale            # batch-norm adjoint: orthogonal to 1
+            assert float((gxd * xhat).sum(dim=(0, 2, 3)).abs().max()) < 1e-4 * scale * float(xhat.abs().max())   # and to xhat
+        assert abs(float((m.running_mean_source.double() - 0.1 * mean[0]).abs().max())) < 1e-6

@@ -81,3 +81,57 @@ def test_pool_backward_is_the_adjoint(shape, seed):
     lhs = float((g * (mu_p - mu_m) / (2 * eps)).sum())
     rhs = float((gx * dx).sum())
     assert abs(lhs - rhs) <= 1e-6 * max(1.0, abs(rhs))
+
+
+# ---- TransNorm (8(f) rank 4): the laws tests/test_gpu_transnorm.py relies on at full size
+tn_shapes = st.tuples(st.integers(2, 6), st.integers(1, 6), st.integers(2, 5), st.integers(1, 5))
+
+
+@settings(max_examples=40, deadline=None)
+@given(tn_shapes, st.integers(0, 2 ** 31 - 1))
+def test_transnorm_normalises_each_half_and_alpha_sums_to_c(shape, seed):
+    B, C, H, W = shape
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((B, C, H, W)) * rng.uniform(0.5, 3.0, (1, C, 1, 1)) + rng.standard_normal((1, C, 1, 1))
+    gamma, beta = rng.uniform(0.5, 1.5, C), rng.standard_normal(C)
+    eps = 1e-5
+    fw = O.transnorm_train(x, gamma, beta, eps)
+    assert np.isclose(fw["alpha"].sum(), C, rtol=1e-12)                 # alpha = C prob / sum(prob)
+    h = B // 2
+    z = fw["y"] / (1.0 + fw["alpha"])[None, :, None, None]
+    for d, sl in enumerate((slice(0, h), slice(h, B))):
+        m = z[sl].mean(axis=(0, 2, 3))
+        v = z[sl].var(axis=(0, 2, 3))
+        assert np.allclose(m, beta, atol=1e-9)                           # every half is centred on beta ...
+        assert np.allclose(v, gamma ** 2 * fw["var_b"][d] / (fw["var_b"][d] + eps), rtol=1e-9, atol=1e-12)   # ... with scale gamma
+    # permuting the samples inside each half or the pixels changes nothing but the order of the outputs
+    pb = np.concatenate([rng.permutation(h), h + rng.permutation(B - h)])
+    pp = rng.permutation(H * W)
+    xp = x[pb].reshape(B, C, -1)[:, :, pp].reshape(x.shape)
+    fp = O.transnorm_train(xp, gamma, beta, eps)
+    assert np.allclose(fp["y"], fw["y"][pb].reshape(B, C, -1)[:, :, pp].reshape(x.shape), rtol=1e-10, atol=1e-10)
+    assert np.allclose(fp["alpha"], fw["alpha"], rtol=1e-10)
+
+
+@settings(max_examples=30, deadline=None)
+@given(tn_shapes, st.integers(0, 2 ** 31 - 1))
+def test_transnorm_backward_is_the_adjoint(shape, seed):
+    """<gy, J dx> == <J^T gy, dx> with alpha held constant, by central differences of the forward with frozen alpha."""
+    B, C, H, W = shape
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((B, C, H, W)) * 1.5 + rng.standard_normal((1, C, 1, 1))
+    gamma = rng.uniform(0.5, 1.5, C)
+    gy, dx = rng.standard_normal(x.shape), rng.standard_normal(x.shape)
+    gx, gw, gb = O.transnorm_train_backward(x, gamma, gy)
+    alpha = O.transnorm_train(x, gamma, None)["alpha"]
+
+    def frozen(xx, gg):
+        fw = O.transnorm_train(xx, gg, None)
+        return fw["y"] / (1.0 + fw["alpha"])[None, :, None, None] * (1.0 + alpha)[None, :, None, None]
+    e = 1e-6
+    jv = (frozen(x + e * dx, gamma) - frozen(x - e * dx, gamma)) / (2 * e)
+    assert np.isclose((gy * jv).sum(), (gx * dx).sum(), rtol=2e-5, atol=1e-7)
+    dg = rng.standard_normal(C)
+    jg = (frozen(x, gamma + e * dg) - frozen(x, gamma - e * dg)) / (2 * e)
+    assert np.isclose((gy * jg).sum(), (gw * dg).sum(), rtol=2e-5, atol=1e-7)
+    assert np.allclose(gb, (gy * (1.0 + alpha)[None, :, None, None]).sum(axis=(0, 2, 3)), rtol=1e-10)
