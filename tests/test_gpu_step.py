@@ -659,3 +659,29 @@ def test_plan_run_is_cuda_graph_capturable():
         got = snapshot(st_g, pl_g)
         for g_, e_ in zip(got, exp):
             assert torch.equal(g_, e_)
+
+
+@pytest.mark.parametrize("K,C,H", [(2, 256, 64), (3, 37, 16), (8, 24, 16)])
+def test_merged_backward_launch_equals_two_launches(K, C, H):
+    """clr_step_run writes both gradient maps in ONE launch ([disc finish | gradient of xt | gated gradient of xs]); with
+    "bwd_merge_off" = 1 it uses the two launches it replaced.  Same arithmetic: bit-identical outputs, EMA steps included."""
+    from uda_clr_b200 import _lib
+    lib = _lib.load()
+    b = synth.make_batch(B=2, C=C, H=H, W=H, K=K, T=4, up=4, seed=11 + C, image_res=True)
+    t = {k: getattr(b, k).to(DEV) for k in ("xs", "ys", "xt", "oT_before", "preds", "oT", "oT_aug")}
+    res = []
+    for off in (0, 1):
+        try:
+            _lib.check(lib.clr_set_tunable(b"bwd_merge_off", off), "bwd_merge_off")
+            step = clr.CLRStep(K=K, retrify=True, use_disc=True, use_cons=True, backprop_aug=True)
+            plan = step.plan(t["xs"], t["ys"], t["xt"], oT_before=t["oT_before"], preds=t["preds"], T=4, oT=t["oT"],
+                             oT_aug=t["oT_aug"], epoch=1.0)
+            for _ in range(3):
+                plan.run()
+            torch.cuda.synchronize()
+            res.append([plan.losses.clone(), plan.gxs.clone(), plan.gxt.clone(), plan.g_oT_aug.clone(), step.stored_s.clone()])
+        finally:
+            lib.clr_set_tunable(b"bwd_merge_off", 0)
+    assert float(res[0][0][7]) == 0.0            # no gate time-out
+    for x, y in zip(res[0], res[1]):
+        assert torch.equal(x, y)

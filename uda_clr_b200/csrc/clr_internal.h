@@ -52,6 +52,8 @@ struct DiscFinishParams;
 int pool_finish_launch(const PoolFinishParams& p, cudaStream_t st);
 int disc_finish_launch(const DiscFinishParams& p, cudaStream_t st);
 int pool_bwd_one(const clr_bwd_dom* dom, int C, int HW, int K, const DiscFinishParams* f, bool source, cudaStream_t st);
+int pool_bwd_merged(const clr_bwd_dom* first, const clr_bwd_dom* gated, int C, int HW, int K, const DiscFinishParams* f,
+                    unsigned int* gate, float* gate_err, cudaStream_t st);
 
 // MC statistics + retrify weights in one pass (mc_stats.cu); CLR_ERR_UNSUPPORTED -> run the two kernels.
 int mc_retrify_fused(const float* preds, const float* oT_before, int T, int B, int K, int H, int W, int Hi, int Wi,

@@ -39,6 +39,10 @@ struct BwdParams {
     BwdDom dom[2];
     int ndom, C, HW, K, nPx, nSpan;
     int trace_id;
+    // merged backward launch ([disc finish | gradient of xt | gradient of xs]): the CTAs of domain `gate_dom` need the
+    // finish CTAs' output (g of that domain, xtab) and wait until `gate` (bumped once by every finish CTA, zeroed by the
+    // step's pooling kernel) reaches gate_n; they then read those vectors through coherent loads only.
+    unsigned int* gate; unsigned int gate_n; int gate_dom; float* gate_err;
 };
 
 constexpr int kBwdSpan = 32;   // channels per CTA
@@ -72,6 +76,13 @@ __device__ __forceinline__ void pool_bwd_body(const BwdParams& p, int bid) {
             cf[q] = ld_keep<VEC>(src + px);
         }
     }
+    const bool gated = p.gate != nullptr && d == p.gate_dom;      // CTA-uniform
+    if (gated) {
+        if (tid == 0 && !spin_until_at_least(p.gate, p.gate_n) && p.gate_err) *p.gate_err = 1.f;
+        __syncthreads();
+    }
+    // vectors the finish CTAs of the same launch may have written: coherent loads when gated
+    auto ldv = [gated](const float* q_) -> float { return gated ? __ldcg(q_) : __ldg(q_); };
     // ---- per-CTA table for channels c0 .. c0+31: T[0] constant term, T[1+q] coefficient of plane q.
     //      One thread per (row q, channel j) entry so the g / N loads and divides are a single parallel round.
     {
@@ -86,18 +97,18 @@ __device__ __forceinline__ void pool_bwd_body(const BwdParams& p, int bid) {
                 if (row == 0) {
                     if (D.fmt == CLR_W_COMPLEMENT)
                         for (int k = 0; k < K; ++k)
-                            t += scale * __ldg(D.g + (size_t)(K + k) * p.C + c) / (__ldg(sums + (size_t)(K + k) * (p.C + 1) + p.C) + nadd);
+                            t += scale * ldv(D.g + (size_t)(K + k) * p.C + c) / (__ldg(sums + (size_t)(K + k) * (p.C + 1) + p.C) + nadd);
                 } else if (row - 1 < QW) {
                     const int r = row - 1;
-                    const float gr = scale * __ldg(D.g + (size_t)r * p.C + c) / (__ldg(sums + (size_t)r * (p.C + 1) + p.C) + nadd);
+                    const float gr = scale * ldv(D.g + (size_t)r * p.C + c) / (__ldg(sums + (size_t)r * (p.C + 1) + p.C) + nadd);
                     if (D.fmt == CLR_W_COMPLEMENT) {
-                        const float gb = scale * __ldg(D.g + (size_t)(K + r) * p.C + c) / (__ldg(sums + (size_t)(K + r) * (p.C + 1) + p.C) + nadd);
+                        const float gb = scale * ldv(D.g + (size_t)(K + r) * p.C + c) / (__ldg(sums + (size_t)(K + r) * (p.C + 1) + p.C) + nadd);
                         t = gr - gb;
                     } else {
                         t = gr;
                     }
                 } else if (row - 1 < Q) {
-                    t = (D.scale_dev ? __ldg(D.scale_dev) : 1.f) * __ldg(D.xtab + (size_t)(row - 1 - QW) * p.C + c);
+                    t = (D.scale_dev ? __ldg(D.scale_dev) : 1.f) * ldv(D.xtab + (size_t)(row - 1 - QW) * p.C + c);
                 }
             }
             T[row * kBwdSpan + j] = t;
@@ -142,11 +153,15 @@ __global__ void __launch_bounds__(kThreads, bwd_min_blocks(QT)) bwd_finish_kerne
     if ((int)blockIdx.x < n_fin) {
         kernel_begin(TR_DISC_FIN);
         disc_finish_body(f, blockIdx.x, n_fin);
+        if (p.gate) cta_signal(p.gate, nullptr);
         trace_exit(TR_DISC_FIN);
     } else {
-        kernel_begin(p.trace_id);
-        pool_bwd_body<QT, VEC>(p, blockIdx.x - n_fin);
-        trace_exit(p.trace_id);
+        // merged launch (two domains): target CTAs first, then the gated source CTAs; each keeps its own trace slot
+        const int bid = blockIdx.x - n_fin;
+        const int tr = p.ndom > 1 ? (bid >= p.dom[0].ctas ? TR_BWD_S : TR_BWD_T) : p.trace_id;
+        kernel_begin(tr);
+        pool_bwd_body<QT, VEC>(p, bid);
+        trace_exit(tr);
     }
 }
 
@@ -164,7 +179,7 @@ static int launch_bwd(const BwdParams& p, bool vec4, int ctas, cudaStream_t st, 
 }
 
 int pool_bwd_impl(const BwdDom* doms, int ndom, int C, int HW, int K, cudaStream_t st, const DiscFinishParams* fin = nullptr,
-                  int trace_id = TR_BWD_BOTH) {
+                  int trace_id = TR_BWD_BOTH, unsigned int* gate = nullptr, int gate_dom = 0, float* gate_err = nullptr) {
     CLR_CHECK_ARG(ndom >= 1 && ndom <= 2 && C > 0 && HW > 0 && K >= 1 && K <= CLR_MAX_K);
     bool vec4 = (HW % 4 == 0);
     int Qmax = 0;
@@ -182,6 +197,7 @@ int pool_bwd_impl(const BwdDom* doms, int ndom, int C, int HW, int K, cudaStream
     BwdParams p{};
     p.trace_id = trace_id;
     p.ndom = ndom; p.C = C; p.HW = HW; p.K = K;
+    if (gate && fin) { p.gate = gate; p.gate_n = (unsigned int)disc_finish_ctas(fin->C); p.gate_dom = gate_dom; p.gate_err = gate_err; }
     const int pxb = kThreads * (vec4 ? 4 : 1);
     p.nPx = (HW + pxb - 1) / pxb;
     p.nSpan = (C + kBwdSpan - 1) / kBwdSpan;
@@ -211,6 +227,19 @@ int pool_bwd_one(const clr_bwd_dom* dom, int C, int HW, int K, const DiscFinishP
     BwdDom d{dom->w, dom->g, dom->sums, dom->xcoef, dom->xtab, dom->grad, dom->scale_dev, dom->scale, dom->fmt, dom->B, dom->Kx,
              0, 2 * K, 0, 0.f};
     return pool_bwd_impl(&d, 1, C, HW, K, st, f, source ? TR_BWD_S : TR_BWD_T);
+}
+
+// [disc finish | gradient of `first` | gradient of `gated`] in ONE launch: the CTAs of `gated` (the source features, whose
+// table needs the finish's output) wait on `gate`, a counter zeroed earlier in the same step (step.cu).
+int pool_bwd_merged(const clr_bwd_dom* first, const clr_bwd_dom* gated, int C, int HW, int K, const DiscFinishParams* f,
+                    unsigned int* gate, float* gate_err, cudaStream_t st) {
+    if (!first || !gated || !f || !gate) return CLR_ERR_BAD_ARG;
+    BwdDom d[2];
+    const clr_bwd_dom* src[2] = {first, gated};
+    for (int i = 0; i < 2; ++i)
+        d[i] = BwdDom{src[i]->w, src[i]->g, src[i]->sums, src[i]->xcoef, src[i]->xtab, src[i]->grad, src[i]->scale_dev,
+                      src[i]->scale, src[i]->fmt, src[i]->B, src[i]->Kx, 0, 2 * K, 0, 0.f};
+    return pool_bwd_impl(d, 2, C, HW, K, st, f, TR_BWD_BOTH, gate, 1, gate_err);
 }
 
 }  // namespace clr

@@ -359,8 +359,16 @@ int clr_step_run(const clr_step_args* a, clr_stream_t stream) {
     clr::bwd_doms(a, dd);
     cudaStream_t s0 = static_cast<cudaStream_t>(stream);
     if (a->ev_bwd_begin) cudaEventRecord(static_cast<cudaEvent_t>(a->ev_bwd_begin), s0);
-    rc = clr::pool_bwd_one(&dd[1], a->C, a->H * a->W, a->K, &df, false, s0);
-    if (rc == CLR_OK) rc = clr::pool_bwd_one(&dd[0], a->C, a->H * a->W, a->K, nullptr, true, s0);
+    if (!clr::tunables().bwd_merge_off) {
+        // ONE launch: [disc finish | gradient of xt | gradient of xs]; the source CTAs are dispatched after the ~1000 target
+        // CTAs and wait on the 4th counter word (zeroed by this step's pooling kernel, bumped by every finish CTA)
+        const clr::StepWs w = clr::carve(a);
+        unsigned int* counter = reinterpret_cast<unsigned int*>(w.fin + (size_t)clr::pool_finish_ctas(a->C) * (2 + CLR_MAX_K));
+        rc = clr::pool_bwd_merged(&dd[1], &dd[0], a->C, a->H * a->W, a->K, &df, counter + 3, a->losses + 7, s0);
+    } else {
+        rc = clr::pool_bwd_one(&dd[1], a->C, a->H * a->W, a->K, &df, false, s0);
+        if (rc == CLR_OK) rc = clr::pool_bwd_one(&dd[0], a->C, a->H * a->W, a->K, nullptr, true, s0);
+    }
     if (a->ev_bwd_end) cudaEventRecord(static_cast<cudaEvent_t>(a->ev_bwd_end), s0);
     if (rc != CLR_OK) return rc;
     if (a->use_cons && a->w_aug != 0.f && a->g_oT_aug) {
