@@ -349,7 +349,7 @@ int clr_step_fwd_c(const clr_step_args* a, clr_stream_t stream);
 int clr_step_fwd(const clr_step_args* a, clr_stream_t stream);
 int clr_step_bwd(const clr_step_args* a, clr_stream_t stream);
 /* Forward AND backward in one call, for the common case that the step total enters the training loss with a known
- * (device-side, `gup`, default 1) coefficient: 7 launches; the two finish stages ride as the first CTAs of the
+ * (device-side, `gup`, default 1) coefficient: 6 launches; the two finish stages ride as the first CTAs of the
  * consistency pass / the target-gradient write.  Results are identical to clr_step_fwd + clr_step_bwd. */
 int clr_step_run(const clr_step_args* a, clr_stream_t stream);
 

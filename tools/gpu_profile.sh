@@ -14,6 +14,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 echo "ncu launch list rc=$?"
 # full capture of the streaming kernels (one launch each of the last step)
 $SMALL > $OUT/plain2_${TAG}.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:'pool_fwd_ldg|pool_fwd_tma|pool_bwd_kernel|bwd_finish|disc_fused|mc_stats|pool_finish_cons|retrify' -s 21 -c 7 -o $OUT/prof_${TAG} -f $SMALL > $OUT/ncu_full_${TAG}.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'pool_fwd_ldg|pool_fwd_tma|pool_bwd_kernel|bwd_finish|disc_fused|mc_stats|pool_finish_cons|retrify' -s 18 -c 6 -o $OUT/prof_${TAG} -f $SMALL > $OUT/ncu_full_${TAG}.log 2>&1
 echo "ncu full rc=$?"
 ls -la $OUT | tail -20
