@@ -53,6 +53,7 @@ int clr_set_tunable(const char* name, int value) {
     else if (!strcmp(name, "mc_fuse")) t.mc_fuse = value;
     else if (!strcmp(name, "mc_generic")) t.mc_generic = value;
     else if (!strcmp(name, "bwd_merge_off")) t.bwd_merge_off = value;
+    else if (!strcmp(name, "fin_early_off")) t.fin_early_off = value;
     else if (!strcmp(name, "mc_split")) t.mc_split = value;
     else return CLR_ERR_BAD_ARG;
     return CLR_OK;

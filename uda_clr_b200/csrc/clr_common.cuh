@@ -37,6 +37,7 @@ struct Tunables {
     int mc_precise;    // 1 = ATen-exact sigmoids in clr_mc_stats (slower), 0 = fast intrinsics
     int finish_off;    // 1 = single-GPU step uses the separate reduce / finalize kernels instead of the merged finish kernels
     int hfuse_off;     // 1 = finish bodies get launches of their own instead of riding with cons / the target-gradient write
+    int fin_early_off; // 1 = the pooling finish releases the discriminative kernel only at its very end (after the last-CTA combine)
     int bwd_merge_off; // 1 = clr_step_run writes the two gradient maps with two launches ([finish | xt], then xs) instead of one
     int mc_generic;    // 1 = clr_mc_stats does not use the T == 8 specialisation (A/B runs)
     int mc_fuse;       // 1 = the fused step uses the one-pass mc_retrify kernel instead of mc_stats + retrify_weights

@@ -142,6 +142,7 @@ struct PoolFinishParams {
     PeerXchg x;                // world > 1: sum the packed sums over the ranks before the finalize arithmetic
     unsigned int* done_fin;    // optional completion counters (cta_signal): finish CTAs only / every CTA of the launch
     unsigned int* done_all;
+    int early_signal;          // 1: done_fin is bumped before the last-CTA combine (the consumer sums beta itself), 0: at the CTA's end
     int write_total;           // alignment-only step (no discriminative / consistency term): the last CTA also writes the totals
 };
 static inline int pool_finish_ctas(int C) { return (C + 7) / 8; }
@@ -156,6 +157,17 @@ __device__ __forceinline__ void pool_finish_body(const PoolFinishParams& p, cons
     __shared__ float Nn[2][2 * CLR_MAX_K];
     __shared__ double lp[8 * CLR_MAX_K][NL];
     __shared__ bool is_last;
+    // the stored (EMA) prototypes of this thread's (class, channel) entries: issued before the slot sums, which they do not
+    // depend on, so the chain below has one L2 round trip less
+    float st_pre[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+    if (tid < K * 8 && cta * 8 + (tid & 7) < C) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const size_t e = (size_t)((tid >> 3) + h * K) * C + cta * 8 + (tid & 7);
+            if (!p.first[0]) st_pre[0][h] = __ldcg(p.stored[0] + e);
+            if (!p.first[1]) st_pre[1][h] = __ldcg(p.stored[1] + e);
+        }
+    }
     for (int pair = warp; pair < 2 * R; pair += kWarps) {
         const int d = pair / R, r = pair - d * R;
         const float* part = p.partial[d];
@@ -206,8 +218,8 @@ __device__ __forceinline__ void pool_finish_body(const PoolFinishParams& p, cons
                 const size_t e = (size_t)rr * C + cc;
                 const float cs = S[0][rr][j] / Nn[0][rr];                         // utils/Utils.py:127-130
                 const float ct = S[1][rr][j] / Nn[1][rr];
-                ps[h] = p.first[0] ? cs : __fadd_rn(__fmul_rn(omd, p.stored[0][e]), __fmul_rn(dd, cs));
-                pt[h] = p.first[1] ? ct : __fadd_rn(__fmul_rn(omd, p.stored[1][e]), __fmul_rn(dd, ct));
+                ps[h] = p.first[0] ? cs : __fadd_rn(__fmul_rn(omd, st_pre[0][h]), __fmul_rn(dd, cs));
+                pt[h] = p.first[1] ? ct : __fadd_rn(__fmul_rn(omd, st_pre[1][h]), __fmul_rn(dd, ct));
                 p.P[0][e] = ps[h]; p.P[1][e] = pt[h];
                 p.stored[0][e] = ps[h]; p.stored[1][e] = pt[h];                  // .detach() copies (Trainer_prototype_full.py:341-344)
                 const double df = (double)ps[h] - (double)pt[h];
@@ -239,6 +251,11 @@ __device__ __forceinline__ void pool_finish_body(const PoolFinishParams& p, cons
         __threadfence();
     }
     __syncthreads();
+    // Flag dependency (clr_common.cuh): everything the discriminative kernel needs from THIS CTA is out now -- its slice of
+    // disc_vec and its loss partials (the kernel sums the per-class column itself, in the order used below) -- so the
+    // consumer is released here, before the last-CTA combine, which only serves the logged losses.  done_all (grid-completion
+    // transitivity) is still bumped at the very end of the CTA by the kernel wrapper.
+    if (p.done_fin && p.early_signal) cta_signal(p.done_fin, nullptr);
     if (tid == 0) {
         const unsigned prev = atomicAdd(p.counter, 1u);
         is_last = (prev == (unsigned)ncta - 1u);

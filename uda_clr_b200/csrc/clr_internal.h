@@ -20,6 +20,7 @@ struct DiscFlagDep {   // flag dependency on the preceding [finish | consistency
     const unsigned int* wait_fin; const unsigned int* wait_all;
     unsigned int wait_fin_n, wait_all_n;
     float* err;
+    const double* beta_partial;   // the finish CTAs' loss partials ([wait_fin_n][2 + CLR_MAX_K]): the kernel sums beta itself
 };
 int disc_fused_impl(const float* xs, const float* ys, int B, int C, int HW, int K,
                     const float* disc_vec, const float* disc_beta, float margin,

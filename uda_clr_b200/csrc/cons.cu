@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(kConsThreads, 3) pool_finish_cons_kernel(const
     if ((int)blockIdx.x < n_fin) {
         if (flag_producer) kernel_begin_late_trigger(TR_ALIGN); else kernel_begin(TR_ALIGN);
         pool_finish_body(f, blockIdx.x, n_fin);
-        if (f.done_fin) cta_signal(f.done_fin, f.done_all);
+        if (f.done_all) cta_signal(f.early_signal ? nullptr : f.done_fin, f.done_all);   // (early: done_fin was bumped inside the body)
         trace_exit(TR_ALIGN);
     } else {
         if (flag_producer) kernel_begin_late_trigger(TR_CONS); else kernel_begin(TR_CONS);

@@ -55,6 +55,9 @@ struct DiscParams {
     const unsigned int* wait_fin; const unsigned int* wait_all;
     unsigned int wait_fin_n, wait_all_n;
     float* err;             // set to 1 if a wait times out
+    // with the flag dependency the per-class offsets are summed here from the finish CTAs' loss partials
+    // ([beta_nparts][2 + CLR_MAX_K] doubles, column 2 + k), in pool_finish_body's own order -> the same float
+    const double* beta_partial; int beta_nparts;
 };
 
 constexpr int kDiscPad = 4;
@@ -186,7 +189,16 @@ __global__ void __launch_bounds__(NT, (TP == 32 && STAGES <= 4) ? 2 : 1) disc_fu
         __syncthreads();
     }
     for (int i = tid; i < K * p.C; i += NT) Vs[i] = __ldcg(p.V + i);
-    if (tid < K) betas[tid] = __ldcg(p.beta + tid);
+    if (p.beta_partial) {
+        if (warp < K) {      // K <= 8 = warps of the 256-thread CTA
+            double t = 0.0;
+            for (int bb = lane; bb < p.beta_nparts; bb += 32) t += __ldcg(p.beta_partial + (size_t)bb * (2 + CLR_MAX_K) + 2 + warp);
+            t = warp_sum(t);
+            if (lane == 0) betas[warp] = (float)(t * (1.0 / (double)p.C));
+        }
+    } else if (tid < K) {
+        betas[tid] = __ldcg(p.beta + tid);
+    }
     __syncthreads();
     int stage = 0;
     uint32_t phase = 0;
@@ -550,7 +562,10 @@ int disc_fused_impl(const float* xs, const float* ys, int B, int C, int HW, int 
     p.xs = xs; p.ys = ys; p.V = disc_vec; p.beta = disc_beta; p.coef = coef; p.delta = delta;
     p.partial = partial; p.hinge = hinge; p.alpha = -2.0f / (float)C; p.margin = margin;
     p.B = B; p.C = C; p.HW = HW;
-    if (dep) { p.wait_fin = dep->wait_fin; p.wait_all = dep->wait_all; p.wait_fin_n = dep->wait_fin_n; p.wait_all_n = dep->wait_all_n; p.err = dep->err; }
+    if (dep) {
+        p.wait_fin = dep->wait_fin; p.wait_all = dep->wait_all; p.wait_fin_n = dep->wait_fin_n; p.wait_all_n = dep->wait_all_n; p.err = dep->err;
+        p.beta_partial = dep->beta_partial; p.beta_nparts = (int)dep->wait_fin_n;
+    }
     // "disc_tile" tunable: 0 auto (32-pixel tiles, two CTAs per SM), 64 = 64-pixel tiles, one CTA per SM
     int n = *nparts;
     int rc = CLR_ERR_UNSUPPORTED;

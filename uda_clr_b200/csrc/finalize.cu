@@ -176,7 +176,7 @@ int disc_finalize_impl(float* packed2, const float* P_s, int K, int C, double np
 __global__ void __launch_bounds__(kThreads) pool_finish_kernel(const PoolFinishParams p) {
     if (p.done_fin) kernel_begin_late_trigger(TR_ALIGN); else kernel_begin(TR_ALIGN);
     pool_finish_body(p, blockIdx.x, gridDim.x);
-    if (p.done_fin) cta_signal(p.done_fin, p.done_all);
+    if (p.done_all) cta_signal(p.early_signal ? nullptr : p.done_fin, p.done_all);   // (early: done_fin was bumped inside the body)
     trace_exit(TR_ALIGN);
 }
 __global__ void __launch_bounds__(kThreads) disc_finish_kernel(const DiscFinishParams p) {

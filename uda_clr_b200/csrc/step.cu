@@ -245,7 +245,7 @@ static int step_fwd_core(const clr_step_args* a, cudaStream_t st, DiscFinishPara
     // completion counters right behind the last-CTA counter (all three zeroed by the pooling kernel): the discriminative
     // kernel waits for the finish CTAs only, not for the grid (and its end-of-grid flush) they ride in
     const bool flag_dep = a->use_disc && tunables().disc_impl != 1 && !tunables().flag_dep_off;
-    if (flag_dep) { pf.done_fin = counter + 1; pf.done_all = counter + 2; }
+    if (flag_dep) { pf.done_fin = counter + 1; pf.done_all = counter + 2; pf.early_signal = tunables().fin_early_off ? 0 : 1; }
     const bool align_only = !a->use_disc && !a->use_cons;      // the shipped trainer's step: totals come from the finish itself
     pf.write_total = align_only ? 1 : 0;
     int n_cons = 0;
@@ -268,7 +268,7 @@ static int step_fwd_core(const clr_step_args* a, cudaStream_t st, DiscFinishPara
         float* hinge = partial + (size_t)320 * K * (C + 1);   // layout of clr_disc_fused_ws_bytes: [320][K][C+1] | [320]
         int n_hinge = 320;
         // (a separate consistency launch sits between the finish launch and this kernel when hfuse_off: plain wait then)
-        DiscFlagDep dep{counter + 1, counter + 2, (unsigned int)pool_finish_ctas(C), producers, a->losses + 7};
+        DiscFlagDep dep{counter + 1, counter + 2, (unsigned int)pool_finish_ctas(C), producers, a->losses + 7, tunables().fin_early_off ? nullptr : w.fin};
         const bool use_dep = flag_dep && !(a->use_cons && tunables().hfuse_off);
         rc = disc_fused_impl(a->xs, a->ys, a->B_s, C, HW, K, a->disc_vec, a->disc_beta, a->margin,
                              a->disc_coef, nullptr, partial, hinge, &n_hinge, st, use_dep ? &dep : nullptr);
