@@ -54,6 +54,24 @@ def test_argument_validation_without_gpu(lib):
     assert lib.clr_proto_finalize(None, 4, 8, None, None) == -1
 
 
+def test_transnorm_argument_validation_without_gpu(lib):
+    # clr_tn_*: workspace query and argument checks return before any CUDA call
+    assert lib.clr_tn_ws_bytes(305) > 0 and lib.clr_tn_ws_bytes(0) == 0
+    assert lib.clr_tn_fwd(None, 4, 8, 16, None, None, None, None, None, None, 0.1, 1e-5, None, 0, None, None, None) == -1
+    assert lib.clr_tn_bwd(None, None, 4, 8, 16, None, None, 0, None, 0, None, None, None, None) == -1
+    assert lib.clr_tn_eval(None, 4, 8, 16, None, None, None, None, None, None, 1e-5, None, 0, None, None, None) == -1
+
+
+def test_transnorm_module_refuses_cpu_tensors():
+    import torch
+    from uda_clr_b200 import TransNorm2d
+    m = TransNorm2d(4)
+    assert list(m.state_dict()) == ["weight", "bias", "running_mean_source", "running_var_source", "running_mean_target",
+                                    "running_var_target", "num_batches_tracked"]
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.randn(2, 4, 8, 8))
+
+
 def test_ops_refuse_cpu_tensors():
     import torch
     import uda_clr_b200 as clr
