@@ -1,4 +1,4 @@
-"""Host-side cost of enqueueing one fused CLR step (CLRPlan.run: ONE C call, 7 kernel launches) on a tiny problem, so the
+"""Host-side cost of enqueueing one fused CLR step (CLRPlan.run: ONE C call, 6 kernel launches) on a tiny problem, so the
 GPU is never the bottleneck.  Measured on the B200 box: ~25 us of host time per step against 178 us of device time at
 the bench size -- the step is device-bound with a wide margin."""
 import os
@@ -23,4 +23,4 @@ for _ in range(n): plan.run()
 t1 = time.perf_counter()
 torch.cuda.synchronize()
 t2 = time.perf_counter()
-print("host enqueue per step: %.1f us (7 launches); drained after %.1f us more per step" % ((t1 - t0) / n * 1e6, (t2 - t1) / n * 1e6))
+print("host enqueue per step: %.1f us (6 launches); drained after %.1f us more per step" % ((t1 - t0) / n * 1e6, (t2 - t1) / n * 1e6))
