@@ -92,6 +92,8 @@ def pool_backward_weights(feat: torch.Tensor, fmt: int, K: int, g: torch.Tensor,
 
 
 def _stack_grads(grads: Sequence[Optional[torch.Tensor]], R: int, C: int, device) -> torch.Tensor:
+    if all(gr is not None for gr in grads[:R]):      # the usual case (all 2K prototypes enter the loss): one launch, not 1 + R
+        return torch.cat([gr.reshape(1, C) for gr in grads[:R]], 0).to(torch.float32).contiguous()
     g = torch.zeros(R, C, dtype=torch.float32, device=device)
     for r, gr in enumerate(grads[:R]):
         if gr is not None:
