@@ -19,7 +19,7 @@ def _case(shape, seed, hard=True):
     return x, y
 
 
-@settings(max_examples=40, deadline=None)
+@settings(max_examples=40, deadline=None, derandomize=True)
 @given(shapes, st.integers(0, 2 ** 31 - 1))
 def test_pool_sums_permutation_invariant_and_linear(shape, seed):
     x, y = _case(shape, seed, hard=False)
@@ -39,7 +39,7 @@ def test_pool_sums_permutation_invariant_and_linear(shape, seed):
     assert np.allclose(S4, 2.5 * S + N[:, None], rtol=1e-11, atol=1e-11)
 
 
-@settings(max_examples=40, deadline=None)
+@settings(max_examples=40, deadline=None, derandomize=True)
 @given(shapes, st.integers(0, 2 ** 31 - 1), st.integers(1, 3))
 def test_shard_and_sum_equals_whole_batch(shape, seed, nshard):
     x, y = _case(shape, seed)
@@ -52,7 +52,7 @@ def test_shard_and_sum_equals_whole_batch(shape, seed, nshard):
     assert np.array_equal(N, Ns)                 # hard labels: exact integers
 
 
-@settings(max_examples=40, deadline=None)
+@settings(max_examples=40, deadline=None, derandomize=True)
 @given(shapes, st.integers(0, 2 ** 31 - 1))
 def test_hard_label_counts_are_exact_and_complementary(shape, seed):
     x, y = _case(shape, seed)
@@ -63,7 +63,7 @@ def test_hard_label_counts_are_exact_and_complementary(shape, seed):
     assert np.array_equal(N[:K], y.sum(axis=(0, 2, 3)))
 
 
-@settings(max_examples=30, deadline=None)
+@settings(max_examples=30, deadline=None, derandomize=True)
 @given(shapes, st.integers(0, 2 ** 31 - 1))
 def test_pool_backward_is_the_adjoint(shape, seed):
     """<g, d mu(x)[dx]> == <pool_backward(g), dx> (finite difference of the prototypes along a random direction)."""
@@ -84,10 +84,11 @@ def test_pool_backward_is_the_adjoint(shape, seed):
 
 
 # ---- TransNorm (8(f) rank 4): the laws tests/test_gpu_transnorm.py relies on at full size
-tn_shapes = st.tuples(st.integers(2, 6), st.integers(1, 6), st.integers(2, 5), st.integers(1, 5))
+# at least 8 values per (half, channel): with 2-3 values the variance can be ~eps and the central differences below lose their footing
+tn_shapes = st.tuples(st.integers(2, 6), st.integers(1, 6), st.integers(3, 5), st.integers(3, 5))
 
 
-@settings(max_examples=40, deadline=None)
+@settings(max_examples=40, deadline=None, derandomize=True)
 @given(tn_shapes, st.integers(0, 2 ** 31 - 1))
 def test_transnorm_normalises_each_half_and_alpha_sums_to_c(shape, seed):
     B, C, H, W = shape
@@ -113,7 +114,7 @@ def test_transnorm_normalises_each_half_and_alpha_sums_to_c(shape, seed):
     assert np.allclose(fp["alpha"], fw["alpha"], rtol=1e-10)
 
 
-@settings(max_examples=30, deadline=None)
+@settings(max_examples=30, deadline=None, derandomize=True)
 @given(tn_shapes, st.integers(0, 2 ** 31 - 1))
 def test_transnorm_backward_is_the_adjoint(shape, seed):
     """<gy, J dx> == <J^T gy, dx> with alpha held constant, by central differences of the forward with frozen alpha."""
