@@ -238,3 +238,50 @@ def test_transnorm_oracle_and_port_vs_reference(shape):
     m32.eval()
     with torch.no_grad():
         assert torch.equal(m32(x), TP.trans_norm(x, w, b, *bufs, False, 0.1, 1e-5))
+
+
+# ---- K > 2: the reference is hard-wired to two classes; class k's prototypes depend on channel k only, so the K-class
+# oracle / port must equal the reference applied to channel PAIRS
+def test_k4_generalisation_equals_reference_on_channel_pairs():
+    K = 4
+    g = torch.Generator().manual_seed(31)
+    B, C, H, W = 2, 7, 12, 10
+    y = synth.nested_ellipse_labels(B, K, H, W, g)
+    x = synth.class_shifted_features(y, C, g)
+    soft = torch.sigmoid(synth.confident_logits(y, g))
+    for pred in (y, soft):
+        ours = O.gen_prototype(pred.numpy(), x.numpy())                       # rows obj_0..obj_3, bck_0..bck_3
+        port = _stack(TP.gen_prototype(pred, x))
+        for pair in ((0, 1), (2, 3), (3, 0)):
+            ref = _stack(ref_import.ref_gen_prototype(pred[:, list(pair)].contiguous(), x))   # (c0_obj, c1_obj, c0_bck, c1_bck)
+            rows = [pair[0], pair[1], K + pair[0], K + pair[1]]
+            assert relerr(ours[rows], ref) < 2e-6
+            assert np.array_equal(port[rows], ref)                            # same ATen sequence: bit for bit
+
+
+def test_k4_retrify_equals_reference_on_channel_pairs():
+    """A2 at K = 4 (B = 1, 128 x 128 features as the reference hard-codes, T = 3): std_map, masks and prototypes of classes
+    (2, 3) from the K-class oracle / port against the reference run on that channel pair."""
+    K, T, B, C, Hi = 4, 3, 1, 3, 144
+    g = torch.Generator().manual_seed(41)
+    yt = synth.nested_ellipse_labels(B, K, 128, 128, g)
+    xt = synth.class_shifted_features(yt, C, g)
+    oT = synth.confident_logits(yt, g)
+    base = torch.nn.functional.interpolate(oT, size=(Hi, Hi), mode="nearest")
+    preds = base.repeat(T, 1, 1, 1) + 0.35 * torch.randn(T * B, K, Hi, Hi, generator=g)
+    ours = O.gen_prototype_retrify(oT.numpy(), xt.numpy(), preds.numpy(), T, B)
+    port = TP.gen_prototype_retrify(oT, xt, preds, None, T, B)
+    for pair in ((2, 3), (0, 1)):
+        sel = list(pair)
+        ref = ref_import.ref_gen_prototype_retrify(oT[:, sel].contiguous(), xt, preds[:, sel].contiguous(), T, B)
+        assert relerr(ours["std_map"][:, sel], ref[4].numpy()) < 5e-6
+        rows = [pair[0], pair[1], K + pair[0], K + pair[1]]
+        masks_ref = (ref[5].numpy(), ref[6].numpy())
+        same = all(np.array_equal(ours["masks"][:, k:k + 1], m) for k, m in zip(pair, masks_ref))
+        assert same, "seeded case is expected to have no |std_small - 0.04| knife edge"
+        assert 0.02 < float((masks_ref[0] > 0).mean()) < 0.98      # both mask states exercised
+        assert relerr(ours["protos"][rows], _stack(ref[:4])) < 1e-5
+        # port: same ATen sequence generalised over K -> bit for bit
+        assert np.array_equal(_stack(port[:2 * K])[rows], _stack(ref[:4]))
+        assert torch.equal(port[2 * K][:, sel], ref[4])
+        assert torch.equal(port[2 * K + 1 + pair[0]], ref[5]) and torch.equal(port[2 * K + 1 + pair[1]], ref[6])
