@@ -285,3 +285,37 @@ def test_k4_retrify_equals_reference_on_channel_pairs():
         assert np.array_equal(_stack(port[:2 * K])[rows], _stack(ref[:4]))
         assert torch.equal(port[2 * K][:, sel], ref[4])
         assert torch.equal(port[2 * K + 1 + pair[0]], ref[5]) and torch.equal(port[2 * K + 1 + pair[1]], ref[6])
+
+
+# ---- 8(f) rank 3: validation metrics (utils/metrics.py:81-168) from exact integer confusion counts
+def test_metrics_from_counts_equal_reference_metrics():
+    """``dice_from_counts`` / ``pixel_acc_from_counts`` (host-side formulas over the [K, 4] counts that ``clr_seg_counts``
+    produces on the device) against the reference's ``dice_coeff_2label`` and ``pixel_acc`` on the same logits / labels."""
+    import sys
+    from uda_clr_b200 import ops
+    ref_import.load_utils()
+    M = sys.modules["utils.metrics"]
+    had = hasattr(np, "bool")
+    if not had:
+        np.bool = bool            # the reference predates numpy 1.24 (utils/metrics.py:85-86 use np.bool)
+    try:
+        g = torch.Generator().manual_seed(77)
+        B, K, H, W = 3, 2, 40, 36
+        target = synth.nested_ellipse_labels(B, K, H, W, g)
+        logits = 2.5 * torch.randn(B, K, H, W, generator=g) + 2.0 * (2 * target - 1)
+        d_cup, d_disc = M.dice_coeff_2label(logits.clone(), target.clone())
+        pa_cup, pa_disc, iou_cup, iou_disc = M.pixel_acc(logits.clone(), target.clone())
+    finally:
+        if not had:
+            del np.bool
+    pred = (torch.sigmoid(logits) > 0.75)
+    gt = target != 0
+    counts = torch.zeros(K, 4, dtype=torch.int64)
+    for k in range(K):
+        idx = (2 * gt[:, k].long() + pred[:, k].long()).flatten()
+        counts[k] = torch.bincount(idx, minlength=4)
+    dice = ops.dice_from_counts(counts)
+    pa, miou = ops.pixel_acc_from_counts(counts)
+    assert abs(float(dice[0]) - d_cup) < 1e-15 and abs(float(dice[1]) - d_disc) < 1e-15
+    assert abs(float(pa[0]) - pa_cup) < 1e-15 and abs(float(pa[1]) - pa_disc) < 1e-15
+    assert abs(float(miou[0]) - iou_cup) < 1e-15 and abs(float(miou[1]) - iou_disc) < 1e-15
