@@ -319,3 +319,33 @@ def test_metrics_from_counts_equal_reference_metrics():
     assert abs(float(dice[0]) - d_cup) < 1e-15 and abs(float(dice[1]) - d_disc) < 1e-15
     assert abs(float(pa[0]) - pa_cup) < 1e-15 and abs(float(pa[1]) - pa_disc) < 1e-15
     assert abs(float(miou[0]) - iou_cup) < 1e-15 and abs(float(miou[1]) - iou_disc) < 1e-15
+
+
+# ---- A7 / A8: the Trainer_prototype.py helper methods (98-123), called unbound on a stand-in ``self``
+def test_distance_weight_and_single_vector_ema_vs_trainer_prototype_methods():
+    import sys
+    import types
+    ref_import.load_utils()
+    sys.modules.setdefault("pytz", types.ModuleType("pytz"))
+    import train_process.Trainer_prototype as TPR
+    g = torch.Generator().manual_seed(5)
+    N, C, H, W = 2, 11, 6, 7
+    feat = torch.randn(N, C, H, W, generator=g)
+    proto = torch.randn(C, generator=g)
+    me = types.SimpleNamespace(objective_vectors={"cup": proto.clone()})
+    me.feat_prototype_distance = types.MethodType(TPR.Trainer.feat_prototype_distance, me)
+    d_ref = TPR.Trainer.feat_prototype_distance(me, feat, proto, 1)
+    w_ref = TPR.Trainer.get_prototype_weight(me, feat, 1, "cup")
+    assert relerr(O.feat_prototype_distance(feat.numpy(), proto.numpy()), d_ref[:, 0].numpy()) < 1e-6
+    assert relerr(O.distance_weight(feat.numpy(), proto.numpy()), w_ref[:, 0].numpy()) < 2e-6
+    assert torch.equal(TP.feat_prototype_distance(feat, proto, 1), d_ref) and torch.equal(TP.distance_weight(feat, proto, 1), w_ref)
+    # 0.001-EMA of the stored vectors, skipped when the new vector sums to zero (:117-123)
+    v = torch.randn(1, C, generator=g)
+    TPR.Trainer.update_objective_SingleVector(me, "cup", v)
+    assert relerr(O.ema_single_vector(proto.numpy(), v.numpy().reshape(-1)), me.objective_vectors["cup"].numpy()) < 1e-7
+    from uda_clr_b200 import ops
+    assert torch.allclose(ops.update_objective_single_vector(proto, v), me.objective_vectors["cup"], rtol=0, atol=1e-7)
+    before = me.objective_vectors["cup"].clone()
+    TPR.Trainer.update_objective_SingleVector(me, "cup", torch.zeros(1, C))
+    assert torch.equal(me.objective_vectors["cup"], before)
+    assert torch.equal(ops.update_objective_single_vector(before, torch.zeros(1, C)), before)
