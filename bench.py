@@ -45,7 +45,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="clr3", choices=["clr3", "align"])
+    ap.add_argument("--workload", default="clr3", choices=["clr3", "align", "dropin"])
     ap.add_argument("--B", type=int, default=8, help="per-GPU batch of each domain")
     ap.add_argument("--C", type=int, default=256)
     ap.add_argument("--H", type=int, default=128)
@@ -54,6 +54,8 @@ def parse():
     ap.add_argument("--up", type=int, default=4, help="image resolution / feature resolution")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity block (first two steps vs the eager port on the same GPU)")
+    ap.add_argument("--no-gpu-eager", action="store_true", help="skip timing the eager port on the same GPU (second baseline)")
     ap.add_argument("--cpu-budget-s", type=float, default=25.0)
     ap.add_argument("--tunable", action="append", default=[], help="library knob name=value (clr_set_tunable)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
@@ -63,22 +65,41 @@ def parse():
 
 # ------------------------------------------------------------------------------------------------- byte model
 def algorithmic_bytes(a) -> dict:
-    """SURVEY.md 8(d) / BASELINE.md 3: the minimal traffic of each stage, per step and per GPU."""
+    """the ALGORITHMIC traffic of each stage per step and per GPU -- what `roofline` is computed from.
+    F = one fp32 pass over one feature map, Lb = one pass over a [B,K,H,W] plane set, Li = the same at image resolution.
+      pooling fwd (hard labels)  F + Lb per domain          pooling bwd   F + Lb per domain (write grad + read labels)
+      retrify extras             T*Li (read preds) + Li (write std_map) + masks (Lb)
+      discriminative fwd         F + Lb (second read of xs); its backward rides in the gradient write (0 bytes)
+      consistency fwd            2*Li + Lb
+    clr3 at config 1: 4(F+Lb) + (T*Li + Li + Lb) + (F+Lb) + (2*Li+Lb) = 863 MB."""
     B, C, HW, K, T, up = a.B, a.C, a.H * a.H, a.K, a.T, a.up
     F = 4 * B * C * HW
     Lb = 4 * B * K * HW
     Li = 4 * B * K * HW * up * up
-    d = {}
+    d = {"pool_fwd": 2 * (F + Lb), "pool_bwd": 2 * (F + Lb)}
     if a.workload == "clr3":
-        d["mc_stats"] = T * Li + 2 * Li                       # read preds, write std_map + prediction
-        d["retrify_weights"] = Lb + 2 * Li // 4 + 3 * Lb      # logits + sampled taps in, 2K weights + masks out
-        d["pool_fwd"] = 2 * F + Lb + 2 * Lb                   # both feature maps + labels + explicit target weights
+        d["mc_stats"] = T * Li + Li + Lb
+        d["disc_fwd"] = F + Lb
         d["cons_fwd"] = 2 * Li + Lb
-        d["disc_fwd"] = F + Lb + Lb                           # second read of xs, labels in, coefficients out
-        d["pool_bwd"] = 2 * F + Lb + 2 * Lb + Lb              # both gradient maps + weight / coefficient planes
-    else:
-        d["pool_fwd"] = 2 * F + 2 * Lb
-        d["pool_bwd"] = 2 * F + 2 * Lb
+    d["total"] = sum(d.values())
+    return d
+
+
+def implementation_bytes(a) -> dict:
+    """What the kernels of THIS implementation move on top of the algorithmic minimum (reported separately, never used
+    for a roofline fraction): the full-resolution mean map that clr_mc_stats materialises for the bilinear taps, the
+    explicit 2K target weight planes, the coefficient planes of the discriminative term."""
+    B, C, HW, K, T, up = a.B, a.C, a.H * a.H, a.K, a.T, a.up
+    F = 4 * B * C * HW
+    Lb = 4 * B * K * HW
+    Li = 4 * B * K * HW * up * up
+    d = {"pool_fwd": 2 * F + Lb + (2 * Lb if a.workload == "clr3" else Lb),
+         "pool_bwd": 2 * F + Lb + (2 * Lb + Lb if a.workload == "clr3" else Lb)}
+    if a.workload == "clr3":
+        d["mc_stats"] = T * Li + 2 * Li
+        d["retrify_weights"] = Lb + 2 * Li // 4 + 3 * Lb
+        d["cons_fwd"] = 2 * Li + Lb
+        d["disc_fwd"] = F + Lb + Lb
     d["total"] = sum(d.values())
     return d
 
@@ -187,10 +208,200 @@ def run_reference_cpu(a, steps: int, warmup: int, budget_s: float):
                 torch_threads=torch.get_num_threads(), steps=steps, warmup=warmup)
 
 
+# ------------------------------------------------------------------------------------------------- parity / second baseline
+TOL = {"loss": 1e-4, "proto": 1e-5, "grad": 1e-4}      # BASELINE.json north_star / SURVEY.md 8(d)
+
+
+def _rel(x, y):
+    return float((x - y).abs().max() / y.abs().max().clamp_min(1e-30))
+
+
+def run_parity(a, clr, synth, make_plans, host_batch, dev, rank, world, dist_on, use3, names):
+    """First two steps of a fresh EMA state through the benched call (``CLRPlan.run``), sharded like the timed steps,
+    against ``oracle/clr_torch_port.ClrStepPort`` -- the op-for-op eager restatement of the reference that
+    tests/test_oracle_vs_reference.py pins bit for bit on the imported reference -- run on the SAME GPU over the whole
+    (concatenated) batch.  The oracle is the checker here, never the thing measured."""
+    import torch
+    if dist_on:
+        import torch.distributed as dist
+    K = a.K
+    pstep = clr.CLRStep(K=K, retrify=use3, use_disc=use3, use_cons=use3, backprop_aug=False, global_batch=a.B * world)
+    pplans = make_plans(pstep)
+    snaps, cross = [], {"max_loss_diff": 0.0, "timeout_flag": 0.0}
+    for s_ in range(2):
+        pl = pplans[s_]
+        pl.run()
+        torch.cuda.synchronize()
+        o = pl.outputs()
+        lt = pl.losses.detach().clone()
+        if dist_on:
+            got = [torch.empty_like(lt) for _ in range(world)]
+            dist.all_gather(got, lt)
+            cross["max_loss_diff"] = max(cross["max_loss_diff"], max(float((g[:5] - got[0][:5]).abs().max()) for g in got))
+            cross["timeout_flag"] = max(cross["timeout_flag"], max(float(g[7]) for g in got))
+        else:
+            cross["timeout_flag"] = max(cross["timeout_flag"], float(lt[7]))
+        snaps.append(dict(losses=lt, Ps=torch.cat([p.reshape(1, -1) for p in o.source_prototypes]).clone(),
+                          Pt=torch.cat([p.reshape(1, -1) for p in o.target_prototypes]).clone(),
+                          gxs=pl.gxs.clone(), gxt=pl.gxt.clone(),
+                          masks=None if o.masks is None else torch.cat(o.masks, 1).clone()))
+    del pplans
+    if rank != 0:
+        return None
+    from oracle import clr_torch_port as TP
+    port = TP.ClrStepPort(retrify=use3, use_disc=use3, use_cons=use3, backprop_aug=False)
+    steps, ok = [], cross["timeout_flag"] == 0.0 and cross["max_loss_diff"] == 0.0
+    B = a.B
+    for s_ in range(2):
+        hb = [host_batch(r, s_) for r in range(world)]
+        g = {k: torch.cat([getattr(h, k) for h in hb], 0).to(dev) for k in names if k != "preds"}
+        if use3:
+            Hi = a.H * a.up
+            g["preds"] = torch.cat([h.preds.view(a.T, B, K, Hi, Hi) for h in hb], 1).reshape(a.T * B * world, K, Hi, Hi).to(dev)
+        xs, xt = g["xs"].clone().requires_grad_(True), g["xt"].clone().requires_grad_(True)
+        if use3:
+            res = port.step(xs, g["ys"], xt, g["oT_before"], preds=g["preds"], features=None, T=a.T, oT=g["oT"],
+                            oT_aug=g["oT_aug"], epoch=0.0)
+        else:
+            res = port.step(xs, g["ys"], xt, g["oT_before"])
+        sn = snaps[s_]
+        keys = ["intra", "inter"] + (["disc", "aug"] if use3 else [])
+        idx = {"intra": 0, "inter": 1, "disc": 2, "aug": 3}
+        loss_rel = {k: abs(float(sn["losses"][idx[k]]) - float(res[k])) / max(abs(float(res[k])), 1e-30) for k in keys}
+        if use3 or True:
+            tot_ref = float(res["total"])
+            loss_rel["total"] = abs(float(sn["losses"][4]) - tot_ref) / max(abs(tot_ref), 1e-30)
+        proto_rel = {"Ps": _rel(sn["Ps"], torch.cat([p.reshape(1, -1) for p in res["Ps"]])),
+                     "Pt": _rel(sn["Pt"], torch.cat([p.reshape(1, -1) for p in res["Pt"]]))}
+        # this rank's shard of the port's gradients; the sharded step scales its gradients by the world size (DDP averages)
+        gs_ref, gt_ref = xs.grad[:B] * world, xt.grad[:B] * world
+        bad = (sn["gxs"] - gs_ref).abs() > TOL["grad"] * gs_ref.abs().max()
+        grad = {"gxt_rel": _rel(sn["gxt"], gt_ref), "gxs_rel": _rel(sn["gxs"], gs_ref),
+                "gxs_pixels_above_tol_frac": float(bad.any(dim=1).float().mean())}
+        row = {"loss_rel": loss_rel, "proto_rel": proto_rel, "grad": grad}
+        if use3:
+            ref_masks = torch.cat(res["masks"], 1)[:B]
+            row["mask_mismatch_px"] = int((sn["masks"] != ref_masks).sum())
+            row["mask_px"] = int(ref_masks.numel())
+        steps.append(row)
+        # hinge-kink pixels (A9's gradient flips with the active set) are the only place gxs may exceed the tolerance:
+        # tests/test_gpu_step.py proves every such pixel sits on the kink; here their fraction must be vanishing
+        ok = ok and all(v < TOL["loss"] for v in loss_rel.values()) and all(v < TOL["proto"] for v in proto_rel.values()) \
+            and grad["gxt_rel"] < TOL["grad"] and (grad["gxs_rel"] < TOL["grad"] or grad["gxs_pixels_above_tol_frac"] < 1e-4) \
+            and row.get("mask_mismatch_px", 0) == 0
+        del xs, xt, g, res
+    torch.cuda.empty_cache()
+    return {"ok": bool(ok), "reference": "oracle/clr_torch_port.ClrStepPort (op-for-op eager restatement of the reference) on the same GPU, "
+                                         "global batch %d per domain; this rank's shard of masks / gradients" % (B * world),
+            "tolerances": dict(TOL, masks="bit-exact"), "steps": steps, "cross_rank": cross}
+
+
+def run_eager_gpu(a, devb, use3, n=5):
+    """BASELINE.md 4, second baseline: the reference's eager ATen op sequence for the same step on the same GPU."""
+    import torch
+    from oracle import clr_torch_port as TP
+    port = TP.ClrStepPort(retrify=use3, use_disc=use3, use_cons=use3, backprop_aug=False)
+    ts = []
+    for i in range(n + 2):
+        d = devb[i % len(devb)]
+        xs, xt = d["xs"].clone().requires_grad_(True), d["xt"].clone().requires_grad_(True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        if use3:
+            port.step(xs, d["ys"], xt, d["oT_before"], preds=d["preds"], features=None, T=a.T, oT=d["oT"], oT_aug=d["oT_aug"], epoch=0.0)
+        else:
+            port.step(xs, d["ys"], xt, d["oT_before"])
+        torch.cuda.synchronize()
+        ts.append(time.perf_counter() - t0)
+    med = statistics.median(ts[2:])
+    torch.cuda.empty_cache()
+    return {"value": 2 * a.B * a.H * a.H / med / 1e6, "unit": UNIT, "ms_per_step": med * 1e3, "steps": n,
+            "what": "oracle/clr_torch_port.ClrStepPort (the reference's eager op sequence, without its dead 1.28 GB mean(features)) "
+                    "on this GPU, wall clock around synchronised steps"}
+
+
+# ------------------------------------------------------------------------------------------------- drop-in workload
+def trainer_protocol_step(ops, st, d, T, decay=0.9, pro_weight=0.1):
+    """The CLR block exactly as the shipped trainer drives it (Trainer_prototype_full.py:330-449, ``retrify_pesudo``
+    branch): two calls into the prototype ops, the inline EMA (:335-355, :378-398), the inline MSE alignment /
+    separation losses (:428-444) and ``backward()`` of ``pro_weight * intra`` (:463-468).  ``ops`` is whatever module
+    provides ``gen_prototype`` / ``gen_prototype_retrify`` -- this package (the patched trainer) or the eager port."""
+    import torch
+    mse = torch.nn.MSELoss()
+    xs = d["xs"].detach().requires_grad_(True)
+    xt = d["xt"].detach().requires_grad_(True)
+    K = d["ys"].shape[1]
+    cur_s = ops.gen_prototype(d["ys"], xs)                                                   # :332-334
+    out = ops.gen_prototype_retrify(d["oT_before"], xt, d["preds"], None, T, xt.shape[0])    # :370-373
+    cur_t = out[:2 * K]
+    P = {}
+    for dom, cur in (("s", cur_s), ("t", cur_t)):
+        if st.get(dom) is None:                                                             # First_src / First (:32-33)
+            P[dom] = list(cur)
+        else:
+            P[dom] = [(1 - decay) * old + decay * c for old, c in zip(st[dom], cur)]
+        st[dom] = [p.detach() for p in P[dom]]                                              # :341-344, :384-387
+    intra = sum(mse(ps, pt) for ps, pt in zip(P["s"], P["t"]))                              # :428-441
+    inter = sum(mse(P["s"][k], P["s"][K + k]) for k in reversed(range(K)))                  # :443-444 (logged only)
+    loss = pro_weight * intra                                                               # :463-468
+    loss.backward()
+    return loss.detach(), inter.detach(), xs.grad, xt.grad
+
+
+def bench_dropin(a, dev, lib):
+    """``--workload dropin``: what a reference user gets from ``patch_reference()`` with ZERO trainer changes -- the
+    trainer's inline torch code around the drop-in ops -- next to the same protocol on the eager ops, same GPU."""
+    import torch
+    import uda_clr_b200 as clr
+    from oracle import clr_torch_port as TP      # second arm of the comparison (the eager reference ops), not the product
+    from uda_clr_b200 import synth
+    names = ["xs", "ys", "xt", "oT_before", "preds"]
+    hb = [synth.make_batch(B=a.B, C=a.C, H=a.H, W=a.H, K=a.K, T=a.T, up=a.up, seed=1234 + s_) for s_ in range(2)]
+    devb = [{k: getattr(h, k).to(dev) for k in names} for h in hb]
+
+    def run(ops, steps, warm):
+        st = {}
+        for i in range(warm):
+            trainer_protocol_step(ops, st, devb[i % 2], a.T)
+        torch.cuda.synchronize()
+        l0 = lib.clr_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            res = trainer_protocol_step(ops, st, devb[i % 2], a.T)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps, res, lib.clr_launch_count() - l0
+
+    W_ = max(a.warmup, 3)
+    ms, res, launches = run(clr, a.steps, W_)
+    ms_ref, res_ref, _ = run(TP, max(3, min(a.steps, 20)), 3)
+    # parity of the two protocols after the same number of EMA steps is covered by tests/test_gpu_integration.py; here
+    # the first steps of fresh states are compared
+    st1, st2 = {}, {}
+    r1 = trainer_protocol_step(clr, st1, devb[0], a.T)
+    r2 = trainer_protocol_step(TP, st2, devb[0], a.T)
+    torch.cuda.synchronize()
+    parity = {"loss_rel": abs(float(r1[0]) - float(r2[0])) / abs(float(r2[0])), "gxs_rel": _rel(r1[2], r2[2]), "gxt_rel": _rel(r1[3], r2[3])}
+    parity["ok"] = parity["loss_rel"] < TOL["loss"] and parity["gxs_rel"] < TOL["grad"] and parity["gxt_rel"] < TOL["grad"]
+    px = 2 * a.B * a.H * a.H
+    line = {"metric": METRIC, "value": px / (ms * 1e-3) / 1e6, "unit": UNIT, "n_gpus": 1, "steps": a.steps, "warmup": W_,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": config_dict(a, 1), "gpu_launches": int(launches),
+            "gpu_eager_baseline": {"value": px / (ms_ref * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms_ref,
+                                   "what": "the same protocol on the eager port ops, same GPU"},
+            "parity": parity, "losses": {"total": float(res[0]), "inter": float(res[1])}}
+    print(json.dumps(line))
+    return 0
+
+
 def config_dict(a, n_gpus):
-    return {"workload": ("clr3: A1 hard source + A2 retrify target (MC stats T=%d) + A4 EMA + A5 align + A9 hinge + A10 "
-                         "consistency, fwd+bwd" % a.T) if a.workload == "clr3" else
-                        "align: A1 hard source + A1 soft target + A4 + A5, fwd+bwd (Trainer_prototype_full.py:330-449)",
+    wl = {"clr3": "clr3: A1 hard source + A2 retrify target (MC stats T=%d) + A4 EMA + A5 align + A9 hinge + A10 "
+                  "consistency, fwd+bwd" % a.T,
+          "align": "align: A1 hard source + A1 soft target + A4 + A5, fwd+bwd (Trainer_prototype_full.py:330-449)",
+          "dropin": "dropin: the trainer's own protocol (Trainer_prototype_full.py:330-449: gen_prototype + gen_prototype_retrify "
+                    "drop-in ops, inline EMA / MSE in torch, loss.backward()) with the patched ops"}[a.workload]
+    return {"workload": wl,
             "per_gpu_batch": a.B, "global_batch": a.B * n_gpus, "channels": a.C, "feature_hw": [a.H, a.H],
             "image_hw": [a.H * a.up, a.H * a.up], "classes": a.K, "mc_passes": a.T,
             "parallelism": "dp%d (batch-sharded; packed class sums exchanged %s)" % (
@@ -244,74 +455,108 @@ def main():
         name, val = kv.split("=")
         _lib.check(lib.clr_set_tunable(name.encode(), int(val)), "clr_set_tunable(%s)" % kv)
 
+    if a.workload == "dropin":
+        return bench_dropin(a, dev, lib)
+
     use3 = a.workload == "clr3"
     NSET = 2
-    host = [synth.make_batch(B=a.B, C=a.C, H=a.H, W=a.H, K=a.K, T=a.T, up=a.up, seed=1234 + 17 * rank + s,
-                             image_res=use3) for s in range(NSET)]
     names = ["xs", "ys", "xt", "oT_before"] + (["preds", "oT", "oT_aug"] if use3 else [])
+
+    def host_batch(r, s_):
+        return synth.make_batch(B=a.B, C=a.C, H=a.H, W=a.H, K=a.K, T=a.T, up=a.up, seed=1234 + 17 * r + s_, image_res=use3)
+
+    host = [host_batch(rank, s_) for s_ in range(NSET)]
     devb = [{k: getattr(h, k).to(dev) for k in names} for h in host]
 
-    step = clr.CLRStep(K=a.K, retrify=use3, use_disc=use3, use_cons=use3, backprop_aug=False,
-                       global_batch=a.B * world)
-    plans = []
-    for d in devb:
-        if use3:
-            plans.append(step.plan(d["xs"], d["ys"], d["xt"], oT_before=d["oT_before"], preds=d["preds"], T=a.T,
-                                   oT=d["oT"], oT_aug=d["oT_aug"], epoch=0.0))
-        else:
-            plans.append(step.plan(d["xs"], d["ys"], d["xt"], wt=torch.sigmoid(d["oT_before"])))
+    def make_plans(step_obj):
+        out = []
+        for d in devb:
+            if use3:
+                out.append(step_obj.plan(d["xs"], d["ys"], d["xt"], oT_before=d["oT_before"], preds=d["preds"], T=a.T,
+                                         oT=d["oT"], oT_aug=d["oT_aug"], epoch=0.0))
+            else:
+                out.append(step_obj.plan(d["xs"], d["ys"], d["xt"], wt=torch.sigmoid(d["oT_before"])))
+        return out
 
     def barrier():
         if dist_on:
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- parity (outside the timed region): the first two steps of a FRESH state, sharded exactly like the timed
+    #      steps, against the op-for-op eager port of the reference on the SAME GPU (rank 0; at N > 1 on the concatenated
+    #      global batch), plus the cross-rank agreement of the losses and the device-side time-out flag ---------------
+    parity = None
+    if not a.no_parity:
+        parity = run_parity(a, clr, synth, make_plans, host_batch, dev, rank, world, dist_on, use3, names)
+        barrier()
+
+    step = clr.CLRStep(K=a.K, retrify=use3, use_disc=use3, use_cons=use3, backprop_aug=False, global_batch=a.B * world)
+    plans = make_plans(step)
+
     # ---- warm-up -------------------------------------------------------------------------------
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    for i in range(max(a.warmup, 3)):
+    W_ = max(a.warmup, 3)
+    for i in range(W_):
         plans[i % NSET].run()
     barrier()
 
-    # ---- timed region: exactly K steps, CUDA events on the launching stream ------------------------
+    # ---- timed region: exactly K steps between two CUDA events on the launching stream; NOTHING else is enqueued
+    #      inside it unless K >= 64, where the dominant kernels are bracketed on ~16 evenly spaced steps (an event record
+    #      between two kernels defeats programmatic dependent launch, ~2.5 us per bracket: < 0.03 % of such a region) --
     K = a.steps
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    # the dominant kernels are bracketed by CUDA events INSIDE the timed region, but only on every `ev_stride`-th
-    # step: an event record between two kernels defeats programmatic dependent launch (~2.5 us per bracket), so
-    # bracketing every step would tax the very number being reported.  ~32 samples spread over the region.
-    ev_stride = max(1, K // 32)
-    sampled = [i for i in range(K) if i % ev_stride == 0]
-    pool_ev = {i: (_lib.Event(), _lib.Event()) for i in sampled}
-    bwd_ev = {i: (_lib.Event(), _lib.Event()) for i in sampled}
+    inside = K >= 64
+    ev_stride = max(1, K // 16) if inside else 1
+    n_samples = len(range(0, K, ev_stride)) if inside else 16
+    pool_ev = [(_lib.Event(), _lib.Event()) for _ in range(n_samples)]
+    bwd_ev = [(_lib.Event(), _lib.Event()) for _ in range(n_samples)]
+
+    def bracketed(p, j):
+        p.set_events(pool_ev[j][0], pool_ev[j][1], bwd_ev[j][0], bwd_ev[j][1])
+        p.run()
+        p.set_events()
+
     launches0 = lib.clr_launch_count()
     barrier()
     sampler.mark_begin()
     ev0.record()
-    for i in range(K):
-        p = plans[i % NSET]
-        if i in pool_ev:
-            p.set_events(pool_ev[i][0], pool_ev[i][1], bwd_ev[i][0], bwd_ev[i][1])
-            p.run()
-            p.set_events()
-        else:
-            p.run()
+    if inside:
+        for i in range(K):
+            if i % ev_stride == 0:
+                bracketed(plans[i % NSET], i // ev_stride)
+            else:
+                plans[i % NSET].run()
+    else:
+        for i in range(K):
+            plans[i % NSET].run()
     ev1.record()
+    launches = lib.clr_launch_count() - launches0
+    if not inside:
+        # same loop, same rotating inputs, continuing straight on: the kernel-time samples of a short run
+        for j in range(n_samples):
+            bracketed(plans[(K + j) % NSET], j)
     barrier()
     sampler.mark_end()
-    launches = lib.clr_launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
-    for p in plans:
-        p.set_events()
     ms_total = ev0.elapsed_time(ev1)
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if dist_on:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_per_step = float(t.item()) / K
-    pool_us = statistics.mean(b.elapsed_us(e) for b, e in pool_ev.values())
-    bwd_us = statistics.mean(b.elapsed_us(e) for b, e in bwd_ev.values())
+    pool_us = statistics.mean(b.elapsed_us(e) for b, e in pool_ev)
+    bwd_us = statistics.mean(b.elapsed_us(e) for b, e in bwd_ev)
     value = 2 * a.B * a.H * a.H * world / (ms_per_step * 1e-3) / 1e6
-    losses = plans[0].losses.detach().cpu().tolist()
+    lt = plans[(K - 1) % NSET].losses.detach().clone()
+    flags = [lt]
+    if dist_on:
+        flags = [torch.empty_like(lt) for _ in range(world)]
+        dist.all_gather(flags, lt)
+    losses = lt.cpu().tolist()
+    timed_flag = max(float(f[7]) for f in flags)
+    timed_rank_diff = max(float((f[:5] - flags[0][:5]).abs().max()) for f in flags)
 
     # ---- supplementary (outside the timed region): per-kernel busy time of a live step from the library's own
     #      device-side %globaltimer stamps -- no event records, programmatic dependent launch intact ----------------
@@ -378,8 +623,15 @@ def main():
 
     if rank != 0:
         if dist_on:
+            clr.dist.close_peer()
             dist.destroy_process_group()
         return 0
+
+    # ---- second baseline: the reference's eager op sequence on THIS GPU (op-for-op port), outside
+    #      the timed region; N = 1 only ------------------------------------------------------------------------
+    gpu_eager = None
+    if world == 1 and not a.no_gpu_eager:
+        gpu_eager = run_eager_gpu(a, devb, use3)
 
     # ---- roofline of the dominant kernel (the two-domain pooling launch), measured live above ------
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -388,6 +640,7 @@ def main():
     else:
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
     ab = algorithmic_bytes(a)
+    ib = implementation_bytes(a)
     achieved = ab["pool_fwd"] / (pool_us * 1e-6) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
@@ -400,13 +653,18 @@ def main():
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": ab["pool_fwd"], "kernel_us": pool_us,
                 "kernel_us_device_trace": (device_trace or {}).get("pool_fwd"), "device_trace_us": device_trace,
-                "kernel_samples": len(pool_ev), "kernel_sample_stride": ev_stride,
+                "kernel_samples": n_samples,
+                "kernel_sampling": ("every %d-th step inside the timed region" % ev_stride) if inside else
+                                   "%d extra steps right after the timed region (K < 64: nothing but the K steps is enqueued inside it)" % n_samples,
                 "bwd_kernel": {"kernel": "pool_bwd_kernel (both gradient maps, one launch)", "kernel_us": bwd_us,
+                               "algorithmic_bytes_per_launch": ab["pool_bwd"],
                                "achieved": ab["pool_bwd"] / (bwd_us * 1e-6) / 1e9,
                                "frac": ab["pool_bwd"] / (bwd_us * 1e-6) / 1e9 / peak},
-                "step": {"algorithmic_bytes": ab["total"], "achieved": ab["total"] / (ms_per_step * 1e-3) / 1e9,
+                "step": {"algorithmic_bytes": ab["total"], "algorithmic_bytes_by_stage": ab,
+                         "achieved": ab["total"] / (ms_per_step * 1e-3) / 1e9,
                          "frac": ab["total"] / (ms_per_step * 1e-3) / 1e9 / peak,
-                         "frac_of_nominal_8TBs": ab["total"] / (ms_per_step * 1e-3) / 1e9 / 8000.0}}
+                         "frac_of_nominal_8TBs": ab["total"] / (ms_per_step * 1e-3) / 1e9 / 8000.0,
+                         "implementation_bytes": ib["total"], "implementation_bytes_by_stage": ib}}
 
     cpu_baseline = None
     if not a.no_cpu_baseline and world == 1:
@@ -414,13 +672,16 @@ def main():
         cpu_baseline = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
                         "ms_per_step": r["ms_per_step"]}
 
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(a.warmup, 3),
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W_,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": config_dict(a, world), "clocks": clocks,
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "gpu_eager_baseline": gpu_eager, "parity": parity,
+            "timed_region_check": {"exchange_timeout_flag": timed_flag, "max_cross_rank_loss_diff": timed_rank_diff},
             "losses": {"intra": losses[0], "inter": losses[1], "disc": losses[2], "aug": losses[3], "total": losses[4]}}
     print(json.dumps(line))
     if dist_on:
+        clr.dist.close_peer()
         dist.destroy_process_group()
     return 0
 

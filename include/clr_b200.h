@@ -13,8 +13,16 @@
  *     reference's return order (c0_obj, c1_obj, c0_bck, c1_bck) for K = 2 (utils/Utils.py:131);
  *   - "packed sums" are [R][C+1] floats: columns 0..C-1 hold S_r[c] = sum_{b,p} x[b,c,p] w_r[b,p],
  *     column C holds N_r = sum_{b,p} w_r[b,p].  This is the buffer that is all-reduced across GPUs;
- *   - stream is a cudaStream_t passed as void*; calls only enqueue work (no sync, no allocation,
- *     no global state, re-entrant from any thread -- autograd runs backward on its own thread);
+ *   - stream is a cudaStream_t passed as void*; calls only enqueue work (no sync, no allocation) and are
+ *     re-entrant from any thread (autograd runs backward on its own thread).  Global state is limited to
+ *     the benchmark knobs of clr_set_tunable, the launch counter and the profiling trace pointer
+ *     (atomics; change knobs only while no other thread is launching);
+ *   - the fused step (clr_step_*) uses device-side waits instead of kernel boundaries in three places
+ *     (flag dependency of the discriminative kernel, gated source-gradient CTAs, in-kernel exchange).  Every
+ *     such wait has a ~2 s time-out that sets losses[7] = 1 and turns the step's losses / gradients into
+ *     NaN (the EMA state is left untouched) -- callers poll losses[7] or rely on their NaN check.  The gated
+ *     CTAs assume that the CTAs of one grid are dispatched in block-index order (true on every CUDA GPU to
+ *     date, not a documented guarantee); clr_set_tunable("bwd_merge_off", 1) selects the gate-free form;
  *   - return value: 0 on success, a negative clr_status otherwise; nothing throws across the ABI.
  *     CUDA launch failures return CLR_ERR_CUDA_BASE - (int)cudaError_t.
  */
@@ -55,7 +63,8 @@ const char* clr_status_string(int status);
 /* Number of SMs / L2 bytes of the current device (grid sizing is derived from it; exposed for the bench). */
 int clr_device_info(int* sm_count, int* l2_bytes);
 /* Benchmark / debugging knobs (process-wide): "pool_impl" 0 auto / 1 LDG kernel / 2 TMA ring, "pool_stages" TMA ring
- * depth, "disc_impl" 0 fused / 1 two-pass, "mc_precise" 1 = ATen-exact sigmoids in clr_mc_stats.
+ * depth, "disc_impl" 0 fused / 1 two-pass, "mc_precise" 1 = clr_mc_stats / clr_mc_retrify evaluate the whole maps in
+ * ATen's exact order (slow; parity tests).
  * Defaults select the fastest path. */
 int clr_set_tunable(const char* name, int value);
 /* Number of CUDA kernels this library has launched in this process so far (bench: "gpu_launches"). */
@@ -179,7 +188,13 @@ int clr_disc_fused_fwd(const float* xs, const float* ys, int B, int C, int HW, i
  * ---------------------------------------------------------------------------------------------- */
 int clr_mc_stats(const float* preds /*[T*B,K,Hi,Wi] logits*/, int T, int B, int K, int Hi, int Wi,
                  float* std_map /*[B,K,Hi,Wi] out*/, float* pred_mean /*[B,K,Hi,Wi] out*/, clr_stream_t stream);
+/* clr_mc_stats streams preds once with approximate sigmoids (std error <= ~3e-7).  The uncertainty mask
+ * `std_small < std_thr` is an INTEGER output (bit-exact against eager torch on the same device): pass the MC logits
+ * again as `preds` (+ T) and every pixel whose down-sampled std lies within 1e-5 of the threshold is re-evaluated from
+ * them in ATen's exact order (sigmoid, two-accumulator Welford of torch.std's CUDA reduction, bilinear taps);
+ * preds = NULL skips that guard band (knife-edge pixels may then differ from torch). */
 int clr_retrify_weights(const float* oT_before /*[B,K,H,W]*/, const float* pred_mean, const float* std_map,
+                        const float* preds /*[T*B,K,Hi,Wi] or NULL*/, int T,
                         int B, int K, int H, int W, int Hi, int Wi, float pseudo_thr /*0.75*/, float std_thr /*0.04*/,
                         float* weights /*[B,2K,H,W] out*/, float* masks /*[B,K,H,W] out, {0,2}*/,
                         float* pseudo_out /*[B,K,H,W] or NULL*/, float* small_out /*[2][B,K,H,W] or NULL*/,

@@ -265,12 +265,16 @@ class ClrStepPort:
         if self.retrify:
             out = gen_prototype_retrify(oT_before, xt, preds, features, T, B)
             cur_t, masks = out[:2 * K], out[2 * K + 1:]
+            std_map = out[2 * K]
         else:
             cur_t = gen_prototype(torch.sigmoid(oT_before), xt)
         Pt = self.ema_t.update(cur_t)
         intra, inter = align_losses(Ps, Pt)
         total = self.pro_weight * intra
         res = dict(intra=intra.detach(), inter=inter.detach())
+        if self.retrify:
+            res["masks"] = [m.detach() for m in masks]
+            res["std_map"] = std_map.detach()
         if self.use_disc:
             l_disc = disc_loss(xs, ys, Ps, self.margin)
             total = total + self.src_reg_weight * l_disc

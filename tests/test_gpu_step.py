@@ -25,12 +25,26 @@ def stack(protos):
 
 
 def knife_edge_ok(ours, ref, margin_map, tol=2e-6, max_frac=1e-3):
-    """Integer maps must be identical except where the thresholded quantity sits within `tol` of the threshold."""
+    """CROSS-DEVICE comparisons only (CPU fixture / numpy oracle vs the GPU): the reference's own mask depends on the
+    device it ran on at pixels whose std sits within float noise of the threshold (ATen's CPU and CUDA reductions round
+    differently), so there the maps must be identical except within `tol` of the threshold.  Against eager torch on the
+    SAME device the masks are compared with torch.equal (guard-band re-evaluation in ATen's order, csrc/mc_stats.cu)."""
     diff = ours != ref
     if diff.any():
         assert np.abs(margin_map[diff]).max() < tol, "mismatch away from the threshold"
         assert diff.mean() < max_frac
     return int(diff.sum())
+
+
+def oracle_weights_with_masks(o_r, masks_gpu):
+    """The oracle's retrify weights re-derived with the GPU's mask decisions (identical unless a knife-edge pixel differs
+    between the numpy oracle and the device), so the rest of the oracle comparison never has to be skipped."""
+    pseudo = o_r["pseudo"].astype(bool)
+    m = masks_gpu > 0
+    ps = o_r["pred_small"].astype(np.float32)
+    w_obj = np.where(pseudo & m, ps, np.float32(0.0)).astype(np.float32)
+    w_bck = np.where((~pseudo) & m, (np.float32(1.0) - ps).astype(np.float32), np.float32(0.0)).astype(np.float32)
+    return np.concatenate([w_obj, w_bck], axis=1)
 
 
 # ------------------------------------------------------------------------------------------------ A2
@@ -66,11 +80,69 @@ def test_retrify_pseudo_labels_bit_exact_vs_eager_gpu():
     assert torch.equal(pseudo, ref_pseudo)                       # bit-exact
     ref = TP.gen_prototype_retrify(oT, b.xt.to(DEV), preds, None, 8, 2)
     assert relerr(std_map.cpu().numpy(), ref[4].cpu().numpy()) < 5e-6
-    std_small = small[1].cpu().numpy()
+    # the guard band (preds handed to retrify_weights) makes the masks bit-exact against eager torch on this device
+    _, masks_g = clr.retrify_weights(oT, pred_mean, std_map, 64, 64, preds=preds, T=8)
     for k in range(2):
-        knife_edge_ok(masks[:, k:k + 1].cpu().numpy(), ref[5 + k].cpu().numpy(), std_small[:, k:k + 1] - 0.04)
+        assert torch.equal(masks_g[:, k:k + 1], ref[5 + k])
+    out = clr.gen_prototype_retrify(oT, b.xt.to(DEV), preds, None, 8, 2)       # the drop-in (one-pass kernel)
+    for k in range(2):
+        assert torch.equal(out[5 + k], ref[5 + k])
     frac = float((masks > 0).float().mean())
     assert 0.02 < frac < 0.98, "case must exercise both mask states (got %.3f)" % frac
+
+
+def _set_tunable(name, value):
+    from uda_clr_b200 import _lib
+    _lib.check(_lib.load().clr_set_tunable(name.encode(), int(value)), name)
+
+
+@pytest.mark.parametrize("T,B,K,Hi", [(8, 2, 2, 256), (4, 1, 2, 128), (3, 2, 2, 64), (5, 1, 3, 96), (12, 1, 2, 64), (2, 1, 2, 32),
+                                      (20, 1, 2, 32), (8, 1, 1, 8)])
+def test_mc_statistics_in_aten_order_are_bit_exact(T, B, K, Hi):
+    """``mc_precise`` = 1 evaluates std_T(sigmoid(p/2)) and mean_T(sigmoid(p)) in the order of ATen's CUDA reductions
+    (two interleaved Welford accumulators / four interleaved sums per output, csrc/mc_stats.cu): bit-identical to eager
+    torch on the same device.  This is the arithmetic the mask guard band re-evaluates knife-edge pixels with."""
+    g = torch.Generator(device=DEV).manual_seed(T * 100 + Hi)
+    preds = 3.0 * torch.randn(T * B, K, Hi, Hi, generator=g, device=DEV)
+    p5 = preds.reshape(T, B, K, Hi, Hi)
+    ref_std = torch.std(torch.sigmoid(p5 / 2.0), dim=0)        # utils/Utils.py:165-166
+    ref_mean = torch.mean(torch.sigmoid(p5), dim=0)            # :164, :168
+    try:
+        _set_tunable("mc_precise", 1)
+        s, m = clr.mc_statistics(preds, T, B)
+    finally:
+        _set_tunable("mc_precise", 0)
+    assert torch.equal(s, ref_std)
+    assert torch.equal(m, ref_mean)
+    # and the streaming kernel stays within the guard band's error budget (3e-7 << 1e-5)
+    s_fast, m_fast = clr.mc_statistics(preds, T, B)
+    assert float((s_fast - ref_std).abs().max()) < 1e-6
+    assert float((m_fast - ref_mean).abs().max()) < 1e-6
+
+
+@pytest.mark.parametrize("noise", [0.3, 0.45])
+def test_uncertainty_masks_bit_exact_at_config1_over_50_seeds(noise):
+    """mask_k = std_small_k < 0.04 is an integer output.  BASELINE config-1 geometry (B=8, K=2,
+    128x128 features, 512x512 MC logits, T=8), 50 seeds, bench-like data (noise 0.3) and a stress set whose std
+    distribution is centred on the threshold (0.45): zero flips against eager torch on the same device, for the
+    two-kernel form (the fused step's) and the one-pass kernel (the drop-in's)."""
+    B, K, H, up, T = 8, 2, 128, 4, 8
+    in_band = 0
+    for seed in range(50):
+        g = torch.Generator(device=DEV).manual_seed(7000 + seed)
+        oTb = 2.0 * torch.randn(B, K, H, H, generator=g, device=DEV) + 1.0
+        base = oTb.repeat_interleave(up, 2).repeat_interleave(up, 3)
+        preds = base.repeat(T, 1, 1, 1) + noise * torch.randn(T * B, K, H * up, H * up, generator=g, device=DEV)
+        ref_std = torch.std(torch.sigmoid(preds.reshape(T, B, K, H * up, H * up) / 2.0), dim=0)
+        ref_small = torch.nn.functional.interpolate(ref_std, size=(H, H), mode="bilinear", align_corners=True)
+        ref_mask = torch.where(ref_small < 0.04, 2.0, 0.0)
+        s, m = clr.mc_statistics(preds, T, B)
+        _, mask2 = clr.retrify_weights(oTb, m, s, H, H, preds=preds, T=T)
+        _, _, mask1 = clr.ops.mc_retrify(oTb, preds, T, B, H, H)
+        assert torch.equal(mask2, ref_mask), (seed, int((mask2 != ref_mask).sum()))
+        assert torch.equal(mask1, ref_mask), (seed, int((mask1 != ref_mask).sum()))
+        in_band += int(((ref_small - 0.04).abs() < 1e-5).sum())
+    assert in_band > 0, "the seeds must exercise the guard band"
 
 
 @pytest.mark.parametrize("K,C,H,up,T", [(2, 16, 32, 4, 8), (3, 10, 24, 2, 3), (2, 305, 128, 4, 8)])
@@ -82,15 +154,21 @@ def test_retrify_vs_oracle(K, C, H, up, T):
     assert len(out) == 2 * K + 1 + K
     o = O.gen_prototype_retrify(b.oT_before.numpy(), b.xt.numpy(), b.preds.numpy(), T, B)
     assert relerr(out[2 * K].cpu().numpy(), o["std_map"]) < 5e-6
-    mism = 0
     for k in range(K):
-        mism += knife_edge_ok(out[2 * K + 1 + k].cpu().numpy(), o["masks"][:, k:k + 1], o["std_small"][:, k:k + 1] - 0.04)
-    if mism == 0:
-        assert relerr(stack(out[:2 * K]), o["protos"]) < TOL_PROTO
-        seeds = torch.randn(2 * K, C, generator=torch.Generator().manual_seed(3))
-        sum((p.reshape(-1) * s).sum() for p, s in zip(out[:2 * K], seeds.to(DEV))).backward()
-        gx, _ = O.pool_backward(b.xt.numpy(), o["w"], seeds.numpy())
-        assert relerr(xt.grad.cpu().numpy(), gx) < TOL_GRAD
+        knife_edge_ok(out[2 * K + 1 + k].cpu().numpy(), o["masks"][:, k:k + 1], o["std_small"][:, k:k + 1] - 0.04)
+    # numpy oracle vs device: continue with the device's mask decisions (identical unless a knife-edge pixel differs)
+    masks_gpu = np.concatenate([out[2 * K + 1 + k].cpu().numpy() for k in range(K)], axis=1)
+    w = oracle_weights_with_masks(o, masks_gpu)
+    S, N = O.pool_sums(b.xt.numpy(), w)
+    assert relerr(stack(out[:2 * K]), O.prototypes_from_sums(S, N)) < TOL_PROTO
+    seeds = torch.randn(2 * K, C, generator=torch.Generator().manual_seed(3))
+    sum((p.reshape(-1) * s).sum() for p, s in zip(out[:2 * K], seeds.to(DEV))).backward()
+    gx, _ = O.pool_backward(b.xt.numpy(), w, seeds.numpy())
+    assert relerr(xt.grad.cpu().numpy(), gx) < TOL_GRAD
+    # same device: bit-exact masks against the eager port
+    ref = TP.gen_prototype_retrify(b.oT_before.to(DEV), b.xt.to(DEV), b.preds.to(DEV), None, T, B)
+    for k in range(K):
+        assert torch.equal(out[2 * K + 1 + k], ref[2 * K + 1 + k])
 
 
 def test_src_trg_retrify_joint():
@@ -320,9 +398,10 @@ def test_fused_step_vs_oracle(variant):
             for k in range(K):
                 knife_edge_ok(masks_gpu[:, k:k + 1], o_r["masks"][:, k:k + 1], o_r["std_small"][:, k:k + 1] - 0.04)
             assert relerr(out.std_map.cpu().numpy(), o_r["std_map"]) < 5e-6
-            if not np.array_equal(masks_gpu, o_r["masks"]):
-                pytest.skip("knife-edge mask pixel in this seed")
-            wt, masks = o_r["w"], o_r["masks"]
+            # numpy oracle vs device: a knife-edge pixel may legitimately differ (knife_edge_ok above); the rest of the
+            # comparison then uses the device's decisions, it is never skipped
+            wt, masks = oracle_weights_with_masks(o_r, masks_gpu), masks_gpu
+            assert float(out.error) == 0.0
         else:
             wt, masks = O.sigmoid_f32(b.oT_before.numpy()), None
         cons = None
@@ -382,6 +461,68 @@ def test_fused_step_vs_eager_port_on_gpu():
         g1, g2 = xs1.grad.cpu().numpy(), xs2.grad.cpu().numpy()
         bad = np.abs(g1 - g2) > TOL_GRAD * np.abs(g2).max()
         assert bad.mean() < 1e-4, bad.mean()
+
+
+@pytest.mark.parametrize("C", [256, 305])
+def test_fused_step_at_baseline_config1_vs_eager_port_on_gpu(C):
+    """The BENCHED path under parity (VERDICT r01 next #1a): the clr3 fused step at BASELINE config 1 (B=8, C=256 -- and the
+    real decoder's 305 --, 128x128, K=2, T=8, 512x512 logits, backprop_aug=False) through ``plan.run()`` for two steps (first-step
+    copy, then one EMA step) against the op-for-op eager port on the same GPU: losses 1e-4, prototypes 1e-5, BOTH feature
+    gradients 1e-4, pseudo-labels and uncertainty masks torch.equal, no device-side time-out."""
+    K, H, up, T, B = 2, 128, 4, 8, 8
+    ours = clr.CLRStep(K=K, retrify=True, use_disc=True, use_cons=True, backprop_aug=False)
+    port = TP.ClrStepPort(retrify=True, use_disc=True, use_cons=True, backprop_aug=False)
+    for it in range(2):
+        b = synth.make_batch(B=B, C=C, H=H, W=H, K=K, T=T, up=up, seed=1234 + it)
+        t = {k: getattr(b, k).to(DEV) for k in ("xs", "ys", "xt", "oT_before", "preds", "oT", "oT_aug")}
+        plan = ours.plan(t["xs"], t["ys"], t["xt"], oT_before=t["oT_before"], preds=t["preds"], T=T, oT=t["oT"],
+                         oT_aug=t["oT_aug"], epoch=0.0)
+        plan.run()
+        torch.cuda.synchronize()
+        out = plan.outputs()
+        xs2, xt2 = t["xs"].clone().requires_grad_(True), t["xt"].clone().requires_grad_(True)
+        res = port.step(xs2, t["ys"], xt2, t["oT_before"], preds=t["preds"], features=None, T=T, oT=t["oT"],
+                        oT_aug=t["oT_aug"], epoch=0.0)
+        assert float(plan.error) == 0.0 and float(plan.losses[7]) == 0.0
+        plan.check()
+        # integer outputs: bit-exact on the same device
+        for k in range(K):
+            assert torch.equal(out.masks[k], res["masks"][k]), (it, k, int((out.masks[k] != res["masks"][k]).sum()))
+        pseudo_ref = torch.sigmoid(t["oT_before"]) > 0.75
+        wts = plan.holder["buf"].wt_retrify.view(B, 2 * K, H, H)
+        m_on = torch.cat(out.masks, 1) > 0
+        _, _, pseudo_dbg, _ = clr.retrify_weights(t["oT_before"], plan.holder["buf"].pred_mean.view(B, K, H * up, H * up),
+                                                  out.std_map, H, H, debug=True)
+        assert torch.equal(pseudo_dbg > 0, pseudo_ref)                  # the thresholded pseudo-labels, every pixel
+        assert not bool(((wts[:, :K] != 0) & ~pseudo_ref).any())        # object weights only where the pseudo-label is 1
+        assert not bool(((wts[:, K:] != 0) & pseudo_ref).any())         # background weights only where it is 0
+        assert not bool(((wts != 0) & ~m_on.repeat(1, 2, 1, 1)).any())  # and nothing outside the uncertainty mask
+        assert relerr(out.std_map.cpu().numpy(), res["std_map"].cpu().numpy()) < 5e-6
+        # float outputs
+        for k in ("intra", "inter", "disc", "aug"):
+            assert abs(float(getattr(out, k)) - float(res[k])) < TOL_LOSS * abs(float(res[k])), (it, k)
+        assert abs(float(plan.losses[4]) - float(res["total"])) < TOL_LOSS * abs(float(res["total"]))
+        assert relerr(stack(out.source_prototypes), stack(res["Ps"])) < TOL_PROTO
+        assert relerr(stack(out.target_prototypes), stack(res["Pt"])) < TOL_PROTO
+        assert relerr(plan.gxt.cpu().numpy(), xt2.grad.cpu().numpy()) < TOL_GRAD
+        # gxs carries A9's direct term: d hinge / dx flips with the active set, so a pixel whose hinge argument sits within
+        # float noise of the kink may legitimately differ between two fp32 evaluation orders.  Every OTHER element must
+        # agree to the gradient tolerance, and every differing pixel must be shown to sit on the kink.
+        g1, g2 = plan.gxs, xs2.grad
+        bad = (g1 - g2).abs() > TOL_GRAD * g2.abs().max()
+        if bool(bad.any()):
+            with torch.no_grad():
+                Ps = res["Ps"]
+                arg = []
+                for k in range(K):
+                    d_obj = torch.mean(torch.pow(t["xs"] - Ps[k], 2), dim=1)
+                    d_bck = torch.mean(torch.pow(t["xs"] - Ps[K + k], 2), dim=1)
+                    arg.append(torch.where(t["ys"][:, k] > 0, d_obj - d_bck + 0.01, d_bck - d_obj + 0.01))
+                near_kink = torch.stack(arg, 1).abs().min(dim=1).values < 1e-5          # [B,H,W]
+            bad_px = bad.any(dim=1)
+            assert not bool((bad_px & ~near_kink).any()), "gxs differs away from the hinge kink"
+            assert float(bad_px.float().mean()) < 1e-4
+    assert ours.first_s is False
 
 
 @pytest.mark.parametrize("Bs,Bt,C,H,W,K,up,T", [(3, 2, 37, 24, 40, 3, 2, 5),      # unequal batches, odd C, H != W, up 2, odd T

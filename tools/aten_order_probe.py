@@ -1,0 +1,119 @@
+#!/usr/bin/env python3
+"""GPU probe: is the library's emulation of ATen's CUDA evaluation order bit-exact?
+
+The uncertainty masks of ``gen_prototype_retrify`` (utils/Utils.py:166, 171, 197-200) are integer outputs derived from
+``torch.std(dim=0)`` + bilinear down-sampling; the library re-evaluates pixels near the threshold in ATen's order
+(csrc/mc_stats.cu).  This tool checks that order against eager torch ON THE SAME GPU:
+
+  1. ``mc_precise=1`` maps vs ``torch.std`` / ``torch.mean`` bit for bit, for every candidate ``aten_variant``
+     (fma / no fma in WelfordOps, number of interleaved accumulators) and several T -> which variant IS ATen;
+  2. the down-sampled std (``small_out``) vs ``F.interpolate(bilinear, align_corners=True)`` bit for bit;
+  3. mask flips against eager torch at BASELINE config-1 shape over N seeds, without and with the guard band
+     (``preds=None`` vs ``preds=...``), on the bench's synthetic data and on a stress set whose std distribution is
+     centred on the threshold.
+
+Prints one JSON object (committed as profiles/r02_mask_flips.json).
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch
+import torch.nn.functional as F
+
+import uda_clr_b200 as clr
+from uda_clr_b200 import _lib
+
+
+def set_tunable(lib, name, v):
+    _lib.check(lib.clr_set_tunable(name.encode(), int(v)), name)
+
+
+def torch_maps(preds, T, B):
+    p = preds.reshape(T, B, preds.shape[1], preds.shape[2], preds.shape[3])
+    return torch.std(torch.sigmoid(p / 2.0), dim=0), torch.mean(torch.sigmoid(p), dim=0)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--seeds", type=int, default=50)
+    ap.add_argument("--variants", default="0,1,2,3,4,5,8")
+    a = ap.parse_args()
+    dev = torch.device("cuda:0")
+    lib = _lib.load()
+    out = {"torch": torch.__version__, "gpu": torch.cuda.get_device_name(0)}
+
+    # ---- 1. whole-map order probe ------------------------------------------------------------------------------
+    g = torch.Generator(device=dev).manual_seed(1)
+    probe = {}
+    for T, B, K, Hi in [(8, 2, 2, 256), (4, 1, 2, 128), (3, 2, 2, 64), (5, 1, 3, 96), (12, 1, 2, 64), (2, 1, 2, 32), (20, 1, 2, 32),
+                        (8, 1, 1, 8)]:
+        preds = 3.0 * torch.randn(T * B, K, Hi, Hi, generator=g, device=dev)
+        ref_std, ref_mean = torch_maps(preds, T, B)
+        row = {}
+        for v in [int(x) for x in a.variants.split(",")]:
+            set_tunable(lib, "mc_precise", 1)
+            set_tunable(lib, "aten_variant", v)
+            try:
+                s, m = clr.mc_statistics(preds, T, B)
+            finally:
+                set_tunable(lib, "mc_precise", 0)
+                set_tunable(lib, "aten_variant", 0)
+            row["variant_%d" % v] = {"std_mismatch": int((s != ref_std).sum()), "mean_mismatch": int((m != ref_mean).sum()),
+                                     "n": int(s.numel())}
+        probe["T%d_B%d_K%d_%d" % (T, B, K, Hi)] = row
+    out["order_probe"] = probe
+
+    # ---- 2. bilinear taps ----------------------------------------------------------------------------------------
+    bil = {}
+    for (B, K, H, W, up) in [(2, 2, 128, 128, 4), (1, 2, 24, 40, 2), (1, 3, 17, 23, 3), (1, 2, 128, 128, 8)]:
+        T = 8
+        preds = 2.0 * torch.randn(T * B, K, H * up, W * up, generator=g, device=dev)
+        oT = torch.randn(B, K, H, W, generator=g, device=dev)
+        set_tunable(lib, "mc_precise", 1)
+        try:
+            s, m = clr.mc_statistics(preds, T, B)
+        finally:
+            set_tunable(lib, "mc_precise", 0)
+        w, masks, pseudo, small = clr.retrify_weights(oT, m, s, H, W, debug=True)
+        ref_s = F.interpolate(s, size=(H, W), mode="bilinear", align_corners=True)
+        ref_m = F.interpolate(m, size=(H, W), mode="bilinear", align_corners=True)
+        bil["B%d_K%d_%dx%d_up%d" % (B, K, H, W, up)] = {"std_small_mismatch": int((small[1] != ref_s).sum()),
+                                                         "pred_small_mismatch": int((small[0] != ref_m).sum()),
+                                                         "n": int(ref_s.numel())}
+    out["bilinear_probe"] = bil
+
+    # ---- 3. mask flips at config-1 shape ---------------------------------------------------------------------------
+    B, K, H, up, T = 8, 2, 128, 4, 8
+    flips = {}
+    for name, noise in (("bench_synth_noise0.3", 0.3), ("stress_noise0.45", 0.45)):
+        tot = {"pixels": 0, "flips_no_guard": 0, "flips_guard": 0, "in_band": 0, "mask_on_frac": 0.0}
+        for seed in range(a.seeds):
+            gg = torch.Generator(device=dev).manual_seed(1000 + seed)
+            oTb = 2.0 * torch.randn(B, K, H, H, generator=gg, device=dev) + 1.0
+            base = oTb.repeat_interleave(up, 2).repeat_interleave(up, 3)
+            preds = base.repeat(T, 1, 1, 1) + noise * torch.randn(T * B, K, H * up, H * up, generator=gg, device=dev)
+            ref_std, _ = torch_maps(preds, T, B)
+            ref_small = F.interpolate(ref_std, size=(H, H), mode="bilinear", align_corners=True)
+            ref_mask = torch.where(ref_small < 0.04, 2.0, 0.0)
+            s, m = clr.mc_statistics(preds, T, B)
+            _, mask_ng = clr.retrify_weights(oTb, m, s, H, H)
+            _, mask_g = clr.retrify_weights(oTb, m, s, H, H, preds=preds, T=T)
+            _, _, mask_f = clr.ops.mc_retrify(oTb, preds, T, B, H, H)
+            tot["pixels"] += int(ref_mask.numel())
+            tot["flips_no_guard"] += int((mask_ng != ref_mask).sum())
+            tot["flips_guard"] += int((mask_g != ref_mask).sum())
+            tot["flips_one_pass_kernel"] = tot.get("flips_one_pass_kernel", 0) + int((mask_f != ref_mask).sum())
+            tot["in_band"] += int(((ref_small - 0.04).abs() < 1e-5).sum())
+            tot["mask_on_frac"] += float((ref_mask > 0).float().mean()) / a.seeds
+        flips[name] = tot
+    out["mask_flips_config1"] = flips
+    print(json.dumps(out, indent=1))
+
+
+if __name__ == "__main__":
+    main()

@@ -103,7 +103,7 @@ _SIGNATURES = {
     "clr_disc_fused_ws_bytes": (c_size_t, [c_int, c_int]),
     "clr_disc_fused_fwd": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, c_float, _P, _P, _P, c_size_t, _P, _P]),
     "clr_mc_stats": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P]),
-    "clr_retrify_weights": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float,
+    "clr_retrify_weights": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float,
                                     _P, _P, _P, _P, _P]),
     "clr_mc_retrify": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float, _P, _P, _P, _P, _P]),
     "clr_seg_loss_ws_bytes": (c_size_t, []),

@@ -42,6 +42,7 @@ int clr_set_tunable(const char* name, int value) {
     else if (!strcmp(name, "pool_stages")) t.pool_stages = value;
     else if (!strcmp(name, "pool_threads")) t.pool_threads = value;
     else if (!strcmp(name, "mc_precise")) t.mc_precise = value;
+    else if (!strcmp(name, "aten_variant")) t.aten_variant = value;
     else if (!strcmp(name, "disc_impl")) t.disc_impl = value;
     else if (!strcmp(name, "disc_tile")) t.disc_tile = value;
     else if (!strcmp(name, "disc_threads")) t.disc_threads = value;

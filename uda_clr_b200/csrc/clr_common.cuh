@@ -25,7 +25,9 @@ static inline bool aligned4(const void* p) { return (reinterpret_cast<uintptr_t>
 struct DeviceFacts { int sms; int l2; int max_smem_optin; };
 const DeviceFacts& device_facts();
 
-// Process-wide kernel-selection knobs for benchmarking (clr_set_tunable); defaults pick the fastest path.
+// Process-wide kernel-selection knobs for benchmarking (clr_set_tunable); defaults pick the fastest path.  This is the
+// library's only mutable global state besides the launch counter and the profiling trace pointer: plain ints that a
+// launch reads once; changing one while another thread is launching is not synchronised (bench / test use only).
 struct Tunables {
     int pool_impl;     // 0 = auto (128-bit LDG kernel, 2 CTAs/SM: fastest in the live step), 1 = force LDG, 2 = force the TMA ring
     int pool_stages;   // TMA ring depth (0 = auto)
@@ -34,7 +36,8 @@ struct Tunables {
     int disc_threads;  // 0 = auto (256-thread CTAs: fastest in the live step), 512 = 512-thread CTAs when K <= 2
     int disc_tile;     // 0 = auto, 64 = force 64-pixel tiles in the fused discriminative kernel
     int pdl_off;       // 1 = do not use programmatic dependent launch
-    int mc_precise;    // 1 = ATen-exact sigmoids in clr_mc_stats (slower), 0 = fast intrinsics
+    int mc_precise;    // 1 = clr_mc_stats / clr_mc_retrify evaluate std / mean exactly like ATen's CUDA reductions (slow; tests), 0 = streaming
+    int aten_variant;  // A/B of the ATen-order emulation against torch (mc_stats.cu); 0 = the pinned form
     int finish_off;    // 1 = single-GPU step uses the separate reduce / finalize kernels instead of the merged finish kernels
     int hfuse_off;     // 1 = finish bodies get launches of their own instead of riding with cons / the target-gradient write
     int fin_early_off; // 1 = the pooling finish releases the discriminative kernel only at its very end (after the last-CTA combine)
@@ -266,6 +269,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 
 }  // namespace clr
 
+#include <atomic>
 #include <utility>
 namespace clr {
 
@@ -277,10 +281,15 @@ static inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = tunables().pdl_off ? 0 : 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    {   // install / remove the trace buffer pointer in THIS translation unit's copy of g_trace_dev (stream-ordered)
-        static void* installed = nullptr;
+    {   // install / remove the trace buffer pointer in THIS translation unit's copy of g_trace_dev (stream-ordered).
+        // Launches may come from several host threads (autograd runs backward on its own): the bookkeeping word is atomic,
+        // and two threads that race merely install the same pointer twice.
+        static std::atomic<void*> installed{nullptr};
         void* want = tunables().trace_buf;
-        if (want != installed) { cudaMemcpyToSymbolAsync(g_trace_dev, &want, sizeof(want), 0, cudaMemcpyHostToDevice, st); installed = want; }
+        if (want != installed.load(std::memory_order_acquire)) {
+            cudaMemcpyToSymbolAsync(g_trace_dev, &want, sizeof(want), 0, cudaMemcpyHostToDevice, st);
+            installed.store(want, std::memory_order_release);
+        }
     }
     count_launch();
     cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);

@@ -99,8 +99,12 @@ __device__ __forceinline__ void xchg_push(const PeerXchg& x, int idx, float v) {
     if (x.pull) { *reinterpret_cast<volatile unsigned long long*>(x.rx[x.rank] + off) = w; return; }
     for (int q = 0; q < x.world; ++q) *reinterpret_cast<volatile unsigned long long*>(x.rx[q] + off) = w;
 }
-__device__ __forceinline__ float xchg_pull_sum(const PeerXchg& x, int idx) {
+// A peer that does not answer within ~2 s: losses[7] is set, the caller's `*timed_out` (CTA-shared) is raised and the
+// sum is NaN, so prototypes, losses and gradients of the step are poisoned LOUDLY (the trainer's NaN check fires,
+// Trainer_prototype_full.py:298-299) instead of continuing with stale words; the finish bodies skip the EMA write-back.
+__device__ __forceinline__ float xchg_pull_sum(const PeerXchg& x, int idx, int* timed_out = nullptr) {
     double s = 0.0;
+    bool bad = false;
     for (int q = 0; q < x.world; ++q) {
         // slot [parity][source q] of rank q's own buffer (pull) or of the local buffer (push)
         const volatile unsigned long long* src = x.rx[x.pull ? q : x.rank] + ((size_t)(x.seq & 1u) * x.world + q) * x.n + idx;
@@ -109,10 +113,14 @@ __device__ __forceinline__ float xchg_pull_sum(const PeerXchg& x, int idx) {
             const long long t0 = clock64();
             do {
                 w = *src;
-                if (clock64() - t0 > 4000000000LL) { if (x.err) *x.err = 1.f; break; }     // ~2 s: a peer is gone
+                if (clock64() - t0 > 4000000000LL) { if (x.err) *x.err = 1.f; bad = true; break; }     // ~2 s: a peer is gone
             } while ((unsigned int)(w >> 32) != x.seq);
         }
         s += (double)__uint_as_float((unsigned int)(w & 0xffffffffull));
+    }
+    if (bad) {
+        if (timed_out) *timed_out = 1;
+        return __int_as_float(0x7fc00000);
     }
     return (float)s;
 }
@@ -157,6 +165,8 @@ __device__ __forceinline__ void pool_finish_body(const PoolFinishParams& p, cons
     __shared__ float Nn[2][2 * CLR_MAX_K];
     __shared__ double lp[8 * CLR_MAX_K][NL];
     __shared__ bool is_last;
+    __shared__ int xchg_bad;       // a peer timed out (world > 1): skip the EMA write-back, everything downstream is NaN
+    if (tid == 0) xchg_bad = 0;
     // the stored (EMA) prototypes of this thread's (class, channel) entries: issued before the slot sums, which they do not
     // depend on, so the chain below has one L2 round trip less
     float st_pre[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
@@ -187,22 +197,27 @@ __device__ __forceinline__ void pool_finish_body(const PoolFinishParams& p, cons
         }
     }
     if (p.x.world > 1) {
-        // global sums: thread t < 2R*8 owns (pair, channel), the next 2R threads the weight-sum columns
-        if (tid < 2 * R * 8) {
-            const int pair = tid >> 3, j = tid & 7, d = pair / R, r = pair - d * R, cc = cta * 8 + j;
-            if (cc < C) {
-                const float v = xchg_pull_sum(p.x, (d * R + r) * (C + 1) + cc);
-                S[d][r][j] = v;
-                p.sums[d][(size_t)r * (C + 1) + cc] = v;
+        __syncthreads();           // xchg_bad = 0 is visible before anybody can raise it
+        // global sums: items [0, 2R*8) are (pair, channel) entries, the next 2R the weight-sum columns; looped, because
+        // 2R*8 + 2R exceeds the 256 threads of the CTA for K = 8 (R = 16)
+        for (int it = tid; it < 2 * R * 8 + 2 * R; it += kThreads) {
+            if (it < 2 * R * 8) {
+                const int pair = it >> 3, j = it & 7, d = pair / R, r = pair - d * R, cc = cta * 8 + j;
+                if (cc < C) {
+                    const float v = xchg_pull_sum(p.x, (d * R + r) * (C + 1) + cc, &xchg_bad);
+                    S[d][r][j] = v;
+                    p.sums[d][(size_t)r * (C + 1) + cc] = v;
+                }
+            } else {
+                const int pair = it - 2 * R * 8, d = pair / R, r = pair - d * R;
+                const float v = xchg_pull_sum(p.x, (d * R + r) * (C + 1) + C, &xchg_bad);
+                Nn[d][r] = v;
+                if (cta == 0) p.sums[d][(size_t)r * (C + 1) + C] = v;
             }
-        } else if (tid < 2 * R * 8 + 2 * R) {
-            const int pair = tid - 2 * R * 8, d = pair / R, r = pair - d * R;
-            const float v = xchg_pull_sum(p.x, (d * R + r) * (C + 1) + C);
-            Nn[d][r] = v;
-            if (cta == 0) p.sums[d][(size_t)r * (C + 1) + C] = v;
         }
     }
     __syncthreads();
+    const bool keep_state = xchg_bad == 0;
     if (tid < K * 8) {
         const int k = tid >> 3, j = tid & 7, cc = cta * 8 + j;
         double acc[NL];
@@ -221,7 +236,7 @@ __device__ __forceinline__ void pool_finish_body(const PoolFinishParams& p, cons
                 ps[h] = p.first[0] ? cs : __fadd_rn(__fmul_rn(omd, st_pre[0][h]), __fmul_rn(dd, cs));
                 pt[h] = p.first[1] ? ct : __fadd_rn(__fmul_rn(omd, st_pre[1][h]), __fmul_rn(dd, ct));
                 p.P[0][e] = ps[h]; p.P[1][e] = pt[h];
-                p.stored[0][e] = ps[h]; p.stored[1][e] = pt[h];                  // .detach() copies (Trainer_prototype_full.py:341-344)
+                if (keep_state) { p.stored[0][e] = ps[h]; p.stored[1][e] = pt[h]; }   // .detach() copies (Trainer_prototype_full.py:341-344)
                 const double df = (double)ps[h] - (double)pt[h];
                 acc[0] += df * df;
             }

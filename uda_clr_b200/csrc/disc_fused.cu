@@ -184,11 +184,19 @@ __global__ void __launch_bounds__(NT, (TP == 32 && STAGES <= 4) ? 2 : 1) disc_fu
     // the contraction vectors come from the finish CTAs of the preceding launch: wait for THEM (not for the whole grid),
     // then stage V / beta in shared memory through coherent loads (they were written while this kernel was resident,
     // so the non-coherent __ldg path must not be used for them)
+    // (a missed dependency -- ~2 s -- sets losses[7] and poisons the contraction vectors with NaN: the step's losses and
+    // gradients turn NaN instead of being computed from stale vectors)
+    __shared__ int dep_bad;
+    bool stale = false;
     if (p.wait_fin) {
-        if (tid == 0 && !spin_until_at_least(p.wait_fin, p.wait_fin_n) && p.err) *p.err = 1.f;
+        if (tid == 0) {
+            dep_bad = spin_until_at_least(p.wait_fin, p.wait_fin_n) ? 0 : 1;
+            if (dep_bad && p.err) *p.err = 1.f;
+        }
         __syncthreads();
+        stale = dep_bad != 0;
     }
-    for (int i = tid; i < K * p.C; i += NT) Vs[i] = __ldcg(p.V + i);
+    for (int i = tid; i < K * p.C; i += NT) Vs[i] = stale ? __int_as_float(0x7fc00000) : __ldcg(p.V + i);
     if (p.beta_partial) {
         if (warp < K) {      // K <= 8 = warps of the 256-thread CTA
             double t = 0.0;

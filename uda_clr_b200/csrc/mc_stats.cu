@@ -17,6 +17,78 @@ namespace clr {
 
 __device__ __forceinline__ float sigmoid_aten(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+// ---- torch.std(dim=0) / torch.mean(dim=0) over the T MC passes, in ATen's CUDA evaluation order ------------------
+// (utils/Utils.py:166, 168 run ATen's generic reduction: ReduceMomentKernel.cu / ReduceOps via Reduce.cuh.)  For an
+// outer reduction with fewer than 64 values per output ONE thread reduces an output, with `vt0` interleaved
+// accumulators that are combined at the end (element t goes to accumulator t % vt0): vt0 = 2 Welford accumulators for
+// std, 4 plain sums for mean.  The uncertainty mask `std_small < 0.04` (utils/Utils.py:197-200) is an integer output:
+// it must equal eager torch on the same device, so pixels near the threshold are re-evaluated with exactly this order
+// (guard band, retrify epilogues below); `mc_precise` = 1 computes the whole maps this way (slow, tests).
+// Roundings are pinned with intrinsics to the contraction nvcc applies to ATen's expressions (WelfordOps::reduce:
+// `m2 + delta * (x - new_mean)` -> fma; ::combine: `a.mean + delta * nb_over_n` -> fma, `a.m2 + b.m2 + delta * delta *
+// a.nf * nb_over_n` -> fma of the last product into the sum).  `variant` exists for A/B runs against torch on the GPU
+// (tools/aten_order_probe.py): bit 0 = no fma in reduce, bit 1 = no fma in combine, bits 2-3: vt0 = 2 / 4 / 1.
+struct WelfordAcc { float mean, m2, nf; };
+__device__ __forceinline__ void welford_push(WelfordAcc& a, float x, int variant) {
+    a.nf += 1.0f;
+    const float delta = __fsub_rn(x, a.mean);
+    a.mean = __fadd_rn(a.mean, __fdiv_rn(delta, a.nf));
+    const float nd = __fsub_rn(x, a.mean);
+    a.m2 = (variant & 1) ? __fadd_rn(a.m2, __fmul_rn(delta, nd)) : __fmaf_rn(delta, nd, a.m2);
+}
+__device__ __forceinline__ WelfordAcc welford_merge(const WelfordAcc& a, const WelfordAcc& b, int variant) {
+    if (a.nf == 0.f) return b;
+    if (b.nf == 0.f) return a;
+    const float delta = __fsub_rn(b.mean, a.mean);
+    const float n = __fadd_rn(a.nf, b.nf);
+    const float nb_over_n = __fdiv_rn(b.nf, n);
+    const float dd = __fmul_rn(__fmul_rn(delta, delta), a.nf);
+    WelfordAcc r;
+    if (variant & 2) {
+        r.mean = __fadd_rn(a.mean, __fmul_rn(delta, nb_over_n));
+        r.m2 = __fadd_rn(__fadd_rn(a.m2, b.m2), __fmul_rn(dd, nb_over_n));
+    } else {
+        r.mean = __fmaf_rn(delta, nb_over_n, a.mean);
+        r.m2 = __fmaf_rn(dd, nb_over_n, __fadd_rn(a.m2, b.m2));
+    }
+    r.nf = n;
+    return r;
+}
+__device__ __forceinline__ float sigmoid_half_aten(float p) { return sigmoid_aten(__fmul_rn(p, 0.5f)); }   // preds / 2.0 (:165)
+// std_T(sigmoid(p/2)) (unbiased) at position i of preds [T][n]
+__device__ __noinline__ float std_aten_at(const float* __restrict__ preds, int T, size_t n, size_t i, int variant) {
+    const int vt0 = ((variant >> 2) & 3) == 1 ? 4 : (((variant >> 2) & 3) == 2 ? 1 : 2);
+    WelfordAcc acc[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j] = WelfordAcc{0.f, 0.f, 0.f};
+    for (int t = 0; t < T; ++t) {
+        const float x = sigmoid_half_aten(__ldg(preds + (size_t)t * n + i));
+        const int j = t % vt0;
+        if (j == 0) welford_push(acc[0], x, variant);
+        else if (j == 1) welford_push(acc[1], x, variant);
+        else if (j == 2) welford_push(acc[2], x, variant);
+        else welford_push(acc[3], x, variant);
+    }
+    WelfordAcc r = acc[0];
+    for (int j = 1; j < vt0; ++j) r = welford_merge(r, acc[j], variant);
+    const float divisor = r.nf > 1.0f ? __fsub_rn(r.nf, 1.0f) : 0.0f;      // correction = 1; T = 1 -> 0/0 = NaN like torch
+    return __fsqrt_rn(__fdiv_rn(r.m2, divisor));
+}
+// mean_T(sigmoid(p)) at position i: 4 interleaved partial sums, ((s0 + s1) + s2) + s3, times factor = n_out / numel
+__device__ __noinline__ float mean_aten_at(const float* __restrict__ preds, int T, size_t n, size_t i, float factor) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int t = 0; t < T; ++t) {
+        const float x = sigmoid_aten(__ldg(preds + (size_t)t * n + i));
+        const int j = t & 3;
+        if (j == 0) acc[0] = __fadd_rn(acc[0], x);
+        else if (j == 1) acc[1] = __fadd_rn(acc[1], x);
+        else if (j == 2) acc[2] = __fadd_rn(acc[2], x);
+        else acc[3] = __fadd_rn(acc[3], x);
+    }
+    return __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc[0], acc[1]), acc[2]), acc[3]), factor);
+}
+static inline float mean_factor_aten(size_t n_out, int T) { return (float)n_out / (float)(n_out * (size_t)T); }
+
 // The two sigmoids of one MC logit from ONE exponential:  u = e^{-p/2}:  sigmoid(p/2) = 1/(1+u),
 // sigmoid(p) = 1/(1+u^2).  PRECISE keeps expf + IEEE division for sigmoid(p/2) (ATen's expression, bit for
 // bit); the default uses ex2.approx / rcp.approx (2 MUFU per logit, a few ulp) because with two precise
@@ -44,9 +116,20 @@ __device__ __forceinline__ void mc_sigmoids(float p, float& s_half, float& s_ful
 // preds is [T][n].  TT > 0: T <= TT, values kept in registers (two-pass variance); TT == 0: any T, Welford.
 // EXACT: T == TT is known at compile time (the reference's T = 8): no per-pass predicates -- they were ~10 % of the
 // kernel's instructions (32 BRA + 26 ISETP per thread in the ncu source page) in a pass that is issue / MUFU co-limited.
+struct McAten { int variant; float factor; };     // PRECISE instantiations only: A/B variant, ATen's mean factor
+
 template <int VEC, int TT, bool PRECISE, bool EXACT = false>
-__device__ __forceinline__ void mc_vec_stats(const float* __restrict__ preds, int T_rt, size_t n, size_t i, Pack<VEC>& s, Pack<VEC>& m) {
+__device__ __forceinline__ void mc_vec_stats(const float* __restrict__ preds, int T_rt, size_t n, size_t i, Pack<VEC>& s, Pack<VEC>& m,
+                                             const McAten aten = McAten{0, 0.f}) {
     const int T = EXACT ? TT : T_rt;
+    if constexpr (PRECISE) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            s.v[v] = std_aten_at(preds, T, n, i + v, aten.variant);
+            m.v[v] = mean_aten_at(preds, T, n, i + v, aten.factor);
+        }
+        return;
+    }
     float mean_h[VEC], m2[VEC], mean_f[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) { mean_h[v] = 0.f; m2[v] = 0.f; mean_f[v] = 0.f; }
@@ -102,13 +185,14 @@ __device__ __forceinline__ void mc_vec_stats(const float* __restrict__ preds, in
 
 template <int VEC, int TT, bool PRECISE, bool EXACT = false>
 __global__ void __launch_bounds__(256) mc_stats_kernel(const float* __restrict__ preds, int T, size_t n,
-                                                       float* __restrict__ std_map, float* __restrict__ pred_mean) {
+                                                       float* __restrict__ std_map, float* __restrict__ pred_mean,
+                                                       const McAten aten) {
     kernel_begin(TR_MC_STATS);
     // n = B*K*Hi*Wi positions
     const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
     if (i >= n) { trace_exit(TR_MC_STATS); return; }
     Pack<VEC> s, m;
-    mc_vec_stats<VEC, TT, PRECISE, EXACT>(preds, T, n, i, s, m);
+    mc_vec_stats<VEC, TT, PRECISE, EXACT>(preds, T, n, i, s, m, aten);
     st_keep<VEC>(std_map + i, s);
     st_keep<VEC>(pred_mean + i, m);
     trace_exit(TR_MC_STATS);
@@ -118,10 +202,12 @@ template <int VEC, bool PRECISE>
 static void launch_mc(const float* preds, int T, size_t n, float* std_map, float* pred_mean, cudaStream_t st) {
     const size_t threads = (n + VEC - 1) / VEC;
     const unsigned blocks = (unsigned)((threads + 255) / 256);
-    if (T == 8 && !tunables().mc_generic) launch_k(mc_stats_kernel<VEC, 8, PRECISE, true>, blocks, 256, 0, st, preds, T, n, std_map, pred_mean);
-    else if (T <= 8) launch_k(mc_stats_kernel<VEC, 8, PRECISE>, blocks, 256, 0, st, preds, T, n, std_map, pred_mean);
-    else if (T <= 16) launch_k(mc_stats_kernel<VEC, 16, PRECISE>, blocks, 256, 0, st, preds, T, n, std_map, pred_mean);
-    else launch_k(mc_stats_kernel<VEC, 0, PRECISE>, blocks, 256, 0, st, preds, T, n, std_map, pred_mean);
+    const McAten aten{tunables().aten_variant, mean_factor_aten(n, T)};
+    if (PRECISE) launch_k(mc_stats_kernel<VEC, 0, PRECISE>, blocks, 256, 0, st, preds, T, n, std_map, pred_mean, aten);
+    else if (T == 8 && !tunables().mc_generic) launch_k(mc_stats_kernel<VEC, 8, PRECISE, true>, blocks, 256, 0, st, preds, T, n, std_map, pred_mean, aten);
+    else if (T <= 8) launch_k(mc_stats_kernel<VEC, 8, PRECISE>, blocks, 256, 0, st, preds, T, n, std_map, pred_mean, aten);
+    else if (T <= 16) launch_k(mc_stats_kernel<VEC, 16, PRECISE>, blocks, 256, 0, st, preds, T, n, std_map, pred_mean, aten);
+    else launch_k(mc_stats_kernel<VEC, 0, PRECISE>, blocks, 256, 0, st, preds, T, n, std_map, pred_mean, aten);
 }
 
 // upsample_bilinear2d (align_corners=True) source coordinates, as ATen computes them in fp32
@@ -148,8 +234,22 @@ __device__ __forceinline__ float bilinear_at(const float* __restrict__ plane, in
     return bilinear_mix(__ldg(r0 + w.i0), __ldg(r0 + w.i1), __ldg(r1 + w.i0), __ldg(r1 + w.i1), h, w);
 }
 
+// Guard band of the uncertainty mask: the streaming statistics use approximate sigmoids and a two-pass variance (error
+// of std_small <= ~3e-7); a pixel whose value lies within kMaskBand of the threshold is decided by this
+// exact re-evaluation instead -- its 4 bilinear taps recomputed from the MC logits in ATen's order -- so that mask_k is
+// bit-identical to eager torch on the same device (utils/Utils.py:166, 171, 197-200) at streaming speed.
+constexpr float kMaskBand = 1e-5f;
+__device__ __noinline__ float std_small_aten(const float* __restrict__ preds, int T, size_t n, size_t plane, int Wi,
+                                             const Tap& h, const Tap& w, int variant) {
+    const size_t r0 = plane + (size_t)h.i0 * Wi, r1 = plane + (size_t)h.i1 * Wi;
+    const float a = std_aten_at(preds, T, n, r0 + w.i0, variant), b = std_aten_at(preds, T, n, r0 + w.i1, variant);
+    const float c = std_aten_at(preds, T, n, r1 + w.i0, variant), d = std_aten_at(preds, T, n, r1 + w.i1, variant);
+    return bilinear_mix(a, b, c, d, h, w);
+}
+
 __global__ void __launch_bounds__(256) retrify_weights_kernel(
     const float* __restrict__ oT_before, const float* __restrict__ pred_mean, const float* __restrict__ std_map,
+    const float* __restrict__ preds /*[T][B,K,Hi,Wi] or null: no guard band*/, int T, int variant,
     int B, int K, int H, int W, int Hi, int Wi, float pseudo_thr, float std_thr,
     float* __restrict__ weights /*[B,2K,H,W]*/, float* __restrict__ masks /*[B,K,H,W]*/,
     float* __restrict__ pseudo_out /*[B,K,H,W] or null*/, float* __restrict__ small_out /*[2][B,K,H,W] or null*/) {
@@ -169,7 +269,9 @@ __global__ void __launch_bounds__(256) retrify_weights_kernel(
     const float ps = bilinear_at(pred_mean + plane, Wi, th, tw);
     const float ss = bilinear_at(std_map + plane, Wi, th, tw);
     const bool pseudo = sigmoid_aten(oT_before[i]) > pseudo_thr;
-    const bool m = ss < std_thr;
+    bool m = ss < std_thr;
+    if (preds != nullptr && fabsf(ss - std_thr) < kMaskBand)
+        m = std_small_aten(preds, T, (size_t)B * K * Hi * Wi, plane, Wi, th, tw, variant) < std_thr;
     const size_t hw = (size_t)H * W, pix = (size_t)y * W + x;
     weights[((size_t)b * 2 * K + k) * hw + pix] = (pseudo && m) ? ps : 0.f;
     weights[((size_t)b * 2 * K + K + k) * hw + pix] = (!pseudo && m) ? (1.0f - ps) : 0.f;
@@ -195,6 +297,7 @@ struct McRetrifyParams {
     int parts, cw;            // the image rows are split into `parts` column blocks of cw floats, one CTA each
     float sh, sw, pseudo_thr, std_thr;
     size_t n;
+    McAten aten;
 };
 
 template <int TT, bool PRECISE>
@@ -221,7 +324,7 @@ __global__ void __launch_bounds__(256, 4) mc_retrify_kernel(const McRetrifyParam
         const int row = r0 + rr;
         const size_t i = plane + (size_t)row * p.Wi + c0 + 4 * xv;
         Pack<4> s, m;
-        mc_vec_stats<4, TT, PRECISE>(p.preds, p.T, p.n, i, s, m);
+        mc_vec_stats<4, TT, PRECISE>(p.preds, p.T, p.n, i, s, m, p.aten);
         st_keep<4>(p.std_map + i, s);
         if (p.pred_mean) st_keep<4>(p.pred_mean + i, m);
         if (row == r0) { st_keep<4>(taps + 4 * xv, s); st_keep<4>(taps + 2 * p.cw + 4 * xv, m); }
@@ -243,7 +346,9 @@ __global__ void __launch_bounds__(256, 4) mc_retrify_kernel(const McRetrifyParam
         const size_t i = (size_t)bk * hw + pix;
         const float o = (x == xg) ? o_pre : __ldg(p.oT_before + i);
         const bool pseudo = sigmoid_aten(o) > p.pseudo_thr;
-        const bool m = ss < p.std_thr;
+        bool m = ss < p.std_thr;
+        if (!PRECISE && fabsf(ss - p.std_thr) < kMaskBand)
+            m = std_small_aten(p.preds, p.T, p.n, plane, p.Wi, th, tw, p.aten.variant) < p.std_thr;
         p.weights[((size_t)b * 2 * p.K + k) * hw + pix] = (pseudo && m) ? ps : 0.f;
         p.weights[((size_t)b * 2 * p.K + p.K + k) * hw + pix] = (!pseudo && m) ? (1.0f - ps) : 0.f;
         p.masks[i] = m ? 2.0f : 0.f;
@@ -288,18 +393,13 @@ int mc_retrify_fused(const float* preds, const float* oT_before, int T, int B, i
     p.sh = sh_f; p.sw = sw_f; p.parts = parts; p.cw = Wi / parts;
     p.pseudo_thr = pseudo_thr; p.std_thr = std_thr;
     p.n = (size_t)B * K * Hi * Wi;
+    p.aten = McAten{tunables().aten_variant, mean_factor_aten(p.n, T)};
     const dim3 grid((unsigned)(H * parts), (unsigned)(B * K));
     const bool precise = tunables().mc_precise != 0;
-    if (T <= 8) {
-        if (precise) launch_k(mc_retrify_kernel<8, true>, grid, 256, smem, st, p);
-        else launch_k(mc_retrify_kernel<8, false>, grid, 256, smem, st, p);
-    } else if (T <= 16) {
-        if (precise) launch_k(mc_retrify_kernel<16, true>, grid, 256, smem, st, p);
-        else launch_k(mc_retrify_kernel<16, false>, grid, 256, smem, st, p);
-    } else {
-        if (precise) launch_k(mc_retrify_kernel<0, true>, grid, 256, smem, st, p);
-        else launch_k(mc_retrify_kernel<0, false>, grid, 256, smem, st, p);
-    }
+    if (precise) launch_k(mc_retrify_kernel<0, true>, grid, 256, smem, st, p);
+    else if (T <= 8) launch_k(mc_retrify_kernel<8, false>, grid, 256, smem, st, p);
+    else if (T <= 16) launch_k(mc_retrify_kernel<16, false>, grid, 256, smem, st, p);
+    else launch_k(mc_retrify_kernel<0, false>, grid, 256, smem, st, p);
     return launch_status();
 }
 
@@ -325,13 +425,14 @@ int clr_mc_stats(const float* preds, int T, int B, int K, int Hi, int Wi,
 }
 
 int clr_retrify_weights(const float* oT_before, const float* pred_mean, const float* std_map,
+                        const float* preds, int T,
                         int B, int K, int H, int W, int Hi, int Wi, float pseudo_thr, float std_thr,
                         float* weights, float* masks, float* pseudo_out, float* small_out, clr_stream_t stream) {
     if (!oT_before || !pred_mean || !std_map || !weights || !masks || B < 1 || K < 1 || K > CLR_MAX_K ||
-        H < 1 || W < 1 || Hi < 1 || Wi < 1)
+        H < 1 || W < 1 || Hi < 1 || Wi < 1 || (preds && T < 1))
         return CLR_ERR_BAD_ARG;
     if ((long long)H * W > 0x7fffff00LL || (long long)B * K > 65535) return CLR_ERR_UNSUPPORTED;
-    clr::launch_k(clr::retrify_weights_kernel, dim3((unsigned)((H * W + 255) / 256), (unsigned)(B * K)), 256, 0, static_cast<cudaStream_t>(stream), oT_before, pred_mean, std_map, B, K, H, W, Hi, Wi, pseudo_thr, std_thr, weights, masks, pseudo_out, small_out);
+    clr::launch_k(clr::retrify_weights_kernel, dim3((unsigned)((H * W + 255) / 256), (unsigned)(B * K)), 256, 0, static_cast<cudaStream_t>(stream), oT_before, pred_mean, std_map, preds, T, clr::tunables().aten_variant, B, K, H, W, Hi, Wi, pseudo_thr, std_thr, weights, masks, pseudo_out, small_out);
     return clr::launch_status();
 }
 

@@ -77,10 +77,19 @@ __device__ __forceinline__ void pool_bwd_body(const BwdParams& p, int bid) {
         }
     }
     const bool gated = p.gate != nullptr && d == p.gate_dom;      // CTA-uniform
+    __shared__ int gate_bad;
     if (gated) {
-        if (tid == 0 && !spin_until_at_least(p.gate, p.gate_n) && p.gate_err) *p.gate_err = 1.f;
+        // The finish CTAs have lower block indices than every gated CTA of the same grid and CTAs are dispatched in index
+        // order, so they are resident (or done) before a gated CTA can spin.  That order is de-facto hardware behaviour, not
+        // a documented guarantee: if the gate is ever missed (~2 s) the CTA sets losses[7] and writes NaN gradients -- loud,
+        // never silently wrong -- and "bwd_merge_off" = 1 selects the two-launch form that needs no gate.
+        if (tid == 0) {
+            gate_bad = spin_until_at_least(p.gate, p.gate_n) ? 0 : 1;
+            if (gate_bad && p.gate_err) *p.gate_err = 1.f;
+        }
         __syncthreads();
     }
+    const float poison = (gated && gate_bad) ? __int_as_float(0x7fc00000) : 1.0f;
     // vectors the finish CTAs of the same launch may have written: coherent loads when gated
     auto ldv = [gated](const float* q_) -> float { return gated ? __ldcg(q_) : __ldg(q_); };
     // ---- per-CTA table for channels c0 .. c0+31: T[0] constant term, T[1+q] coefficient of plane q.
@@ -88,7 +97,7 @@ __device__ __forceinline__ void pool_bwd_body(const BwdParams& p, int bid) {
     {
         const int j = tid & (kBwdSpan - 1), q = tid / kBwdSpan;     // q in [0, 8): rows 0..QT handled in rounds
         const int c = c0 + j;
-        const float scale = D.scale_dev ? D.scale * __ldg(D.scale_dev) : D.scale;
+        const float scale = poison * (D.scale_dev ? D.scale * __ldg(D.scale_dev) : D.scale);
         const float* sums = D.per_sample ? D.sums + (size_t)b * D.nrows * (p.C + 1) : D.sums;
         const float nadd = D.n_add;
         for (int row = q; row <= QT; row += kThreads / kBwdSpan) {
@@ -108,7 +117,7 @@ __device__ __forceinline__ void pool_bwd_body(const BwdParams& p, int bid) {
                         t = gr;
                     }
                 } else if (row - 1 < Q) {
-                    t = (D.scale_dev ? __ldg(D.scale_dev) : 1.f) * ldv(D.xtab + (size_t)(row - 1 - QW) * p.C + c);
+                    t = poison * (D.scale_dev ? __ldg(D.scale_dev) : 1.f) * ldv(D.xtab + (size_t)(row - 1 - QW) * p.C + c);
                 }
             }
             T[row * kBwdSpan + j] = t;

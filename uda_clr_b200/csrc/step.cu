@@ -87,7 +87,7 @@ int clr_step_fwd_a(const clr_step_args* a, clr_stream_t stream) {
     if (a->use_retrify) {
         rc = clr_mc_stats(a->preds, a->T, a->B_t, a->K, a->Hi, a->Wi, a->std_map, a->pred_mean, stream);
         if (rc != CLR_OK) return rc;
-        rc = clr_retrify_weights(a->oT_before, a->pred_mean, a->std_map, a->B_t, a->K, a->H, a->W, a->Hi, a->Wi,
+        rc = clr_retrify_weights(a->oT_before, a->pred_mean, a->std_map, a->preds, a->T, a->B_t, a->K, a->H, a->W, a->Hi, a->Wi,
                                  a->pseudo_thr, a->std_thr, a->wt_retrify, a->masks, nullptr, nullptr, stream);
         if (rc != CLR_OK) return rc;
     }
@@ -216,7 +216,7 @@ static int step_fwd_core(const clr_step_args* a, cudaStream_t st, DiscFinishPara
         if (rc == CLR_ERR_UNSUPPORTED) {
             rc = clr_mc_stats(a->preds, a->T, a->B_t, K, a->Hi, a->Wi, a->std_map, a->pred_mean, stream);
             if (rc != CLR_OK) return rc;
-            rc = clr_retrify_weights(a->oT_before, a->pred_mean, a->std_map, a->B_t, K, a->H, a->W, a->Hi, a->Wi,
+            rc = clr_retrify_weights(a->oT_before, a->pred_mean, a->std_map, a->preds, a->T, a->B_t, K, a->H, a->W, a->Hi, a->Wi,
                                      a->pseudo_thr, a->std_thr, a->wt_retrify, a->masks, nullptr, nullptr, stream);
         }
         if (rc != CLR_OK) return rc;

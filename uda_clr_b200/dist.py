@@ -95,6 +95,36 @@ def peer_buffers(K: int, C: int, device) -> dict:
     return _PEER[key]
 
 
+def close_peer() -> None:
+    """Unmap every peer's receive buffer and free the local ones (collective in spirit: call it on every rank once no
+    step is in flight, before ``destroy_process_group``).  Plans built on the freed buffers must not run afterwards."""
+    from . import _lib
+    if not _PEER:
+        return
+    lib = _lib.load()
+    torch.cuda.synchronize()
+    for peer in _PEER.values():
+        for q, pq in enumerate(peer["ptrs"]):
+            if q != peer["rank"] and pq:
+                lib.clr_peer_close(pq)
+        lib.clr_peer_free(peer["local"])
+    _PEER.clear()
+
+
+class local:
+    """Context manager: run the enclosed steps as a single-process job (no exchange), e.g. a rank that recomputes the
+    whole batch as a parity reference next to the sharded step."""
+
+    def __enter__(self):
+        self._saved = dict(_STATE)
+        _STATE.update(enabled=False, peer=False)
+        return self
+
+    def __exit__(self, *exc):
+        _STATE.update(self._saved)
+        return False
+
+
 def next_seq(peer: dict) -> int:
     """Sequence number of the next exchange on these buffers (identical on every rank: one per fused step)."""
     peer["seq"] = (peer["seq"] % 0xFFFFFFFE) + 1

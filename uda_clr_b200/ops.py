@@ -211,9 +211,12 @@ def mc_statistics(preds: torch.Tensor, T: int, stride: int):
 
 
 def retrify_weights(oT_before: torch.Tensor, pred_mean: torch.Tensor, std_map: torch.Tensor, H: int, W: int,
-                    pseudo_thr: float = PSEUDO_THRESHOLD, std_thr: float = STD_THRESHOLD, debug: bool = False):
+                    pseudo_thr: float = PSEUDO_THRESHOLD, std_thr: float = STD_THRESHOLD, debug: bool = False,
+                    preds: Optional[torch.Tensor] = None, T: int = 0):
     """Explicit target weights ``[B,2K,H,W]`` and uncertainty masks ``[B,K,H,W]`` in {0,2}
-    (utils/Utils.py:170-223).  ``debug=True`` also returns the pseudo-labels and the two down-sampled maps."""
+    (utils/Utils.py:170-223).  ``debug=True`` also returns the pseudo-labels and the two down-sampled maps.
+    ``preds`` / ``T`` (the MC logits ``mc_statistics`` was computed from): pixels whose std lies within 1e-5 of the
+    threshold are re-evaluated from them in ATen's exact order, so the masks equal eager torch bit for bit."""
     lib = _lib.load()
     o = _require_cuda_f32(oT_before, "oT_before")
     B, K = o.shape[:2]
@@ -223,7 +226,8 @@ def retrify_weights(oT_before: torch.Tensor, pred_mean: torch.Tensor, std_map: t
     pseudo = torch.empty(B, K, H, W, dtype=torch.float32, device=o.device) if debug else None
     small = torch.empty(2, B, K, H, W, dtype=torch.float32, device=o.device) if debug else None
     with torch.cuda.device(o.device):
-        check(lib.clr_retrify_weights(ptr(o), ptr(pred_mean), ptr(std_map), B, K, H, W, Hi, Wi,
+        pr = None if preds is None else _require_cuda_f32(preds, "preds")
+        check(lib.clr_retrify_weights(ptr(o), ptr(pred_mean), ptr(std_map), ptr(pr), int(T), B, K, H, W, Hi, Wi,
                                       float(pseudo_thr), float(std_thr), ptr(weights), ptr(masks),
                                       ptr(pseudo), ptr(small), _stream()), "clr_retrify_weights")
     if debug:
@@ -251,7 +255,7 @@ def mc_retrify(oT_before: torch.Tensor, preds: torch.Tensor, T: int, stride: int
                                 ptr(std_map), None, ptr(weights), ptr(masks), _stream())
     if rc == _lib.CLR_ERR_UNSUPPORTED:
         std_map, pred_mean = mc_statistics(p, T, stride)
-        weights, masks = retrify_weights(o, pred_mean, std_map, H, W, pseudo_thr, std_thr)
+        weights, masks = retrify_weights(o, pred_mean, std_map, H, W, pseudo_thr, std_thr, preds=p, T=T)
         return std_map, weights, masks
     check(rc, "clr_mc_retrify")
     return std_map, weights, masks

@@ -51,6 +51,13 @@ class CLRStepOutput:
     target_prototypes: List[torch.Tensor]
     std_map: Optional[torch.Tensor]         # [B,K,Hi,Wi] (retrify)
     masks: Optional[List[torch.Tensor]]     # K x [B,1,H,W] in {0,2} (retrify)
+    error: Optional[torch.Tensor] = None    # device scalar, 0 = ok; 1 = a device-side wait of the step timed out (a peer
+                                            # of the in-kernel exchange is gone, or a gate was missed): the step's losses
+                                            # and gradients are NaN then and the EMA state was left untouched
+
+
+class CLRStepError(RuntimeError):
+    """A device-side wait of the fused step timed out (``losses[7]`` != 0)."""
 
 
 class _Buffers:
@@ -78,8 +85,8 @@ class _ClrStepFn(torch.autograd.Function):
     def forward(ctx, step, args_holder, xs, xt, oT_aug, wt_soft=None):
         lib = _lib.load()
         a: StepArgs = args_holder["args"]
-        st = _stream()
         with torch.cuda.device(xs.device):
+            st = _stream()              # the current stream of the tensors' device, not of whatever device is current
             if args_holder["peer"] is not None:
                 a.seq = _dist.next_seq(args_holder["peer"])
                 check(lib.clr_step_fwd(ctypes.byref(a), st), "clr_step_fwd (in-kernel exchange)")
@@ -148,14 +155,26 @@ class CLRStep:
         self.stored_t: Optional[torch.Tensor] = None
         self.first_s = True
         self.first_t = True
-        self._ws: Optional[torch.Tensor] = None
 
     # -- state -------------------------------------------------------------------------------------
     def state_dict(self):
-        return dict(stored_s=self.stored_s, stored_t=self.stored_t, first_s=self.first_s, first_t=self.first_t)
+        """Snapshot (clones: later steps update the live EMA tensors in place)."""
+        return dict(stored_s=None if self.stored_s is None else self.stored_s.clone(),
+                    stored_t=None if self.stored_t is None else self.stored_t.clone(),
+                    first_s=self.first_s, first_t=self.first_t, K=self.K)
 
     def load_state_dict(self, sd):
-        self.stored_s, self.stored_t = sd["stored_s"], sd["stored_t"]
+        ss, st_ = sd["stored_s"], sd["stored_t"]
+        if (ss is None) != (st_ is None):
+            raise ValueError("stored_s / stored_t must both be present or both be None")
+        if ss is not None:
+            for name, t in (("stored_s", ss), ("stored_t", st_)):
+                if not (isinstance(t, torch.Tensor) and t.dtype == torch.float32 and t.dim() == 2 and t.shape[0] == 2 * self.K):
+                    raise ValueError("%s must be a float32 [2K=%d, C] tensor" % (name, 2 * self.K))
+            if ss.shape != st_.shape or ss.device != st_.device:
+                raise ValueError("stored_s / stored_t disagree in shape or device")
+            ss, st_ = ss.detach().clone().contiguous(), st_.detach().clone().contiguous()
+        self.stored_s, self.stored_t = ss, st_
         self.first_s, self.first_t = bool(sd["first_s"]), bool(sd["first_t"])
 
     # -- the step ------------------------------------------------------------------------------------
@@ -206,6 +225,9 @@ class CLRStep:
         if self.stored_s is None:
             self.stored_s = torch.zeros(2 * K, C, dtype=torch.float32, device=dev)
             self.stored_t = torch.zeros(2 * K, C, dtype=torch.float32, device=dev)
+        elif self.stored_s.shape != (2 * K, C) or self.stored_s.device != dev or not self.stored_s.is_cuda:
+            raise ValueError("EMA state is %s on %s, the step needs [%d, %d] on %s (load_state_dict / a different C?)"
+                             % (tuple(self.stored_s.shape), self.stored_s.device, 2 * K, C, dev))
 
         a = StepArgs()
         a.B_s, a.B_t, a.C, a.H, a.W, a.K = B_s, B_t, C, H, W, K
@@ -243,13 +265,14 @@ class CLRStep:
                 a.peer_rx[q] = pq
         a.ws = None
         ws_bytes = lib.clr_step_ws_bytes(ctypes.byref(a))
-        if self._ws is None or self._ws.numel() < ws_bytes or self._ws.device != dev:
-            self._ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        a.ws, a.ws_bytes = ptr(self._ws), ws_bytes
+        # one workspace per call / plan (it holds the per-CTA partials and the completion / gate counters of ONE step in
+        # flight): two plans of the same CLRStep never share it.  The EMA state IS shared -- drive one CLRStep from one stream.
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        a.ws, a.ws_bytes = ptr(ws), ws_bytes
 
         wt_soft = wt if (not self.retrify and isinstance(wt, torch.Tensor) and wt.requires_grad) else None
         holder = dict(args=a, buf=buf, xs=xs, xt=xt, oT_aug=oTa, dims=(B_s, B_t, C, H, W, K, Hi, Wi), peer=peer, wt_soft=wt_soft,
-                      keep=(xs, ys, xt, wt_t, oTb, pr, oT_d, oTa, self.stored_s, self.stored_t, self._ws,
+                      keep=(xs, ys, xt, wt_t, oTb, pr, oT_d, oTa, self.stored_s, self.stored_t, ws,
                             masks_t if (use_cons and not self.retrify) else None))
         return holder
 
@@ -266,7 +289,7 @@ class CLRStep:
             m = buf.masks.view(B_t, K, H, W)
             mask_list = [m[:, k:k + 1] for k in range(K)]
         return CLRStepOutput(total=total, intra=L[0], inter=L[1], disc=L[2], aug=L[3], source_prototypes=Ps,
-                             target_prototypes=Pt, std_map=std_map, masks=mask_list)
+                             target_prototypes=Pt, std_map=std_map, masks=mask_list, error=L[7])
 
     def __call__(self, xs_feature, pred_oS, xt_feature, oT_before=None, wt=None, preds=None, T: int = 8,
                  oT=None, oT_aug=None, masks=None, epoch: float = 0.0) -> CLRStepOutput:
@@ -327,7 +350,22 @@ class CLRPlan:
         a.ev_bwd_begin = None if bwd_begin is None else bwd_begin.handle
         a.ev_bwd_end = None if bwd_end is None else bwd_end.handle
 
+    @property
+    def error(self) -> torch.Tensor:
+        """Device scalar (``losses[7]``): 0 = ok, 1 = a device-side wait timed out (see :class:`CLRStepOutput`)."""
+        return self.losses[7]
+
+    def check(self) -> None:
+        """Synchronise and raise :class:`CLRStepError` if any step run so far on this plan timed out on the device."""
+        if float(self.losses[7]) != 0.0:
+            raise CLRStepError("fused CLR step: a device-side wait timed out (in-kernel exchange peer missing or gate missed); "
+                               "losses / gradients of that step are NaN, the EMA state was not advanced")
+
     def run(self) -> None:
+        with torch.cuda.device(self.device):
+            self._run()
+
+    def _run(self) -> None:
         a: StepArgs = self.holder["args"]
         st = _stream()
         a.first_s, a.first_t = int(self.step.first_s), int(self.step.first_t)
