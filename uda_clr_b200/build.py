@@ -77,12 +77,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJDIR, exist_ok=True)
     with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 2)) as ex:
         objs = list(ex.map(lambda s: _compile(nvcc, s, verbose), sources()))
-    cmd = [nvcc, "-shared", "-cudart", "static", "-o", LIB] + objs
+    # link into a temporary name and rename: a reader (ctypes.CDLL, a snapshot of the tree) never sees a half-written file
+    tmp = LIB + ".tmp%d" % os.getpid()
+    cmd = [nvcc, "-shared", "-cudart", "static", "-o", tmp] + objs
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
-    with open(STAMP, "w") as fh:
+    os.replace(tmp, LIB)
+    with open(STAMP + ".tmp", "w") as fh:
         fh.write(source_digest())
+    os.replace(STAMP + ".tmp", STAMP)
     return LIB
 
 

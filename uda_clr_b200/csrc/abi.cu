@@ -56,6 +56,9 @@ int clr_set_tunable(const char* name, int value) {
     else if (!strcmp(name, "bwd_merge_off")) t.bwd_merge_off = value;
     else if (!strcmp(name, "fin_early_off")) t.fin_early_off = value;
     else if (!strcmp(name, "mc_split")) t.mc_split = value;
+    else if (!strcmp(name, "disc_reverse")) t.disc_reverse = value;
+    else if (!strcmp(name, "pool_order")) t.pool_order = value;
+    else if (!strcmp(name, "cons_ef")) t.cons_ef = value;
     else return CLR_ERR_BAD_ARG;
     return CLR_OK;
 }

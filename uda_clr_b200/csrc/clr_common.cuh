@@ -47,6 +47,9 @@ struct Tunables {
     int mc_split;      // 1 = one-pass mc_retrify kernel splits image rows into column blocks (more, smaller CTAs)
     int flag_dep_off;  // 1 = the discriminative kernel waits for the whole [finish | consistency] grid (griddepcontrol.wait)
                        //     instead of the finish CTAs' completion counter
+    int disc_reverse;  // 1 = the one-read discriminative kernel walks its tiles in descending address order
+    int pool_order;    // 1 = two-domain pooling: every CTA reads its share of domain 0 (target) first, then domain 1 (source)
+    int cons_ef;       // 1 = the consistency pass loads its logits with an L2 evict-first policy
     int xchg_pull;     // in-kernel exchange: 1 = readers poll the peers' buffers (no remote stores), 0 = senders push
     void* trace_buf;   // device TraceRec[kTraceSlots] or NULL (clr_trace_set): device-side timeline of the kernels
 };
@@ -153,6 +156,24 @@ template <>
 __device__ __forceinline__ Pack<1> ld_stream<1>(const float* p) {
     Pack<1> r;
     asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r.v[0]) : "l"(p));
+    return r;
+}
+
+// The same with an explicit L2 policy (createpolicy.*): e.g. evict-first for a stream that must not displace lines a later
+// kernel of the step re-reads from L2.
+template <int VEC>
+__device__ __forceinline__ Pack<VEC> ld_stream_hint(const float* p, uint64_t pol);
+template <>
+__device__ __forceinline__ Pack<4> ld_stream_hint<4>(const float* p, uint64_t pol) {
+    Pack<4> r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]) : "l"(p), "l"(pol));
+    return r;
+}
+template <>
+__device__ __forceinline__ Pack<1> ld_stream_hint<1>(const float* p, uint64_t pol) {
+    Pack<1> r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(r.v[0]) : "l"(p), "l"(pol));
     return r;
 }
 

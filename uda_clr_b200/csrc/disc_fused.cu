@@ -49,6 +49,7 @@ struct DiscParams {
     float* hinge;           // [grid]
     float alpha, margin;
     int B, C, HW, tilesPerSample, total, stages;
+    int reverse;            // 1: walk the tiles in DESCENDING address order (L2 harvest of what the pooling pass read last)
     int rows_box, nbox;     // TMA path: the [C x 32] tile is fetched as nbox boxes of rows_box channel rows (rows_box % 8 == 0)
     // flag dependency (clr_common.cuh): instead of griddepcontrol.wait on the whole producer grid, wait until `wait_fin`
     // reaches wait_fin_n before the first read of V / beta, and until `wait_all` reaches wait_all_n before exiting
@@ -158,8 +159,13 @@ __global__ void __launch_bounds__(NT, (TP == 32 && STAGES <= 4) ? 2 : 1) disc_fu
     };
     // (b, tile) of the item `step` further on
     auto advance = [&](int& b, int& tile) {
-        tile += step;
-        while (tile >= p.tilesPerSample) { tile -= p.tilesPerSample; ++b; }
+        if (p.reverse) {
+            tile -= step;
+            while (tile < 0) { tile += p.tilesPerSample; --b; }
+        } else {
+            tile += step;
+            while (tile >= p.tilesPerSample) { tile -= p.tilesPerSample; ++b; }
+        }
     };
 
     const int g = tid % NG, s = tid / NG;
@@ -173,7 +179,8 @@ __global__ void __launch_bounds__(NT, (TP == 32 && STAGES <= 4) ? 2 : 1) disc_fu
 #pragma unroll
     for (int i = 0; i < NE; ++i) ncf[i] = 0.f;
 
-    int b = begin / p.tilesPerSample, tile = begin - b * p.tilesPerSample;   // current item
+    const int first = p.reverse ? (p.total - 1 - begin) : begin;             // (negative only when this CTA has no item)
+    int b = first >= 0 ? first / p.tilesPerSample : 0, tile = first >= 0 ? first - b * p.tilesPerSample : 0;   // current item
     int fb = b, ftile = tile;                                               // next item to fetch
     int fetched = begin;
 #pragma unroll
@@ -408,6 +415,7 @@ static int finish_launch_geometry(DiscParams& p, int TP, int occ, int* nparts) {
     const long long total = (long long)p.B * p.tilesPerSample;
     if (total > 0x3fffffff) return -1;
     p.total = (int)total;
+    p.reverse = tunables().disc_reverse;
     int grid = device_facts().sms * occ;
     if (grid > p.total) grid = p.total;
     if (grid > *nparts) grid = *nparts;

@@ -49,6 +49,7 @@ struct PoolParams {
     int stages;       // TMA ring depth
     int reduce_trace_id;
     int skip_reduce;               // 1: the caller reduces the partials itself (pool_finish_kernel)
+    int phase_split;               // LDG kernel, two domains: all of domain 0 before all of domain 1 (see the kernel)
     unsigned int* counter_reset;   // optional: 4 words zeroed by CTA 0 (the finish stage's last-CTA and completion counters)
 };
 
@@ -198,10 +199,20 @@ __global__ void __launch_bounds__(NT, 2) pool_fwd_ldg_kernel(const PoolParams p)
     float* wsm = smem;                 // [R][PX]
     float* red = smem + R * PX;        // [2][NB][kWarps][32]
     const int tid = threadIdx.x;
-    int begin, end;
-    partition(p.total, gridDim.x, blockIdx.x, begin, end);
     int cur_key = -1, parity = 0;
     auto sync = [] { __syncthreads(); };
+    // phase_split: every CTA first walks its share of domain 0 and then its share of domain 1, so the whole grid reads the
+    // second map (the source features in the fused step) LAST -- the part of it that is still in L2 when the discriminative
+    // pass re-reads it is then as large as the cache allows.  Otherwise one contiguous range of [dom 0 | dom 1] per CTA.
+    const int nph = p.phase_split ? p.ndom : 1;
+    for (int ph = 0; ph < nph; ++ph) {
+    int begin, end;
+    if (p.phase_split) {
+        partition(p.dom[ph].items, gridDim.x, blockIdx.x, begin, end);
+        if (ph) { begin += p.dom[0].items; end += p.dom[0].items; }
+    } else {
+        partition(p.total, gridDim.x, blockIdx.x, begin, end);
+    }
     for (int it = begin; it < end; ++it) {
         const ItemCoord ic = decode_item(p, it);
         const PoolDom& D = p.dom[ic.d];
@@ -241,6 +252,7 @@ __global__ void __launch_bounds__(NT, 2) pool_fwd_ldg_kernel(const PoolParams p)
         }
         float* out = D.partial + (size_t)ic.slot * R * (p.C + 1);
         reduce_and_store<R, CG, VEC, REPS, NT>(acc, wsm, red, parity, out, p.C, c0, ic.grp == 0, tid, sync);
+    }
     }
     trace_exit(TR_POOL);
 }
@@ -551,6 +563,7 @@ int pool_fwd_impl(const float* feat0, const float* w0, int fmt0, int B0, float* 
         p.dom[1] = PoolDom{feat1, w1, wsf + partial_floats(B0, C, HW, R), sums1, B1, fmt1, (int)items1, B1 * p.nChunk, keep1};
     p.total = (int)(items0 + items1);
     p.reduce_trace_id = TR_POOL_REDUCE;
+    p.phase_split = (ndom == 2 && tunables().pool_order) ? 1 : 0;
     p.counter_reset = counter_reset;
     if (skip_reduce_layout) {
         p.skip_reduce = 1;
