@@ -167,3 +167,27 @@ def test_two_rank_gloo_shard_and_allreduce_equals_whole_batch():
     gxt = np.concatenate([r[4] for r in res], 0) / world
     assert np.allclose(gxs, whole["gxs"], rtol=1e-10, atol=1e-18)
     assert np.allclose(gxt, whole["gxt"], rtol=1e-10, atol=1e-18)
+
+
+@pytest.mark.reference
+def test_real_trainer_train_epoch_stock_vs_port_at_the_patch_seam():
+    """Whole-trainer integration: the UNMODIFIED ``Trainer_prototype_full.Trainer.train_epoch`` runs two
+    steps (MobileNetV2 DeepLab, 512x512, batch 2) stock and with ``gen_prototype`` / ``gen_prototype_retrify`` rebound on
+    the trainer module -- the seam ``patch_reference()`` uses -- to the eager port; every prototype either run's ops
+    returned must be identical.  ~100 s of CPU: opt-in with CLR_RUN_TRAINER_TEST=1 (result of the last run:
+    profiles/r02_trainer_harness_cpu.json).  The GPU form (patched = the CUDA ops) is tests/test_gpu_integration.py."""
+    if os.environ.get("CLR_RUN_TRAINER_TEST") != "1":
+        pytest.skip("opt-in (CLR_RUN_TRAINER_TEST=1): ~100 s")
+    from oracle import ref_import
+    if not ref_import.available():
+        pytest.skip("reference tree not present")
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools"))
+    import trainer_harness as TH
+    stock = TH.run_train_epoch(ref_import.REFERENCE_ROOT, False, steps=2, batch_size=2)
+    port = TH.run_train_epoch(ref_import.REFERENCE_ROOT, "port", steps=2, batch_size=2)
+    assert len(stock["calls"]) == len(port["calls"]) == 4
+    for a, b in zip(stock["calls"], port["calls"]):
+        assert a["name"] == b["name"]
+        for x, y in zip(a["protos"], b["protos"]):
+            assert np.array_equal(x, y)
+    assert stock["running_intra"] == port["running_intra"]

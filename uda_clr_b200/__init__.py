@@ -14,7 +14,8 @@ from .ops import (adaptation_factor, bmm_prototypes, dice_from_counts, distance_
                   get_prototype_weight, mc_statistics, pixel_acc_from_counts, retrify_weights, seg_loss,
                   uncertainty_map, validation_counts,
                   update_objective_single_vector, weighted_prototypes)
-from .step import CLRPlan, CLRStep, CLRStepOutput, consistency_threshold, sigmoid_rampup  # noqa: F401
+from .step import CLRPlan, CLRStep, CLRStepError, CLRStepOutput, consistency_threshold, sigmoid_rampup  # noqa: F401
+from .offline import OfflinePrototypes, offline_masks  # noqa: F401
 from . import dist, ops  # noqa: F401
 from .patch import patch_reference, patch_transnorm, unpatch_reference  # noqa: F401
 from .transnorm import TransNorm1d, TransNorm2d, trans_norm  # noqa: F401
