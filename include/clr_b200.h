@@ -208,6 +208,26 @@ int clr_mc_retrify(const float* preds, const float* oT_before, int T, int B, int
                    float pseudo_thr, float std_thr, float* std_map, float* pred_mean /*nullable*/,
                    float* weights /*[B,2K,H,W] out*/, float* masks /*[B,K,H,W] out*/, clr_stream_t stream);
 
+/* MC statistics without the staging buffer of the trainer's loop (Trainer_prototype_full.py:359-368):
+ * hand every MC forward's logits ([passes*B,K,Hi,Wi], pass-major like preds) to clr_mc_accumulate (first = 1 on the first
+ * call of a step), then clr_mc_finalize writes std_map / pred_mean for clr_retrify_weights (preds = NULL: the raw logits
+ * are gone, so the knife-edge guard of the mask is not available on this path).  state: clr_mc_state_floats() floats. */
+size_t clr_mc_state_floats(int B, int K, int Hi, int Wi);
+int clr_mc_accumulate(const float* logits, int passes, int B, int K, int Hi, int Wi, int first, float* state,
+                      clr_stream_t stream);
+int clr_mc_finalize(const float* state, int T, int B, int K, int Hi, int Wi, float* std_map, float* pred_mean,
+                    clr_stream_t stream);
+
+/* F.interpolate(target_map, size=(H, W), mode='nearest') of the hard labels (Trainer_prototype_full.py:329-330):
+ * src [planes,Hi,Wi] -> dst [planes,H,W], ATen's source index min(floor(dst * (float)in / out), in - 1). */
+int clr_label_downsample(const float* src, int planes, int Hi, int Wi, int H, int W, float* dst, clr_stream_t stream);
+
+/* Stored-prototype EMA of Trainer.update_objective_SingleVector (Trainer_prototype.py:117-123), R vectors per launch:
+ * out[r] = stored[r] * (1 - rate) + rate * v[r] unless sum_c v[r][c] == 0 (then out[r] = stored[r]); the zero test runs
+ * on the device (the reference pays one .item() sync per vector).  out may alias stored. */
+int clr_ema_rows(const float* v /*[R][C]*/, const float* stored /*[R][C]*/, int R, int C, float rate, float* out,
+                 clr_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Augmented-consistency masked BCE (Trainer_prototype_mt.cpython-38.pyc L502-561).
  * stats = { sum(m*l), sum(m), loss, 0 }.

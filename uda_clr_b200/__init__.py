@@ -13,7 +13,7 @@ from .ops import (adaptation_factor, bmm_prototypes, dice_from_counts, distance_
                   gen_prototype_retrify, gen_prototype_src_trg, gen_prototype_src_trg_retrify,
                   get_prototype_weight, mc_statistics, pixel_acc_from_counts, retrify_weights, seg_loss,
                   uncertainty_map, validation_counts,
-                  update_objective_single_vector, weighted_prototypes)
+                  update_objective_single_vector, weighted_prototypes, nearest_labels, MCAccumulator)
 from .step import CLRPlan, CLRStep, CLRStepError, CLRStepOutput, consistency_threshold, sigmoid_rampup  # noqa: F401
 from .offline import OfflinePrototypes, offline_masks  # noqa: F401
 from . import dist, ops  # noqa: F401

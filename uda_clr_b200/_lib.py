@@ -105,6 +105,11 @@ _SIGNATURES = {
     "clr_mc_stats": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P]),
     "clr_retrify_weights": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float,
                                     _P, _P, _P, _P, _P]),
+    "clr_mc_state_floats": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "clr_mc_accumulate": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P]),
+    "clr_mc_finalize": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P]),
+    "clr_label_downsample": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
+    "clr_ema_rows": (c_int, [_P, _P, c_int, c_int, c_float, _P, _P]),
     "clr_mc_retrify": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float, _P, _P, _P, _P, _P]),
     "clr_seg_loss_ws_bytes": (c_size_t, []),
     "clr_seg_loss_fwd": (c_int, [_P, _P, c_size_t, _P, _P, c_size_t, _P, c_size_t, _P, _P]),
@@ -148,6 +153,16 @@ def load() -> ctypes.CDLL:
     with _lock:
         if _lib is not None:
             return _lib
+        # a library older than its sources (edited tree, interrupted build) is rebuilt when nvcc is at hand; a missing
+        # library without a compiler is an error -- there is no CPU fallback for the CLR ops
+        try:
+            from . import build as _build
+            if not _build.is_fresh():
+                _build.build()
+        except Exception as e:
+            if not os.path.isfile(LIB_PATH):
+                raise ClrError("libclr_b200.so not built and could not be built (%s): run `python -m uda_clr_b200.build` "
+                               "(there is no CPU fallback for the CLR ops)" % str(e)[:200])
         if not os.path.isfile(LIB_PATH):
             raise ClrError("libclr_b200.so not built: run `python -m uda_clr_b200.build` "
                            "(there is no CPU fallback for the CLR ops)")

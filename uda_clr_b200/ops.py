@@ -403,10 +403,89 @@ def bmm_prototypes(masks: torch.Tensor, feat: torch.Tensor, n_add: float = 1.0) 
 
 
 def update_objective_single_vector(obj: torch.Tensor, vector: torch.Tensor, rate: float = 0.001) -> torch.Tensor:
-    """``Trainer.update_objective_SingleVector`` (Trainer_prototype.py:117-123): ``obj = (1-rate) obj + rate v``
-    unless ``v`` sums to zero -- decided on the device (``torch.where``), without the reference's host sync."""
-    v = vector.detach().reshape(obj.shape)
-    return torch.where(v.sum() == 0, obj, obj * (1.0 - rate) + rate * v)
+    """``Trainer.update_objective_SingleVector`` (Trainer_prototype.py:117-123): ``obj = obj * (1-rate) + rate * v``
+    unless ``v`` sums to zero -- decided on the device inside the kernel (``clr_ema_rows``), without the reference's
+    ``.item()`` host sync.  ``obj`` may be one vector ``[C]`` or a stack ``[R, C]`` (e.g. bu / cup / disc with equal C):
+    every row gets its own zero test.  Returns a new tensor, like the reference's dict assignment."""
+    lib = _lib.load()
+    o = obj.detach()
+    if not o.is_cuda or o.dtype != torch.float32:
+        raise RuntimeError("update_objective_single_vector needs CUDA float32 tensors (no CPU fallback)")
+    o = o.contiguous()
+    C = o.shape[-1]
+    R = o.numel() // C
+    v = vector.detach().to(torch.float32).reshape(R, C).contiguous()
+    out = torch.empty_like(o)
+    with torch.cuda.device(o.device):
+        check(lib.clr_ema_rows(ptr(v), ptr(o), R, C, float(rate), ptr(out), _stream()), "clr_ema_rows")
+    return out
+
+
+def nearest_labels(target_map: torch.Tensor, H: int, W: int) -> torch.Tensor:
+    """``F.interpolate(target_map, size=(H, W), mode='nearest')`` of the hard source labels
+    (Trainer_prototype_full.py:329-330) -> ``[B,K,H,W]``; ATen's nearest source index, bit for bit."""
+    lib = _lib.load()
+    t = _require_cuda_f32(target_map.detach(), "target_map")
+    B, K, Hi, Wi = t.shape
+    out = torch.empty(B, K, H, W, dtype=torch.float32, device=t.device)
+    with torch.cuda.device(t.device):
+        check(lib.clr_label_downsample(ptr(t), B * K, Hi, Wi, int(H), int(W), ptr(out), _stream()), "clr_label_downsample")
+    return out
+
+
+class MCAccumulator:
+    """MC-dropout statistics without the trainer's staging buffers (Trainer_prototype_full.py:359-368 fills a
+    ``[T*B,2,512,512]`` ``preds_trg`` and a dead 1.28 GB ``features_trg`` every step):
+
+        acc = MCAccumulator()
+        for i in range(T // 2):
+            with torch.no_grad():
+                logits = model(volume_batch_r)[0]            # [2*stride, K, Hi, Wi]: two MC passes per forward
+            acc.add(logits, passes=2)
+        std_map, pred_mean = acc.finalize()                  # what mc_statistics(preds_trg, T, stride) returns
+
+    Four running maps per position (pivot, shifted sum, shifted sum of squares, sum of sigmoid(p)); more bytes than one
+    read of staged logits, no staging memory.  The raw logits are gone afterwards, so ``retrify_weights`` runs without the
+    knife-edge guard of the uncertainty mask on this path (``preds=None``)."""
+
+    def __init__(self):
+        self.state: Optional[torch.Tensor] = None
+        self.shape = None
+        self.T = 0
+
+    def reset(self) -> None:
+        self.T = 0
+
+    def add(self, logits: torch.Tensor, passes: int = 1) -> None:
+        lib = _lib.load()
+        x = _require_cuda_f32(logits.detach(), "logits")
+        if x.shape[0] % passes:
+            raise ValueError("logits has %d maps, not a multiple of passes = %d" % (x.shape[0], passes))
+        B, K, Hi, Wi = x.shape[0] // passes, x.shape[1], x.shape[2], x.shape[3]
+        if self.T == 0:
+            n = lib.clr_mc_state_floats(B, K, Hi, Wi)
+            if self.state is None or self.state.numel() != n or self.state.device != x.device:
+                self.state = torch.empty(n, dtype=torch.float32, device=x.device)
+            self.shape = (B, K, Hi, Wi)
+        elif self.shape != (B, K, Hi, Wi):
+            raise ValueError("MC passes of one step must agree in shape: %s vs %s" % (self.shape, (B, K, Hi, Wi)))
+        with torch.cuda.device(x.device):
+            check(lib.clr_mc_accumulate(ptr(x), int(passes), B, K, Hi, Wi, int(self.T == 0), ptr(self.state), _stream()),
+                  "clr_mc_accumulate")
+        self.T += passes
+
+    def finalize(self):
+        if self.T == 0:
+            raise RuntimeError("MCAccumulator.finalize() before any add()")
+        lib = _lib.load()
+        B, K, Hi, Wi = self.shape
+        std_map = torch.empty(B, K, Hi, Wi, dtype=torch.float32, device=self.state.device)
+        pred_mean = torch.empty_like(std_map)
+        with torch.cuda.device(self.state.device):
+            check(lib.clr_mc_finalize(ptr(self.state), self.T, B, K, Hi, Wi, ptr(std_map), ptr(pred_mean), _stream()),
+                  "clr_mc_finalize")
+        self.T = 0
+        return std_map, pred_mean
 
 
 # ----------------------------------------------------------------------------------------------- A8

@@ -80,6 +80,14 @@ class _Buffers:
             off += (n + 63) // 64 * 64
 
 
+def _downsample_labels(lib, holder, st) -> None:
+    full = holder["ys_full"]
+    if full is not None:
+        ys = holder["ys"]
+        check(lib.clr_label_downsample(ptr(full), full.shape[0] * full.shape[1], full.shape[2], full.shape[3],
+                                       ys.shape[2], ys.shape[3], ptr(ys), st), "clr_label_downsample")
+
+
 class _ClrStepFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, step, args_holder, xs, xt, oT_aug, wt_soft=None):
@@ -87,6 +95,7 @@ class _ClrStepFn(torch.autograd.Function):
         a: StepArgs = args_holder["args"]
         with torch.cuda.device(xs.device):
             st = _stream()              # the current stream of the tensors' device, not of whatever device is current
+            _downsample_labels(lib, args_holder, st)
             if args_holder["peer"] is not None:
                 a.seq = _dist.next_seq(args_holder["peer"])
                 check(lib.clr_step_fwd(ctypes.byref(a), st), "clr_step_fwd (in-kernel exchange)")
@@ -187,6 +196,13 @@ class CLRStep:
         xt = _require_cuda_f32(xt_feature, "xt_feature")
         dev = xs.device
         B_s, C, H, W = xs.shape
+        # the hard source labels may come at IMAGE resolution (the trainer's target_map): the step then does the
+        # trainer's F.interpolate(target_map, size=..., mode='nearest') (Trainer_prototype_full.py:329-330) itself, as one
+        # small launch in front of every run (clr_label_downsample)
+        ys_full = None
+        if ys.shape[:2] == (B_s, self.K) and tuple(ys.shape[2:]) != (H, W):
+            ys_full = ys
+            ys = torch.empty(B_s, self.K, H, W, dtype=torch.float32, device=dev)
         B_t = xt.shape[0]
         K = self.K
         if ys.shape != (B_s, K, H, W) or xt.shape[1:] != (C, H, W):
@@ -272,6 +288,7 @@ class CLRStep:
 
         wt_soft = wt if (not self.retrify and isinstance(wt, torch.Tensor) and wt.requires_grad) else None
         holder = dict(args=a, buf=buf, xs=xs, xt=xt, oT_aug=oTa, dims=(B_s, B_t, C, H, W, K, Hi, Wi), peer=peer, wt_soft=wt_soft,
+                      ys=ys, ys_full=ys_full,
                       keep=(xs, ys, xt, wt_t, oTb, pr, oT_d, oTa, self.stored_s, self.stored_t, ws,
                             masks_t if (use_cons and not self.retrify) else None))
         return holder
@@ -369,6 +386,7 @@ class CLRPlan:
         a: StepArgs = self.holder["args"]
         st = _stream()
         a.first_s, a.first_t = int(self.step.first_s), int(self.step.first_t)
+        _downsample_labels(self._lib, self.holder, st)
         if self.holder["peer"] is not None:
             a.seq = _dist.next_seq(self.holder["peer"])
             check(self._lib.clr_step_run(self._ref, st), "clr_step_run (in-kernel exchange)")
