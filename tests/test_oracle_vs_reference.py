@@ -343,9 +343,11 @@ def test_distance_weight_and_single_vector_ema_vs_trainer_prototype_methods():
     v = torch.randn(1, C, generator=g)
     TPR.Trainer.update_objective_SingleVector(me, "cup", v)
     assert relerr(O.ema_single_vector(proto.numpy(), v.numpy().reshape(-1)), me.objective_vectors["cup"].numpy()) < 1e-7
-    from uda_clr_b200 import ops
-    assert torch.allclose(ops.update_objective_single_vector(proto, v), me.objective_vectors["cup"], rtol=0, atol=1e-7)
     before = me.objective_vectors["cup"].clone()
     TPR.Trainer.update_objective_SingleVector(me, "cup", torch.zeros(1, C))
     assert torch.equal(me.objective_vectors["cup"], before)
-    assert torch.equal(ops.update_objective_single_vector(before, torch.zeros(1, C)), before)
+    # the product op (clr_ema_rows) is CUDA-only -- it is compared with this same ATen expression bit for bit on the GPU
+    # (tests/test_gpu_widen.py) and refuses CPU tensors here
+    from uda_clr_b200 import ops
+    with pytest.raises(RuntimeError):
+        ops.update_objective_single_vector(proto, v)
