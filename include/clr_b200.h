@@ -89,6 +89,11 @@ int clr_event_elapsed_us(void* begin, void* end, float* us /*valid once both eve
 size_t clr_pool_ws_bytes(int B, int C, int HW, int K);
 int clr_pool_fwd(const float* feat /*[B,C,HW]*/, const float* w, int fmt, int B, int C, int HW, int K,
                  void* ws, size_t ws_bytes, float* sums /*[2K][C+1] out*/, clr_stream_t stream);
+/* clr_pool_fwd + clr_proto_finalize in the same two launches (the reduce launch also writes mu [2K][C] = S_r / N_r): the
+ * single-process form of gen_prototype's forward (utils/Utils.py:114-130).  Sharded callers all-reduce sums and call
+ * clr_proto_finalize instead. */
+int clr_pool_fwd_mu(const float* feat, const float* w, int fmt, int B, int C, int HW, int K,
+                    void* ws, size_t ws_bytes, float* sums /*[2K][C+1] out*/, float* mu /*[2K][C] out*/, clr_stream_t stream);
 /* Same kernel for R arbitrary explicit weight rows [B,R,HW] (1 <= R <= 16): sums is [R][C+1].
  * Used for the discriminative term's active-set sums and the per-sample (bmm-style) pooling. */
 size_t clr_pool_rows_ws_bytes(int B, int C, int HW, int R);

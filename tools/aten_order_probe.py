@@ -5,8 +5,9 @@ The uncertainty masks of ``gen_prototype_retrify`` (utils/Utils.py:166, 171, 197
 ``torch.std(dim=0)`` + bilinear down-sampling; the library re-evaluates pixels near the threshold in ATen's order
 (csrc/mc_stats.cu).  This tool checks that order against eager torch ON THE SAME GPU:
 
-  1. ``mc_precise=1`` maps vs ``torch.std`` / ``torch.mean`` bit for bit, for every candidate ``aten_variant``
-     (fma / no fma in WelfordOps, number of interleaved accumulators) and several T -> which variant IS ATen;
+  1. ``mc_precise=1`` maps vs ``torch.std`` / ``torch.mean`` bit for bit for several T (round 2's first run also tried
+     the candidate orders -- no fma in WelfordOps::reduce / ::combine, 1 or 4 interleaved accumulators -- through a knob
+     that has since been removed: only the pinned form matched, profiles/r02_aten_order_probe.json);
   2. the down-sampled std (``small_out``) vs ``F.interpolate(bilinear, align_corners=True)`` bit for bit;
   3. mask flips against eager torch at BASELINE config-1 shape over N seeds, without and with the guard band
      (``preds=None`` vs ``preds=...``), on the bench's synthetic data and on a stress set whose std distribution is
@@ -41,7 +42,6 @@ def torch_maps(preds, T, B):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seeds", type=int, default=50)
-    ap.add_argument("--variants", default="0,1,2,3,4,5,8")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     lib = _lib.load()
@@ -54,17 +54,12 @@ def main():
                         (8, 1, 1, 8)]:
         preds = 3.0 * torch.randn(T * B, K, Hi, Hi, generator=g, device=dev)
         ref_std, ref_mean = torch_maps(preds, T, B)
-        row = {}
-        for v in [int(x) for x in a.variants.split(",")]:
-            set_tunable(lib, "mc_precise", 1)
-            set_tunable(lib, "aten_variant", v)
-            try:
-                s, m = clr.mc_statistics(preds, T, B)
-            finally:
-                set_tunable(lib, "mc_precise", 0)
-                set_tunable(lib, "aten_variant", 0)
-            row["variant_%d" % v] = {"std_mismatch": int((s != ref_std).sum()), "mean_mismatch": int((m != ref_mean).sum()),
-                                     "n": int(s.numel())}
+        set_tunable(lib, "mc_precise", 1)
+        try:
+            s, m = clr.mc_statistics(preds, T, B)
+        finally:
+            set_tunable(lib, "mc_precise", 0)
+        row = {"std_mismatch": int((s != ref_std).sum()), "mean_mismatch": int((m != ref_mean).sum()), "n": int(s.numel())}
         probe["T%d_B%d_K%d_%d" % (T, B, K, Hi)] = row
     out["order_probe"] = probe
 

@@ -87,6 +87,7 @@ _SIGNATURES = {
     "clr_bmm_finalize": (c_int, [_P, c_int, c_int, c_int, c_float, _P, _P]),
     "clr_pool_bwd_ps": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, c_float, c_float, _P, _P]),
     "clr_pool_fwd": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P, _P]),
+    "clr_pool_fwd_mu": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P, _P, _P]),
     "clr_pool_fwd2": (c_int, [_P, _P, c_int, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P, _P, _P]),
     "clr_proto_finalize": (c_int, [_P, c_int, c_int, _P, _P]),
     "clr_pool_bwd": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_float, _P, _P, c_int, _P, _P]),

@@ -42,7 +42,6 @@ int clr_set_tunable(const char* name, int value) {
     else if (!strcmp(name, "pool_stages")) t.pool_stages = value;
     else if (!strcmp(name, "pool_threads")) t.pool_threads = value;
     else if (!strcmp(name, "mc_precise")) t.mc_precise = value;
-    else if (!strcmp(name, "aten_variant")) t.aten_variant = value;
     else if (!strcmp(name, "disc_impl")) t.disc_impl = value;
     else if (!strcmp(name, "disc_tile")) t.disc_tile = value;
     else if (!strcmp(name, "disc_threads")) t.disc_threads = value;
@@ -57,8 +56,7 @@ int clr_set_tunable(const char* name, int value) {
     else if (!strcmp(name, "fin_early_off")) t.fin_early_off = value;
     else if (!strcmp(name, "mc_split")) t.mc_split = value;
     else if (!strcmp(name, "disc_reverse")) t.disc_reverse = value;
-    else if (!strcmp(name, "pool_order")) t.pool_order = value;
-    else if (!strcmp(name, "cons_ef")) t.cons_ef = value;
+
     else return CLR_ERR_BAD_ARG;
     return CLR_OK;
 }

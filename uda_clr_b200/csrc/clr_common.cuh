@@ -37,7 +37,6 @@ struct Tunables {
     int disc_tile;     // 0 = auto, 64 = force 64-pixel tiles in the fused discriminative kernel
     int pdl_off;       // 1 = do not use programmatic dependent launch
     int mc_precise;    // 1 = clr_mc_stats / clr_mc_retrify evaluate std / mean exactly like ATen's CUDA reductions (slow; tests), 0 = streaming
-    int aten_variant;  // A/B of the ATen-order emulation against torch (mc_stats.cu); 0 = the pinned form
     int finish_off;    // 1 = single-GPU step uses the separate reduce / finalize kernels instead of the merged finish kernels
     int hfuse_off;     // 1 = finish bodies get launches of their own instead of riding with cons / the target-gradient write
     int fin_early_off; // 1 = the pooling finish releases the discriminative kernel only at its very end (after the last-CTA combine)
@@ -47,9 +46,8 @@ struct Tunables {
     int mc_split;      // 1 = one-pass mc_retrify kernel splits image rows into column blocks (more, smaller CTAs)
     int flag_dep_off;  // 1 = the discriminative kernel waits for the whole [finish | consistency] grid (griddepcontrol.wait)
                        //     instead of the finish CTAs' completion counter
-    int disc_reverse;  // 1 = the one-read discriminative kernel walks its tiles in descending address order
-    int pool_order;    // 1 = two-domain pooling: every CTA reads its share of domain 0 (target) first, then domain 1 (source)
-    int cons_ef;       // 1 = the consistency pass loads its logits with an L2 evict-first policy
+    int disc_reverse;  // 1 = the one-read discriminative kernel walks its tiles in descending address order (round 2: the re-read of
+                       //     xs then misses DRAM for 102 instead of 110 of 135 MB, the kernel is not faster -- it is not DRAM-bound)
     int xchg_pull;     // in-kernel exchange: 1 = readers poll the peers' buffers (no remote stores), 0 = senders push
     void* trace_buf;   // device TraceRec[kTraceSlots] or NULL (clr_trace_set): device-side timeline of the kernels
 };
@@ -314,6 +312,26 @@ static inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_
     }
     count_launch();
     cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
+}
+
+// cudaFuncSetAttribute(max dynamic smem) + cudaOccupancyMaxActiveBlocksPerMultiprocessor are constants of (kernel, device,
+// block size, dynamic smem): asked once per thread and cached, instead of two driver round trips in front of every launch
+// (the drop-in ops and the fused step are enqueued from the host every training step).
+static inline int kernel_occupancy(const void* kern, int threads, size_t smem, int* occ) {
+    struct Entry { const void* kern; int dev, threads; size_t smem; int occ; };
+    constexpr int kCap = 32;
+    static thread_local Entry cache[kCap];
+    static thread_local int used = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    for (int i = 0; i < used; ++i)
+        if (cache[i].kern == kern && cache[i].dev == dev && cache[i].threads == threads && cache[i].smem == smem) { *occ = cache[i].occ; return CLR_OK; }
+    if (smem > 48 * 1024) CLR_RETURN_IF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int o = 0;
+    CLR_RETURN_IF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, threads, smem));
+    if (used < kCap) cache[used++] = Entry{kern, dev, threads, smem, o};
+    *occ = o;
+    return CLR_OK;
 }
 
 // Static contiguous partition of `total` items over `parts` workers.

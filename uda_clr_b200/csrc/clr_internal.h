@@ -10,7 +10,7 @@ struct PoolLayout;
 int pool_fwd_impl(const float* feat0, const float* w0, int fmt0, int B0, float* sums0,
                   const float* feat1, const float* w1, int fmt1, int B1, float* sums1,
                   int C, int HW, int R, void* ws, size_t ws_bytes, cudaStream_t st, int keep0 = 0, int keep1 = 0,
-                  struct PoolLayout* skip_reduce_layout = nullptr, unsigned int* counter_reset = nullptr);
+                  struct PoolLayout* skip_reduce_layout = nullptr, unsigned int* counter_reset = nullptr, float* mu0 = nullptr);
 size_t pool_partial_bytes(int B, int C, int HW, int R);
 // sums[r][c] = sum_slot partial[slot][r][c] (fp64, fixed order) for a [slots][R][C+1] partial buffer
 void launch_partial_reduce(const float* partial, int slots, int R, int C, float* sums, cudaStream_t st);

@@ -97,7 +97,6 @@ struct ConsArgs {
     ConsGeom g; LabelRule thr;
     double* partial;                                   // forward: [ctas][2] per-CTA { sum m*l, sum m }
     const float* stats; const float* gscale_dev; float gscale; float* grad;    // backward
-    int evict_first;                                   // 1: the logits are streamed with an L2 evict-first policy ("cons_ef")
 };
 
 // `cta` of `ncta` CTAs (the body may share a launch with other work, see pool_finish_cons_kernel)
@@ -111,7 +110,6 @@ __device__ __forceinline__ void cons_body(const ConsArgs& a, const unsigned cta,
     float coef = 0.f;
     if (BWD) coef = (gscale_dev ? gscale * __ldg(gscale_dev) : gscale) / __ldg(stats + 1);
     float num = 0.f, den = 0.f;
-    const uint64_t pol_ef = a.evict_first ? policy_evict_first() : 0ull;
     constexpr int U = 4;
     const unsigned nthreads = ncta * kConsThreads;
     for (unsigned v0 = cta * kConsThreads + threadIdx.x; v0 < g.total_vec; v0 += U * nthreads) {
@@ -123,13 +121,8 @@ __device__ __forceinline__ void cons_body(const ConsArgs& a, const unsigned cta,
         for (int u = 0; u < U; ++u) {
             const unsigned v = v0 + u * nthreads;
             if (v < g.total_vec) {
-                if (a.evict_first) {
-                    zt[u] = ld_stream_hint<VEC>(oT + (size_t)v * VEC, pol_ef);
-                    za[u] = ld_stream_hint<VEC>(oT_aug + (size_t)v * VEC, pol_ef);
-                } else {
-                    zt[u] = ld_stream<VEC>(oT + (size_t)v * VEC);
-                    za[u] = ld_stream<VEC>(oT_aug + (size_t)v * VEC);
-                }
+                zt[u] = ld_stream<VEC>(oT + (size_t)v * VEC);
+                za[u] = ld_stream<VEC>(oT_aug + (size_t)v * VEC);
                 const unsigned row = g.wv_shift >= 0 ? (v >> g.wv_shift) : (v / g.wv);
                 xv[u] = v - row * g.wv;
                 const unsigned plane = g.hi_shift >= 0 ? (row >> g.hi_shift) : (row / (unsigned)g.Hi);
@@ -253,7 +246,7 @@ static int make_geom(int B, int K, int Hi, int Wi, int H, int W, int vec, ConsGe
 template <int VEC, bool BWD>
 static int cons_grid(const ConsGeom& g, int& grid) {
     int occ = 0;
-    CLR_RETURN_IF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cons_kernel<VEC, BWD>, kConsThreads, 0));
+    { const int rc = kernel_occupancy(reinterpret_cast<const void*>(cons_kernel<VEC, BWD>), kConsThreads, 0, &occ); if (rc != CLR_OK) return rc; }
     if (occ < 1) occ = 1;
     long long want = (long long)device_facts().sms * occ;
     const long long need = ((long long)g.total_vec + kConsThreads - 1) / kConsThreads;
@@ -274,7 +267,6 @@ int cons_fwd_partials(const float* oT, const float* oT_aug, const float* masks, 
     rc = vec4 ? cons_grid<4, false>(a.g, grid) : cons_grid<1, false>(a.g, grid);
     if (rc != CLR_OK) return rc;
     a.oT = oT; a.oT_aug = oT_aug; a.masks = masks; a.thr = make_rule(threshold); a.partial = partial;
-    a.evict_first = tunables().cons_ef;
     if (fused_finish) {
         const int n_fin = pool_finish_ctas(fused_finish->C);
         if (grid > n_fin + 1) grid -= n_fin;          // keep the launch at one resident wave
@@ -319,7 +311,7 @@ int clr_cons_bwd(const float* oT, const float* oT_aug, const float* masks, int B
     int grid = 1;
     rc = vec4 ? clr::cons_grid<4, true>(g, grid) : clr::cons_grid<1, true>(g, grid);
     if (rc != CLR_OK) return rc;
-    clr::ConsArgs a{oT, oT_aug, masks, g, clr::make_rule(threshold), nullptr, stats, gscale_dev, gscale * aug_weight, grad_oT_aug, 0};
+    clr::ConsArgs a{oT, oT_aug, masks, g, clr::make_rule(threshold), nullptr, stats, gscale_dev, gscale * aug_weight, grad_oT_aug};
     if (vec4) clr::launch_k(clr::cons_kernel<4, true>, grid, clr::kConsThreads, 0, st, a);
     else clr::launch_k(clr::cons_kernel<1, true>, grid, clr::kConsThreads, 0, st, a);
     return clr::launch_status();

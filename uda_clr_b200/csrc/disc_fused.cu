@@ -429,9 +429,8 @@ template <int K, int TP, int STAGES, int NT, int CPT>
 static int launch_disc_c(DiscParams& p, int* nparts, cudaStream_t st) {
     const size_t smem = disc_smem<K, TP, NT>(p.C, STAGES);
     auto kern = disc_fused_kernel<K, TP, STAGES, NT, false, CPT>;
-    CLR_RETURN_IF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    CLR_RETURN_IF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem));
+    { const int rc = kernel_occupancy(reinterpret_cast<const void*>(kern), NT, smem, &occ); if (rc != CLR_OK) return rc; }
     if (occ < 1) return CLR_ERR_UNSUPPORTED;
     const int grid = finish_launch_geometry(p, TP, occ, nparts);
     if (grid < 1) return CLR_ERR_UNSUPPORTED;
@@ -477,9 +476,8 @@ template <int K, int STAGES, int NT, int CPT>
 static int launch_disc_tma_c(DiscParams& p, const CUtensorMap& tmap, int* nparts, cudaStream_t st) {
     const size_t smem = disc_smem_tma<K, NT>(p.C, p.rows_box * p.nbox, STAGES);
     auto kern = disc_fused_kernel<K, 32, STAGES, NT, true, CPT>;
-    CLR_RETURN_IF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    CLR_RETURN_IF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem));
+    { const int rc = kernel_occupancy(reinterpret_cast<const void*>(kern), NT, smem, &occ); if (rc != CLR_OK) return rc; }
     if (occ < 1) return CLR_ERR_UNSUPPORTED;
     const int grid = finish_launch_geometry(p, 32, occ, nparts);
     if (grid < 1) return CLR_ERR_UNSUPPORTED;

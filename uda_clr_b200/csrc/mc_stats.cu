@@ -26,64 +26,59 @@ __device__ __forceinline__ float sigmoid_aten(float x) { return 1.0f / (1.0f + e
 // (guard band, retrify epilogues below); `mc_precise` = 1 computes the whole maps this way (slow, tests).
 // Roundings are pinned with intrinsics to the contraction nvcc applies to ATen's expressions (WelfordOps::reduce:
 // `m2 + delta * (x - new_mean)` -> fma; ::combine: `a.mean + delta * nb_over_n` -> fma, `a.m2 + b.m2 + delta * delta *
-// a.nf * nb_over_n` -> fma of the last product into the sum).  `variant` exists for A/B runs against torch on the GPU
-// (tools/aten_order_probe.py): bit 0 = no fma in reduce, bit 1 = no fma in combine, bits 2-3: vt0 = 2 / 4 / 1.
+// a.nf * nb_over_n` -> fma of the last product into the sum).  Verified bit for bit against torch 2.11 on the B200 for
+// T = 2..20 (tools/aten_order_probe.py, profiles/r02_aten_order_probe.json: the no-fma forms and vt0 = 1 / 4 all
+// mismatch, this form has 0 mismatches in 4.7 M values) and by tests/test_gpu_step.py on every GPU test run.
 struct WelfordAcc { float mean, m2, nf; };
-__device__ __forceinline__ void welford_push(WelfordAcc& a, float x, int variant) {
+__device__ __forceinline__ void welford_push(WelfordAcc& a, float x) {
     a.nf += 1.0f;
     const float delta = __fsub_rn(x, a.mean);
     a.mean = __fadd_rn(a.mean, __fdiv_rn(delta, a.nf));
-    const float nd = __fsub_rn(x, a.mean);
-    a.m2 = (variant & 1) ? __fadd_rn(a.m2, __fmul_rn(delta, nd)) : __fmaf_rn(delta, nd, a.m2);
+    a.m2 = __fmaf_rn(delta, __fsub_rn(x, a.mean), a.m2);
 }
-__device__ __forceinline__ WelfordAcc welford_merge(const WelfordAcc& a, const WelfordAcc& b, int variant) {
+__device__ __forceinline__ WelfordAcc welford_merge(const WelfordAcc& a, const WelfordAcc& b) {
     if (a.nf == 0.f) return b;
     if (b.nf == 0.f) return a;
     const float delta = __fsub_rn(b.mean, a.mean);
     const float n = __fadd_rn(a.nf, b.nf);
     const float nb_over_n = __fdiv_rn(b.nf, n);
-    const float dd = __fmul_rn(__fmul_rn(delta, delta), a.nf);
     WelfordAcc r;
-    if (variant & 2) {
-        r.mean = __fadd_rn(a.mean, __fmul_rn(delta, nb_over_n));
-        r.m2 = __fadd_rn(__fadd_rn(a.m2, b.m2), __fmul_rn(dd, nb_over_n));
-    } else {
-        r.mean = __fmaf_rn(delta, nb_over_n, a.mean);
-        r.m2 = __fmaf_rn(dd, nb_over_n, __fadd_rn(a.m2, b.m2));
-    }
+    r.mean = __fmaf_rn(delta, nb_over_n, a.mean);
+    r.m2 = __fmaf_rn(__fmul_rn(__fmul_rn(delta, delta), a.nf), nb_over_n, __fadd_rn(a.m2, b.m2));
     r.nf = n;
     return r;
 }
 __device__ __forceinline__ float sigmoid_half_aten(float p) { return sigmoid_aten(__fmul_rn(p, 0.5f)); }   // preds / 2.0 (:165)
-// std_T(sigmoid(p/2)) (unbiased) at position i of preds [T][n]
-__device__ __noinline__ float std_aten_at(const float* __restrict__ preds, int T, size_t n, size_t i, int variant) {
-    const int vt0 = ((variant >> 2) & 3) == 1 ? 4 : (((variant >> 2) & 3) == 2 ? 1 : 2);
-    WelfordAcc acc[4];
+// std_T(sigmoid(p/2)) (unbiased) at position i of preds [T][n].  Eight loads in flight per round (a guard-band pixel sits
+// on the kernel's critical path: its T logits must not be T dependent DRAM round trips).
+__device__ __noinline__ float std_aten_at(const float* __restrict__ preds, int T, size_t n, size_t i) {
+    WelfordAcc a0{0.f, 0.f, 0.f}, a1{0.f, 0.f, 0.f};      // even / odd passes
+    for (int t0 = 0; t0 < T; t0 += 8) {
+        float x[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[j] = WelfordAcc{0.f, 0.f, 0.f};
-    for (int t = 0; t < T; ++t) {
-        const float x = sigmoid_half_aten(__ldg(preds + (size_t)t * n + i));
-        const int j = t % vt0;
-        if (j == 0) welford_push(acc[0], x, variant);
-        else if (j == 1) welford_push(acc[1], x, variant);
-        else if (j == 2) welford_push(acc[2], x, variant);
-        else welford_push(acc[3], x, variant);
+        for (int u = 0; u < 8; ++u) x[u] = (t0 + u < T) ? __ldg(preds + (size_t)(t0 + u) * n + i) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (t0 + u < T) {
+                const float sgm = sigmoid_half_aten(x[u]);
+                if (u & 1) welford_push(a1, sgm); else welford_push(a0, sgm);
+            }
+        }
     }
-    WelfordAcc r = acc[0];
-    for (int j = 1; j < vt0; ++j) r = welford_merge(r, acc[j], variant);
+    const WelfordAcc r = welford_merge(a0, a1);
     const float divisor = r.nf > 1.0f ? __fsub_rn(r.nf, 1.0f) : 0.0f;      // correction = 1; T = 1 -> 0/0 = NaN like torch
     return __fsqrt_rn(__fdiv_rn(r.m2, divisor));
 }
 // mean_T(sigmoid(p)) at position i: 4 interleaved partial sums, ((s0 + s1) + s2) + s3, times factor = n_out / numel
 __device__ __noinline__ float mean_aten_at(const float* __restrict__ preds, int T, size_t n, size_t i, float factor) {
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int t = 0; t < T; ++t) {
-        const float x = sigmoid_aten(__ldg(preds + (size_t)t * n + i));
-        const int j = t & 3;
-        if (j == 0) acc[0] = __fadd_rn(acc[0], x);
-        else if (j == 1) acc[1] = __fadd_rn(acc[1], x);
-        else if (j == 2) acc[2] = __fadd_rn(acc[2], x);
-        else acc[3] = __fadd_rn(acc[3], x);
+    for (int t0 = 0; t0 < T; t0 += 8) {
+        float x[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) x[u] = (t0 + u < T) ? __ldg(preds + (size_t)(t0 + u) * n + i) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (t0 + u < T) acc[u & 3] = __fadd_rn(acc[u & 3], sigmoid_aten(x[u]));
     }
     return __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc[0], acc[1]), acc[2]), acc[3]), factor);
 }
@@ -116,16 +111,16 @@ __device__ __forceinline__ void mc_sigmoids(float p, float& s_half, float& s_ful
 // preds is [T][n].  TT > 0: T <= TT, values kept in registers (two-pass variance); TT == 0: any T, Welford.
 // EXACT: T == TT is known at compile time (the reference's T = 8): no per-pass predicates -- they were ~10 % of the
 // kernel's instructions (32 BRA + 26 ISETP per thread in the ncu source page) in a pass that is issue / MUFU co-limited.
-struct McAten { int variant; float factor; };     // PRECISE instantiations only: A/B variant, ATen's mean factor
+struct McAten { float factor; };     // PRECISE instantiations only: ATen's mean factor (n_out / numel as float)
 
 template <int VEC, int TT, bool PRECISE, bool EXACT = false>
 __device__ __forceinline__ void mc_vec_stats(const float* __restrict__ preds, int T_rt, size_t n, size_t i, Pack<VEC>& s, Pack<VEC>& m,
-                                             const McAten aten = McAten{0, 0.f}) {
+                                             const McAten aten = McAten{0.f}) {
     const int T = EXACT ? TT : T_rt;
     if constexpr (PRECISE) {
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
-            s.v[v] = std_aten_at(preds, T, n, i + v, aten.variant);
+            s.v[v] = std_aten_at(preds, T, n, i + v);
             m.v[v] = mean_aten_at(preds, T, n, i + v, aten.factor);
         }
         return;
@@ -202,7 +197,7 @@ template <int VEC, bool PRECISE>
 static void launch_mc(const float* preds, int T, size_t n, float* std_map, float* pred_mean, cudaStream_t st) {
     const size_t threads = (n + VEC - 1) / VEC;
     const unsigned blocks = (unsigned)((threads + 255) / 256);
-    const McAten aten{tunables().aten_variant, mean_factor_aten(n, T)};
+    const McAten aten{mean_factor_aten(n, T)};
     if (PRECISE) launch_k(mc_stats_kernel<VEC, 0, PRECISE>, blocks, 256, 0, st, preds, T, n, std_map, pred_mean, aten);
     else if (T == 8 && !tunables().mc_generic) launch_k(mc_stats_kernel<VEC, 8, PRECISE, true>, blocks, 256, 0, st, preds, T, n, std_map, pred_mean, aten);
     else if (T <= 8) launch_k(mc_stats_kernel<VEC, 8, PRECISE>, blocks, 256, 0, st, preds, T, n, std_map, pred_mean, aten);
@@ -235,49 +230,72 @@ __device__ __forceinline__ float bilinear_at(const float* __restrict__ plane, in
 }
 
 // Guard band of the uncertainty mask: the streaming statistics use approximate sigmoids and a two-pass variance (error
-// of std_small <= ~3e-7); a pixel whose value lies within kMaskBand of the threshold is decided by this
+// of std_small <= ~3e-7); a pixel whose value lies within kMaskBand of the threshold is decided by an
 // exact re-evaluation instead -- its 4 bilinear taps recomputed from the MC logits in ATen's order -- so that mask_k is
 // bit-identical to eager torch on the same device (utils/Utils.py:166, 171, 197-200) at streaming speed.
+// About one pixel in 2000 is in the band, and it sits on the kernel's critical path, so the WARP re-evaluates it: up to 8
+// flagged pixels per round, 4 lanes per pixel (one bilinear tap each, all T logits of a tap in flight), the owner lane
+// gathers its 4 taps by shuffle.  Must be called by all 32 lanes (converged); `need` / geometry are per lane.
 constexpr float kMaskBand = 1e-5f;
-__device__ __noinline__ float std_small_aten(const float* __restrict__ preds, int T, size_t n, size_t plane, int Wi,
-                                             const Tap& h, const Tap& w, int variant) {
-    const size_t r0 = plane + (size_t)h.i0 * Wi, r1 = plane + (size_t)h.i1 * Wi;
-    const float a = std_aten_at(preds, T, n, r0 + w.i0, variant), b = std_aten_at(preds, T, n, r0 + w.i1, variant);
-    const float c = std_aten_at(preds, T, n, r1 + w.i0, variant), d = std_aten_at(preds, T, n, r1 + w.i1, variant);
-    return bilinear_mix(a, b, c, d, h, w);
+__device__ __forceinline__ float std_small_exact_warp(bool need, float ss, const float* __restrict__ preds, int T, size_t n,
+                                                      size_t plane, int Wi, const Tap& h, const Tap& w) {
+    const unsigned lane = threadIdx.x & 31u;
+    unsigned pending = __ballot_sync(0xffffffffu, need);
+    while (pending) {                                   // warp-uniform
+        const unsigned slot = lane >> 2, tap = lane & 3u;
+        const unsigned src = __fns(pending, 0, (int)slot + 1);             // lane of the slot-th flagged pixel, or ~0u
+        const unsigned sl = src < 32u ? src : 0u;
+        const unsigned long long pl = __shfl_sync(0xffffffffu, (unsigned long long)plane, sl);
+        const int hi0 = __shfl_sync(0xffffffffu, h.i0, sl), hi1 = __shfl_sync(0xffffffffu, h.i1, sl);
+        const int wi0 = __shfl_sync(0xffffffffu, w.i0, sl), wi1 = __shfl_sync(0xffffffffu, w.i1, sl);
+        float val = 0.f;
+        if (src < 32u) val = std_aten_at(preds, T, n, (size_t)pl + (size_t)((tap & 2u) ? hi1 : hi0) * Wi + ((tap & 1u) ? wi1 : wi0));
+        const unsigned rank = __popc(pending & ((1u << lane) - 1u));       // this lane's position among the flagged ones
+        const unsigned base = (rank & 7u) * 4u;
+        const float a = __shfl_sync(0xffffffffu, val, base), b = __shfl_sync(0xffffffffu, val, base + 1);
+        const float c = __shfl_sync(0xffffffffu, val, base + 2), d = __shfl_sync(0xffffffffu, val, base + 3);
+        if (((pending >> lane) & 1u) && rank < 8u) ss = bilinear_mix(a, b, c, d, h, w);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pending &= pending - 1u;               // the 8 lowest flagged lanes are done
+    }
+    return ss;
 }
 
 __global__ void __launch_bounds__(256) retrify_weights_kernel(
     const float* __restrict__ oT_before, const float* __restrict__ pred_mean, const float* __restrict__ std_map,
-    const float* __restrict__ preds /*[T][B,K,Hi,Wi] or null: no guard band*/, int T, int variant,
+    const float* __restrict__ preds /*[T][B,K,Hi,Wi] or null: no guard band*/, int T,
     int B, int K, int H, int W, int Hi, int Wi, float pseudo_thr, float std_thr,
     float* __restrict__ weights /*[B,2K,H,W]*/, float* __restrict__ masks /*[B,K,H,W]*/,
     float* __restrict__ pseudo_out /*[B,K,H,W] or null*/, float* __restrict__ small_out /*[2][B,K,H,W] or null*/) {
     kernel_begin(TR_RETRIFY);
-    // grid.y = b*K + k (one plane), grid.x covers the plane: no 64-bit divisions
+    // grid.y = b*K + k (one plane), grid.x covers the plane: no 64-bit divisions.  No early return: the guard band below
+    // is evaluated by whole warps.
     const size_t n = (size_t)B * K * H * W;
     const int pixi = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pixi >= H * W) { trace_exit(TR_RETRIFY); return; }
+    const bool valid = pixi < H * W;
+    const int pc = valid ? pixi : 0;
     const int bk = blockIdx.y;
     const int b = bk / K, k = bk - b * K;
-    const int y = pixi / W, x = pixi - y * W;
-    const size_t i = (size_t)bk * H * W + pixi;
+    const int y = pc / W, x = pc - y * W;
+    const size_t i = (size_t)bk * H * W + pc;
     const float sh = H > 1 ? (float)(Hi - 1) / (float)(H - 1) : 0.f;
     const float sw = W > 1 ? (float)(Wi - 1) / (float)(W - 1) : 0.f;
     const Tap th = bilinear_tap(y, Hi, sh), tw = bilinear_tap(x, Wi, sw);
     const size_t plane = ((size_t)b * K + k) * Hi * Wi;
     const float ps = bilinear_at(pred_mean + plane, Wi, th, tw);
-    const float ss = bilinear_at(std_map + plane, Wi, th, tw);
+    float ss = bilinear_at(std_map + plane, Wi, th, tw);
     const bool pseudo = sigmoid_aten(oT_before[i]) > pseudo_thr;
-    bool m = ss < std_thr;
-    if (preds != nullptr && fabsf(ss - std_thr) < kMaskBand)
-        m = std_small_aten(preds, T, (size_t)B * K * Hi * Wi, plane, Wi, th, tw, variant) < std_thr;
-    const size_t hw = (size_t)H * W, pix = (size_t)y * W + x;
-    weights[((size_t)b * 2 * K + k) * hw + pix] = (pseudo && m) ? ps : 0.f;
-    weights[((size_t)b * 2 * K + K + k) * hw + pix] = (!pseudo && m) ? (1.0f - ps) : 0.f;
-    masks[i] = m ? 2.0f : 0.f;
-    if (pseudo_out) pseudo_out[i] = pseudo ? 1.0f : 0.f;
-    if (small_out) { small_out[i] = ps; small_out[n + i] = ss; }
+    if (preds != nullptr)      // kernel-uniform
+        ss = std_small_exact_warp(valid && fabsf(ss - std_thr) < kMaskBand, ss, preds, T, (size_t)B * K * Hi * Wi, plane, Wi, th, tw);
+    const bool m = ss < std_thr;
+    if (valid) {
+        const size_t hw = (size_t)H * W, pix = (size_t)y * W + x;
+        weights[((size_t)b * 2 * K + k) * hw + pix] = (pseudo && m) ? ps : 0.f;
+        weights[((size_t)b * 2 * K + K + k) * hw + pix] = (!pseudo && m) ? (1.0f - ps) : 0.f;
+        masks[i] = m ? 2.0f : 0.f;
+        if (pseudo_out) pseudo_out[i] = pseudo ? 1.0f : 0.f;
+        if (small_out) { small_out[i] = ps; small_out[n + i] = ss; }
+    }
     trace_exit(TR_RETRIFY);
 }
 
@@ -336,19 +354,21 @@ __global__ void __launch_bounds__(256, 4) mc_retrify_kernel(const McRetrifyParam
     const float* s1 = taps + p.cw;          // std, row i1
     const float* m0 = taps + 2 * p.cw;      // mean, row i0
     const float* m1 = taps + 3 * p.cw;      // mean, row i1
-    for (int x = threadIdx.x; x < p.W; x += 256) {
-        const Tap tw = bilinear_tap(x, p.Wi, p.sw);
-        if (tw.i0 < c0 || tw.i0 >= c0 + p.cw) continue;    // another column block's pixel
-        const int a0 = tw.i0 - c0, a1 = tw.i1 - c0;
+    for (int x0 = 0; x0 < p.W; x0 += 256) {                 // CTA-uniform trip count: the guard band is evaluated by whole warps
+        const int x = x0 + (int)threadIdx.x;
+        const int xc = x < p.W ? x : 0;
+        const Tap tw = bilinear_tap(xc, p.Wi, p.sw);
+        const bool mine = x < p.W && tw.i0 >= c0 && tw.i0 < c0 + p.cw;    // else: past the row / another column block's pixel
+        const int a0 = mine ? tw.i0 - c0 : 0, a1 = mine ? tw.i1 - c0 : 0;
         const float ps = bilinear_mix(m0[a0], m0[a1], m1[a0], m1[a1], th, tw);
-        const float ss = bilinear_mix(s0[a0], s0[a1], s1[a0], s1[a1], th, tw);
+        float ss = bilinear_mix(s0[a0], s0[a1], s1[a0], s1[a1], th, tw);
+        if (!PRECISE) ss = std_small_exact_warp(mine && fabsf(ss - p.std_thr) < kMaskBand, ss, p.preds, p.T, p.n, plane, p.Wi, th, tw);
+        if (!mine) continue;
         const size_t pix = (size_t)y * p.W + x;
         const size_t i = (size_t)bk * hw + pix;
         const float o = (x == xg) ? o_pre : __ldg(p.oT_before + i);
         const bool pseudo = sigmoid_aten(o) > p.pseudo_thr;
-        bool m = ss < p.std_thr;
-        if (!PRECISE && fabsf(ss - p.std_thr) < kMaskBand)
-            m = std_small_aten(p.preds, p.T, p.n, plane, p.Wi, th, tw, p.aten.variant) < p.std_thr;
+        const bool m = ss < p.std_thr;
         p.weights[((size_t)b * 2 * p.K + k) * hw + pix] = (pseudo && m) ? ps : 0.f;
         p.weights[((size_t)b * 2 * p.K + p.K + k) * hw + pix] = (!pseudo && m) ? (1.0f - ps) : 0.f;
         p.masks[i] = m ? 2.0f : 0.f;
@@ -393,7 +413,7 @@ int mc_retrify_fused(const float* preds, const float* oT_before, int T, int B, i
     p.sh = sh_f; p.sw = sw_f; p.parts = parts; p.cw = Wi / parts;
     p.pseudo_thr = pseudo_thr; p.std_thr = std_thr;
     p.n = (size_t)B * K * Hi * Wi;
-    p.aten = McAten{tunables().aten_variant, mean_factor_aten(p.n, T)};
+    p.aten = McAten{mean_factor_aten(p.n, T)};
     const dim3 grid((unsigned)(H * parts), (unsigned)(B * K));
     const bool precise = tunables().mc_precise != 0;
     if (precise) launch_k(mc_retrify_kernel<0, true>, grid, 256, smem, st, p);
@@ -432,7 +452,7 @@ int clr_retrify_weights(const float* oT_before, const float* pred_mean, const fl
         H < 1 || W < 1 || Hi < 1 || Wi < 1 || (preds && T < 1))
         return CLR_ERR_BAD_ARG;
     if ((long long)H * W > 0x7fffff00LL || (long long)B * K > 65535) return CLR_ERR_UNSUPPORTED;
-    clr::launch_k(clr::retrify_weights_kernel, dim3((unsigned)((H * W + 255) / 256), (unsigned)(B * K)), 256, 0, static_cast<cudaStream_t>(stream), oT_before, pred_mean, std_map, preds, T, clr::tunables().aten_variant, B, K, H, W, Hi, Wi, pseudo_thr, std_thr, weights, masks, pseudo_out, small_out);
+    clr::launch_k(clr::retrify_weights_kernel, dim3((unsigned)((H * W + 255) / 256), (unsigned)(B * K)), 256, 0, static_cast<cudaStream_t>(stream), oT_before, pred_mean, std_map, preds, T, B, K, H, W, Hi, Wi, pseudo_thr, std_thr, weights, masks, pseudo_out, small_out);
     return clr::launch_status();
 }
 

@@ -33,6 +33,7 @@ struct PoolDom {
     const float* w;
     float* partial;   // [B*nChunk][R][C+1]
     float* sums;      // [R][C+1]
+    float* mu;        // optional [R][C]: the reduce kernel also writes S_r[c] / N_r (single-GPU drop-in: no finalize launch)
     int B;
     int fmt;
     int items;        // B*nChunk*nGroup
@@ -49,7 +50,6 @@ struct PoolParams {
     int stages;       // TMA ring depth
     int reduce_trace_id;
     int skip_reduce;               // 1: the caller reduces the partials itself (pool_finish_kernel)
-    int phase_split;               // LDG kernel, two domains: all of domain 0 before all of domain 1 (see the kernel)
     unsigned int* counter_reset;   // optional: 4 words zeroed by CTA 0 (the finish stage's last-CTA and completion counters)
 };
 
@@ -199,20 +199,13 @@ __global__ void __launch_bounds__(NT, 2) pool_fwd_ldg_kernel(const PoolParams p)
     float* wsm = smem;                 // [R][PX]
     float* red = smem + R * PX;        // [2][NB][kWarps][32]
     const int tid = threadIdx.x;
+    int begin, end;
+    partition(p.total, gridDim.x, blockIdx.x, begin, end);
     int cur_key = -1, parity = 0;
     auto sync = [] { __syncthreads(); };
-    // phase_split: every CTA first walks its share of domain 0 and then its share of domain 1, so the whole grid reads the
-    // second map (the source features in the fused step) LAST -- the part of it that is still in L2 when the discriminative
-    // pass re-reads it is then as large as the cache allows.  Otherwise one contiguous range of [dom 0 | dom 1] per CTA.
-    const int nph = p.phase_split ? p.ndom : 1;
-    for (int ph = 0; ph < nph; ++ph) {
-    int begin, end;
-    if (p.phase_split) {
-        partition(p.dom[ph].items, gridDim.x, blockIdx.x, begin, end);
-        if (ph) { begin += p.dom[0].items; end += p.dom[0].items; }
-    } else {
-        partition(p.total, gridDim.x, blockIdx.x, begin, end);
-    }
+    // (Letting every CTA walk its share of domain 0 before its share of domain 1 -- so that the source map is what the grid
+    // read last and the discriminative pass finds more of it in L2 -- was measured in round 2: the re-read's DRAM bytes
+    // did not move (109.6 vs 109.9 MB of 135.3) and the step got 1.7 us slower; profiles/r02_l2_harvest.md.)
     for (int it = begin; it < end; ++it) {
         const ItemCoord ic = decode_item(p, it);
         const PoolDom& D = p.dom[ic.d];
@@ -252,7 +245,6 @@ __global__ void __launch_bounds__(NT, 2) pool_fwd_ldg_kernel(const PoolParams p)
         }
         float* out = D.partial + (size_t)ic.slot * R * (p.C + 1);
         reduce_and_store<R, CG, VEC, REPS, NT>(acc, wsm, red, parity, out, p.C, c0, ic.grp == 0, tid, sync);
-    }
     }
     trace_exit(TR_POOL);
 }
@@ -394,12 +386,39 @@ __global__ void __launch_bounds__(256) pool_reduce_kernel(const PoolParams p, in
         for (; sl < D.slots; sl += 8) s += (double)D.partial[(size_t)sl * n + col];
     }
     sh[threadIdx.y][threadIdx.x] = s;
+    // mu requested: every thread also sums its row's weight-sum column (same slot split, same order as the thread that owns
+    // that column), so the prototype S_r[c] / N_r leaves this launch too -- from the fp32-rounded sums, like clr_proto_finalize
+    __shared__ double shn[8][33];
+    const int row = col < n ? col / (p.C + 1) : 0;
+    if (D.mu) {
+        double sn = 0.0;
+        if (col < n) {
+            const size_t ncol = (size_t)row * (p.C + 1) + p.C;
+            int sl = threadIdx.y;
+            for (; sl + 56 < D.slots; sl += 64) {
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = D.partial[(size_t)(sl + 8 * u) * n + ncol];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) sn += (double)v[u];
+            }
+            for (; sl < D.slots; sl += 8) sn += (double)D.partial[(size_t)sl * n + ncol];
+        }
+        shn[threadIdx.y][threadIdx.x] = sn;
+    }
     __syncthreads();
     if (threadIdx.y == 0 && col < n) {
         double t = 0.0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) t += sh[i][threadIdx.x];
         D.sums[col] = (float)t;
+        const int c = col - row * (p.C + 1);
+        if (D.mu && c < p.C) {
+            double tn = 0.0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) tn += shn[i][threadIdx.x];
+            D.mu[(size_t)row * p.C + c] = (float)t / (float)tn;      // 0/0 -> NaN, as the reference (utils/Utils.py:127-130)
+        }
     }
     trace_exit(p.reduce_trace_id);
 }
@@ -459,9 +478,8 @@ static int launch_ldg_nt(const PoolParams& p, cudaStream_t st) {
     constexpr int PX = kThreads * VEC * pool_reps(R);
     constexpr size_t smem = sizeof(float) * (R * PX + 2 * (pool_nacc(R) / 32) * (NT / 32) * 32);
     auto kern = pool_fwd_ldg_kernel<R, VEC, NT>;
-    CLR_RETURN_IF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    CLR_RETURN_IF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem));
+    { const int rc = kernel_occupancy(reinterpret_cast<const void*>(kern), NT, smem, &occ); if (rc != CLR_OK) return rc; }
     if (occ < 1) occ = 1;
     int grid = device_facts().sms * occ;
     if (grid > p.total) grid = p.total;
@@ -532,7 +550,7 @@ size_t pool_partial_bytes(int B, int C, int HW, int R) { return sizeof(float) * 
 int pool_fwd_impl(const float* feat0, const float* w0, int fmt0, int B0, float* sums0,
                   const float* feat1, const float* w1, int fmt1, int B1, float* sums1,
                   int C, int HW, int R, void* ws, size_t ws_bytes, cudaStream_t st, int keep0, int keep1,
-                  PoolLayout* skip_reduce_layout, unsigned int* counter_reset) {
+                  PoolLayout* skip_reduce_layout, unsigned int* counter_reset, float* mu0) {
     const int ndom = feat1 ? 2 : 1;
     CLR_CHECK_ARG(feat0 && w0 && sums0 && ws && B0 > 0 && C > 0 && HW > 0 && R >= 1 && R <= 2 * CLR_MAX_K);
     CLR_CHECK_ARG(fmt0 == CLR_W_COMPLEMENT || fmt0 == CLR_W_EXPLICIT);
@@ -558,12 +576,11 @@ int pool_fwd_impl(const float* feat0, const float* w0, int fmt0, int B0, float* 
     const long long items0 = (long long)B0 * p.nChunk * p.nGroup;
     const long long items1 = ndom == 2 ? (long long)B1 * p.nChunk * p.nGroup : 0;
     if (items0 + items1 > 0x3fffffff) return CLR_ERR_UNSUPPORTED;
-    p.dom[0] = PoolDom{feat0, w0, wsf, sums0, B0, fmt0, (int)items0, B0 * p.nChunk, keep0};
+    p.dom[0] = PoolDom{feat0, w0, wsf, sums0, mu0, B0, fmt0, (int)items0, B0 * p.nChunk, keep0};
     if (ndom == 2)
-        p.dom[1] = PoolDom{feat1, w1, wsf + partial_floats(B0, C, HW, R), sums1, B1, fmt1, (int)items1, B1 * p.nChunk, keep1};
+        p.dom[1] = PoolDom{feat1, w1, wsf + partial_floats(B0, C, HW, R), sums1, nullptr, B1, fmt1, (int)items1, B1 * p.nChunk, keep1};
     p.total = (int)(items0 + items1);
     p.reduce_trace_id = TR_POOL_REDUCE;
-    p.phase_split = (ndom == 2 && tunables().pool_order) ? 1 : 0;
     p.counter_reset = counter_reset;
     if (skip_reduce_layout) {
         p.skip_reduce = 1;
@@ -626,6 +643,13 @@ int clr_pool_fwd(const float* feat, const float* w, int fmt, int B, int C, int H
     if (K < 1 || K > CLR_MAX_K) return CLR_ERR_BAD_ARG;
     return clr::pool_fwd_impl(feat, w, fmt, B, sums, nullptr, nullptr, 0, 0, nullptr, C, HW, 2 * K, ws, ws_bytes,
                               static_cast<cudaStream_t>(stream));
+}
+
+int clr_pool_fwd_mu(const float* feat, const float* w, int fmt, int B, int C, int HW, int K,
+                    void* ws, size_t ws_bytes, float* sums, float* mu, clr_stream_t stream) {
+    if (K < 1 || K > CLR_MAX_K || !mu) return CLR_ERR_BAD_ARG;
+    return clr::pool_fwd_impl(feat, w, fmt, B, sums, nullptr, nullptr, 0, 0, nullptr, C, HW, 2 * K, ws, ws_bytes,
+                              static_cast<cudaStream_t>(stream), 0, 0, nullptr, nullptr, mu);
 }
 
 int clr_pool_fwd2(const float* feat0, const float* w0, int fmt0, int B0,

@@ -40,15 +40,36 @@ def _check_k(K: int) -> None:
         raise ValueError("number of classes K=%d outside [1, %d]" % (K, _lib.CLR_MAX_K))
 
 
-def pool_sums(feat: torch.Tensor, w: torch.Tensor, fmt: int, K: int) -> torch.Tensor:
-    """Packed class-wise sums ``[2K, C+1]`` (column C = weight sums) of one domain.  Local to this rank."""
+# Scratch of the drop-in ops (per-CTA partials, consumed inside the same call): cached per (device, stream, size class)
+# instead of a torch.empty per call -- the zero-line drop-in is host-bound, every allocator round trip counts.  Keyed by
+# stream because two streams may run the same op concurrently; outputs are always fresh tensors (autograd owns them).
+_WS_CACHE = {}
+
+
+def _workspace(nbytes: int, device, tag: str) -> torch.Tensor:
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream, tag)
+    ws = _WS_CACHE.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
+        _WS_CACHE[key] = ws
+    return ws
+
+
+def pool_sums(feat: torch.Tensor, w: torch.Tensor, fmt: int, K: int, with_mu: bool = False):
+    """Packed class-wise sums ``[2K, C+1]`` (column C = weight sums) of one domain.  Local to this rank.
+    ``with_mu=True`` also returns the prototypes ``[2K, C]`` from the same two launches (``clr_pool_fwd_mu``)."""
     lib = _lib.load()
     B, C, H, W = feat.shape
     HW = H * W
-    ws_bytes = lib.clr_pool_ws_bytes(B, C, HW, K)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=feat.device)
-    sums = torch.empty(2 * K, C + 1, dtype=torch.float32, device=feat.device)
     with torch.cuda.device(feat.device):
+        ws_bytes = lib.clr_pool_ws_bytes(B, C, HW, K)
+        ws = _workspace(ws_bytes, feat.device, "pool")
+        sums = torch.empty(2 * K, C + 1, dtype=torch.float32, device=feat.device)
+        if with_mu:
+            mu = torch.empty(2 * K, C, dtype=torch.float32, device=feat.device)
+            check(lib.clr_pool_fwd_mu(ptr(feat), ptr(w), fmt, B, C, HW, K, ptr(ws), ws_bytes, ptr(sums), ptr(mu), _stream()),
+                  "clr_pool_fwd_mu")
+            return sums, mu
         check(lib.clr_pool_fwd(ptr(feat), ptr(w), fmt, B, C, HW, K, ptr(ws), ws_bytes, ptr(sums), _stream()),
               "clr_pool_fwd")
     return sums
@@ -83,7 +104,7 @@ def pool_backward_weights(feat: torch.Tensor, fmt: int, K: int, g: torch.Tensor,
     B, C, H, W = feat.shape
     Q = K if fmt == CLR_W_COMPLEMENT else 2 * K
     ws_bytes = lib.clr_pool_bwd_w_ws_bytes(C, K, fmt)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=feat.device)
+    ws = _workspace(ws_bytes, feat.device, "bwd_w")
     out = torch.empty(B, Q, H, W, dtype=torch.float32, device=feat.device)
     with torch.cuda.device(feat.device):
         check(lib.clr_pool_bwd_w(ptr(feat), fmt, B, C, H * W, K, ptr(g), ptr(sums), float(scale),
@@ -118,15 +139,18 @@ class _WeightedPrototypes(torch.autograd.Function):
     def forward(ctx, K: int, fmts, *tensors):
         n_dom = len(tensors) // 2
         ws, feats = tensors[0::2], tensors[1::2]
-        sums = None
-        for w, f, fmt in zip(ws, feats, fmts):
-            s = pool_sums(f, w, fmt, K)
-            sums = s if sums is None else sums + s
         scale = 1.0
-        if _dist.enabled():
-            _dist.all_reduce_sums(sums)
-            scale = _dist.grad_scale()
-        mu = protos_from_sums(sums)
+        if n_dom == 1 and not _dist.enabled():
+            sums, mu = pool_sums(feats[0], ws[0], fmts[0], K, with_mu=True)     # prototypes leave the reduce launch
+        else:
+            sums = None
+            for w, f, fmt in zip(ws, feats, fmts):
+                s = pool_sums(f, w, fmt, K)
+                sums = s if sums is None else sums + s
+            if _dist.enabled():
+                _dist.all_reduce_sums(sums)
+                scale = _dist.grad_scale()
+            mu = protos_from_sums(sums)
         ctx.fmts, ctx.K, ctx.n_dom, ctx.scale = tuple(fmts), K, n_dom, scale
         ctx.shapes = [tuple(f.shape) for f in feats]
         need_w = [ctx.needs_input_grad[2 + 2 * i] for i in range(n_dom)]
@@ -275,15 +299,18 @@ class _RetrifyPrototypes(torch.autograd.Function):
         K = oT_before.shape[1]
         H, W = xt_feature.shape[2:]
         std_map, weights, masks = mc_retrify(oT_before, preds, T, stride, H, W)
-        sums = pool_sums(xt_feature, weights, CLR_W_EXPLICIT, K)
         joint = xs_feature is not None
-        if joint:
-            sums = sums + pool_sums(xs_feature, pred_oS, CLR_W_COMPLEMENT, K)
         scale = 1.0
-        if _dist.enabled():
-            _dist.all_reduce_sums(sums)
-            scale = _dist.grad_scale()
-        mu = protos_from_sums(sums)
+        if not joint and not _dist.enabled():
+            sums, mu = pool_sums(xt_feature, weights, CLR_W_EXPLICIT, K, with_mu=True)
+        else:
+            sums = pool_sums(xt_feature, weights, CLR_W_EXPLICIT, K)
+            if joint:
+                sums = sums + pool_sums(xs_feature, pred_oS, CLR_W_COMPLEMENT, K)
+            if _dist.enabled():
+                _dist.all_reduce_sums(sums)
+                scale = _dist.grad_scale()
+            mu = protos_from_sums(sums)
         ctx.K, ctx.scale, ctx.joint = K, scale, joint
         ctx.n_in = 7 if joint else 5
         ctx.t_shape = tuple(xt_feature.shape)
