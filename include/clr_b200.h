@@ -383,6 +383,10 @@ int clr_peer_close(void* ptr);
 size_t clr_step_xchg_bytes(int world, int K, int C);
 
 size_t clr_step_ws_bytes(const clr_step_args* a);
+/* Which launch schedule clr_step_fwd / clr_step_run use for these arguments: 2 = source pooled first, finish halves hidden
+ * behind the MC statistics / the discriminative pass (retrify + discriminative term), 1 = both maps pooled in one launch.
+ * The optional ev_pool_* events bracket the two-domain pooling launch (1) or the source pooling launch (2). */
+int clr_step_schedule(const clr_step_args* a);
 int clr_step_fwd_a(const clr_step_args* a, clr_stream_t stream);
 int clr_step_fwd_b(const clr_step_args* a, clr_stream_t stream);
 int clr_step_fwd_c(const clr_step_args* a, clr_stream_t stream);

@@ -826,3 +826,42 @@ def test_merged_backward_launch_equals_two_launches(K, C, H):
     assert float(res[0][0][7]) == 0.0            # no gate time-out
     for x, y in zip(res[0], res[1]):
         assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize("K,C,H,B", [(2, 256, 64, 2), (2, 305, 32, 3), (3, 37, 16, 2), (8, 24, 16, 2)])
+def test_schedule2_equals_schedule1_bit_for_bit(K, C, H, B):
+    """The fused step's default launch schedule for clr3 (source pooled first, finish halves hidden behind the MC statistics
+    and the discriminative pass; csrc/step.cu) against schedule 1 ("sched_v1" = 1: both maps pooled in one launch): the
+    arithmetic and every summation order are the same, so losses, prototypes, EMA state and both gradient maps must be
+    bit-identical over three steps, through the prebound plan and through autograd."""
+    from uda_clr_b200 import _lib
+    lib = _lib.load()
+    b = synth.make_batch(B=B, C=C, H=H, W=H, K=K, T=8, up=4, seed=21 + C, image_res=True)
+    t = {k: getattr(b, k).to(DEV) for k in ("xs", "ys", "xt", "oT_before", "preds", "oT", "oT_aug")}
+    res = []
+    for v1 in (0, 1):
+        try:
+            _lib.check(lib.clr_set_tunable(b"sched_v1", v1), "sched_v1")
+            step = clr.CLRStep(K=K, retrify=True, use_disc=True, use_cons=True, backprop_aug=True)
+            plan = step.plan(t["xs"], t["ys"], t["xt"], oT_before=t["oT_before"], preds=t["preds"], T=8, oT=t["oT"],
+                             oT_aug=t["oT_aug"], epoch=1.0)
+            assert lib.clr_step_schedule(plan._ref) == (1 if v1 else 2)
+            for _ in range(3):
+                plan.run()
+            torch.cuda.synchronize()
+            o = plan.outputs()
+            row = [plan.losses.clone(), plan.gxs.clone(), plan.gxt.clone(), plan.g_oT_aug.clone(), step.stored_s.clone(),
+                   step.stored_t.clone(), torch.cat([p.reshape(-1) for p in o.source_prototypes + o.target_prototypes]),
+                   torch.cat(o.masks, 1).clone()]
+            step2 = clr.CLRStep(K=K, retrify=True, use_disc=True, use_cons=True, backprop_aug=True)
+            for _ in range(2):
+                xs, xt = t["xs"].clone().requires_grad_(True), t["xt"].clone().requires_grad_(True)
+                out = step2(xs, t["ys"], xt, oT_before=t["oT_before"], preds=t["preds"], T=8, oT=t["oT"], oT_aug=t["oT_aug"], epoch=1.0)
+                out.total.backward()
+            row += [out.total.detach().clone(), xs.grad.clone(), xt.grad.clone()]
+            res.append(row)
+        finally:
+            lib.clr_set_tunable(b"sched_v1", 0)
+    assert float(res[0][0][7]) == 0.0
+    for x, y in zip(res[0], res[1]):
+        assert torch.equal(x, y)

@@ -132,6 +132,7 @@ _SIGNATURES = {
     "clr_disc_finalize": (c_int, [_P, _P, c_int, c_int, c_double, c_float, c_float, c_float, _P, _P,
                                   c_float, c_float, c_float, c_float, c_int, c_int, _P, _P]),
     "clr_step_ws_bytes": (c_size_t, [POINTER(StepArgs)]),
+    "clr_step_schedule": (c_int, [POINTER(StepArgs)]),
     "clr_step_fwd_a": (c_int, [POINTER(StepArgs), _P]),
     "clr_step_fwd_b": (c_int, [POINTER(StepArgs), _P]),
     "clr_step_fwd_c": (c_int, [POINTER(StepArgs), _P]),

@@ -56,6 +56,7 @@ int clr_set_tunable(const char* name, int value) {
     else if (!strcmp(name, "fin_early_off")) t.fin_early_off = value;
     else if (!strcmp(name, "mc_split")) t.mc_split = value;
     else if (!strcmp(name, "disc_reverse")) t.disc_reverse = value;
+    else if (!strcmp(name, "sched_v1")) t.sched_v1 = value;
 
     else return CLR_ERR_BAD_ARG;
     return CLR_OK;
@@ -82,7 +83,7 @@ int clr_trace_slots(void) { return clr::kTraceSlots; }
 const char* clr_trace_name(int slot) {
     static const char* names[clr::kTraceSlots] = {"mc_stats", "retrify_weights", "pool_fwd", "pool_reduce", "align_finalize",
         "cons_fwd", "disc_fused", "disc_reduce", "disc_finalize", "pool_bwd_target", "pool_bwd_source", "pool_bwd_both",
-        "cons_bwd", "step_pack", "other", "", "dbg0", "dbg1", "dbg2", "dbg3", "dbg4", "dbg5", "dbg6", "dbg7"};
+        "cons_bwd", "step_pack", "other", "pool_fwd_target", "dbg0", "dbg1", "dbg2", "dbg3", "dbg4", "dbg5", "dbg6", "finish_source"};
     return (slot >= 0 && slot < clr::kTraceSlots) ? names[slot] : "";
 }
 int clr_trace_read(unsigned long long* out_host) {

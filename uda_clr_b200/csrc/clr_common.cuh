@@ -48,6 +48,7 @@ struct Tunables {
                        //     instead of the finish CTAs' completion counter
     int disc_reverse;  // 1 = the one-read discriminative kernel walks its tiles in descending address order (round 2: the re-read of
                        //     xs then misses DRAM for 102 instead of 110 of 135 MB, the kernel is not faster -- it is not DRAM-bound)
+    int sched_v1;      // 1 = the fused step keeps schedule 1 (both maps pooled in one launch after the MC statistics; step.cu)
     int xchg_pull;     // in-kernel exchange: 1 = readers poll the peers' buffers (no remote stores), 0 = senders push
     void* trace_buf;   // device TraceRec[kTraceSlots] or NULL (clr_trace_set): device-side timeline of the kernels
 };
@@ -70,8 +71,8 @@ void count_launch();
 // serialises kernels and event records break programmatic dependent launch.
 struct TraceRec { unsigned long long t_first, t_ready, t_last, n_cta; };
 enum TraceId { TR_MC_STATS = 0, TR_RETRIFY, TR_POOL, TR_POOL_REDUCE, TR_ALIGN, TR_CONS, TR_DISC, TR_DISC_REDUCE,
-               TR_DISC_FIN, TR_BWD_T, TR_BWD_S, TR_BWD_BOTH, TR_CONS_BWD, TR_PACK, TR_OTHER, TR_DBG0 = 16, TR_DBG1, TR_DBG2, TR_DBG3, TR_DBG4, TR_DBG5,
-               TR_DBG6, TR_DBG7, kTraceSlots = 24 };
+               TR_DISC_FIN, TR_BWD_T, TR_BWD_S, TR_BWD_BOTH, TR_CONS_BWD, TR_PACK, TR_OTHER, TR_POOL_T /*schedule 2: target pooling*/, TR_DBG0 = 16, TR_DBG1, TR_DBG2, TR_DBG3, TR_DBG4, TR_DBG5,
+               TR_DBG6, TR_FIN_S /*schedule 2: source half of the pooling finish*/, kTraceSlots = 24 };
 static __device__ TraceRec* g_trace_dev = nullptr;     // one copy per translation unit, installed by launch_k
 __device__ __forceinline__ unsigned long long global_ns() {
     unsigned long long t;

@@ -152,6 +152,12 @@ struct PoolFinishParams {
     unsigned int* done_all;
     int early_signal;          // 1: done_fin is bumped before the last-CTA combine (the consumer sums beta itself), 0: at the CTA's end
     int write_total;           // alignment-only step (no discriminative / consistency term): the last CTA also writes the totals
+    // Split form (fused step, schedule 2): the SOURCE half runs right after the source pooling (mode 1: sums, EMA'd source
+    // prototypes, separation loss, the discriminative term's vectors) hidden behind the MC statistics; the TARGET half
+    // (mode 2: target sums / prototypes, alignment loss, all gradients) runs after the target pooling, reads the source
+    // prototypes the first half left in P[0] and waits (already satisfied in practice) on that half's completion counter.
+    int mode;                  // 0 = both domains in one body, 1 = source half, 2 = target half
+    const unsigned int* wait_src; unsigned int wait_src_n; float* wait_err;     // mode 2
 };
 static inline int pool_finish_ctas(int C) { return (C + 7) / 8; }
 
@@ -161,6 +167,8 @@ __device__ __forceinline__ void pool_finish_body(const PoolFinishParams& p, cons
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ch = lane >> 2, sl0 = lane & 3;
     const int c = cta * 8 + ch;
+    const bool do_s = p.mode != 2, do_t = p.mode != 1;            // which domains THIS body reduces / finalises
+    const int d_lo = do_s ? 0 : 1, d_hi = do_t ? 2 : 1;
     __shared__ float S[2][2 * CLR_MAX_K][8];
     __shared__ float Nn[2][2 * CLR_MAX_K];
     __shared__ double lp[8 * CLR_MAX_K][NL];
@@ -174,11 +182,11 @@ __device__ __forceinline__ void pool_finish_body(const PoolFinishParams& p, cons
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const size_t e = (size_t)((tid >> 3) + h * K) * C + cta * 8 + (tid & 7);
-            if (!p.first[0]) st_pre[0][h] = __ldcg(p.stored[0] + e);
-            if (!p.first[1]) st_pre[1][h] = __ldcg(p.stored[1] + e);
+            if (do_s && !p.first[0]) st_pre[0][h] = __ldcg(p.stored[0] + e);
+            if (do_t && !p.first[1]) st_pre[1][h] = __ldcg(p.stored[1] + e);
         }
     }
-    for (int pair = warp; pair < 2 * R; pair += kWarps) {
+    for (int pair = d_lo * R + warp; pair < d_hi * R; pair += kWarps) {
         const int d = pair / R, r = pair - d * R;
         const float* part = p.partial[d];
         const int slots = p.slots[d];
@@ -198,23 +206,30 @@ __device__ __forceinline__ void pool_finish_body(const PoolFinishParams& p, cons
     }
     if (p.x.world > 1) {
         __syncthreads();           // xchg_bad = 0 is visible before anybody can raise it
-        // global sums: items [0, 2R*8) are (pair, channel) entries, the next 2R the weight-sum columns; looped, because
-        // 2R*8 + 2R exceeds the 256 threads of the CTA for K = 8 (R = 16)
-        for (int it = tid; it < 2 * R * 8 + 2 * R; it += kThreads) {
-            if (it < 2 * R * 8) {
-                const int pair = it >> 3, j = it & 7, d = pair / R, r = pair - d * R, cc = cta * 8 + j;
+        // global sums: items [0, nd*R*8) are (pair, channel) entries, the next nd*R the weight-sum columns (nd = domains of
+        // this body); looped, because 2R*8 + 2R exceeds the 256 threads of the CTA for K = 8 (R = 16)
+        const int npairs = (d_hi - d_lo) * R;
+        for (int it = tid; it < npairs * 8 + npairs; it += kThreads) {
+            if (it < npairs * 8) {
+                const int pair = d_lo * R + (it >> 3), j = it & 7, d = pair / R, r = pair - d * R, cc = cta * 8 + j;
                 if (cc < C) {
                     const float v = xchg_pull_sum(p.x, (d * R + r) * (C + 1) + cc, &xchg_bad);
                     S[d][r][j] = v;
                     p.sums[d][(size_t)r * (C + 1) + cc] = v;
                 }
             } else {
-                const int pair = it - 2 * R * 8, d = pair / R, r = pair - d * R;
+                const int pair = d_lo * R + (it - npairs * 8), d = pair / R, r = pair - d * R;
                 const float v = xchg_pull_sum(p.x, (d * R + r) * (C + 1) + C, &xchg_bad);
                 Nn[d][r] = v;
                 if (cta == 0) p.sums[d][(size_t)r * (C + 1) + C] = v;
             }
         }
+    }
+    if (p.mode == 2 && p.wait_src) {
+        // the source half's prototypes (P[0]) are read below through coherent loads; its completion counter was bumped tens
+        // of microseconds ago in practice (it ran behind the MC statistics) -- this wait is the formal ordering.  A miss
+        // (~2 s) sets losses[7] and poisons this half like a lost peer does.
+        if (tid == 0 && !spin_until_at_least(p.wait_src, p.wait_src_n)) { if (p.wait_err) *p.wait_err = 1.f; xchg_bad = 1; }
     }
     __syncthreads();
     const bool keep_state = xchg_bad == 0;
@@ -231,29 +246,41 @@ __device__ __forceinline__ void pool_finish_body(const PoolFinishParams& p, cons
             for (int h = 0; h < 2; ++h) {
                 const int rr = k + h * K;
                 const size_t e = (size_t)rr * C + cc;
-                const float cs = S[0][rr][j] / Nn[0][rr];                         // utils/Utils.py:127-130
-                const float ct = S[1][rr][j] / Nn[1][rr];
-                ps[h] = p.first[0] ? cs : __fadd_rn(__fmul_rn(omd, st_pre[0][h]), __fmul_rn(dd, cs));
-                pt[h] = p.first[1] ? ct : __fadd_rn(__fmul_rn(omd, st_pre[1][h]), __fmul_rn(dd, ct));
-                p.P[0][e] = ps[h]; p.P[1][e] = pt[h];
-                if (keep_state) { p.stored[0][e] = ps[h]; p.stored[1][e] = pt[h]; }   // .detach() copies (Trainer_prototype_full.py:341-344)
-                const double df = (double)ps[h] - (double)pt[h];
-                acc[0] += df * df;
+                if (do_s) {
+                    const float cs = S[0][rr][j] / Nn[0][rr];                     // utils/Utils.py:127-130
+                    ps[h] = p.first[0] ? cs : __fadd_rn(__fmul_rn(omd, st_pre[0][h]), __fmul_rn(dd, cs));
+                    p.P[0][e] = ps[h];
+                    if (keep_state) p.stored[0][e] = ps[h];                       // .detach() copy (Trainer_prototype_full.py:341-344)
+                } else {
+                    ps[h] = keep_state ? __ldcg(p.P[0] + e) : __int_as_float(0x7fc00000);   // written by the source half
+                }
+                if (do_t) {
+                    const float ct = S[1][rr][j] / Nn[1][rr];
+                    pt[h] = p.first[1] ? ct : __fadd_rn(__fmul_rn(omd, st_pre[1][h]), __fmul_rn(dd, ct));
+                    p.P[1][e] = pt[h];
+                    if (keep_state) p.stored[1][e] = pt[h];                       // (:384-387)
+                    const double df = (double)ps[h] - (double)pt[h];
+                    acc[0] += df * df;
+                }
             }
             const float dob = ps[0] - ps[1];
-            acc[1] += (double)dob * dob;
-            const float gsep = ds * p.w_inter * 2.0f * dob * invC;
+            if (do_s) acc[1] += (double)dob * dob;
+            if (do_t) {
+                const float gsep = ds * p.w_inter * 2.0f * dob * invC;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const size_t e = (size_t)(k + h * K) * C + cc;
-                const float gi = p.w_intra * 2.0f * (ps[h] - pt[h]) * invC;
-                p.g[0][e] = ds * gi + (h == 0 ? gsep : -gsep);
-                p.g[1][e] = -dt * gi;
+                for (int h = 0; h < 2; ++h) {
+                    const size_t e = (size_t)(k + h * K) * C + cc;
+                    const float gi = p.w_intra * 2.0f * (ps[h] - pt[h]) * invC;
+                    p.g[0][e] = ds * gi + (h == 0 ? gsep : -gsep);
+                    p.g[1][e] = -dt * gi;
+                }
             }
-            if (p.disc_vec) p.disc_vec[(size_t)k * C + cc] = dob;
+            if (do_s) {
+                if (p.disc_vec) p.disc_vec[(size_t)k * C + cc] = dob;
 #pragma unroll
-            for (int kk = 0; kk < CLR_MAX_K; ++kk)
-                if (kk == k) acc[2 + kk] = (double)ps[0] * ps[0] - (double)ps[1] * ps[1];
+                for (int kk = 0; kk < CLR_MAX_K; ++kk)
+                    if (kk == k) acc[2 + kk] = (double)ps[0] * ps[0] - (double)ps[1] * ps[1];
+            }
         }
 #pragma unroll
         for (int i = 0; i < NL; ++i) lp[tid][i] = acc[i];
@@ -278,8 +305,11 @@ __device__ __forceinline__ void pool_finish_body(const PoolFinishParams& p, cons
     __syncthreads();
     if (is_last) {
         __threadfence();
-        // warp i sums value i over the CTAs: lanes take CTAs lane, lane+32, .. (loads in flight together), fixed order
+        // warp i sums value i over the CTAs: lanes take CTAs lane, lane+32, .. (loads in flight together), fixed order.
+        // value 0 = alignment (needs both domains: written by the body that has the target), 1 = separation and 2.. = the
+        // discriminative offsets (source only)
         for (int i = warp; i < 2 + K; i += kWarps) {
+            if ((i == 0 && !do_t) || (i >= 1 && !do_s)) continue;            // warp-uniform
             double t = 0.0;
             for (int b = lane; b < ncta; b += 32) t += __ldcg(p.loss_partial + (size_t)b * NL + i);
             t = warp_sum(t);

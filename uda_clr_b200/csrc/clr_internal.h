@@ -10,7 +10,8 @@ struct PoolLayout;
 int pool_fwd_impl(const float* feat0, const float* w0, int fmt0, int B0, float* sums0,
                   const float* feat1, const float* w1, int fmt1, int B1, float* sums1,
                   int C, int HW, int R, void* ws, size_t ws_bytes, cudaStream_t st, int keep0 = 0, int keep1 = 0,
-                  struct PoolLayout* skip_reduce_layout = nullptr, unsigned int* counter_reset = nullptr, float* mu0 = nullptr);
+                  struct PoolLayout* skip_reduce_layout = nullptr, unsigned int* counter_reset = nullptr, float* mu0 = nullptr,
+                  int trace_id = 2 /*TR_POOL*/);
 size_t pool_partial_bytes(int B, int C, int HW, int R);
 // sums[r][c] = sum_slot partial[slot][r][c] (fp64, fixed order) for a [slots][R][C+1] partial buffer
 void launch_partial_reduce(const float* partial, int slots, int R, int C, float* sums, cudaStream_t st);
@@ -56,6 +57,9 @@ int pool_bwd_one(const clr_bwd_dom* dom, int C, int HW, int K, const DiscFinishP
 int pool_bwd_merged(const clr_bwd_dom* first, const clr_bwd_dom* gated, int C, int HW, int K, const DiscFinishParams* f,
                     unsigned int* gate, float* gate_err, cudaStream_t st);
 
+// clr_mc_stats with the option to skip griddepcontrol.wait (fused step, schedule 2: see the kernel)
+int mc_stats_impl(const float* preds, int T, int B, int K, int Hi, int Wi, float* std_map, float* pred_mean, cudaStream_t st,
+                  bool nowait);
 // MC statistics + retrify weights in one pass (mc_stats.cu); CLR_ERR_UNSUPPORTED -> run the two kernels.
 int mc_retrify_fused(const float* preds, const float* oT_before, int T, int B, int K, int H, int W, int Hi, int Wi,
                      float pseudo_thr, float std_thr, float* std_map, float* pred_mean /*nullable*/, float* weights,

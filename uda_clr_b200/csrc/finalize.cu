@@ -174,10 +174,11 @@ int disc_finalize_impl(float* packed2, const float* P_s, int K, int C, double np
 // Stand-alone launches of the merged reduce + finalize bodies (clr_finish.cuh); the fused step co-schedules them with
 // the consistency pass / the target-gradient write instead (cons.cu, pool_bwd.cu).
 __global__ void __launch_bounds__(kThreads) pool_finish_kernel(const PoolFinishParams p) {
-    if (p.done_fin) kernel_begin_late_trigger(TR_ALIGN); else kernel_begin(TR_ALIGN);
+    const int tr = p.mode == 1 ? TR_FIN_S : TR_ALIGN;
+    if (p.done_fin || p.done_all) kernel_begin_late_trigger(tr); else kernel_begin(tr);
     pool_finish_body(p, blockIdx.x, gridDim.x);
     if (p.done_all) cta_signal(p.early_signal ? nullptr : p.done_fin, p.done_all);   // (early: done_fin was bumped inside the body)
-    trace_exit(TR_ALIGN);
+    trace_exit(tr);
 }
 __global__ void __launch_bounds__(kThreads) disc_finish_kernel(const DiscFinishParams p) {
     kernel_begin(TR_DISC_FIN);

@@ -181,8 +181,15 @@ __device__ __forceinline__ void mc_vec_stats(const float* __restrict__ preds, in
 template <int VEC, int TT, bool PRECISE, bool EXACT = false>
 __global__ void __launch_bounds__(256) mc_stats_kernel(const float* __restrict__ preds, int T, size_t n,
                                                        float* __restrict__ std_map, float* __restrict__ pred_mean,
-                                                       const McAten aten) {
-    kernel_begin(TR_MC_STATS);
+                                                       const McAten aten, const int nowait) {
+    // nowait (fused step, schedule 2): the launch in front of this one is the source half of the pooling finish -- a few
+    // CTAs whose results this kernel does not read, and which trigger their dependents only AFTER their own
+    // griddepcontrol.wait (everything older in the stream has completed by then).  Skipping the wait lets the whole
+    // machine stream the MC logits while that latency chain (and, sharded, its cross-GPU exchange) runs.
+    trace_enter(TR_MC_STATS);
+    pdl_trigger();
+    if (!nowait) pdl_wait();
+    trace_ready(TR_MC_STATS);
     // n = B*K*Hi*Wi positions
     const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
     if (i >= n) { trace_exit(TR_MC_STATS); return; }
@@ -194,15 +201,15 @@ __global__ void __launch_bounds__(256) mc_stats_kernel(const float* __restrict__
 }
 
 template <int VEC, bool PRECISE>
-static void launch_mc(const float* preds, int T, size_t n, float* std_map, float* pred_mean, cudaStream_t st) {
+static void launch_mc(const float* preds, int T, size_t n, float* std_map, float* pred_mean, cudaStream_t st, int nowait) {
     const size_t threads = (n + VEC - 1) / VEC;
     const unsigned blocks = (unsigned)((threads + 255) / 256);
     const McAten aten{mean_factor_aten(n, T)};
-    if (PRECISE) launch_k(mc_stats_kernel<VEC, 0, PRECISE>, blocks, 256, 0, st, preds, T, n, std_map, pred_mean, aten);
-    else if (T == 8 && !tunables().mc_generic) launch_k(mc_stats_kernel<VEC, 8, PRECISE, true>, blocks, 256, 0, st, preds, T, n, std_map, pred_mean, aten);
-    else if (T <= 8) launch_k(mc_stats_kernel<VEC, 8, PRECISE>, blocks, 256, 0, st, preds, T, n, std_map, pred_mean, aten);
-    else if (T <= 16) launch_k(mc_stats_kernel<VEC, 16, PRECISE>, blocks, 256, 0, st, preds, T, n, std_map, pred_mean, aten);
-    else launch_k(mc_stats_kernel<VEC, 0, PRECISE>, blocks, 256, 0, st, preds, T, n, std_map, pred_mean, aten);
+    if (PRECISE) launch_k(mc_stats_kernel<VEC, 0, PRECISE>, blocks, 256, 0, st, preds, T, n, std_map, pred_mean, aten, nowait);
+    else if (T == 8 && !tunables().mc_generic) launch_k(mc_stats_kernel<VEC, 8, PRECISE, true>, blocks, 256, 0, st, preds, T, n, std_map, pred_mean, aten, nowait);
+    else if (T <= 8) launch_k(mc_stats_kernel<VEC, 8, PRECISE>, blocks, 256, 0, st, preds, T, n, std_map, pred_mean, aten, nowait);
+    else if (T <= 16) launch_k(mc_stats_kernel<VEC, 16, PRECISE>, blocks, 256, 0, st, preds, T, n, std_map, pred_mean, aten, nowait);
+    else launch_k(mc_stats_kernel<VEC, 0, PRECISE>, blocks, 256, 0, st, preds, T, n, std_map, pred_mean, aten, nowait);
 }
 
 // upsample_bilinear2d (align_corners=True) source coordinates, as ATen computes them in fp32
@@ -241,6 +248,34 @@ __device__ __forceinline__ float std_small_exact_warp(bool need, float ss, const
                                                       size_t plane, int Wi, const Tap& h, const Tap& w) {
     const unsigned lane = threadIdx.x & 31u;
     unsigned pending = __ballot_sync(0xffffffffu, need);
+    if (T <= 8) {
+        // the reference's T = 8: one flagged pixel per round, lane = (tap, MC pass): ONE load and ONE exact sigmoid per lane,
+        // then every lane of a tap group runs the (cheap) Welford recurrence over the group's 8 values by shuffle
+        while (pending) {                               // warp-uniform
+            const unsigned src = __ffs(pending) - 1u;
+            pending &= pending - 1u;
+            const unsigned long long pl = __shfl_sync(0xffffffffu, (unsigned long long)plane, src);
+            const int hi0 = __shfl_sync(0xffffffffu, h.i0, src), hi1 = __shfl_sync(0xffffffffu, h.i1, src);
+            const int wi0 = __shfl_sync(0xffffffffu, w.i0, src), wi1 = __shfl_sync(0xffffffffu, w.i1, src);
+            const unsigned tap = lane >> 3, t = lane & 7u;
+            float x = 0.f;
+            if ((int)t < T)
+                x = sigmoid_half_aten(__ldg(preds + (size_t)t * n + (size_t)pl + (size_t)((tap & 2u) ? hi1 : hi0) * Wi + ((tap & 1u) ? wi1 : wi0)));
+            WelfordAcc a0{0.f, 0.f, 0.f}, a1{0.f, 0.f, 0.f};
+#pragma unroll
+            for (int tt = 0; tt < 8; ++tt) {
+                const float v = __shfl_sync(0xffffffffu, x, (lane & 24u) + tt);
+                if (tt < T) { if (tt & 1) welford_push(a1, v); else welford_push(a0, v); }
+            }
+            const WelfordAcc r = welford_merge(a0, a1);
+            const float divisor = r.nf > 1.0f ? __fsub_rn(r.nf, 1.0f) : 0.0f;
+            const float val = __fsqrt_rn(__fdiv_rn(r.m2, divisor));
+            const float a = __shfl_sync(0xffffffffu, val, 0), b = __shfl_sync(0xffffffffu, val, 8);
+            const float c = __shfl_sync(0xffffffffu, val, 16), d = __shfl_sync(0xffffffffu, val, 24);
+            if (lane == src) ss = bilinear_mix(a, b, c, d, h, w);
+        }
+        return ss;
+    }
     while (pending) {                                   // warp-uniform
         const unsigned slot = lane >> 2, tap = lane & 3u;
         const unsigned src = __fns(pending, 0, (int)slot + 1);             // lane of the slot-th flagged pixel, or ~0u
@@ -423,25 +458,30 @@ int mc_retrify_fused(const float* preds, const float* oT_before, int T, int B, i
     return launch_status();
 }
 
+int mc_stats_impl(const float* preds, int T, int B, int K, int Hi, int Wi, float* std_map, float* pred_mean, cudaStream_t st,
+                  bool nowait) {
+    if (!preds || !std_map || !pred_mean || T < 1 || B < 1 || K < 1 || Hi < 1 || Wi < 1) return CLR_ERR_BAD_ARG;
+    const size_t n = (size_t)B * K * Hi * Wi;
+    const bool vec4 = (n % 4 == 0) && aligned16(preds) && aligned16(std_map) && aligned16(pred_mean);
+    const bool precise = tunables().mc_precise != 0;
+    const int nw = nowait ? 1 : 0;
+    if (vec4) {
+        if (precise) launch_mc<4, true>(preds, T, n, std_map, pred_mean, st, nw);
+        else launch_mc<4, false>(preds, T, n, std_map, pred_mean, st, nw);
+    } else {
+        if (precise) launch_mc<1, true>(preds, T, n, std_map, pred_mean, st, nw);
+        else launch_mc<1, false>(preds, T, n, std_map, pred_mean, st, nw);
+    }
+    return launch_status();
+}
+
 }  // namespace clr
 
 extern "C" {
 
 int clr_mc_stats(const float* preds, int T, int B, int K, int Hi, int Wi,
                  float* std_map, float* pred_mean, clr_stream_t stream) {
-    if (!preds || !std_map || !pred_mean || T < 1 || B < 1 || K < 1 || Hi < 1 || Wi < 1) return CLR_ERR_BAD_ARG;
-    const size_t n = (size_t)B * K * Hi * Wi;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const bool vec4 = (n % 4 == 0) && clr::aligned16(preds) && clr::aligned16(std_map) && clr::aligned16(pred_mean);
-    const bool precise = clr::tunables().mc_precise != 0;
-    if (vec4) {
-        if (precise) clr::launch_mc<4, true>(preds, T, n, std_map, pred_mean, st);
-        else clr::launch_mc<4, false>(preds, T, n, std_map, pred_mean, st);
-    } else {
-        if (precise) clr::launch_mc<1, true>(preds, T, n, std_map, pred_mean, st);
-        else clr::launch_mc<1, false>(preds, T, n, std_map, pred_mean, st);
-    }
-    return clr::launch_status();
+    return clr::mc_stats_impl(preds, T, B, K, Hi, Wi, std_map, pred_mean, static_cast<cudaStream_t>(stream), false);
 }
 
 int clr_retrify_weights(const float* oT_before, const float* pred_mean, const float* std_map,

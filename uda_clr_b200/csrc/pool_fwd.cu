@@ -49,8 +49,9 @@ struct PoolParams {
     int total;
     int stages;       // TMA ring depth
     int reduce_trace_id;
+    int trace_id;                  // TR_POOL, or TR_POOL_T for the target pooling launch of schedule 2
     int skip_reduce;               // 1: the caller reduces the partials itself (pool_finish_kernel)
-    unsigned int* counter_reset;   // optional: 4 words zeroed by CTA 0 (the finish stage's last-CTA and completion counters)
+    unsigned int* counter_reset;   // optional: 8 words zeroed by CTA 0 (the finish stages' last-CTA / completion counters, the gate)
 };
 
 // Register blocking: a thread keeps CG x R accumulators -- 32 of them up to R = 8, 64 beyond (R = 16 would otherwise
@@ -191,8 +192,8 @@ __device__ __forceinline__ void reduce_and_store(float (&acc)[pool_nacc(R)], con
 // FADD were as many instructions as the FMAs themselves (ncu source page, K = 8: 33.5 M FFMA vs 33.3 M).
 template <int R, int VEC, int NT>
 __global__ void __launch_bounds__(NT, 2) pool_fwd_ldg_kernel(const PoolParams p) {
-    kernel_begin(TR_POOL);
-    if (p.counter_reset && blockIdx.x == 0 && threadIdx.x < 4) p.counter_reset[threadIdx.x] = 0u;   // last-CTA counter + completion counters
+    kernel_begin(p.trace_id);
+    if (p.counter_reset && blockIdx.x == 0 && threadIdx.x < 8) p.counter_reset[threadIdx.x] = 0u;   // last-CTA counters + completion counters + gate
     constexpr int CG = pool_cg(R), REPS = pool_reps(R) * (kThreads / NT), PX = NT * VEC * REPS;
     static_assert(PX == kThreads * VEC * pool_reps(R), "chunk size is independent of the CTA size");
     extern __shared__ __align__(16) float smem[];
@@ -246,7 +247,7 @@ __global__ void __launch_bounds__(NT, 2) pool_fwd_ldg_kernel(const PoolParams p)
         float* out = D.partial + (size_t)ic.slot * R * (p.C + 1);
         reduce_and_store<R, CG, VEC, REPS, NT>(acc, wsm, red, parity, out, p.C, c0, ic.grp == 0, tid, sync);
     }
-    trace_exit(TR_POOL);
+    trace_exit(p.trace_id);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -267,8 +268,8 @@ struct PoolTmaSmem {
 
 template <int R>
 __global__ void __launch_bounds__(kPoolTmaThreads, 1) pool_fwd_tma_kernel(const PoolParams p) {
-    kernel_begin(TR_POOL);
-    if (p.counter_reset && blockIdx.x == 0 && threadIdx.x < 4) p.counter_reset[threadIdx.x] = 0u;   // last-CTA counter + completion counters
+    kernel_begin(p.trace_id);
+    if (p.counter_reset && blockIdx.x == 0 && threadIdx.x < 8) p.counter_reset[threadIdx.x] = 0u;   // last-CTA counters + completion counters + gate
     using SM = PoolTmaSmem<R>;
     constexpr int CG = SM::CG, REPS = SM::REPS, PX = SM::PX, VEC = 4;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -360,7 +361,7 @@ __global__ void __launch_bounds__(kPoolTmaThreads, 1) pool_fwd_tma_kernel(const 
         float* out = D.partial + (size_t)ic.slot * R * (p.C + 1);
         reduce_and_store<R, CG, VEC, REPS>(acc, wsm, red, parity, out, p.C, c0, ic.grp == 0, tid, sync);
     }
-    trace_exit(TR_POOL);
+    trace_exit(p.trace_id);
 }
 
 // sums[r][c] = sum over (b,chunk) slots of partial[slot][r][c], fp64, fixed order.
@@ -550,7 +551,7 @@ size_t pool_partial_bytes(int B, int C, int HW, int R) { return sizeof(float) * 
 int pool_fwd_impl(const float* feat0, const float* w0, int fmt0, int B0, float* sums0,
                   const float* feat1, const float* w1, int fmt1, int B1, float* sums1,
                   int C, int HW, int R, void* ws, size_t ws_bytes, cudaStream_t st, int keep0, int keep1,
-                  PoolLayout* skip_reduce_layout, unsigned int* counter_reset, float* mu0) {
+                  PoolLayout* skip_reduce_layout, unsigned int* counter_reset, float* mu0, int trace_id) {
     const int ndom = feat1 ? 2 : 1;
     CLR_CHECK_ARG(feat0 && w0 && sums0 && ws && B0 > 0 && C > 0 && HW > 0 && R >= 1 && R <= 2 * CLR_MAX_K);
     CLR_CHECK_ARG(fmt0 == CLR_W_COMPLEMENT || fmt0 == CLR_W_EXPLICIT);
@@ -581,6 +582,7 @@ int pool_fwd_impl(const float* feat0, const float* w0, int fmt0, int B0, float* 
         p.dom[1] = PoolDom{feat1, w1, wsf + partial_floats(B0, C, HW, R), sums1, nullptr, B1, fmt1, (int)items1, B1 * p.nChunk, keep1};
     p.total = (int)(items0 + items1);
     p.reduce_trace_id = TR_POOL_REDUCE;
+    p.trace_id = trace_id;
     p.counter_reset = counter_reset;
     if (skip_reduce_layout) {
         p.skip_reduce = 1;

@@ -34,7 +34,9 @@ static StepWs carve(const clr_step_args* a) {
     w.rows_bytes = align_up(rows);
     w.hinge_bytes = a->use_disc ? align_up(sizeof(float) * (size_t)clr_disc_partials_cap() * (1 + a->K)) : 0;
     w.cons_bytes = a->use_cons ? align_up(clr_cons_ws_bytes()) : 0;
-    w.fin_bytes = align_up(sizeof(double) * (size_t)pool_finish_ctas(a->C) * (2 + CLR_MAX_K) + 64);
+    // pool finish: per-CTA loss partials of the two halves (source / target, schedule 2; the one-body form uses the first) + the
+    // step's 8 counter words (last-CTA counters, completion counters, gate; all zeroed by the step's first pooling kernel)
+    w.fin_bytes = align_up(sizeof(double) * 2 * (size_t)pool_finish_ctas(a->C) * (2 + CLR_MAX_K) + 64);
     char* base = static_cast<char*>(a->ws);
     size_t off = 0;
     w.pool = base + off; off += w.pool_bytes;
@@ -65,6 +67,11 @@ static int check_args(const clr_step_args* a) {
     return CLR_OK;
 }
 
+// counter words: [0] last-CTA counter (one-body finish / target half), [1] done_fin, [2] done_all of the [finish | consistency]
+// launch, [3] gate of the merged backward, [4] last-CTA counter of the source half, [5] source half: vectors published, [6] source half: CTAs finished
+static unsigned int* step_counters(const StepWs& w, int C) {
+    return reinterpret_cast<unsigned int*>(w.fin + 2 * (size_t)pool_finish_ctas(C) * (2 + CLR_MAX_K));
+}
 static const float* target_weights(const clr_step_args* a) { return a->use_retrify ? a->wt_retrify : a->wt; }
 static int target_fmt(const clr_step_args* a) { return a->use_retrify ? CLR_W_EXPLICIT : a->wt_fmt; }
 
@@ -201,7 +208,129 @@ static PeerXchg make_xchg(const clr_step_args* a, int which) {
     return x;
 }
 
+// Schedule 2 of the single-call fused step (clr3: retrify target + discriminative term, one-read kernel available):
+//
+//   pool(xs) -> finish/source  ||  mc_stats -> retrify_weights -> pool(xt) -> [finish/target + align | consistency]  ||  disc(xs)
+//            -> [disc finish | gradient of xt | gradient of xs (gated)]
+//
+// The source features do not depend on the MC statistics, and the discriminative pass depends on the SOURCE prototypes
+// only.  So the source map is pooled first, the source half of the finish (EMA'd source prototypes, the discriminative
+// term's vectors) runs as 33 CTAs of its own launch while the whole machine streams the MC logits (mc_stats skips its
+// griddepcontrol.wait), and the discriminative kernel no longer waits for the latency chain that follows the target
+// pooling -- that chain (target prototypes, alignment loss, all prototype gradients) now has the consistency AND the
+// discriminative pass to hide behind.  Sharded, both halves carry their part of the in-kernel exchange: every cross-GPU
+// rendezvous of the step then sits next to >= 20 us of independent streaming, so rank skew is absorbed instead of added.
+// Same arithmetic as schedule 1 (bit-identical results: tests/test_gpu_step.py); "sched_v1" = 1 selects schedule 1.
+static bool use_schedule2(const clr_step_args* a) {
+    const Tunables& t = tunables();
+    return a->use_retrify && a->use_disc && t.disc_impl != 1 && !t.finish_off && !t.hfuse_off && !t.flag_dep_off && !t.mc_fuse &&
+           !t.sched_v1;
+}
+
+static int step_fwd_v2(const clr_step_args* a, cudaStream_t st, DiscFinishParams* defer, int* deferred) {
+    const StepWs w = carve(a);
+    clr_stream_t stream = st;
+    const int HW = a->H * a->W, R = 2 * a->K, C = a->C, K = a->K;
+    const int nfin = pool_finish_ctas(C);
+    float* sums_s = a->packed1;
+    float* sums_t = a->packed1 + (size_t)R * (C + 1);
+    double* fin_s = w.fin;
+    double* fin_t = w.fin + (size_t)nfin * (2 + CLR_MAX_K);
+    unsigned int* counter = step_counters(w, C);
+    const int early = tunables().fin_early_off ? 0 : 1;
+    int rc;
+    // 1. source pooling (first kernel of the step: zeroes the counters)
+    PoolLayout lay_s{}, lay_t{};
+    const size_t pb_s = pool_partial_bytes(a->B_s, C, HW, R);
+    if (a->ev_pool_begin) cudaEventRecord(static_cast<cudaEvent_t>(a->ev_pool_begin), st);
+    rc = pool_fwd_impl(a->xs, a->ys, CLR_W_COMPLEMENT, a->B_s, sums_s, nullptr, nullptr, 0, 0, nullptr,
+                       C, HW, R, w.pool, pb_s, st, 0, 0, &lay_s, counter);
+    if (a->ev_pool_end) cudaEventRecord(static_cast<cudaEvent_t>(a->ev_pool_end), st);
+    if (rc != CLR_OK) return rc;
+    // 2. source half of the finish
+    PoolFinishParams pf{};
+    pf.K = K; pf.C = C; pf.d = (float)a->decay; pf.omd = (float)(1.0 - a->decay);
+    pf.w_intra = a->w_intra; pf.w_inter = a->w_inter;
+    pf.first[0] = a->first_s; pf.first[1] = a->first_t;
+    pf.stored[0] = a->stored_s; pf.stored[1] = a->stored_t; pf.P[0] = a->P_s; pf.P[1] = a->P_t;
+    pf.g[0] = a->g_s; pf.g[1] = a->g_t; pf.sums[0] = sums_s; pf.sums[1] = sums_t;
+    pf.losses = a->losses; pf.x = make_xchg(a, 1);
+    PoolFinishParams ps = pf;
+    ps.mode = 1;
+    ps.partial[0] = lay_s.partial[0]; ps.slots[0] = lay_s.slots[0];
+    ps.disc_vec = a->disc_vec; ps.disc_beta = a->disc_beta;
+    ps.loss_partial = fin_s; ps.counter = counter + 4;
+    ps.done_fin = counter + 5; ps.done_all = counter + 6; ps.early_signal = early;      // [5]: vectors out (early), [6]: CTA finished
+    rc = pool_finish_launch(ps, st);
+    if (rc != CLR_OK) return rc;
+    // 3. MC statistics (not waiting for 2) + retrify weights
+    rc = mc_stats_impl(a->preds, a->T, a->B_t, K, a->Hi, a->Wi, a->std_map, a->pred_mean, st, true);
+    if (rc != CLR_OK) return rc;
+    rc = clr_retrify_weights(a->oT_before, a->pred_mean, a->std_map, a->preds, a->T, a->B_t, K, a->H, a->W, a->Hi, a->Wi,
+                             a->pseudo_thr, a->std_thr, a->wt_retrify, a->masks, nullptr, nullptr, stream);
+    if (rc != CLR_OK) return rc;
+    // 4. target pooling
+    rc = pool_fwd_impl(a->xt, a->wt_retrify, CLR_W_EXPLICIT, a->B_t, sums_t, nullptr, nullptr, 0, 0, nullptr,
+                       C, HW, R, w.pool + pb_s, w.pool_bytes - pb_s, st, 0, 0, &lay_t, nullptr, nullptr, TR_POOL_T);
+    if (rc != CLR_OK) return rc;
+    // 5. [target half + alignment | consistency]
+    PoolFinishParams pt = pf;
+    pt.mode = 2;
+    pt.partial[1] = lay_t.partial[0]; pt.slots[1] = lay_t.slots[0];
+    pt.loss_partial = fin_t; pt.counter = counter;
+    pt.done_fin = nullptr; pt.done_all = counter + 2; pt.early_signal = 0;
+    // waits for the source half's CTAs to have FINISHED ([6], not just published their vectors): completion of this launch then
+    // implies completion of that one, and the discriminative kernel's exit check makes both visible to the backward launch
+    pt.wait_src = counter + 6; pt.wait_src_n = (unsigned int)nfin; pt.wait_err = a->losses + 7;
+    int n_cons = 0;
+    unsigned int producers = (unsigned int)nfin;
+    if (a->use_cons) {
+        rc = cons_fwd_partials(a->oT, a->oT_aug, a->masks, a->B_t, K, a->Hi, a->Wi, a->H, a->W,
+                               a->cons_threshold, w.cons, &n_cons, st, &pt);
+        if (rc != CLR_OK) return rc;
+        producers += (unsigned int)n_cons;
+    } else {
+        rc = pool_finish_launch(pt, st);
+        if (rc != CLR_OK) return rc;
+    }
+    // 6. discriminative pass: depends on the source half only (flag), checks the [5]-launch's completion before it exits
+    const float ema = a->first_s ? 1.0f : (float)a->decay;
+    const double* cons = a->use_cons ? w.cons : nullptr;
+    float* partial = reinterpret_cast<float*>(w.rows);
+    float* hinge = partial + (size_t)320 * K * (C + 1);   // layout of clr_disc_fused_ws_bytes: [320][K][C+1] | [320]
+    int n_hinge = 320;
+    DiscFlagDep dep{counter + 5, counter + 2, (unsigned int)nfin, producers, a->losses + 7, early ? fin_s : nullptr};
+    rc = disc_fused_impl(a->xs, a->ys, a->B_s, C, HW, K, a->disc_vec, a->disc_beta, a->margin,
+                         a->disc_coef, nullptr, partial, hinge, &n_hinge, st, &dep);
+    if (rc == CLR_OK) {
+        DiscFinishParams df{};
+        df.partial = partial; df.slots = n_hinge; df.packed2 = a->packed2; df.P_s = a->P_s; df.g_s = a->g_s;
+        df.xtab = a->xtab; df.losses = a->losses; df.K = K; df.C = C; df.npx = a->npx_global;
+        df.coef = (float)(2.0 / ((double)C * a->npx_global));
+        df.w_disc = a->w_disc; df.ema_factor = ema; df.gscale = a->grad_scale; df.w_intra = a->w_intra;
+        df.w_inter = a->w_inter; df.w_aug = a->w_aug; df.aug_weight = a->aug_weight; df.use_cons = a->use_cons;
+        df.ps = PackSrc{hinge, n_hinge, 1, cons, n_cons};
+        df.x = make_xchg(a, 2);
+        if (defer) { *defer = df; *deferred = 1; return CLR_OK; }
+        return disc_finish_launch(df, st);
+    }
+    if (rc != CLR_ERR_UNSUPPORTED) return rc;
+    // geometry the one-read kernel cannot take (ragged planes): the two-pass form (ordinary kernel boundaries from here on)
+    if (a->world > 1) return CLR_ERR_UNSUPPORTED;
+    n_hinge = 0;
+    rc = disc_fwd_impl(a->xs, a->ys, a->B_s, C, HW, K, a->disc_vec, a->disc_beta, a->margin,
+                       a->disc_coef, nullptr, w.hinge, clr_disc_partials_cap(), &n_hinge, st);
+    if (rc != CLR_OK) return rc;
+    rc = pool_fwd_impl(a->xs, a->disc_coef, CLR_W_EXPLICIT, a->B_s, a->packed2, nullptr, nullptr, 0, 0, nullptr,
+                       C, HW, K, w.rows, w.rows_bytes, st);
+    if (rc != CLR_OK) return rc;
+    return disc_finalize_impl(a->packed2, a->P_s, K, C, a->npx_global, a->w_disc, ema, a->grad_scale,
+                              a->g_s, a->xtab, a->w_intra, a->w_inter, a->w_aug, a->aug_weight,
+                              a->use_disc, a->use_cons, a->losses, w.hinge, n_hinge, 1 + K, cons, n_cons, st);
+}
+
 static int step_fwd_core(const clr_step_args* a, cudaStream_t st, DiscFinishParams* defer, int* deferred) {
+    if (use_schedule2(a)) return step_fwd_v2(a, st, defer, deferred);
     const StepWs w = carve(a);
     clr_stream_t stream = st;
     const int HW = a->H * a->W, R = 2 * a->K, C = a->C, K = a->K;
@@ -223,7 +352,7 @@ static int step_fwd_core(const clr_step_args* a, cudaStream_t st, DiscFinishPara
     }
     float* sums_s = a->packed1;
     float* sums_t = a->packed1 + (size_t)R * (C + 1);
-    unsigned int* counter = reinterpret_cast<unsigned int*>(w.fin + (size_t)pool_finish_ctas(C) * (2 + CLR_MAX_K));
+    unsigned int* counter = step_counters(w, C);
     PoolLayout lay{};
     if (a->ev_pool_begin) cudaEventRecord(static_cast<cudaEvent_t>(a->ev_pool_begin), st);
     rc = pool_fwd_impl(a->xt, target_weights(a), target_fmt(a), a->B_t, sums_t,
@@ -363,7 +492,7 @@ int clr_step_run(const clr_step_args* a, clr_stream_t stream) {
         // ONE launch: [disc finish | gradient of xt | gradient of xs]; the source CTAs are dispatched after the ~1000 target
         // CTAs and wait on the 4th counter word (zeroed by this step's pooling kernel, bumped by every finish CTA)
         const clr::StepWs w = clr::carve(a);
-        unsigned int* counter = reinterpret_cast<unsigned int*>(w.fin + (size_t)clr::pool_finish_ctas(a->C) * (2 + CLR_MAX_K));
+        unsigned int* counter = clr::step_counters(w, a->C);
         rc = clr::pool_bwd_merged(&dd[1], &dd[0], a->C, a->H * a->W, a->K, &df, counter + 3, a->losses + 7, s0);
     } else {
         rc = clr::pool_bwd_one(&dd[1], a->C, a->H * a->W, a->K, &df, false, s0);
@@ -397,6 +526,11 @@ int clr_step_bwd(const clr_step_args* a, clr_stream_t stream) {
                           a->aug_weight, stats + 1, a->gup, a->grad_scale * a->w_aug, a->g_oT_aug, stream);
     }
     return rc;
+}
+
+int clr_step_schedule(const clr_step_args* a) {
+    if (!a) return 0;
+    return clr::use_schedule2(a) ? 2 : 1;
 }
 
 size_t clr_step_xchg_bytes(int world, int K, int C) {
