@@ -33,6 +33,7 @@ def main():
     ap.add_argument("--workload", default="clr3", choices=["clr3", "align"])
     ap.add_argument("--tunable", action="append", default=[])
     ap.add_argument("--json", default=None)
+    ap.add_argument("--all-ranks", action="store_true", help="under torchrun: every rank writes its own <json>.rank<r>")
     ap.add_argument("--pipelined", type=int, default=0,
                     help="also enqueue N steps back to back under ONE trace window: (last exit - first start) / N is the steady-state step time on the device")
     a = ap.parse_args()
@@ -91,6 +92,10 @@ def main():
             rows.append((slot_names[i], t_first, t_ready, t_last, ncta))
         t0 = min(r[1] for r in rows)
         rows.sort(key=lambda r: r[2])
+        total = (max(r[3] for r in rows) - t0) / 1e3
+        out.append({"step": s, "span_us": total,
+                    "kernels": [{"name": r[0], "start_us": (r[1] - t0) / 1e3, "ready_us": (r[2] - t0) / 1e3,
+                                 "exit_us": (r[3] - t0) / 1e3, "ctas": int(r[4])} for r in rows]})
         if rank != 0:
             continue
         print("step %d (%s, %d GPU%s): kernel, first CTA start, predecessor done, last CTA exit, busy, CTAs [us]"
@@ -101,11 +106,7 @@ def main():
             print("  %-18s start %8.2f  ready %8.2f  exit %8.2f  busy %7.2f  ctas %5d%s"
                   % (name, (tf - t0) / 1e3, (tr - t0) / 1e3, (tl - t0) / 1e3, (tl - tr) / 1e3, ncta, gap))
             prev_end = tl
-        total = (max(r[3] for r in rows) - t0) / 1e3
         print("  step span %.2f us" % total)
-        out.append({"step": s, "span_us": total,
-                    "kernels": [{"name": r[0], "start_us": (r[1] - t0) / 1e3, "ready_us": (r[2] - t0) / 1e3,
-                                 "exit_us": (r[3] - t0) / 1e3, "ctas": int(r[4])} for r in rows]})
     if a.pipelined > 0:
         for i in range(a.pipelined):
             plans[i % NSET].run()
@@ -120,9 +121,10 @@ def main():
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
-    if a.json and rank == 0:
-        with open(a.json, "w") as fh:
-            json.dump({"config": vars(a), "steps": out}, fh, indent=1)
+    if a.json and (rank == 0 or a.all_ranks):
+        path = a.json if world == 1 or not a.all_ranks else "%s.rank%d" % (a.json, rank)
+        with open(path, "w") as fh:
+            json.dump({"config": vars(a), "rank": rank, "world": world, "steps": out}, fh, indent=1)
 
 
 if __name__ == "__main__":
