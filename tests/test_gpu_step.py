@@ -830,8 +830,8 @@ def test_merged_backward_launch_equals_two_launches(K, C, H):
 
 @pytest.mark.parametrize("K,C,H,B", [(2, 256, 64, 2), (2, 305, 32, 3), (3, 37, 16, 2), (8, 24, 16, 2)])
 def test_schedule2_equals_schedule1_bit_for_bit(K, C, H, B):
-    """The fused step's default launch schedule for clr3 (source pooled first, finish halves hidden behind the MC statistics
-    and the discriminative pass; csrc/step.cu) against schedule 1 ("sched_v1" = 1: both maps pooled in one launch): the
+    """The fused step's second launch schedule for clr3 (source pooled first, finish halves hidden behind the MC statistics
+    and the discriminative pass; csrc/step.cu) against schedule 1 ("sched" = 1: both maps pooled in one launch; 2 is the default of the sharded step): the
     arithmetic and every summation order are the same, so losses, prototypes, EMA state and both gradient maps must be
     bit-identical over three steps, through the prebound plan and through autograd."""
     from uda_clr_b200 import _lib
@@ -841,7 +841,7 @@ def test_schedule2_equals_schedule1_bit_for_bit(K, C, H, B):
     res = []
     for v1 in (0, 1):
         try:
-            _lib.check(lib.clr_set_tunable(b"sched_v1", v1), "sched_v1")
+            _lib.check(lib.clr_set_tunable(b"sched", 1 if v1 else 2), "sched")
             step = clr.CLRStep(K=K, retrify=True, use_disc=True, use_cons=True, backprop_aug=True)
             plan = step.plan(t["xs"], t["ys"], t["xt"], oT_before=t["oT_before"], preds=t["preds"], T=8, oT=t["oT"],
                              oT_aug=t["oT_aug"], epoch=1.0)
@@ -861,7 +861,7 @@ def test_schedule2_equals_schedule1_bit_for_bit(K, C, H, B):
             row += [out.total.detach().clone(), xs.grad.clone(), xt.grad.clone()]
             res.append(row)
         finally:
-            lib.clr_set_tunable(b"sched_v1", 0)
+            lib.clr_set_tunable(b"sched", 0)
     assert float(res[0][0][7]) == 0.0
     for x, y in zip(res[0], res[1]):
         assert torch.equal(x, y)

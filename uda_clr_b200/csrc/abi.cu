@@ -56,7 +56,7 @@ int clr_set_tunable(const char* name, int value) {
     else if (!strcmp(name, "fin_early_off")) t.fin_early_off = value;
     else if (!strcmp(name, "mc_split")) t.mc_split = value;
     else if (!strcmp(name, "disc_reverse")) t.disc_reverse = value;
-    else if (!strcmp(name, "sched_v1")) t.sched_v1 = value;
+    else if (!strcmp(name, "sched")) t.sched = value;
 
     else return CLR_ERR_BAD_ARG;
     return CLR_OK;

@@ -48,7 +48,7 @@ struct Tunables {
                        //     instead of the finish CTAs' completion counter
     int disc_reverse;  // 1 = the one-read discriminative kernel walks its tiles in descending address order (round 2: the re-read of
                        //     xs then misses DRAM for 102 instead of 110 of 135 MB, the kernel is not faster -- it is not DRAM-bound)
-    int sched_v1;      // 1 = the fused step keeps schedule 1 (both maps pooled in one launch after the MC statistics; step.cu)
+    int sched;         // fused step launch schedule (step.cu): 0 = auto (2 when sharded over several GPUs, else 1), 1, 2
     int xchg_pull;     // in-kernel exchange: 1 = readers poll the peers' buffers (no remote stores), 0 = senders push
     void* trace_buf;   // device TraceRec[kTraceSlots] or NULL (clr_trace_set): device-side timeline of the kernels
 };

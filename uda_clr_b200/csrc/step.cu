@@ -220,11 +220,15 @@ static PeerXchg make_xchg(const clr_step_args* a, int which) {
 // pooling -- that chain (target prototypes, alignment loss, all prototype gradients) now has the consistency AND the
 // discriminative pass to hide behind.  Sharded, both halves carry their part of the in-kernel exchange: every cross-GPU
 // rendezvous of the step then sits next to >= 20 us of independent streaming, so rank skew is absorbed instead of added.
-// Same arithmetic as schedule 1 (bit-identical results: tests/test_gpu_step.py); "sched_v1" = 1 selects schedule 1.
+// Same arithmetic as schedule 1 (bit-identical results: tests/test_gpu_step.py).  Measured (profiles/r02_schedule2.md): on ONE
+// GPU it is 9 us SLOWER than schedule 1 (0.1855 vs 0.1762 ms) -- two pooling launches cost 51 instead of 45 us (each pays its
+// own ramp and one-item tail), one more kernel boundary, and the discriminative CTAs still cannot become resident before the
+// consistency CTAs leave -- so it is selected only for the sharded step ("sched" = 0: auto; 1 / 2 force a schedule).
 static bool use_schedule2(const clr_step_args* a) {
     const Tunables& t = tunables();
-    return a->use_retrify && a->use_disc && t.disc_impl != 1 && !t.finish_off && !t.hfuse_off && !t.flag_dep_off && !t.mc_fuse &&
-           !t.sched_v1;
+    const bool possible = a->use_retrify && a->use_disc && t.disc_impl != 1 && !t.finish_off && !t.hfuse_off && !t.flag_dep_off && !t.mc_fuse;
+    if (!possible || t.sched == 1) return false;
+    return t.sched == 2 || a->world > 1;
 }
 
 static int step_fwd_v2(const clr_step_args* a, cudaStream_t st, DiscFinishParams* defer, int* deferred) {
