@@ -73,7 +73,10 @@ def main():
                             T=T, oT=full["oT"], oT_aug=full["oT_aug"], epoch=0.0)
             errs = dict(total=abs(float(out.total) - float(res["total"])) / abs(float(res["total"])),
                         gW=relerr(conv.module.weight.grad, ref_conv.weight.grad),
-                        gb=relerr(conv.module.bias.grad, ref_conv.bias.grad))
+                        # (on the first step the loss is invariant to a common shift of all features -- the bias gradient is
+                        #  pure rounding noise around 0 -- so its error is measured on the scale of the weight gradient)
+                        gb=float((conv.module.bias.grad - ref_conv.bias.grad).abs().max()
+                                 / torch.maximum(ref_conv.bias.grad.abs().max(), ref_conv.weight.grad.abs().max())))
             bad = {k: v for k, v in errs.items() if not v < 1e-4}
             if flag != 0.0:
                 bad["timeout_flag"] = flag

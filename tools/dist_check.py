@@ -28,7 +28,20 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
-    K, C, H, up, T = 2, 64, 64, 4, 8
+    ok = True
+    for K, C, H, up, T in ((2, 64, 64, 4, 8), (8, 24, 32, 4, 4)):      # K = 8: 2R*8 + 2R = 288 exchange items > 256 threads
+        ok = run_case(rank, world, dev, K, C, H, up, T) and ok
+    flag = torch.tensor([0 if ok else 1], device=dev)
+    dist.all_reduce(flag)
+    clr.dist.close_peer()
+    dist.destroy_process_group()
+    if int(flag.item()) != 0:
+        sys.exit(1)
+    if rank == 0:
+        print("DIST_CHECK_OK world=%d" % world)
+
+
+def run_case(rank, world, dev, K, C, H, up, T):
     Bg = 4 * world
     b = synth.make_batch(B=Bg, C=C, H=H, W=H, K=K, T=T, up=up, seed=4321)
     full = {k: getattr(b, k).to(dev) for k in ("xs", "ys", "xt", "oT_before", "oT", "oT_aug")}
@@ -38,7 +51,13 @@ def main():
     mine = {k: v[lo:hi].contiguous() for k, v in full.items()}
     preds_mine = preds[:, lo:hi].reshape(T * (hi - lo), K, H * up, H * up).contiguous()
     ok = True
-    for variant, mode in (("align", "nccl"), ("clr3", "nccl"), ("align", "peer"), ("clr3", "peer"), ("clr3", "peer_plan")):
+    from uda_clr_b200 import _lib
+    lib = _lib.load()
+    # peer_plan: the sharded step's default launch schedule (2) and disc-finish split; peer_plan_s1: schedule 1, merged backward
+    for variant, mode in (("align", "nccl"), ("clr3", "nccl"), ("align", "peer"), ("clr3", "peer"), ("clr3", "peer_plan"),
+                          ("clr3", "peer_plan_s1")):
+        lib.clr_set_tunable(b"sched", 1 if mode == "peer_plan_s1" else 0)
+        lib.clr_set_tunable(b"dfin_split", 2 if mode == "peer_plan_s1" else 0)
         use3 = variant == "clr3"
         # single-GPU reference on the whole batch (every rank computes it redundantly)
         ref = clr.CLRStep(K=K, retrify=use3, use_disc=use3, use_cons=use3, backprop_aug=use3)
@@ -58,7 +77,7 @@ def main():
             xs_s, xt_s, a_s = (mine[k].clone().requires_grad_(True) for k in ("xs", "xt", "oT_aug"))
             kw_s = dict(oT_before=mine["oT_before"], preds=preds_mine, T=T, oT=mine["oT"], oT_aug=a_s) if use3 \
                 else dict(wt=torch.sigmoid(mine["oT_before"]))
-            if mode == "peer_plan":
+            if mode.startswith("peer_plan"):
                 plan = sh.plan(xs_s.detach(), mine["ys"], xt_s.detach(), **{k: (v.detach() if torch.is_tensor(v) else v) for k, v in kw_s.items()})
                 plan.run()
                 out_s = plan.outputs()
@@ -83,16 +102,12 @@ def main():
                 errs["disc"] = abs(float(out_s.disc) - float(out_f.disc)) / abs(float(out_f.disc))
                 errs["aug"] = abs(float(out_s.aug) - float(out_f.aug)) / abs(float(out_f.aug))
             bad = {k: v for k, v in errs.items() if not (v < (1e-5 if k in ("Ps", "Pt") else 1e-4))}
-            print("rank %d %s/%s step %d: %s %s" % (rank, variant, mode, it, {k: "%.1e" % v for k, v in errs.items()},
+            print("rank %d K=%d %s/%s step %d: %s %s" % (rank, K, variant, mode, it, {k: "%.1e" % v for k, v in errs.items()},
                                                    "FAIL " + str(bad) if bad else "ok"), flush=True)
             ok = ok and not bad
-    flag = torch.tensor([0 if ok else 1], device=dev)
-    dist.all_reduce(flag)
-    dist.destroy_process_group()
-    if int(flag.item()) != 0:
-        sys.exit(1)
-    if rank == 0:
-        print("DIST_CHECK_OK world=%d" % world)
+    lib.clr_set_tunable(b"sched", 0)
+    lib.clr_set_tunable(b"dfin_split", 0)
+    return ok
 
 
 if __name__ == "__main__":

@@ -348,6 +348,7 @@ struct DiscFinishParams {
     int use_cons;
     PackSrc ps;
     PeerXchg x;       // world > 1: sum the active-set sums and the loss numerators over the ranks
+    unsigned int* gate_signal;   // stand-alone launch in front of a gated backward launch: bumped once per CTA when it is done
 };
 static inline int disc_finish_ctas(int C) { return (C + 7) / 8 + 1; }
 

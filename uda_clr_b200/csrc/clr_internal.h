@@ -56,6 +56,8 @@ int disc_finish_launch(const DiscFinishParams& p, cudaStream_t st);
 int pool_bwd_one(const clr_bwd_dom* dom, int C, int HW, int K, const DiscFinishParams* f, bool source, cudaStream_t st);
 int pool_bwd_merged(const clr_bwd_dom* first, const clr_bwd_dom* gated, int C, int HW, int K, const DiscFinishParams* f,
                     unsigned int* gate, float* gate_err, cudaStream_t st);
+int pool_bwd_gated(const clr_bwd_dom* first, const clr_bwd_dom* gated, int C, int HW, int K, unsigned int* gate, unsigned int gate_n,
+                   float* gate_err, cudaStream_t st);
 
 // clr_mc_stats with the option to skip griddepcontrol.wait (fused step, schedule 2: see the kernel)
 int mc_stats_impl(const float* preds, int T, int B, int K, int Hi, int Wi, float* std_map, float* pred_mean, cudaStream_t st,

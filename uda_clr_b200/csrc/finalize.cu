@@ -181,8 +181,11 @@ __global__ void __launch_bounds__(kThreads) pool_finish_kernel(const PoolFinishP
     trace_exit(tr);
 }
 __global__ void __launch_bounds__(kThreads) disc_finish_kernel(const DiscFinishParams p) {
-    kernel_begin(TR_DISC_FIN);
+    // gate_signal: the backward launch behind this one skips its griddepcontrol.wait (its source CTAs wait on the gate
+    // instead), so it must not be launched before everything older has completed: trigger AFTER the wait
+    if (p.gate_signal) kernel_begin_late_trigger(TR_DISC_FIN); else kernel_begin(TR_DISC_FIN);
     disc_finish_body(p, blockIdx.x, gridDim.x);
+    if (p.gate_signal) cta_signal(p.gate_signal, nullptr);
     trace_exit(TR_DISC_FIN);
 }
 int pool_finish_launch(const PoolFinishParams& p, cudaStream_t st) {

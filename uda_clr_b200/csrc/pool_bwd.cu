@@ -43,6 +43,10 @@ struct BwdParams {
     // finish CTAs' output (g of that domain, xtab) and wait until `gate` (bumped once by every finish CTA, zeroed by the
     // step's pooling kernel) reaches gate_n; they then read those vectors through coherent loads only.
     unsigned int* gate; unsigned int gate_n; int gate_dom; float* gate_err;
+    // the finish runs as its OWN launch in front of this one (sharded step: a grid that touched peer memory pays a ~3.5 us
+    // longer end-of-grid flush -- kept out of the big backward grid, whose completion the next step waits for): this kernel
+    // then skips griddepcontrol.wait; the finish triggered it only after its own wait, the gated CTAs wait on the gate
+    int nowait;
 };
 
 constexpr int kBwdSpan = 32;   // channels per CTA
@@ -149,9 +153,13 @@ constexpr int bwd_min_blocks(int QT) { return QT <= 4 ? 4 : (QT <= 8 ? 3 : 2); }
 
 template <int QT, int VEC>
 __global__ void __launch_bounds__(kThreads, bwd_min_blocks(QT)) pool_bwd_kernel(const BwdParams p) {
-    kernel_begin(p.trace_id);
+    const int tr = (p.ndom > 1 && p.gate) ? ((int)blockIdx.x >= p.dom[0].ctas ? TR_BWD_S : TR_BWD_T) : p.trace_id;
+    trace_enter(tr);
+    pdl_trigger();
+    if (!p.nowait) pdl_wait();
+    trace_ready(tr);
     pool_bwd_body<QT, VEC>(p, blockIdx.x);
-    trace_exit(p.trace_id);
+    trace_exit(tr);
 }
 
 // Horizontal fusion for the fused step: CTAs [0, n_fin) run the discriminative finish (partial reduce + prototype
@@ -188,7 +196,8 @@ static int launch_bwd(const BwdParams& p, bool vec4, int ctas, cudaStream_t st, 
 }
 
 int pool_bwd_impl(const BwdDom* doms, int ndom, int C, int HW, int K, cudaStream_t st, const DiscFinishParams* fin = nullptr,
-                  int trace_id = TR_BWD_BOTH, unsigned int* gate = nullptr, int gate_dom = 0, float* gate_err = nullptr) {
+                  int trace_id = TR_BWD_BOTH, unsigned int* gate = nullptr, int gate_dom = 0, float* gate_err = nullptr,
+                  unsigned int gate_n_ext = 0) {
     CLR_CHECK_ARG(ndom >= 1 && ndom <= 2 && C > 0 && HW > 0 && K >= 1 && K <= CLR_MAX_K);
     bool vec4 = (HW % 4 == 0);
     int Qmax = 0;
@@ -207,6 +216,7 @@ int pool_bwd_impl(const BwdDom* doms, int ndom, int C, int HW, int K, cudaStream
     p.trace_id = trace_id;
     p.ndom = ndom; p.C = C; p.HW = HW; p.K = K;
     if (gate && fin) { p.gate = gate; p.gate_n = (unsigned int)disc_finish_ctas(fin->C); p.gate_dom = gate_dom; p.gate_err = gate_err; }
+    else if (gate && gate_n_ext) { p.gate = gate; p.gate_n = gate_n_ext; p.gate_dom = gate_dom; p.gate_err = gate_err; p.nowait = 1; }
     const int pxb = kThreads * (vec4 ? 4 : 1);
     p.nPx = (HW + pxb - 1) / pxb;
     p.nSpan = (C + kBwdSpan - 1) / kBwdSpan;
@@ -249,6 +259,19 @@ int pool_bwd_merged(const clr_bwd_dom* first, const clr_bwd_dom* gated, int C, i
         d[i] = BwdDom{src[i]->w, src[i]->g, src[i]->sums, src[i]->xcoef, src[i]->xtab, src[i]->grad, src[i]->scale_dev,
                       src[i]->scale, src[i]->fmt, src[i]->B, src[i]->Kx, 0, 2 * K, 0, 0.f};
     return pool_bwd_impl(d, 2, C, HW, K, st, f, TR_BWD_BOTH, gate, 1, gate_err);
+}
+
+// The same two gradient maps behind a disc finish that was launched on its own (gate_signal = gate): [gradient of `first` |
+// gradient of `gated`], no griddepcontrol.wait, the gated CTAs wait for `gate_n` finish CTAs.
+int pool_bwd_gated(const clr_bwd_dom* first, const clr_bwd_dom* gated, int C, int HW, int K, unsigned int* gate, unsigned int gate_n,
+                   float* gate_err, cudaStream_t st) {
+    if (!first || !gated || !gate || !gate_n) return CLR_ERR_BAD_ARG;
+    BwdDom d[2];
+    const clr_bwd_dom* src[2] = {first, gated};
+    for (int i = 0; i < 2; ++i)
+        d[i] = BwdDom{src[i]->w, src[i]->g, src[i]->sums, src[i]->xcoef, src[i]->xtab, src[i]->grad, src[i]->scale_dev,
+                      src[i]->scale, src[i]->fmt, src[i]->B, src[i]->Kx, 0, 2 * K, 0, 0.f};
+    return pool_bwd_impl(d, 2, C, HW, K, st, nullptr, TR_BWD_BOTH, gate, 1, gate_err, gate_n);
 }
 
 }  // namespace clr

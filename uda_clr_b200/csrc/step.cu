@@ -492,7 +492,18 @@ int clr_step_run(const clr_step_args* a, clr_stream_t stream) {
     clr::bwd_doms(a, dd);
     cudaStream_t s0 = static_cast<cudaStream_t>(stream);
     if (a->ev_bwd_begin) cudaEventRecord(static_cast<cudaEvent_t>(a->ev_bwd_begin), s0);
-    if (!clr::tunables().bwd_merge_off) {
+    const int split = clr::tunables().dfin_split;      // 0 = auto: own launch for the disc finish when it exchanges over peer memory
+    if (!clr::tunables().bwd_merge_off && (split == 1 || (split == 0 && a->world > 1))) {
+        // [disc finish] as its own small launch (late trigger, bumps the gate), then [gradient of xt | gated gradient of xs]
+        // WITHOUT griddepcontrol.wait: the finish grid's slow end-of-grid flush (it wrote peer memory) overlaps the gradient
+        // write instead of extending the grid the next step has to wait for
+        const clr::StepWs w = clr::carve(a);
+        unsigned int* counter = clr::step_counters(w, a->C);
+        df.gate_signal = counter + 3;
+        rc = clr::disc_finish_launch(df, s0);
+        if (rc == CLR_OK) rc = clr::pool_bwd_gated(&dd[1], &dd[0], a->C, a->H * a->W, a->K, counter + 3,
+                                                   (unsigned int)clr::disc_finish_ctas(a->C), a->losses + 7, s0);
+    } else if (!clr::tunables().bwd_merge_off) {
         // ONE launch: [disc finish | gradient of xt | gradient of xs]; the source CTAs are dispatched after the ~1000 target
         // CTAs and wait on the 4th counter word (zeroed by this step's pooling kernel, bumped by every finish CTA)
         const clr::StepWs w = clr::carve(a);
