@@ -87,8 +87,8 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tmap, 
 //              thread; completion through an mbarrier per stage.  The LDGSTS form is bound by the SM's load/store
 //              pipe (measured: ~2300 cycles per tile spent behind the next tile's 2048 LDGSTS, none waiting for
 //              data), the tensor form leaves that pipe to the two compute phases.
-template <int K, int TP, int STAGES, int NT, bool TMA, int CPT>
-__global__ void __launch_bounds__(NT, (TP == 32 && STAGES <= 4) ? 2 : 1) disc_fused_kernel(const DiscParams p, const __grid_constant__ CUtensorMap tmap) {
+template <int K, int TP, int STAGES, int NT, bool TMA, int CPT, int MB = ((TP == 32 && STAGES <= 4) ? 2 : 1)>
+__global__ void __launch_bounds__(NT, MB) disc_fused_kernel(const DiscParams p, const __grid_constant__ CUtensorMap tmap) {
     trace_enter(TR_DISC);
     pdl_trigger();
     if (!p.wait_fin) pdl_wait();      // else: the feature tiles are inputs -- start fetching, wait for the flag below
@@ -472,10 +472,10 @@ static bool make_feature_tmap(const float* xs, int B, int C, int HW, int rows_bo
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int K, int STAGES, int NT, int CPT>
+template <int K, int STAGES, int NT, int CPT, int MB = 2>
 static int launch_disc_tma_c(DiscParams& p, const CUtensorMap& tmap, int* nparts, cudaStream_t st) {
     const size_t smem = disc_smem_tma<K, NT>(p.C, p.rows_box * p.nbox, STAGES);
-    auto kern = disc_fused_kernel<K, 32, STAGES, NT, true, CPT>;
+    auto kern = disc_fused_kernel<K, 32, STAGES, NT, true, CPT, MB>;
     int occ = 0;
     { const int rc = kernel_occupancy(reinterpret_cast<const void*>(kern), NT, smem, &occ); if (rc != CLR_OK) return rc; }
     if (occ < 1) return CLR_ERR_UNSUPPORTED;
@@ -507,6 +507,10 @@ static int launch_disc_tma(DiscParams& p, int* nparts, cudaStream_t st) {
             if (disc_smem_tma<K, 512>(p.C, rt, 3) <= per_cta) return launch_disc_tma_s<K, 3, 512>(p, tmap, nparts, st);
             if (disc_smem_tma<K, 512>(p.C, rt, 2) <= per_cta) return launch_disc_tma_s<K, 2, 512>(p, tmap, nparts, st);
         }
+        // "disc_ctas" = 3: THREE resident CTAs per SM on a 2-stage ring (<= 85 registers), C <= 320: the kernel is bound by
+        // its per-tile latency chain, not by DRAM (profiles/r02_l2_harvest.md) -- a third CTA to interleave
+        if (tunables().disc_ctas == 3 && p.C <= kDiscSmallCPT * kDiscCols && disc_smem_tma<K, 256>(p.C, rt, 2) <= (budget - 3072) / 3)
+            return launch_disc_tma_c<K, 2, 256, kDiscSmallCPT, 3>(p, tmap, nparts, st);
     }
     if (disc_smem_tma<K, 256>(p.C, rt, 3) <= per_cta) return launch_disc_tma_s<K, 3, 256>(p, tmap, nparts, st);
     if (disc_smem_tma<K, 256>(p.C, rt, 2) <= per_cta) return launch_disc_tma_s<K, 2, 256>(p, tmap, nparts, st);
