@@ -53,11 +53,12 @@ def run_case(rank, world, dev, K, C, H, up, T):
     ok = True
     from uda_clr_b200 import _lib
     lib = _lib.load()
-    # peer_plan: the default launch schedule (1, merged backward); peer_plan_s2: schedule 2 with the split disc finish (knobs)
+    # peer_plan: the default ("sched" = 0: schedule 1 below 8 ranks, schedule 2 + split disc finish from 8 on); peer_plan_s1 /
+    # peer_plan_s2 force one schedule so that both are checked at every world size
     for variant, mode in (("align", "nccl"), ("clr3", "nccl"), ("align", "peer"), ("clr3", "peer"), ("clr3", "peer_plan"),
-                          ("clr3", "peer_plan_s2")):
-        lib.clr_set_tunable(b"sched", 2 if mode == "peer_plan_s2" else 0)
-        lib.clr_set_tunable(b"dfin_split", 1 if mode == "peer_plan_s2" else 0)
+                          ("clr3", "peer_plan_s1"), ("clr3", "peer_plan_s2")):
+        lib.clr_set_tunable(b"sched", {"peer_plan_s1": 1, "peer_plan_s2": 2}.get(mode, 0))
+        lib.clr_set_tunable(b"dfin_split", {"peer_plan_s1": 2, "peer_plan_s2": 1}.get(mode, 0))
         use3 = variant == "clr3"
         # single-GPU reference on the whole batch (every rank computes it redundantly)
         ref = clr.CLRStep(K=K, retrify=use3, use_disc=use3, use_cons=use3, backprop_aug=use3)

@@ -223,12 +223,13 @@ static PeerXchg make_xchg(const clr_step_args* a, int which) {
 // Same arithmetic as schedule 1 (bit-identical results: tests/test_gpu_step.py).  Measured (profiles/r02_schedule2.md): on ONE
 // GPU it is 9 us SLOWER than schedule 1 (0.1855 vs 0.1762 ms) -- two pooling launches cost 51 instead of 45 us (each pays its
 // own ramp and one-item tail), one more kernel boundary, and the discriminative CTAs still cannot become resident before the
-// consistency CTAs leave; sharded it loses as well (2 GPUs 0.1854 vs 0.1837 ms, 8 GPUs 0.1928 vs 0.1909 ms) -- so schedule 1
-// stays the default everywhere and this one is a knob ("sched" = 2) with its evidence on file.
+// consistency CTAs leave.  Sharded, its cost is almost flat in the world size (+3.5 us at 8 GPUs against +14.8 us for schedule 1):
+// 2 GPUs 0.1854 vs 0.1837 ms, 4 GPUs 0.1875 vs 0.1867 ms, 8 GPUs 0.1888 vs 0.1907 ms (two repetitions each, interleaved).  So
+// "sched" = 0 (auto) picks schedule 2 -- with the split disc finish -- from 8 ranks on, schedule 1 below; 1 / 2 force one.
 static bool use_schedule2(const clr_step_args* a) {
     const Tunables& t = tunables();
     const bool possible = a->use_retrify && a->use_disc && t.disc_impl != 1 && !t.finish_off && !t.hfuse_off && !t.flag_dep_off && !t.mc_fuse;
-    return possible && t.sched == 2;
+    return possible && (t.sched == 2 || (t.sched == 0 && a->world >= 8));
 }
 
 static int step_fwd_v2(const clr_step_args* a, cudaStream_t st, DiscFinishParams* defer, int* deferred) {
@@ -492,8 +493,10 @@ int clr_step_run(const clr_step_args* a, clr_stream_t stream) {
     clr::bwd_doms(a, dd);
     cudaStream_t s0 = static_cast<cudaStream_t>(stream);
     if (a->ev_bwd_begin) cudaEventRecord(static_cast<cudaEvent_t>(a->ev_bwd_begin), s0);
-    // "dfin_split" = 1 (measured slower with schedule 1: 8 GPUs 0.1950 vs 0.1909 ms; kept as a knob): own launch for the disc finish
-    if (!clr::tunables().bwd_merge_off && clr::tunables().dfin_split == 1) {
+    // own launch for the disc finish: measured slower with schedule 1 (8 GPUs 0.1916 vs 0.1910 ms), faster with schedule 2
+    // (2 GPUs 0.1854 vs 0.1931 ms) -- "dfin_split" = 0 (auto) follows the schedule, 1 = always, 2 = never
+    const int split = clr::tunables().dfin_split;
+    if (!clr::tunables().bwd_merge_off && (split == 1 || (split == 0 && clr::use_schedule2(a)))) {
         // [disc finish] as its own small launch (late trigger, bumps the gate), then [gradient of xt | gated gradient of xs]
         // WITHOUT griddepcontrol.wait: the finish grid's slow end-of-grid flush (it wrote peer memory) overlaps the gradient
         // write instead of extending the grid the next step has to wait for

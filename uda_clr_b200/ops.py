@@ -23,6 +23,25 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+class _NoGuard:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def _on(device):
+    """Device guard for a launch: ``torch.cuda.device(device)`` only when ``device`` is not already current (the context
+    manager costs ~10 us of host time per op, and the zero-line drop-in is host-bound)."""
+    if device.index is None or device.index == torch.cuda.current_device():
+        return _NO_GUARD
+    return torch.cuda.device(device)
+
+
 def _require_cuda_f32(t: torch.Tensor, name: str, ndim: int = 4) -> torch.Tensor:
     if not isinstance(t, torch.Tensor):
         raise TypeError("%s must be a torch.Tensor" % name)
@@ -61,7 +80,7 @@ def pool_sums(feat: torch.Tensor, w: torch.Tensor, fmt: int, K: int, with_mu: bo
     lib = _lib.load()
     B, C, H, W = feat.shape
     HW = H * W
-    with torch.cuda.device(feat.device):
+    with _on(feat.device):
         ws_bytes = lib.clr_pool_ws_bytes(B, C, HW, K)
         ws = _workspace(ws_bytes, feat.device, "pool")
         sums = torch.empty(2 * K, C + 1, dtype=torch.float32, device=feat.device)
@@ -80,7 +99,7 @@ def protos_from_sums(sums: torch.Tensor) -> torch.Tensor:
     lib = _lib.load()
     R, C1 = sums.shape
     mu = torch.empty(R, C1 - 1, dtype=torch.float32, device=sums.device)
-    with torch.cuda.device(sums.device):
+    with _on(sums.device):
         check(lib.clr_proto_finalize(ptr(sums), R, C1 - 1, ptr(mu), _stream()), "clr_proto_finalize")
     return mu
 
@@ -92,7 +111,7 @@ def pool_backward_feat(w: torch.Tensor, fmt: int, K: int, feat_shape, g: torch.T
     B, C, H, W = feat_shape
     grad = torch.empty(feat_shape, dtype=torch.float32, device=w.device)
     Kx = 0 if xcoef is None else xcoef.shape[1]
-    with torch.cuda.device(w.device):
+    with _on(w.device):
         check(lib.clr_pool_bwd(ptr(w), fmt, B, C, H * W, K, ptr(g), ptr(sums), float(scale),
                                ptr(xcoef), ptr(xtab), Kx, ptr(grad), _stream()), "clr_pool_bwd")
     return grad
@@ -106,7 +125,7 @@ def pool_backward_weights(feat: torch.Tensor, fmt: int, K: int, g: torch.Tensor,
     ws_bytes = lib.clr_pool_bwd_w_ws_bytes(C, K, fmt)
     ws = _workspace(ws_bytes, feat.device, "bwd_w")
     out = torch.empty(B, Q, H, W, dtype=torch.float32, device=feat.device)
-    with torch.cuda.device(feat.device):
+    with _on(feat.device):
         check(lib.clr_pool_bwd_w(ptr(feat), fmt, B, C, H * W, K, ptr(g), ptr(sums), float(scale),
                                  ptr(ws), ws_bytes, ptr(out), _stream()), "clr_pool_bwd_w")
     return out
@@ -229,7 +248,7 @@ def mc_statistics(preds: torch.Tensor, T: int, stride: int):
     _, K, Hi, Wi = p.shape
     std_map = torch.empty(stride, K, Hi, Wi, dtype=torch.float32, device=p.device)
     pred_mean = torch.empty_like(std_map)
-    with torch.cuda.device(p.device):
+    with _on(p.device):
         check(lib.clr_mc_stats(ptr(p), T, stride, K, Hi, Wi, ptr(std_map), ptr(pred_mean), _stream()), "clr_mc_stats")
     return std_map, pred_mean
 
@@ -249,7 +268,7 @@ def retrify_weights(oT_before: torch.Tensor, pred_mean: torch.Tensor, std_map: t
     masks = torch.empty(B, K, H, W, dtype=torch.float32, device=o.device)
     pseudo = torch.empty(B, K, H, W, dtype=torch.float32, device=o.device) if debug else None
     small = torch.empty(2, B, K, H, W, dtype=torch.float32, device=o.device) if debug else None
-    with torch.cuda.device(o.device):
+    with _on(o.device):
         pr = None if preds is None else _require_cuda_f32(preds, "preds")
         check(lib.clr_retrify_weights(ptr(o), ptr(pred_mean), ptr(std_map), ptr(pr), int(T), B, K, H, W, Hi, Wi,
                                       float(pseudo_thr), float(std_thr), ptr(weights), ptr(masks),
@@ -274,7 +293,7 @@ def mc_retrify(oT_before: torch.Tensor, preds: torch.Tensor, T: int, stride: int
     std_map = torch.empty(stride, K, Hi, Wi, dtype=torch.float32, device=p.device)
     weights = torch.empty(B, 2 * K, H, W, dtype=torch.float32, device=o.device)
     masks = torch.empty(B, K, H, W, dtype=torch.float32, device=o.device)
-    with torch.cuda.device(p.device):
+    with _on(p.device):
         rc = lib.clr_mc_retrify(ptr(p), ptr(o), int(T), int(stride), K, H, W, Hi, Wi, float(pseudo_thr), float(std_thr),
                                 ptr(std_map), None, ptr(weights), ptr(masks), _stream())
     if rc == _lib.CLR_ERR_UNSUPPORTED:
@@ -390,7 +409,7 @@ class _BmmPrototypes(torch.autograd.Function):
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=feat.device)
         sums_b = torch.empty(B, R, C + 1, dtype=torch.float32, device=feat.device)
         out = torch.empty(R, C, dtype=torch.float32, device=feat.device)
-        with torch.cuda.device(feat.device):
+        with _on(feat.device):
             check(lib.clr_pool_rows_fwd_ps(ptr(feat), ptr(masks), B, C, HW, R, ptr(ws), ws_bytes, ptr(sums_b), _stream()),
                   "clr_pool_rows_fwd_ps")
             check(lib.clr_bmm_finalize(ptr(sums_b), B, R, C, float(n_add), ptr(out), _stream()), "clr_bmm_finalize")
@@ -408,7 +427,7 @@ class _BmmPrototypes(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             g = g.contiguous()
             gf = torch.empty(ctx.shape, dtype=torch.float32, device=masks.device)
-            with torch.cuda.device(masks.device):
+            with _on(masks.device):
                 check(lib.clr_pool_bwd_ps(ptr(masks), B, C, H * W, R, ptr(g), ptr(sums_b), ctx.n_add, 1.0 / B,
                                           ptr(gf), _stream()), "clr_pool_bwd_ps")
         return None, gf, None
@@ -443,7 +462,7 @@ def update_objective_single_vector(obj: torch.Tensor, vector: torch.Tensor, rate
     R = o.numel() // C
     v = vector.detach().to(torch.float32).reshape(R, C).contiguous()
     out = torch.empty_like(o)
-    with torch.cuda.device(o.device):
+    with _on(o.device):
         check(lib.clr_ema_rows(ptr(v), ptr(o), R, C, float(rate), ptr(out), _stream()), "clr_ema_rows")
     return out
 
@@ -455,7 +474,7 @@ def nearest_labels(target_map: torch.Tensor, H: int, W: int) -> torch.Tensor:
     t = _require_cuda_f32(target_map.detach(), "target_map")
     B, K, Hi, Wi = t.shape
     out = torch.empty(B, K, H, W, dtype=torch.float32, device=t.device)
-    with torch.cuda.device(t.device):
+    with _on(t.device):
         check(lib.clr_label_downsample(ptr(t), B * K, Hi, Wi, int(H), int(W), ptr(out), _stream()), "clr_label_downsample")
     return out
 
@@ -496,7 +515,7 @@ class MCAccumulator:
             self.shape = (B, K, Hi, Wi)
         elif self.shape != (B, K, Hi, Wi):
             raise ValueError("MC passes of one step must agree in shape: %s vs %s" % (self.shape, (B, K, Hi, Wi)))
-        with torch.cuda.device(x.device):
+        with _on(x.device):
             check(lib.clr_mc_accumulate(ptr(x), int(passes), B, K, Hi, Wi, int(self.T == 0), ptr(self.state), _stream()),
                   "clr_mc_accumulate")
         self.T += passes
@@ -508,7 +527,7 @@ class MCAccumulator:
         B, K, Hi, Wi = self.shape
         std_map = torch.empty(B, K, Hi, Wi, dtype=torch.float32, device=self.state.device)
         pred_mean = torch.empty_like(std_map)
-        with torch.cuda.device(self.state.device):
+        with _on(self.state.device):
             check(lib.clr_mc_finalize(ptr(self.state), self.T, B, K, Hi, Wi, ptr(std_map), ptr(pred_mean), _stream()),
                   "clr_mc_finalize")
         self.T = 0
@@ -527,7 +546,7 @@ def feat_prototype_distance(feat: torch.Tensor, prototype: torch.Tensor, class_n
     P = prototype.detach().to(device=f.device, dtype=torch.float32).reshape(-1, C).contiguous()
     Q = P.shape[0]
     out = torch.empty(N, Q, H, W, dtype=torch.float32, device=f.device)
-    with torch.cuda.device(f.device):
+    with _on(f.device):
         check(lib.clr_proto_distance(ptr(f), N, C, H * W, ptr(P), Q, ptr(out), _stream()), "clr_proto_distance")
     if Q == 1 and class_numbers > 1:
         out = out.expand(N, class_numbers, H, W).contiguous()
@@ -540,7 +559,7 @@ def distance_weight(feat: torch.Tensor, prototype: torch.Tensor, class_num: int 
     lib = _lib.load()
     d = feat_prototype_distance(feat, prototype, class_num)
     ws = torch.empty(512, dtype=torch.float32, device=d.device)
-    with torch.cuda.device(d.device):
+    with _on(d.device):
         check(lib.clr_minmax_normalize(ptr(d), d.numel(), ptr(ws), _stream()), "clr_minmax_normalize")
     return d
 
@@ -555,7 +574,7 @@ def get_prototype_weight(feat, class_num, prototype):
     P = prototype.detach().to(device=f.device, dtype=torch.float32).reshape(C).contiguous()
     out = torch.empty(N, 1, H, W, dtype=torch.float32, device=f.device)
     ws = torch.empty(4, dtype=torch.float32, device=f.device)
-    with torch.cuda.device(f.device):
+    with _on(f.device):
         check(lib.clr_proto_cosine(ptr(f), N, C, H * W, ptr(P), ptr(ws), ptr(out), _stream()), "clr_proto_cosine")
     return out
 
@@ -578,7 +597,7 @@ class _SegLoss(torch.autograd.Function):
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=oS.device)
         out = torch.empty(4, dtype=torch.float32, device=oS.device)
         n2 = 0 if boundaryS is None else boundaryS.numel()
-        with torch.cuda.device(oS.device):
+        with _on(oS.device):
             check(lib.clr_seg_loss_fwd(ptr(oS), ptr(target_map), oS.numel(), ptr(boundaryS), ptr(target_boundary), n2,
                                        ptr(ws), ws_bytes, ptr(out), _stream()), "clr_seg_loss_fwd")
         ctx.save_for_backward(oS, boundaryS, target_map, target_boundary)
@@ -593,7 +612,7 @@ class _SegLoss(torch.autograd.Function):
         g2 = None if boundaryS is None else torch.empty_like(boundaryS)
         gup = gup.to(torch.float32).contiguous()
         n2 = 0 if boundaryS is None else boundaryS.numel()
-        with torch.cuda.device(oS.device):
+        with _on(oS.device):
             check(lib.clr_seg_loss_bwd(ptr(oS), ptr(target_map), oS.numel(), ptr(boundaryS), ptr(target_boundary), n2,
                                        ptr(gup), 1.0, ptr(g1), ptr(g2), _stream()), "clr_seg_loss_bwd")
         return g1, g2, None, None
@@ -621,7 +640,7 @@ class _EntropyMap(torch.autograd.Function):
     def forward(ctx, o, smooth):
         lib = _lib.load()
         out = torch.empty_like(o)
-        with torch.cuda.device(o.device):
+        with _on(o.device):
             check(lib.clr_entropy_fwd(ptr(o), o.numel(), float(smooth), ptr(out), _stream()), "clr_entropy_fwd")
         ctx.save_for_backward(o)
         ctx.smooth = float(smooth)
@@ -633,7 +652,7 @@ class _EntropyMap(torch.autograd.Function):
         (o,) = ctx.saved_tensors
         gout = gout.contiguous()
         gin = torch.empty_like(o)
-        with torch.cuda.device(o.device):
+        with _on(o.device):
             check(lib.clr_entropy_bwd(ptr(o), ptr(gout), o.numel(), ctx.smooth, ptr(gin), _stream()), "clr_entropy_bwd")
         return gin, None
 
@@ -656,7 +675,7 @@ def validation_counts(pred_logits: torch.Tensor, target: torch.Tensor, thr: floa
         raise ValueError("pred_logits %s and target %s disagree" % (tuple(z.shape), tuple(t.shape)))
     B, K, H, W = z.shape
     counts = torch.empty(K, 4, dtype=torch.int64, device=z.device)
-    with torch.cuda.device(z.device):
+    with _on(z.device):
         check(lib.clr_seg_counts(ptr(z), ptr(t), B, K, H * W, float(thr), ptr(counts), _stream()), "clr_seg_counts")
     return counts
 
