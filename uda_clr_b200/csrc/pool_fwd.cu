@@ -73,9 +73,26 @@ __device__ __forceinline__ ItemCoord decode_item(const PoolParams& p, int it) {
     return c;
 }
 
+// Shared-memory layout of the staged weight rows.  Plain: [r][PX].  PAIR (even R >= 6, LDG kernel): rows 2q and 2q+1 are
+// interleaved pixel by pixel, [q][PX][2], so that one 128-bit load yields the (w_2q, w_2q+1) pairs of two pixels -- the
+// operands of the packed FFMA2 (two fp32 FMAs per issue slot on sm_100) that halves the FMA instruction count of the
+// issue-bound K >= 3 pooling; every accumulator still sees the same products in the same order (bit-identical results).
+constexpr bool pool_pair(int R) { return R % 2 == 0 && R >= 6; }
+template <int PX, bool PAIR>
+__device__ __forceinline__ int wsm_idx(int r, int px) { return PAIR ? (((r >> 1) * PX + px) * 2 + (r & 1)) : (r * PX + px); }
+template <int VEC, int PX, bool PAIR>
+__device__ __forceinline__ void wsm_store(float* wsm, int r, int px, const Pack<VEC>& w) {
+    if constexpr (PAIR) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) wsm[wsm_idx<PX, true>(r, px + v)] = w.v[v];
+    } else {
+        st_keep<VEC>(wsm + r * PX + px, w);
+    }
+}
+
 // Stage the R weight rows of (b, chunk) in shared memory (complement rows are materialised here:
 // w_bck = 1 - w_obj, utils/Utils.py:111-112).  Pixels past the plane are staged as 0 for every row.
-template <int R, int VEC, int REPS, int NT = kThreads>
+template <int R, int VEC, int REPS, int NT = kThreads, bool PAIR = false>
 __device__ __forceinline__ void stage_weights(const PoolDom& D, int b, int px0, int HW, float* wsm, int tid) {
     constexpr int PX = NT * VEC * REPS, K = R / 2;
     const int WP = (D.fmt == CLR_W_COMPLEMENT) ? K : R;
@@ -95,8 +112,8 @@ __device__ __forceinline__ void stage_weights(const PoolDom& D, int b, int px0, 
 #pragma unroll
                     for (int v = 0; v < VEC; ++v) wc.v[v] = 1.0f - wo.v[v];
                 }
-                st_keep<VEC>(wsm + k * PX + off, wo);
-                st_keep<VEC>(wsm + (K + k) * PX + off, wc);
+                wsm_store<VEC, PX, PAIR>(wsm, k, off, wo);
+                wsm_store<VEC, PX, PAIR>(wsm, K + k, off, wc);
             }
         } else {
 #pragma unroll
@@ -105,7 +122,7 @@ __device__ __forceinline__ void stage_weights(const PoolDom& D, int b, int px0, 
 #pragma unroll
                 for (int v = 0; v < VEC; ++v) wr.v[v] = 0.f;
                 if (ok) wr = ld_keep<VEC>(wb + (size_t)r * HW + px0 + off);
-                st_keep<VEC>(wsm + r * PX + off, wr);
+                wsm_store<VEC, PX, PAIR>(wsm, r, off, wr);
             }
         }
     }
@@ -125,7 +142,7 @@ __device__ __forceinline__ Pack<VEC> lds_pack(const float* p) {
 
 // CTA-level combine of the per-thread accumulators of one item and store of the partial row slices.
 // sync() is the barrier over the 256 compute threads.
-template <int R, int CG, int VEC, int REPS, int NT = kThreads, typename Sync>
+template <int R, int CG, int VEC, int REPS, int NT = kThreads, bool PAIR = false, typename Sync>
 __device__ __forceinline__ void reduce_and_store(float (&acc)[pool_nacc(R)], const float* wsm, float* red, int& parity,
                                                  float* out, int C, int c0, bool owns_counts,
                                                  int tid, Sync sync) {
@@ -141,7 +158,7 @@ __device__ __forceinline__ void reduce_and_store(float (&acc)[pool_nacc(R)], con
             for (int rep = 0; rep < REPS; ++rep) {
                 const int off = (rep * NT + tid) * VEC;
 #pragma unroll
-                for (int v = 0; v < VEC; ++v) s += wsm[r * PX + off + v];
+                for (int v = 0; v < VEC; ++v) s += wsm[wsm_idx<PX, PAIR>(r, off + v)];
             }
             nsum[r] = s;
         }
@@ -195,6 +212,7 @@ __global__ void __launch_bounds__(NT, 2) pool_fwd_ldg_kernel(const PoolParams p)
     kernel_begin(p.trace_id);
     if (p.counter_reset && blockIdx.x == 0 && threadIdx.x < 8) p.counter_reset[threadIdx.x] = 0u;   // last-CTA counters + completion counters + gate
     constexpr int CG = pool_cg(R), REPS = pool_reps(R) * (kThreads / NT), PX = NT * VEC * REPS;
+    constexpr bool PAIR = pool_pair(R) && VEC == 4;
     static_assert(PX == kThreads * VEC * pool_reps(R), "chunk size is independent of the CTA size");
     extern __shared__ __align__(16) float smem[];
     float* wsm = smem;                 // [R][PX]
@@ -215,7 +233,7 @@ __global__ void __launch_bounds__(NT, 2) pool_fwd_ldg_kernel(const PoolParams p)
         if (key != cur_key) {
             __syncthreads();
             cur_key = key;
-            stage_weights<R, VEC, REPS, NT>(D, ic.b, px0, p.HW, wsm, tid);
+            stage_weights<R, VEC, REPS, NT, PAIR>(D, ic.b, px0, p.HW, wsm, tid);
             __syncthreads();
         }
         float acc[pool_nacc(R)];
@@ -235,17 +253,39 @@ __global__ void __launch_bounds__(NT, 2) pool_fwd_ldg_kernel(const PoolParams p)
                 if (ok && c0 + j < p.C) x[j] = ld_stream<VEC>(xb + (size_t)j * p.HW + off);
             }
             // weight row outermost: one row vector live at a time (R = 16 rows would not fit in registers otherwise)
+            if constexpr (PAIR) {
+                // packed form: (acc[j][2q], acc[j][2q+1]) += (x, x) * (w_2q, w_2q+1), pixel by pixel, in the scalar order
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const Pack<VEC> w = lds_pack<VEC>(wsm + r * PX + off);
+                for (int q = 0; q < R / 2; ++q) {
+                    float2 wp[VEC];
 #pragma unroll
-                for (int j = 0; j < CG; ++j)
+                    for (int h = 0; h < VEC / 2; ++h) {
+                        const float4 t = *reinterpret_cast<const float4*>(wsm + (size_t)(q * PX + off + 2 * h) * 2);
+                        wp[2 * h] = make_float2(t.x, t.y);
+                        wp[2 * h + 1] = make_float2(t.z, t.w);
+                    }
 #pragma unroll
-                    for (int v = 0; v < VEC; ++v) acc[j * R + r] = fmaf(x[j].v[v], w.v[v], acc[j * R + r]);
+                    for (int j = 0; j < CG; ++j) {
+                        float2 a = make_float2(acc[j * R + 2 * q], acc[j * R + 2 * q + 1]);
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) a = __ffma2_rn(make_float2(x[j].v[v], x[j].v[v]), wp[v], a);
+                        acc[j * R + 2 * q] = a.x;
+                        acc[j * R + 2 * q + 1] = a.y;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const Pack<VEC> w = lds_pack<VEC>(wsm + r * PX + off);
+#pragma unroll
+                    for (int j = 0; j < CG; ++j)
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) acc[j * R + r] = fmaf(x[j].v[v], w.v[v], acc[j * R + r]);
+                }
             }
         }
         float* out = D.partial + (size_t)ic.slot * R * (p.C + 1);
-        reduce_and_store<R, CG, VEC, REPS, NT>(acc, wsm, red, parity, out, p.C, c0, ic.grp == 0, tid, sync);
+        reduce_and_store<R, CG, VEC, REPS, NT, PAIR>(acc, wsm, red, parity, out, p.C, c0, ic.grp == 0, tid, sync);
     }
     trace_exit(p.trace_id);
 }
