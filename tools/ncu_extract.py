@@ -68,11 +68,18 @@ def main(rep, out_prefix):
             traffic.setdefault(name, tot)
     tpath = os.path.join(os.path.dirname(out_prefix) or ".", "dram_traffic.json")
     cur = json.load(open(tpath)) if os.path.isfile(tpath) else {}
+    cur.pop("pool_bwd_bytes_per_launch", None)          # (stale key of an early round-1 build: the backward is bwd_finish_kernel)
     for name, tot in traffic.items():
-        if "pool_fwd_tma_kernel<4>" in name:
+        if "pool_fwd_ldg_kernel<4" in name or "pool_fwd_tma_kernel<4>" in name:
             cur["pool_fwd_bytes_per_launch"] = tot
-        if "pool_bwd_kernel" in name:
-            cur["pool_bwd_bytes_per_launch"] = tot
+        if "pool_bwd_kernel" in name or "bwd_finish_kernel" in name:
+            # both gradient maps in one launch; ncu sees only what reached DRAM inside the kernel's window (~60 MB of the
+            # 268 MB are still dirty in L2 when it ends and drain during the next step)
+            cur["bwd_bytes_per_launch_inside_kernel_window"] = tot
+        if "retrify" in name:
+            cur["retrify_weights_bytes_per_launch"] = tot
+        if "pool_finish_cons" in name:
+            cur["pool_finish_cons_bytes_per_launch"] = tot
         if "disc_fused" in name:
             cur["disc_fused_bytes_per_launch"] = tot
         if "mc_stats" in name:

@@ -41,6 +41,7 @@ int clr_set_tunable(const char* name, int value) {
     if (!strcmp(name, "pool_impl")) t.pool_impl = value;
     else if (!strcmp(name, "pool_stages")) t.pool_stages = value;
     else if (!strcmp(name, "pool_threads")) t.pool_threads = value;
+    else if (!strcmp(name, "pool_pair")) t.pool_pair = value;
     else if (!strcmp(name, "mc_precise")) t.mc_precise = value;
     else if (!strcmp(name, "disc_impl")) t.disc_impl = value;
     else if (!strcmp(name, "disc_tile")) t.disc_tile = value;

@@ -77,9 +77,15 @@ __device__ __forceinline__ ItemCoord decode_item(const PoolParams& p, int it) {
 // interleaved pixel by pixel, [q][PX][2], so that one 128-bit load yields the (w_2q, w_2q+1) pairs of two pixels -- the
 // operands of the packed FFMA2 (two fp32 FMAs per issue slot on sm_100) that halves the FMA instruction count of the
 // issue-bound K >= 3 pooling; every accumulator still sees the same products in the same order (bit-identical results).
+// The pairs of pixels {0,1} and {2,3} of a thread's 4-pixel group live in two planes, [q][2][PX/4][4], so that consecutive
+// threads read consecutive 16-byte words (stride 32 bytes would be a 2-way bank conflict on every 128-bit load).
 constexpr bool pool_pair(int R) { return R % 2 == 0 && R >= 6; }
 template <int PX, bool PAIR>
-__device__ __forceinline__ int wsm_idx(int r, int px) { return PAIR ? (((r >> 1) * PX + px) * 2 + (r & 1)) : (r * PX + px); }
+__device__ __forceinline__ int wsm_idx(int r, int px) {
+    if (!PAIR) return r * PX + px;
+    const int t = px >> 2, v = px & 3;
+    return ((((r >> 1) * 2 + (v >> 1)) * (PX / 4) + t) << 2) + ((v & 1) << 1) + (r & 1);
+}
 template <int VEC, int PX, bool PAIR>
 __device__ __forceinline__ void wsm_store(float* wsm, int r, int px, const Pack<VEC>& w) {
     if constexpr (PAIR) {
@@ -207,12 +213,12 @@ __device__ __forceinline__ void reduce_and_store(float (&acc)[pool_nacc(R)], con
 // over NT threads: NT = 128 gives every thread twice the pixels per item, i.e. twice the FMAs per accumulator between two
 // transposing butterflies -- for R > 8 (64 accumulators, 4 channels x 1024 pixels per item) the butterfly's FSEL / SHFL /
 // FADD were as many instructions as the FMAs themselves (ncu source page, K = 8: 33.5 M FFMA vs 33.3 M).
-template <int R, int VEC, int NT>
+template <int R, int VEC, int NT, bool PAIR_ON = true>
 __global__ void __launch_bounds__(NT, 2) pool_fwd_ldg_kernel(const PoolParams p) {
     kernel_begin(p.trace_id);
     if (p.counter_reset && blockIdx.x == 0 && threadIdx.x < 8) p.counter_reset[threadIdx.x] = 0u;   // last-CTA counters + completion counters + gate
     constexpr int CG = pool_cg(R), REPS = pool_reps(R) * (kThreads / NT), PX = NT * VEC * REPS;
-    constexpr bool PAIR = pool_pair(R) && VEC == 4;
+    constexpr bool PAIR = PAIR_ON && pool_pair(R) && VEC == 4;
     static_assert(PX == kThreads * VEC * pool_reps(R), "chunk size is independent of the CTA size");
     extern __shared__ __align__(16) float smem[];
     float* wsm = smem;                 // [R][PX]
@@ -260,7 +266,7 @@ __global__ void __launch_bounds__(NT, 2) pool_fwd_ldg_kernel(const PoolParams p)
                     float2 wp[VEC];
 #pragma unroll
                     for (int h = 0; h < VEC / 2; ++h) {
-                        const float4 t = *reinterpret_cast<const float4*>(wsm + (size_t)(q * PX + off + 2 * h) * 2);
+                        const float4 t = *reinterpret_cast<const float4*>(wsm + ((size_t)(q * 2 + h) * (PX / 4) + (off >> 2)) * 4);
                         wp[2 * h] = make_float2(t.x, t.y);
                         wp[2 * h + 1] = make_float2(t.z, t.w);
                     }
@@ -519,6 +525,9 @@ static int launch_ldg_nt(const PoolParams& p, cudaStream_t st) {
     constexpr int PX = kThreads * VEC * pool_reps(R);
     constexpr size_t smem = sizeof(float) * (R * PX + 2 * (pool_nacc(R) / 32) * (NT / 32) * 32);
     auto kern = pool_fwd_ldg_kernel<R, VEC, NT>;
+    if constexpr (pool_pair(R) && VEC == 4) {
+        if (tunables().pool_pair == 2) kern = pool_fwd_ldg_kernel<R, VEC, NT, false>;      // A/B: the scalar-FMA inner loop
+    }
     int occ = 0;
     { const int rc = kernel_occupancy(reinterpret_cast<const void*>(kern), NT, smem, &occ); if (rc != CLR_OK) return rc; }
     if (occ < 1) occ = 1;
