@@ -31,7 +31,7 @@ const DeviceFacts& device_facts();
 struct Tunables {
     int pool_impl;     // 0 = auto (128-bit LDG kernel, 2 CTAs/SM: fastest in the live step), 1 = force LDG, 2 = force the TMA ring
     int pool_stages;   // TMA ring depth (0 = auto)
-    int pool_pair;     // LDG pooling kernel, even R >= 6: 0 = packed FFMA2 inner loop, 2 = scalar FMAs (A/B)
+    int pool_pair;     // LDG pooling kernel, even R >= 8: 0 = packed FFMA2 inner loop, 2 = scalar FMAs (A/B)
     int pool_threads;  // LDG pooling kernel CTA size: 0 = auto (128 for R > 8, else 256), 128 / 256 = forced
     int disc_impl;     // 0 = auto (one-read fused kernel, tensor-map TMA tiles), 1 = two-pass form, 2 = one-read kernel with cp.async tiles
     int disc_threads;  // 0 = auto (256-thread CTAs: fastest in the live step), 512 = 512-thread CTAs when K <= 2

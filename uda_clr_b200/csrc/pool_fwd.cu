@@ -73,13 +73,15 @@ __device__ __forceinline__ ItemCoord decode_item(const PoolParams& p, int it) {
     return c;
 }
 
-// Shared-memory layout of the staged weight rows.  Plain: [r][PX].  PAIR (even R >= 6, LDG kernel): rows 2q and 2q+1 are
+// Shared-memory layout of the staged weight rows.  Plain: [r][PX].  PAIR (even R >= 8, LDG kernel): rows 2q and 2q+1 are
 // interleaved pixel by pixel, [q][PX][2], so that one 128-bit load yields the (w_2q, w_2q+1) pairs of two pixels -- the
 // operands of the packed FFMA2 (two fp32 FMAs per issue slot on sm_100) that halves the FMA instruction count of the
 // issue-bound K >= 3 pooling; every accumulator still sees the same products in the same order (bit-identical results).
 // The pairs of pixels {0,1} and {2,3} of a thread's 4-pixel group live in two planes, [q][2][PX/4][4], so that consecutive
 // threads read consecutive 16-byte words (stride 32 bytes would be a 2-way bank conflict on every 128-bit load).
-constexpr bool pool_pair(int R) { return R % 2 == 0 && R >= 6; }
+// Measured in the live step (B200, config 1 with K classes; "pool_pair" = 2 selects the scalar loop): R = 16 (K = 8) pooling
+// 114.3 -> 108.9 us, R = 8 (K = 4) 69.5 -> 63.0 us, R = 6 (K = 3) 51.2 -> 53.9 us (slower: few FMAs per staged pair) -> R >= 8.
+constexpr bool pool_pair(int R) { return R % 2 == 0 && R >= 8; }
 template <int PX, bool PAIR>
 __device__ __forceinline__ int wsm_idx(int r, int px) {
     if (!PAIR) return r * PX + px;
