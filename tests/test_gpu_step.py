@@ -839,13 +839,13 @@ def test_schedule2_equals_schedule1_bit_for_bit(K, C, H, B):
     b = synth.make_batch(B=B, C=C, H=H, W=H, K=K, T=8, up=4, seed=21 + C, image_res=True)
     t = {k: getattr(b, k).to(DEV) for k in ("xs", "ys", "xt", "oT_before", "preds", "oT", "oT_aug")}
     res = []
-    for v1 in (0, 1):
+    for sched in (2, 1, 3):          # 3 = schedule 2 with [pool(xs) | mc_stats] in one persistent launch
         try:
-            _lib.check(lib.clr_set_tunable(b"sched", 1 if v1 else 2), "sched")
+            _lib.check(lib.clr_set_tunable(b"sched", sched), "sched")
             step = clr.CLRStep(K=K, retrify=True, use_disc=True, use_cons=True, backprop_aug=True)
             plan = step.plan(t["xs"], t["ys"], t["xt"], oT_before=t["oT_before"], preds=t["preds"], T=8, oT=t["oT"],
                              oT_aug=t["oT_aug"], epoch=1.0)
-            assert lib.clr_step_schedule(plan._ref) == (1 if v1 else 2)
+            assert lib.clr_step_schedule(plan._ref) == (1 if sched == 1 else 2)
             for _ in range(3):
                 plan.run()
             torch.cuda.synchronize()
@@ -863,5 +863,6 @@ def test_schedule2_equals_schedule1_bit_for_bit(K, C, H, B):
         finally:
             lib.clr_set_tunable(b"sched", 0)
     assert float(res[0][0][7]) == 0.0
-    for x, y in zip(res[0], res[1]):
-        assert torch.equal(x, y)
+    for other in res[1:]:
+        for x, y in zip(res[0], other):
+            assert torch.equal(x, y)
