@@ -839,7 +839,7 @@ def test_schedule2_equals_schedule1_bit_for_bit(K, C, H, B):
     b = synth.make_batch(B=B, C=C, H=H, W=H, K=K, T=8, up=4, seed=21 + C, image_res=True)
     t = {k: getattr(b, k).to(DEV) for k in ("xs", "ys", "xt", "oT_before", "preds", "oT", "oT_aug")}
     res = []
-    for sched in (2, 1, 3):          # 3 = schedule 2 with [pool(xs) | mc_stats] in one persistent launch
+    for sched in (2, 1):
         try:
             _lib.check(lib.clr_set_tunable(b"sched", sched), "sched")
             step = clr.CLRStep(K=K, retrify=True, use_disc=True, use_cons=True, backprop_aug=True)

@@ -59,7 +59,6 @@ int clr_set_tunable(const char* name, int value) {
     else if (!strcmp(name, "mc_split")) t.mc_split = value;
     else if (!strcmp(name, "disc_reverse")) t.disc_reverse = value;
     else if (!strcmp(name, "sched")) t.sched = value;
-    else if (!strcmp(name, "pool_pct")) t.pool_pct = value;
     else if (!strcmp(name, "dfin_split")) t.dfin_split = value;
 
     else return CLR_ERR_BAD_ARG;

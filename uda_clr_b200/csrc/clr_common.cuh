@@ -50,8 +50,7 @@ struct Tunables {
                        //     instead of the finish CTAs' completion counter
     int disc_reverse;  // 1 = the one-read discriminative kernel walks its tiles in descending address order (round 2: the re-read of
                        //     xs then misses DRAM for 102 instead of 110 of 135 MB, the kernel is not faster -- it is not DRAM-bound)
-    int sched;         // fused step launch schedule (step.cu): 0 = auto (schedule 2 from 8 ranks on, else 1), 1, 2, 3 (= 2 with [pool(xs) | mc_stats] in one launch)
-    int pool_pct;      // schedule 3: share (percent) of the CTAs of the fused launch that pool (0 = default 45)
+    int sched;         // fused step launch schedule (step.cu): 0 = auto (schedule 2 from 8 ranks on, else 1), 1, 2
     int dfin_split;    // clr_step_run: disc finish as its own launch in front of a no-wait gated backward: 0 = auto (with schedule 2), 1, 2 = never
     int xchg_pull;     // in-kernel exchange: 1 = readers poll the peers' buffers (no remote stores), 0 = senders push
     void* trace_buf;   // device TraceRec[kTraceSlots] or NULL (clr_trace_set): device-side timeline of the kernels

@@ -65,11 +65,6 @@ int mc_stats_impl(const float* preds, int T, int B, int K, int Hi, int Wi, float
 int retrify_weights_impl(const float* oT_before, const float* pred_mean, const float* std_map, const float* preds, int T,
                          int B, int K, int H, int W, int Hi, int Wi, float pseudo_thr, float std_thr,
                          float* weights, float* masks, float* pseudo_out, float* small_out, cudaStream_t stream, bool nowait);
-// One domain pooled + the MC statistics (T = 8) in ONE persistent launch (pool_fwd.cu: pool_mc_kernel); CLR_ERR_UNSUPPORTED ->
-// two launches.  pool_pct = share of the CTAs that pool.
-int pool_mc_fused_impl(const float* feat, const float* w, int fmt, int B, int C, int HW, int R, void* ws, size_t ws_bytes,
-                       struct PoolLayout* layout, unsigned int* counter_reset,
-                       const float* preds, int T, size_t n_mc, float* std_map, float* pred_mean, int pool_pct, cudaStream_t st);
 // MC statistics + retrify weights in one pass (mc_stats.cu); CLR_ERR_UNSUPPORTED -> run the two kernels.
 int mc_retrify_fused(const float* preds, const float* oT_before, int T, int B, int K, int H, int W, int Hi, int Wi,
                      float pseudo_thr, float std_thr, float* std_map, float* pred_mean /*nullable*/, float* weights,

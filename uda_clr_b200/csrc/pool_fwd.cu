@@ -25,7 +25,6 @@
 //            fallback (VEC = 1) for ragged planes / 4-byte-aligned bases.
 #include "clr_common.cuh"
 #include "clr_internal.h"
-#include "clr_mc.cuh"
 
 namespace clr {
 
@@ -216,7 +215,8 @@ __device__ __forceinline__ void reduce_and_store(float (&acc)[pool_nacc(R)], con
 // over NT threads: NT = 128 gives every thread twice the pixels per item, i.e. twice the FMAs per accumulator between two
 // transposing butterflies -- for R > 8 (64 accumulators, 4 channels x 1024 pixels per item) the butterfly's FSEL / SHFL /
 // FADD were as many instructions as the FMAs themselves (ncu source page, K = 8: 33.5 M FFMA vs 33.3 M).
-// `bid` of `nblk` CTAs walk the items (the body may share a launch with other work: pool_mc_kernel)
+// `bid` of `nblk` CTAs walk the items.  (Round 2 shared this body's launch with the MC statistics -- [pool(xs) | mc_stats] as one
+// persistent grid -- and lost: at this kernel's 126 registers the MC CTAs run at 2 per SM and take 58 us; profiles/r02_schedule2.md.)
 template <int R, int VEC, int NT, bool PAIR_ON = true>
 __device__ __forceinline__ void pool_ldg_body(const PoolParams& p, const int bid, const int nblk) {
     if (p.counter_reset && bid == 0 && threadIdx.x < 8) p.counter_reset[threadIdx.x] = 0u;   // last-CTA counters + completion counters + gate
@@ -303,36 +303,6 @@ __global__ void __launch_bounds__(NT, 2) pool_fwd_ldg_kernel(const PoolParams p)
     kernel_begin(p.trace_id);
     pool_ldg_body<R, VEC, NT, PAIR_ON>(p, blockIdx.x, gridDim.x);
     trace_exit(p.trace_id);
-}
-
-// Horizontal fusion for schedule 3 of the fused step: ONE persistent launch in which `n_pool` CTAs pool the source features
-// while the others stream the MC-dropout logits (clr_mc_stats' arithmetic, T = 8) -- two independent HBM-bound passes that
-// otherwise each pay their own ramp and tail.  Roles are interleaved over the block indices (Bresenham) so that an SM gets
-// CTAs of both kinds; MC blocks of 1024 positions are dealt round-robin to the MC CTAs.
-struct McFuse { const float* preds; float* std_map; float* pred_mean; size_t n; int nblocks; };
-template <int R>
-__global__ void __launch_bounds__(kThreads, 2) pool_mc_kernel(const PoolParams p, const int n_pool, const McFuse m) {
-    const int b = blockIdx.x, g = gridDim.x;
-    const int before = (int)(((long long)b * n_pool) / g);                       // pooling CTAs among [0, b)
-    const bool is_pool = (int)(((long long)(b + 1) * n_pool) / g) > before;
-    if (is_pool) {
-        kernel_begin(p.trace_id);
-        pool_ldg_body<R, 4, kThreads>(p, before, n_pool);
-        trace_exit(p.trace_id);
-    } else {
-        kernel_begin(TR_MC_STATS);
-        const int n_mc = g - n_pool;
-        for (int blk = b - before; blk < m.nblocks; blk += n_mc) {
-            const size_t i = ((size_t)blk * kThreads + threadIdx.x) * 4;
-            if (i < m.n) {
-                Pack<4> sd, mn;
-                mc_vec_stats<4, 8, false, true>(m.preds, 8, m.n, i, sd, mn);
-                st_keep<4>(m.std_map + i, sd);
-                st_keep<4>(m.pred_mean + i, mn);
-            }
-        }
-        trace_exit(TR_MC_STATS);
-    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -624,23 +594,6 @@ static int dispatch(int R, bool vec4, bool tma, const PoolParams& p, cudaStream_
     return CLR_ERR_UNSUPPORTED;
 }
 
-template <int R>
-static int launch_pool_mc(const PoolParams& p, const McFuse& m, int pool_pct, cudaStream_t st) {
-    constexpr int PX = kThreads * 4 * pool_reps(R);
-    constexpr size_t smem = sizeof(float) * (R * PX + 2 * (pool_nacc(R) / 32) * (kThreads / 32) * 32);
-    auto kern = pool_mc_kernel<R>;
-    int occ = 0;
-    { const int rc = kernel_occupancy(reinterpret_cast<const void*>(kern), kThreads, smem, &occ); if (rc != CLR_OK) return rc; }
-    if (occ < 1) occ = 1;
-    const int grid = device_facts().sms * occ;
-    int n_pool = (int)((long long)grid * pool_pct / 100);
-    if (n_pool < 1) n_pool = 1;
-    if (n_pool > grid - 1) n_pool = grid - 1;
-    if (n_pool > p.total) n_pool = p.total;
-    clr::launch_k(kern, grid, kThreads, smem, st, p, n_pool, m);
-    return launch_status();
-}
-
 static int chunk_px(int R, int vec) { return kThreads * vec * pool_reps(R); }
 
 // Workspace: partials for one domain, sized for the scalar (smallest-chunk) path.
@@ -696,42 +649,6 @@ int pool_fwd_impl(const float* feat0, const float* w0, int fmt0, int B0, float* 
         skip_reduce_layout->slots[1] = ndom == 2 ? p.dom[1].slots : 0;
     }
     return dispatch(R, vec4, tma, p, st);
-}
-
-// One domain pooled (per-(b,chunk) partials only: the caller reduces them) and the MC statistics of T = 8 passes, in ONE launch.
-// CLR_ERR_UNSUPPORTED when the geometry does not allow it (ragged / misaligned planes, R not 2 / 4 / 6 / 8, T != 8).
-int pool_mc_fused_impl(const float* feat, const float* w, int fmt, int B, int C, int HW, int R, void* ws, size_t ws_bytes,
-                       PoolLayout* layout, unsigned int* counter_reset,
-                       const float* preds, int T, size_t n_mc, float* std_map, float* pred_mean, int pool_pct, cudaStream_t st) {
-    CLR_CHECK_ARG(feat && w && ws && layout && preds && std_map && pred_mean && B > 0 && C > 0 && HW > 0);
-    if (T != 8 || (n_mc % 4) != 0 || !aligned16(preds) || !aligned16(std_map) || !aligned16(pred_mean)) return CLR_ERR_UNSUPPORTED;
-    if ((HW % 4) != 0 || !aligned16(feat) || !aligned16(w)) return CLR_ERR_UNSUPPORTED;
-    if (R != 2 && R != 4 && R != 6 && R != 8) return CLR_ERR_UNSUPPORTED;
-    if (n_mc / 1024 + 1 > 0x7fffffffull) return CLR_ERR_UNSUPPORTED;
-    const int px = chunk_px(R, 4), CG = pool_cg(R);
-    PoolParams p{};
-    p.ndom = 1; p.C = C; p.HW = HW;
-    p.nChunk = (HW + px - 1) / px;
-    p.nGroup = (C + CG - 1) / CG;
-    if (ws_bytes < sizeof(float) * partial_floats(B, C, HW, R)) return CLR_ERR_WORKSPACE;
-    const long long items = (long long)B * p.nChunk * p.nGroup;
-    if (items > 0x3fffffff) return CLR_ERR_UNSUPPORTED;
-    p.dom[0] = PoolDom{feat, w, static_cast<float*>(ws), nullptr, nullptr, B, fmt, (int)items, B * p.nChunk, 0};
-    p.total = (int)items;
-    p.reduce_trace_id = TR_POOL_REDUCE;
-    p.trace_id = TR_POOL;
-    p.counter_reset = counter_reset;
-    p.skip_reduce = 1;
-    layout->partial[0] = p.dom[0].partial; layout->slots[0] = p.dom[0].slots;
-    layout->partial[1] = nullptr; layout->slots[1] = 0;
-    McFuse m{preds, std_map, pred_mean, n_mc, (int)((n_mc / 4 + kThreads - 1) / kThreads)};
-    switch (R) {
-        case 2: return launch_pool_mc<2>(p, m, pool_pct, st);
-        case 4: return launch_pool_mc<4>(p, m, pool_pct, st);
-        case 6: return launch_pool_mc<6>(p, m, pool_pct, st);
-        case 8: return launch_pool_mc<8>(p, m, pool_pct, st);
-    }
-    return CLR_ERR_UNSUPPORTED;
 }
 
 }  // namespace clr

@@ -229,7 +229,7 @@ static PeerXchg make_xchg(const clr_step_args* a, int which) {
 static bool use_schedule2(const clr_step_args* a) {
     const Tunables& t = tunables();
     const bool possible = a->use_retrify && a->use_disc && t.disc_impl != 1 && !t.finish_off && !t.hfuse_off && !t.flag_dep_off && !t.mc_fuse;
-    return possible && (t.sched == 2 || t.sched == 3 || (t.sched == 0 && a->world >= 8));
+    return possible && (t.sched == 2 || (t.sched == 0 && a->world >= 8));
 }
 
 static int step_fwd_v2(const clr_step_args* a, cudaStream_t st, DiscFinishParams* defer, int* deferred) {
@@ -244,22 +244,12 @@ static int step_fwd_v2(const clr_step_args* a, cudaStream_t st, DiscFinishParams
     unsigned int* counter = step_counters(w, C);
     const int early = tunables().fin_early_off ? 0 : 1;
     int rc;
-    // 1. source pooling (first kernel of the step: zeroes the counters).  Schedule 3: in ONE persistent launch with the MC
-    //    statistics ([pool(xs) | mc_stats]: two independent HBM-bound passes share one ramp and one tail)
+    // 1. source pooling (first kernel of the step: zeroes the counters)
     PoolLayout lay_s{}, lay_t{};
     const size_t pb_s = pool_partial_bytes(a->B_s, C, HW, R);
-    bool fused_mc = tunables().sched == 3 && !tunables().mc_precise;
     if (a->ev_pool_begin) cudaEventRecord(static_cast<cudaEvent_t>(a->ev_pool_begin), st);
-    if (fused_mc) {
-        const int pct = tunables().pool_pct > 0 ? tunables().pool_pct : 45;
-        rc = pool_mc_fused_impl(a->xs, a->ys, CLR_W_COMPLEMENT, a->B_s, C, HW, R, w.pool, pb_s, &lay_s, counter,
-                                a->preds, a->T, (size_t)a->B_t * K * a->Hi * a->Wi, a->std_map, a->pred_mean, pct, st);
-        if (rc == CLR_ERR_UNSUPPORTED) fused_mc = false;
-        else if (rc != CLR_OK) return rc;
-    }
-    if (!fused_mc)
-        rc = pool_fwd_impl(a->xs, a->ys, CLR_W_COMPLEMENT, a->B_s, sums_s, nullptr, nullptr, 0, 0, nullptr,
-                           C, HW, R, w.pool, pb_s, st, 0, 0, &lay_s, counter);
+    rc = pool_fwd_impl(a->xs, a->ys, CLR_W_COMPLEMENT, a->B_s, sums_s, nullptr, nullptr, 0, 0, nullptr,
+                       C, HW, R, w.pool, pb_s, st, 0, 0, &lay_s, counter);
     if (a->ev_pool_end) cudaEventRecord(static_cast<cudaEvent_t>(a->ev_pool_end), st);
     if (rc != CLR_OK) return rc;
     // 2. source half of the finish
@@ -278,13 +268,11 @@ static int step_fwd_v2(const clr_step_args* a, cudaStream_t st, DiscFinishParams
     ps.done_fin = counter + 5; ps.done_all = counter + 6; ps.early_signal = early;      // [5]: vectors out (early), [6]: CTA finished
     rc = pool_finish_launch(ps, st);
     if (rc != CLR_OK) return rc;
-    // 3. MC statistics (not waiting for 2; schedule 3: already done in launch 1) + retrify weights (schedule 3: not waiting for 2)
-    if (!fused_mc) {
-        rc = mc_stats_impl(a->preds, a->T, a->B_t, K, a->Hi, a->Wi, a->std_map, a->pred_mean, st, true);
-        if (rc != CLR_OK) return rc;
-    }
-    rc = retrify_weights_impl(a->oT_before, a->pred_mean, a->std_map, a->preds, a->T, a->B_t, K, a->H, a->W, a->Hi, a->Wi,
-                              a->pseudo_thr, a->std_thr, a->wt_retrify, a->masks, nullptr, nullptr, st, fused_mc);
+    // 3. MC statistics (not waiting for 2) + retrify weights
+    rc = mc_stats_impl(a->preds, a->T, a->B_t, K, a->Hi, a->Wi, a->std_map, a->pred_mean, st, true);
+    if (rc != CLR_OK) return rc;
+    rc = clr_retrify_weights(a->oT_before, a->pred_mean, a->std_map, a->preds, a->T, a->B_t, K, a->H, a->W, a->Hi, a->Wi,
+                             a->pseudo_thr, a->std_thr, a->wt_retrify, a->masks, nullptr, nullptr, stream);
     if (rc != CLR_OK) return rc;
     // 4. target pooling
     rc = pool_fwd_impl(a->xt, a->wt_retrify, CLR_W_EXPLICIT, a->B_t, sums_t, nullptr, nullptr, 0, 0, nullptr,
