@@ -203,7 +203,10 @@ def run_reference_cpu(a, steps: int, warmup: int, budget_s: float):
     med = statistics.median(ts)
     mpix = 2 * Bs * a.H * a.H / med / 1e6
     sample = "%d steps x (B=%d of %d per domain, C=%d, %dx%d, K=%d%s), median of per-step wall times" % (
-        steps, Bs, a.B, a.C, a.H, a.H, a.K, (", T=%d, %dx%d preds" % (a.T, a.H * a.up, a.H * a.up)) if use3 else "")
+        steps, Bs, a.B * max(1, a.gpus), a.C, a.H, a.H, a.K, (", T=%d, %dx%d preds" % (a.T, a.H * a.up, a.H * a.up)) if use3 else "")
+    if a.gpus > 1:
+        sample += "; ONE CPU job on this host timing a %d-sample shard of the %d-sample global batch (throughput in pixels/s does not " \
+                  "depend on which shard): compare with the 1-GPU line, not with the %d-GPU aggregate" % (Bs, a.B * a.gpus, a.gpus)
     return dict(value=mpix, unit=UNIT, cores=cores, kind="port", sample=sample, ms_per_step=med * 1e3,
                 torch_threads=torch.get_num_threads(), steps=steps, warmup=warmup)
 

@@ -191,3 +191,35 @@ def test_real_trainer_train_epoch_stock_vs_port_at_the_patch_seam():
         for x, y in zip(a["protos"], b["protos"]):
             assert np.array_equal(x, y)
     assert stock["running_intra"] == port["running_intra"]
+
+
+def test_step_state_dict_is_a_snapshot_and_load_validates():
+    """``state_dict()`` must not hand out the live EMA tensors (later steps update them in place) and
+    ``load_state_dict`` must reject state that does not fit the step before raw pointers reach the kernels."""
+    step = clr.CLRStep(K=2)
+    assert step.state_dict()["stored_s"] is None and step.state_dict()["first_s"] is True
+    step.stored_s, step.stored_t = torch.ones(4, 7), torch.full((4, 7), 2.0)
+    step.first_s = step.first_t = False
+    sd = step.state_dict()
+    step.stored_s.add_(1.0)                                   # what a later step does, in place
+    assert float(sd["stored_s"][0, 0]) == 1.0                 # the snapshot did not move
+    other = clr.CLRStep(K=2)
+    other.load_state_dict(sd)
+    assert other.first_s is False and torch.equal(other.stored_s, sd["stored_s"]) and other.stored_s is not sd["stored_s"]
+    for bad in (dict(sd, stored_s=torch.ones(3, 7)),                      # wrong 2K
+                dict(sd, stored_t=torch.ones(4, 8)),                      # shapes disagree
+                dict(sd, stored_s=torch.ones(4, 7, dtype=torch.float64)),
+                dict(sd, stored_t=None)):
+        with pytest.raises(ValueError):
+            clr.CLRStep(K=2).load_state_dict(bad)
+
+
+def test_dist_local_context_restores_the_exchange_settings():
+    saved = dict(clr.dist._STATE)
+    try:
+        clr.dist._STATE.update(enabled=True, peer=True, grad_scale=4.0)
+        with clr.dist.local():
+            assert not clr.dist.enabled() and not clr.dist.peer_enabled() and clr.dist.world_size() == 1
+        assert clr.dist._STATE["enabled"] and clr.dist._STATE["peer"] and clr.dist._STATE["grad_scale"] == 4.0
+    finally:
+        clr.dist._STATE.update(saved)
