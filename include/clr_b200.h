@@ -323,7 +323,8 @@ typedef struct clr_step_args {
     float* P_s; float* P_t;               /* [2K][C] EMA'd prototypes */
     float* g_s; float* g_t;               /* [2K][C] dL/d(current prototypes) */
     float* losses;                        /* [8] */
-    float* std_map; float* pred_mean;     /* [B_t,K,Hi,Wi] (retrify) */
+    float* std_map; float* pred_mean;     /* [B_t,K,Hi,Wi] (retrify); pred_mean is scratch of the step: only the bilinear source
+                                           * rows the down-sample reads are written (power-of-two image sizes), the rest is untouched */
     float* wt_retrify; float* masks;      /* [B_t,2K,H,W], [B_t,K,H,W] (retrify) */
     float* disc_coef;                     /* [B_s,K,H,W] (disc) */
     float* disc_vec; float* disc_beta; float* xtab; /* [K][C], [K], [K][C] (disc) */

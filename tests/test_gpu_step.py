@@ -866,3 +866,29 @@ def test_schedule2_equals_schedule1_bit_for_bit(K, C, H, B):
     for other in res[1:]:
         for x, y in zip(res[0], other):
             assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize("B,H,up", [(2, 32, 4), (1, 16, 8), (2, 24, 4)])
+def test_mean_map_written_on_tap_rows_only_changes_nothing(B, H, up):
+    """The fused step's MC statistics write the full-resolution mean map only on the bilinear source rows that the
+    down-sample reads (power-of-two image sizes; "mc_all_rows" = 1 writes every row): identical step results."""
+    from uda_clr_b200 import _lib
+    lib = _lib.load()
+    K, C, T = 2, 24, 8
+    b = synth.make_batch(B=B, C=C, H=H, W=H, K=K, T=T, up=up, seed=5 + H)
+    t = {k: getattr(b, k).to(DEV) for k in ("xs", "ys", "xt", "oT_before", "preds", "oT", "oT_aug")}
+    res = []
+    for all_rows in (0, 1):
+        try:
+            _lib.check(lib.clr_set_tunable(b"mc_all_rows", all_rows), "mc_all_rows")
+            step = clr.CLRStep(K=K, retrify=True, use_disc=True, use_cons=True)
+            plan = step.plan(t["xs"], t["ys"], t["xt"], oT_before=t["oT_before"], preds=t["preds"], T=T, oT=t["oT"], oT_aug=t["oT_aug"])
+            plan.run(); plan.run()
+            torch.cuda.synchronize()
+            o = plan.outputs()
+            res.append([plan.losses.clone(), plan.gxs.clone(), plan.gxt.clone(), torch.cat(o.masks, 1).clone(), o.std_map.clone(),
+                        plan.holder["buf"].wt_retrify.clone()])
+        finally:
+            lib.clr_set_tunable(b"mc_all_rows", 0)
+    for x, y in zip(res[0], res[1]):
+        assert torch.equal(x, y)

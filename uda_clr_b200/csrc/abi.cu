@@ -54,6 +54,7 @@ int clr_set_tunable(const char* name, int value) {
     else if (!strcmp(name, "flag_dep_off")) t.flag_dep_off = value;
     else if (!strcmp(name, "mc_fuse")) t.mc_fuse = value;
     else if (!strcmp(name, "mc_generic")) t.mc_generic = value;
+    else if (!strcmp(name, "mc_all_rows")) t.mc_all_rows = value;
     else if (!strcmp(name, "bwd_merge_off")) t.bwd_merge_off = value;
     else if (!strcmp(name, "fin_early_off")) t.fin_early_off = value;
     else if (!strcmp(name, "mc_split")) t.mc_split = value;

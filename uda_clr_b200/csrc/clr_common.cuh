@@ -43,6 +43,7 @@ struct Tunables {
     int hfuse_off;     // 1 = finish bodies get launches of their own instead of riding with cons / the target-gradient write
     int fin_early_off; // 1 = the pooling finish releases the discriminative kernel only at its very end (after the last-CTA combine)
     int bwd_merge_off; // 1 = clr_step_run writes the two gradient maps with two launches ([finish | xt], then xs) instead of one
+    int mc_all_rows;   // 1 = the fused step's MC statistics write the full-resolution mean map on every row (A/B; default: bilinear source rows only)
     int mc_generic;    // 1 = clr_mc_stats does not use the T == 8 specialisation (A/B runs)
     int mc_fuse;       // 1 = the fused step uses the one-pass mc_retrify kernel instead of mc_stats + retrify_weights
     int mc_split;      // 1 = one-pass mc_retrify kernel splits image rows into column blocks (more, smaller CTAs)

@@ -61,7 +61,7 @@ int pool_bwd_gated(const clr_bwd_dom* first, const clr_bwd_dom* gated, int C, in
 
 // clr_mc_stats with the option to skip griddepcontrol.wait (fused step, schedule 2: see the kernel)
 int mc_stats_impl(const float* preds, int T, int B, int K, int Hi, int Wi, float* std_map, float* pred_mean, cudaStream_t st,
-                  bool nowait);
+                  bool nowait, int tap_H = 0);
 int retrify_weights_impl(const float* oT_before, const float* pred_mean, const float* std_map, const float* preds, int T,
                          int B, int K, int H, int W, int Hi, int Wi, float pseudo_thr, float std_thr,
                          float* weights, float* masks, float* pseudo_out, float* small_out, cudaStream_t stream, bool nowait);

@@ -16,10 +16,31 @@
 
 namespace clr {
 
+// The full-resolution mean map exists only to be down-sampled (utils/Utils.py:170): the fused step reads it at the two
+// bilinear source rows of every feature row and nowhere else.  With `rows.H` > 0 the kernel writes pred_mean only on those
+// rows (half of them at the reference's 512 -> 128): 8.4 MB less write traffic per step.  Same source-row formula as
+// bilinear_tap (ATen's); only for power-of-two image sizes and scale >= 1, otherwise every row is written.
+struct McTapRows { int H, Hi, wi_shift, hi_shift; float sh, inv_sh; };
+__device__ __forceinline__ bool is_tap_row(const McTapRows& g, size_t i) {
+    const int r = (int)((i >> g.wi_shift) & (size_t)(g.Hi - 1));
+    const int yc = (int)((float)r * g.inv_sh);
+    bool tap = false;
+#pragma unroll
+    for (int dy = -2; dy <= 2; ++dy) {       // r = i0(y) or i0(y) + 1  =>  y within [r/sh - 1, r/sh + 1]; +-1 for the fp32 quotient
+        const int y = yc + dy;
+        if (y >= 0 && y < g.H) {
+            const int i0 = (int)(g.sh * (float)y);
+            const int i1 = i0 + ((i0 < g.Hi - 1) ? 1 : 0);
+            tap = tap || r == i0 || r == i1;
+        }
+    }
+    return tap;
+}
+
 template <int VEC, int TT, bool PRECISE, bool EXACT = false>
 __global__ void __launch_bounds__(256) mc_stats_kernel(const float* __restrict__ preds, int T, size_t n,
                                                        float* __restrict__ std_map, float* __restrict__ pred_mean,
-                                                       const McAten aten, const int nowait) {
+                                                       const McAten aten, const int nowait, const McTapRows rows) {
     // nowait (fused step, schedule 2): the launch in front of this one is the source half of the pooling finish -- a few
     // CTAs whose results this kernel does not read, and which trigger their dependents only AFTER their own
     // griddepcontrol.wait (everything older in the stream has completed by then).  Skipping the wait lets the whole
@@ -34,20 +55,21 @@ __global__ void __launch_bounds__(256) mc_stats_kernel(const float* __restrict__
     Pack<VEC> s, m;
     mc_vec_stats<VEC, TT, PRECISE, EXACT>(preds, T, n, i, s, m, aten);
     st_keep<VEC>(std_map + i, s);
-    st_keep<VEC>(pred_mean + i, m);
+    if (rows.H == 0 || is_tap_row(rows, i)) st_keep<VEC>(pred_mean + i, m);
     trace_exit(TR_MC_STATS);
 }
 
 template <int VEC, bool PRECISE>
-static void launch_mc(const float* preds, int T, size_t n, float* std_map, float* pred_mean, cudaStream_t st, int nowait) {
+static void launch_mc(const float* preds, int T, size_t n, float* std_map, float* pred_mean, cudaStream_t st, int nowait,
+                      const McTapRows rows) {
     const size_t threads = (n + VEC - 1) / VEC;
     const unsigned blocks = (unsigned)((threads + 255) / 256);
     const McAten aten{mean_factor_aten(n, T)};
-    if (PRECISE) launch_k(mc_stats_kernel<VEC, 0, PRECISE>, blocks, 256, 0, st, preds, T, n, std_map, pred_mean, aten, nowait);
-    else if (T == 8 && !tunables().mc_generic) launch_k(mc_stats_kernel<VEC, 8, PRECISE, true>, blocks, 256, 0, st, preds, T, n, std_map, pred_mean, aten, nowait);
-    else if (T <= 8) launch_k(mc_stats_kernel<VEC, 8, PRECISE>, blocks, 256, 0, st, preds, T, n, std_map, pred_mean, aten, nowait);
-    else if (T <= 16) launch_k(mc_stats_kernel<VEC, 16, PRECISE>, blocks, 256, 0, st, preds, T, n, std_map, pred_mean, aten, nowait);
-    else launch_k(mc_stats_kernel<VEC, 0, PRECISE>, blocks, 256, 0, st, preds, T, n, std_map, pred_mean, aten, nowait);
+    if (PRECISE) launch_k(mc_stats_kernel<VEC, 0, PRECISE>, blocks, 256, 0, st, preds, T, n, std_map, pred_mean, aten, nowait, rows);
+    else if (T == 8 && !tunables().mc_generic) launch_k(mc_stats_kernel<VEC, 8, PRECISE, true>, blocks, 256, 0, st, preds, T, n, std_map, pred_mean, aten, nowait, rows);
+    else if (T <= 8) launch_k(mc_stats_kernel<VEC, 8, PRECISE>, blocks, 256, 0, st, preds, T, n, std_map, pred_mean, aten, nowait, rows);
+    else if (T <= 16) launch_k(mc_stats_kernel<VEC, 16, PRECISE>, blocks, 256, 0, st, preds, T, n, std_map, pred_mean, aten, nowait, rows);
+    else launch_k(mc_stats_kernel<VEC, 0, PRECISE>, blocks, 256, 0, st, preds, T, n, std_map, pred_mean, aten, nowait, rows);
 }
 
 // upsample_bilinear2d (align_corners=True) source coordinates, as ATen computes them in fp32
@@ -301,19 +323,34 @@ int mc_retrify_fused(const float* preds, const float* oT_before, int T, int B, i
     return launch_status();
 }
 
+static int log2_pow2(int x) {
+    if (x <= 0 || (x & (x - 1))) return -1;
+    int s = 0;
+    while ((1 << s) != x) ++s;
+    return s;
+}
+
+// tap_H > 0: the caller only ever reads pred_mean at the bilinear source rows of a tap_H-row feature map (fused step)
 int mc_stats_impl(const float* preds, int T, int B, int K, int Hi, int Wi, float* std_map, float* pred_mean, cudaStream_t st,
-                  bool nowait) {
+                  bool nowait, int tap_H) {
     if (!preds || !std_map || !pred_mean || T < 1 || B < 1 || K < 1 || Hi < 1 || Wi < 1) return CLR_ERR_BAD_ARG;
     const size_t n = (size_t)B * K * Hi * Wi;
     const bool vec4 = (n % 4 == 0) && aligned16(preds) && aligned16(std_map) && aligned16(pred_mean);
     const bool precise = tunables().mc_precise != 0;
     const int nw = nowait ? 1 : 0;
+    McTapRows rows{};
+    const int ws = log2_pow2(Wi), hs = log2_pow2(Hi);
+    if (tap_H > 1 && ws >= 2 && hs >= 0 && Hi >= tap_H && !tunables().mc_all_rows) {
+        const float sh = (float)(Hi - 1) / (float)(tap_H - 1);      // bilinear_tap's scale
+        if (sh >= 1.0f) rows = McTapRows{tap_H, Hi, ws, hs, sh, 1.0f / sh};
+    }
     if (vec4) {
-        if (precise) launch_mc<4, true>(preds, T, n, std_map, pred_mean, st, nw);
-        else launch_mc<4, false>(preds, T, n, std_map, pred_mean, st, nw);
+        if (precise) launch_mc<4, true>(preds, T, n, std_map, pred_mean, st, nw, rows);
+        else launch_mc<4, false>(preds, T, n, std_map, pred_mean, st, nw, rows);
     } else {
-        if (precise) launch_mc<1, true>(preds, T, n, std_map, pred_mean, st, nw);
-        else launch_mc<1, false>(preds, T, n, std_map, pred_mean, st, nw);
+        rows = McTapRows{};          // (a scalar thread's position is not row-aligned: write everything)
+        if (precise) launch_mc<1, true>(preds, T, n, std_map, pred_mean, st, nw, rows);
+        else launch_mc<1, false>(preds, T, n, std_map, pred_mean, st, nw, rows);
     }
     return launch_status();
 }
@@ -336,7 +373,7 @@ extern "C" {
 
 int clr_mc_stats(const float* preds, int T, int B, int K, int Hi, int Wi,
                  float* std_map, float* pred_mean, clr_stream_t stream) {
-    return clr::mc_stats_impl(preds, T, B, K, Hi, Wi, std_map, pred_mean, static_cast<cudaStream_t>(stream), false);
+    return clr::mc_stats_impl(preds, T, B, K, Hi, Wi, std_map, pred_mean, static_cast<cudaStream_t>(stream), false, 0);
 }
 
 int clr_retrify_weights(const float* oT_before, const float* pred_mean, const float* std_map,

@@ -269,7 +269,7 @@ static int step_fwd_v2(const clr_step_args* a, cudaStream_t st, DiscFinishParams
     rc = pool_finish_launch(ps, st);
     if (rc != CLR_OK) return rc;
     // 3. MC statistics (not waiting for 2) + retrify weights
-    rc = mc_stats_impl(a->preds, a->T, a->B_t, K, a->Hi, a->Wi, a->std_map, a->pred_mean, st, true);
+    rc = mc_stats_impl(a->preds, a->T, a->B_t, K, a->Hi, a->Wi, a->std_map, a->pred_mean, st, true, a->H);
     if (rc != CLR_OK) return rc;
     rc = clr_retrify_weights(a->oT_before, a->pred_mean, a->std_map, a->preds, a->T, a->B_t, K, a->H, a->W, a->Hi, a->Wi,
                              a->pseudo_thr, a->std_thr, a->wt_retrify, a->masks, nullptr, nullptr, stream);
@@ -348,7 +348,7 @@ static int step_fwd_core(const clr_step_args* a, cudaStream_t st, DiscFinishPara
                                    : mc_retrify_fused(a->preds, a->oT_before, a->T, a->B_t, K, a->H, a->W, a->Hi, a->Wi,
                                                       a->pseudo_thr, a->std_thr, a->std_map, nullptr, a->wt_retrify, a->masks, st);
         if (rc == CLR_ERR_UNSUPPORTED) {
-            rc = clr_mc_stats(a->preds, a->T, a->B_t, K, a->Hi, a->Wi, a->std_map, a->pred_mean, stream);
+            rc = mc_stats_impl(a->preds, a->T, a->B_t, K, a->Hi, a->Wi, a->std_map, a->pred_mean, st, false, a->H);
             if (rc != CLR_OK) return rc;
             rc = clr_retrify_weights(a->oT_before, a->pred_mean, a->std_map, a->preds, a->T, a->B_t, K, a->H, a->W, a->Hi, a->Wi,
                                      a->pseudo_thr, a->std_thr, a->wt_retrify, a->masks, nullptr, nullptr, stream);
