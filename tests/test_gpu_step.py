@@ -892,3 +892,36 @@ def test_mean_map_written_on_tap_rows_only_changes_nothing(B, H, up):
             lib.clr_set_tunable(b"mc_all_rows", 0)
     for x, y in zip(res[0], res[1]):
         assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize("C,H,B", [(256, 64, 2), (305, 32, 3), (64, 16, 1)])
+def test_disc_kernel_variants_are_bit_identical(C, H, B):
+    """Knobs of the one-read discriminative kernel that change its schedule, not its arithmetic: "disc_lag" = 1 (phase 2 lags one
+    tile: two barriers per tile), "disc_ctas" = 3 (three CTAs per SM on a 2-stage ring -- different CTA count, so only the per-pixel
+    outputs and the tolerance-level sums are compared), "disc_reverse" = 1 (tiles walked in descending order)."""
+    from uda_clr_b200 import _lib
+    lib = _lib.load()
+    K, T = 2, 8
+    b = synth.make_batch(B=B, C=C, H=H, W=H, K=K, T=T, up=4, seed=3 + C)
+    t = {k: getattr(b, k).to(DEV) for k in ("xs", "ys", "xt", "oT_before", "preds", "oT", "oT_aug")}
+
+    def run(knob, val):
+        try:
+            _lib.check(lib.clr_set_tunable(knob, val), knob.decode())
+            step = clr.CLRStep(K=K, retrify=True, use_disc=True, use_cons=True)
+            plan = step.plan(t["xs"], t["ys"], t["xt"], oT_before=t["oT_before"], preds=t["preds"], T=T, oT=t["oT"], oT_aug=t["oT_aug"])
+            plan.run(); plan.run()
+            torch.cuda.synchronize()
+            return [plan.losses.clone(), plan.gxs.clone(), plan.gxt.clone(), plan.holder["buf"].disc_coef.clone()]
+        finally:
+            lib.clr_set_tunable(knob, 0)
+
+    base = run(b"disc_lag", 0)
+    lag = run(b"disc_lag", 1)
+    for x, y in zip(base, lag):
+        assert torch.equal(x, y)
+    for knob in (b"disc_ctas", b"disc_reverse"):
+        other = run(knob, 3 if knob == b"disc_ctas" else 1)
+        assert torch.equal(base[3], other[3])                                   # coefficient planes: per pixel, exact
+        assert relerr(other[0][:5].cpu().numpy(), base[0][:5].cpu().numpy()) < 1e-5
+        assert relerr(other[1].cpu().numpy(), base[1].cpu().numpy()) < 1e-5
