@@ -896,9 +896,9 @@ def test_mean_map_written_on_tap_rows_only_changes_nothing(B, H, up):
 
 @pytest.mark.parametrize("C,H,B", [(256, 64, 2), (305, 32, 3), (64, 16, 1)])
 def test_disc_kernel_variants_are_bit_identical(C, H, B):
-    """Knobs of the one-read discriminative kernel that change its schedule, not its arithmetic: "disc_lag" = 1 (phase 2 lags one
-    tile: two barriers per tile), "disc_ctas" = 3 (three CTAs per SM on a 2-stage ring -- different CTA count, so only the per-pixel
-    outputs and the tolerance-level sums are compared), "disc_reverse" = 1 (tiles walked in descending order)."""
+    """Knobs of the one-read discriminative kernel that change its schedule, not its arithmetic: "disc_ctas" = 3 (three CTAs per
+    SM on a 2-stage ring) and "disc_reverse" = 1 (tiles walked in descending order).  The CTA count / tile order differ, so the
+    per-pixel outputs are compared exactly and the sums at tolerance level."""
     from uda_clr_b200 import _lib
     lib = _lib.load()
     K, T = 2, 8
@@ -916,10 +916,7 @@ def test_disc_kernel_variants_are_bit_identical(C, H, B):
         finally:
             lib.clr_set_tunable(knob, 0)
 
-    base = run(b"disc_lag", 0)
-    lag = run(b"disc_lag", 1)
-    for x, y in zip(base, lag):
-        assert torch.equal(x, y)
+    base = run(b"disc_reverse", 0)
     for knob in (b"disc_ctas", b"disc_reverse"):
         other = run(knob, 3 if knob == b"disc_ctas" else 1)
         assert torch.equal(base[3], other[3])                                   # coefficient planes: per pixel, exact

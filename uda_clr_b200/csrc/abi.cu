@@ -46,7 +46,6 @@ int clr_set_tunable(const char* name, int value) {
     else if (!strcmp(name, "disc_impl")) t.disc_impl = value;
     else if (!strcmp(name, "disc_tile")) t.disc_tile = value;
     else if (!strcmp(name, "disc_ctas")) t.disc_ctas = value;
-    else if (!strcmp(name, "disc_lag")) t.disc_lag = value;
     else if (!strcmp(name, "disc_threads")) t.disc_threads = value;
     else if (!strcmp(name, "pdl_off")) t.pdl_off = value;
     else if (!strcmp(name, "finish_off")) t.finish_off = value;

@@ -36,7 +36,6 @@ struct Tunables {
     int disc_impl;     // 0 = auto (one-read fused kernel, tensor-map TMA tiles), 1 = two-pass form, 2 = one-read kernel with cp.async tiles
     int disc_threads;  // 0 = auto (256-thread CTAs: fastest in the live step), 512 = 512-thread CTAs when K <= 2
     int disc_ctas;     // 3 = fused discriminative kernel with three CTAs per SM on a 2-stage ring (K <= 2, C <= 320)
-    int disc_lag;      // 1 = fused discriminative kernel with phase 2 lagging one tile (two barriers per tile; K <= 2, C <= 320)
     int disc_tile;     // 0 = auto, 64 = force 64-pixel tiles in the fused discriminative kernel
     int pdl_off;       // 1 = do not use programmatic dependent launch
     int mc_precise;    // 1 = clr_mc_stats / clr_mc_retrify evaluate std / mean exactly like ATen's CUDA reductions (slow; tests), 0 = streaming

@@ -87,10 +87,7 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tmap, 
 //              thread; completion through an mbarrier per stage.  The LDGSTS form is bound by the SM's load/store
 //              pipe (measured: ~2300 cycles per tile spent behind the next tile's 2048 LDGSTS, none waiting for
 //              data), the tensor form leaves that pipe to the two compute phases.
-// LAG (tensor-map path, 3 stages; "disc_lag" = 1): phase 2 of tile i runs in the loop iteration of tile i+1, between that
-// tile's phase 1 and its barrier -- two CTA-wide barriers per tile instead of three, and the two phases of different tiles
-// share one barrier interval.  The ring then holds tiles i-1 (phase 2 pending), i and the prefetch of i+1.
-template <int K, int TP, int STAGES, int NT, bool TMA, int CPT, int MB = ((TP == 32 && STAGES <= 4) ? 2 : 1), bool LAG = false>
+template <int K, int TP, int STAGES, int NT, bool TMA, int CPT, int MB = ((TP == 32 && STAGES <= 4) ? 2 : 1)>
 __global__ void __launch_bounds__(NT, MB) disc_fused_kernel(const DiscParams p, const __grid_constant__ CUtensorMap tmap) {
     trace_enter(TR_DISC);
     pdl_trigger();
@@ -108,8 +105,8 @@ __global__ void __launch_bounds__(NT, MB) disc_fused_kernel(const DiscParams p, 
     const size_t stage_floats = (size_t)rows_total * RS;
     float* tiles = reinterpret_cast<float*>(smem_raw);                       // [STAGES][rows][RS]
     float* red = tiles + (size_t)STAGES * stage_floats;                      // [NW][K][TP]
-    float* cfs = red + (size_t)NW * K * TP;                              // [2][K][TP] (second copy: LAG only)
-    float* wred = cfs + (size_t)2 * K * TP;                                  // [1 + NE][NW]
+    float* cfs = red + (size_t)NW * K * TP;                              // [K][TP]
+    float* wred = cfs + (size_t)K * TP;                                      // [1 + NE][NW]
     uint64_t* full = reinterpret_cast<uint64_t*>(wred + (1 + NE) * NW + ((1 + NE) * NW & 1));   // [STAGES] (TMA), 8-byte aligned
     float* Vs = reinterpret_cast<float*>(full + STAGES);                     // [K][C] contraction vectors + [K] offsets
     float* betas = Vs + (size_t)K * p.C;
@@ -186,10 +183,8 @@ __global__ void __launch_bounds__(NT, MB) disc_fused_kernel(const DiscParams p, 
     int b = first >= 0 ? first / p.tilesPerSample : 0, tile = first >= 0 ? first - b * p.tilesPerSample : 0;   // current item
     int fb = b, ftile = tile;                                               // next item to fetch
     int fetched = begin;
-    constexpr int PRE = LAG ? STAGES - 2 : STAGES - 1;      // tiles in flight ahead of the one being consumed
-    static_assert(!LAG || (TMA && STAGES == 3), "the lagged schedule is written for the 3-stage tensor-map ring");
 #pragma unroll
-    for (int j = 0; j < PRE; ++j) {
+    for (int j = 0; j < STAGES - 1; ++j) {
         issue(fetched < end ? fb : p.B, ftile, j);
         advance(fb, ftile); fetched += step;
     }
@@ -222,7 +217,6 @@ __global__ void __launch_bounds__(NT, MB) disc_fused_kernel(const DiscParams p, 
     __syncthreads();
     int stage = 0;
     uint32_t phase = 0;
-    int lag_it = 0;                      // LAG: tiles whose phase 1 + epilogue are done (the last one still owes its phase 2)
     PH_DECL
     for (int it = begin; it < end; it += step, advance(b, tile)) {
         const int px0 = tile * TP;
@@ -241,13 +235,12 @@ __global__ void __launch_bounds__(NT, MB) disc_fused_kernel(const DiscParams p, 
         __syncthreads();                 // ... everyone's have, and everyone is done with the previous tile
         PH_MARK(0)
         {
-            int nst = stage + PRE;                        // the stage the previous tile occupied (LAG: the one before that --
-            if (nst >= STAGES) nst -= STAGES;             // its phase 2 finished before the barrier above)
-            issue(fetched < end ? fb : p.B, ftile, nst);
+            int nst = stage + STAGES - 1;
+            if (nst >= STAGES) nst -= STAGES;
+            issue(fetched < end ? fb : p.B, ftile, nst);  // refill the stage the previous tile occupied
             advance(fb, ftile); fetched += step;
         }
         const float* xt = tiles + (size_t)stage * stage_floats;
-        float* cfs_cur = LAG ? cfs + (size_t)(lag_it & 1) * K * TP : cfs;
         // ---- phase 1: K dot products over the channel axis ----------------------------------------
         float acc[K][4];
 #pragma unroll
@@ -283,40 +276,6 @@ __global__ void __launch_bounds__(NT, MB) disc_fused_kernel(const DiscParams p, 
                 *reinterpret_cast<float4*>(red + ((size_t)warp * K + k) * TP + 4 * g) =
                     make_float4(acc[k][0], acc[k][1], acc[k][2], acc[k][3]);
         }
-        if constexpr (LAG) {
-            // ---- phase 2 of the PREVIOUS tile (its coefficients were published before this iteration's first barrier)
-            if (lag_it > 0) {
-                int pst = stage - 1;
-                if (pst < 0) pst += STAGES;
-                const float* xp = tiles + (size_t)pst * stage_floats;
-                const float* cfp = cfs + (size_t)((lag_it - 1) & 1) * K * TP;
-                const int cp = tid % kDiscCols, h = tid / kDiscCols;
-                constexpr int JQ = NG / PS;
-                float4 cf[JQ][K];
-#pragma unroll
-                for (int jq = 0; jq < JQ; ++jq)
-#pragma unroll
-                    for (int k = 0; k < K; ++k) cf[jq][k] = *reinterpret_cast<const float4*>(cfp + k * TP + 4 * (h * JQ + jq));
-#pragma unroll
-                for (int i = 0; i < CPT; ++i) {
-                    const int c = cp + i * kDiscCols;
-                    if (c < p.C) {
-                        const float* row = xp + (size_t)c * RS;
-#pragma unroll
-                        for (int jq = 0; jq < JQ; ++jq) {
-                            const float4 x = *reinterpret_cast<const float4*>(row + chunk_off(c, h * JQ + jq));
-#pragma unroll
-                            for (int k = 0; k < K; ++k) {
-                                A[i][k] = fmaf(x.x, cf[jq][k].x, A[i][k]);
-                                A[i][k] = fmaf(x.y, cf[jq][k].y, A[i][k]);
-                                A[i][k] = fmaf(x.z, cf[jq][k].z, A[i][k]);
-                                A[i][k] = fmaf(x.w, cf[jq][k].w, A[i][k]);
-                            }
-                        }
-                    }
-                }
-            }
-        }
         __syncthreads();
         PH_MARK(1)
         // ---- epilogue: thread e -> (k, pixel j) ------------------------------------------------------
@@ -338,12 +297,9 @@ __global__ void __launch_bounds__(NT, MB) disc_fused_kernel(const DiscParams p, 
                 p.coef[o] = cf;
                 if (p.delta) p.delta[o] = delta;
             }
-            cfs_cur[e] = cf;
+            cfs[e] = cf;
             ncf[ei] += cf;
         }
-        if constexpr (LAG) {
-            ++lag_it;                    // (this tile's phase 2 runs in the next iteration, after that iteration's first barrier)
-        } else {
         __syncthreads();
         PH_MARK(2)
         // ---- phase 2: coefficient-weighted sums over the pixel axis.  Thread = (channel column cp, pixel quarter h):
@@ -377,41 +333,10 @@ __global__ void __launch_bounds__(NT, MB) disc_fused_kernel(const DiscParams p, 
                 }
             }
         }
-        }
         PH_MARK(3)
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         // `red` is next written after the next tile's first barrier, `cfs` after its second: both after every
         // thread finished this tile's phase 2, so no trailing barrier is needed
-    }
-    if constexpr (LAG) {
-        if (lag_it > 0) {                // the last tile's phase 2
-            __syncthreads();
-            int pst = stage - 1;
-            if (pst < 0) pst += STAGES;
-            const float* xp = tiles + (size_t)pst * stage_floats;
-            const float* cfp = cfs + (size_t)((lag_it - 1) & 1) * K * TP;
-            const int cp = tid % kDiscCols, h = tid / kDiscCols;
-            constexpr int JQ = NG / PS;
-#pragma unroll
-            for (int i = 0; i < CPT; ++i) {
-                const int c = cp + i * kDiscCols;
-                if (c < p.C) {
-                    const float* row = xp + (size_t)c * RS;
-#pragma unroll
-                    for (int jq = 0; jq < JQ; ++jq) {
-                        const float4 x = *reinterpret_cast<const float4*>(row + chunk_off(c, h * JQ + jq));
-#pragma unroll
-                        for (int k = 0; k < K; ++k) {
-                            const float4 cfv = *reinterpret_cast<const float4*>(cfp + k * TP + 4 * (h * JQ + jq));
-                            A[i][k] = fmaf(x.x, cfv.x, A[i][k]);
-                            A[i][k] = fmaf(x.y, cfv.y, A[i][k]);
-                            A[i][k] = fmaf(x.z, cfv.z, A[i][k]);
-                            A[i][k] = fmaf(x.w, cfv.w, A[i][k]);
-                        }
-                    }
-                }
-            }
-        }
     }
     PH_FLUSH
     if (!TMA) cp_async_wait<0>();
@@ -469,7 +394,7 @@ __global__ void __launch_bounds__(NT, MB) disc_fused_kernel(const DiscParams p, 
 template <int K, int TP, int NT>
 static size_t disc_smem(int C, int stages) {
     constexpr int RS = TP + kDiscPad, NW = NT / 32, NE = (K * TP + NT - 1) / NT;
-    size_t fl = (size_t)stages * C * RS + (size_t)NW * K * TP + (size_t)2 * K * TP + (1 + NE) * NW;
+    size_t fl = (size_t)stages * C * RS + (size_t)NW * K * TP + (size_t)K * TP + (1 + NE) * NW;
     const size_t comb = (size_t)(NT / kDiscCols) * K * C;     // end-of-kernel combine buffer aliases the tile ring
     if (comb > (size_t)stages * C * RS) fl += comb - (size_t)stages * C * RS;
     return (fl + (size_t)K * C + K + 2) * sizeof(float) + 16 + sizeof(uint64_t) * 8;
@@ -479,7 +404,7 @@ static size_t disc_smem(int C, int stages) {
 template <int K, int NT>
 static size_t disc_smem_tma(int C, int rows_total, int stages) {
     constexpr int TP = 32, NW = NT / 32, NE = (K * TP + NT - 1) / NT;
-    size_t fl = (size_t)stages * rows_total * TP + (size_t)NW * K * TP + (size_t)2 * K * TP + (1 + NE) * NW + 2;
+    size_t fl = (size_t)stages * rows_total * TP + (size_t)NW * K * TP + (size_t)K * TP + (1 + NE) * NW + 2;
     const size_t comb = (size_t)(NT / kDiscCols) * K * C;
     if (comb > (size_t)stages * rows_total * TP) fl += comb - (size_t)stages * rows_total * TP;
     return (fl + (size_t)K * C + K + 2) * sizeof(float) + sizeof(uint64_t) * stages;
@@ -547,10 +472,10 @@ static bool make_feature_tmap(const float* xs, int B, int C, int HW, int rows_bo
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int K, int STAGES, int NT, int CPT, int MB = 2, bool LAG = false>
+template <int K, int STAGES, int NT, int CPT, int MB = 2>
 static int launch_disc_tma_c(DiscParams& p, const CUtensorMap& tmap, int* nparts, cudaStream_t st) {
     const size_t smem = disc_smem_tma<K, NT>(p.C, p.rows_box * p.nbox, STAGES);
-    auto kern = disc_fused_kernel<K, 32, STAGES, NT, true, CPT, MB, LAG>;
+    auto kern = disc_fused_kernel<K, 32, STAGES, NT, true, CPT, MB>;
     int occ = 0;
     { const int rc = kernel_occupancy(reinterpret_cast<const void*>(kern), NT, smem, &occ); if (rc != CLR_OK) return rc; }
     if (occ < 1) return CLR_ERR_UNSUPPORTED;
@@ -586,8 +511,6 @@ static int launch_disc_tma(DiscParams& p, int* nparts, cudaStream_t st) {
         // its per-tile latency chain, not by DRAM (profiles/r02_l2_harvest.md) -- a third CTA to interleave
         if (tunables().disc_ctas == 3 && p.C <= kDiscSmallCPT * kDiscCols && disc_smem_tma<K, 256>(p.C, rt, 2) <= (budget - 3072) / 3)
             return launch_disc_tma_c<K, 2, 256, kDiscSmallCPT, 3>(p, tmap, nparts, st);
-        if (tunables().disc_lag == 1 && p.C <= kDiscSmallCPT * kDiscCols && disc_smem_tma<K, 256>(p.C, rt, 3) <= per_cta)
-            return launch_disc_tma_c<K, 3, 256, kDiscSmallCPT, 2, true>(p, tmap, nparts, st);
     }
     if (disc_smem_tma<K, 256>(p.C, rt, 3) <= per_cta) return launch_disc_tma_s<K, 3, 256>(p, tmap, nparts, st);
     if (disc_smem_tma<K, 256>(p.C, rt, 2) <= per_cta) return launch_disc_tma_s<K, 2, 256>(p, tmap, nparts, st);
