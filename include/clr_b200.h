@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define CLR_B200_VERSION 100 /* major*100 + minor */
+#define CLR_B200_VERSION 200 /* major*100 + minor; 2.0: clr_retrify_weights takes the MC logits (exact masks), new entry points */
 #define CLR_MAX_K 8          /* classes per call */
 #define CLR_MAX_WORLD 8      /* ranks of one NVLink domain that can share the fused step's in-kernel exchange */
 

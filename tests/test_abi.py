@@ -36,7 +36,7 @@ def test_binding_table_matches_header():
 
 
 def test_version_and_status_strings(lib):
-    assert lib.clr_version() == 100
+    assert lib.clr_version() == 200
     assert lib.clr_status_string(0) == b"ok"
     assert b"workspace" in lib.clr_status_string(-3)
     assert lib.clr_status_string(-1000 - 700)  # CUDA error range resolves to a string
