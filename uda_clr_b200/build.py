@@ -72,9 +72,23 @@ def _compile(nvcc, src, verbose):
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and is_fresh():
         return LIB
-    nvcc = nvcc_path()
     os.makedirs(LIBDIR, exist_ok=True)
     os.makedirs(OBJDIR, exist_ok=True)
+    # one builder at a time (torchrun starts N ranks that may all find a stale library): the others wait on the lock and
+    # then find the library fresh
+    import fcntl
+    with open(os.path.join(LIBDIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and is_fresh():
+                return LIB
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose: bool) -> str:
+    nvcc = nvcc_path()
     with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 2)) as ex:
         objs = list(ex.map(lambda s: _compile(nvcc, s, verbose), sources()))
     # link into a temporary name and rename: a reader (ctypes.CDLL, a snapshot of the tree) never sees a half-written file
