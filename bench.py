@@ -170,16 +170,23 @@ def run_reference_cpu(a, steps: int, warmup: int, budget_s: float):
         feats = torch.zeros(a.T * Bs, a.C, a.H, a.H) if use3 else None   # the reference's dead staging buffer
         return b, feats
 
-    def one(port, b, feats):
+    first = {}      # results of the FIRST step of a fresh state on the full-size batch (seed 1234 = rank 0's first input set)
+
+    def one(port, b, feats, keep=False):
         xs = b.xs.clone().requires_grad_(True)
         xt = b.xt.clone().requires_grad_(True)
         t0 = time.perf_counter()
         if use3:
             oTa = b.oT_aug.clone().requires_grad_(True)
-            port.step(xs, b.ys, xt, b.oT_before, preds=b.preds, features=feats, T=a.T, oT=b.oT, oT_aug=oTa, epoch=0.0)
+            res = port.step(xs, b.ys, xt, b.oT_before, preds=b.preds, features=feats, T=a.T, oT=b.oT, oT_aug=oTa, epoch=0.0)
         else:
-            port.step(xs, b.ys, xt, b.oT_before)
-        return time.perf_counter() - t0
+            res = port.step(xs, b.ys, xt, b.oT_before)
+        dt = time.perf_counter() - t0
+        if keep and not first:
+            first.update({k: float(res[k]) for k in ("intra", "inter", "disc", "aug", "total") if k in res})
+            first["Ps"] = torch.cat([p.reshape(1, -1) for p in res["Ps"]])
+            first["Pt"] = torch.cat([p.reshape(1, -1) for p in res["Pt"]])
+        return dt
 
     def new_port():
         return TP.ClrStepPort(retrify=use3, use_disc=use3, use_cons=use3, backprop_aug=False)
@@ -197,9 +204,8 @@ def run_reference_cpu(a, steps: int, warmup: int, budget_s: float):
         steps = n_total - warmup
     b, feats = (b1, f1) if Bs == 1 else make(Bs)
     port = new_port()
-    for _ in range(warmup):
-        one(port, b, feats)
-    ts = [one(port, b, feats) for _ in range(steps)]
+    seq = [one(port, b, feats, keep=(i == 0 and Bs == a.B)) for i in range(warmup + steps)]
+    ts = seq[warmup:]
     med = statistics.median(ts)
     mpix = 2 * Bs * a.H * a.H / med / 1e6
     sample = "%d steps x (B=%d of %d per domain, C=%d, %dx%d, K=%d%s), median of per-step wall times" % (
@@ -208,7 +214,7 @@ def run_reference_cpu(a, steps: int, warmup: int, budget_s: float):
         sample += "; ONE CPU job on this host timing a %d-sample shard of the %d-sample global batch (throughput in pixels/s does not " \
                   "depend on which shard): compare with the 1-GPU line, not with the %d-GPU aggregate" % (Bs, a.B * a.gpus, a.gpus)
     return dict(value=mpix, unit=UNIT, cores=cores, kind="port", sample=sample, ms_per_step=med * 1e3,
-                torch_threads=torch.get_num_threads(), steps=steps, warmup=warmup)
+                torch_threads=torch.get_num_threads(), steps=steps, warmup=warmup, first_step=first or None)
 
 
 # ------------------------------------------------------------------------------------------------- parity / second baseline
@@ -294,7 +300,11 @@ def run_parity(a, clr, synth, make_plans, host_batch, dev, rank, world, dist_on,
             and row.get("mask_mismatch_px", 0) == 0
         del xs, xt, g, res
     torch.cuda.empty_cache()
-    return {"ok": bool(ok), "reference": "oracle/clr_torch_port.ClrStepPort (op-for-op eager restatement of the reference) on the same GPU, "
+    g0 = snaps[0]
+    gpu_first = {"intra": float(g0["losses"][0]), "inter": float(g0["losses"][1]), "disc": float(g0["losses"][2]),
+                 "aug": float(g0["losses"][3]), "total": float(g0["losses"][4]), "Ps": g0["Ps"].cpu(), "Pt": g0["Pt"].cpu()}
+    return {"ok": bool(ok), "_gpu_first": gpu_first,
+            "reference": "oracle/clr_torch_port.ClrStepPort (op-for-op eager restatement of the reference) on the same GPU, "
                                          "global batch %d per domain; this rank's shard of masks / gradients" % (B * world),
             "tolerances": dict(TOL, masks="bit-exact"), "steps": steps, "cross_rank": cross}
 
@@ -735,10 +745,21 @@ def main():
                          "implementation_bytes": ib["total"], "implementation_bytes_by_stage": ib}}
 
     cpu_baseline = None
+    gpu_first = parity.pop("_gpu_first", None) if parity else None
     if not a.no_cpu_baseline and world == 1:
         r = run_reference_cpu(a, steps=3, warmup=1, budget_s=a.cpu_budget_s)
         cpu_baseline = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
                         "ms_per_step": r["ms_per_step"]}
+        # the same first step of a fresh state on the CPU (the reference's own device): cross-device, so the uncertainty masks may
+        # differ at knife-edge pixels (the reference's mask depends on the device it runs on) -- losses / prototypes at tolerance
+        cf = r.get("first_step")
+        if cf and gpu_first and parity is not None:
+            keys = [k for k in ("intra", "inter", "disc", "aug", "total") if k in cf]
+            rel = {k: abs(gpu_first[k] - cf[k]) / max(abs(cf[k]), 1e-30) for k in keys}
+            prot = {k: _rel(gpu_first[k], cf[k]) for k in ("Ps", "Pt")}
+            parity["vs_cpu_port_step1"] = {"loss_rel": rel, "proto_rel": prot,
+                                           "ok": bool(all(v < TOL["loss"] for v in rel.values()) and all(v < TOL["proto"] for v in prot.values()))}
+            parity["ok"] = bool(parity["ok"] and parity["vs_cpu_port_step1"]["ok"])
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W_,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
