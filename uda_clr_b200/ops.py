@@ -19,7 +19,15 @@ from . import dist as _dist
 
 
 # ----------------------------------------------------------------------------------------------- helpers
+_RAW_STREAM = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream() -> int:
+    """``cudaStream_t`` of the current stream of the current device, as an integer.  ``torch.cuda.current_stream()`` builds a
+    Python ``Stream`` object per call (17 us, seven calls per training step of the drop-in ops -- measured with
+    tools/dropin_profile.py); the raw getter behind it costs ~1 us."""
+    if _RAW_STREAM is not None:
+        return _RAW_STREAM(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -66,7 +74,8 @@ _WS_CACHE = {}
 
 
 def _workspace(nbytes: int, device, tag: str) -> torch.Tensor:
-    key = (device.index, torch.cuda.current_stream(device).cuda_stream, tag)
+    key = (device.index, _RAW_STREAM(device.index) if (_RAW_STREAM is not None and device.index is not None)
+           else torch.cuda.current_stream(device).cuda_stream, tag)
     ws = _WS_CACHE.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
